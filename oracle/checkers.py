@@ -1,0 +1,285 @@
+"""oracle/checkers.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front ends for the two checkers:
+  * ``Oracle``     oracle/_build/liboracle.so  (oracle/rlpt_oracle.cpp, the CPU restatement)
+  * ``Reference``  oracle/_ref/libref_host.so or libref_cuda.so (the unmodified reference engine behind
+                   oracle/ref_harness.cu)
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+A = 144
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", HERE], env={**os.environ, "CXX": "g++"})
+    return os.path.join(HERE, "_build", "liboracle.so")
+
+
+class Oracle:
+    def __init__(self, path=None):
+        path = path or os.path.join(HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.L = ctypes.CDLL(path)
+        self.L.orc_tri_area.restype = ctypes.c_float
+        self.ns = self.nl = 0
+
+    def threads(self):
+        return self.L.orc_threads()
+
+    def philox(self, seed, pixel, sample, bounce, purpose):
+        u = np.zeros(4, np.float32)
+        self.L.orc_philox(ctypes.c_uint32(seed), ctypes.c_uint32(pixel), ctypes.c_uint32(sample), ctypes.c_uint32(bounce), ctypes.c_uint32(purpose), _p(u))
+        return u
+
+    def scene_set(self, sv, srgb, lv, lrgb):
+        sv, srgb, lv, lrgb = _f32(sv).reshape(-1, 9), _f32(srgb).reshape(-1, 3), _f32(lv).reshape(-1, 9), _f32(lrgb).reshape(-1, 3)
+        self.ns, self.nl = len(sv), len(lv)
+        assert self.L.orc_scene_set(_p(sv), _p(srgb), self.ns, _p(lv), _p(lrgb), self.nl) == 0
+
+    def scene_normals(self):
+        sn, sl = np.zeros((self.ns, 3), np.float32), np.zeros(self.ns, np.float32)
+        ln, ll = np.zeros((self.nl, 3), np.float32), np.zeros(self.nl, np.float32)
+        self.L.orc_scene_normals(_p(sn), _p(sl), _p(ln), _p(ll))
+        return sn, sl, ln, ll
+
+    def closest_hit(self, org, dir, screen_height, fma_mode):
+        org, dir = _f32(org).reshape(-1, 3), _f32(dir).reshape(-1, 3)
+        n = len(org)
+        ty, ix = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        t, pos = np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        self.L.orc_closest_hit(_p(org), _p(dir), n, int(screen_height), int(fma_mode), _p(ty), _p(ix), _p(t), _p(pos))
+        return ty, ix, t, pos
+
+    def map(self, x, y):
+        out = np.zeros(3, np.float32)
+        self.L.orc_map(ctypes.c_float(x), ctypes.c_float(y), _p(out))
+        return out
+
+    def grid_dir(self, gx, gy, pos, nrm):
+        gx, gy, pos, nrm = _f32(gx), _f32(gy), _f32(pos), _f32(nrm)
+        out = np.zeros((len(gx), 3), np.float32)
+        self.L.orc_grid_dir(_p(gx), _p(gy), len(gx), _p(pos), _p(nrm), _p(out))
+        return out
+
+    def uniform_hemisphere(self, nrm, r1, r2):
+        out = np.zeros(3, np.float32)
+        self.L.orc_uniform_hemisphere(_p(_f32(nrm)), ctypes.c_float(r1), ctypes.c_float(r2), _p(out))
+        return out
+
+    def tri_area(self, i):
+        return self.L.orc_tri_area(int(i))
+
+    def rmap_build(self, area_per_sample=0.001):
+        self.nv = self.L.orc_rmap_build(ctypes.c_float(area_per_sample))
+        return self.nv
+
+    def rmap_counts(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self.L.orc_rmap_counts(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def rmap_volumes(self):
+        nv, _ = self.rmap_counts()
+        pos, nrm, surf = np.zeros((nv, 3), np.float32), np.zeros((nv, 3), np.float32), np.zeros(nv, np.int32)
+        self.L.orc_rmap_get_volumes(_p(pos), _p(nrm), _p(surf))
+        return pos, nrm, surf
+
+    def rmap_tree(self):
+        _, nt = self.rmap_counts()
+        dim, leaf = np.zeros(nt, np.int32), np.zeros(nt, np.int32)
+        left, right = np.zeros(nt, np.uint32), np.zeros(nt, np.uint32)
+        data, pos, nrm = np.zeros(nt, np.float32), np.zeros((nt, 3), np.float32), np.zeros((nt, 3), np.float32)
+        self.L.orc_rmap_get_tree(_p(dim), _p(leaf), _p(left), _p(right), _p(data), _p(pos), _p(nrm))
+        return dict(dim=dim, leaf=leaf, left=left, right=right, data=data, pos=pos, nrm=nrm)
+
+    def rmap_state(self):
+        nv, _ = self.rmap_counts()
+        q, cdf = np.zeros((nv, A), np.float32), np.zeros((nv, A), np.float32)
+        vis, irr = np.zeros((nv, A), np.uint32), np.zeros(nv, np.float32)
+        self.L.orc_rmap_get_state(_p(q), _p(cdf), _p(vis), _p(irr))
+        return q, cdf, vis, irr
+
+    def rmap_acc(self):
+        nv, _ = self.rmap_counts()
+        s, c = np.zeros((nv, A), np.float64), np.zeros((nv, A), np.uint32)
+        self.L.orc_rmap_get_acc(_p(s), _p(c))
+        return s, c
+
+    def rmap_set_q(self, q):
+        q = _f32(q)
+        self.L.orc_rmap_set_q(_p(q))
+
+    def rmap_update_distributions(self):
+        self.L.orc_rmap_update_distributions()
+
+    def rmap_merge_frame(self):
+        self.L.orc_rmap_merge_frame()
+
+    def find_closest(self, pos, nrm, fma_mode, max_dist=0.003):
+        pos, nrm = _f32(pos).reshape(-1, 3), _f32(nrm).reshape(-1, 3)
+        out = np.zeros(len(pos), np.int32)
+        self.L.orc_find_closest(_p(pos), _p(nrm), len(pos), ctypes.c_float(max_dist), int(fma_mode), _p(out))
+        return out
+
+    def sample_sector(self, cdf_row, r):
+        pdf = ctypes.c_float()
+        s = self.L.orc_sample_sector(_p(_f32(cdf_row)), ctypes.c_float(r), ctypes.byref(pdf))
+        return s, pdf.value
+
+    def cell_cos(self, vol):
+        out = np.zeros(A, np.float32)
+        self.L.orc_cell_cos(int(vol), _p(out))
+        return out
+
+    def render_frame(self, method, width, height, spp, sample0=0, max_bounces=80, env=0.0, seed=1984, cam=(0, 0, -3),
+                     yaw_y=0.0, yaw_x=0.0, fma_mode=1, td_mode=1, clamp_last_bin=1, max_dist=0.003):
+        out = np.zeros((width * height, 3), np.float32)
+        stats = np.zeros(4, np.float64)
+        cam = _f32(cam)
+        self.L.orc_render_frame(int(method), int(width), int(height), int(spp), int(sample0), int(max_bounces), ctypes.c_float(env),
+                                ctypes.c_uint(seed), _p(cam), ctypes.c_float(yaw_y), ctypes.c_float(yaw_x), int(fma_mode), int(td_mode),
+                                int(clamp_last_bin), ctypes.c_float(max_dist), _p(out), _p(stats))
+        return out, dict(total_path_length=stats[0], zero_contribution=stats[1], failed=stats[2], paths=stats[3])
+
+
+class Reference:
+    """The unmodified reference engine. kind: 'host' (g++ shim build) or 'cuda' (its own kernels, GPU box only)."""
+
+    def __init__(self, kind="host"):
+        path = os.path.join(HERE, "_ref", "libref_%s.so" % kind)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run oracle/build_ref.sh where /root/reference exists)")
+        self.kind = kind
+        self.L = ctypes.CDLL(path)
+        w, h, s, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.L.ref_dims(ctypes.byref(w), ctypes.byref(h), ctypes.byref(s), ctypes.byref(b))
+        self.width, self.height, self.spp, self.max_bounces = w.value, h.value, s.value, b.value
+
+    @staticmethod
+    def available(kind="host"):
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_%s.so" % kind))
+
+    def threads(self):
+        return self.L.ref_threads()
+
+    def scene_cornell(self):
+        assert self.L.ref_scene_cornell() == 0
+
+    def scene_obj(self, path, lights_in_obj):
+        rc = self.L.ref_scene_obj(path.encode(), int(bool(lights_in_obj)))
+        assert rc == 0, rc
+
+    def scene_arrays(self, sv, srgb, lv, lrgb):
+        sv, srgb, lv, lrgb = _f32(sv).reshape(-1, 9), _f32(srgb).reshape(-1, 3), _f32(lv).reshape(-1, 9), _f32(lrgb).reshape(-1, 3)
+        assert self.L.ref_scene_arrays(_p(sv), _p(srgb), len(sv), _p(lv), _p(lrgb), len(lv)) == 0
+
+    def scene_get(self):
+        ns, nl = ctypes.c_int(), ctypes.c_int()
+        assert self.L.ref_scene_counts(ctypes.byref(ns), ctypes.byref(nl)) == 0
+        ns, nl = ns.value, nl.value
+        d = dict(sv=np.zeros((ns, 9), np.float32), srgb=np.zeros((ns, 3), np.float32), snrm=np.zeros((ns, 3), np.float32), slum=np.zeros(ns, np.float32),
+                 lv=np.zeros((nl, 9), np.float32), lrgb=np.zeros((nl, 3), np.float32), lnrm=np.zeros((nl, 3), np.float32), llum=np.zeros(nl, np.float32))
+        assert self.L.ref_scene_get(*[_p(d[k]) for k in ("sv", "srgb", "snrm", "slum", "lv", "lrgb", "lnrm", "llum")]) == 0
+        return d
+
+    def camera(self, x, y, z, yaw_y=0.0, yaw_x=0.0):
+        assert self.L.ref_camera(*[ctypes.c_float(v) for v in (x, y, z, yaw_y, yaw_x)]) == 0
+
+    def closest_hit(self, org, dir):
+        org, dir = _f32(org).reshape(-1, 3), _f32(dir).reshape(-1, 3)
+        n = len(org)
+        ty, ix = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        t, pos = np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        assert self.L.ref_closest_hit(_p(org), _p(dir), n, _p(ty), _p(ix), _p(t), _p(pos)) == 0
+        return ty, ix, t, pos
+
+    def rmap_build(self):
+        nv = self.L.ref_rmap_build()
+        assert nv >= 0
+        return nv
+
+    def rmap_counts(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        assert self.L.ref_rmap_counts(ctypes.byref(a), ctypes.byref(b)) == 0
+        return a.value, b.value
+
+    def rmap_volumes(self):
+        nv, _ = self.rmap_counts()
+        pos, nrm, surf = np.zeros((nv, 3), np.float32), np.zeros((nv, 3), np.float32), np.zeros(nv, np.int32)
+        self.L.ref_rmap_get_volumes(_p(pos), _p(nrm), _p(surf))
+        return pos, nrm, surf
+
+    def rmap_tree(self):
+        _, nt = self.rmap_counts()
+        dim, leaf = np.zeros(nt, np.int32), np.zeros(nt, np.int32)
+        left, right = np.zeros(nt, np.uint32), np.zeros(nt, np.uint32)
+        data, pos, nrm = np.zeros(nt, np.float32), np.zeros((nt, 3), np.float32), np.zeros((nt, 3), np.float32)
+        self.L.ref_rmap_get_tree(_p(dim), _p(leaf), _p(left), _p(right), _p(data), _p(pos), _p(nrm))
+        return dict(dim=dim, leaf=leaf, left=left, right=right, data=data, pos=pos, nrm=nrm)
+
+    def rmap_state(self):
+        nv, _ = self.rmap_counts()
+        q, cdf = np.zeros((nv, A), np.float32), np.zeros((nv, A), np.float32)
+        vis, irr = np.zeros((nv, A), np.uint32), np.zeros(nv, np.float32)
+        self.L.ref_rmap_get_state(_p(q), _p(cdf), _p(vis), _p(irr))
+        return q, cdf, vis, irr
+
+    def rmap_set_q(self, q):
+        q = _f32(q)
+        assert self.L.ref_rmap_set_q(_p(q)) == 0
+
+    def rmap_update_distributions(self):
+        assert self.L.ref_rmap_update_distributions() == 0
+
+    def find_closest(self, pos, nrm, on_device=False):
+        pos, nrm = _f32(pos).reshape(-1, 3), _f32(nrm).reshape(-1, 3)
+        out = np.zeros(len(pos), np.int32)
+        assert self.L.ref_find_closest(_p(pos), _p(nrm), len(pos), _p(out), int(on_device)) == 0
+        return out
+
+    def grid_dir(self, vol, gx, gy):
+        gx, gy = _f32(gx), _f32(gy)
+        out = np.zeros((len(gx), 3), np.float32)
+        assert self.L.ref_grid_dir(int(vol), _p(gx), _p(gy), len(gx), _p(out)) == 0
+        return out
+
+    def render_default(self, frames):
+        out = np.zeros((self.width * self.height, 3), np.float32)
+        stats = np.zeros((frames, 2), np.float64)
+        assert self.L.ref_render_default(int(frames), _p(out), _p(stats)) == 0
+        return out, stats
+
+    def render_sarsa(self, frames, skip_frames=0):
+        mean = np.zeros((self.width * self.height, 3), np.float32)
+        last = np.zeros((self.width * self.height, 3), np.float32)
+        stats = np.zeros((frames, 5), np.float64)
+        assert self.L.ref_render_sarsa(int(frames), int(skip_frames), _p(mean), _p(last), _p(stats)) == 0
+        return mean, last, stats
+
+
+def mape_score(gt_rgb8, pred_rgb8):
+    """Graphing/mape.py:10-21 of the reference: sum(|gt/255 - p/255| / ((gt + 0.01)/255)) / (H*W*3) on 8-bit RGB."""
+    gt = np.asarray(gt_rgb8, np.float64)
+    p = np.asarray(pred_rgb8, np.float64)
+    return float(np.sum(np.abs(gt / 255.0 - p / 255.0) / ((gt + 0.01) / 255.0)) / gt.size)
+
+
+def to_rgb8(rgb_float):
+    """SDLScreen::PutPixelSDL colour conversion (G/sdl/sdl_screen.cpp:96-108): uint32(clamp(255*c, 0, 255)), truncation."""
+    c = np.nan_to_num(np.asarray(rgb_float, np.float32), nan=0.0)
+    return np.clip(np.float32(255.0) * c, 0.0, 255.0).astype(np.uint32).astype(np.uint8)
