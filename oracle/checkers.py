@@ -160,8 +160,8 @@ class Oracle:
 class Reference:
     """The unmodified reference engine. kind: 'host' (g++ shim build) or 'cuda' (its own kernels, GPU box only)."""
 
-    def __init__(self, kind="host"):
-        path = os.path.join(HERE, "_ref", "libref_%s.so" % kind)
+    def __init__(self, kind="host", suffix=""):
+        path = os.path.join(HERE, "_ref", "libref_%s%s.so" % (kind, suffix))
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (run oracle/build_ref.sh where /root/reference exists)")
         self.kind = kind
@@ -171,8 +171,8 @@ class Reference:
         self.width, self.height, self.spp, self.max_bounces = w.value, h.value, s.value, b.value
 
     @staticmethod
-    def available(kind="host"):
-        return os.path.exists(os.path.join(HERE, "_ref", "libref_%s.so" % kind))
+    def available(kind="host", suffix=""):
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_%s%s.so" % (kind, suffix)))
 
     def threads(self):
         return self.L.ref_threads()

@@ -1,0 +1,193 @@
+// rlpt_bvh.cu -- BVH construction on the GPU (sm_100a) for the SoA triangle buffer the scene upload emits.
+// The reference has no acceleration structure (brute force over every Surface and AreaLight, G/rays/ray.cu:22-35);
+// this is new work asked for by BASELINE.json north_star.
+//
+// Linear BVH (Karras 2012): 30-bit Morton code of each primitive's centroid, radix sort (CUB), one thread per
+// internal node finds its range and split from the sorted keys, AABBs are fitted bottom-up with one atomic flag per
+// node, then nodes are emitted breadth-first in the traversal layout (so "the first K nodes" is the top of the tree,
+// which is what kernels stage in shared memory when the whole tree does not fit):
+//   node = 4 x float4:  (c0.min.xyz, c0.max.x) (c0.max.yz, c1.min.xy) (c1.min.z, c1.max.xyz) (as_float(c0), as_float(c1), 0, 0)
+//   child link >= 0: node index;  < 0: ~primitive id (one primitive per leaf)
+// Leaf boxes are padded (kPad * primitive extent + kAbs) so that traversal can never cull a primitive that the
+// reference's FP32 Cramer test would accept for a ray passing just outside the exact triangle.
+#include "rlpt_internal.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <vector>
+#include <queue>
+#include <cfloat>
+
+namespace rlpt {
+
+namespace {
+constexpr float kPad = 1.f / 128.f;
+constexpr float kAbs = 1e-4f;
+
+struct Box { float lo[3], hi[3]; };
+
+__global__ void k_prim_bounds(const float4* __restrict__ tri, int n, Box* __restrict__ boxes, float* __restrict__ scene /*6*/) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = tri[3 * i], b = tri[3 * i + 1], c = tri[3 * i + 2];
+    float v0[3] = { a.x, a.y, a.z }, e1[3] = { a.w, b.x, b.y }, e2[3] = { b.z, b.w, c.x };
+    Box bx; float ext = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        float p1 = v0[k] + e1[k], p2 = v0[k] + e2[k];
+        bx.lo[k] = fminf(v0[k], fminf(p1, p2)); bx.hi[k] = fmaxf(v0[k], fmaxf(p1, p2));
+        ext = fmaxf(ext, bx.hi[k] - bx.lo[k]);
+    }
+    float pad = kPad * ext + kAbs;
+    for (int k = 0; k < 3; ++k) { bx.lo[k] -= pad + 1e-6f * fabsf(bx.lo[k]); bx.hi[k] += pad + 1e-6f * fabsf(bx.hi[k]); }
+    boxes[i] = bx;
+    // scene bounds: float atomics via ordered-int trick are not needed for <= thousands of primitives; use CAS min/max
+    for (int k = 0; k < 3; ++k) {
+        int* lo = reinterpret_cast<int*>(scene + k); int* hi = reinterpret_cast<int*>(scene + 3 + k);
+        int old = *lo; while (__int_as_float(old) > bx.lo[k]) { int prev = atomicCAS(lo, old, __float_as_int(bx.lo[k])); if (prev == old) break; old = prev; }
+        old = *hi; while (__int_as_float(old) < bx.hi[k]) { int prev = atomicCAS(hi, old, __float_as_int(bx.hi[k])); if (prev == old) break; old = prev; }
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu; v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__global__ void k_morton(const Box* __restrict__ boxes, int n, const float* __restrict__ scene, uint64_t* __restrict__ keys, int* __restrict__ ids) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t code = 0;
+    for (int k = 0; k < 3; ++k) {
+        float lo = scene[k], hi = scene[3 + k], c = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
+        float u = hi > lo ? (c - lo) / (hi - lo) : 0.5f;
+        uint32_t q = (uint32_t)fminf(fmaxf(u * 1024.f, 0.f), 1023.f);
+        code |= expand_bits(q) << (2 - k);
+    }
+    keys[i] = ((uint64_t)code << 32) | (uint32_t)i;        // primitive id in the low word makes every key unique
+    ids[i] = i;
+}
+
+__device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll(keys[i] ^ keys[j]);
+}
+// Karras 2012, one thread per internal node i in [0, n-1): children/parents in the temporary "LBVH numbering":
+// internal nodes 0..n-2, leaves encoded as (n-1) + sorted position.
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2; while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0; for (int t = lmax >> 1; t >= 1; t >>= 1) if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0; int t = l;
+    do { t = (t + 1) >> 1; if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int lc = (lo == gamma) ? (n - 1) + gamma : gamma;
+    int rc = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+    left[i] = lc; right[i] = rc; parent[lc] = i; parent[rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+// bottom-up AABB fit: each leaf walks up; the second thread to reach a node merges its children's boxes
+__global__ void k_fit(const Box* __restrict__ prim_boxes, const int* __restrict__ ids, int n, const int* __restrict__ left, const int* __restrict__ right,
+                      const int* __restrict__ parent, Box* __restrict__ node_boxes /* 2n-1 */, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = (n - 1) + i;
+    node_boxes[node] = prim_boxes[ids[i]];
+    __threadfence();
+    int p = parent[node];
+    while (p >= 0) {
+        if (atomicAdd(flags + p, 1) == 0) return;
+        Box a = node_boxes[left[p]], b = node_boxes[right[p]], m;
+        for (int k = 0; k < 3; ++k) { m.lo[k] = fminf(a.lo[k], b.lo[k]); m.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+        node_boxes[p] = m;
+        __threadfence();
+        p = parent[p];
+    }
+}
+// emit traversal nodes; `order[k]` = LBVH internal node placed at output slot k (breadth-first), `slot_of[i]` its inverse
+__global__ void k_emit(const Box* __restrict__ node_boxes, const int* __restrict__ ids, int n, const int* __restrict__ left, const int* __restrict__ right,
+                       const int* __restrict__ order, const int* __restrict__ slot_of, float4* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n - 1) return;
+    int i = order[k];
+    int lc = left[i], rc = right[i];
+    Box a = node_boxes[lc], b = node_boxes[rc];
+    int l0 = lc >= n - 1 ? ~ids[lc - (n - 1)] : slot_of[lc];
+    int l1 = rc >= n - 1 ? ~ids[rc - (n - 1)] : slot_of[rc];
+    out[4 * k + 0] = make_float4(a.lo[0], a.lo[1], a.lo[2], a.hi[0]);
+    out[4 * k + 1] = make_float4(a.hi[1], a.hi[2], b.lo[0], b.lo[1]);
+    out[4 * k + 2] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
+    out[4 * k + 3] = make_float4(__int_as_float(l0), __int_as_float(l1), 0.f, 0.f);
+}
+}  // namespace
+
+#define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
+
+int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s) {
+    int rc = 0;
+    Box *boxes = nullptr, *node_boxes = nullptr; float* scene = nullptr; uint64_t *keys = nullptr, *keys_s = nullptr; int *ids = nullptr, *ids_s = nullptr;
+    int *left = nullptr, *right = nullptr, *parent = nullptr, *flags = nullptr, *order = nullptr, *slot_of = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+    float4* out = nullptr;
+    const int T = 128;
+    *d_bvh = nullptr; *n_nodes = 0; *depth = 0;
+    if (n <= 0) return 0;
+    BVH_CK(cudaMalloc(&boxes, sizeof(Box) * n)); BVH_CK(cudaMalloc(&scene, sizeof(float) * 6));
+    {
+        float init[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        BVH_CK(cudaMemcpyAsync(scene, init, sizeof init, cudaMemcpyHostToDevice, s));
+    }
+    k_prim_bounds<<<(n + T - 1) / T, T, 0, s>>>(d_tri, n, boxes, scene);
+    if (n == 1) {
+        // a single primitive: one node whose second child is an empty box
+        Box b; BVH_CK(cudaStreamSynchronize(s)); BVH_CK(cudaMemcpy(&b, boxes, sizeof(Box), cudaMemcpyDeviceToHost));
+        float4 h[4] = { make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]), make_float4(b.hi[1], b.hi[2], FLT_MAX, FLT_MAX),
+                        make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX), make_float4(0, 0, 0, 0) };
+        int l0 = ~0; memcpy(&h[3].x, &l0, 4); memcpy(&h[3].y, &l0, 4);
+        BVH_CK(cudaMalloc(&out, sizeof(float4) * 4)); BVH_CK(cudaMemcpy(out, h, sizeof h, cudaMemcpyHostToDevice));
+        *d_bvh = out; out = nullptr; *n_nodes = 1; *depth = 1; goto done;
+    }
+    BVH_CK(cudaMalloc(&keys, sizeof(uint64_t) * n)); BVH_CK(cudaMalloc(&keys_s, sizeof(uint64_t) * n));
+    BVH_CK(cudaMalloc(&ids, sizeof(int) * n)); BVH_CK(cudaMalloc(&ids_s, sizeof(int) * n));
+    k_morton<<<(n + T - 1) / T, T, 0, s>>>(boxes, n, scene, keys, ids);
+    BVH_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
+    BVH_CK(cudaMalloc(&tmp, tmp_bytes));
+    BVH_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
+    BVH_CK(cudaMalloc(&left, sizeof(int) * (n - 1))); BVH_CK(cudaMalloc(&right, sizeof(int) * (n - 1)));
+    BVH_CK(cudaMalloc(&parent, sizeof(int) * (2 * n - 1))); BVH_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
+    BVH_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), s));
+    BVH_CK(cudaMalloc(&node_boxes, sizeof(Box) * (2 * n - 1)));
+    k_karras<<<(n - 1 + T - 1) / T, T, 0, s>>>(keys_s, n, left, right, parent);
+    k_fit<<<(n + T - 1) / T, T, 0, s>>>(boxes, ids_s, n, left, right, parent, node_boxes, flags);
+    {
+        // breadth-first numbering of the internal nodes (host walk over the n-1 child links; O(n), one-off)
+        std::vector<int> hl(n - 1), hr(n - 1), ord, slot(n - 1, -1);
+        BVH_CK(cudaStreamSynchronize(s));
+        BVH_CK(cudaMemcpy(hl.data(), left, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost));
+        BVH_CK(cudaMemcpy(hr.data(), right, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost));
+        std::queue<std::pair<int, int>> q; q.push({ 0, 1 }); int maxd = 1;
+        while (!q.empty()) {
+            auto [i, d] = q.front(); q.pop();
+            slot[i] = (int)ord.size(); ord.push_back(i); if (d > maxd) maxd = d;
+            if (hl[i] < n - 1) q.push({ hl[i], d + 1 });
+            if (hr[i] < n - 1) q.push({ hr[i], d + 1 });
+        }
+        if ((int)ord.size() != n - 1) { rc = -2; goto done; }
+        BVH_CK(cudaMalloc(&order, sizeof(int) * (n - 1))); BVH_CK(cudaMalloc(&slot_of, sizeof(int) * (n - 1)));
+        BVH_CK(cudaMemcpy(order, ord.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice));
+        BVH_CK(cudaMemcpy(slot_of, slot.data(), sizeof(int) * (n - 1), cudaMemcpyHostToDevice));
+        *depth = maxd + 1;
+    }
+    BVH_CK(cudaMalloc(&out, sizeof(float4) * 4 * (n - 1)));
+    k_emit<<<(n - 1 + T - 1) / T, T, 0, s>>>(node_boxes, ids_s, n, left, right, order, slot_of, out);
+    BVH_CK(cudaStreamSynchronize(s));
+    BVH_CK(cudaGetLastError());
+    *d_bvh = out; out = nullptr; *n_nodes = n - 1;
+done:
+    cudaFree(boxes); cudaFree(node_boxes); cudaFree(scene); cudaFree(keys); cudaFree(keys_s); cudaFree(ids); cudaFree(ids_s);
+    cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(flags); cudaFree(order); cudaFree(slot_of); cudaFree(tmp); cudaFree(out);
+    return rc;
+}
+
+}  // namespace rlpt

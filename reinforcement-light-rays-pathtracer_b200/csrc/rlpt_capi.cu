@@ -1,0 +1,659 @@
+// rlpt_capi.cu -- the extern "C" boundary declared in include/rlpt.h: context, scene upload (SoA + GPU BVH), radiance
+// map lifecycle, the per-frame launch sequences, frame buffer and statistics. Host code only; every number the hot
+// path produces comes from the kernels in rlpt_kernels.cu / rlpt_bvh.cu. No CPU fallback exists: without a usable
+// GPU rlpt_ctx_create fails and nothing else can be called.
+#include "../../include/rlpt.h"
+#include "rlpt_internal.h"
+#include "rlpt_radiance_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <array>
+
+using namespace rlpt;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// same text as the reference's check_cuda (G/utils/cuda_helpers.cu:6-14), but returned instead of exit(99)
+#define CK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { char b_[512]; \
+    snprintf(b_, sizeof b_, "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)e_, __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+    return fail(RLPT_ERR_CUDA, b_); } } while (0)
+
+struct rlpt_ctx {
+    int device = 0; int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    rlpt_config cfg{};
+    rlpt_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
+    // scene
+    bool have_scene = false;
+    int n_surf = 0, n_light = 0, bvh_depth = 0;
+    float4 *d_tri = nullptr, *d_shade = nullptr, *d_bvh = nullptr; float* d_surf_lum_over_pi = nullptr;
+    std::vector<float> h_surf_v, h_surf_nrm, h_surf_rgb, h_light_v, h_light_rgb;
+    std::vector<int> h_surf_class;
+    SceneDev scene{};
+    // camera / per-frame
+    float cam[3] = { 0.f, 0.f, -3.f }; float yaw_y = 0.f, yaw_x = 0.f;
+    FrameDyn* d_dyn = nullptr;
+    // radiance map
+    bool have_rmap = false;
+    std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
+    float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
+    float *d_q = nullptr, *d_cdf = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
+    RadianceDev rm{};
+    // wavefront state
+    size_t queue_capacity = 0; PathQueue q[2]{}; int* d_counts = nullptr; int counts_len = 0;
+    float4* d_accum = nullptr; int accum_pixels = 0;
+    unsigned long long* d_stats = nullptr;
+    float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
+    size_t smem_bytes = 0; int grid = 148;
+    uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
+    double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0;
+};
+
+static void free_scene(rlpt_ctx* c) {
+    cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_surf_lum_over_pi);
+    c->d_tri = c->d_shade = c->d_bvh = nullptr; c->d_surf_lum_over_pi = nullptr; c->have_scene = false;
+}
+static void free_rmap(rlpt_ctx* c) {
+    cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
+    cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt);
+    c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
+    c->have_rmap = false; c->rm = RadianceDev{};
+}
+static void free_frame(rlpt_ctx* c) {
+    for (int k = 0; k < 2; ++k) { cudaFree(c->q[k].o); cudaFree(c->q[k].d); cudaFree(c->q[k].thr); cudaFree(c->q[k].meta); c->q[k] = PathQueue{}; }
+    cudaFree(c->d_counts); cudaFree(c->d_accum); c->d_counts = nullptr; c->d_accum = nullptr; c->queue_capacity = 0; c->accum_pixels = 0; c->counts_len = 0;
+}
+
+static float luminance3(const float* c) { float mx = std::max(c[2], std::max(c[0], c[1])), mn = std::min(c[2], std::min(c[0], c[1])); return 0.5f * (mx + mn); }
+
+extern "C" {
+
+const char* rlpt_last_error(void) { return g_err.c_str(); }
+int rlpt_version(void) { return 100; }
+
+int rlpt_config_default(rlpt_config* cfg) {
+    if (!cfg) return fail(RLPT_ERR_ARG, "rlpt_config_default: null");
+    cfg->width = 512; cfg->height = 512; cfg->spp = 32; cfg->max_bounces = 80; cfg->env_light = 0.f;
+    cfg->area_per_sample = 0.001f; cfg->max_dist = 0.003f;
+    cfg->initial_radiance = (1.f / (12.f * 12.f)) * 100.f; cfg->radiance_threshold = (1.f / (12.f * 12.f)) * 0.8f;
+    cfg->seed = 1984u; cfg->traversal = RLPT_TRAVERSAL_AUTO; cfg->rank = 0; cfg->world_size = 1;
+    return RLPT_OK;
+}
+
+int rlpt_ctx_create(int device, rlpt_ctx** out) {
+    if (!out) return fail(RLPT_ERR_ARG, "rlpt_ctx_create: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(RLPT_ERR_CUDA, std::string("rlpt_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= n) return fail(RLPT_ERR_ARG, "rlpt_ctx_create: device out of range");
+    CK(cudaSetDevice(device));
+    rlpt_ctx* c = new rlpt_ctx; c->device = device;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_dyn, sizeof(FrameDyn))); CK(cudaMemset(c->d_dyn, 0, sizeof(FrameDyn)));
+    CK(cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8)); CK(cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
+    CK(cudaMalloc(&c->d_cap_n, sizeof(int))); CK(cudaMemset(c->d_cap_n, 0, sizeof(int)));
+    rlpt_config_default(&c->cfg);
+    float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
+    upload_cell_cos(cs);
+    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin);
+    if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
+    *out = c;
+    return RLPT_OK;
+}
+
+int rlpt_ctx_destroy(rlpt_ctx* c) {
+    if (!c) return RLPT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c); free_rmap(c); free_frame(c);
+    cudaFree(c->d_dyn); cudaFree(c->d_stats); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
+    delete c;
+    return RLPT_OK;
+}
+
+int rlpt_sync(rlpt_ctx* c) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError()); return RLPT_OK; }
+int rlpt_stream(rlpt_ctx* c, void** s) { if (!c || !s) return fail(RLPT_ERR_ARG, "null"); *s = (void*)c->stream; return RLPT_OK; }
+int rlpt_config_get(rlpt_ctx* c, rlpt_config* cfg) { if (!c || !cfg) return fail(RLPT_ERR_ARG, "null"); *cfg = c->cfg; return RLPT_OK; }
+int rlpt_set_allreduce(rlpt_ctx* c, rlpt_allreduce_fn fn, void* user) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); c->allreduce = fn; c->allreduce_user = user; return RLPT_OK; }
+
+static int choose_traversal(rlpt_ctx* c, int traversal) {
+    int n_tri = c->n_surf + c->n_light;
+    size_t optin = 0; { cudaDeviceProp prop; cudaGetDeviceProperties(&prop, c->device); optin = prop.sharedMemPerBlockOptin; }
+    SceneDev& sc = c->scene;
+    int mode = traversal ? traversal : c->cfg.traversal;
+    if (mode == RLPT_TRAVERSAL_AUTO) mode = n_tri <= 48 ? RLPT_TRAVERSAL_BRUTE : RLPT_TRAVERSAL_BVH;
+    sc.brute = mode == RLPT_TRAVERSAL_BRUTE;
+    // shared-memory budget: leave room for >= 2 CTAs per SM when the scene is small, otherwise take what one CTA can have
+    size_t tri_b = (size_t)n_tri * 48, shade_b = (size_t)n_tri * 64, node_b = (size_t)sc.n_nodes * 64;
+    size_t budget = optin > 4096 ? optin - 2048 : optin;
+    if (tri_b + shade_b + node_b <= budget) { sc.smem_tris = n_tri; sc.smem_shade = 1; sc.smem_nodes = sc.n_nodes; }
+    else {
+        sc.smem_tris = 0; sc.smem_shade = 0;
+        if (sc.brute) return fail(RLPT_ERR_UNSUPPORTED, "brute-force traversal needs the whole scene in shared memory");
+        size_t top = std::min(node_b, (size_t)64 * 1024);          // top of the BFS-ordered tree
+        sc.smem_nodes = (int)(top / 64);
+    }
+    c->smem_bytes = scene_smem_bytes(sc);
+    return RLPT_OK;
+}
+
+int rlpt_config_set(rlpt_ctx* c, const rlpt_config* cfg) {
+    if (!c || !cfg) return fail(RLPT_ERR_ARG, "rlpt_config_set: null");
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->spp <= 0) return fail(RLPT_ERR_ARG, "rlpt_config_set: width, height, spp must be positive");
+    if (cfg->max_bounces <= 0 || cfg->max_bounces > 255) return fail(RLPT_ERR_ARG, "rlpt_config_set: max_bounces must be in 1..255");
+    if (cfg->world_size <= 0 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(RLPT_ERR_ARG, "rlpt_config_set: bad rank/world_size");
+    if ((double)cfg->width * cfg->height * cfg->spp > 2.0e9) return fail(RLPT_ERR_ARG, "rlpt_config_set: width*height*spp exceeds 2^31 paths per frame");
+    bool geometry_changed = cfg->width != c->cfg.width || cfg->height != c->cfg.height;
+    c->cfg = *cfg;
+    CK(cudaSetDevice(c->device));
+    if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); free_frame(c); }
+    if (c->have_scene) { int rc = choose_traversal(c, 0); if (rc) return rc; }
+    if (c->have_rmap) c->rm.max_dist = cfg->max_dist;
+    return RLPT_OK;
+}
+
+int rlpt_scene_upload(rlpt_ctx* c, const float* sv, const float* srgb, int ns, const float* lv, const float* lrgb, int nl) {
+    if (!c) return fail(RLPT_ERR_ARG, "rlpt_scene_upload: null ctx");
+    if (ns < 0 || nl < 0 || ns + nl == 0) return fail(RLPT_ERR_ARG, "rlpt_scene_upload: empty scene");
+    if ((ns && (!sv || !srgb)) || (nl && (!lv || !lrgb))) return fail(RLPT_ERR_ARG, "rlpt_scene_upload: null array");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    free_scene(c); free_rmap(c);
+    const int n = ns + nl;
+    c->n_surf = ns; c->n_light = nl;
+    c->h_surf_v.assign(sv, sv + 9 * (size_t)ns); c->h_surf_rgb.assign(srgb, srgb + 3 * (size_t)ns);
+    c->h_light_v.assign(lv, lv + 9 * (size_t)nl); c->h_light_rgb.assign(lrgb, lrgb + 3 * (size_t)nl);
+    c->h_surf_nrm.resize(3 * (size_t)ns); c->h_surf_class.resize(ns);
+    std::vector<float4> tri(3 * (size_t)n), shade(4 * (size_t)n); std::vector<float> lum_pi(std::max(ns, 1));
+    // normal classes: surfaces whose normals compare equal component-wise (the reference's `normal == leaf.normal`,
+    // radiance_map.cu:175) share a class; -0 == +0; a NaN normal equals nothing.
+    std::map<std::array<uint32_t, 3>, int> classes;
+    for (int g = 0; g < n; ++g) {
+        const float* v = g < ns ? sv + 9 * (size_t)g : lv + 9 * (size_t)(g - ns);
+        const float* col = g < ns ? srgb + 3 * (size_t)g : lrgb + 3 * (size_t)(g - ns);
+        float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+        float T1 = fmaf(e1[1], e2[2], -(e1[2] * e2[1]));
+        tri[3 * g] = make_float4(v[0], v[1], v[2], e1[0]); tri[3 * g + 1] = make_float4(e1[1], e1[2], e2[0], e2[1]); tri[3 * g + 2] = make_float4(e2[2], T1, 0.f, 0.f);
+        float nrm[3]; host_triangle_normal(v, nrm);
+        f3 N = { nrm[0], nrm[1], nrm[2] }, T, B; tangent_frame(N, T, B);
+        float lum = luminance3(col);
+        int cls;
+        if (std::isnan(nrm[0]) || std::isnan(nrm[1]) || std::isnan(nrm[2])) cls = -2;
+        else {
+            std::array<uint32_t, 3> key; for (int k = 0; k < 3; ++k) { float f = nrm[k] == 0.f ? 0.f : nrm[k]; memcpy(&key[k], &f, 4); }
+            auto it = classes.find(key); if (it == classes.end()) it = classes.emplace(key, (int)classes.size()).first; cls = it->second;
+        }
+        if (g < ns) {
+            for (int k = 0; k < 3; ++k) c->h_surf_nrm[3 * (size_t)g + k] = nrm[k];
+            c->h_surf_class[g] = cls; lum_pi[g] = lum / PI_F;
+            shade[4 * g] = make_float4(nrm[0], nrm[1], nrm[2], lum / PI_F);
+            shade[4 * g + 3] = make_float4(col[0] / PI_F, col[1] / PI_F, col[2] / PI_F, 0.f);     // BRDF = diffuse_c / (float)M_PI
+        } else {
+            shade[4 * g] = make_float4(nrm[0], nrm[1], nrm[2], lum);
+            shade[4 * g + 3] = make_float4(col[0], col[1], col[2], 0.f);
+        }
+        int qcls = cls == -2 ? -3 : cls;           // a query with a NaN normal matches no leaf
+        float fc; memcpy(&fc, &qcls, 4);
+        shade[4 * g + 1] = make_float4(T.x, T.y, T.z, fc);
+        shade[4 * g + 2] = make_float4(B.x, B.y, B.z, 0.f);
+    }
+    CK(cudaMalloc(&c->d_tri, sizeof(float4) * tri.size())); CK(cudaMalloc(&c->d_shade, sizeof(float4) * shade.size()));
+    CK(cudaMalloc(&c->d_surf_lum_over_pi, sizeof(float) * lum_pi.size()));
+    CK(cudaMemcpyAsync(c->d_tri, tri.data(), sizeof(float4) * tri.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_surf_lum_over_pi, lum_pi.data(), sizeof(float) * lum_pi.size(), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int n_nodes = 0, depth = 0;
+    int rc = bvh_build_gpu(c->d_tri, n, &c->d_bvh, &n_nodes, &depth, c->stream);
+    if (rc) { char b[128]; snprintf(b, sizeof b, "rlpt_scene_upload: GPU BVH build failed (%d: %s)", rc, rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "topology"); return fail(RLPT_ERR_CUDA, b); }
+    if (depth > 30) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_scene_upload: BVH deeper than the traversal stack");
+    c->bvh_depth = depth;
+    c->scene = SceneDev{}; c->scene.tri = c->d_tri; c->scene.shade = c->d_shade; c->scene.bvh = c->d_bvh;
+    c->scene.n_tri = n; c->scene.n_surf = ns; c->scene.n_light = nl; c->scene.n_nodes = n_nodes;
+    c->have_scene = true;
+    return choose_traversal(c, 0);
+}
+
+int rlpt_scene_info(rlpt_ctx* c, int* ns, int* nl, int* nodes, int* depth) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_scene_info: no scene");
+    if (ns) *ns = c->n_surf; if (nl) *nl = c->n_light; if (nodes) *nodes = c->scene.n_nodes; if (depth) *depth = c->bvh_depth;
+    return RLPT_OK;
+}
+int rlpt_scene_bvh_download(rlpt_ctx* c, float* nodes16, int max_nodes) {
+    if (!c || !c->have_scene || !nodes16) return fail(RLPT_ERR_ARG, "rlpt_scene_bvh_download: no scene");
+    CK(cudaSetDevice(c->device));
+    int n = std::min(max_nodes, c->scene.n_nodes);
+    CK(cudaMemcpy(nodes16, c->d_bvh, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost));
+    return RLPT_OK;
+}
+
+int rlpt_camera_set(rlpt_ctx* c, const float position[4], float yaw_y, float yaw_x) {
+    if (!c || !position) return fail(RLPT_ERR_ARG, "rlpt_camera_set: null");
+    c->cam[0] = position[0]; c->cam[1] = position[1]; c->cam[2] = position[2]; c->yaw_y = yaw_y; c->yaw_x = yaw_x;
+    return RLPT_OK;
+}
+
+int rlpt_closest_hit_device(rlpt_ctx* c, const float* d_org, const float* d_dir, int n, int traversal, int* d_type, int* d_index, float* d_t, unsigned long long* d_counters) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: upload a scene first");
+    if (n < 0) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: negative ray count");
+    if (n == 0) return RLPT_OK;
+    CK(cudaSetDevice(c->device));
+    SceneDev saved = c->scene; size_t saved_smem = c->smem_bytes;
+    if (traversal) { int rc = choose_traversal(c, traversal); if (rc) { c->scene = saved; c->smem_bytes = saved_smem; return rc; } }
+    launch_closest_hit(c->scene, d_org, d_dir, n, (float)c->cfg.height, d_type, d_index, d_t, d_counters, c->smem_bytes, c->stream);
+    c->scene = saved; c->smem_bytes = saved_smem;
+    CK(cudaGetLastError());
+    return RLPT_OK;
+}
+
+int rlpt_closest_hit(rlpt_ctx* c, const float* org, const float* dir, int n, int traversal, int* type, int* index, float* t, unsigned long long* counters) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: upload a scene first");
+    if (n < 0) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: negative ray count");
+    if (n == 0) return RLPT_OK;
+    if (!org || !dir || !type || !index || !t) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: null array");
+    CK(cudaSetDevice(c->device));
+    float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int *d_ty = nullptr, *d_ix = nullptr; unsigned long long* d_c = nullptr;
+    CK(cudaMalloc(&d_o, sizeof(float) * 3 * (size_t)n)); CK(cudaMalloc(&d_d, sizeof(float) * 3 * (size_t)n)); CK(cudaMalloc(&d_t, sizeof(float) * (size_t)n));
+    CK(cudaMalloc(&d_ty, sizeof(int) * (size_t)n)); CK(cudaMalloc(&d_ix, sizeof(int) * (size_t)n));
+    if (counters) { CK(cudaMalloc(&d_c, sizeof(unsigned long long) * 2)); CK(cudaMemsetAsync(d_c, 0, sizeof(unsigned long long) * 2, c->stream)); }
+    CK(cudaMemcpyAsync(d_o, org, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_d, dir, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    int rc = rlpt_closest_hit_device(c, d_o, d_d, n, traversal, d_ty, d_ix, d_t, d_c);
+    if (rc == RLPT_OK) {
+        CK(cudaMemcpyAsync(type, d_ty, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(index, d_ix, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(t, d_t, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        if (counters) CK(cudaMemcpyAsync(counters, d_c, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_ty); cudaFree(d_ix); cudaFree(d_c);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ radiance map
+int rlpt_radiance_map_build(rlpt_ctx* c) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build: upload a scene first");
+    if (c->n_surf == 0) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build: scene has no surfaces");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    free_rmap(c);
+    host_build_radiance_map(c->h_surf_v.data(), c->h_surf_nrm.data(), c->n_surf, c->cfg.area_per_sample, c->h_vol, c->h_tree);
+    const int nv = (int)c->h_vol.size(), nt = (int)c->h_tree.size();
+    if (nv == 0) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build: no radiance volumes (surfaces smaller than area_per_sample)");
+    if (nv >= (1 << 24)) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_radiance_map_build: more than 2^24 radiance volumes");
+    // re-lay the reference's flattened tree out as inner nodes only; leaf children carry the volume in the child word
+    std::vector<int> inner_of(nt, -1); int n_inner = 0;
+    for (int i = 0; i < nt; ++i) if (!c->h_tree[i].leaf) inner_of[i] = n_inner++;
+    auto child_word = [&](unsigned idx) -> uint32_t { const HostTreeElement& e = c->h_tree[idx]; return e.leaf ? (KD_LEAF | (uint32_t)(int)e.data) : (uint32_t)inner_of[idx]; };
+    std::vector<float4> kd(std::max(n_inner, 1));
+    for (int i = 0; i < nt; ++i) {
+        const HostTreeElement& e = c->h_tree[i]; if (e.leaf) continue;
+        uint32_t l = child_word(e.left), r = child_word(e.right); float fl, fr, fd; int dim = e.dim;
+        memcpy(&fl, &l, 4); memcpy(&fr, &r, 4); memcpy(&fd, &dim, 4);
+        kd[inner_of[i]] = make_float4(e.data, fl, fr, fd);
+    }
+    std::vector<float4> posn(nv); std::vector<int> vsurf(nv);
+    for (int i = 0; i < nv; ++i) {
+        int cls = c->h_surf_class[c->h_vol[i].surface]; float fc; memcpy(&fc, &cls, 4);
+        posn[i] = make_float4(c->h_vol[i].pos[0], c->h_vol[i].pos[1], c->h_vol[i].pos[2], fc); vsurf[i] = c->h_vol[i].surface;
+    }
+    const size_t cells = (size_t)nv * CELLS;
+    CK(cudaMalloc(&c->d_kd, sizeof(float4) * kd.size())); CK(cudaMalloc(&c->d_posn, sizeof(float4) * nv)); CK(cudaMalloc(&c->d_vol_surface, sizeof(int) * nv));
+    CK(cudaMalloc(&c->d_q, 4 * cells)); CK(cudaMalloc(&c->d_cdf, 4 * cells)); CK(cudaMalloc(&c->d_visits, 4 * cells)); CK(cudaMalloc(&c->d_irr, 4 * (size_t)nv));
+    CK(cudaMalloc(&c->d_acc_sum, 4 * cells)); CK(cudaMalloc(&c->d_acc_cnt, 4 * cells));
+    CK(cudaMemcpy(c->d_kd, kd.data(), sizeof(float4) * kd.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_posn, posn.data(), sizeof(float4) * nv, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_vol_surface, vsurf.data(), sizeof(int) * nv, cudaMemcpyHostToDevice));
+    // initial state: Q = INITIAL_RADIANCE everywhere, visits 0 (radiance_volume.cu:49-89); the CDF and the irradiance
+    // estimate are derived from Q by the merge kernel (deliberate deviation: the reference starts from the exclusive
+    // CDF k/144, under which 1 sample in 144 fails until the first update)
+    std::vector<float> q0(cells, c->cfg.initial_radiance);
+    CK(cudaMemcpy(c->d_q, q0.data(), 4 * cells, cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->d_visits, 0, 4 * cells)); CK(cudaMemset(c->d_acc_sum, 0, 4 * cells)); CK(cudaMemset(c->d_acc_cnt, 0, 4 * cells));
+    RadianceDev& rm = c->rm;
+    rm.kd_inner = c->d_kd; rm.vol_posn = c->d_posn; rm.vol_surface = c->d_vol_surface; rm.q = c->d_q; rm.cdf = c->d_cdf; rm.visits = c->d_visits;
+    rm.irradiance = c->d_irr; rm.acc_sum = c->d_acc_sum; rm.acc_cnt = c->d_acc_cnt; rm.n_vol = nv; rm.n_inner = n_inner;
+    rm.root = child_word(0);
+    rm.root_px = c->h_tree[0].pos[0]; rm.root_py = c->h_tree[0].pos[1]; rm.root_pz = c->h_tree[0].pos[2];
+    rm.max_dist = c->cfg.max_dist;
+    c->have_rmap = true;
+    launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    return RLPT_OK;
+}
+
+int rlpt_radiance_map_info(rlpt_ctx* c, int* nv, int* nt) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_info: no radiance map");
+    if (nv) *nv = (int)c->h_vol.size(); if (nt) *nt = (int)c->h_tree.size();
+    return RLPT_OK;
+}
+int rlpt_radiance_map_tree(rlpt_ctx* c, int* dim, int* leaf, unsigned* left, unsigned* right, float* data, float* pos3, float* nrm3) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_tree: no radiance map");
+    for (size_t i = 0; i < c->h_tree.size(); ++i) {
+        const HostTreeElement& e = c->h_tree[i];
+        if (dim) dim[i] = e.dim; if (leaf) leaf[i] = e.leaf; if (left) left[i] = e.left; if (right) right[i] = e.right; if (data) data[i] = e.data;
+        for (int k = 0; k < 3; ++k) { if (pos3) pos3[3 * i + k] = e.pos[k]; if (nrm3) nrm3[3 * i + k] = e.nrm[k]; }
+    }
+    return RLPT_OK;
+}
+
+int rlpt_radiance_map_find_closest(rlpt_ctx* c, const float* pos, const float* nrm, int n, int* out) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_find_closest: no radiance map");
+    if (n <= 0) return n == 0 ? RLPT_OK : fail(RLPT_ERR_ARG, "negative count");
+    CK(cudaSetDevice(c->device));
+    // query normal -> normal class (exact component-wise equality with some surface's normal, else "matches nothing")
+    std::vector<int> cls(n, -3);
+    for (int i = 0; i < n; ++i) {
+        const float* q = nrm + 3 * (size_t)i;
+        for (int s = 0; s < c->n_surf; ++s) { const float* m = &c->h_surf_nrm[3 * (size_t)s]; if (q[0] == m[0] && q[1] == m[1] && q[2] == m[2]) { cls[i] = c->h_surf_class[s]; break; } }
+    }
+    float* d_pos = nullptr; int *d_cls = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)n)); CK(cudaMalloc(&d_cls, sizeof(int) * (size_t)n)); CK(cudaMalloc(&d_out, sizeof(int) * (size_t)n));
+    CK(cudaMemcpyAsync(d_pos, pos, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_cls, cls.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_find_closest(c->rm, c->scene, d_pos, reinterpret_cast<const float*>(d_cls), n, d_out, c->stream);
+    CK(cudaMemcpyAsync(out, d_out, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    cudaFree(d_pos); cudaFree(d_cls); cudaFree(d_out);
+    return RLPT_OK;
+}
+
+int rlpt_radiance_map_set_q(rlpt_ctx* c, const float* q, const unsigned* visits) {
+    if (!c || !c->have_rmap || !q) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_set_q: no radiance map / null");
+    CK(cudaSetDevice(c->device));
+    const size_t cells = (size_t)c->rm.n_vol * CELLS;
+    CK(cudaMemcpyAsync(c->d_q, q, 4 * cells, cudaMemcpyHostToDevice, c->stream));
+    if (visits) CK(cudaMemcpyAsync(c->d_visits, visits, 4 * cells, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return RLPT_OK;
+}
+int rlpt_radiance_map_update_distributions(rlpt_ctx* c) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_update_distributions: no radiance map");
+    CK(cudaSetDevice(c->device));
+    launch_merge(c->rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
+    CK(cudaGetLastError());
+    return RLPT_OK;
+}
+int rlpt_radiance_map_download(rlpt_ctx* c, float* q, float* cdf, unsigned* visits, float* irr, float* pos3, float* nrm3, int* surface) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_download: no radiance map");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    const size_t cells = (size_t)c->rm.n_vol * CELLS;
+    if (q) CK(cudaMemcpy(q, c->d_q, 4 * cells, cudaMemcpyDeviceToHost));
+    if (cdf) CK(cudaMemcpy(cdf, c->d_cdf, 4 * cells, cudaMemcpyDeviceToHost));
+    if (visits) CK(cudaMemcpy(visits, c->d_visits, 4 * cells, cudaMemcpyDeviceToHost));
+    if (irr) CK(cudaMemcpy(irr, c->d_irr, 4 * (size_t)c->rm.n_vol, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < c->h_vol.size(); ++i) {
+        for (int k = 0; k < 3; ++k) { if (pos3) pos3[3 * i + k] = c->h_vol[i].pos[k]; if (nrm3) nrm3[3 * i + k] = c->h_vol[i].nrm[k]; }
+        if (surface) surface[i] = c->h_vol[i].surface;
+    }
+    return RLPT_OK;
+}
+int rlpt_radiance_map_delta_download(rlpt_ctx* c, float* sum, unsigned* cnt) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_delta_download: no radiance map");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    const size_t cells = (size_t)c->rm.n_vol * CELLS;
+    if (sum) CK(cudaMemcpy(sum, c->d_acc_sum, 4 * cells, cudaMemcpyDeviceToHost));
+    if (cnt) CK(cudaMemcpy(cnt, c->d_acc_cnt, 4 * cells, cudaMemcpyDeviceToHost));
+    return RLPT_OK;
+}
+
+int rlpt_radiance_map_save_q(rlpt_ctx* c, const char* path) {
+    if (!c || !c->have_rmap || !path) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_save_q: no radiance map / null path");
+    const int nv = c->rm.n_vol; std::vector<float> q((size_t)nv * CELLS);
+    int rc = rlpt_radiance_map_download(c, q.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); if (rc) return rc;
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(RLPT_ERR_IO, std::string("Unable to save the RadianceMap: ") + path);
+    fprintf(f, "%d\n", CELLS);
+    for (int i = 0; i < nv; ++i) {
+        fprintf(f, "%g %g %g", c->h_vol[i].pos[0], c->h_vol[i].pos[1], c->h_vol[i].pos[2]);     // ofstream << float prints %g with 6 digits
+        for (int k = 0; k < CELLS; ++k) fprintf(f, " %g", q[(size_t)i * CELLS + k]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return RLPT_OK;
+}
+int rlpt_radiance_map_load_q(rlpt_ctx* c, const char* path) {
+    if (!c || !c->have_rmap || !path) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_load_q: no radiance map / null path");
+    FILE* f = fopen(path, "r");
+    if (!f) return fail(RLPT_ERR_IO, std::string("Could not read radiance volumes: ") + path);
+    int cells = 0; const int nv = c->rm.n_vol;
+    if (fscanf(f, "%d", &cells) != 1 || cells != CELLS) { fclose(f); return fail(RLPT_ERR_IO, "rlpt_radiance_map_load_q: first line must be 144"); }
+    std::vector<float> q((size_t)nv * CELLS);
+    for (int i = 0; i < nv; ++i) {
+        float p[3]; if (fscanf(f, "%f %f %f", p, p + 1, p + 2) != 3) { fclose(f); return fail(RLPT_ERR_IO, "rlpt_radiance_map_load_q: file has fewer volumes than the map"); }
+        for (int k = 0; k < CELLS; ++k) if (fscanf(f, "%f", &q[(size_t)i * CELLS + k]) != 1) { fclose(f); return fail(RLPT_ERR_IO, "rlpt_radiance_map_load_q: truncated row"); }
+    }
+    fclose(f);
+    int rc = rlpt_radiance_map_set_q(c, q.data(), nullptr); if (rc) return rc;
+    return rlpt_radiance_map_update_distributions(c);
+}
+
+// ------------------------------------------------------------------------------------------------ frames
+static int ensure_frame_buffers(rlpt_ctx* c) {
+    const rlpt_config& g = c->cfg;
+    size_t paths = (size_t)g.width * g.height * g.spp;
+    if (paths > c->queue_capacity) {
+        for (int k = 0; k < 2; ++k) { cudaFree(c->q[k].o); cudaFree(c->q[k].d); cudaFree(c->q[k].thr); cudaFree(c->q[k].meta); c->q[k] = PathQueue{}; }
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc(&c->q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&c->q[k].d, sizeof(float4) * paths));
+            CK(cudaMalloc(&c->q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&c->q[k].meta, sizeof(uint32_t) * paths));
+        }
+        c->queue_capacity = paths;
+    }
+    if (c->counts_len < g.max_bounces + 2) { cudaFree(c->d_counts); CK(cudaMalloc(&c->d_counts, sizeof(int) * (g.max_bounces + 2))); c->counts_len = g.max_bounces + 2; }
+    if (c->accum_pixels != g.width * g.height) {
+        cudaFree(c->d_accum); CK(cudaMalloc(&c->d_accum, sizeof(float4) * (size_t)g.width * g.height));
+        CK(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)g.width * g.height, c->stream)); c->accum_pixels = g.width * g.height;
+    }
+    return RLPT_OK;
+}
+
+// Enqueue one frame of `method` (0 default, 1 SARSA): primary cast + (max_bounces-1) bounce launches, all asynchronous;
+// the live-ray count of every bounce stays on the device.
+static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
+    int rc = ensure_frame_buffers(c); if (rc) return rc;
+    const rlpt_config& g = c->cfg;
+    FrameDyn dyn{};
+    dyn.sample_base = (uint32_t)((c->frames_done * (uint64_t)g.world_size + (uint64_t)g.rank) * (uint64_t)g.spp);
+    dyn.learn = learn; dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
+    dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
+    dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
+    dyn.capture_bounce = c->cap_bounce; dyn.capture_max = c->cap_bounce >= 0 ? c->cap_max : 0;
+    CK(cudaMemcpyAsync(c->d_dyn, &dyn, sizeof dyn, cudaMemcpyHostToDevice, c->stream));     // pageable source: staged before the call returns
+    CK(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * (g.max_bounces + 2), c->stream));
+    FrameParams p{};
+    p.scene = c->scene; p.rm = c->rm; p.q[0] = c->q[0]; p.q[1] = c->q[1]; p.counts = c->d_counts; p.accum = c->d_accum; p.stats = c->d_stats;
+    p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n; p.dyn = c->d_dyn;
+    p.width = g.width; p.height = g.height; p.spp = g.spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
+    const int grid = c->n_sm * 8;
+    launch_primary(p, method, grid, c->smem_bytes, c->stream);
+    for (int b = 1; b < g.max_bounces; ++b) launch_bounce(p, method, b, grid, c->smem_bytes, c->stream);
+    c->launches += g.max_bounces;
+    CK(cudaGetLastError());
+    c->frames_done++;
+    c->cap_bounce = -1;
+    return RLPT_OK;
+}
+
+static int enqueue_merge(rlpt_ctx* c) {
+    if (c->allreduce && c->cfg.world_size > 1) {
+        const uint64_t cells = (uint64_t)c->rm.n_vol * CELLS;
+        if (c->allreduce(c->d_acc_sum, cells, 0, (void*)c->stream, c->allreduce_user)) return fail(RLPT_ERR_COLLECTIVE, "all-reduce hook failed (target sums)");
+        if (c->allreduce(c->d_acc_cnt, cells, 1, (void*)c->stream, c->allreduce_user)) return fail(RLPT_ERR_COLLECTIVE, "all-reduce hook failed (visit counts)");
+    }
+    launch_merge(c->rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 0, c->stream);
+    c->launches += 1;
+    CK(cudaGetLastError());
+    return RLPT_OK;
+}
+
+static int timed_begin(rlpt_ctx* c) { CK(cudaSetDevice(c->device)); CK(cudaEventRecord(c->ev0, c->stream)); return RLPT_OK; }
+static int timed_end(rlpt_ctx* c, int frames) {
+    CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->device_seconds += ms * 1e-3; c->frames_rendered += frames;
+    CK(cudaGetLastError());
+    return RLPT_OK;
+}
+
+int rlpt_render_default(rlpt_ctx* c, int frames) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_render_default: upload a scene first");
+    if (frames < 0) return fail(RLPT_ERR_ARG, "rlpt_render_default: negative frame count");
+    int rc = timed_begin(c); if (rc) return rc;
+    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 0, 0); if (rc) return rc; }
+    return timed_end(c, frames);
+}
+int rlpt_sarsa_trace(rlpt_ctx* c) {
+    if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_sarsa_trace: needs a scene and a radiance map");
+    CK(cudaSetDevice(c->device));
+    return enqueue_trace(c, 1, 1);
+}
+int rlpt_sarsa_merge(rlpt_ctx* c) {
+    if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_sarsa_merge: no radiance map");
+    CK(cudaSetDevice(c->device));
+    return enqueue_merge(c);
+}
+int rlpt_render_sarsa(rlpt_ctx* c, int frames) {
+    if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa: needs a scene and a radiance map");
+    if (frames < 0) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa: negative frame count");
+    int rc = timed_begin(c); if (rc) return rc;
+    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 1, 1); if (rc) return rc; rc = enqueue_merge(c); if (rc) return rc; }
+    return timed_end(c, frames);
+}
+int rlpt_render_sarsa_frozen(rlpt_ctx* c, int frames) {
+    if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa_frozen: needs a scene and a radiance map");
+    if (frames < 0) return fail(RLPT_ERR_ARG, "negative frame count");
+    int rc = timed_begin(c); if (rc) return rc;
+    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 1, 0); if (rc) return rc; }
+    return timed_end(c, frames);
+}
+
+int rlpt_frame_reset(rlpt_ctx* c) {
+    if (!c) return fail(RLPT_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (c->d_accum) CK(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)c->accum_pixels, c->stream));
+    return RLPT_OK;
+}
+int rlpt_frame_allreduce(rlpt_ctx* c) {
+    if (!c || !c->d_accum) return fail(RLPT_ERR_ARG, "rlpt_frame_allreduce: nothing rendered");
+    if (!c->allreduce || c->cfg.world_size <= 1) return RLPT_OK;
+    CK(cudaSetDevice(c->device));
+    if (c->allreduce(c->d_accum, (uint64_t)c->accum_pixels * 4, 0, (void*)c->stream, c->allreduce_user)) return fail(RLPT_ERR_COLLECTIVE, "all-reduce hook failed (frame buffer)");
+    return RLPT_OK;
+}
+int rlpt_frame_download(rlpt_ctx* c, float* rgb) {
+    if (!c || !c->d_accum || !rgb) return fail(RLPT_ERR_ARG, "rlpt_frame_download: nothing rendered / null");
+    CK(cudaSetDevice(c->device));
+    float* d = nullptr; size_t n = (size_t)c->accum_pixels;
+    CK(cudaMalloc(&d, sizeof(float) * 3 * n));
+    launch_frame_mean(c->d_accum, d, (int)n, c->stream);
+    CK(cudaMemcpyAsync(rgb, d, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    cudaFree(d);
+    return RLPT_OK;
+}
+int rlpt_frame_download_argb(rlpt_ctx* c, uint32_t* argb) {
+    if (!c || !c->d_accum || !argb) return fail(RLPT_ERR_ARG, "rlpt_frame_download_argb: nothing rendered / null");
+    CK(cudaSetDevice(c->device));
+    uint32_t* d = nullptr; size_t n = (size_t)c->accum_pixels;
+    CK(cudaMalloc(&d, sizeof(uint32_t) * n));
+    launch_pack_argb(c->d_accum, d, c->cfg.width, c->cfg.height, c->stream);
+    CK(cudaMemcpyAsync(argb, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    cudaFree(d);
+    return RLPT_OK;
+}
+
+// 32-bpp BMP exactly as SDL_SaveBMP writes the reference's ARGB8888 surface (Images/render.bmp): BITMAPV4HEADER (108 bytes),
+// BI_BITFIELDS, masks R 00ff0000 G 0000ff00 B 000000ff A ff000000, pixel data at offset 122, rows bottom-up.
+int rlpt_frame_save_bmp(rlpt_ctx* c, const char* path) {
+    if (!c || !path) return fail(RLPT_ERR_ARG, "rlpt_frame_save_bmp: null");
+    const int w = c->cfg.width, h = c->cfg.height;
+    std::vector<uint32_t> px((size_t)w * h);
+    int rc = rlpt_frame_download_argb(c, px.data()); if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RLPT_ERR_IO, std::string("rlpt_frame_save_bmp: cannot open ") + path);
+    auto u16 = [&](uint16_t v) { fwrite(&v, 2, 1, f); }; auto u32 = [&](uint32_t v) { fwrite(&v, 4, 1, f); };
+    const uint32_t data = (uint32_t)w * h * 4, off = 14 + 108;
+    fputc('B', f); fputc('M', f); u32(off + data); u16(0); u16(0); u32(off);
+    u32(108); u32((uint32_t)w); u32((uint32_t)h); u16(1); u16(32); u32(3 /*BI_BITFIELDS*/); u32(data); u32(0); u32(0); u32(0); u32(0);
+    u32(0x00ff0000u); u32(0x0000ff00u); u32(0x000000ffu); u32(0xff000000u);
+    u32(0x57696e20u /*LCS_WINDOWS_COLOR_SPACE*/); for (int i = 0; i < 9; ++i) u32(0); u32(0); u32(0); u32(0);
+    for (int y = h - 1; y >= 0; --y) fwrite(&px[(size_t)y * w], 4, (size_t)w, f);
+    fclose(f);
+    return RLPT_OK;
+}
+
+int rlpt_stats(rlpt_ctx* c, rlpt_stats_t* out) {
+    if (!c || !out) return fail(RLPT_ERR_ARG, "rlpt_stats: null");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    unsigned long long h[8]; CK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+    out->path_length_sum = (double)h[0]; out->zero_contribution_paths = (double)h[1]; out->paths = (double)h[2];
+    out->ray_casts = (double)h[0]; out->device_seconds = c->device_seconds; out->frames = c->frames_rendered; out->kernel_launches = c->launches;
+    return RLPT_OK;
+}
+int rlpt_stats_reset(rlpt_ctx* c) {
+    if (!c) return fail(RLPT_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * 8, c->stream));
+    c->device_seconds = 0.0; c->frames_rendered = 0.0; c->launches = 0.0;
+    return RLPT_OK;
+}
+
+int rlpt_measure_fp32_peak(rlpt_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(RLPT_ERR_ARG, "null");
+    CK(cudaSetDevice(c->device));
+    const int grid = c->n_sm * 8, iters = 4096; float* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * (size_t)grid * 256));
+    launch_fp32_peak(d, 64, grid, c->stream);                         // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        launch_fp32_peak(d, iters, grid, c->stream);
+        CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        double flops = (double)grid * 256.0 * iters * 16.0 * 8.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaFree(d);
+    *tflops = best;
+    return RLPT_OK;
+}
+
+int rlpt_capture_rays(rlpt_ctx* c, int method, int bounce, float* org, float* dir, int max_rays, int* n_captured) {
+    if (!c || !c->have_scene || (method == 1 && !c->have_rmap)) return fail(RLPT_ERR_ARG, "rlpt_capture_rays: needs a scene (and a radiance map for method 1)");
+    if (max_rays <= 0 || bounce < 0 || !org || !dir || !n_captured) return fail(RLPT_ERR_ARG, "rlpt_capture_rays: bad arguments");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); c->d_cap_o = c->d_cap_d = nullptr;
+    CK(cudaMalloc(&c->d_cap_o, sizeof(float4) * (size_t)max_rays)); CK(cudaMalloc(&c->d_cap_d, sizeof(float4) * (size_t)max_rays));
+    CK(cudaMemset(c->d_cap_n, 0, sizeof(int)));
+    c->cap_max = max_rays; c->cap_bounce = bounce;
+    // trace one frame that is not counted: no learning, frame counter and accumulators restored afterwards
+    uint64_t saved_frames = c->frames_done;
+    std::vector<float4> keep; if (c->d_accum) { keep.resize((size_t)c->accum_pixels); CK(cudaMemcpy(keep.data(), c->d_accum, sizeof(float4) * keep.size(), cudaMemcpyDeviceToHost)); }
+    unsigned long long hs[8]; CK(cudaMemcpy(hs, c->d_stats, sizeof hs, cudaMemcpyDeviceToHost));
+    int rc = enqueue_trace(c, method, 0); if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    c->frames_done = saved_frames; c->launches -= c->cfg.max_bounces;
+    if (!keep.empty()) CK(cudaMemcpy(c->d_accum, keep.data(), sizeof(float4) * keep.size(), cudaMemcpyHostToDevice));
+    else CK(cudaMemset(c->d_accum, 0, sizeof(float4) * (size_t)c->accum_pixels));
+    CK(cudaMemcpy(c->d_stats, hs, sizeof hs, cudaMemcpyHostToDevice));
+    int n = 0; CK(cudaMemcpy(&n, c->d_cap_n, sizeof(int), cudaMemcpyDeviceToHost)); n = std::min(n, max_rays);
+    std::vector<float4> o(n), d(n);
+    if (n) { CK(cudaMemcpy(o.data(), c->d_cap_o, sizeof(float4) * n, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(d.data(), c->d_cap_d, sizeof(float4) * n, cudaMemcpyDeviceToHost)); }
+    for (int i = 0; i < n; ++i) { org[3 * i] = o[i].x; org[3 * i + 1] = o[i].y; org[3 * i + 2] = o[i].z; dir[3 * i] = d[i].x; dir[3 * i + 1] = d[i].y; dir[3 * i + 2] = d[i].z; }
+    *n_captured = n;
+    return RLPT_OK;
+}
+
+}  // extern "C"

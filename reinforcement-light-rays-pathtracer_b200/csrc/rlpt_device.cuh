@@ -1,0 +1,243 @@
+// rlpt_device.cuh -- per-ray device functions of the hot path (sm_100a). Everything here is FP32 scalar math on the
+// FP32 pipes; no tensor-core work belongs here (BASELINE.json north_star).
+//
+// Bit-exactness: the closest-hit test, the ray normalisation and the nearest-volume distance reproduce the exact
+// rounding sequence of the reference's kernels as nvcc 12.9 builds them for sm_100a (-fmad=true); the sequences were
+// read from the SASS of G/rays/ray.cu and G/radiance_volumes/radiance_map.cu and are spelled out with explicit
+// round-to-nearest intrinsics so no compiler setting can re-associate or re-contract them ("Bit-exact
+// arithmetic"). The functions are __host__ __device__ only so that tests/ can also exercise them on the CPU through
+// tests/devfn_host.cpp; the product library never runs them on the host.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RLPT_HD __host__ __device__ __forceinline__
+#else
+#define RLPT_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define RLPT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define RLPT_MUL(a, b) __fmul_rn((a), (b))
+#define RLPT_ADD(a, b) __fadd_rn((a), (b))
+#define RLPT_SUB(a, b) __fsub_rn((a), (b))
+#define RLPT_DIV(a, b) __fdiv_rn((a), (b))
+#define RLPT_SQRT(a) __fsqrt_rn((a))
+#else
+// host instantiation (tests only): compiled with -ffp-contract=off so each operator is one rounding
+#define RLPT_FMA(a, b, c) fmaf((a), (b), (c))
+#define RLPT_MUL(a, b) ((a) * (b))
+#define RLPT_ADD(a, b) ((a) + (b))
+#define RLPT_SUB(a, b) ((a) - (b))
+#define RLPT_DIV(a, b) ((a) / (b))
+#define RLPT_SQRT(a) sqrtf((a))
+#endif
+
+namespace rlpt {
+
+constexpr int GRID = 12;
+constexpr int CELLS = 144;
+constexpr float RHO = 1.f / (2.f * 3.1415926535f);        // G/constants/image_settings.h:13
+constexpr float GRID_RHO = 1.f / 144.f;                   // G/constants/radiance_volumes_settings.h:10
+constexpr float PI_F = 3.14159265358979323846f;           // (float)M_PI
+constexpr float T_MISS = 999999.f;                        // G/rays/ray.cu:18
+constexpr float RAY_EPS = 0.00001f;                       // G/path_tracing/default_path_tracing.cu:80
+
+struct f3 { float x, y, z; };
+
+// ---------------------------------------------------------------- RNG: Philox4x32-10, counter = (pixel, sample, bounce, purpose)
+// Replaces the per-pixel XORWOW state array of init_rand_state (G/utils/cuda_helpers.cu:16-25): no state in HBM, and
+// a path's random numbers do not depend on which GPU or which queue slot traces it.
+enum { PURPOSE_CAMERA = 0, PURPOSE_BOUNCE = 1 };
+RLPT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+RLPT_HD void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// cuRAND's curand_uniform convention, (0,1]
+RLPT_HD float u01(uint32_t x) { return x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
+RLPT_HD void draw4(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t purpose, float& u0, float& u1, float& u2, float& u3) {
+    uint32_t c0 = pixel, c1 = sample, c2 = bounce, c3 = purpose;
+    philox4x32_10(seed, 0u, c0, c1, c2, c3);
+    u0 = u01(c0); u1 = u01(c1); u2 = u01(c2); u3 = u01(c3);
+}
+
+// ---------------------------------------------------------------- ray setup
+// glm::normalize as Ray::Ray applies it (G/rays/ray.cu:6-14): v * (1/sqrt(dot)), dot = fma(z,z,fma(x,x,y*y)).
+RLPT_HD f3 normalize_ref(f3 v) {
+    float d = RLPT_FMA(v.z, v.z, RLPT_FMA(v.x, v.x, RLPT_MUL(v.y, v.y)));
+    float inv = RLPT_DIV(1.f, RLPT_SQRT(d));
+    return { RLPT_MUL(v.x, inv), RLPT_MUL(v.y, inv), RLPT_MUL(v.z, inv) };
+}
+
+// Ray::sample_ray_through_pixel + rotate_ray (G/rays/ray.cu:144-172). cy/sy/cx/sx = cos/sin of yaw_y, yaw_x.
+RLPT_HD f3 camera_dir(int px, int py, float u0, float u1, int width, int height, bool rotated, float cy, float sy, float cx, float sx) {
+    float x = (float)px + u0, y = (float)py + u1;
+    f3 d = normalize_ref(f3{ x - (float)width / 2.f, y - (float)height / 2.f, (float)height });
+    if (rotated) {
+        f3 r1 = { (cy * d.x + 0.f * d.y) + (-sy) * d.z, d.y, (sy * d.x + 0.f * d.y) + cy * d.z };
+        d = f3{ r1.x, (cx * r1.y) + sx * r1.z, ((-sx) * r1.y) + cx * r1.z };
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------- ray / triangle (G/rays/ray.cu:39-74,115-141)
+// Triangle record, three float4: q0 = (v0.x, v0.y, v0.z, e1.x), q1 = (e1.y, e1.z, e2.x, e2.y), q2 = (e2.z, T1, -, -)
+// with e1 = v1-v0, e2 = v2-v0 and T1 = fma(e1.y, e2.z, -(e1.z*e2.y)) -- all ray-independent single roundings of the
+// reference's own expressions, so storing them changes no bit of the result.
+struct TriRec { float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, T1; };
+
+// One Cramer solve. a = -(dir*SCREEN_HEIGHT) (the first column of A), o = ray origin.
+// Returns true when the reference's acceptance test passes; t is the reference's solution.x.
+RLPT_HD bool tri_solve(const TriRec& r, float ox, float oy, float oz, float a0, float a1, float a2, float& t) {
+    float T2 = RLPT_FMA(r.e2z, a1, -RLPT_MUL(r.e2y, a2));
+    float T3 = RLPT_FMA(r.e1z, a1, -RLPT_MUL(r.e1y, a2));
+    float detA = RLPT_FMA(r.e2x, T3, RLPT_FMA(a0, r.T1, -RLPT_MUL(r.e1x, T2)));
+    float bx = RLPT_SUB(ox, r.v0x), by = RLPT_SUB(oy, r.v0y), bz = RLPT_SUB(oz, r.v0z);
+    float p75 = RLPT_MUL(r.e1z, by), p80 = RLPT_MUL(r.e1y, bz);
+    float U2 = RLPT_FMA(r.e2z, by, -RLPT_MUL(r.e2y, bz));
+    float V3 = RLPT_FMA(a1, bz, -RLPT_MUL(a2, by));
+    float dy = RLPT_FMA(r.e2x, V3, RLPT_FMA(a0, U2, -RLPT_MUL(T2, bx)));
+    float dz = RLPT_FMA(T3, bx, RLPT_FMA(a0, RLPT_SUB(p80, p75), -RLPT_MUL(r.e1x, V3)));
+    if (!(detA != 0.f)) return false;
+    // Exact-safe early outs. rn(n/d) is negative exactly when n and d have strictly opposite signs and the quotient
+    // does not round to -0, which needs |n/d| > 2^-150; for |d| < 2^23 that holds whenever n*d < -2^-100.
+    // Anything the filter does not reject goes through the reference's own divisions below.
+    const float kTiny = -7.888609052210118e-31f;   // -2^-100
+    if (fabsf(detA) < 8388608.f) {
+        if (RLPT_MUL(dy, detA) < kTiny || RLPT_MUL(dz, detA) < kTiny) return false;
+    }
+    float u = RLPT_DIV(dy, detA), v = RLPT_DIV(dz, detA);
+    if (!(u >= 0.f && v >= 0.f && RLPT_ADD(u, v) <= 1.f)) return false;
+    float dx = RLPT_FMA(r.e2x, RLPT_SUB(p75, p80), RLPT_FMA(r.T1, bx, -RLPT_MUL(r.e1x, U2)));
+    t = RLPT_DIV(dx, detA);
+    return t >= 0.f;
+}
+
+// ---------------------------------------------------------------- hemisphere helpers (G/utils/hemisphere_helpers.cu)
+// create_normal_coordinate_system (:31-44); evaluated once per surface at upload, kept beside the triangle.
+RLPT_HD void tangent_frame(f3 n, f3& T, f3& B) {
+    f3 t = fabsf(n.x) > fabsf(n.y) ? f3{ n.z, 0.f, -n.x } : f3{ 0.f, -n.z, n.y };
+    float inv = 1.f / sqrtf(t.x * t.x + t.y * t.y + t.z * t.z);
+    T = f3{ t.x * inv, t.y * inv, t.z * inv };
+    B = f3{ n.y * T.z - T.y * n.z, n.z * T.x - T.z * n.x, n.x * T.y - T.x * n.y };
+}
+// Shirley-Chiu concentric map of the unit square onto the hemisphere, the function map() computes (:134-226), in
+// its four-quadrant form: radius r = max(|a|,|b|), angle from the quadrant; y_h = cos(theta) = 1 - r^2 and
+// sin(theta) = r*sqrt(2 - r^2) (the reference takes acos(1-r^2) and then sin/cos of it).
+RLPT_HD void square_to_hemisphere(float sx, float sy, float& xh, float& yh, float& zh) {
+    float a = 2.f * sx - 1.f, b = 2.f * sy - 1.f, r, phi;
+    const float q = 0.78539816339744830962f;   // pi/4
+    if (a > -b) {
+        if (a > b) { r = a; phi = q * (b / a); }
+        else { r = b; phi = q * (2.f - a / b); }
+    } else {
+        if (a < b) { r = -a; phi = q * (4.f + b / a); }
+        else { r = -b; phi = (b != 0.f) ? q * (6.f - a / b) : 0.f; }
+    }
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(phi, &s, &c);
+#else
+    s = sinf(phi); c = cosf(phi);
+#endif
+    float st = r * sqrtf(2.f - r * r);
+    xh = st * c; yh = 1.f - r * r; zh = st * s;
+}
+// convert_grid_pos_to_direction (:96-105): the matrix is a rotation (T,N,B) plus the volume position, and the
+// position cancels in normalize(world - position); so the direction is the rotated hemisphere point.
+RLPT_HD f3 grid_to_direction(float gx, float gy, f3 T, f3 N, f3 B) {
+    float xh, yh, zh;
+    square_to_hemisphere(gx * (1.f / 12.f), gy * (1.f / 12.f), xh, yh, zh);
+    f3 w = { T.x * xh + N.x * yh + B.x * zh, T.y * xh + N.y * yh + B.y * zh, T.z * xh + N.z * yh + B.z * zh };
+    float inv = 1.f / sqrtf(w.x * w.x + w.y * w.y + w.z * w.z);
+    return f3{ w.x * inv, w.y * inv, w.z * inv };
+}
+// cos(theta) of a cell centre: dot(direction, N) = y_h = 1 - r^2 with r = max(|2x-1|,|2y-1|):
+// it depends only on the cell, not on the volume.
+RLPT_HD float cell_centre_cos(int cell) {
+    float a = 2.f * (((float)(cell / GRID) + 0.5f) * (1.f / 12.f)) - 1.f, b = 2.f * (((float)(cell % GRID) + 0.5f) * (1.f / 12.f)) - 1.f;
+    float r = fmaxf(fabsf(a), fabsf(b));
+    return 1.f - r * r;
+}
+// sample_random_direction_around_intersection + uniform_hemisphere_sample (:8-25,67-93): cos(theta) = r1
+RLPT_HD f3 uniform_hemisphere(float r1, float r2, f3 T, f3 N, f3 B) {
+    float st = sqrtf(1.f - r1 * r1), phi = 6.28318530717958647692f * r2, s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(phi, &s, &c);
+#else
+    s = sinf(phi); c = cosf(phi);
+#endif
+    float x = st * c, z = st * s;
+    return f3{ x * B.x + r1 * N.x + z * T.x, x * B.y + r1 * N.y + z * T.y, x * B.z + r1 * N.z + z * T.z };
+}
+
+// ---------------------------------------------------------------- radiance-volume CDF sampling
+// RadianceVolume::sample_direction_from_radiance_distribution (G/radiance_volumes/radiance_volume.cu:192-244): bin 0 when
+// r <= cdf[0], otherwise the bin with cdf[k-1] <= r < cdf[k]. Deliberate deviation: when r lies past the
+// last bin the reference returns a zero direction and pdf 0 (a NaN sample); here it is clamped to the last bin of
+// non-zero width. `load(k)` reads cdf[k] of the volume.
+template <class Load>
+RLPT_HD int sample_sector(Load load, float r, float& pdf) {
+    float c0 = load(0);
+    if (r <= c0) { pdf = RHO * (c0 / GRID_RHO); return 0; }
+    int lo = 1, hi = CELLS;            // first k in [1,144) with cdf[k] > r
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (load(mid) > r) hi = mid; else lo = mid + 1; }
+    int k = lo;
+    if (k >= CELLS) { k = CELLS - 1; while (k > 0 && !(load(k) - load(k - 1) > 0.f)) --k; }
+    float hi_v = load(k), lo_v = k > 0 ? load(k - 1) : 0.f;
+    pdf = RHO * ((hi_v - lo_v) / GRID_RHO);
+    return k;
+}
+
+// ---------------------------------------------------------------- nearest radiance volume
+// RadianceMap::find_closest_radiance_volume_iterative (G/radiance_volumes/radiance_map.cu:150-203) over the reference's
+// own kd-tree, re-laid-out: inner nodes only, one float4 each (split, left, right, dim) with leaf children encoded
+// in the child word as (KD_LEAF | volume); a leaf visit reads vol_posn[volume] = (position, normal class).
+// Visit order, strict-< tie rule, the "within" test in double and the distance rounding are the reference's.
+constexpr uint32_t KD_LEAF = 0x80000000u;
+RLPT_HD float kd_distance(float px, float py, float pz, float qx, float qy, float qz) {
+    float dx = RLPT_SUB(qx, px), dy = RLPT_SUB(qy, py), dz = RLPT_SUB(qz, pz);
+    return RLPT_SQRT(RLPT_FMA(dz, dz, RLPT_FMA(dx, dx, RLPT_MUL(dy, dy))));
+}
+template <class LoadInner, class LoadVol>
+RLPT_HD int kd_find(LoadInner load_inner, LoadVol load_vol, uint32_t root, float root_px, float root_py, float root_pz,
+                    float px, float py, float pz, int normal_class, float max_dist) {
+    uint32_t stack[32]; int top = 0;
+    int best = 0; float best_d = kd_distance(px, py, pz, root_px, root_py, root_pz);
+    uint32_t cur = root; bool have = true;
+    const double md = (double)max_dist;
+    while (have) {
+        if (cur & KD_LEAF) {
+            int vol = (int)(cur & ~KD_LEAF);
+            float vx, vy, vz; int cls; load_vol(vol, vx, vy, vz, cls);
+            float d = kd_distance(px, py, pz, vx, vy, vz);
+            if (cls == normal_class && d < best_d) { best = vol; best_d = d; }
+            if (top > 0) cur = stack[--top]; else have = false;
+        } else {
+            float split; uint32_t left, right; int dim; load_inner(cur, split, left, right, dim);
+            float c = dim == 0 ? px : (dim == 1 ? py : pz);
+            float delta = RLPT_SUB(c, split);
+            bool within = (double)delta * (double)delta < md;
+            uint32_t near_c = (c < split) ? left : right, far_c = (c < split) ? right : left;
+            if (within && top < 32) stack[top++] = far_c;
+            cur = near_c;
+        }
+    }
+    return best;
+}
+
+}  // namespace rlpt

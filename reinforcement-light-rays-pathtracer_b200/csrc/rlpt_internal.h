@@ -1,0 +1,91 @@
+// rlpt_internal.h -- device-side data layout shared by the kernels and the C-ABI host code (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rlpt_device.cuh"
+
+namespace rlpt {
+
+// ---- scene in HBM: SoA float4 buffers (the .obj loader / scene upload emits these; DESIGN.md "Scene layout")
+// Primitive id ("gid"): surfaces 0..n_surf-1 then lights n_surf..n_tri-1, the order Ray::closest_intersection scans
+// them in (G/rays/ray.cu:22-35), so "lowest gid wins a tie" is the reference's tie rule.
+//   tri[3*gid+0] = (v0.x, v0.y, v0.z, e1.x)   tri[3*gid+1] = (e1.y, e1.z, e2.x, e2.y)   tri[3*gid+2] = (e2.z, T1, 0, 0)
+//   shade[4*gid+0] = (N.x, N.y, N.z, luminance/pi)                [lights: luminance]
+//   shade[4*gid+1] = (T.x, T.y, T.z, as_float(normal class))
+//   shade[4*gid+2] = (B.x, B.y, B.z, 0)
+//   shade[4*gid+3] = (diffuse_c / pi  rgb, 0)                     [lights: diffuse_p rgb]
+//   bvh[4*node+0..3]: two child boxes + two child links, see rlpt_bvh.cu
+struct SceneDev {
+    const float4* tri;
+    const float4* shade;
+    const float4* bvh;
+    int n_tri, n_surf, n_light, n_nodes;
+    int brute;          // 1: scan all primitives in gid order from shared memory; 0: BVH traversal
+    int smem_tris;      // primitives staged in shared memory (all of them, or 0 when they do not fit)
+    int smem_nodes;     // BVH nodes staged in shared memory (BFS order, so this is the top of the tree)
+    int smem_shade;     // 1 when the shading records are staged too
+};
+
+// ---- radiance map in HBM (SoA; the reference keeps one 1832-byte AoS record per volume, radiance_volume.cuh:40-49)
+struct RadianceDev {
+    const float4* kd_inner;   // (split, as_float(left), as_float(right), as_float(dim)); leaf children = KD_LEAF | volume
+    const float4* vol_posn;   // (position, as_float(normal class))
+    const int* vol_surface;
+    float* q;                 // [n_vol][144]  Q(x, omega)                      radiance_grid
+    float* cdf;               // [n_vol][144]  inclusive CDF frozen per frame  radiance_distribution
+    uint32_t* visits;         // [n_vol][144]
+    float* irradiance;        // [n_vol]       sum_k Q_k cos_k lum/pi           irradiance_accum
+    float* acc_sum;           // [n_vol][144]  sum of TD targets this iteration
+    uint32_t* acc_cnt;        // [n_vol][144]  visits this iteration
+    int n_vol, n_inner;
+    uint32_t root;            // KD child word of the root
+    float root_px, root_py, root_pz;   // radiance_array[0].position as the reference initialises its search with
+    float max_dist;
+};
+
+// ---- wavefront path state, SoA, one slot per live path (two queues, ping-pong per bounce)
+//   o   = (origin, as_float(pixel))       d = (direction, BRDF luminance/pi of the surface the ray left)
+//   thr = (throughput rgb, as_float(volume << 8 | sector))       meta = sample << 8 | bounce
+struct PathQueue { float4* o; float4* d; float4* thr; uint32_t* meta; };
+
+// per-frame values that change between launches of the same (graph-captured) kernel sequence live in device memory
+struct FrameDyn {
+    uint32_t sample_base; int learn;
+    float cam_x, cam_y, cam_z, cy, sy, cx, sx; int rotated;
+    int capture_bounce, capture_max;
+};
+
+struct FrameParams {
+    SceneDev scene;
+    RadianceDev rm;
+    PathQueue q[2];
+    int* counts;                    // [max_bounces + 1] live paths entering each bounce
+    float4* accum;                  // [W*H] radiance sums (rgb) + sample count in w
+    unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests
+    float4* capture_o; float4* capture_d; int* capture_n;
+    const FrameDyn* dyn;
+    int width, height, spp, max_bounces;
+    uint32_t seed;
+    float env;
+};
+
+constexpr int BLOCK = 256;
+
+// host-visible launchers (rlpt_kernels.cu)
+void launch_primary(const FrameParams& p, int method, int grid, size_t smem, cudaStream_t s);
+void launch_bounce(const FrameParams& p, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float threshold, int rebuild_only, cudaStream_t s);
+void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
+                        unsigned long long* counters, size_t smem, cudaStream_t s);
+void launch_find_closest(const RadianceDev& rm, const SceneDev& sc, const float* pos, const float* nrm, int n, int* out, cudaStream_t s);
+void launch_frame_mean(const float4* accum, float* rgb, int n, cudaStream_t s);
+void launch_pack_argb(const float4* accum, uint32_t* argb, int width, int height, cudaStream_t s);
+void launch_fp32_peak(float* out, int iters, int grid, cudaStream_t s);
+size_t scene_smem_bytes(const SceneDev& sc);
+void upload_cell_cos(const float* cos144);
+int kernels_set_smem_limit(size_t bytes);
+
+// rlpt_bvh.cu: builds the BVH on the GPU from the tri buffer; returns node count and depth; d_bvh is allocated by the callee
+int bvh_build_gpu(const float4* d_tri, int n_tri, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s);
+
+}  // namespace rlpt

@@ -1,0 +1,426 @@
+// rlpt_kernels.cu -- the hot-path kernels (sm_100a): closest hit, wavefront path tracing with ray compaction,
+// Expected-SARSA sampling / TD accumulation, Q merge + CDF rebuild, pixel accumulation.
+//
+// Design (DESIGN.md has the long form):
+//  * one thread per live path per bounce; the scene (SoA float4 triangles, shading records, BVH nodes) is staged in
+//    shared memory by every CTA with vectorised float4 loads; B200 has no RT cores, traversal is FP32-pipe work
+//  * persistent grids sized in multiples of the SM count; the live-path count of each bounce lives in device memory
+//    (counts[b]) so a whole frame is a fixed launch sequence with no host round trip, captured in a CUDA graph
+//  * live rays are compacted every bounce with ballot/popc + one atomicAdd per warp (wavefront-style compaction)
+//  * TD targets are accumulated as (sum, count) per (volume, sector) with __match_any_sync warp aggregation
+//  * radiance is accumulated into a float4-per-pixel buffer in HBM with one vector RED per terminated path
+#include "rlpt_internal.h"
+
+namespace rlpt {
+
+__constant__ float c_cell_cos[CELLS];
+void upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_cell_cos, cos144, sizeof(float) * CELLS); }
+
+// ------------------------------------------------------------------------------------------------ scene access
+extern __shared__ float4 s_scene[];
+
+template <bool STAGED>
+struct SceneView {
+    const float4* tri_s; const float4* shade_s; const float4* nodes_s;
+    const float4* tri_g; const float4* shade_g; const float4* nodes_g;
+    int n_tri, n_surf, smem_nodes, brute;
+    __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
+    __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
+    __device__ __forceinline__ float4 node(int i) const {
+        if (STAGED) return nodes_s[i];
+        return i < smem_nodes ? nodes_s[i] : __ldg(nodes_g + i);
+    }
+};
+
+// Every CTA copies what fits of the scene into shared memory once (vectorised 16-byte loads, coalesced).
+template <bool STAGED>
+__device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
+    SceneView<STAGED> v;
+    v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute;
+    float4* p = s_scene;
+    int nt = 3 * sc.smem_tris, ns = sc.smem_shade ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
+    v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) p[i] = __ldg(sc.tri + i);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) p[nt + ns + i] = __ldg(sc.bvh + i);
+    __syncthreads();
+    return v;
+}
+
+size_t scene_smem_bytes(const SceneDev& sc) {
+    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes);
+}
+
+// ------------------------------------------------------------------------------------------------ closest hit
+template <bool STAGED>
+__device__ __forceinline__ TriRec load_tri(const SceneView<STAGED>& v, int gid) {
+    float4 a = v.tri(3 * gid), b = v.tri(3 * gid + 1), c = v.tri(3 * gid + 2);
+    return TriRec{ a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y };
+}
+
+__device__ __forceinline__ void slab(float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                     float ox, float oy, float oz, float ix, float iy, float iz, float& tn, float& tf) {
+    float x0 = (lox - ox) * ix, x1 = (hix - ox) * ix;
+    float y0 = (loy - oy) * iy, y1 = (hiy - oy) * iy;
+    float z0 = (loz - oz) * iz, z1 = (hiz - oz) * iz;
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+}
+
+// Closest hit of one ray: Ray::closest_intersection (G/rays/ray.cu:16-36). (dx,dy,dz) is the normalised direction;
+// H = SCREEN_HEIGHT. Result: best_t in the reference's units and the primitive id (-1 = NOTHING). The winner is the
+// lexicographic minimum of (t, gid), which is what the reference's scan order with strict < produces.
+template <bool STAGED, bool COUNT>
+__device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox, float oy, float oz, float dx, float dy, float dz, float H,
+                                            float& best_t, int& best_gid, float& sdx, float& sdy, float& sdz, unsigned& n_tri, unsigned& n_box) {
+    sdx = RLPT_MUL(dx, H); sdy = RLPT_MUL(dy, H); sdz = RLPT_MUL(dz, H);          // dir * SCREEN_HEIGHT (ray.cu:53)
+    const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
+    best_t = T_MISS; best_gid = -1;
+    if (v.brute) {
+        for (int gid = 0; gid < v.n_tri; ++gid) {
+            TriRec r = load_tri(v, gid); float t;
+            if (COUNT) n_tri++;
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && t < best_t) { best_t = t; best_gid = gid; }
+        }
+        return;
+    }
+    const float ix = 1.f / sdx, iy = 1.f / sdy, iz = 1.f / sdz;
+    int stack[32]; int top = 0; int cur = 0;
+    while (true) {
+        float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
+        float tn0, tf0, tn1, tf1;
+        slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
+        slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
+        if (COUNT) n_box += 2;
+        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
+        if (h0 && c0 < 0) {
+            int gid = ~c0; TriRec r = load_tri(v, gid); float t;
+            if (COUNT) n_tri++;
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+            h0 = false;
+        }
+        if (h1 && c1 < 0) {
+            int gid = ~c1; TriRec r = load_tri(v, gid); float t;
+            if (COUNT) n_tri++;
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+            h1 = false;
+        }
+        if (h0 && h1) {
+            bool swap = tn1 < tn0;
+            if (top < 32) stack[top++] = swap ? c0 : c1;
+            cur = swap ? c1 : c0;
+        } else if (h0) cur = c0;
+        else if (h1) cur = c1;
+        else { if (top == 0) break; cur = stack[--top]; }
+    }
+}
+
+template <bool STAGED, bool COUNT>
+__global__ void __launch_bounds__(BLOCK) k_closest_hit(SceneDev sc, const float* __restrict__ org, const float* __restrict__ dir, int n, float H,
+                                                       int* __restrict__ type, int* __restrict__ index, float* __restrict__ t_out,
+                                                       unsigned long long* __restrict__ counters) {
+    SceneView<STAGED> v = stage_scene<STAGED>(sc);
+    unsigned nt = 0, nb = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        f3 d = normalize_ref(f3{ dir[3 * i], dir[3 * i + 1], dir[3 * i + 2] });
+        float t, sx, sy, sz; int gid;
+        closest_hit<STAGED, COUNT>(v, org[3 * i], org[3 * i + 1], org[3 * i + 2], d.x, d.y, d.z, H, t, gid, sx, sy, sz, nt, nb);
+        type[i] = gid < 0 ? 0 : (gid < sc.n_surf ? 2 : 1);
+        index[i] = gid < 0 ? -1 : (gid < sc.n_surf ? gid : gid - sc.n_surf);
+        t_out[i] = t;
+    }
+    if (COUNT) {
+        nt = __reduce_add_sync(0xffffffffu, nt); nb = __reduce_add_sync(0xffffffffu, nb);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], (unsigned long long)nt); atomicAdd(&counters[1], (unsigned long long)nb); }
+    }
+}
+
+void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
+                        unsigned long long* counters, size_t smem, cudaStream_t s) {
+    int grid = (n + BLOCK - 1) / BLOCK; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    if (staged) {
+        if (counters) k_closest_hit<true, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+        else k_closest_hit<true, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+    } else {
+        if (counters) k_closest_hit<false, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+        else k_closest_hit<false, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ nearest volume
+__device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, float py, float pz, int cls) {
+    const float4* __restrict__ inner = rm.kd_inner; const float4* __restrict__ posn = rm.vol_posn;
+    return kd_find(
+        [&](uint32_t idx, float& split, uint32_t& l, uint32_t& r, int& dim) {
+            float4 n = __ldg(inner + idx); split = n.x; l = __float_as_uint(n.y); r = __float_as_uint(n.z); dim = __float_as_int(n.w);
+        },
+        [&](int vol, float& x, float& y, float& z, int& c) { float4 p = __ldg(posn + vol); x = p.x; y = p.y; z = p.z; c = __float_as_int(p.w); },
+        rm.root, rm.root_px, rm.root_py, rm.root_pz, px, py, pz, cls, rm.max_dist);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_find_closest(RadianceDev rm, const float* __restrict__ pos, const int* __restrict__ cls, int n, int* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = find_volume(rm, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], cls[i]);
+}
+void launch_find_closest(const RadianceDev& rm, const SceneDev&, const float* pos, const float* cls_as_float, int n, int* out, cudaStream_t s) {
+    k_find_closest<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(rm, pos, reinterpret_cast<const int*>(cls_as_float), n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ warp helpers
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// Warp-aggregated TD accumulation: lanes that update the same (volume, sector) are found with __match_any_sync, their
+// targets summed by shuffles, and the group leader issues one RED.ADD.F32 + one RED.ADD.U32.
+__device__ __forceinline__ void td_accumulate(const RadianceDev& rm, bool active, uint32_t key, float target) {
+    const unsigned full = 0xffffffffu;
+    unsigned lane = threadIdx.x & 31;
+    uint32_t k = active ? key : (0xffffffffu - lane);             // inactive lanes get unique dummy keys
+    unsigned peers = __match_any_sync(full, k);
+    if (__all_sync(full, peers == (1u << lane))) {                // common case after compaction: all keys distinct
+        if (active) { atomicAdd(rm.acc_sum + key, target); atomicAdd(rm.acc_cnt + key, 1u); }
+        return;
+    }
+    int n = __popc(peers), nmax = __reduce_max_sync(full, n);
+    unsigned m = peers; float total = 0.f;
+    for (int it = 0; it < nmax; ++it) {
+        int src = m ? (__ffs(m) - 1) : (int)lane;
+        float val = __shfl_sync(full, target, src);
+        if (m) total += val;
+        m &= m - 1;
+    }
+    if (active && lane == (unsigned)(__ffs(peers) - 1)) { atomicAdd(rm.acc_sum + key, total); atomicAdd(rm.acc_cnt + key, (unsigned)n); }
+}
+
+// ------------------------------------------------------------------------------------------------ wavefront kernels
+// One bounce of one path. PRIMARY: the path is generated here (raygen fused with the first cast).
+template <bool STAGED, bool SARSA, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameParams p, int bounce) {
+    SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
+    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
+    unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0;
+    const float H = (float)p.height;
+    const FrameDyn dyn = *p.dyn;
+    const int n_round = (n_in + 31) & ~31;                        // whole warps stay together for the collectives
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n_in;
+        float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, tr = 1, tg = 1, tb = 1, cur_brdf = 0;
+        uint32_t pixel = 0, sample = 0, volsec = 0;
+        if (valid) {
+            if (PRIMARY) {
+                pixel = (uint32_t)(i / p.spp); sample = dyn.sample_base + (uint32_t)(i % p.spp);
+                float u0, u1, u2, u3; draw4(p.seed, pixel, sample, 0u, PURPOSE_CAMERA, u0, u1, u2, u3);
+                f3 d = camera_dir((int)(pixel / (uint32_t)p.height), (int)(pixel % (uint32_t)p.height), u0, u1, p.width, p.height, dyn.rotated != 0, dyn.cy, dyn.sy, dyn.cx, dyn.sx);
+                ox = dyn.cam_x; oy = dyn.cam_y; oz = dyn.cam_z; dx = d.x; dy = d.y; dz = d.z;
+                if (i % p.spp == 0) atomicAdd(&p.accum[pixel].w, (float)p.spp);          // samples accumulated for this pixel
+            } else {
+                float4 a = qi.o[i], b = qi.d[i], c = qi.thr[i]; uint32_t m = qi.meta[i];
+                ox = a.x; oy = a.y; oz = a.z; pixel = __float_as_uint(a.w);
+                dx = b.x; dy = b.y; dz = b.z; cur_brdf = b.w;
+                tr = c.x; tg = c.y; tb = c.z; volsec = __float_as_uint(c.w); sample = m >> 8;
+            }
+        }
+        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce && valid) {
+            int slot = atomicAdd(p.capture_n, 1);
+            if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+        }
+        float t = T_MISS, sdx = 0, sdy = 0, sdz = 0; int gid = -1;
+        if (valid) closest_hit<STAGED, false>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        const bool surface = valid && gid >= 0 && gid < v.n_surf;
+        const bool light = valid && gid >= v.n_surf;
+        float hx = 0, hy = 0, hz = 0; float4 sN = make_float4(0, 1, 0, 0), sT = make_float4(1, 0, 0, 0);
+        int nv = 0;
+        if (surface) {
+            hx = RLPT_FMA(sdx, t, ox); hy = RLPT_FMA(sdy, t, oy); hz = RLPT_FMA(sdz, t, oz);   // position = start + t*dir (ray.cu:65)
+            sN = v.shade(4 * gid); sT = v.shade(4 * gid + 1);
+            if (SARSA) nv = find_volume(p.rm, hx, hy, hz, __float_as_int(sT.w));
+        }
+        if (SARSA && !PRIMARY) {
+            // RadianceMap::temporal_difference_update_radiance_volume_sector (radiance_map.cu:111-146): target by hit type
+            float target = 0.f;
+            if (surface) target = __ldg(p.rm.irradiance + nv) * ((2.f * PI_F) / 144.f) * cur_brdf;   // get_irradiance_estimate (radiance_volume.cu:305-307)
+            else if (light) target = cur_brdf * v.shade(4 * gid).w;
+            else target = cur_brdf * p.env;
+            td_accumulate(p.rm, valid && dyn.learn, (volsec >> 8) * (uint32_t)CELLS + (volsec & 0xffu), target);
+        }
+        bool alive = false;
+        if (valid && !surface) {
+            // NOTHING: throughput * ENVIRONMENT_LIGHT; AREA_LIGHT: throughput * diffuse_p (default_path_tracing.cu:52-63)
+            float lr = p.env, lg = p.env, lb = p.env;
+            if (light) { float4 e = v.shade(4 * gid + 3); lr = e.x; lg = e.y; lb = e.z; }
+            lr *= tr; lg *= tg; lb *= tb;
+            if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + pixel, make_float4(lr, lg, lb, 0.f));
+            st_len += (unsigned)bounce + 1u; st_term++;
+            if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;                                         // THROUGHPUT_THRESHOLD
+        } else if (surface) {
+            if (bounce + 1 >= p.max_bounces) {            // the reference's loop ends here and returns vec3(0), path_length = MAX_RAY_BOUNCES
+                st_len += (unsigned)p.max_bounces; st_term++; st_zero++;
+            } else {
+                float4 sB = v.shade(4 * gid + 2), sC = v.shade(4 * gid + 3);
+                f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
+                float u0, u1, u2, u3; draw4(p.seed, pixel, sample, (uint32_t)bounce, PURPOSE_BOUNCE, u0, u1, u2, u3);
+                f3 nd; float scale;
+                if (SARSA) {
+                    // importance_sample_ray_direction -> sample_direction_from_radiance_distribution (radiance_volume.cu:192-244)
+                    const float* __restrict__ row = p.rm.cdf + (size_t)nv * CELLS;
+                    float pdf; int sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
+                    nd = grid_to_direction((float)(sector / GRID) + u1, (float)(sector % GRID) + u2, T, N, B);
+                    float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;                       // reinforcement_path_tracing.cu:107
+                    scale = cos_theta / pdf;
+                    volsec = ((uint32_t)nv << 8) | (uint32_t)sector;
+                    cur_brdf = sN.w;                                                              // material.luminance / pi (:109)
+                } else {
+                    nd = uniform_hemisphere(u0, u1, T, N, B);                                     // cos_theta = u0, pdf = RHO
+                    scale = u0 / RHO;
+                }
+                tr *= sC.x * scale; tg *= sC.y * scale; tb *= sC.z * scale;
+                ox = RLPT_FMA(RAY_EPS, nd.x, hx); oy = RLPT_FMA(RAY_EPS, nd.y, hy); oz = RLPT_FMA(RAY_EPS, nd.z, hz);
+                f3 nn = normalize_ref(nd); dx = nn.x; dy = nn.y; dz = nn.z;
+                alive = true;
+            }
+        }
+        // wavefront compaction: survivors are packed densely into the next bounce's queue
+        unsigned bal = __ballot_sync(full, alive);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.counts + bounce + 1, __popc(bal));
+            base = __shfl_sync(full, base, 0);
+            if (alive) {
+                int slot = base + __popc(bal & lanemask_lt());
+                qo.o[slot] = make_float4(ox, oy, oz, __uint_as_float(pixel));
+                qo.d[slot] = make_float4(dx, dy, dz, cur_brdf);
+                qo.thr[slot] = make_float4(tr, tg, tb, __uint_as_float(volsec));
+                qo.meta[slot] = (sample << 8) | (uint32_t)(bounce + 1);
+            }
+        }
+    }
+    st_len = __reduce_add_sync(full, st_len); st_zero = __reduce_add_sync(full, st_zero); st_term = __reduce_add_sync(full, st_term);
+    if (lane == 0 && st_term) {
+        atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term);
+    }
+}
+
+template <bool SARSA, bool PRIMARY>
+static void launch_bounce_t(const FrameParams& p, int bounce, int grid, size_t smem, cudaStream_t s) {
+    const SceneDev& sc = p.scene;
+    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    if (staged) k_bounce<true, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, bounce);
+    else k_bounce<false, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, bounce);
+}
+void launch_primary(const FrameParams& p, int method, int grid, size_t smem, cudaStream_t s) {
+    if (method == 1) launch_bounce_t<true, true>(p, 0, grid, smem, s); else launch_bounce_t<false, true>(p, 0, grid, smem, s);
+}
+void launch_bounce(const FrameParams& p, int method, int bounce, int grid, size_t smem, cudaStream_t s) {
+    if (method == 1) launch_bounce_t<true, false>(p, bounce, grid, smem, s); else launch_bounce_t<false, false>(p, bounce, grid, smem, s);
+}
+
+int kernels_set_smem_limit(size_t bytes) {
+    cudaError_t e = cudaSuccess;
+#define RLPT_SET(k) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+    RLPT_SET((k_bounce<true, true, true>)); RLPT_SET((k_bounce<true, true, false>)); RLPT_SET((k_bounce<true, false, true>)); RLPT_SET((k_bounce<true, false, false>));
+    RLPT_SET((k_bounce<false, true, true>)); RLPT_SET((k_bounce<false, true, false>)); RLPT_SET((k_bounce<false, false, true>)); RLPT_SET((k_bounce<false, false, false>));
+    RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));
+#undef RLPT_SET
+    return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------ Q merge + CDF rebuild
+// One warp per radiance volume. Consumes the (all-reduced) accumulators: running-mean merge
+//   Q <- (visits*Q + sum_targets) / (visits + count), clamp at RADIANCE_THRESHOLD, visits += count
+// (the closed form of the reference's per-visit alpha = 1/(1+visits) update, radiance_volume.cu:283-301), then
+// update_radiance_distribution (radiance_volume.cu:149-188) as a warp prefix sum, and the irradiance estimate
+// sum_k Q_k cos_k luminance/pi (radiance_volume.cu:57-68) recomputed from cell centres.
+__global__ void __launch_bounds__(BLOCK) k_merge_cdf(RadianceDev rm, const float* __restrict__ surf_lum_over_pi, float threshold, int rebuild_only) {
+    const unsigned full = 0xffffffffu;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int vol = warp; vol < rm.n_vol; vol += nwarps) {
+        size_t base = (size_t)vol * CELLS;
+        float temp[5]; float qv[5]; float tsum = 0.f, irr = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            int k = c * 32 + lane; temp[c] = 0.f; qv[c] = 0.f;
+            if (k < CELLS) {
+                float q = rm.q[base + k];
+                if (!rebuild_only) {
+                    uint32_t cnt = rm.acc_cnt[base + k];
+                    if (cnt) {
+                        float vs = (float)rm.visits[base + k];
+                        q = (vs * q + rm.acc_sum[base + k]) / (vs + (float)cnt);
+                        q = q > threshold ? q : threshold;
+                        rm.q[base + k] = q; rm.visits[base + k] += cnt;
+                        rm.acc_cnt[base + k] = 0u; rm.acc_sum[base + k] = 0.f;
+                    }
+                }
+                float w = q * c_cell_cos[k];
+                irr += w;
+                temp[c] = w > 0.f ? w : 0.f;                 // DISTRIBUTION_THRESHOLD = 0
+                tsum += temp[c];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { tsum += __shfl_xor_sync(full, tsum, o); irr += __shfl_xor_sync(full, irr, o); }
+        float total = 0.0000000001f + tsum;
+        float carry = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            float x = temp[c] / total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { float y = __shfl_up_sync(full, x, o); if (lane >= o) x += y; }
+            x += carry;
+            int k = c * 32 + lane;
+            if (k < CELLS) rm.cdf[base + k] = x;
+            carry = __shfl_sync(full, x, 31);
+        }
+        if (lane == 0) rm.irradiance[vol] = irr * __ldg(surf_lum_over_pi + __ldg(rm.vol_surface + vol));
+    }
+}
+void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float threshold, int rebuild_only, cudaStream_t s) {
+    int warps_per_block = BLOCK / 32;
+    int grid = (rm.n_vol + warps_per_block - 1) / warps_per_block; if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    k_merge_cdf<<<grid, BLOCK, 0, s>>>(rm, surf_lum_over_pi, threshold, rebuild_only);
+}
+
+// ------------------------------------------------------------------------------------------------ frame buffer
+__global__ void k_frame_mean(const float4* __restrict__ accum, float* __restrict__ rgb, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 a = accum[i]; float inv = a.w > 0.f ? 1.f / a.w : 0.f; rgb[3 * i] = a.x * inv; rgb[3 * i + 1] = a.y * inv; rgb[3 * i + 2] = a.z * inv; }
+}
+void launch_frame_mean(const float4* accum, float* rgb, int n, cudaStream_t s) { k_frame_mean<<<(n + 255) / 256, 256, 0, s>>>(accum, rgb, n); }
+
+// SDLScreen::PutPixelSDL (G/sdl/sdl_screen.cpp:96-108): (128<<24) + (r<<16) + (g<<8) + b with r = uint32(clamp(255*c, 0, 255)),
+// written at buffer[y*width + x] from pixel x*height + y (G/main.cu:235-239).
+__global__ void k_pack_argb(const float4* __restrict__ accum, uint32_t* __restrict__ argb, int width, int height) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= width * height) return;
+    int y = o / width, x = o % width;
+    float4 a = accum[x * height + y]; float inv = a.w > 0.f ? 1.f / a.w : 0.f;
+    uint32_t r = (uint32_t)fminf(fmaxf(255.f * (a.x * inv), 0.f), 255.f), g = (uint32_t)fminf(fmaxf(255.f * (a.y * inv), 0.f), 255.f), b = (uint32_t)fminf(fmaxf(255.f * (a.z * inv), 0.f), 255.f);
+    argb[o] = (128u << 24) + (r << 16) + (g << 8) + b;
+}
+void launch_pack_argb(const float4* accum, uint32_t* argb, int width, int height, cudaStream_t s) {
+    k_pack_argb<<<(width * height + 255) / 256, 256, 0, s>>>(accum, argb, width, height);
+}
+
+// ------------------------------------------------------------------------------------------------ FP32 peak probe
+// 8 independent FMA chains per thread, 2 flop per FMA: the FP32-pipe roofline denominator measured on this GPU at the
+// clocks it actually holds (MEASURED_PEAKS.json has no FP32 figure).
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+void launch_fp32_peak(float* out, int iters, int grid, cudaStream_t s) { k_fp32_peak<<<grid, 256, 0, s>>>(out, iters); }
+
+}  // namespace rlpt

@@ -1,0 +1,273 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the oracle, the golden vectors and -- when the prebuilt
+oracle/_ref/libref_cuda.so travelled to the box -- the reference's own kernels.
+
+Bars (BASELINE.json north_star): closest-hit (type, index) bit-exact and t bit-equal; nearest-volume indices bit-exact;
+CDFs within 1e-5 relative; rendered radiance against the oracle tracing the same Philox paths within 2e-3 relative
+per pixel for >= 99.5% of pixels (libm vs CUDA sin/cos differ by an ulp, which moves a few paths across an edge).
+"""
+import numpy as np
+import pytest
+
+from conftest import bits, load_scene
+
+pytestmark = pytest.mark.gpu
+SCENES = ["cornell", "door_room", "archway", "complex_light_room", "simple_room", "Medieval_House"]
+
+
+def rays_for(name, golden_hits, n_extra, oracle_scene_normals=None):
+    g = golden_hits[name]
+    return g["org"], g["dir"]
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("traversal", [1, 2])
+def test_closest_hit_bit_exact_vs_oracle(ctx, oracle, golden_scenes, golden_hits, name, traversal):
+    s = golden_scenes[name]
+    if traversal == 2 and len(s["sv"]) + len(s["lv"]) > 1500:
+        pytest.skip("brute-force traversal needs the whole scene in shared memory")
+    load_scene(ctx, s); load_scene(oracle, s)
+    ctx.configure(height=512, width=512)
+    org, dir = golden_hits[name]["org"], golden_hits[name]["dir"]
+    ty, ix, t = ctx.closest_hit(org, dir, traversal=traversal)
+    oty, oix, ot, _ = oracle.closest_hit(org, dir, 512, 1)       # fma_mode 1 = the sm_100a rounding sequence
+    assert np.array_equal(ty, oty)
+    assert np.array_equal(ix, oix)
+    assert np.array_equal(bits(t), bits(ot))
+    # against the reference's host arithmetic (golden): identical except where an FMA moves a ray across an edge
+    g = golden_hits[name]
+    assert np.mean((ty != g["type"]) | (ix != g["index"])) < 2e-3
+
+
+@pytest.mark.parametrize("name", ["cornell", "archway", "Medieval_House"])
+def test_closest_hit_bit_exact_vs_reference_kernels(ctx, ref_cuda, golden_scenes, golden_hits, name):
+    """the reference's own Ray::closest_intersection compiled for sm_100a, same rays"""
+    s = golden_scenes[name]
+    load_scene(ctx, s)
+    ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"])
+    ctx.configure(height=ref_cuda.height, width=ref_cuda.width)
+    rs = np.random.RandomState(5)
+    g = golden_hits[name]
+    reps = max(1, (1 << 20) // len(g["org"])) if name != "Medieval_House" else 8
+    org = np.tile(g["org"], (reps, 1)); dir = np.tile(g["dir"], (reps, 1)) + rs.randn(len(org), 3).astype(np.float32) * np.float32(0.05)
+    rty, rix, rt, _ = ref_cuda.closest_hit(org, dir)
+    for traversal in (1, 2):
+        if traversal == 2 and len(s["sv"]) > 1500:
+            continue
+        ty, ix, t = ctx.closest_hit(org, dir, traversal=traversal)
+        assert np.array_equal(ty, rty), (name, traversal, int((ty != rty).sum()))
+        assert np.array_equal(ix, rix), (name, traversal, int((ix != rix).sum()))
+        assert np.array_equal(bits(t), bits(rt)), (name, traversal, int((bits(t) != bits(rt)).sum()))
+
+
+def test_closest_hit_edge_cases(ctx, oracle, golden_scenes):
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    # no rays; a single ray; rays that start on a surface; a zero direction (NaN after normalisation -> NOTHING)
+    ty, ix, t = ctx.closest_hit(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert len(ty) == 0
+    org = np.array([[0, 0, -3], [0, 0, -3], [0.5, 0.99999, 0.2], [0, 0, 0]], np.float32)
+    dir = np.array([[0, 0, 1], [0, 0, -1], [0, -1, 0], [0, 0, 0]], np.float32)
+    for trav in (1, 2):
+        ty, ix, t = ctx.closest_hit(org, dir, traversal=trav)
+        oty, oix, ot, _ = oracle.closest_hit(org, dir, 512, 1)
+        assert np.array_equal(ty, oty) and np.array_equal(ix, oix) and np.array_equal(bits(t), bits(ot))
+        assert ty[1] == 0 and ty[3] == 0 and ix[3] == -1 and t[3] == np.float32(999999.0)
+
+
+def test_bvh_is_built_on_device_and_encloses_scene(ctx, golden_scenes):
+    s = golden_scenes["Medieval_House"]
+    load_scene(ctx, s)
+    info = ctx.scene_info()
+    n = info["n_surfaces"] + info["n_lights"]
+    assert info["bvh_nodes"] == n - 1 and 2 <= info["bvh_depth"] <= 30
+    nodes = ctx.bvh_download()
+    links = nodes[:, 12:14].view(np.int32)
+    leaves = ~links[links < 0]
+    assert sorted(leaves.tolist()) == list(range(n))           # every primitive is referenced exactly once
+    inner = links[links >= 0]
+    assert sorted(inner.tolist()) == list(range(1, n - 1))      # every node but the root has exactly one parent
+    v = np.concatenate([s["sv"], s["lv"]]).reshape(-1, 3, 3)
+    lo, hi = v.min(1), v.max(1)
+    for side, (a, b) in enumerate([((0, 1, 2), (3, 4, 5)), ((6, 7, 8), (9, 10, 11))]):
+        is_leaf = links[:, side] < 0
+        gid = ~links[is_leaf, side]
+        assert np.all(nodes[is_leaf][:, list(a)] <= lo[gid]) and np.all(nodes[is_leaf][:, list(b)] >= hi[gid])
+
+
+def test_nearest_volume_bit_exact(ctx, oracle, golden_scenes, golden_rmap):
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    nv = ctx.radiance_map_build()
+    assert nv == int(golden_rmap["n_volumes"]) == oracle.rmap_build()
+    d = ctx.radiance_map_download()
+    assert np.array_equal(bits(d["pos"]), bits(golden_rmap["pos"])) and np.array_equal(d["surface"], golden_rmap["surface"])
+    tree = ctx.radiance_map_tree()
+    assert np.array_equal(tree["left"], golden_rmap["tree_left"]) and np.array_equal(bits(tree["data"]), bits(golden_rmap["tree_data"]))
+    found = ctx.find_closest(golden_rmap["query_pos"], golden_rmap["query_nrm"])
+    ofound = oracle.find_closest(golden_rmap["query_pos"], golden_rmap["query_nrm"], 1)
+    assert np.array_equal(found, ofound)
+    assert np.mean(found != golden_rmap["query_found"]) < 1e-3    # reference host arithmetic (no FMA in the distance)
+    # a large batch: points on and near surfaces, plus points far from everything (falls back to volume 0 semantics)
+    rs = np.random.RandomState(3)
+    idx = rs.randint(0, nv, 1 << 18)
+    pos = d["pos"][idx] + rs.randn(len(idx), 3).astype(np.float32) * np.float32(0.03)
+    pos[::97] = rs.uniform(-3, 3, (len(pos[::97]), 3))
+    nrm = d["nrm"][idx]
+    assert np.array_equal(ctx.find_closest(pos, nrm), oracle.find_closest(pos, nrm, 1))
+
+
+def test_nearest_volume_vs_reference_kernels(ctx, ref_cuda, golden_scenes, golden_rmap):
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); ctx.radiance_map_build()
+    ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"]); ref_cuda.rmap_build()
+    rs = np.random.RandomState(11)
+    d = ctx.radiance_map_download()
+    idx = rs.randint(0, ctx.n_vol, 1 << 18)
+    pos = d["pos"][idx] + rs.randn(len(idx), 3).astype(np.float32) * np.float32(0.03)
+    nrm = d["nrm"][idx]
+    assert np.array_equal(ctx.find_closest(pos, nrm), ref_cuda.find_closest(pos, nrm, on_device=True))
+
+
+def test_cdf_within_1e5(ctx, oracle, golden_scenes, golden_rmap):
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    nv = ctx.radiance_map_build(); oracle.rmap_build()
+    sub = golden_rmap["cdf_volumes"]
+    rs = np.random.RandomState(0)
+    cases = {"constant": np.full((nv, 144), np.float32(100.0 / 144.0), np.float32), "lognormal": np.exp(rs.randn(nv, 144) * 2).astype(np.float32)}
+    cases["lognormal"][sub] = golden_rmap["q_lognormal_rows"]
+    cases["one_hot"] = np.full((nv, 144), np.float32(0.8 / 144.0), np.float32); cases["one_hot"][sub] = golden_rmap["q_one_hot_rows"]
+    for name, q in cases.items():
+        ctx.radiance_map_set_q(q); ctx.radiance_map_update_distributions()
+        oracle.rmap_set_q(q); oracle.rmap_update_distributions()
+        cdf = ctx.radiance_map_download()["cdf"]
+        ocdf = oracle.rmap_state()[1]
+        rel = np.abs(cdf - ocdf) / np.maximum(np.abs(ocdf), 1e-30)
+        assert rel.max() <= 1e-5, (name, rel.max())
+        gold = golden_rmap["cdf_" + name]
+        assert (np.abs(cdf[sub] - gold) / np.maximum(np.abs(gold), 1e-30)).max() <= 1e-5
+        assert np.all(np.diff(cdf, axis=1) >= 0) and np.all(np.abs(cdf[:, -1] - 1) < 1e-5)
+
+
+def test_cdf_vs_reference_kernels(ctx, ref_cuda, golden_scenes):
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); nv = ctx.radiance_map_build()
+    ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"]); assert ref_cuda.rmap_build() == nv
+    q = np.exp(np.random.RandomState(1984).randn(nv, 144) * 2).astype(np.float32)
+    ctx.radiance_map_set_q(q); ctx.radiance_map_update_distributions()
+    ref_cuda.rmap_set_q(q); ref_cuda.rmap_update_distributions()
+    cdf = ctx.radiance_map_download()["cdf"]; rcdf = ref_cuda.rmap_state()[1]
+    assert (np.abs(cdf - rcdf) / np.maximum(np.abs(rcdf), 1e-30)).max() <= 1e-5
+
+
+def _render_pair(ctx, oracle, s, method, w, h, spp, frames, bounces, cam):
+    load_scene(ctx, s); load_scene(oracle, s)
+    ctx.configure(width=w, height=h, spp=spp, max_bounces=bounces)
+    ctx.camera_set(cam)
+    if method == 1:
+        ctx.radiance_map_build(); oracle.rmap_build(); oracle.rmap_update_distributions(); oracle.rmap_merge_frame()
+    acc = np.zeros((w * h, 3), np.float64)
+    ost = dict(total_path_length=0.0, zero_contribution=0.0, paths=0.0)
+    for f in range(frames):
+        if method == 0:
+            ctx.render_default(1)
+        else:
+            ctx.render_sarsa(1)
+        o, st = oracle.render_frame(method, w, h, spp, sample0=f * spp, max_bounces=bounces, cam=cam, fma_mode=1, td_mode=1)
+        if method == 1:
+            oracle.rmap_merge_frame(); oracle.rmap_update_distributions()
+        acc += o
+        for k in ost:
+            ost[k] += st[k]
+    return ctx.frame_download(), (acc / (spp * frames)).astype(np.float32), ctx.stats(), ost
+
+
+def _assert_images_close(img, oimg, frac=0.995, tol=2e-3):
+    err = np.abs(img - oimg).max(1) / np.maximum(np.abs(oimg).max(1), 1e-2)
+    assert np.mean(err <= tol) >= frac, (float(np.mean(err <= tol)), float(err.max()))
+    assert abs(float(img.mean()) - float(oimg.mean())) <= 2e-3 * max(float(oimg.mean()), 1e-6)
+
+
+def test_default_render_matches_oracle_same_paths(ctx, oracle, golden_scenes):
+    img, oimg, st, ost = _render_pair(ctx, oracle, golden_scenes["cornell"], 0, 64, 64, 8, 2, 80, (0, 0, -3))
+    _assert_images_close(img, oimg)
+    assert st["paths"] == ost["paths"] == 64 * 64 * 16
+    assert abs(st["path_length_sum"] - ost["total_path_length"]) <= 2e-3 * ost["total_path_length"]
+    assert abs(st["zero_contribution_paths"] - ost["zero_contribution"]) <= 2e-3 * ost["paths"]
+
+
+def test_sarsa_first_frame_accumulators_match_oracle(ctx, oracle, golden_scenes):
+    """one training iteration from the initial table: same paths => same (volume, sector) visit counts"""
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    w = h = 48; spp = 4
+    ctx.configure(width=w, height=h, spp=spp, max_bounces=80); ctx.camera_set((0, 0, -3))
+    ctx.radiance_map_build(); oracle.rmap_build(); oracle.rmap_update_distributions(); oracle.rmap_merge_frame()
+    ctx.sarsa_trace(); ctx.sync()
+    gsum, gcnt = ctx.radiance_map_delta()
+    oracle.render_frame(1, w, h, spp, sample0=0, max_bounces=80, cam=(0, 0, -3), fma_mode=1, td_mode=1)
+    osum, ocnt = oracle.rmap_acc()
+    assert int(gcnt.sum()) > 0
+    mism = int(np.abs(gcnt.astype(np.int64) - ocnt.astype(np.int64)).sum())
+    assert mism <= 0.01 * int(ocnt.sum()), (mism, int(ocnt.sum()))
+    both = (gcnt == ocnt) & (ocnt > 0)
+    assert np.allclose(gsum[both], osum[both], rtol=2e-3, atol=1e-6)
+    ctx.sarsa_merge(); ctx.sync()
+    oracle.rmap_merge_frame(); oracle.rmap_update_distributions()
+    d = ctx.radiance_map_download(); oq, ocdf, ovis, oirr = oracle.rmap_state()
+    same = np.all(gcnt == ocnt, axis=1)
+    assert np.array_equal(d["visits"][same], ovis[same])
+    assert np.allclose(d["q"][same], oq[same], rtol=2e-3, atol=1e-6)
+    assert np.allclose(d["irradiance"][same], oirr[same], rtol=2e-3)
+
+
+def test_sarsa_render_matches_oracle_same_paths(ctx, oracle, golden_scenes):
+    img, oimg, st, ost = _render_pair(ctx, oracle, golden_scenes["cornell"], 1, 48, 48, 4, 3, 80, (0, 0, -3))
+    _assert_images_close(img, oimg, frac=0.97, tol=5e-3)
+    assert st["paths"] == ost["paths"]
+    assert abs(st["path_length_sum"] - ost["total_path_length"]) <= 1e-2 * ost["total_path_length"]
+
+
+def test_sarsa_learns_and_stays_finite(ctx, golden_scenes):
+    """size-independent properties at the BASELINE resolution: visits add up to the TD updates made, Q stays >= the clamp,
+    CDFs stay monotone and end at 1, zero-contribution paths fall as the table is learned (Radiance_Map_Data/sarsa_cornell.txt)."""
+    load_scene(ctx, golden_scenes["cornell"])
+    ctx.configure(width=512, height=512, spp=4, max_bounces=80); ctx.camera_set((0, 0, -3))
+    nv = ctx.radiance_map_build()
+    zero = []
+    for f in range(6):
+        ctx.stats_reset(); ctx.render_sarsa(1); st = ctx.stats(); zero.append(st["zero_contribution_paths"] / st["paths"])
+        assert st["paths"] == 512 * 512 * 4
+    d = ctx.radiance_map_download()
+    assert np.isfinite(d["q"]).all() and d["q"].min() >= np.float32(0.8 / 144) * (1 - 1e-6)
+    assert np.all(np.diff(d["cdf"], axis=1) >= 0) and np.all(np.abs(d["cdf"][:, -1] - 1) < 1e-5)
+    assert zero[-1] < zero[0]
+    img = ctx.frame_download()
+    assert np.isfinite(img).all() and img.mean() > 0.05
+
+
+def test_frame_argb_and_bmp(ctx, golden_scenes, tmp_path):
+    from checkers import to_rgb8
+    load_scene(ctx, golden_scenes["cornell"])
+    ctx.configure(width=64, height=32, spp=4, max_bounces=8)
+    ctx.render_default(1)
+    rgb = ctx.frame_download().reshape(64, 32, 3).transpose(1, 0, 2)       # (h, w, 3)
+    argb = ctx.frame_download_argb()
+    exp = to_rgb8(rgb).astype(np.uint32)
+    assert np.array_equal(argb, (128 << 24) + (exp[..., 0] << 16) + (exp[..., 1] << 8) + exp[..., 2])
+    p = str(tmp_path / "render.bmp"); ctx.frame_save_bmp(p)
+    raw = open(p, "rb").read()
+    assert raw[:2] == b"BM" and int.from_bytes(raw[10:14], "little") == 122 and int.from_bytes(raw[14:18], "little") == 108
+    assert int.from_bytes(raw[28:30], "little") == 32 and int.from_bytes(raw[30:34], "little") == 3 and len(raw) == 122 + 64 * 32 * 4
+    px = np.frombuffer(raw[122:], np.uint32).reshape(32, 64)[::-1]
+    assert np.array_equal(px, argb)
+
+
+def test_error_behaviour(ctx):
+    import rlpt
+    with pytest.raises(rlpt.RlptError):
+        ctx.render_default(1)                       # no scene yet
+    with pytest.raises(rlpt.RlptError):
+        ctx.configure(max_bounces=0)
+    with pytest.raises(rlpt.RlptError):
+        ctx.scene_upload(np.zeros((0, 9)), np.zeros((0, 3)), np.zeros((0, 9)), np.zeros((0, 3)))
