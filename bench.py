@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- Mpaths/s of the reinforcement-learned path tracing hot path (BASELINE.json metric).
+
+One *step* = one frame of the reference's method-1 loop (G/main.cu:301-364): trace `spp` samples per pixel with
+Expected-SARSA importance sampling and TD accumulation, all-reduce the Q accumulators (N > 1), merge into Q, rebuild the
+CDFs. Default workload = BASELINE.json configs[1]: Cornell box 512x512, 12x12 radiance volumes, 32 spp per frame
+(32 timed frames = 1024 spp). One *path* = one camera sample of one pixel traced to termination.
+
+  value     whole-job Mpaths/s, device-timed (CUDA events on the library's stream, max over ranks), scene / Q-table /
+            path queues already resident in HBM
+  e2e       the same frames driven one by one through the C ABI the way the reference's frame loop runs: camera upload,
+            render, frame-buffer download to pinned host memory and the statistics read-back, every step (G/main.cu:307-349)
+  roofline  dominant kernel = the per-bounce tracing kernel (k_bounce): executed ray-triangle / ray-box tests (counted in
+            the kernel) x 72 / 18 flop / its device time, against the FP32 FMA rate measured on this GPU
+  cpu_baseline / --impl reference   the reference's own sources compiled for the host (oracle/_ref/libref_host_spp2.so:
+            G/path_tracing/reinforcement_path_tracing.cu etc. behind oracle/host_shim, OpenMP over pixels), same scene and
+            method, a bounded sample (2 spp per frame: resolution and spp are compile-time constants in the reference)
+
+N > 1 (torchrun): sample-partitioned, weak scaling -- every rank traces `spp` samples of every pixel per frame
+(global frame = N*spp samples, disjoint Philox sample indices), Q accumulators are all-reduced every frame (NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "reinforcement-light-rays-pathtracer_b200"))
+
+F_TRI, F_AABB = 72.0, 18.0          # flop per ray-triangle solve (reference form) / per ray-AABB slab test
+
+WORKLOADS = {
+    # name: (scene in tests/golden/scenes.npz, method, camera, env_light)
+    "cornell_sarsa": ("cornell", 1, (0.0, 0.0, -3.0), 0.0),
+    "cornell_default": ("cornell", 0, (0.0, 0.0, -3.0), 0.0),
+    "door_room_sarsa": ("door_room", 1, (0.0, 0.5, -0.9), 0.0),
+    "archway_sarsa": ("archway", 1, (-1.0, 0.2, -0.99), 0.0),
+}
+
+
+def load_scene(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes.npz"))
+    return {k.split("/")[1]: z[k] for k in z.files if k.startswith(name + "/")}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows]
+        if not rows:
+            return None
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons, "samples": len(rows)}
+        except (ValueError, IndexError):
+            return None
+
+
+class c_stdout_to_stderr:
+    """The reference printf()s progress text; keep stdout to the one JSON line by pointing fd 1 at stderr meanwhile."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_reference_run(frames, warmup, want_seconds=None):
+    """The reference's SARSA frame loop on the host cores. Returns (Mpaths/s, kind, cores, sample, ms_per_step)."""
+    with c_stdout_to_stderr():
+        return _cpu_reference_run(frames, warmup, want_seconds)
+
+
+def _cpu_reference_run(frames, warmup, want_seconds=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from checkers import Oracle, Reference
+    if Reference.available("host", "_spp2"):
+        R = Reference("host", "_spp2")
+        R.scene_cornell(); R.camera(0.0, 0.0, -3.0)
+        R.rmap_build()
+        for _ in range(warmup):
+            R.render_sarsa(1, 0)
+        t0 = time.perf_counter(); done = 0
+        for _ in range(frames):
+            R.render_sarsa(1, 0); done += 1
+            if want_seconds and time.perf_counter() - t0 > want_seconds:
+                break
+        dt = time.perf_counter() - t0
+        paths = done * R.width * R.height * R.spp
+        sample = "%d frames x %d spp, Cornell %dx%d, Expected SARSA, after %d warm-up frames (%.2f M paths); unmodified reference sources built for the host with g++ -O2 -fopenmp" % (
+            done, R.spp, R.width, R.height, warmup, paths / 1e6)
+        return paths / dt / 1e6, "reference", R.threads(), sample, dt / done * 1e3
+    orc = Oracle()
+    s = load_scene("cornell")
+    orc.scene_set(s["sv"], s["srgb"], s["lv"], s["lrgb"]); orc.rmap_build(); orc.rmap_update_distributions(); orc.rmap_merge_frame()
+    w = h = 512; spp = 2
+    def frame(i):
+        orc.render_frame(1, w, h, spp, sample0=i * spp, fma_mode=1, td_mode=1); orc.rmap_merge_frame(); orc.rmap_update_distributions()
+    for i in range(warmup):
+        frame(i)
+    t0 = time.perf_counter(); done = 0
+    for i in range(frames):
+        frame(warmup + i); done += 1
+        if want_seconds and time.perf_counter() - t0 > want_seconds:
+            break
+    dt = time.perf_counter() - t0
+    paths = done * w * h * spp
+    return paths / dt / 1e6, "port", orc.threads(), "%d frames x %d spp, Cornell 512x512, Expected SARSA (oracle port, OpenMP)" % (done, spp), dt / done * 1e3
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    v, kind, cores, sample, ms = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "built-in Cornell box scene (no dataset)",
+            "config": {"workload": "cornell_sarsa", "scene": "Cornell box (36 surfaces + 2 area lights)", "width": 512, "height": 512, "spp_per_frame": 2,
+                       "radiance_volumes": 24526, "grid": "12x12", "max_bounces": 80, "note": "CPU arm: bounded sample, 2 spp per frame"},
+            "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell_sarsa", choices=sorted(WORKLOADS))
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--spp", type=int, default=32)
+    ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+    if args.warmup < 3:
+        args.warmup = 3                                    # timing rule: at least 3 warm-up steps
+    import torch
+    import torch.distributed as dist
+    import rlpt
+    from rlpt.dist import torch_allreduce_hook
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene_name, method, cam, env = WORKLOADS[args.workload]
+    s = load_scene(scene_name)
+    ctx = rlpt.Context(local, width=args.width, height=args.height, spp=args.spp, max_bounces=80, env_light=env, traversal=args.traversal,
+                       rank=rank, world_size=world)
+    ctx.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"])
+    ctx.camera_set(cam)
+    nv = ctx.radiance_map_build() if method == 1 else 0
+    if world > 1:
+        ctx.set_allreduce(torch_allreduce_hook(local))
+    fp32_peak = ctx.measure_fp32_peak()
+    render = ctx.render_sarsa if method == 1 else ctx.render_default
+
+    def barrier():
+        ctx.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    render(args.warmup)
+    # ---- timed region: K frames enqueued back to back, device-timed inside the library (events on its stream)
+    barrier(); ctx.stats_reset(); ctx.sync()
+    clocks = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    render(args.steps)
+    barrier()
+    t1 = time.perf_counter()
+    st = ctx.stats()
+    clk = clocks.stop(t0, t1) if clocks else None
+    dev_s = torch.tensor([st["device_seconds"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dev_s, op=dist.ReduceOp.MAX)
+    dev_s = float(dev_s.item())
+    paths_rank = st["paths"]
+    paths_total = paths_rank * world
+    value = paths_total / dev_s / 1e6
+
+    # ---- e2e: the reference's per-frame protocol through the C ABI with host buffers
+    pinned = torch.empty((args.width * args.height, 3), dtype=torch.float32, pin_memory=True)
+    frame_np = pinned.numpy()
+    barrier(); ctx.stats_reset()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.camera_set(cam)                                 # cudaMemcpy(device_camera, &camera) every frame (G/main.cu:307)
+        render(1)
+        ctx.frame_download(frame_np)                        # cudaMemcpy(host_buffer, device_buffer) (G/main.cu:349)
+        est = ctx.stats()                                   # path lengths / zero-contribution read-back (G/main.cu:322-339)
+    barrier()
+    e1 = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e1, op=dist.ReduceOp.MAX)
+    e2e_value = est["paths"] * world / float(e1.item()) / 1e6
+    h2d = 48                                                # FrameDyn: camera position + rotation + sample base, staged by the render call
+    d2h = args.width * args.height * 3 * 4 + 8 * 8          # frame buffer + statistics block
+
+    if rank == 0:
+        flops = st["triangle_tests"] * F_TRI + st["box_tests"] * F_AABB
+        trace_s = max(st["trace_seconds"], 1e-12)
+        bounce_launches = st["kernel_launches"] - (st["frames"] if method == 1 else 0)
+        achieved = flops / trace_s / 1e12
+        line = {
+            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "built-in Cornell box scene / bundled .obj geometry (no dataset); radiance volumes start untrained, trained by the %d warm-up frames" % args.warmup,
+            "config": {"workload": args.workload, "scene": "%s (%d surfaces + %d area lights)" % (scene_name, len(s["sv"]), len(s["lv"])),
+                       "method": "Expected SARSA radiance volumes, train + render" if method == 1 else "default path tracer",
+                       "width": args.width, "height": args.height, "spp_per_frame": args.spp, "frames": args.steps, "spp_total_per_gpu": args.spp * args.steps,
+                       "radiance_volumes": nv, "grid": "12x12", "max_bounces": 80, "partition": "samples (rank r traces samples r*spp..(r+1)*spp-1 of each global frame)",
+                       "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 52 * 2 / 1e9, nv * 144 * 20 / 1e6)},
+            "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "mray_casts_per_s": st["ray_casts"] * world / dev_s / 1e6,
+            "zero_contribution_fraction": st["zero_contribution_paths"] / max(st["paths"], 1),
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timed": "wall clock around K x (camera_set, render 1 frame, frame download to pinned host memory, stats read-back), synchronised on both sides"},
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": {"kernel": "k_bounce (closest hit + shade + SARSA step + compaction)", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "peak_source": "FP32 FMA microbenchmark run by this bench on this GPU (MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
+                         "flop_per_launch": flops / max(bounce_launches, 1), "avg_launch_ms": trace_s / max(bounce_launches, 1) * 1e3,
+                         "triangle_tests": st["triangle_tests"], "box_tests": st["box_tests"], "trace_seconds": st["trace_seconds"], "merge_seconds": st["merge_seconds"],
+                         "trace_share_of_step": st["trace_seconds"] / max(st["device_seconds"], 1e-12)},
+            "clocks": clk,
+        }
+        if method == 1 and st["merge_seconds"] > 0:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except (OSError, ValueError):
+                pass
+            hbm_peak = peaks.get("hbm_gbs", 6650.0)
+            merge_bytes = nv * 144 * 4 * 4.0                 # per frame: read Q + accumulator counts, write Q-derived CDF (+ sums/visits for touched cells): >= 4 arrays
+            line["roofline_merge"] = {"kernel": "k_merge_cdf", "bound": "hbm", "achieved": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None,
+                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+        if world == 1 and not args.no_cpu_baseline:
+            v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

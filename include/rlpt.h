@@ -41,7 +41,7 @@ enum rlpt_status {
 enum rlpt_traversal { RLPT_TRAVERSAL_AUTO = 0, RLPT_TRAVERSAL_BVH = 1, RLPT_TRAVERSAL_BRUTE = 2 };
 enum rlpt_hit_type { RLPT_HIT_NOTHING = 0, RLPT_HIT_AREA_LIGHT = 1, RLPT_HIT_SURFACE = 2 };   /* G/rays/ray.cuh:30-34 */
 
-/* Run-time form of the reference's compile-time settings (G/constants/*.h). rlpt_config_default() fills in the
+/* Run-time form of the reference's compile-time settings (G/constants/ headers). rlpt_config_default() fills in the
  * reference's committed values, with the BASELINE.json resolution. */
 typedef struct rlpt_config {
     int32_t width;               /* SCREEN_WIDTH            image_settings.h:9   */
@@ -77,7 +77,7 @@ int rlpt_ctx_destroy(rlpt_ctx* ctx);
 int rlpt_sync(rlpt_ctx* ctx);
 int rlpt_stream(rlpt_ctx* ctx, void** cuda_stream);
 int rlpt_config_default(rlpt_config* cfg);
-int rlpt_config_set(rlpt_ctx* ctx, const rlpt_config* cfg);      /* replaces G/constants/*.h #defines */
+int rlpt_config_set(rlpt_ctx* ctx, const rlpt_config* cfg);      /* replaces G/constants/ headers #defines */
 int rlpt_config_get(rlpt_ctx* ctx, rlpt_config* cfg);
 int rlpt_set_allreduce(rlpt_ctx* ctx, rlpt_allreduce_fn fn, void* user);
 
@@ -170,6 +170,10 @@ typedef struct rlpt_stats_t {
     double device_seconds;
     double frames;
     double kernel_launches;
+    double triangle_tests;        /* ray-triangle solves executed by the tracing kernels (72 flop each) */
+    double box_tests;             /* ray-AABB slab tests executed (18 flop each) */
+    double trace_seconds;         /* device seconds inside the per-bounce tracing kernels (CUDA events) */
+    double merge_seconds;         /* device seconds inside all-reduce + Q merge + CDF rebuild */
 } rlpt_stats_t;
 int rlpt_stats(rlpt_ctx* ctx, rlpt_stats_t* out);
 int rlpt_stats_reset(rlpt_ctx* ctx);

@@ -141,6 +141,11 @@ class Oracle:
         s = self.L.orc_sample_sector(_p(_f32(cdf_row)), ctypes.c_float(r), ctypes.byref(pdf))
         return s, pdf.value
 
+    def sample_sector_clamped(self, cdf_row, r):
+        pdf = ctypes.c_float()
+        s = self.L.orc_sample_sector_clamped(_p(_f32(cdf_row)), ctypes.c_float(r), ctypes.byref(pdf))
+        return s, pdf.value
+
     def cell_cos(self, vol):
         out = np.zeros(A, np.float32)
         self.L.orc_cell_cos(int(vol), _p(out))
@@ -270,6 +275,12 @@ class Reference:
         stats = np.zeros((frames, 5), np.float64)
         assert self.L.ref_render_sarsa(int(frames), int(skip_frames), _p(mean), _p(last), _p(stats)) == 0
         return mean, last, stats
+
+
+def philox_raw(oracle, ctr4, key2):
+    c, k, o = np.array(ctr4, np.uint32), np.array(key2, np.uint32), np.zeros(4, np.uint32)
+    oracle.L.orc_philox_raw(_p(c), _p(k), _p(o))
+    return tuple(int(x) for x in o)
 
 
 def mape_score(gt_rgb8, pred_rgb8):

@@ -330,6 +330,15 @@ static int sample_sector(const float* cdf, float r, float& pdf) {
     pdf = 0.f; return -1;
 }
 
+/* Product behaviour where the reference's search fails (r past the last bin, or r exactly equal to a CDF entry the
+ * binary search probes): the first bin k >= 1 with cdf[k] > r, else the last bin of non-zero width. Stated deviation. */
+static int sample_sector_fallback(const float* cdf, float r, float& pdf) {
+    int sector = 1; while (sector < A && !(cdf[sector] > r)) ++sector;
+    if (sector >= A) { sector = A - 1; while (sector > 0 && !(cdf[sector] - cdf[sector - 1] > 0.f)) --sector; }
+    float pv = sector > 0 ? cdf[sector - 1] : 0.f; pdf = RHO * ((cdf[sector] - pv) / GRID_RHO);
+    return sector;
+}
+
 /* ------------------------------------------------------------------ path tracers */
 struct Cfg {
     int width, height, spp, max_bounces; float env; uint32_t seed; float cam[3]; float yaw_y, yaw_x;
@@ -451,10 +460,7 @@ static V3 trace_sarsa(const Cfg& c, uint32_t pixel, int px, int py, uint32_t sam
         const float* cdf = &g_rm.cdf[(size_t)cur_vol * A];
         float pdf = 0.f;
         int sector = sample_sector(cdf, u[0], pdf);
-        if (sector < 0 && c.clamp_last_bin) {          /* product behaviour: clamp to the last bin of non-zero width */
-            sector = A - 1; while (sector > 0 && !(cdf[sector] - cdf[sector - 1] > 0.f)) --sector;
-            float pv = sector > 0 ? cdf[sector - 1] : 0.f; pdf = RHO * ((cdf[sector] - pv) / GRID_RHO);
-        }
+        if (sector < 0 && c.clamp_last_bin) sector = sample_sector_fallback(cdf, u[0], pdf);
         V3 nd;
         if (sector < 0) { failed = true; nd = { 0.f, 0.f, 0.f }; }
         else {
@@ -588,6 +594,8 @@ int orc_find_closest(const float* pos, const float* nrm, int n, float max_dist, 
     return 0;
 }
 int orc_sample_sector(const float* cdf_row, float r, float* pdf) { return sample_sector(cdf_row, r, *pdf); }
+int orc_sample_sector_clamped(const float* cdf_row, float r, float* pdf) { int s = sample_sector(cdf_row, r, *pdf); return s >= 0 ? s : sample_sector_fallback(cdf_row, r, *pdf); }
+void orc_philox_raw(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) { uint32_t c[4] = { ctr4[0], ctr4[1], ctr4[2], ctr4[3] }; philox4x32_10(key2[0], key2[1], c); for (int i = 0; i < 4; ++i) out4[i] = c[i]; }
 void orc_cell_cos(int vol, float* out144) { for (int k = 0; k < A; ++k) out144[k] = cell_cos(g_rm.vol[vol], k / GRID, k % GRID); }
 
 /* cfg: see struct Cfg. One frame = spp samples for every pixel, samples numbered sample0 .. sample0+spp-1.

@@ -45,6 +45,7 @@ struct rlpt_ctx {
     bool have_rmap = false;
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
     float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
+    int *d_grid_start = nullptr, *d_grid_vol = nullptr; float4* d_grid_posn = nullptr; float grid_h = 0.f;
     float *d_q = nullptr, *d_cdf = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // wavefront state
@@ -53,8 +54,10 @@ struct rlpt_ctx {
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
     size_t smem_bytes = 0; int grid = 148;
+    void* d_stage = nullptr; size_t stage_bytes = 0;     // device staging for frame downloads (kept across calls)
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
-    double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0;
+    double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;
+    std::vector<cudaEvent_t> phase_ev; size_t phase_used = 0;      // per-frame phase marks of the current render call
 };
 
 static void free_scene(rlpt_ctx* c) {
@@ -64,6 +67,7 @@ static void free_scene(rlpt_ctx* c) {
 static void free_rmap(rlpt_ctx* c) {
     cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
     cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt);
+    cudaFree(c->d_grid_start); cudaFree(c->d_grid_vol); cudaFree(c->d_grid_posn); c->d_grid_start = c->d_grid_vol = nullptr; c->d_grid_posn = nullptr;
     c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
     c->have_rmap = false; c->rm = RadianceDev{};
 }
@@ -72,6 +76,23 @@ static void free_frame(rlpt_ctx* c) {
     cudaFree(c->d_counts); cudaFree(c->d_accum); c->d_counts = nullptr; c->d_accum = nullptr; c->queue_capacity = 0; c->accum_pixels = 0; c->counts_len = 0;
 }
 
+// largest float f with (double)f*f < (double)max_dist: fabsf(delta) <= f is the reference's pow(delta,2) < max_dist
+static float within_abs_of(float max_dist) {
+    const double md = (double)max_dist;
+    if (!(md > 0.0)) return -1.f;
+    float f = (float)std::sqrt(md);
+    while (f > 0.f && (double)f * (double)f >= md) f = std::nextafterf(f, 0.f);
+    for (float n = std::nextafterf(f, INFINITY); (double)n * (double)n < md; n = std::nextafterf(f, INFINITY)) f = n;
+    return f;
+}
+static float grid_accept_r(float h, float within_abs) { return std::min(h * (1.f - 1e-3f), within_abs * (1.f - 1e-5f)); }
+
+static int ensure_stage(rlpt_ctx* c, size_t bytes) {
+    if (bytes <= c->stage_bytes) return RLPT_OK;
+    cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMalloc(&c->d_stage, bytes)); c->stage_bytes = bytes;
+    return RLPT_OK;
+}
 static float luminance3(const float* c) { float mx = std::max(c[2], std::max(c[0], c[1])), mn = std::min(c[2], std::min(c[0], c[1])); return 0.5f * (mx + mn); }
 
 extern "C" {
@@ -117,7 +138,8 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c); free_rmap(c); free_frame(c);
-    cudaFree(c->d_dyn); cudaFree(c->d_stats); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
+    cudaFree(c->d_stage); cudaFree(c->d_dyn); cudaFree(c->d_stats); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
+    for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
     delete c;
     return RLPT_OK;
@@ -160,7 +182,7 @@ int rlpt_config_set(rlpt_ctx* c, const rlpt_config* cfg) {
     CK(cudaSetDevice(c->device));
     if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); free_frame(c); }
     if (c->have_scene) { int rc = choose_traversal(c, 0); if (rc) return rc; }
-    if (c->have_rmap) c->rm.max_dist = cfg->max_dist;
+    if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.grid.accept_r = grid_accept_r(c->grid_h, c->rm.within_abs); }
     return RLPT_OK;
 }
 
@@ -325,7 +347,33 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     rm.irradiance = c->d_irr; rm.acc_sum = c->d_acc_sum; rm.acc_cnt = c->d_acc_cnt; rm.n_vol = nv; rm.n_inner = n_inner;
     rm.root = child_word(0);
     rm.root_px = c->h_tree[0].pos[0]; rm.root_py = c->h_tree[0].pos[1]; rm.root_pz = c->h_tree[0].pos[2];
-    rm.max_dist = c->cfg.max_dist;
+    rm.within_abs = within_abs_of(c->cfg.max_dist);
+    {
+        // uniform grid over the volume positions, one empty cell of padding all round; cell size just above the kd search
+        // radius (or coarser for very large scenes: at most 254 cells per axis)
+        float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
+        for (int i = 0; i < nv; ++i) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], c->h_vol[i].pos[k]); hi[k] = std::max(hi[k], c->h_vol[i].pos[k]); }
+        float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+        float h = std::max(std::max(rm.within_abs, 0.f) * 1.01f, std::max(ext / 254.f, 1e-6f));
+        VolGrid g{}; g.inv_h = 1.f / h; g.ox = lo[0] - h; g.oy = lo[1] - h; g.oz = lo[2] - h;
+        g.nx = (int)grid_coord(hi[0], g.ox, g.inv_h) + 2; g.ny = (int)grid_coord(hi[1], g.oy, g.inv_h) + 2; g.nz = (int)grid_coord(hi[2], g.oz, g.inv_h) + 2;
+        c->grid_h = h; g.accept_r = grid_accept_r(h, rm.within_abs);
+        const size_t ncell = (size_t)g.nx * g.ny * g.nz;
+        std::vector<int> start(ncell + 1, 0), cell_of(nv), gvol(nv); std::vector<float4> gposn(nv);
+        for (int i = 0; i < nv; ++i) {
+            const float* p = c->h_vol[i].pos;
+            int cx = (int)grid_coord(p[0], g.ox, g.inv_h), cy = (int)grid_coord(p[1], g.oy, g.inv_h), cz = (int)grid_coord(p[2], g.oz, g.inv_h);
+            cell_of[i] = (cz * g.ny + cy) * g.nx + cx; start[cell_of[i] + 1]++;
+        }
+        for (size_t k = 0; k < ncell; ++k) start[k + 1] += start[k];
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int i = 0; i < nv; ++i) { int slot = fill[cell_of[i]]++; gvol[slot] = i; gposn[slot] = posn[i]; }
+        CK(cudaMalloc(&c->d_grid_start, sizeof(int) * (ncell + 1))); CK(cudaMalloc(&c->d_grid_vol, sizeof(int) * nv)); CK(cudaMalloc(&c->d_grid_posn, sizeof(float4) * nv));
+        CK(cudaMemcpy(c->d_grid_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_grid_vol, gvol.data(), sizeof(int) * nv, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_grid_posn, gposn.data(), sizeof(float4) * nv, cudaMemcpyHostToDevice));
+        rm.grid = g; rm.grid_start = c->d_grid_start; rm.grid_vol = c->d_grid_vol; rm.grid_posn = c->d_grid_posn;
+    }
     c->have_rmap = true;
     launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
@@ -497,11 +545,26 @@ static int enqueue_merge(rlpt_ctx* c) {
     return RLPT_OK;
 }
 
-static int timed_begin(rlpt_ctx* c) { CK(cudaSetDevice(c->device)); CK(cudaEventRecord(c->ev0, c->stream)); return RLPT_OK; }
+// phase marks: events recorded in stream order around the tracing kernels and around the merge of every frame of one
+// render call; read back (after the call's final synchronisation) into trace_seconds / merge_seconds
+static int phase_mark(rlpt_ctx* c) {
+    if (c->phase_used == c->phase_ev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->phase_ev.push_back(e); }
+    CK(cudaEventRecord(c->phase_ev[c->phase_used++], c->stream));
+    return RLPT_OK;
+}
+static int timed_begin(rlpt_ctx* c) { CK(cudaSetDevice(c->device)); c->phase_used = 0; CK(cudaEventRecord(c->ev0, c->stream)); return RLPT_OK; }
 static int timed_end(rlpt_ctx* c, int frames) {
     CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
     float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->device_seconds += ms * 1e-3; c->frames_rendered += frames;
+    // marks come in (trace begin, trace end[, merge end]) groups of `marks_per_frame`
+    const size_t per = frames > 0 ? c->phase_used / (size_t)frames : 0;
+    for (size_t f = 0; per >= 2 && f < (size_t)frames; ++f) {
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c->phase_ev[f * per], c->phase_ev[f * per + 1])); c->trace_seconds += a * 1e-3;
+        if (per >= 3) { CK(cudaEventElapsedTime(&b, c->phase_ev[f * per + 1], c->phase_ev[f * per + 2])); c->merge_seconds += b * 1e-3; }
+    }
+    c->phase_used = 0;
     CK(cudaGetLastError());
     return RLPT_OK;
 }
@@ -510,7 +573,7 @@ int rlpt_render_default(rlpt_ctx* c, int frames) {
     if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_render_default: upload a scene first");
     if (frames < 0) return fail(RLPT_ERR_ARG, "rlpt_render_default: negative frame count");
     int rc = timed_begin(c); if (rc) return rc;
-    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 0, 0); if (rc) return rc; }
+    for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_trace(c, 0, 0); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
     return timed_end(c, frames);
 }
 int rlpt_sarsa_trace(rlpt_ctx* c) {
@@ -527,14 +590,20 @@ int rlpt_render_sarsa(rlpt_ctx* c, int frames) {
     if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa: needs a scene and a radiance map");
     if (frames < 0) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa: negative frame count");
     int rc = timed_begin(c); if (rc) return rc;
-    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 1, 1); if (rc) return rc; rc = enqueue_merge(c); if (rc) return rc; }
+    for (int f = 0; f < frames; ++f) {
+        rc = phase_mark(c); if (rc) return rc;
+        rc = enqueue_trace(c, 1, 1); if (rc) return rc;
+        rc = phase_mark(c); if (rc) return rc;
+        rc = enqueue_merge(c); if (rc) return rc;
+        rc = phase_mark(c); if (rc) return rc;
+    }
     return timed_end(c, frames);
 }
 int rlpt_render_sarsa_frozen(rlpt_ctx* c, int frames) {
     if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa_frozen: needs a scene and a radiance map");
     if (frames < 0) return fail(RLPT_ERR_ARG, "negative frame count");
     int rc = timed_begin(c); if (rc) return rc;
-    for (int f = 0; f < frames; ++f) { rc = enqueue_trace(c, 1, 0); if (rc) return rc; }
+    for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_trace(c, 1, 0); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
     return timed_end(c, frames);
 }
 
@@ -554,23 +623,23 @@ int rlpt_frame_allreduce(rlpt_ctx* c) {
 int rlpt_frame_download(rlpt_ctx* c, float* rgb) {
     if (!c || !c->d_accum || !rgb) return fail(RLPT_ERR_ARG, "rlpt_frame_download: nothing rendered / null");
     CK(cudaSetDevice(c->device));
-    float* d = nullptr; size_t n = (size_t)c->accum_pixels;
-    CK(cudaMalloc(&d, sizeof(float) * 3 * n));
+    size_t n = (size_t)c->accum_pixels;
+    int rc = ensure_stage(c, sizeof(float) * 3 * n); if (rc) return rc;
+    float* d = (float*)c->d_stage;
     launch_frame_mean(c->d_accum, d, (int)n, c->stream);
     CK(cudaMemcpyAsync(rgb, d, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
-    cudaFree(d);
     return RLPT_OK;
 }
 int rlpt_frame_download_argb(rlpt_ctx* c, uint32_t* argb) {
     if (!c || !c->d_accum || !argb) return fail(RLPT_ERR_ARG, "rlpt_frame_download_argb: nothing rendered / null");
     CK(cudaSetDevice(c->device));
-    uint32_t* d = nullptr; size_t n = (size_t)c->accum_pixels;
-    CK(cudaMalloc(&d, sizeof(uint32_t) * n));
+    size_t n = (size_t)c->accum_pixels;
+    int rc = ensure_stage(c, sizeof(uint32_t) * n); if (rc) return rc;
+    uint32_t* d = (uint32_t*)c->d_stage;
     launch_pack_argb(c->d_accum, d, c->cfg.width, c->cfg.height, c->stream);
     CK(cudaMemcpyAsync(argb, d, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
-    cudaFree(d);
     return RLPT_OK;
 }
 
@@ -600,13 +669,14 @@ int rlpt_stats(rlpt_ctx* c, rlpt_stats_t* out) {
     unsigned long long h[8]; CK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
     out->path_length_sum = (double)h[0]; out->zero_contribution_paths = (double)h[1]; out->paths = (double)h[2];
     out->ray_casts = (double)h[0]; out->device_seconds = c->device_seconds; out->frames = c->frames_rendered; out->kernel_launches = c->launches;
+    out->triangle_tests = (double)h[3]; out->box_tests = (double)h[4]; out->trace_seconds = c->trace_seconds; out->merge_seconds = c->merge_seconds;
     return RLPT_OK;
 }
 int rlpt_stats_reset(rlpt_ctx* c) {
     if (!c) return fail(RLPT_ERR_ARG, "null ctx");
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * 8, c->stream));
-    c->device_seconds = 0.0; c->frames_rendered = 0.0; c->launches = 0.0;
+    c->device_seconds = 0.0; c->frames_rendered = 0.0; c->launches = 0.0; c->trace_seconds = 0.0; c->merge_seconds = 0.0;
     return RLPT_OK;
 }
 

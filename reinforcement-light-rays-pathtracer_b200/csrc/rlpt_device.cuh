@@ -213,13 +213,14 @@ RLPT_HD float kd_distance(float px, float py, float pz, float qx, float qy, floa
     float dx = RLPT_SUB(qx, px), dy = RLPT_SUB(qy, py), dz = RLPT_SUB(qz, pz);
     return RLPT_SQRT(RLPT_FMA(dz, dz, RLPT_FMA(dx, dx, RLPT_MUL(dy, dy))));
 }
+// `within_abs` is the largest float f with (double)f*f < (double)MAX_DIST, so that fabsf(delta) <= f is exactly the
+// reference's `pow(delta, 2) < max_dist` (evaluated in double there, radiance_map.cu:185,193) without FP64 in the loop.
 template <class LoadInner, class LoadVol>
 RLPT_HD int kd_find(LoadInner load_inner, LoadVol load_vol, uint32_t root, float root_px, float root_py, float root_pz,
-                    float px, float py, float pz, int normal_class, float max_dist) {
+                    float px, float py, float pz, int normal_class, float within_abs) {
     uint32_t stack[32]; int top = 0;
     int best = 0; float best_d = kd_distance(px, py, pz, root_px, root_py, root_pz);
     uint32_t cur = root; bool have = true;
-    const double md = (double)max_dist;
     while (have) {
         if (cur & KD_LEAF) {
             int vol = (int)(cur & ~KD_LEAF);
@@ -231,13 +232,53 @@ RLPT_HD int kd_find(LoadInner load_inner, LoadVol load_vol, uint32_t root, float
             float split; uint32_t left, right; int dim; load_inner(cur, split, left, right, dim);
             float c = dim == 0 ? px : (dim == 1 ? py : pz);
             float delta = RLPT_SUB(c, split);
-            bool within = (double)delta * (double)delta < md;
+            bool within = fabsf(delta) <= within_abs;
             uint32_t near_c = (c < split) ? left : right, far_c = (c < split) ? right : left;
             if (within && top < 32) stack[top++] = far_c;
             cur = near_c;
         }
     }
     return best;
+}
+
+// Uniform-grid front end of the nearest-volume search (DESIGN.md "Nearest volume"). The kd search above visits every
+// leaf whose position differs from the query by at most within_abs in every coordinate (a far child is entered when
+// the query is within within_abs of the split plane, and the split lies between query and leaf), keeps the closest
+// same-normal leaf with strict <, and starts from (volume 0, |query - root.position|). Hence: if the closest same-normal
+// volume N found among ALL volumes within one grid cell of the query has distance r <= accept_r
+// (accept_r < min(cell size, within_abs)), N is also the kd search's winner among leaves, and the kd answer is
+// r < d0 ? N : 0. Anything else -- no candidate, r > accept_r, an exact distance tie (the kd answer then depends on visit
+// order), a query outside the grid -- returns -1 and the caller runs the kd search itself.
+// Cells: dense nx*ny*nz array of start offsets (x fastest) into volumes sorted by cell; cell(x) = floor((x - origin) / h).
+struct VolGrid { float ox, oy, oz, inv_h, accept_r; int nx, ny, nz; };
+RLPT_HD float grid_coord(float x, float o, float inv_h) { return floorf(RLPT_MUL(RLPT_SUB(x, o), inv_h)); }
+template <class LoadStart, class LoadCand>
+RLPT_HD int grid_find(const VolGrid& g, LoadStart load_start, LoadCand load_cand, float px, float py, float pz, int normal_class,
+                      float d0, int& best_slot) {
+    float ux = grid_coord(px, g.ox, g.inv_h), uy = grid_coord(py, g.oy, g.inv_h), uz = grid_coord(pz, g.oz, g.inv_h);
+    if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz)) return -1;
+    const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
+    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < g.nx ? cx + 1 : g.nx - 1;
+    float best_d = 3.0e38f; int best = -1; bool tie = false;
+    for (int z = cz - 1; z <= cz + 1; ++z) {
+        if (z < 0 || z >= g.nz) continue;
+        for (int y = cy - 1; y <= cy + 1; ++y) {
+            if (y < 0 || y >= g.ny) continue;
+            const int row = (z * g.ny + y) * g.nx;
+            const int s = load_start(row + x0), e = load_start(row + x1 + 1);
+            for (int i = s; i < e; ++i) {
+                float vx, vy, vz; int cls; load_cand(i, vx, vy, vz, cls);
+                float d = kd_distance(px, py, pz, vx, vy, vz);
+                if (cls == normal_class) {
+                    if (d < best_d) { best_d = d; best = i; tie = false; }
+                    else if (d == best_d) tie = true;
+                }
+            }
+        }
+    }
+    if (best < 0 || tie || !(best_d <= g.accept_r)) return -1;
+    best_slot = best;
+    return best_d < d0 ? 1 : 0;          // 1: the volume in slot `best_slot` wins; 0: volume 0 stays
 }
 
 }  // namespace rlpt

@@ -40,7 +40,12 @@ struct RadianceDev {
     int n_vol, n_inner;
     uint32_t root;            // KD child word of the root
     float root_px, root_py, root_pz;   // radiance_array[0].position as the reference initialises its search with
-    float max_dist;
+    float within_abs;         // exact float form of the reference's pow(delta,2) < MAX_DIST test (rlpt_device.cuh, kd_find)
+    // uniform-grid front end of the nearest-volume search (rlpt_device.cuh, grid_find)
+    VolGrid grid;
+    const int* grid_start;    // [nx*ny*nz + 1]
+    const float4* grid_posn;  // [n_vol] (position, as_float(normal class)) sorted by cell
+    const int* grid_vol;      // [n_vol] volume index of each sorted slot
 };
 
 // ---- wavefront path state, SoA, one slot per live path (two queues, ping-pong per bounce)

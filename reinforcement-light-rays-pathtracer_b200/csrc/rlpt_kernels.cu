@@ -152,12 +152,23 @@ void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, 
 // ------------------------------------------------------------------------------------------------ nearest volume
 __device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, float py, float pz, int cls) {
     const float4* __restrict__ inner = rm.kd_inner; const float4* __restrict__ posn = rm.vol_posn;
+    if (rm.grid_start) {
+        const int* __restrict__ gs = rm.grid_start; const float4* __restrict__ gp = rm.grid_posn;
+        const float d0 = kd_distance(px, py, pz, rm.root_px, rm.root_py, rm.root_pz);
+        int slot = 0;
+        int r = grid_find(rm.grid, [&](int i) { return __ldg(gs + i); },
+                          [&](int i, float& x, float& y, float& z, int& c) { float4 p = __ldg(gp + i); x = p.x; y = p.y; z = p.z; c = __float_as_int(p.w); },
+                          px, py, pz, cls, d0, slot);
+        if (r == 1) return __ldg(rm.grid_vol + slot);
+        if (r == 0) return 0;
+    }
+    // exact reference search: the rare queries the grid cannot decide (far from every volume, distance ties)
     return kd_find(
         [&](uint32_t idx, float& split, uint32_t& l, uint32_t& r, int& dim) {
             float4 n = __ldg(inner + idx); split = n.x; l = __float_as_uint(n.y); r = __float_as_uint(n.z); dim = __float_as_int(n.w);
         },
         [&](int vol, float& x, float& y, float& z, int& c) { float4 p = __ldg(posn + vol); x = p.x; y = p.y; z = p.z; c = __float_as_int(p.w); },
-        rm.root, rm.root_px, rm.root_py, rm.root_pz, px, py, pz, cls, rm.max_dist);
+        rm.root, rm.root_px, rm.root_py, rm.root_pz, px, py, pz, cls, rm.within_abs);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_find_closest(RadianceDev rm, const float* __restrict__ pos, const int* __restrict__ cls, int n, int* __restrict__ out) {
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameP
             if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
         }
         float t = T_MISS, sdx = 0, sdy = 0, sdz = 0; int gid = -1;
-        if (valid) closest_hit<STAGED, false>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        if (valid) closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
         const bool surface = valid && gid >= 0 && gid < v.n_surf;
         const bool light = valid && gid >= v.n_surf;
         float hx = 0, hy = 0, hz = 0; float4 sN = make_float4(0, 1, 0, 0), sT = make_float4(1, 0, 0, 0);
@@ -302,6 +313,10 @@ __global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameP
     if (lane == 0 && st_term) {
         atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term);
     }
+    // work counters for the roofline: triangle tests and box tests actually executed; two integer adds per
+    // test next to ~72 / ~18 FP32 operations, so they stay on in the product build
+    n_tri = __reduce_add_sync(full, n_tri); n_box = __reduce_add_sync(full, n_box);
+    if (lane == 0 && (n_tri | n_box)) { atomicAdd(p.stats + 3, (unsigned long long)n_tri); atomicAdd(p.stats + 4, (unsigned long long)n_box); }
 }
 
 template <bool SARSA, bool PRIMARY>

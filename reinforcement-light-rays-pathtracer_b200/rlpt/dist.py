@@ -1,0 +1,43 @@
+"""All-reduce hook for rlpt_set_allreduce built on torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU
+tests). The library hands over a raw device pointer on its own stream; the hook wraps it as a tensor without copying
+and runs the collective in that stream's order, so no host synchronisation is needed between tracing, all-reduce and
+the merge kernel. PyTorch is plumbing here: the reduction itself is NCCL's.
+"""
+import numpy as np
+
+
+class _DevicePtr:
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def torch_allreduce_hook(device_index, group=None):
+    """hook(ptr, count, dtype, stream) for Context.set_allreduce; dtype 0 = float32, 1 = uint32 (summed as int32)."""
+    import torch
+    import torch.distributed as dist
+    cache = {}
+
+    def hook(ptr, count, dtype, stream):
+        key = (ptr, count, dtype)
+        t = cache.get(key)
+        if t is None:
+            t = torch.as_tensor(_DevicePtr(ptr, count, "<f4" if dtype == 0 else "<i4"), device="cuda:%d" % device_index)
+            cache[key] = t
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=device_index)):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return hook
+
+
+def host_allreduce_hook(group=None):
+    """The same contract over host memory (gloo), for the world_size-2 CPU tests of the merge logic: `ptr` is a host
+    address of `count` elements."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, count, dtype, stream):
+        ctype = ctypes.c_float if dtype == 0 else ctypes.c_int32
+        a = np.ctypeslib.as_array((ctype * count).from_address(ptr))
+        t = torch.from_numpy(a)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return hook
