@@ -359,19 +359,39 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
         g.nx = (int)grid_coord(hi[0], g.ox, g.inv_h) + 2; g.ny = (int)grid_coord(hi[1], g.oy, g.inv_h) + 2; g.nz = (int)grid_coord(hi[2], g.oz, g.inv_h) + 2;
         c->grid_h = h; g.accept_r = grid_accept_r(h, rm.within_abs);
         const size_t ncell = (size_t)g.nx * g.ny * g.nz;
-        std::vector<int> start(ncell + 1, 0), cell_of(nv), gvol(nv); std::vector<float4> gposn(nv);
+        // own-cell buckets first, then each cell's candidate list = the volumes of its 27-cell neighbourhood
+        std::vector<int> own(ncell + 1, 0), cell_of(nv), sorted(nv);
         for (int i = 0; i < nv; ++i) {
             const float* p = c->h_vol[i].pos;
             int cx = (int)grid_coord(p[0], g.ox, g.inv_h), cy = (int)grid_coord(p[1], g.oy, g.inv_h), cz = (int)grid_coord(p[2], g.oz, g.inv_h);
-            cell_of[i] = (cz * g.ny + cy) * g.nx + cx; start[cell_of[i] + 1]++;
+            cell_of[i] = (cz * g.ny + cy) * g.nx + cx; own[cell_of[i] + 1]++;
         }
-        for (size_t k = 0; k < ncell; ++k) start[k + 1] += start[k];
-        std::vector<int> fill(start.begin(), start.end() - 1);
-        for (int i = 0; i < nv; ++i) { int slot = fill[cell_of[i]]++; gvol[slot] = i; gposn[slot] = posn[i]; }
-        CK(cudaMalloc(&c->d_grid_start, sizeof(int) * (ncell + 1))); CK(cudaMalloc(&c->d_grid_vol, sizeof(int) * nv)); CK(cudaMalloc(&c->d_grid_posn, sizeof(float4) * nv));
+        for (size_t k = 0; k < ncell; ++k) own[k + 1] += own[k];
+        { std::vector<int> fill(own.begin(), own.end() - 1); for (int i = 0; i < nv; ++i) sorted[fill[cell_of[i]]++] = i; }
+        std::vector<int> start(ncell + 1, 0);
+        auto neighbourhood = [&](int x, int y, int z, auto&& visit) {
+            for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
+                int xx = x + dx, yy = y + dy, zz = z + dz;
+                if (xx < 0 || yy < 0 || zz < 0 || xx >= g.nx || yy >= g.ny || zz >= g.nz) continue;
+                visit((size_t)(zz * g.ny + yy) * g.nx + xx);
+            }
+        };
+        size_t total = 0;
+        for (int z = 0; z < g.nz; ++z) for (int y = 0; y < g.ny; ++y) for (int x = 0; x < g.nx; ++x) {
+            size_t cell = (size_t)(z * g.ny + y) * g.nx + x; start[cell] = (int)total;
+            neighbourhood(x, y, z, [&](size_t nb) { total += (size_t)(own[nb + 1] - own[nb]); });
+            if (total > 0x7fffffffu) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_radiance_map_build: nearest-volume candidate lists exceed 2^31 entries");
+        }
+        start[ncell] = (int)total;
+        std::vector<int> gvol(std::max<size_t>(total, 1)); std::vector<float4> gposn(std::max<size_t>(total, 1));
+        for (int z = 0; z < g.nz; ++z) for (int y = 0; y < g.ny; ++y) for (int x = 0; x < g.nx; ++x) {
+            size_t cell = (size_t)(z * g.ny + y) * g.nx + x; size_t w = (size_t)start[cell];
+            neighbourhood(x, y, z, [&](size_t nb) { for (int k = own[nb]; k < own[nb + 1]; ++k) { gvol[w] = sorted[k]; gposn[w] = posn[sorted[k]]; ++w; } });
+        }
+        CK(cudaMalloc(&c->d_grid_start, sizeof(int) * (ncell + 1))); CK(cudaMalloc(&c->d_grid_vol, sizeof(int) * gvol.size())); CK(cudaMalloc(&c->d_grid_posn, sizeof(float4) * gposn.size()));
         CK(cudaMemcpy(c->d_grid_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_grid_vol, gvol.data(), sizeof(int) * nv, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_grid_posn, gposn.data(), sizeof(float4) * nv, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_grid_vol, gvol.data(), sizeof(int) * gvol.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_grid_posn, gposn.data(), sizeof(float4) * gposn.size(), cudaMemcpyHostToDevice));
         rm.grid = g; rm.grid_start = c->d_grid_start; rm.grid_vol = c->d_grid_vol; rm.grid_posn = c->d_grid_posn;
     }
     c->have_rmap = true;

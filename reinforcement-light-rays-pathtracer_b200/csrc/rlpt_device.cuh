@@ -245,38 +245,42 @@ RLPT_HD int kd_find(LoadInner load_inner, LoadVol load_vol, uint32_t root, float
 // leaf whose position differs from the query by at most within_abs in every coordinate (a far child is entered when
 // the query is within within_abs of the split plane, and the split lies between query and leaf), keeps the closest
 // same-normal leaf with strict <, and starts from (volume 0, |query - root.position|). Hence: if the closest same-normal
-// volume N found among ALL volumes within one grid cell of the query has distance r <= accept_r
-// (accept_r < min(cell size, within_abs)), N is also the kd search's winner among leaves, and the kd answer is
-// r < d0 ? N : 0. Anything else -- no candidate, r > accept_r, an exact distance tie (the kd answer then depends on visit
-// order), a query outside the grid -- returns -1 and the caller runs the kd search itself.
-// Cells: dense nx*ny*nz array of start offsets (x fastest) into volumes sorted by cell; cell(x) = floor((x - origin) / h).
+// volume N among ALL volumes within one grid cell of the query (the 27-cell neighbourhood) has distance
+// r <= accept_r (accept_r < min(cell size, within_abs)), N is also the kd search's winner among leaves, and the kd answer
+// is r < d0 ? N : 0. Anything else -- no candidate, r > accept_r, two candidates whose rounded distances tie (the kd
+// answer then depends on visit order), a query outside the grid -- returns -1 and the caller runs the kd search itself.
+// Layout: dense nx*ny*nz array of start offsets (x fastest) into per-cell candidate lists; the list of a cell holds
+// every volume of its 27-cell neighbourhood as (position, normal class), so a query reads ONE contiguous range.
+// cell(x) = floor((x - origin) / h). Candidates are ranked on the squared distance (the argument of the reference's
+// sqrt, same rounding sequence); only the winner and the runner-up are square-rooted, to detect ties after rounding.
 struct VolGrid { float ox, oy, oz, inv_h, accept_r; int nx, ny, nz; };
 RLPT_HD float grid_coord(float x, float o, float inv_h) { return floorf(RLPT_MUL(RLPT_SUB(x, o), inv_h)); }
+RLPT_HD float kd_distance2(float px, float py, float pz, float qx, float qy, float qz) {
+    float dx = RLPT_SUB(qx, px), dy = RLPT_SUB(qy, py), dz = RLPT_SUB(qz, pz);
+    return RLPT_FMA(dz, dz, RLPT_FMA(dx, dx, RLPT_MUL(dy, dy)));
+}
 template <class LoadStart, class LoadCand>
 RLPT_HD int grid_find(const VolGrid& g, LoadStart load_start, LoadCand load_cand, float px, float py, float pz, int normal_class,
                       float d0, int& best_slot) {
     float ux = grid_coord(px, g.ox, g.inv_h), uy = grid_coord(py, g.oy, g.inv_h), uz = grid_coord(pz, g.oz, g.inv_h);
     if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz)) return -1;
-    const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
-    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < g.nx ? cx + 1 : g.nx - 1;
-    float best_d = 3.0e38f; int best = -1; bool tie = false;
-    for (int z = cz - 1; z <= cz + 1; ++z) {
-        if (z < 0 || z >= g.nz) continue;
-        for (int y = cy - 1; y <= cy + 1; ++y) {
-            if (y < 0 || y >= g.ny) continue;
-            const int row = (z * g.ny + y) * g.nx;
-            const int s = load_start(row + x0), e = load_start(row + x1 + 1);
-            for (int i = s; i < e; ++i) {
-                float vx, vy, vz; int cls; load_cand(i, vx, vy, vz, cls);
-                float d = kd_distance(px, py, pz, vx, vy, vz);
-                if (cls == normal_class) {
-                    if (d < best_d) { best_d = d; best = i; tie = false; }
-                    else if (d == best_d) tie = true;
-                }
-            }
+    const int cell = ((int)uz * g.ny + (int)uy) * g.nx + (int)ux;
+    const int s = load_start(cell), e = load_start(cell + 1);
+    float best2 = 3.0e38f, second2 = 3.0e38f; int best = -1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (int i = s; i < e; ++i) {
+        float vx, vy, vz; int cls; load_cand(i, vx, vy, vz, cls);
+        float d2 = kd_distance2(px, py, pz, vx, vy, vz);
+        if (cls == normal_class) {
+            second2 = fminf(second2, fmaxf(d2, best2));
+            if (d2 < best2) { best2 = d2; best = i; }
         }
     }
-    if (best < 0 || tie || !(best_d <= g.accept_r)) return -1;
+    if (best < 0) return -1;
+    const float best_d = RLPT_SQRT(best2);
+    if (!(best_d <= g.accept_r) || RLPT_SQRT(second2) == best_d) return -1;
     best_slot = best;
     return best_d < d0 ? 1 : 0;          // 1: the volume in slot `best_slot` wins; 0: volume 0 stays
 }

@@ -44,8 +44,8 @@ struct RadianceDev {
     // uniform-grid front end of the nearest-volume search (rlpt_device.cuh, grid_find)
     VolGrid grid;
     const int* grid_start;    // [nx*ny*nz + 1]
-    const float4* grid_posn;  // [n_vol] (position, as_float(normal class)) sorted by cell
-    const int* grid_vol;      // [n_vol] volume index of each sorted slot
+    const float4* grid_posn;  // [n_cand] per-cell candidate lists: (position, as_float(normal class)) of the 27-cell neighbourhood
+    const int* grid_vol;      // [n_cand] volume index of each candidate slot
 };
 
 // ---- wavefront path state, SoA, one slot per live path (two queues, ping-pong per bounce)
