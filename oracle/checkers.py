@@ -120,6 +120,10 @@ class Oracle:
         self.L.orc_rmap_get_acc(_p(s), _p(c))
         return s, c
 
+    def rmap_set_acc(self, s, c):
+        s, c = np.ascontiguousarray(s, dtype=np.float64), np.ascontiguousarray(c, dtype=np.uint32)
+        self.L.orc_rmap_set_acc(_p(s), _p(c))
+
     def rmap_set_q(self, q):
         q = _f32(q)
         self.L.orc_rmap_set_q(_p(q))

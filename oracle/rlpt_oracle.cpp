@@ -580,6 +580,10 @@ int orc_rmap_get_acc(double* sum, unsigned* cnt) {
     if (cnt) memcpy(cnt, g_rm.acc_cnt.data(), g_rm.acc_cnt.size() * 4);
     return 0;
 }
+int orc_rmap_set_acc(const double* sum, const unsigned* cnt) {
+    for (size_t i = 0; i < g_rm.acc_sum.size(); ++i) { g_rm.acc_sum[i] = sum[i]; g_rm.acc_cnt[i] = cnt[i]; }
+    return 0;
+}
 int orc_rmap_set_q(const float* q) { memcpy(g_rm.q.data(), q, g_rm.q.size() * 4); return 0; }
 int orc_rmap_update_distributions(void) {
     int nv = (int)g_rm.vol.size();
