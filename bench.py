@@ -157,7 +157,7 @@ def run_reference_arm(args, rank):
                        "radiance_volumes": 24526, "grid": "12x12", "max_bounces": 80, "note": "CPU arm: bounded sample, 2 spp per frame"},
             "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -175,6 +175,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    # stdout carries exactly one JSON line: everything libraries print there (NCCL's version banner, the reference's
+    # progress text) goes to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if args.impl == "reference":
         return run_reference_arm(args, rank)
     if args.warmup < 3:
@@ -282,7 +290,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

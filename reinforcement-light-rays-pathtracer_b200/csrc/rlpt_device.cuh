@@ -102,7 +102,7 @@ struct TriRec { float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, T1; };
 
 // One Cramer solve. a = -(dir*SCREEN_HEIGHT) (the first column of A), o = ray origin.
 // Returns true when the reference's acceptance test passes; t is the reference's solution.x.
-RLPT_HD bool tri_solve(const TriRec& r, float ox, float oy, float oz, float a0, float a1, float a2, float& t) {
+RLPT_HD bool tri_solve(const TriRec& r, float ox, float oy, float oz, float a0, float a1, float a2, float best_t, float& t) {
     float T2 = RLPT_FMA(r.e2z, a1, -RLPT_MUL(r.e2y, a2));
     float T3 = RLPT_FMA(r.e1z, a1, -RLPT_MUL(r.e1y, a2));
     float detA = RLPT_FMA(r.e2x, T3, RLPT_FMA(a0, r.T1, -RLPT_MUL(r.e1x, T2)));
@@ -113,16 +113,28 @@ RLPT_HD bool tri_solve(const TriRec& r, float ox, float oy, float oz, float a0, 
     float dy = RLPT_FMA(r.e2x, V3, RLPT_FMA(a0, U2, -RLPT_MUL(T2, bx)));
     float dz = RLPT_FMA(T3, bx, RLPT_FMA(a0, RLPT_SUB(p80, p75), -RLPT_MUL(r.e1x, V3)));
     if (!(detA != 0.f)) return false;
-    // Exact-safe early outs. rn(n/d) is negative exactly when n and d have strictly opposite signs and the quotient
-    // does not round to -0, which needs |n/d| > 2^-150; for |d| < 2^23 that holds whenever n*d < -2^-100.
-    // Anything the filter does not reject goes through the reference's own divisions below.
+    // Exact-safe early outs: each rejects only what the reference's own rounded quotients reject too; everything else
+    // goes through the reference's divisions below.
+    // (1) rn(n/d) is negative exactly when n and d have strictly opposite signs and the quotient does not round to -0,
+    //     which needs |n/d| > 2^-150; for |d| < 2^23 that holds whenever n*d < -2^-100.
     const float kTiny = -7.888609052210118e-31f;   // -2^-100
-    if (fabsf(detA) < 8388608.f) {
+    const float ad = fabsf(detA);
+    if (ad < 8388608.f) {
         if (RLPT_MUL(dy, detA) < kTiny || RLPT_MUL(dz, detA) < kTiny) return false;
     }
+    // (2) u + v > 1: with a = dy/detA, b = dz/detA, |dy + dz| > |detA| (1 + 1e-6) in floats means a + b > 1 + 8e-7 when
+    //     a, b >= 0 (and b > 1 + 8e-7 when the other quotient rounds to -0), so rn(rn(a) + rn(b)) > 1: three roundings
+    //     of relative error 2^-24 cannot bring it back to 1. Opposite-sign pairs never trigger it wrongly: they make the
+    //     sum smaller, not larger. NaN/inf compare false and fall through.
+    if (fabsf(RLPT_ADD(dy, dz)) > RLPT_MUL(ad, 1.000001f)) return false;
+    // (3) farther than the current best: |dx| > best_t |detA| (1 + 1e-6) means rn(dx/detA) > best_t or < 0; the caller
+    //     keeps a hit only when t < best_t, or t == best_t with a lower primitive id
+    float dx = RLPT_FMA(r.e2x, RLPT_SUB(p75, p80), RLPT_FMA(r.T1, bx, -RLPT_MUL(r.e1x, U2)));
+    //     (not used while best_t == 0: a quotient that underflows to -0 ties with it)
+    const float lim = RLPT_MUL(RLPT_MUL(best_t, ad), 1.000001f);
+    if (lim > 0.f && fabsf(dx) > lim) return false;
     float u = RLPT_DIV(dy, detA), v = RLPT_DIV(dz, detA);
     if (!(u >= 0.f && v >= 0.f && RLPT_ADD(u, v) <= 1.f)) return false;
-    float dx = RLPT_FMA(r.e2x, RLPT_SUB(p75, p80), RLPT_FMA(r.T1, bx, -RLPT_MUL(r.e1x, U2)));
     t = RLPT_DIV(dx, detA);
     return t >= 0.f;
 }
@@ -267,15 +279,22 @@ RLPT_HD int grid_find(const VolGrid& g, LoadStart load_start, LoadCand load_cand
     const int cell = ((int)uz * g.ny + (int)uy) * g.nx + (int)ux;
     const int s = load_start(cell), e = load_start(cell + 1);
     float best2 = 3.0e38f, second2 = 3.0e38f; int best = -1;
+    // four candidates per trip: the loads are issued together (independent addresses), then ranked in list order
+    for (int i = s; i < e; i += 4) {
+        float vx[4], vy[4], vz[4]; int cls[4];
 #if defined(__CUDA_ARCH__)
-#pragma unroll 2
+#pragma unroll
 #endif
-    for (int i = s; i < e; ++i) {
-        float vx, vy, vz; int cls; load_cand(i, vx, vy, vz, cls);
-        float d2 = kd_distance2(px, py, pz, vx, vy, vz);
-        if (cls == normal_class) {
-            second2 = fminf(second2, fmaxf(d2, best2));
-            if (d2 < best2) { best2 = d2; best = i; }
+        for (int k = 0; k < 4; ++k) { int j = i + k < e ? i + k : e - 1; load_cand(j, vx[k], vy[k], vz[k], cls[k]); }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            float d2 = kd_distance2(px, py, pz, vx[k], vy[k], vz[k]);
+            if (i + k < e && cls[k] == normal_class) {
+                second2 = fminf(second2, fmaxf(d2, best2));
+                if (d2 < best2) { best2 = d2; best = i + k; }
+            }
         }
     }
     if (best < 0) return -1;

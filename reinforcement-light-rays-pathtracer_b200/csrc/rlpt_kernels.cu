@@ -80,7 +80,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
         for (int gid = 0; gid < v.n_tri; ++gid) {
             TriRec r = load_tri(v, gid); float t;
             if (COUNT) n_tri++;
-            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && t < best_t) { best_t = t; best_gid = gid; }
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && t < best_t) { best_t = t; best_gid = gid; }
         }
         return;
     }
@@ -97,13 +97,13 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
         if (h0 && c0 < 0) {
             int gid = ~c0; TriRec r = load_tri(v, gid); float t;
             if (COUNT) n_tri++;
-            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
             h0 = false;
         }
         if (h1 && c1 < 0) {
             int gid = ~c1; TriRec r = load_tri(v, gid); float t;
             if (COUNT) n_tri++;
-            if (tri_solve(r, ox, oy, oz, a0, a1, a2, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+            if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
             h1 = false;
         }
         if (h0 && h1) {

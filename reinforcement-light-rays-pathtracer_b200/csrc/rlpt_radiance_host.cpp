@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <cstdint>
 
 namespace rlpt {
 
@@ -73,7 +75,13 @@ struct Builder {
 void host_build_radiance_map(const float* surface_v, const float* surface_nrm, int n_surfaces, float area_per_sample,
                              std::vector<HostVolume>& volumes, std::vector<HostTreeElement>& tree) {
     volumes.clear(); tree.clear();
-    srand(1);
+    // The reference draws volume positions with the process-wide rand(), never seeded (= srand(1)). random_r on a private
+    // state reproduces exactly that glibc stream without touching (or racing on) the global generator, so every context
+    // -- in any thread, built any number of times -- samples the same volumes, which multi-GPU replicas rely on.
+    struct random_data rng; char rng_state[128];
+    memset(&rng, 0, sizeof rng); memset(rng_state, 0, sizeof rng_state);
+    initstate_r(1u, rng_state, sizeof rng_state, &rng);
+    auto next_rand = [&]() { int32_t r = 0; random_r(&rng, &r); return (int)r; };
     for (int j = 0; j < n_surfaces; ++j) {
         const float* v = surface_v + 9 * j;
         int count = (int)std::floor(host_triangle_area(v) / area_per_sample);
@@ -81,7 +89,7 @@ void host_build_radiance_map(const float* surface_v, const float* surface_nrm, i
         for (int i = 0; i < count; ++i) {
             HostVolume hv; float a1, a2;
             do {
-                a1 = (float)rand() / (float)RAND_MAX; a2 = (float)rand() / (float)RAND_MAX;
+                a1 = (float)next_rand() / (float)RAND_MAX; a2 = (float)next_rand() / (float)RAND_MAX;
                 for (int k = 0; k < 3; ++k) hv.pos[k] = (v[k] + a1 * e1[k]) + a2 * e2[k];
             } while (a1 + a2 > 1.f);
             for (int k = 0; k < 3; ++k) hv.nrm[k] = surface_nrm[3 * j + k];
