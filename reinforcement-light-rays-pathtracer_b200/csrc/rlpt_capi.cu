@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -40,7 +41,6 @@ struct rlpt_ctx {
     SceneDev scene{};
     // camera / per-frame
     float cam[3] = { 0.f, 0.f, -3.f }; float yaw_y = 0.f, yaw_x = 0.f;
-    FrameDyn* d_dyn = nullptr;
     // radiance map
     bool have_rmap = false;
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
@@ -49,7 +49,8 @@ struct rlpt_ctx {
     float *d_q = nullptr, *d_cdf = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // wavefront state
-    size_t queue_capacity = 0; PathQueue q[2]{}; int* d_counts = nullptr; int counts_len = 0;
+    struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
+    std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; cudaEvent_t ev_fork = nullptr;
     float4* d_accum = nullptr; int accum_pixels = 0;
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
@@ -71,9 +72,16 @@ static void free_rmap(rlpt_ctx* c) {
     c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
     c->have_rmap = false; c->rm = RadianceDev{};
 }
+static void free_lanes(rlpt_ctx* c) {
+    for (auto& l : c->lanes) {
+        for (int k = 0; k < 2; ++k) { cudaFree(l.q[k].o); cudaFree(l.q[k].d); cudaFree(l.q[k].thr); cudaFree(l.q[k].meta); }
+        cudaFree(l.d_counts); if (l.done) cudaEventDestroy(l.done); if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    c->lanes.clear(); c->lane_capacity = 0; c->counts_len = 0; c->lane_spp = 0;
+}
 static void free_frame(rlpt_ctx* c) {
-    for (int k = 0; k < 2; ++k) { cudaFree(c->q[k].o); cudaFree(c->q[k].d); cudaFree(c->q[k].thr); cudaFree(c->q[k].meta); c->q[k] = PathQueue{}; }
-    cudaFree(c->d_counts); cudaFree(c->d_accum); c->d_counts = nullptr; c->d_accum = nullptr; c->queue_capacity = 0; c->accum_pixels = 0; c->counts_len = 0;
+    free_lanes(c);
+    cudaFree(c->d_accum); c->d_accum = nullptr; c->accum_pixels = 0;
 }
 
 // largest float f with (double)f*f < (double)max_dist: fabsf(delta) <= f is the reference's pow(delta,2) < max_dist
@@ -121,7 +129,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     c->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
-    CK(cudaMalloc(&c->d_dyn, sizeof(FrameDyn))); CK(cudaMemset(c->d_dyn, 0, sizeof(FrameDyn)));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8)); CK(cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
     CK(cudaMalloc(&c->d_cap_n, sizeof(int))); CK(cudaMemset(c->d_cap_n, 0, sizeof(int)));
     rlpt_config_default(&c->cfg);
@@ -138,7 +146,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c); free_rmap(c); free_frame(c);
-    cudaFree(c->d_stage); cudaFree(c->d_dyn); cudaFree(c->d_stats); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
+    cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
     delete c;
@@ -180,7 +188,7 @@ int rlpt_config_set(rlpt_ctx* c, const rlpt_config* cfg) {
     bool geometry_changed = cfg->width != c->cfg.width || cfg->height != c->cfg.height;
     c->cfg = *cfg;
     CK(cudaSetDevice(c->device));
-    if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); free_frame(c); }
+    if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); for (auto& l : c->lanes) if (l.stream) CK(cudaStreamSynchronize(l.stream)); free_frame(c); }
     if (c->have_scene) { int rc = choose_traversal(c, 0); if (rc) return rc; }
     if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.grid.accept_r = grid_accept_r(c->grid_h, c->rm.within_abs); }
     return RLPT_OK;
@@ -507,18 +515,35 @@ int rlpt_radiance_map_load_q(rlpt_ctx* c, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------------ frames
+// Lanes: the frame's spp are split into L equal slices (L = RLPT_LANES or 2, reduced until it divides spp and every
+// slice still holds >= 2^19 paths), each traced on its own stream with its own queues.
+static int choose_lanes(const rlpt_config& g) {
+    int want = 2;
+    if (const char* e = getenv("RLPT_LANES")) want = std::max(1, atoi(e));
+    int L = std::min(want, g.spp);
+    while (L > 1 && (g.spp % L != 0 || (double)g.width * g.height * (g.spp / L) < 524288.0)) --L;
+    return L;
+}
 static int ensure_frame_buffers(rlpt_ctx* c) {
     const rlpt_config& g = c->cfg;
-    size_t paths = (size_t)g.width * g.height * g.spp;
-    if (paths > c->queue_capacity) {
-        for (int k = 0; k < 2; ++k) { cudaFree(c->q[k].o); cudaFree(c->q[k].d); cudaFree(c->q[k].thr); cudaFree(c->q[k].meta); c->q[k] = PathQueue{}; }
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaMalloc(&c->q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&c->q[k].d, sizeof(float4) * paths));
-            CK(cudaMalloc(&c->q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&c->q[k].meta, sizeof(uint32_t) * paths));
+    const int L = choose_lanes(g), lane_spp = g.spp / L;
+    const size_t paths = (size_t)g.width * g.height * lane_spp;
+    if ((int)c->lanes.size() != L || paths > c->lane_capacity || c->counts_len < g.max_bounces + 2) {
+        CK(cudaStreamSynchronize(c->stream));
+        for (auto& l : c->lanes) if (l.stream) CK(cudaStreamSynchronize(l.stream));
+        free_lanes(c);
+        c->lanes.resize(L);
+        for (auto& l : c->lanes) {
+            CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+            for (int k = 0; k < 2; ++k) {
+                CK(cudaMalloc(&l.q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * paths));
+                CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * paths));
+            }
+            CK(cudaMalloc(&l.d_counts, sizeof(int) * (g.max_bounces + 2)));
         }
-        c->queue_capacity = paths;
+        c->lane_capacity = paths; c->counts_len = g.max_bounces + 2;
     }
-    if (c->counts_len < g.max_bounces + 2) { cudaFree(c->d_counts); CK(cudaMalloc(&c->d_counts, sizeof(int) * (g.max_bounces + 2))); c->counts_len = g.max_bounces + 2; }
+    c->lane_spp = lane_spp;
     if (c->accum_pixels != g.width * g.height) {
         cudaFree(c->d_accum); CK(cudaMalloc(&c->d_accum, sizeof(float4) * (size_t)g.width * g.height));
         CK(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)g.width * g.height, c->stream)); c->accum_pixels = g.width * g.height;
@@ -526,27 +551,36 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
     return RLPT_OK;
 }
 
-// Enqueue one frame of `method` (0 default, 1 SARSA): primary cast + (max_bounces-1) bounce launches, all asynchronous;
-// the live-ray count of every bounce stays on the device.
+// Enqueue one frame of `method` (0 default, 1 SARSA): per lane, primary cast + (max_bounces-1) bounce launches, all
+// asynchronous; the live-ray count of every bounce stays on the device. The lanes fork from and join back into the
+// context stream with events, so callers still see one ordered stream.
 static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     int rc = ensure_frame_buffers(c); if (rc) return rc;
     const rlpt_config& g = c->cfg;
     FrameDyn dyn{};
-    dyn.sample_base = (uint32_t)((c->frames_done * (uint64_t)g.world_size + (uint64_t)g.rank) * (uint64_t)g.spp);
+    const uint32_t frame_base = (uint32_t)((c->frames_done * (uint64_t)g.world_size + (uint64_t)g.rank) * (uint64_t)g.spp);
     dyn.learn = learn; dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
     dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
     dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
     dyn.capture_bounce = c->cap_bounce; dyn.capture_max = c->cap_bounce >= 0 ? c->cap_max : 0;
-    CK(cudaMemcpyAsync(c->d_dyn, &dyn, sizeof dyn, cudaMemcpyHostToDevice, c->stream));     // pageable source: staged before the call returns
-    CK(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * (g.max_bounces + 2), c->stream));
     FrameParams p{};
-    p.scene = c->scene; p.rm = c->rm; p.q[0] = c->q[0]; p.q[1] = c->q[1]; p.counts = c->d_counts; p.accum = c->d_accum; p.stats = c->d_stats;
-    p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n; p.dyn = c->d_dyn;
-    p.width = g.width; p.height = g.height; p.spp = g.spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
+    p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats;
+    p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n;
+    p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
     const int grid = c->n_sm * 8;
-    launch_primary(p, method, grid, c->smem_bytes, c->stream);
-    for (int b = 1; b < g.max_bounces; ++b) launch_bounce(p, method, b, grid, c->smem_bytes, c->stream);
-    c->launches += g.max_bounces;
+    CK(cudaEventRecord(c->ev_fork, c->stream));
+    for (size_t li = 0; li < c->lanes.size(); ++li) {
+        rlpt_ctx::Lane& l = c->lanes[li];
+        CK(cudaStreamWaitEvent(l.stream, c->ev_fork, 0));
+        CK(cudaMemsetAsync(l.d_counts, 0, sizeof(int) * (g.max_bounces + 2), l.stream));
+        p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts;
+        dyn.sample_base = frame_base + (uint32_t)li * (uint32_t)c->lane_spp;
+        launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream);
+        for (int b = 1; b < g.max_bounces; ++b) launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream);
+        CK(cudaEventRecord(l.done, l.stream));
+        CK(cudaStreamWaitEvent(c->stream, l.done, 0));
+    }
+    c->launches += (double)g.max_bounces * (double)c->lanes.size();
     CK(cudaGetLastError());
     c->frames_done++;
     c->cap_bounce = -1;
@@ -734,7 +768,7 @@ int rlpt_capture_rays(rlpt_ctx* c, int method, int bounce, float* org, float* di
     unsigned long long hs[8]; CK(cudaMemcpy(hs, c->d_stats, sizeof hs, cudaMemcpyDeviceToHost));
     int rc = enqueue_trace(c, method, 0); if (rc) return rc;
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
-    c->frames_done = saved_frames; c->launches -= c->cfg.max_bounces;
+    c->frames_done = saved_frames; c->launches -= (double)c->cfg.max_bounces * (double)c->lanes.size();
     if (!keep.empty()) CK(cudaMemcpy(c->d_accum, keep.data(), sizeof(float4) * keep.size(), cudaMemcpyHostToDevice));
     else CK(cudaMemset(c->d_accum, 0, sizeof(float4) * (size_t)c->accum_pixels));
     CK(cudaMemcpy(c->d_stats, hs, sizeof hs, cudaMemcpyHostToDevice));

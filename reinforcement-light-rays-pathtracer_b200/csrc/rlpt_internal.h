@@ -53,23 +53,24 @@ struct RadianceDev {
 //   thr = (throughput rgb, as_float(volume << 8 | sector))       meta = sample << 8 | bounce
 struct PathQueue { float4* o; float4* d; float4* thr; uint32_t* meta; };
 
-// per-frame values that change between launches of the same (graph-captured) kernel sequence live in device memory
+// per-frame, per-lane values; passed to the kernels by value
 struct FrameDyn {
     uint32_t sample_base; int learn;
     float cam_x, cam_y, cam_z, cy, sy, cx, sx; int rotated;
     int capture_bounce, capture_max;
 };
 
+// One lane = one slice of a frame's samples traced on its own stream with its own queues, so that the latency-bound
+// tail bounces of one slice overlap the wide early bounces of the next (DESIGN.md "Wavefront").
 struct FrameParams {
     SceneDev scene;
     RadianceDev rm;
     PathQueue q[2];
-    int* counts;                    // [max_bounces + 1] live paths entering each bounce
+    int* counts;                    // [max_bounces + 1] live paths entering each bounce (this lane)
     float4* accum;                  // [W*H] radiance sums (rgb) + sample count in w
     unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests
     float4* capture_o; float4* capture_d; int* capture_n;
-    const FrameDyn* dyn;
-    int width, height, spp, max_bounces;
+    int width, height, spp, max_bounces;     // spp = samples per pixel traced by this lane
     uint32_t seed;
     float env;
 };
@@ -77,8 +78,8 @@ struct FrameParams {
 constexpr int BLOCK = 256;
 
 // host-visible launchers (rlpt_kernels.cu)
-void launch_primary(const FrameParams& p, int method, int grid, size_t smem, cudaStream_t s);
-void launch_bounce(const FrameParams& p, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s);
+void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s);
 void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float threshold, int rebuild_only, cudaStream_t s);
 void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
                         unsigned long long* counters, size_t smem, cudaStream_t s);

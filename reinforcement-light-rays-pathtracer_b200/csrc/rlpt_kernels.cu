@@ -207,7 +207,7 @@ __device__ __forceinline__ void td_accumulate(const RadianceDev& rm, bool active
 // ------------------------------------------------------------------------------------------------ wavefront kernels
 // One bounce of one path. PRIMARY: the path is generated here (raygen fused with the first cast).
 template <bool STAGED, bool SARSA, bool PRIMARY>
-__global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameParams p, int bounce) {
+__global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameP
     const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
     unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0;
     const float H = (float)p.height;
-    const FrameDyn dyn = *p.dyn;
     const int n_round = (n_in + 31) & ~31;                        // whole warps stay together for the collectives
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool valid = i < n_in;
@@ -320,17 +319,17 @@ __global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameP
 }
 
 template <bool SARSA, bool PRIMARY>
-static void launch_bounce_t(const FrameParams& p, int bounce, int grid, size_t smem, cudaStream_t s) {
+static void launch_bounce_t(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     const SceneDev& sc = p.scene;
     bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
-    if (staged) k_bounce<true, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, bounce);
-    else k_bounce<false, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, bounce);
+    if (staged) k_bounce<true, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
+    else k_bounce<false, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
 }
-void launch_primary(const FrameParams& p, int method, int grid, size_t smem, cudaStream_t s) {
-    if (method == 1) launch_bounce_t<true, true>(p, 0, grid, smem, s); else launch_bounce_t<false, true>(p, 0, grid, smem, s);
+void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s) {
+    if (method == 1) launch_bounce_t<true, true>(p, dyn, 0, grid, smem, s); else launch_bounce_t<false, true>(p, dyn, 0, grid, smem, s);
 }
-void launch_bounce(const FrameParams& p, int method, int bounce, int grid, size_t smem, cudaStream_t s) {
-    if (method == 1) launch_bounce_t<true, false>(p, bounce, grid, smem, s); else launch_bounce_t<false, false>(p, bounce, grid, smem, s);
+void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s) {
+    if (method == 1) launch_bounce_t<true, false>(p, dyn, bounce, grid, smem, s); else launch_bounce_t<false, false>(p, dyn, bounce, grid, smem, s);
 }
 
 int kernels_set_smem_limit(size_t bytes) {
