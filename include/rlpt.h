@@ -178,6 +178,26 @@ typedef struct rlpt_stats_t {
 int rlpt_stats(rlpt_ctx* ctx, rlpt_stats_t* out);
 int rlpt_stats_reset(rlpt_ctx* ctx);
 
+/* --- Neural-Q network (DQN) ------------------------------------------------------------------------------ */
+/* The network of N/dq_network.cu:8-49: input = every scene vertex minus the query point (9 floats per triangle,
+ * G/deep_learning/nn_rendering_helpers.cu:280-298), 200-300-200-144 with ReLU after every layer, evaluated on the
+ * tensor cores (bf16 operands, fp32 accumulation; layer 1 in fp32). Parameters are the 8 DyNet blocks in file order
+ * (W1 b1 W2 b2 W3 b3 W4 b4), each W row-major [out][in]; total 200*k_in + 200 + 60000 + 300 + 60000 + 200 + 28800 + 144 floats. */
+/* replaces: Scene::vertices as the network's constant input (G/main.cu:171-176). Default when not called: the uploaded
+ * triangles, surfaces then lights, in v0 v1 v2 order. Call after rlpt_scene_upload. */
+int rlpt_dqn_set_vertices(rlpt_ctx* ctx, const float* vertices, int count);
+/* replaces: DQNetwork::initialize + DyNet's default Glorot initialiser (G/deep_learning/neural_q_pathtracer.cu:44-50) */
+int rlpt_dqn_init(rlpt_ctx* ctx, uint32_t seed);
+/* replaces: dynet::TextFileLoader::populate / TextFileSaver::save (neural_q_pathtracer.cu:55-59,191-196); same text format */
+int rlpt_dqn_load_text(rlpt_ctx* ctx, const char* path);
+int rlpt_dqn_save_text(rlpt_ctx* ctx, const char* path);
+int rlpt_dqn_param_count(rlpt_ctx* ctx, int* count, int* k_in);
+int rlpt_dqn_set_params(rlpt_ctx* ctx, const float* params, int count);
+int rlpt_dqn_get_params(rlpt_ctx* ctx, float* params, int count);
+/* replaces: convert_vertices_to_point_coord_system + network_inference + forward for a batch of query points
+ * (neural_q_pathtracer.cu:292-325). q: n*144 floats, row-major [point][action]. */
+int rlpt_dqn_forward(rlpt_ctx* ctx, const float* pos3, int n, float* q);
+
 /* --- measurement helpers (bench.py) ---------------------------------------------------------------------- */
 /* FP32 FMA microbenchmark on the context's GPU: returns achieved TFLOP/s (2 flop per FMA). */
 int rlpt_measure_fp32_peak(rlpt_ctx* ctx, double* tflops);

@@ -298,3 +298,60 @@ def to_rgb8(rgb_float):
     """SDLScreen::PutPixelSDL colour conversion (G/sdl/sdl_screen.cpp:96-108): uint32(clamp(255*c, 0, 255)), truncation."""
     c = np.nan_to_num(np.asarray(rgb_float, np.float32), nan=0.0)
     return np.clip(np.float32(255.0) * c, 0.0, 255.0).astype(np.uint32).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------- Neural-Q network (numpy restatement)
+DQN_ROWS = (200, 300, 200, 144)
+
+
+def dqn_shapes(k_in):
+    cols = (k_in, 200, 300, 200)
+    return [(DQN_ROWS[l], cols[l]) for l in range(4)]
+
+
+def dqn_split(params, k_in):
+    """flat parameter vector (W1 b1 W2 b2 W3 b3 W4 b4, W row-major [out][in]) -> [(W, b)] * 4"""
+    out, o = [], 0
+    for r, c in dqn_shapes(k_in):
+        W = np.asarray(params[o:o + r * c], np.float32).reshape(r, c); o += r * c
+        b = np.asarray(params[o:o + r], np.float32); o += r
+        out.append((W, b))
+    assert o == len(params)
+    return out
+
+
+def dqn_forward_numpy(params, vertices, pos):
+    """N/dq_network.cu:37-49 + N/fc_layer.cu:43-50 on the input of nn_rendering_helpers.cu:280-298:
+    x_i = vertices[i] - pos[i % 3]; h = relu(b + W h) four times (ReLU on the output layer too), all float32."""
+    vertices = np.asarray(vertices, np.float32).ravel(); pos = np.asarray(pos, np.float32).reshape(-1, 3)
+    h = vertices[None, :] - np.tile(pos, (1, len(vertices) // 3))
+    for W, b in dqn_split(params, len(vertices)):
+        h = np.maximum(h @ W.T + b[None, :], np.float32(0)).astype(np.float32)
+    return h
+
+
+def dynet_text_load(path):
+    """DyNet TextFileSaver dump -> flat parameter vector + k_in ("#Parameter# /_i {rows,cols} nbytes ZERO_GRAD", values column-major)"""
+    blocks = []
+    with open(path) as f:
+        lines = f.read().split("\n")
+    k_in = None
+    for i in range(0, 16, 2):
+        dims = [int(x) for x in lines[i][lines[i].index("{") + 1:lines[i].index("}")].split(",")]
+        vals = np.array(lines[i + 1].split(), np.float32)
+        if len(dims) == 2:
+            blocks.append(vals.reshape(dims[1], dims[0]).T.copy().ravel())         # column-major -> row-major
+            if i == 0:
+                k_in = dims[1]
+        else:
+            blocks.append(vals)
+    return np.concatenate(blocks).astype(np.float32), k_in
+
+
+def dynet_text_save(path, params, k_in):
+    with open(path, "w") as f:
+        for l, (W, b) in enumerate(dqn_split(params, k_in)):
+            f.write("#Parameter# /_%d {%d,%d} %d ZERO_GRAD\n" % (2 * l, W.shape[0], W.shape[1], W.size * 16 + 1))
+            f.write("".join("%+.8e " % v for v in W.T.ravel()) + "\n")
+            f.write("#Parameter# /_%d {%d} %d ZERO_GRAD\n" % (2 * l + 1, len(b), len(b) * 16 + 1))
+            f.write("".join("%+.8e " % v for v in b) + "\n")

@@ -5,6 +5,7 @@
 #include "../../include/rlpt.h"
 #include "rlpt_internal.h"
 #include "rlpt_radiance_host.h"
+#include "rlpt_dqn.h"
 
 #include <algorithm>
 #include <cmath>
@@ -48,6 +49,8 @@ struct rlpt_ctx {
     int *d_grid_start = nullptr, *d_grid_vol = nullptr; float4* d_grid_posn = nullptr; float grid_h = 0.f;
     float *d_q = nullptr, *d_cdf = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
+    // Neural-Q network
+    DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
     // wavefront state
     struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
     std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; cudaEvent_t ev_fork = nullptr;
@@ -136,6 +139,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
     upload_cell_cos(cs);
     int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin);
+    if (!lim) lim = dqn_set_smem_limit();
     if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
     *out = c;
     return RLPT_OK;
@@ -145,7 +149,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     if (!c) return RLPT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    free_scene(c); free_rmap(c); free_frame(c);
+    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq);
     cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
@@ -252,6 +256,7 @@ int rlpt_scene_upload(rlpt_ctx* c, const float* sv, const float* srgb, int ns, c
     c->scene = SceneDev{}; c->scene.tri = c->d_tri; c->scene.shade = c->d_shade; c->scene.bvh = c->d_bvh;
     c->scene.n_tri = n; c->scene.n_surf = ns; c->scene.n_light = nl; c->scene.n_nodes = n_nodes;
     c->have_scene = true;
+    c->dq_vertices.clear(); c->dq_vertices_custom = false; c->dq.ready = false;
     return choose_traversal(c, 0);
 }
 
@@ -512,6 +517,90 @@ int rlpt_radiance_map_load_q(rlpt_ctx* c, const char* path) {
     fclose(f);
     int rc = rlpt_radiance_map_set_q(c, q.data(), nullptr); if (rc) return rc;
     return rlpt_radiance_map_update_distributions(c);
+}
+
+// ------------------------------------------------------------------------------------------------ Neural-Q network
+static const std::vector<float>& dqn_vertices(rlpt_ctx* c) {
+    if (c->dq_vertices.empty()) { c->dq_vertices = c->h_surf_v; c->dq_vertices.insert(c->dq_vertices.end(), c->h_light_v.begin(), c->h_light_v.end()); }
+    return c->dq_vertices;
+}
+static int dqn_push(rlpt_ctx* c) {          // host parameters -> device, operands derived
+    const std::vector<float>& v = dqn_vertices(c);
+    if ((int)v.size() != c->dq_host.k_in) return fail(RLPT_ERR_ARG, "DQN input width " + std::to_string(c->dq_host.k_in) + " does not match the scene (" + std::to_string(v.size()) + " vertex floats)");
+    int rc = dqn_upload(c->dq, c->dq_host, v.data(), c->stream);
+    if (rc) return fail(RLPT_ERR_CUDA, std::string("DQN upload failed: ") + cudaGetErrorString((cudaError_t)rc));
+    return RLPT_OK;
+}
+int rlpt_dqn_set_vertices(rlpt_ctx* c, const float* vertices, int count) {
+    if (!c || !c->have_scene || !vertices) return fail(RLPT_ERR_ARG, "rlpt_dqn_set_vertices: upload a scene first");
+    if (count != 9 * (c->n_surf + c->n_light)) return fail(RLPT_ERR_ARG, "rlpt_dqn_set_vertices: expected 9 floats per triangle of the uploaded scene");
+    c->dq_vertices.assign(vertices, vertices + count); c->dq_vertices_custom = true; c->dq.ready = false;
+    return RLPT_OK;
+}
+int rlpt_dqn_init(rlpt_ctx* c, uint32_t seed) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_dqn_init: upload a scene first");
+    CK(cudaSetDevice(c->device));
+    dqn_init_glorot(c->dq_host, (int)dqn_vertices(c).size(), seed);
+    return dqn_push(c);
+}
+int rlpt_dqn_load_text(rlpt_ctx* c, const char* path) {
+    if (!c || !c->have_scene || !path) return fail(RLPT_ERR_ARG, "rlpt_dqn_load_text: upload a scene first");
+    CK(cudaSetDevice(c->device));
+    std::string err; if (dqn_load_text(c->dq_host, path, err)) return fail(RLPT_ERR_IO, "rlpt_dqn_load_text: " + err);
+    return dqn_push(c);
+}
+int rlpt_dqn_save_text(rlpt_ctx* c, const char* path) {
+    if (!c || !c->dq.ready || !path) return fail(RLPT_ERR_ARG, "rlpt_dqn_save_text: no network");
+    CK(cudaSetDevice(c->device));
+    int rc = dqn_download(c->dq, c->dq_host, c->stream); if (rc) return fail(RLPT_ERR_CUDA, "DQN download failed");
+    std::string err; if (dqn_save_text(c->dq_host, path, err)) return fail(RLPT_ERR_IO, "rlpt_dqn_save_text: " + err);
+    return RLPT_OK;
+}
+static int dqn_total(const DqnHost& h) { int n = 0; for (int l = 0; l < 4; ++l) n += DqnHost::rows(l) * h.cols(l) + DqnHost::rows(l); return n; }
+int rlpt_dqn_param_count(rlpt_ctx* c, int* count, int* k_in) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_dqn_param_count: upload a scene first");
+    DqnHost shape; shape.k_in = (int)dqn_vertices(c).size();
+    if (count) *count = dqn_total(shape); if (k_in) *k_in = shape.k_in;
+    return RLPT_OK;
+}
+int rlpt_dqn_set_params(rlpt_ctx* c, const float* params, int count) {
+    if (!c || !c->have_scene || !params) return fail(RLPT_ERR_ARG, "rlpt_dqn_set_params: upload a scene first");
+    CK(cudaSetDevice(c->device));
+    DqnHost& h = c->dq_host; h.k_in = (int)dqn_vertices(c).size();
+    if (count != dqn_total(h)) return fail(RLPT_ERR_ARG, "rlpt_dqn_set_params: wrong parameter count");
+    const float* p = params;
+    for (int l = 0; l < 4; ++l) { size_t nw = (size_t)DqnHost::rows(l) * h.cols(l); h.w[l].assign(p, p + nw); p += nw; h.b[l].assign(p, p + DqnHost::rows(l)); p += DqnHost::rows(l); }
+    return dqn_push(c);
+}
+int rlpt_dqn_get_params(rlpt_ctx* c, float* params, int count) {
+    if (!c || !c->dq.ready || !params) return fail(RLPT_ERR_ARG, "rlpt_dqn_get_params: no network");
+    CK(cudaSetDevice(c->device));
+    if (dqn_download(c->dq, c->dq_host, c->stream)) return fail(RLPT_ERR_CUDA, "DQN download failed");
+    const DqnHost& h = c->dq_host;
+    if (count != dqn_total(h)) return fail(RLPT_ERR_ARG, "rlpt_dqn_get_params: wrong parameter count");
+    float* p = params;
+    for (int l = 0; l < 4; ++l) { p = std::copy(h.w[l].begin(), h.w[l].end(), p); p = std::copy(h.b[l].begin(), h.b[l].end(), p); }
+    return RLPT_OK;
+}
+int rlpt_dqn_forward(rlpt_ctx* c, const float* pos3, int n, float* q) {
+    if (!c || !c->dq.ready) return fail(RLPT_ERR_ARG, "rlpt_dqn_forward: no network (rlpt_dqn_init / rlpt_dqn_load_text first)");
+    if (n < 0 || (n && (!pos3 || !q))) return fail(RLPT_ERR_ARG, "rlpt_dqn_forward: bad arguments");
+    if (n == 0) return RLPT_OK;
+    CK(cudaSetDevice(c->device));
+    std::vector<float4> h_pos(n); for (int i = 0; i < n; ++i) h_pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 0.f);
+    float4* d_pos = nullptr; float* d_q = nullptr;
+    CK(cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); CK(cudaMalloc(&d_q, sizeof(float) * (size_t)n * DQ_OUT));
+    CK(cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    DqnFwdParams p{}; p.pos = d_pos; p.n = n; p.c1 = c->dq.c1; p.m1 = c->dq.m1; p.b2 = c->dq.b[1]; p.b3 = c->dq.b[2]; p.b4 = c->dq.b[3];
+    p.w2p = c->dq.w2p; p.w3p = c->dq.w3p; p.w4p = c->dq.w4p; p.q = d_q; p.q_stride = n;
+    int rc = dqn_forward(c->dq, p, c->stream);
+    if (rc) { cudaFree(d_pos); cudaFree(d_q); return fail(RLPT_ERR_CUDA, std::string("rlpt_dqn_forward: launch failed: ") + cudaGetErrorString((cudaError_t)rc)); }
+    std::vector<float> qt((size_t)n * DQ_OUT);
+    CK(cudaMemcpyAsync(qt.data(), d_q, sizeof(float) * qt.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    for (int a = 0; a < DQ_OUT; ++a) for (int i = 0; i < n; ++i) q[(size_t)i * DQ_OUT + a] = qt[(size_t)a * n + i];     // action-major on the device
+    cudaFree(d_pos); cudaFree(d_q);
+    return RLPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ frames

@@ -1,0 +1,354 @@
+// rlpt_dqn.cu -- Neural-Q network forward pass on tcgen05 tensor cores (sm_100a), parameter handling, DyNet text IO.
+//
+// Replaces: convert_vertices_to_point_coord_system (G/deep_learning/nn_rendering_helpers.cu:280-298, which materialises
+// a K-float input per ray: 358 MB at 512^2 x 342) + DQNetwork::network_inference through DyNet
+// (N/dq_network.cu:37-49, called at G/deep_learning/neural_q_pathtracer.cu:321-325,440-444,494-499).
+//
+// One CTA = one tile of 128 rays = the M dimension of tcgen05.mma (cta_group::1), accumulators in TMEM (128 lanes x
+// 512 fp32 columns: layer 2 in columns [0,304), layer 3 in [304,512), layer 4 reuses [0,144)). Per tile:
+//   layer 1   fp32 on the CUDA cores, c1 - M1 x (rlpt_dqn.h), ReLU, written as the bf16 A operand into shared memory
+//   layer 2-4 weights stream from L2 in 64-row chunks with cp.async.bulk into a double-buffered B operand; one elected
+//             thread issues K/16 tcgen05.mma per chunk; tcgen05.commit signals mbarriers (buffer free / layer done);
+//             the epilogue reads TMEM with tcgen05.ld (thread t <-> lane t <-> ray t), adds the bias, applies ReLU and
+//             writes the next layer's A operand (bf16) straight back into shared memory -- activations never touch HBM
+//   output    Q values, fp32, action-major [144][n] so that producer and consumers are coalesced
+// Operand layout (both A and B): K-major, SWIZZLE_NONE canonical form: 8x8 core matrices of 128 contiguous bytes
+// (8 rows x 16 bytes), K-adjacent core matrices 128 bytes apart (LBO), 8-row groups K_pad*16 bytes apart (SBO).
+#include "rlpt_dqn.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace rlpt {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread for the whole CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units, version 1, no swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// byte offset of element (row, k) in a K-major canonical operand with K_pad columns
+__host__ __device__ __forceinline__ size_t operand_offset(int row, int k, int k_pad) {
+    return (size_t)(row >> 3) * ((size_t)k_pad * 16) + (size_t)(k >> 3) * 128 + (size_t)(row & 7) * 16 + (size_t)(k & 7) * 2;
+}
+
+// ------------------------------------------------------------------------------------------------ forward kernel
+constexpr uint32_t SM_A1 = 0;                                             // 128 x 208 bf16: layer-2 A, later layer-4 A
+constexpr uint32_t SM_A2 = SM_A1 + DQ_TILE * DQ_K2 * 2;                   // 128 x 304 bf16: layer-3 A
+constexpr uint32_t SM_B0 = SM_A2 + DQ_TILE * DQ_K3 * 2;                   // 64 x 304 bf16 (largest chunk)
+constexpr uint32_t SM_B1 = SM_B0 + DQ_CHUNK * DQ_K3 * 2;
+constexpr uint32_t SM_C1 = SM_B1 + DQ_CHUNK * DQ_K3 * 2;                  // fp32 constants
+constexpr uint32_t SM_M1 = SM_C1 + DQ_K2 * 4;
+constexpr uint32_t SM_BIAS2 = SM_M1 + DQ_K2 * 3 * 4;
+constexpr uint32_t SM_BIAS3 = SM_BIAS2 + DQ_N2 * 4;
+constexpr uint32_t SM_BIAS4 = SM_BIAS3 + DQ_N3 * 4;
+constexpr uint32_t SM_BAR = SM_BIAS4 + DQ_N4 * 4;                         // 5 mbarriers + the TMEM base address
+constexpr uint32_t SM_TOTAL = SM_BAR + 64;
+static_assert(SM_TOTAL <= 227 * 1024, "shared-memory budget");
+static_assert(SM_BAR % 8 == 0, "mbarrier alignment");
+
+struct LayerPipe {            // bookkeeping of the elected thread: which buffer a chunk uses and how often each barrier fired
+    uint32_t chunk = 0; uint32_t full_uses[2] = { 0, 0 }, free_uses[2] = { 0, 0 };
+};
+
+// One dense layer on the tensor cores: D[128 x n_pad] = A[128 x k_pad] * W[n_pad x k_pad]^T into TMEM columns [tmem_col, +n_pad).
+// Called by thread 0 only. Chunk c+1 is copied while chunk c multiplies.
+__device__ __forceinline__ void issue_layer(LayerPipe& lp, uint8_t* smem, uint64_t* b_full, uint64_t* b_free, uint64_t* layer_done,
+                                            uint32_t a_off, int k_pad, const __nv_bfloat16* wp, int n_pad, uint32_t tmem_base, uint32_t tmem_col) {
+    const int n_chunks = (n_pad + DQ_CHUNK - 1) / DQ_CHUNK;
+    auto copy = [&](int c) {
+        const uint32_t g = lp.chunk + (uint32_t)c, buf = g & 1u;
+        if (lp.free_uses[buf]) mbar_wait(&b_free[buf], (lp.free_uses[buf] - 1u) & 1u);       // the MMAs that read this buffer last have finished
+        const int rows = min(DQ_CHUNK, n_pad - c * DQ_CHUNK);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)k_pad * 2u;
+        mbar_expect_tx(&b_full[buf], bytes);
+        bulk_copy_g2s(smem + (buf ? SM_B1 : SM_B0), reinterpret_cast<const uint8_t*>(wp) + (size_t)c * DQ_CHUNK * k_pad * 2, bytes, &b_full[buf]);
+    };
+    copy(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t g = lp.chunk + (uint32_t)c, buf = g & 1u;
+        if (c + 1 < n_chunks) copy(c + 1);
+        mbar_wait(&b_full[buf], lp.full_uses[buf] & 1u); lp.full_uses[buf]++;
+        tc_fence_after();
+        const int rows = min(DQ_CHUNK, n_pad - c * DQ_CHUNK);
+        const uint32_t idesc = idesc_bf16(DQ_TILE, rows);
+        const uint32_t a_addr = smem_u32(smem + a_off), b_addr = smem_u32(smem + (buf ? SM_B1 : SM_B0));
+        const uint32_t d_addr = tmem_base + tmem_col + (uint32_t)c * DQ_CHUNK;
+        for (int k = 0; k < k_pad / 16; ++k)
+            umma_bf16(d_addr, smem_desc(a_addr + (uint32_t)k * 256u, 128u, (uint32_t)k_pad * 16u), smem_desc(b_addr + (uint32_t)k * 256u, 128u, (uint32_t)k_pad * 16u), idesc, k > 0);
+        umma_commit(&b_free[buf]); lp.free_uses[buf]++;
+    }
+    umma_commit(layer_done);
+    lp.chunk += (uint32_t)n_chunks;
+}
+
+// Epilogue of a hidden layer: TMEM -> (+bias, ReLU) -> bf16 A operand of the next layer; optionally also kept in HBM
+// feature-major for the backward pass. Thread t owns TMEM lane t = ray t of the tile.
+__device__ __forceinline__ void hidden_epilogue(uint8_t* smem, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad, const float* bias, uint32_t a_next_off, int k_pad_next,
+                                                int row, __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
+    for (int c0 = 0; c0 < n_pad; c0 += 16) {
+        uint32_t r[16]; tmem_ld16(tmem_lane_addr + tmem_col + (uint32_t)c0, r);
+        __nv_bfloat162 pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = fmaxf(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j], 0.f), b = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1], 0.f);
+            pk[j] = __floats2bfloat162_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[0]);
+        *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0 + 8, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[4]);
+        if (keep && ray_valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { keep[(size_t)(c0 + 2 * j) * keep_stride + ray] = pk[j].x; keep[(size_t)(c0 + 2 * j + 1) * keep_stride + ray] = pk[j].y; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constant__ DqnFwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_c1 = reinterpret_cast<float*>(smem + SM_C1); float* s_m1 = reinterpret_cast<float*>(smem + SM_M1);
+    float* s_b2 = reinterpret_cast<float*>(smem + SM_BIAS2); float* s_b3 = reinterpret_cast<float*>(smem + SM_BIAS3); float* s_b4 = reinterpret_cast<float*>(smem + SM_BIAS4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t *b_full = bars, *b_free = bars + 2, *layer_done = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int t = threadIdx.x, warp = t >> 5;
+
+    for (int i = t; i < DQ_K2; i += DQ_TILE) { s_c1[i] = i < DQ_H1 ? p.c1[i] : 0.f; for (int d = 0; d < 3; ++d) s_m1[3 * i + d] = i < DQ_H1 ? p.m1[3 * i + d] : 0.f; }
+    for (int i = t; i < DQ_N2; i += DQ_TILE) s_b2[i] = i < DQ_H2 ? p.b2[i] : 0.f;
+    for (int i = t; i < DQ_N3; i += DQ_TILE) s_b3[i] = i < DQ_H3 ? p.b3[i] : 0.f;
+    for (int i = t; i < DQ_N4; i += DQ_TILE) s_b4[i] = i < DQ_OUT ? p.b4[i] : 0.f;
+    if (t == 0) { mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(&b_free[0], 1); mbar_init(&b_free[1], 1); mbar_init(layer_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's 32 lanes
+
+    LayerPipe lp; uint32_t done_uses = 0;
+    const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int ray = tile * DQ_TILE + t; const bool valid = ray < p.n;
+        // ---- layer 1 (fp32): h1 = relu(c1 - M1 x), 8 outputs per 16-byte store into the A operand
+        float4 x = valid ? p.pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = 0; j0 < DQ_K2; j0 += 8) {
+            __nv_bfloat162 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = j0 + 2 * j, b = a + 1;
+                float ha = fmaxf(s_c1[a] - (s_m1[3 * a] * x.x + s_m1[3 * a + 1] * x.y + s_m1[3 * a + 2] * x.z), 0.f);
+                float hb = fmaxf(s_c1[b] - (s_m1[3 * b] * x.x + s_m1[3 * b + 1] * x.y + s_m1[3 * b + 2] * x.z), 0.f);
+                pk[j] = __floats2bfloat162_rn(ha, hb);
+            }
+            *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(t, j0, DQ_K2)) = *reinterpret_cast<uint4*>(&pk[0]);
+            if (p.h1t && valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { p.h1t[(size_t)(j0 + 2 * j) * p.h_stride + ray] = pk[j].x; p.h1t[(size_t)(j0 + 2 * j + 1) * p.h_stride + ray] = pk[j].y; }
+            }
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- layer 2: 200 -> 300
+        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K2, p.w2p, DQ_N2, tmem_base, 0); }
+        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
+        hidden_epilogue(smem, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, t, p.h2t, p.h_stride, ray, valid);
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- layer 3: 300 -> 200
+        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A2, DQ_K3, p.w3p, DQ_N3, tmem_base, DQ_N2); }
+        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
+        hidden_epilogue(smem, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, t, p.h3t, p.h_stride, ray, valid);
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        // ---- layer 4: 200 -> 144, ReLU on the output as well (N/dq_network.cu:17)
+        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K4, p.w4p, DQ_N4, tmem_base, 0); }
+        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
+        for (int c0 = 0; c0 < DQ_N4; c0 += 16) {
+            uint32_t r[16]; tmem_ld16(tmem_lane + (uint32_t)c0, r);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p.q[(size_t)(c0 + j) * p.q_stride + ray] = fmaxf(__uint_as_float(r[j]) + s_b4[c0 + j], 0.f);
+            }
+        }
+        tc_fence_before(); __syncthreads();       // TMEM and A1 are reused by the next tile
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+int dqn_set_smem_limit() { return (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); }
+
+int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
+    if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;
+    int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE;
+    k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_TILE, SM_TOTAL, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ operands from parameters
+// one thread per packed element: bf16 copy of W [n][k] (row-major fp32, n x k) into the canonical [n_pad][k_pad] operand, zero padding
+__global__ void k_pack_weights(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, __nv_bfloat16* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * k_pad) return;
+    int row = i / k_pad, col = i % k_pad;
+    float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + operand_offset(row, col, k_pad)) = __float2bfloat16_rn(v);
+}
+// c1 = b1 + W1 v, M1[:, d] = sum_{i % 3 == d} W1[:, i]; one warp per output row, fp32 with pairwise lane sums
+__global__ void k_layer1_operands(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ v, int k_in, float* __restrict__ c1, float* __restrict__ m1) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= DQ_H1) return;
+    float acc = 0.f, m[3] = { 0.f, 0.f, 0.f };
+    for (int i = lane; i < k_in; i += 32) { float w = w1[(size_t)row * k_in + i]; acc += w * v[i]; int d = i % 3; m[0] += d == 0 ? w : 0.f; m[1] += d == 1 ? w : 0.f; m[2] += d == 2 ? w : 0.f; }
+    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); for (int d = 0; d < 3; ++d) m[d] += __shfl_xor_sync(0xffffffffu, m[d], o); }
+    if (lane == 0) { c1[row] = b1[row] + acc; m1[3 * row] = m[0]; m1[3 * row + 1] = m[1]; m1[3 * row + 2] = m[2]; }
+}
+
+int dqn_refresh_operands(DqnDev& d, cudaStream_t s) {
+    k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);
+    k_pack_weights<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N2, DQ_K2, d.w2p);
+    k_pack_weights<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N3, DQ_K3, d.w3p);
+    k_pack_weights<<<(DQ_N4 * DQ_K4 + 255) / 256, 256, 0, s>>>(d.w[3], DQ_OUT, DQ_H3, DQ_N4, DQ_K4, d.w4p);
+    return (int)cudaGetLastError();
+}
+
+void dqn_free(DqnDev& d) {
+    for (int l = 0; l < 4; ++l) { cudaFree(d.w[l]); cudaFree(d.b[l]); d.w[l] = d.b[l] = nullptr; }
+    cudaFree(d.vertices); cudaFree(d.c1); cudaFree(d.m1); cudaFree(d.w2p); cudaFree(d.w3p); cudaFree(d.w4p);
+    d = DqnDev{};
+}
+int dqn_alloc(DqnDev& d, int k_in) {
+    dqn_free(d);
+    d.k_in = k_in;
+    DqnHost shape; shape.k_in = k_in;
+#define DQ_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+    for (int l = 0; l < 4; ++l) { DQ_CK(cudaMalloc(&d.w[l], sizeof(float) * (size_t)DqnHost::rows(l) * shape.cols(l))); DQ_CK(cudaMalloc(&d.b[l], sizeof(float) * DqnHost::rows(l))); }
+    DQ_CK(cudaMalloc(&d.vertices, sizeof(float) * (size_t)k_in)); DQ_CK(cudaMalloc(&d.c1, sizeof(float) * DQ_H1)); DQ_CK(cudaMalloc(&d.m1, sizeof(float) * DQ_H1 * 3));
+    DQ_CK(cudaMalloc(&d.w2p, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&d.w3p, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&d.w4p, 2 * (size_t)DQ_N4 * DQ_K4));
+    return 0;
+}
+int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s) {
+    if (d.k_in != h.k_in || !d.w[0]) { int rc = dqn_alloc(d, h.k_in); if (rc) return rc; }
+    for (int l = 0; l < 4; ++l) {
+        DQ_CK(cudaMemcpyAsync(d.w[l], h.w[l].data(), sizeof(float) * h.w[l].size(), cudaMemcpyHostToDevice, s));
+        DQ_CK(cudaMemcpyAsync(d.b[l], h.b[l].data(), sizeof(float) * h.b[l].size(), cudaMemcpyHostToDevice, s));
+    }
+    DQ_CK(cudaMemcpyAsync(d.vertices, vertices, sizeof(float) * (size_t)h.k_in, cudaMemcpyHostToDevice, s));
+    DQ_CK(cudaStreamSynchronize(s));
+    int rc = dqn_refresh_operands(d, s); if (rc) return rc;
+    d.ready = true;
+    return 0;
+}
+int dqn_download(const DqnDev& d, DqnHost& h, cudaStream_t s) {
+    h.k_in = d.k_in;
+    for (int l = 0; l < 4; ++l) {
+        h.w[l].resize((size_t)DqnHost::rows(l) * h.cols(l)); h.b[l].resize(DqnHost::rows(l));
+        DQ_CK(cudaMemcpyAsync(h.w[l].data(), d.w[l], sizeof(float) * h.w[l].size(), cudaMemcpyDeviceToHost, s));
+        DQ_CK(cudaMemcpyAsync(h.b[l].data(), d.b[l], sizeof(float) * h.b[l].size(), cudaMemcpyDeviceToHost, s));
+    }
+    DQ_CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host: init + DyNet text files
+// DyNet's default initialiser (ParameterInitGlorot, DyNet 2.x -- the reference pins no version): uniform in
+// [-s, s], s = sqrt(3 * n_dims) / sqrt(sum of dims): sqrt(6 / (rows + cols)) for a matrix, sqrt(3 / rows) for a bias vector.
+// The random stream is this library's own (splitmix64); training dynamics are "parity unpinned" by construction.
+void dqn_init_glorot(DqnHost& h, int k_in, uint32_t seed) {
+    h.k_in = k_in;
+    uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)(seed + 1u);
+    auto next = [&]() { st += 0x9E3779B97F4A7C15ull; uint64_t z = st; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return (float)((z >> 40) * (1.0 / 16777216.0)); };
+    for (int l = 0; l < 4; ++l) {
+        const int r = DqnHost::rows(l), c = h.cols(l);
+        h.w[l].resize((size_t)r * c); h.b[l].resize(r);
+        const float sw = std::sqrt(6.f / (float)(r + c)), sb = std::sqrt(3.f / (float)r);
+        for (float& x : h.w[l]) x = (2.f * next() - 1.f) * sw;
+        for (float& x : h.b[l]) x = (2.f * next() - 1.f) * sb;
+    }
+}
+
+// DyNet TextFileSaver: per parameter "#Parameter# /_i {rows,cols} nbytes ZERO_GRAD\n" then rows*cols values "%+.8e" separated by
+// spaces, column-major (Radiance_Map_Data/*.model; G/deep_learning/neural_q_pathtracer.cu:55-59,191-196)
+int dqn_load_text(DqnHost& h, const char* path, std::string& err) {
+    std::ifstream in(path);
+    if (!in.is_open()) { err = std::string("cannot open ") + path; return 1; }
+    std::string header, values;
+    for (int blk = 0; blk < 8; ++blk) {
+        if (!std::getline(in, header) || !std::getline(in, values)) { err = "truncated model file (expected 8 parameter blocks)"; return 1; }
+        int rows = 0, cols = 1; char name[64];
+        if (header.rfind("#Parameter#", 0) != 0) { err = "not a DyNet text model: " + header.substr(0, 40); return 1; }
+        const size_t lb = header.find('{'), rb = header.find('}');
+        if (lb == std::string::npos || rb == std::string::npos) { err = "bad header: " + header; return 1; }
+        (void)name;
+        if (sscanf(header.c_str() + lb, "{%d,%d}", &rows, &cols) < 1) { err = "bad dims: " + header; return 1; }
+        const int l = blk / 2; const bool is_w = blk % 2 == 0;
+        if (rows != DqnHost::rows(l)) { err = "unexpected layer shape in " + header; return 1; }
+        if (is_w && l == 0) h.k_in = cols;
+        if (is_w && cols != h.cols(l)) { err = "unexpected layer shape in " + header; return 1; }
+        std::vector<float>& dst = is_w ? h.w[l] : h.b[l];
+        const int c = is_w ? cols : 1;
+        dst.assign((size_t)rows * c, 0.f);
+        const char* sp = values.c_str(); char* end = nullptr;
+        for (int j = 0; j < c; ++j) for (int i = 0; i < rows; ++i) {            // column-major in the file
+            float v = strtof(sp, &end);
+            if (end == sp) { err = "too few values in block " + std::to_string(blk); return 1; }
+            dst[(size_t)i * c + j] = v; sp = end;
+        }
+    }
+    return 0;
+}
+int dqn_save_text(const DqnHost& h, const char* path, std::string& err) {
+    FILE* f = fopen(path, "w");
+    if (!f) { err = std::string("cannot open ") + path; return 1; }
+    for (int blk = 0; blk < 8; ++blk) {
+        const int l = blk / 2; const bool is_w = blk % 2 == 0;
+        const int rows = DqnHost::rows(l), c = is_w ? h.cols(l) : 1;
+        const std::vector<float>& src = is_w ? h.w[l] : h.b[l];
+        const long nbytes = (long)rows * c * 16 + 1;                               // 15 characters + separator per value, + newline (DyNet writes the byte count)
+        if (is_w) fprintf(f, "#Parameter# /_%d {%d,%d} %ld ZERO_GRAD\n", blk, rows, c, nbytes); else fprintf(f, "#Parameter# /_%d {%d} %ld ZERO_GRAD\n", blk, rows, nbytes);
+        for (int j = 0; j < c; ++j) for (int i = 0; i < rows; ++i) fprintf(f, "%+.8e ", src[(size_t)i * c + j]);
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    return 0;
+}
+
+}  // namespace rlpt

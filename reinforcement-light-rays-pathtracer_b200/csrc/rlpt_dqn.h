@@ -1,0 +1,58 @@
+// rlpt_dqn.h -- the Neural-Q network (DQN) of the reference: K -> 200 -> 300 -> 200 -> 144, ReLU after every layer
+// including the output (N/dq_network.cu:8-49, N/fc_layer.cu:29-72), on 5th-generation tensor cores (tcgen05).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+namespace rlpt {
+
+constexpr int DQ_H1 = 200, DQ_H2 = 300, DQ_H3 = 200, DQ_OUT = 144;
+// MMA shapes: K padded to a multiple of 16 (bf16 UMMA_K), N to a multiple of 16 (UMMA_N granularity at M = 128)
+constexpr int DQ_K2 = 208, DQ_N2 = 304, DQ_K3 = 304, DQ_N3 = 208, DQ_K4 = 208, DQ_N4 = 144;
+constexpr int DQ_TILE = 128;        // rays per CTA tile = UMMA_M = TMEM lanes
+constexpr int DQ_CHUNK = 64;        // weight rows (outputs) staged per shared-memory buffer
+
+// Host copy of the parameters in the reference's order (DyNet TextFileSaver blocks /_0 .. /_7), row-major [out][in].
+struct DqnHost {
+    int k_in = 0;                                   // input width: 9 floats per triangle (scene vertices) -- 342 Cornell, 918 archway
+    std::vector<float> w[4], b[4];                  // w[0]: 200 x k_in, w[1]: 300 x 200, w[2]: 200 x 300, w[3]: 144 x 200
+    static int rows(int l) { return l == 0 ? DQ_H1 : l == 1 ? DQ_H2 : l == 2 ? DQ_H3 : DQ_OUT; }
+    int cols(int l) const { return l == 0 ? k_in : l == 1 ? DQ_H1 : l == 2 ? DQ_H2 : DQ_H3; }
+};
+
+// Device state. fp32 master parameters (the optimiser works on these) and the operands derived from them:
+//   layer 1 is affine in the 3-vector x because the input is (v_i - x) for every scene vertex v_i (nn_rendering_helpers.cu:280-298):
+//   W1 (v - 1 (x) x) + b1 = c1 - M1 x with c1 = b1 + W1 v, M1[:, d] = sum of the columns i of W1 with i % 3 == d; evaluated in fp32.
+//   layers 2..4: bf16 copies in the tcgen05 shared-memory operand layout (K-major, no swizzle, 8x8 core matrices).
+struct DqnDev {
+    int k_in = 0;
+    float* w[4] = { nullptr, nullptr, nullptr, nullptr }; float* b[4] = { nullptr, nullptr, nullptr, nullptr };
+    float* vertices = nullptr;                      // [k_in] scene vertices, the network's constant input part
+    float *c1 = nullptr, *m1 = nullptr;             // [200], [200][3]
+    __nv_bfloat16 *w2p = nullptr, *w3p = nullptr, *w4p = nullptr;       // packed [N_pad][K_pad]
+    bool ready = false;
+};
+
+struct DqnFwdParams {
+    const float4* pos; int n;                       // ray positions (xyz)
+    const float *c1, *m1, *b2, *b3, *b4;
+    const __nv_bfloat16 *w2p, *w3p, *w4p;
+    float* q; int q_stride;                         // out: [144][q_stride], action-major (coalesced for producer and consumers)
+    __nv_bfloat16 *h1t, *h2t, *h3t; int h_stride;   // optional: activations kept for the backward pass, feature-major [K_pad][h_stride]
+};
+
+int dqn_alloc(DqnDev& d, int k_in);
+void dqn_free(DqnDev& d);
+int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s);       // copies parameters, derives operands
+int dqn_download(const DqnDev& d, DqnHost& h, cudaStream_t s);
+int dqn_refresh_operands(DqnDev& d, cudaStream_t s);                                       // after the parameters changed on the device
+int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s);                   // launches k_dqn_forward
+int dqn_set_smem_limit();
+void dqn_init_glorot(DqnHost& h, int k_in, uint32_t seed);
+int dqn_load_text(DqnHost& h, const char* path, std::string& err);
+int dqn_save_text(const DqnHost& h, const char* path, std::string& err);
+
+}  // namespace rlpt

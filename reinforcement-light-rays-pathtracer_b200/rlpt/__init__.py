@@ -44,6 +44,8 @@ SYMBOLS = [
     "rlpt_radiance_map_save_q", "rlpt_radiance_map_load_q", "rlpt_render_default", "rlpt_render_sarsa", "rlpt_sarsa_trace", "rlpt_sarsa_merge",
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
+    "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
+    "rlpt_dqn_forward",
 ]
 
 _lib = None
@@ -265,6 +267,41 @@ class Context:
         v = ctypes.c_double()
         self._ck(self.L.rlpt_measure_fp32_peak(self.h, ctypes.byref(v)))
         return v.value
+
+    # ---- Neural-Q network
+    def dqn_set_vertices(self, vertices):
+        v = _f32(vertices).ravel()
+        self._ck(self.L.rlpt_dqn_set_vertices(self.h, _p(v), len(v)))
+
+    def dqn_init(self, seed=1984):
+        self._ck(self.L.rlpt_dqn_init(self.h, ctypes.c_uint32(seed)))
+
+    def dqn_load_text(self, path):
+        self._ck(self.L.rlpt_dqn_load_text(self.h, path.encode()))
+
+    def dqn_save_text(self, path):
+        self._ck(self.L.rlpt_dqn_save_text(self.h, path.encode()))
+
+    def dqn_param_count(self):
+        n, k = ctypes.c_int(), ctypes.c_int()
+        self._ck(self.L.rlpt_dqn_param_count(self.h, ctypes.byref(n), ctypes.byref(k)))
+        return n.value, k.value
+
+    def dqn_set_params(self, params):
+        p = _f32(params).ravel()
+        self._ck(self.L.rlpt_dqn_set_params(self.h, _p(p), len(p)))
+
+    def dqn_get_params(self):
+        n, _ = self.dqn_param_count()
+        p = np.zeros(n, np.float32)
+        self._ck(self.L.rlpt_dqn_get_params(self.h, _p(p), n))
+        return p
+
+    def dqn_forward(self, pos):
+        pos = _f32(pos).reshape(-1, 3)
+        q = np.zeros((len(pos), CELLS), np.float32)
+        self._ck(self.L.rlpt_dqn_forward(self.h, _p(pos), len(pos), _p(q)))
+        return q
 
     def capture_rays(self, method, bounce, max_rays):
         org, dir = np.zeros((max_rays, 3), np.float32), np.zeros((max_rays, 3), np.float32)

@@ -1,0 +1,87 @@
+"""-m gpu: the Neural-Q network on the tensor cores against the float32 numpy restatement of the reference's network
+function (oracle/checkers.py::dqn_forward_numpy), driven by the reference's committed trained weights
+(tests/golden/dqn_cornell.npz <- Radiance_Map_Data/cornell_12_12.model). Tolerance: layers 2-4 run in bf16 with fp32
+accumulation (DyNet runs fp32), so outputs agree to about 1% of the row's largest Q value; stated at each assert."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dqn_golden():
+    return dict(np.load(os.path.join(GOLDEN, "dqn_cornell.npz")))
+
+
+def test_forward_matches_numpy_on_reference_weights(ctx, golden_scenes, dqn_golden):
+    from checkers import dqn_forward_numpy
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    n, k = ctx.dqn_param_count()
+    assert (n, k) == (218044, 342) and n == len(dqn_golden["params"])
+    ctx.dqn_set_params(dqn_golden["params"])
+    q = ctx.dqn_forward(dqn_golden["pos"])
+    ref = dqn_golden["q"]
+    scale = np.maximum(ref.max(1, keepdims=True), 1.0)
+    err = np.abs(q - ref) / scale
+    assert err.max() <= 3e-2 and np.median(err) <= 2e-3, (float(err.max()), float(np.median(err)))
+    assert np.mean(np.argmax(q, 1) == np.argmax(ref, 1)) >= 0.9                   # the greedy action survives bf16
+    # sizes around the 128-ray tile: 1, 127, 128, 129 points, and the empty batch
+    for m in (1, 127, 128, 129):
+        qm = ctx.dqn_forward(dqn_golden["pos"][:m])
+        assert np.array_equal(qm, q[:m])
+    assert ctx.dqn_forward(np.zeros((0, 3))).shape == (0, 144)
+    # fresh numpy evaluation at new points (not only the stored ones)
+    rs = np.random.RandomState(7)
+    pos = rs.uniform(-1, 1, (3000, 3)).astype(np.float32)
+    vertices = np.concatenate([s["sv"].ravel(), s["lv"].ravel()])
+    ref2 = dqn_forward_numpy(dqn_golden["params"], vertices, pos)
+    q2 = ctx.dqn_forward(pos)
+    # points anywhere in the cube are outside what the network was trained on (it only ever saw surface points): a few rows
+    # cancel heavily and amplify the bf16 rounding, so the bar here is on quantiles: median 0.3%, 99.9% of entries 5%, max 20%
+    e2 = np.abs(q2 - ref2) / np.maximum(ref2.max(1, keepdims=True), 1.0)
+    assert np.median(e2) <= 3e-3 and np.quantile(e2, 0.999) <= 5e-2 and e2.max() <= 0.2, (float(np.median(e2)), float(np.quantile(e2, 0.999)), float(e2.max()))
+
+
+def test_dynet_text_round_trip(ctx, golden_scenes, dqn_golden, tmp_path):
+    from checkers import dynet_text_load, dynet_text_save
+    load_scene(ctx, golden_scenes["cornell"])
+    p = str(tmp_path / "in.model")
+    dynet_text_save(p, dqn_golden["params"], 342)
+    assert open(p).readline().strip() == str(dqn_golden["header0"])               # byte-identical header to the reference's file
+    ctx.dqn_load_text(p)
+    assert np.array_equal(ctx.dqn_get_params(), dqn_golden["params"])
+    out = str(tmp_path / "out.model")
+    ctx.dqn_save_text(out)
+    assert open(out).read() == open(p).read()                                     # the library writes the same text DyNet does
+    back, k = dynet_text_load(out)
+    assert k == 342 and np.array_equal(back, dqn_golden["params"])
+
+
+def test_init_and_errors(ctx, golden_scenes, tmp_path):
+    import rlpt
+    with pytest.raises(rlpt.RlptError):
+        ctx.dqn_forward(np.zeros((4, 3)))                                         # no network yet
+    load_scene(ctx, golden_scenes["archway"])
+    n, k = ctx.dqn_param_count()
+    assert k == 918 and n == 333244
+    ctx.dqn_init(seed=3)
+    p = ctx.dqn_get_params()
+    w1 = p[:200 * 918]
+    assert abs(w1).max() <= np.sqrt(6.0 / (200 + 918)) + 1e-6 and w1.std() > 0.02   # Glorot uniform
+    q = ctx.dqn_forward(np.zeros((5, 3)))
+    assert np.isfinite(q).all() and (q >= 0).all()
+    with pytest.raises(rlpt.RlptError):
+        ctx.dqn_set_params(np.zeros(10))
+    with pytest.raises(rlpt.RlptError):
+        ctx.dqn_load_text(str(tmp_path / "missing.model"))
+    load_scene(ctx, golden_scenes["cornell"])                                     # a Cornell-sized file does not fit the archway scene and vice versa
+    bad = str(tmp_path / "arch.model")
+    from checkers import dynet_text_save
+    dynet_text_save(bad, p, 918)
+    with pytest.raises(rlpt.RlptError):
+        ctx.dqn_load_text(bad)
