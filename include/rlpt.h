@@ -198,6 +198,11 @@ int rlpt_dqn_get_params(rlpt_ctx* ctx, float* params, int count);
  * (neural_q_pathtracer.cu:292-325). q: n*144 floats, row-major [point][action]. */
 int rlpt_dqn_forward(rlpt_ctx* ctx, const float* pos3, int n, float* q);
 
+/* replaces: PretrainedPathtracer(frames, batch, screen, scene, camera, ...) (G/deep_learning/pre_trained_pathtracer.cu:10-491):
+ * path tracing with directions importance-sampled from the network's Q values, no learning. Each frame adds cfg.spp
+ * samples per pixel to the frame buffer. */
+int rlpt_render_pretrained(rlpt_ctx* ctx, int frames);
+
 /* --- measurement helpers (bench.py) ---------------------------------------------------------------------- */
 /* FP32 FMA microbenchmark on the context's GPU: returns achieved TFLOP/s (2 flop per FMA). */
 int rlpt_measure_fp32_peak(rlpt_ctx* ctx, double* tflops);

@@ -51,6 +51,7 @@ struct rlpt_ctx {
     RadianceDev rm{};
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
+    float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
     struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
     std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; cudaEvent_t ev_fork = nullptr;
@@ -149,7 +150,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     if (!c) return RLPT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq);
+    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq); cudaFree(c->d_nq_q);
     cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
@@ -747,6 +748,52 @@ int rlpt_render_sarsa_frozen(rlpt_ctx* c, int frames) {
     if (frames < 0) return fail(RLPT_ERR_ARG, "negative frame count");
     int rc = timed_begin(c); if (rc) return rc;
     for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_trace(c, 1, 0); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
+    return timed_end(c, frames);
+}
+
+// replaces: PretrainedPathtracer (G/deep_learning/pre_trained_pathtracer.cu:10-185 host loop, :186-378 render_frame). The
+// frame's samples are traced in slices of at most 2^21 paths (bounds the Q buffer: 144 floats per live path).
+static int enqueue_nq_inference(rlpt_ctx* c) {
+    int rc = ensure_frame_buffers(c); if (rc) return rc;
+    const rlpt_config& g = c->cfg;
+    int slice = c->lane_spp;
+    while (slice > 1 && ((double)g.width * g.height * slice > 2097152.0 || c->lane_spp % slice != 0)) --slice;
+    const size_t cap = (size_t)g.width * g.height * slice;
+    if (cap > c->nq_q_capacity) { cudaFree(c->d_nq_q); c->d_nq_q = nullptr; c->nq_q_capacity = 0; CK(cudaMalloc(&c->d_nq_q, sizeof(float) * DQ_OUT * cap)); c->nq_q_capacity = cap; }
+    FrameDyn dyn{};
+    const uint32_t frame_base = (uint32_t)((c->frames_done * (uint64_t)g.world_size + (uint64_t)g.rank) * (uint64_t)g.spp);
+    dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
+    dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
+    dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
+    rlpt_ctx::Lane& l = c->lanes[0];
+    FrameParams p{};
+    p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats; p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts;
+    p.width = g.width; p.height = g.height; p.spp = slice; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
+    DqnFwdParams fp{}; fp.c1 = c->dq.c1; fp.m1 = c->dq.m1; fp.b2 = c->dq.b[1]; fp.b3 = c->dq.b[2]; fp.b4 = c->dq.b[3];
+    fp.w2p = c->dq.w2p; fp.w3p = c->dq.w3p; fp.w4p = c->dq.w4p; fp.q = c->d_nq_q; fp.q_stride = (int)cap; fp.n = (int)cap;
+    const int grid = c->n_sm * 8;
+    for (int s0 = 0; s0 < g.spp; s0 += slice) {
+        dyn.sample_base = frame_base + (uint32_t)s0;
+        CK(cudaMemsetAsync(l.d_counts, 0, sizeof(int) * (g.max_bounces + 2), c->stream));
+        launch_nq_trace(p, dyn, 0, grid, c->smem_bytes, c->stream);
+        for (int b = 1; b < g.max_bounces; ++b) {
+            fp.pos = p.q[b & 1].o; fp.n_ptr = l.d_counts + b;
+            int frc = dqn_forward(c->dq, fp, c->stream);
+            if (frc) return fail(RLPT_ERR_CUDA, std::string("DQN forward launch failed: ") + cudaGetErrorString((cudaError_t)frc));
+            launch_nq_sample(p, dyn, b, c->d_nq_q, (int)cap, 0.f, nullptr, grid, c->stream);
+            launch_nq_trace(p, dyn, b, grid, c->smem_bytes, c->stream);
+        }
+        c->launches += 1.0 + 3.0 * (g.max_bounces - 1);
+    }
+    CK(cudaGetLastError());
+    c->frames_done++;
+    return RLPT_OK;
+}
+int rlpt_render_pretrained(rlpt_ctx* c, int frames) {
+    if (!c || !c->have_scene || !c->dq.ready) return fail(RLPT_ERR_ARG, "rlpt_render_pretrained: needs a scene and a network (rlpt_dqn_load_text / rlpt_dqn_init)");
+    if (frames < 0) return fail(RLPT_ERR_ARG, "rlpt_render_pretrained: negative frame count");
+    int rc = timed_begin(c); if (rc) return rc;
+    for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_nq_inference(c); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
     return timed_end(c, frames);
 }
 

@@ -166,9 +166,10 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's 32 lanes
 
     LayerPipe lp; uint32_t done_uses = 0;
-    const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE;
+    const int n_rays = p.n_ptr ? min(*p.n_ptr, p.n) : p.n;
+    const int n_tiles = (n_rays + DQ_TILE - 1) / DQ_TILE;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int ray = tile * DQ_TILE + t; const bool valid = ray < p.n;
+        const int ray = tile * DQ_TILE + t; const bool valid = ray < n_rays;
         // ---- layer 1 (fp32): h1 = relu(c1 - M1 x), 8 outputs per 16-byte store into the A operand
         float4 x = valid ? p.pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j0 = 0; j0 < DQ_K2; j0 += 8) {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
 int dqn_set_smem_limit() { return (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); }
 
 int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
-    if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;
+    if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
     int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE;
     k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_TILE, SM_TOTAL, s>>>(p);

@@ -38,6 +38,7 @@ struct DqnDev {
 
 struct DqnFwdParams {
     const float4* pos; int n;                       // ray positions (xyz)
+    const int* n_ptr;                               // when non-null the ray count is read from device memory (wavefront live count)
     const float *c1, *m1, *b2, *b3, *b4;
     const __nv_bfloat16 *w2p, *w3p, *w4p;
     float* q; int q_stride;                         // out: [144][q_stride], action-major (coalesced for producer and consumers)

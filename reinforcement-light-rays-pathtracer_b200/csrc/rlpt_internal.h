@@ -80,6 +80,9 @@ constexpr int BLOCK = 256;
 // host-visible launchers (rlpt_kernels.cu)
 void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s);
 void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+// Neural-Q wavefront (rlpt_kernels.cu): trace without sampling (the direction comes from the network), and the sampler
+void launch_nq_trace(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_nq_sample(const FrameParams& p, const FrameDyn& dyn, int bounce, const float* q, int q_stride, float epsilon, uint32_t* action_out, int grid, cudaStream_t s);
 void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float threshold, int rebuild_only, cudaStream_t s);
 void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
                         unsigned long long* counters, size_t smem, cudaStream_t s);

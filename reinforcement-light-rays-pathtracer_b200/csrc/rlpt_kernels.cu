@@ -332,11 +332,135 @@ void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bo
     if (method == 1) launch_bounce_t<true, false>(p, dyn, bounce, grid, smem, s); else launch_bounce_t<false, false>(p, dyn, bounce, grid, smem, s);
 }
 
+// ------------------------------------------------------------------------------------------------ Neural-Q wavefront
+// PretrainedPathtracer (G/deep_learning/pre_trained_pathtracer.cu:186-491) as a compacted wavefront: per bounce
+//   k_nq_trace  closest hit of every live path (initialise_ray :379-418 fused into bounce 0), throughput *= light power
+//               / diffuse_c/pi (trace_ray :420-491), terminated paths go to the frame buffer, survivors are compacted with
+//               their hit point (the network's query point) and surface id
+//   k_dqn_forward over the survivors' hit points (rlpt_dqn.cu)   [replaces :228-271]
+//   k_nq_sample importance-samples the next direction from Q(s, .) cos(theta) (importance_sample_direction,
+//               nn_rendering_helpers.cu:391-489) and applies cos(theta)/pdf to the throughput
+enum { PURPOSE_NQ = 2 };
+template <bool STAGED, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK) k_nq_trace(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
+    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
+    unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0;
+    const float H = (float)p.height;
+    const int n_round = (n_in + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n_in;
+        float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, tr = 1, tg = 1, tb = 1; uint32_t pixel = 0, sample = 0;
+        if (valid) {
+            if (PRIMARY) {
+                pixel = (uint32_t)(i / p.spp); sample = dyn.sample_base + (uint32_t)(i % p.spp);
+                float u0, u1, u2, u3; draw4(p.seed, pixel, sample, 0u, PURPOSE_CAMERA, u0, u1, u2, u3);
+                f3 d = camera_dir((int)(pixel / (uint32_t)p.height), (int)(pixel % (uint32_t)p.height), u0, u1, p.width, p.height, dyn.rotated != 0, dyn.cy, dyn.sy, dyn.cx, dyn.sx);
+                ox = dyn.cam_x; oy = dyn.cam_y; oz = dyn.cam_z; dx = d.x; dy = d.y; dz = d.z;
+                if (i % p.spp == 0) atomicAdd(&p.accum[pixel].w, (float)p.spp);
+            } else {
+                float4 a = qi.o[i], b = qi.d[i], c = qi.thr[i]; uint32_t m = qi.meta[i];
+                pixel = __float_as_uint(a.w); sample = m >> 8; tr = c.x; tg = c.y; tb = c.z;
+                ox = RLPT_FMA(RAY_EPS, b.x, a.x); oy = RLPT_FMA(RAY_EPS, b.y, a.y); oz = RLPT_FMA(RAY_EPS, b.z, a.z);      // position + dir * 0.00001f (:439)
+                f3 nn = normalize_ref(f3{ b.x, b.y, b.z }); dx = nn.x; dy = nn.y; dz = nn.z;
+            }
+        }
+        float t = T_MISS, sdx = 0, sdy = 0, sdz = 0; int gid = -1;
+        if (valid) closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        const bool surface = valid && gid >= 0 && gid < v.n_surf;
+        bool alive = false; float hx = 0, hy = 0, hz = 0;
+        if (valid && !surface) {
+            float lr = p.env, lg = p.env, lb = p.env;
+            if (gid >= v.n_surf) { float4 e = v.shade(4 * gid + 3); lr = e.x; lg = e.y; lb = e.z; }
+            lr *= tr; lg *= tg; lb *= tb;
+            if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + pixel, make_float4(lr, lg, lb, 0.f));
+            st_len += (unsigned)bounce + 1u; st_term++;
+            if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;
+        } else if (surface) {
+            if (bounce + 1 >= p.max_bounces) { st_len += (unsigned)p.max_bounces; st_term++; st_zero++; }     // out of bounces: contributes nothing (DESIGN.md deviation 8)
+            else {
+                hx = RLPT_FMA(sdx, t, ox); hy = RLPT_FMA(sdy, t, oy); hz = RLPT_FMA(sdz, t, oz);
+                float4 sC = v.shade(4 * gid + 3); tr *= sC.x; tg *= sC.y; tb *= sC.z;                      // BRDF = diffuse_c / pi (:476-480)
+                alive = true;
+            }
+        }
+        unsigned bal = __ballot_sync(full, alive);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.counts + bounce + 1, __popc(bal));
+            base = __shfl_sync(full, base, 0);
+            if (alive) {
+                int slot = base + __popc(bal & lanemask_lt());
+                qo.o[slot] = make_float4(hx, hy, hz, __uint_as_float(pixel));
+                qo.d[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(gid));
+                qo.thr[slot] = make_float4(tr, tg, tb, 0.f);
+                qo.meta[slot] = (sample << 8) | (uint32_t)(bounce + 1);
+            }
+        }
+    }
+    st_len = __reduce_add_sync(full, st_len); st_zero = __reduce_add_sync(full, st_zero); st_term = __reduce_add_sync(full, st_term);
+    if (lane == 0 && st_term) { atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term); }
+    n_tri = __reduce_add_sync(full, n_tri); n_box = __reduce_add_sync(full, n_box);
+    if (lane == 0 && (n_tri | n_box)) { atomicAdd(p.stats + 3, (unsigned long long)n_tri); atomicAdd(p.stats + 4, (unsigned long long)n_box); }
+}
+void launch_nq_trace(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
+    const SceneDev& sc = p.scene;
+    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    if (bounce == 0) { if (staged) k_nq_trace<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_nq_trace<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
+    else { if (staged) k_nq_trace<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_nq_trace<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
+}
+
+// One thread per live path of queue `bounce`. q: [144][q_stride] from k_dqn_forward. Weighting uses the cell-centre cosine
+// table (the reference draws a fresh random point in every cell just to weight it, :418-437; DESIGN.md deviation 7).
+// epsilon > 0: epsilon-greedy exploration (sample_batch_ray_directions_epsilon_greedy, :330-389); action_out (may be null)
+// receives the chosen cell per queue slot.
+__global__ void __launch_bounds__(BLOCK) k_nq_sample(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce,
+                                                     const float* __restrict__ q, int q_stride, float epsilon, uint32_t* __restrict__ action_out) {
+    const PathQueue qu = p.q[bounce & 1];
+    const int n = p.counts[bounce];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = qu.o[i], b = qu.d[i], c = qu.thr[i]; const uint32_t m = qu.meta[i];
+        const int gid = __float_as_int(b.w); const uint32_t pixel = __float_as_uint(a.w), sample = m >> 8;
+        float4 sN = __ldg(p.scene.shade + 4 * gid), sT = __ldg(p.scene.shade + 4 * gid + 1), sB = __ldg(p.scene.shade + 4 * gid + 2);
+        f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
+        float u0, u1, u2, u3; draw4(p.seed, pixel, sample, (uint32_t)bounce, PURPOSE_NQ, u0, u1, u2, u3);
+        int cell; float pdf;
+        if (u3 <= epsilon) {                                                   // explore: a uniformly chosen cell, pdf = RHO (:366-387, :30-36)
+            cell = min((int)(u0 * (float)CELLS), CELLS - 1); pdf = RHO;
+        } else {
+            float total = 0.f;
+            for (int k = 0; k < CELLS; ++k) total += __ldg(q + (size_t)k * q_stride + i) * c_cell_cos[k];
+            const bool dead = !(total > 0.f);                                 // ReLU on the output layer can zero a whole row: fall back to cosine weighting
+            if (dead) { total = 0.f; for (int k = 0; k < CELLS; ++k) total += c_cell_cos[k]; }
+            const float r = u0 * total; float run = 0.f, w = 0.f; cell = -1; int last = 0; float last_w = 0.f;
+            for (int k = 0; k < CELLS; ++k) {
+                w = (dead ? 1.f : __ldg(q + (size_t)k * q_stride + i)) * c_cell_cos[k]; run += w;
+                if (w > 0.f) { last = k; last_w = w; }
+                if (run > r && w > 0.f) { cell = k; break; }
+            }
+            if (cell < 0) { cell = last; w = last_w; }                          // r == total after rounding: the last cell with weight
+            pdf = RHO * ((w / total) / GRID_RHO);
+        }
+        f3 nd = grid_to_direction((float)(cell / GRID) + u1, (float)(cell % GRID) + u2, T, N, B);
+        const float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;
+        const float scale = cos_theta / pdf;
+        qu.d[i] = make_float4(nd.x, nd.y, nd.z, b.w);
+        qu.thr[i] = make_float4(c.x * scale, c.y * scale, c.z * scale, 0.f);
+        if (action_out) action_out[i] = (uint32_t)cell;
+    }
+}
+void launch_nq_sample(const FrameParams& p, const FrameDyn& dyn, int bounce, const float* q, int q_stride, float epsilon, uint32_t* action_out, int grid, cudaStream_t s) {
+    k_nq_sample<<<grid, BLOCK, 0, s>>>(p, dyn, bounce, q, q_stride, epsilon, action_out);
+}
+
 int kernels_set_smem_limit(size_t bytes) {
     cudaError_t e = cudaSuccess;
 #define RLPT_SET(k) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
     RLPT_SET((k_bounce<true, true, true>)); RLPT_SET((k_bounce<true, true, false>)); RLPT_SET((k_bounce<true, false, true>)); RLPT_SET((k_bounce<true, false, false>));
     RLPT_SET((k_bounce<false, true, true>)); RLPT_SET((k_bounce<false, true, false>)); RLPT_SET((k_bounce<false, false, true>)); RLPT_SET((k_bounce<false, false, false>));
+    RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));
 #undef RLPT_SET
     return (int)e;

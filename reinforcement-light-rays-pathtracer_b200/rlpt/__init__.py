@@ -45,7 +45,7 @@ SYMBOLS = [
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
     "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
-    "rlpt_dqn_forward",
+    "rlpt_dqn_forward", "rlpt_render_pretrained",
 ]
 
 _lib = None
@@ -224,6 +224,9 @@ class Context:
 
     def render_sarsa(self, frames=1):
         self._ck(self.L.rlpt_render_sarsa(self.h, int(frames)))
+
+    def render_pretrained(self, frames=1):
+        self._ck(self.L.rlpt_render_pretrained(self.h, int(frames)))
 
     def render_sarsa_frozen(self, frames=1):
         self._ck(self.L.rlpt_render_sarsa_frozen(self.h, int(frames)))

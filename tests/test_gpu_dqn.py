@@ -85,3 +85,27 @@ def test_init_and_errors(ctx, golden_scenes, tmp_path):
     dynet_text_save(bad, p, 918)
     with pytest.raises(rlpt.RlptError):
         ctx.dqn_load_text(bad)
+
+
+def test_pretrained_tracer_is_unbiased_and_guided(ctx, golden_scenes, dqn_golden):
+    """PretrainedPathtracer with the reference's trained Cornell network: importance sampling must not change the
+    expectation (image means equal the default path tracer's within Monte-Carlo error: 1.5% here, 32 spp at 256^2),
+    and must do what the thesis reports for Neural-Q -- fewer zero-contribution paths than uniform sampling. (Paths get LONGER
+    in the Cornell box: the network steers rays away from the open front, where uniform sampling loses most paths early.)"""
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    ctx.configure(width=256, height=256, spp=16, max_bounces=80); ctx.camera_set((0, 0, -3))
+    ctx.render_default(2); base = ctx.frame_download().copy(); st0 = ctx.stats()
+    ctx.frame_reset(); ctx.stats_reset()
+    ctx.dqn_set_params(dqn_golden["params"])
+    ctx.render_pretrained(2)
+    img = ctx.frame_download(); st1 = ctx.stats()
+    assert st1["paths"] == st0["paths"] == 256 * 256 * 32
+    assert np.isfinite(img).all()
+    assert np.allclose(img.mean(0), base.mean(0), rtol=1.5e-2), (img.mean(0), base.mean(0))
+    blk = lambda a: a.reshape(16, 16, 16, 16, 3).mean((1, 3))
+    assert np.abs(blk(img) - blk(base)).mean() <= 0.05 * blk(base).mean()
+    assert st1["zero_contribution_paths"] < st0["zero_contribution_paths"]
+    print("pretrained: path length %.2f vs %.2f, zero-contribution %.3f vs %.3f, %.1f Mpaths/s" % (
+        st1["path_length_sum"] / st1["paths"], st0["path_length_sum"] / st0["paths"], st1["zero_contribution_paths"] / st1["paths"],
+        st0["zero_contribution_paths"] / st0["paths"], st1["paths"] / st1["device_seconds"] / 1e6))
