@@ -198,6 +198,13 @@ int rlpt_dqn_get_params(rlpt_ctx* ctx, float* params, int count);
  * (neural_q_pathtracer.cu:292-325). q: n*144 floats, row-major [point][action]. */
 int rlpt_dqn_forward(rlpt_ctx* ctx, const float* pos3, int n, float* q);
 
+/* replaces: one optimiser step of the reference's training loop (G/deep_learning/neural_q_pathtracer.cu:476-512): forward
+ * of the states pos3 with training=true, loss = sum_b (target_b - Q(s_b)[action_b])^2 (dynet::pick, pow, sum_batches),
+ * backward, AdamTrainer::update (DyNet defaults). apply_update = 0 computes loss and gradients only. loss may be NULL. */
+int rlpt_dqn_train_batch(rlpt_ctx* ctx, const float* pos3, const uint32_t* actions, const float* targets, int n, int apply_update, float* loss);
+/* gradients of the last rlpt_dqn_train_batch in parameter order (tests) */
+int rlpt_dqn_get_grads(rlpt_ctx* ctx, float* grads, int count);
+
 /* replaces: PretrainedPathtracer(frames, batch, screen, scene, camera, ...) (G/deep_learning/pre_trained_pathtracer.cu:10-491):
  * path tracing with directions importance-sampled from the network's Q values, no learning. Each frame adds cfg.spp
  * samples per pixel to the frame buffer. */

@@ -355,3 +355,66 @@ def dynet_text_save(path, params, k_in):
             f.write("".join("%+.8e " % v for v in W.T.ravel()) + "\n")
             f.write("#Parameter# /_%d {%d} %d ZERO_GRAD\n" % (2 * l + 1, len(b), len(b) * 16 + 1))
             f.write("".join("%+.8e " % v for v in b) + "\n")
+
+
+def bf16_round(a):
+    """round-to-nearest-even to bfloat16, returned as float32 (what __float2bfloat16_rn does)"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
+
+
+def dqn_loss_and_grads_numpy(params, vertices, pos, actions, targets, bf16=False):
+    """G/deep_learning/neural_q_pathtracer.cu:476-512 in float64 numpy: loss = sum_b (target_b - Q(s_b)[a_b])^2 and its
+    gradient w.r.t. every parameter (flat, parameter order). ReLU follows every layer, the output included.
+    bf16=True rounds exactly what the tensor-core path rounds (weights of layers 2-4, hidden activations, deltas, the query
+    point in the layer-1 weight gradient) so that ReLU masks agree and the comparison can be tight."""
+    r = bf16_round if bf16 else (lambda a: a)
+    vertices = np.asarray(vertices, np.float64).ravel(); pos = np.asarray(pos, np.float64).reshape(-1, 3)
+    layers = [(W.astype(np.float64), b.astype(np.float64)) for W, b in dqn_split(params, len(vertices))]
+    x0 = vertices[None, :] - np.tile(pos, (1, len(vertices) // 3))
+    hs = [x0]
+    for l, (W, b) in enumerate(layers):
+        Wl = W if l == 0 else r(W).astype(np.float64)
+        pre = hs[-1] @ Wl.T + b[None, :]
+        if l == 0 and bf16:
+            pre = pre.astype(np.float32).astype(np.float64)
+        h = np.maximum(pre, 0.0)
+        hs.append(r(h).astype(np.float64) if l < 3 else h.astype(np.float32).astype(np.float64) if bf16 else h)
+    q = hs[-1]; n = len(pos); idx = np.arange(n); a = np.asarray(actions, np.int64); t = np.asarray(targets, np.float64)
+    qa = q[idx, a]
+    loss = float(((t - qa) ** 2).sum())
+    g = 2.0 * (qa - t) * (qa > 0)
+    W4 = layers[3][0]
+    gw4 = np.zeros_like(W4); gb4 = np.zeros(W4.shape[0])
+    np.add.at(gw4, a, g[:, None] * hs[3] * (hs[3] > 0)); np.add.at(gb4, a, g)
+    d3 = r(g[:, None] * W4[a] * (hs[3] > 0)).astype(np.float64)
+    d2 = r((d3 @ r(layers[2][0]).astype(np.float64)) * (hs[2] > 0)).astype(np.float64)
+    d1 = r((d2 @ r(layers[1][0]).astype(np.float64)) * (hs[1] > 0)).astype(np.float64)
+    gw3, gb3 = d3.T @ hs[2], d3.sum(0)
+    gw2, gb2 = d2.T @ hs[1], d2.sum(0)
+    if bf16:                                                         # rank-3 form with the query point rounded to bf16
+        s1 = d1.sum(0); G = d1.T @ r(pos).astype(np.float64)
+        gw1 = s1[:, None] * vertices[None, :] - np.tile(G, (1, len(vertices) // 3)); gb1 = s1
+    else:
+        gw1, gb1 = d1.T @ x0, d1.sum(0)
+    grads = [(gw1, gb1), (gw2, gb2), (gw3, gb3), (gw4, gb4)]
+    return loss, np.concatenate([np.concatenate([gw.ravel(), gb]) for gw, gb in grads]).astype(np.float32)
+
+
+class AdamNumpy:
+    """DyNet AdamTrainer defaults restated (lr 1e-3, beta 0.9 / 0.999, eps 1e-8, gradient clipping at norm 5). DyNet's source is
+    not in the image and the reference pins no version: parity unpinned, this is the published algorithm."""
+
+    def __init__(self, n, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, clip=5.0):
+        self.m, self.v, self.t = np.zeros(n), np.zeros(n), 0
+        self.lr, self.b1, self.b2, self.eps, self.clip = lr, b1, b2, eps, clip
+
+    def step(self, params, grads):
+        g = np.asarray(grads, np.float64); norm = np.sqrt((g * g).sum())
+        if self.clip > 0 and norm > self.clip:
+            g = g * (self.clip / norm)
+        self.t += 1
+        self.m = self.b1 * self.m + (1 - self.b1) * g; self.v = self.b2 * self.v + (1 - self.b2) * g * g
+        step = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        return (np.asarray(params, np.float64) - step * self.m / (np.sqrt(self.v) + self.eps)).astype(np.float32)

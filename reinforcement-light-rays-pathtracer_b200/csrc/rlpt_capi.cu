@@ -51,6 +51,7 @@ struct rlpt_ctx {
     RadianceDev rm{};
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
+    DqnTrain dq_train;
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
     struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
@@ -150,7 +151,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     if (!c) return RLPT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq); cudaFree(c->d_nq_q);
+    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq); dqn_train_free(c->dq_train); cudaFree(c->d_nq_q);
     cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
@@ -528,6 +529,7 @@ static const std::vector<float>& dqn_vertices(rlpt_ctx* c) {
 static int dqn_push(rlpt_ctx* c) {          // host parameters -> device, operands derived
     const std::vector<float>& v = dqn_vertices(c);
     if ((int)v.size() != c->dq_host.k_in) return fail(RLPT_ERR_ARG, "DQN input width " + std::to_string(c->dq_host.k_in) + " does not match the scene (" + std::to_string(v.size()) + " vertex floats)");
+    dqn_train_free(c->dq_train);                     // new parameters: fresh optimiser state
     int rc = dqn_upload(c->dq, c->dq_host, v.data(), c->stream);
     if (rc) return fail(RLPT_ERR_CUDA, std::string("DQN upload failed: ") + cudaGetErrorString((cudaError_t)rc));
     return RLPT_OK;
@@ -601,6 +603,46 @@ int rlpt_dqn_forward(rlpt_ctx* c, const float* pos3, int n, float* q) {
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
     for (int a = 0; a < DQ_OUT; ++a) for (int i = 0; i < n; ++i) q[(size_t)i * DQ_OUT + a] = qt[(size_t)a * n + i];     // action-major on the device
     cudaFree(d_pos); cudaFree(d_q);
+    return RLPT_OK;
+}
+
+static int dqn_hook(void* d_buf, uint64_t count, int dtype, void* stream, void* user) {
+    rlpt_ctx* c = (rlpt_ctx*)user;
+    return c->allreduce(d_buf, count, dtype, stream, c->allreduce_user);
+}
+int rlpt_dqn_train_batch(rlpt_ctx* c, const float* pos3, const uint32_t* actions, const float* targets, int n, int apply_update, float* loss) {
+    if (!c || !c->dq.ready) return fail(RLPT_ERR_ARG, "rlpt_dqn_train_batch: no network");
+    if (n <= 0 || !pos3 || !actions || !targets) return fail(RLPT_ERR_ARG, "rlpt_dqn_train_batch: bad arguments");
+    for (int i = 0; i < n; ++i) if (actions[i] >= (uint32_t)DQ_OUT) return fail(RLPT_ERR_ARG, "rlpt_dqn_train_batch: action index out of range");
+    CK(cudaSetDevice(c->device));
+    std::vector<float4> h_pos(n); for (int i = 0; i < n; ++i) h_pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 0.f);
+    float4* d_pos = nullptr; uint32_t* d_act = nullptr; float* d_tgt = nullptr;
+    CK(cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); CK(cudaMalloc(&d_act, 4 * (size_t)n)); CK(cudaMalloc(&d_tgt, 4 * (size_t)n));
+    CK(cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_act, actions, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream)); CK(cudaMemcpyAsync(d_tgt, targets, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    const bool dist = c->allreduce && c->cfg.world_size > 1;
+    int rc = dqn_train_batch(c->dq, c->dq_train, d_pos, d_act, d_tgt, n, apply_update != 0, dist ? dqn_hook : nullptr, c, c->stream);
+    float h_loss = 0.f;
+    if (!rc) { CK(cudaMemcpyAsync(&h_loss, c->dq_train.scalars, 4, cudaMemcpyDeviceToHost, c->stream)); }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_pos); cudaFree(d_act); cudaFree(d_tgt);
+    if (rc) return fail(rc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, rc == -2 ? "gradient all-reduce hook failed" : std::string("rlpt_dqn_train_batch: ") + cudaGetErrorString((cudaError_t)rc));
+    if (e != cudaSuccess) return fail(RLPT_ERR_CUDA, std::string("rlpt_dqn_train_batch: ") + cudaGetErrorString(e));
+    if (loss) *loss = h_loss;
+    return RLPT_OK;
+}
+int rlpt_dqn_get_grads(rlpt_ctx* c, float* grads, int count) {
+    if (!c || !c->dq.ready || !c->dq_train.gw[0] || !grads) return fail(RLPT_ERR_ARG, "rlpt_dqn_get_grads: no gradients (call rlpt_dqn_train_batch first)");
+    CK(cudaSetDevice(c->device));
+    DqnHost shape; shape.k_in = c->dq.k_in;
+    if (count != dqn_total(shape)) return fail(RLPT_ERR_ARG, "rlpt_dqn_get_grads: wrong parameter count");
+    CK(cudaStreamSynchronize(c->stream));
+    float* p = grads;
+    for (int l = 0; l < 4; ++l) {
+        const size_t nw = (size_t)DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
+        CK(cudaMemcpy(p, c->dq_train.gw[l], 4 * nw, cudaMemcpyDeviceToHost)); p += nw;
+        CK(cudaMemcpy(p, c->dq_train.gb[l], 4 * nb, cudaMemcpyDeviceToHost)); p += nb;
+    }
     return RLPT_OK;
 }
 

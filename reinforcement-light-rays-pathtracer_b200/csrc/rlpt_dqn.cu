@@ -24,6 +24,8 @@
 
 namespace rlpt {
 
+#define DQ_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-int dqn_set_smem_limit() { return (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); }
+int dqn_gemm_set_smem_limit();
+int dqn_set_smem_limit() { int rc = (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); return rc ? rc : dqn_gemm_set_smem_limit(); }
 
 int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
     if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
@@ -260,7 +263,6 @@ int dqn_alloc(DqnDev& d, int k_in) {
     dqn_free(d);
     d.k_in = k_in;
     DqnHost shape; shape.k_in = k_in;
-#define DQ_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
     for (int l = 0; l < 4; ++l) { DQ_CK(cudaMalloc(&d.w[l], sizeof(float) * (size_t)DqnHost::rows(l) * shape.cols(l))); DQ_CK(cudaMalloc(&d.b[l], sizeof(float) * DqnHost::rows(l))); }
     DQ_CK(cudaMalloc(&d.vertices, sizeof(float) * (size_t)k_in)); DQ_CK(cudaMalloc(&d.c1, sizeof(float) * DQ_H1)); DQ_CK(cudaMalloc(&d.m1, sizeof(float) * DQ_H1 * 3));
     DQ_CK(cudaMalloc(&d.w2p, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&d.w3p, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&d.w4p, 2 * (size_t)DQ_N4 * DQ_K4));
@@ -351,5 +353,265 @@ int dqn_save_text(const DqnHost& h, const char* path, std::string& err) {
     fclose(f);
     return 0;
 }
+
+}  // namespace rlpt
+
+// ================================================================================================ training
+namespace rlpt {
+
+// ------------------------------------------------------------------------------------------------ generic tcgen05 GEMM
+// C[M x N] (+)= A[M x K] * B[N x K]^T; A, B bf16 with K contiguous (row strides lda, ldb, multiples of 8), C fp32 row-major.
+// CTA tile 128 x BN (BN <= 160, multiple of 16), K in chunks of 64 through two shared-memory stages; grid.z splits K,
+// partial tiles are combined with atomicAdd (C zeroed by the caller) -- used for the backward pass, where M or K is the batch.
+constexpr int GM_KC = 64, GM_BN = 160;
+constexpr uint32_t GM_A = 0, GM_B = GM_A + 2 * DQ_TILE * GM_KC * 2, GM_BAR = GM_B + 2 * GM_BN * GM_KC * 2, GM_TOTAL = GM_BAR + 64;
+
+__global__ void __launch_bounds__(DQ_TILE, 1) k_gemm_bf16_tn(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                              int M, int N, int K, int k_per_split) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_BAR);          // [0,1]: stage free (MMAs done), [2]: all done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const int t = threadIdx.x, warp = t >> 5;
+    const int m0 = blockIdx.x * DQ_TILE, n0 = blockIdx.y * GM_BN, bn = min(GM_BN, N - n0);
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    uint32_t uses[2] = { 0, 0 };
+    const uint32_t idesc = idesc_bf16(DQ_TILE, bn);
+    int chunk = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += GM_KC, ++chunk) {
+        const int st = chunk & 1;
+        if (uses[st]) mbar_wait(&bars[st], (uses[st] - 1u) & 1u);         // the MMAs that read this stage have completed
+        uint8_t* sa = smem + GM_A + st * (DQ_TILE * GM_KC * 2); uint8_t* sb = smem + GM_B + st * (GM_BN * GM_KC * 2);
+        {   // A: thread t stages row m0 + t, 64 k-values = 8 x 16 bytes
+            const int m = m0 + t; const bool ok = m < M;
+            const uint4* src = reinterpret_cast<const uint4*>(A + (size_t)(ok ? m : 0) * lda + k0);
+#pragma unroll
+            for (int j = 0; j < GM_KC / 8; ++j) {
+                uint4 v = (ok && k0 + 8 * j < k_end) ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sa + operand_offset(t, 8 * j, GM_KC)) = v;
+            }
+        }
+        for (int r = t; r < bn; r += DQ_TILE) {
+            const uint4* src = reinterpret_cast<const uint4*>(B + (size_t)(n0 + r) * ldb + k0);
+#pragma unroll
+            for (int j = 0; j < GM_KC / 8; ++j) {
+                uint4 v = (k0 + 8 * j < k_end) ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sb + operand_offset(r, 8 * j, GM_KC)) = v;
+            }
+        }
+        fence_proxy_async(); tc_fence_before(); __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+            for (int k = 0; k < GM_KC / 16; ++k)
+                umma_bf16(tmem_base, smem_desc(a_addr + (uint32_t)k * 256u, 128u, GM_KC * 16u), smem_desc(b_addr + (uint32_t)k * 256u, 128u, GM_KC * 16u), idesc, (chunk | k) != 0);
+            umma_commit(&bars[st]);
+        }
+        uses[st]++;
+    }
+    if (t == 0) umma_commit(&bars[2]);
+    mbar_wait(&bars[2], 0); tc_fence_after();
+    const int m = m0 + t; const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool split = gridDim.z > 1;
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+        uint32_t r[16]; tmem_ld16(lane_addr + (uint32_t)c0, r);
+        if (m < M && chunk > 0) {
+            float* dst = C + (size_t)m * ldc + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j, __uint_as_float(r[j])); else dst[j] = __uint_as_float(r[j]); }
+        }
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s) {
+    int k_per = ((K + k_splits - 1) / k_splits + GM_KC - 1) / GM_KC * GM_KC; if (k_per < GM_KC) k_per = GM_KC;
+    const int zs = (K + k_per - 1) / k_per;
+    dim3 grid((M + DQ_TILE - 1) / DQ_TILE, (N + GM_BN - 1) / GM_BN, zs);
+    k_gemm_bf16_tn<<<grid, DQ_TILE, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ element-wise pieces
+__global__ void k_transpose_bf16(const float* __restrict__ w, int rows, int cols, int out_rows_pad, int out_cols_pad, __nv_bfloat16* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;                       // out[c][r] = w[r][c], zero padded to [out_rows_pad][out_cols_pad]
+    if (i >= out_rows_pad * out_cols_pad) return;
+    int c = i / out_cols_pad, r = i % out_cols_pad;
+    out[i] = __float2bfloat16_rn((c < cols && r < rows) ? w[(size_t)r * cols + c] : 0.f);
+}
+// batch inputs for the gradient GEMMs: xt rows (x, y, z, 1), the "ones" rows of h1t / h2t, zero padding rows
+__global__ void k_train_prepare(const float4* __restrict__ pos, int n, int S, __nv_bfloat16* __restrict__ xt, __nv_bfloat16* __restrict__ h1t, __nv_bfloat16* __restrict__ h2t, __nv_bfloat16* __restrict__ h3t) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const bool ok = i < n; float4 x = ok ? pos[i] : make_float4(0, 0, 0, 0);
+    const __nv_bfloat16 one = __float2bfloat16_rn(ok ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
+    xt[i] = __float2bfloat16_rn(x.x); xt[(size_t)S + i] = __float2bfloat16_rn(x.y); xt[(size_t)2 * S + i] = __float2bfloat16_rn(x.z); xt[(size_t)3 * S + i] = one;
+    for (int r = 4; r < 16; ++r) xt[(size_t)r * S + i] = zero;
+    if (!ok) {                                                             // rays past n are not written by the forward kernel
+        for (int r = 0; r < DQ_K2; ++r) { h1t[(size_t)r * S + i] = zero; h3t[(size_t)r * S + i] = zero; }
+        for (int r = 0; r < DQ_K3; ++r) h2t[(size_t)r * S + i] = zero;
+    } else {
+        h1t[(size_t)DQ_H1 * S + i] = one; h2t[(size_t)DQ_H2 * S + i] = one;
+    }
+}
+// output-layer delta (one action per ray): g = d/dq (target - q_a)^2 * relu'(q_a); delta3 = g W4[a, :] relu'(h3);
+// dW4[a, :] += g h3, db4[a] += g; loss accumulated. One thread per ray.
+__global__ void k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, const float* __restrict__ targets, int n, int S,
+                         const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t,
+                         float* __restrict__ gw4, float* __restrict__ gb4, float* __restrict__ scalars) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    float g = 0.f; int a = 0; float loss = 0.f;
+    if (i < n) {
+        a = (int)actions[i]; const float qa = q[(size_t)a * S + i], diff = qa - targets[i];
+        loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f;
+    }
+    for (int j = 0; j < DQ_K4; ++j) {
+        float h = (i < n && j < DQ_H3) ? __bfloat162float(h3t[(size_t)j * S + i]) : 0.f;
+        float d = (g != 0.f && h > 0.f) ? g * __ldg(w4 + (size_t)a * DQ_H3 + j) : 0.f;
+        __nv_bfloat16 db = __float2bfloat16_rn(d);
+        d3[(size_t)i * DQ_K4 + j] = db; d3t[(size_t)j * S + i] = db;
+        if (g != 0.f && h > 0.f) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
+    }
+    if (g != 0.f) atomicAdd(gb4 + a, g);
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(scalars, loss);
+}
+// hidden-layer delta: d = pre * relu'(h); written ray-major (next data GEMM's A) and feature-major (weight-gradient GEMM's A)
+__global__ void k_delta_hidden(const float* __restrict__ pre, int ld_pre, const __nv_bfloat16* __restrict__ ht, int S, int n_feat, int k_pad,
+                               __nv_bfloat16* __restrict__ d_ray, __nv_bfloat16* __restrict__ d_feat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= S) return;
+    float d = 0.f;
+    if (j < n_feat) { float h = __bfloat162float(ht[(size_t)j * S + i]); d = h > 0.f ? pre[(size_t)i * ld_pre + j] : 0.f; }
+    __nv_bfloat16 db = __float2bfloat16_rn(d);
+    if (d_ray) d_ray[(size_t)i * k_pad + j] = db;
+    d_feat[(size_t)j * S + i] = db;
+}
+// gather the gradient of every parameter from the GEMM outputs; W1 through the rank-3 identity dW1[j][i] = db1_j v_i - G[j][i % 3]
+__global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __restrict__ dw2x, const float* __restrict__ dg, const float* __restrict__ v, int k_in,
+                                float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = DQ_H1 * k_in, n2 = DQ_H2 * DQ_H1, n3 = DQ_H3 * DQ_H2;
+    if (i < n1) { int j = i / k_in, c = i % k_in; gw1[i] = dg[j * 16 + 3] * v[c] - dg[j * 16 + c % 3]; return; }
+    i -= n1;
+    if (i < n2) { int r = i / DQ_H1, c = i % DQ_H1; gw2[i] = dw2x[(size_t)r * DQ_K2 + c]; return; }
+    i -= n2;
+    if (i < n3) { int r = i / DQ_H2, c = i % DQ_H2; gw3[i] = dw3x[(size_t)r * DQ_K3 + c]; return; }
+    i -= n3;
+    if (i < DQ_H1) { gb1[i] = dg[i * 16 + 3]; return; }
+    i -= DQ_H1;
+    if (i < DQ_H2) { gb2[i] = dw2x[(size_t)i * DQ_K2 + DQ_H1]; return; }
+    i -= DQ_H2;
+    if (i < DQ_H3) gb3[i] = dw3x[(size_t)i * DQ_K3 + DQ_H2];
+}
+__global__ void k_sqnorm(const float* __restrict__ g, int n, float* __restrict__ out) {
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += g[i] * g[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+// Adam as DyNet's AdamTrainer applies it: gradient scaled by min(1, clip / ||g||), m and v updated, step size
+// lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
+__global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n, const float* __restrict__ scalars,
+                       float clip, float beta1, float beta2, float eps, float step_size) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float norm = sqrtf(scalars[1]); const float scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
+    const float gi = g[i] * scale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi, vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    x[i] -= step_size * mi / (sqrtf(vi) + eps);
+}
+
+void dqn_train_free(DqnTrain& t) {
+    for (int l = 0; l < 4; ++l) { cudaFree(t.gw[l]); cudaFree(t.gb[l]); cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
+    cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
+    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars);
+    t = DqnTrain{};
+}
+int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
+    const int S = (capacity + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    DqnHost shape; shape.k_in = d.k_in;
+    const bool fresh = t.gw[0] == nullptr;
+    if (fresh) {
+        for (int l = 0; l < 4; ++l) {
+            const size_t nw = (size_t)DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
+            DQ_CK(cudaMalloc(&t.gw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.gb[l], 4 * nb)); DQ_CK(cudaMalloc(&t.mw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.mb[l], 4 * nb));
+            DQ_CK(cudaMalloc(&t.vw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.vb[l], 4 * nb));
+            DQ_CK(cudaMemset(t.mw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.mb[l], 0, 4 * nb)); DQ_CK(cudaMemset(t.vw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.vb[l], 0, 4 * nb));
+        }
+        DQ_CK(cudaMalloc(&t.dw3x, 4 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.dw2x, 4 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.dg, 4 * (size_t)DQ_K2 * 16));
+        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4));
+        t.step = 0;
+    }
+    if (S > t.capacity) {
+        cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt); cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q);
+        DQ_CK(cudaMalloc(&t.h1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.h2t, 2 * (size_t)DQ_K3 * S)); DQ_CK(cudaMalloc(&t.h3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.xt, 2 * (size_t)16 * S));
+        DQ_CK(cudaMalloc(&t.d3, 2 * (size_t)S * DQ_K4)); DQ_CK(cudaMalloc(&t.d2, 2 * (size_t)S * DQ_K3)); DQ_CK(cudaMalloc(&t.d3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.d2t, 2 * (size_t)DQ_K3 * S));
+        DQ_CK(cudaMalloc(&t.d1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.p2, 4 * (size_t)S * DQ_N2)); DQ_CK(cudaMalloc(&t.p1, 4 * (size_t)S * DQ_N3)); DQ_CK(cudaMalloc(&t.q, 4 * (size_t)DQ_OUT * S));
+        t.capacity = S;
+    }
+    return 0;
+}
+static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
+    // W3 is [200][300]: W3^T as [304][208] (row = layer-2 unit, K = layer-3 unit); W2 is [300][200]: W2^T as [208][304]
+    k_transpose_bf16<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N2, DQ_K2, t.w3t);
+    k_transpose_bf16<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N3, DQ_K3, t.w2t);
+    return (int)cudaGetLastError();
+}
+
+int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s) {
+    if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
+    int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
+    const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    DqnHost shape; shape.k_in = d.k_in;
+    if (t.step == 0 || true) { rc = refresh_transposes(d, t, s); if (rc) return rc; }
+    for (int l = 0; l < 4; ++l) { DQ_CK(cudaMemsetAsync(t.gw[l], 0, 4 * (size_t)DqnHost::rows(l) * shape.cols(l), s)); DQ_CK(cudaMemsetAsync(t.gb[l], 0, 4 * (size_t)DqnHost::rows(l), s)); }
+    DQ_CK(cudaMemsetAsync(t.dw3x, 0, 4 * (size_t)DQ_N3 * DQ_K3, s)); DQ_CK(cudaMemsetAsync(t.dw2x, 0, 4 * (size_t)DQ_N2 * DQ_K2, s)); DQ_CK(cudaMemsetAsync(t.dg, 0, 4 * (size_t)DQ_K2 * 16, s));
+    DQ_CK(cudaMemsetAsync(t.scalars, 0, 4 * 4, s));
+    // forward, activations kept
+    DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
+    fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
+    rc = dqn_forward(d, fp, s); if (rc) return rc;
+    k_train_prepare<<<(S + 127) / 128, 128, 0, s>>>(pos, n, S, t.xt, t.h1t, t.h2t, t.h3t);
+    // backward: data path
+    k_delta3<<<(S + 127) / 128, 128, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+    rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, DQ_N2, S, DQ_N2, DQ_K4, 1, s); if (rc) return rc;                  // [S x 208] x [304 x 208]^T
+    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, DQ_N2, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
+    rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, DQ_N3, S, DQ_N3, DQ_K3, 1, s); if (rc) return rc;                  // [S x 304] x [208 x 304]^T
+    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K2), 128, 0, s>>>(t.p1, DQ_N3, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
+    // backward: weight gradients, K = the batch, split over CTAs
+    const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
+    rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, s); if (rc) return rc;                      // [208 x S] x [304 x S]^T
+    rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, s); if (rc) return rc;                      // [304 x S] x [208 x S]^T
+    rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
+    const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
+    k_collect_grads<<<(n_collect + 255) / 256, 256, 0, s>>>(t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.gw[0], t.gb[0], t.gw[1], t.gb[1], t.gw[2], t.gb[2]);
+    if (allreduce) {
+        for (int l = 0; l < 4; ++l) {
+            if (allreduce(t.gw[l], (uint64_t)DqnHost::rows(l) * shape.cols(l), 0, (void*)s, allreduce_user)) return -2;
+            if (allreduce(t.gb[l], (uint64_t)DqnHost::rows(l), 0, (void*)s, allreduce_user)) return -2;
+        }
+        if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
+    }
+    if (!apply_update) return (int)cudaGetLastError();
+    for (int l = 0; l < 4; ++l) { k_sqnorm<<<64, 256, 0, s>>>(t.gw[l], DqnHost::rows(l) * shape.cols(l), t.scalars + 1); k_sqnorm<<<1, 256, 0, s>>>(t.gb[l], DqnHost::rows(l), t.scalars + 1); }
+    t.step++;
+    const float step_size = t.lr * std::sqrt(1.f - std::pow(t.beta2, (float)t.step)) / (1.f - std::pow(t.beta1, (float)t.step));
+    for (int l = 0; l < 4; ++l) {
+        const int nw = DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
+        k_adam<<<(nw + 255) / 256, 256, 0, s>>>(d.w[l], t.gw[l], t.mw[l], t.vw[l], nw, t.scalars, t.clip, t.beta1, t.beta2, t.eps, step_size);
+        k_adam<<<(nb + 255) / 256, 256, 0, s>>>(d.b[l], t.gb[l], t.mb[l], t.vb[l], nb, t.scalars, t.clip, t.beta1, t.beta2, t.eps, step_size);
+    }
+    rc = dqn_refresh_operands(d, s); if (rc) return rc;
+    return (int)cudaGetLastError();
+}
+
+int dqn_gemm_set_smem_limit() { return (int)cudaFuncSetAttribute(k_gemm_bf16_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_TOTAL); }
 
 }  // namespace rlpt

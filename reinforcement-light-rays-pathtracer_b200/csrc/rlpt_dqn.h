@@ -45,6 +45,34 @@ struct DqnFwdParams {
     __nv_bfloat16 *h1t, *h2t, *h3t; int h_stride;   // optional: activations kept for the backward pass, feature-major [K_pad][h_stride]
 };
 
+// Training state: gradients, Adam moments (DyNet AdamTrainer defaults: lr 1e-3, beta1 0.9, beta2 0.999, eps 1e-8, gradient
+// clipping at norm 5), batch activations. Layouts for a batch of n rays, S = n rounded up to 128:
+//   h1t [208][S], h2t [304][S], h3t [208][S]  bf16, feature-major (k_dqn_forward keeps them); rows 200 of h1t and 300 of h2t
+//   are set to one so that the weight-gradient GEMMs also produce the bias gradients; xt [16][S] = (x, y, z, 1, 0...)
+//   d3 [S][208], d2 [S][304] ray-major and d3t [208][S], d2t [304][S], d1t [208][S] feature-major deltas (bf16)
+struct DqnTrain {
+    int capacity = 0;                               // S the buffers were allocated for
+    float *gw[4] = { nullptr, nullptr, nullptr, nullptr }, *gb[4] = { nullptr, nullptr, nullptr, nullptr };      // gradients
+    float *mw[4] = { nullptr, nullptr, nullptr, nullptr }, *mb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam first moments
+    float *vw[4] = { nullptr, nullptr, nullptr, nullptr }, *vb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam second moments
+    float *dw3x = nullptr, *dw2x = nullptr, *dg = nullptr;      // GEMM outputs: [208][304] (col 300 = db3), [304][208] (col 200 = db2), [208][16] (cols 0-2 = G, col 3 = db1)
+    __nv_bfloat16 *w3t = nullptr, *w2t = nullptr;   // transposed bf16 copies: W3^T [304][208], W2^T [208][304]
+    __nv_bfloat16 *h1t = nullptr, *h2t = nullptr, *h3t = nullptr, *xt = nullptr;
+    __nv_bfloat16 *d3 = nullptr, *d2 = nullptr, *d3t = nullptr, *d2t = nullptr, *d1t = nullptr;
+    float *p2 = nullptr, *p1 = nullptr;             // pre-activation deltas [S][304], [S][208] (fp32 GEMM outputs)
+    float* q = nullptr;                             // [144][S] predictions of the batch
+    float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm
+    unsigned long long step = 0;
+    float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
+};
+int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
+void dqn_train_free(DqnTrain& t);
+// One optimiser step on a batch (G/deep_learning/neural_q_pathtracer.cu:476-512): forward with kept activations, loss
+// sum_b (target_b - Q(s_b)[a_b])^2, backward, Adam update, operands refreshed. pos/actions/targets are device pointers.
+// all-reduce hook (may be null): sums the gradient buffers across ranks before the update.
+typedef int (*dqn_allreduce_fn)(void* d_buf, uint64_t count, int dtype, void* cuda_stream, void* user);
+int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s);
 int dqn_alloc(DqnDev& d, int k_in);
 void dqn_free(DqnDev& d);
 int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s);       // copies parameters, derives operands

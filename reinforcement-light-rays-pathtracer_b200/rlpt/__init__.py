@@ -45,7 +45,7 @@ SYMBOLS = [
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
     "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
-    "rlpt_dqn_forward", "rlpt_render_pretrained",
+    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_get_grads",
 ]
 
 _lib = None
@@ -305,6 +305,19 @@ class Context:
         q = np.zeros((len(pos), CELLS), np.float32)
         self._ck(self.L.rlpt_dqn_forward(self.h, _p(pos), len(pos), _p(q)))
         return q
+
+    def dqn_train_batch(self, pos, actions, targets, apply_update=True):
+        pos = _f32(pos).reshape(-1, 3)
+        a = np.ascontiguousarray(actions, dtype=np.uint32); t = _f32(targets)
+        loss = ctypes.c_float()
+        self._ck(self.L.rlpt_dqn_train_batch(self.h, _p(pos), _p(a), _p(t), len(pos), int(bool(apply_update)), ctypes.byref(loss)))
+        return loss.value
+
+    def dqn_get_grads(self):
+        n, _ = self.dqn_param_count()
+        g = np.zeros(n, np.float32)
+        self._ck(self.L.rlpt_dqn_get_grads(self.h, _p(g), n))
+        return g
 
     def capture_rays(self, method, bounce, max_rays):
         org, dir = np.zeros((max_rays, 3), np.float32), np.zeros((max_rays, 3), np.float32)

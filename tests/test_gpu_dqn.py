@@ -109,3 +109,68 @@ def test_pretrained_tracer_is_unbiased_and_guided(ctx, golden_scenes, dqn_golden
     print("pretrained: path length %.2f vs %.2f, zero-contribution %.3f vs %.3f, %.1f Mpaths/s" % (
         st1["path_length_sum"] / st1["paths"], st0["path_length_sum"] / st0["paths"], st1["zero_contribution_paths"] / st1["paths"],
         st0["zero_contribution_paths"] / st0["paths"], st1["paths"] / st1["device_seconds"] / 1e6))
+
+
+def _tensor_report(g, ref, k_in):
+    from checkers import dqn_shapes
+    out, o = [], 0
+    for r, c in dqn_shapes(k_in):
+        for n in (r * c, r):
+            a, b = g[o:o + n].astype(np.float64), ref[o:o + n].astype(np.float64); o += n
+            cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30)); rel = float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+            out.append((cos, rel))
+    return out
+
+
+def test_training_step_gradients_match_numpy(ctx, golden_scenes, dqn_golden):
+    """Loss and every parameter gradient of one batch against the numpy restatement.
+    (1) against numpy with the same bf16 roundings the tensor-core path applies (operands of the layer 2-4 GEMMs, deltas):
+        ReLU masks agree, so the bar is tight -- each tensor within 2% relative L2, cosine >= 0.9995, loss within 0.5%;
+    (2) against plain float64 numpy (what DyNet's fp32 graph computes up to rounding): a hidden unit whose pre-activation is
+        within bf16 rounding of zero flips its ReLU mask and contributes a whole term, so the bar is cosine >= 0.99, 15%."""
+    from checkers import dqn_loss_and_grads_numpy
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    vertices = np.concatenate([s["sv"].ravel(), s["lv"].ravel()])
+    ctx.dqn_set_params(dqn_golden["params"])
+    rs = np.random.RandomState(11)
+    for n in (300, 4096):                                          # a ragged batch and the reference's batch size
+        pos = dqn_golden["pos"][rs.randint(0, len(dqn_golden["pos"]), n)]
+        actions = rs.randint(0, 144, n).astype(np.uint32)
+        targets = (rs.rand(n) * 1500).astype(np.float32)
+        loss = ctx.dqn_train_batch(pos, actions, targets, apply_update=False)
+        g = ctx.dqn_get_grads()
+        b_loss, b_g = dqn_loss_and_grads_numpy(dqn_golden["params"], vertices, pos, actions, targets, bf16=True)
+        assert abs(loss - b_loss) <= 5e-3 * b_loss, (loss, b_loss)
+        rep = _tensor_report(g, b_g, 342)
+        assert all(c >= 0.9995 and r <= 2e-2 for c, r in rep), rep
+        ref_loss, ref_g = dqn_loss_and_grads_numpy(dqn_golden["params"], vertices, pos, actions, targets)
+        assert abs(loss - ref_loss) <= 1e-2 * ref_loss, (loss, ref_loss)
+        rep = _tensor_report(g, ref_g, 342)
+        assert all(c >= 0.99 and r <= 0.15 for c, r in rep), rep
+    assert np.array_equal(ctx.dqn_get_params(), dqn_golden["params"])              # apply_update=False left the weights alone
+
+
+def test_adam_training_tracks_numpy_and_reduces_loss(ctx, golden_scenes, dqn_golden):
+    from checkers import AdamNumpy, dqn_loss_and_grads_numpy
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    vertices = np.concatenate([s["sv"].ravel(), s["lv"].ravel()])
+    ctx.dqn_init(seed=5)
+    p0 = ctx.dqn_get_params()
+    rs = np.random.RandomState(2)
+    pos = dqn_golden["pos"][:512]; actions = rs.randint(0, 144, 512).astype(np.uint32); targets = (rs.rand(512) * 3 + 1).astype(np.float32)
+    opt = AdamNumpy(len(p0)); p_ref = p0.copy(); losses, ref_losses = [], []
+    for it in range(20):
+        losses.append(ctx.dqn_train_batch(pos, actions, targets))
+        l, g = dqn_loss_and_grads_numpy(p_ref, vertices, pos, actions, targets); ref_losses.append(l)
+        p_ref = opt.step(p_ref, g)
+    p = ctx.dqn_get_params()
+    assert losses[-1] < 0.7 * losses[0] and ref_losses[-1] < 0.7 * ref_losses[0], (losses[0], losses[-1], ref_losses[0], ref_losses[-1])
+    # the two optimisation trajectories start identical and separate slowly (bf16 forward/backward vs float64): the first 8
+    # losses agree to 2%, afterwards only the trend is compared
+    assert np.allclose(losses[:8], ref_losses[:8], rtol=2e-2), (losses, ref_losses)
+    assert 0.5 <= losses[-1] / ref_losses[-1] <= 2.0, (losses, ref_losses)
+    # Adam moves every parameter by about lr per step: after 20 steps the two trajectories stay within a few lr of each other
+    moved = np.abs(p - p0); assert moved.max() <= 20 * 1.05e-3 + 1e-6 and moved.mean() > 1e-3
+    assert np.mean(np.abs(p - p_ref) <= 6e-3) >= 0.9
