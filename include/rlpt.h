@@ -210,6 +210,14 @@ int rlpt_dqn_get_grads(rlpt_ctx* ctx, float* grads, int count);
  * samples per pixel to the frame buffer. */
 int rlpt_render_pretrained(rlpt_ctx* ctx, int frames);
 
+/* replaces: NeuralQPathtracer(frames, batch_size, screen, scene, camera, argc, argv) (G/deep_learning/neural_q_pathtracer.cu:5-600):
+ * train the network while rendering. Each frame makes cfg.spp passes over all pixels; every bounce of a pass performs
+ * ceil(width*height / batch) sequential optimiser steps (batch = 4096 in G/main.cu:116-118). With an all-reduce hook and
+ * world_size > 1 the gradients of every step are summed across ranks. */
+int rlpt_render_neuralq(rlpt_ctx* ctx, int frames, int batch);
+/* the loss summed over the last frame ("loss" of nn_training_stats.txt, neural_q_pathtracer.cu:578-583) */
+int rlpt_neuralq_last_loss(rlpt_ctx* ctx, double* loss);
+
 /* --- measurement helpers (bench.py) ---------------------------------------------------------------------- */
 /* FP32 FMA microbenchmark on the context's GPU: returns achieved TFLOP/s (2 flop per FMA). */
 int rlpt_measure_fp32_peak(rlpt_ctx* ctx, double* tflops);

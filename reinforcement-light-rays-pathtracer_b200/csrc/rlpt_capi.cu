@@ -52,6 +52,8 @@ struct rlpt_ctx {
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
     DqnTrain dq_train;
+    NqTrainState nqt{}; int nqt_n = 0; float *d_nqt_qcur = nullptr, *d_nqt_qnext = nullptr, *d_nqt_targets = nullptr, *d_nqt_loss = nullptr; int nqt_batch = 0;
+    float nq_epsilon = 0.05f; double nq_loss_total = 0.0;     // EPSILON_START (G/constants/deep_learning_settings.h:5)
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
     struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
@@ -84,8 +86,13 @@ static void free_lanes(rlpt_ctx* c) {
     }
     c->lanes.clear(); c->lane_capacity = 0; c->counts_len = 0; c->lane_spp = 0;
 }
+static void free_nqt(rlpt_ctx* c) {
+    cudaFree(c->nqt.loc); cudaFree(c->nqt.sloc); cudaFree(c->nqt.dir); cudaFree(c->nqt.thr); cudaFree(c->nqt.state); cudaFree(c->nqt.reward); cudaFree(c->nqt.discount);
+    cudaFree(c->nqt.action); cudaFree(c->nqt.alive); cudaFree(c->d_nqt_qcur); cudaFree(c->d_nqt_qnext); cudaFree(c->d_nqt_targets); cudaFree(c->d_nqt_loss);
+    c->nqt = NqTrainState{}; c->nqt_n = 0; c->nqt_batch = 0; c->d_nqt_qcur = c->d_nqt_qnext = c->d_nqt_targets = c->d_nqt_loss = nullptr;
+}
 static void free_frame(rlpt_ctx* c) {
-    free_lanes(c);
+    free_lanes(c); free_nqt(c);
     cudaFree(c->d_accum); c->d_accum = nullptr; c->accum_pixels = 0;
 }
 
@@ -234,7 +241,7 @@ int rlpt_scene_upload(rlpt_ctx* c, const float* sv, const float* srgb, int ns, c
             for (int k = 0; k < 3; ++k) c->h_surf_nrm[3 * (size_t)g + k] = nrm[k];
             c->h_surf_class[g] = cls; lum_pi[g] = lum / PI_F;
             shade[4 * g] = make_float4(nrm[0], nrm[1], nrm[2], lum / PI_F);
-            shade[4 * g + 3] = make_float4(col[0] / PI_F, col[1] / PI_F, col[2] / PI_F, 0.f);     // BRDF = diffuse_c / (float)M_PI
+            shade[4 * g + 3] = make_float4(col[0] / PI_F, col[1] / PI_F, col[2] / PI_F, lum);     // BRDF = diffuse_c / (float)M_PI; w = luminance (Neural-Q discount)
         } else {
             shade[4 * g] = make_float4(nrm[0], nrm[1], nrm[2], lum);
             shade[4 * g + 3] = make_float4(col[0], col[1], col[2], 0.f);
@@ -838,6 +845,90 @@ int rlpt_render_pretrained(rlpt_ctx* c, int frames) {
     for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_nq_inference(c); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
     return timed_end(c, frames);
 }
+
+// replaces: NeuralQPathtracer (G/deep_learning/neural_q_pathtracer.cu:5-223 host loop, :226-600 render_frame). One frame =
+// cfg.spp passes over all pixels; in every pass each bounce samples directions from the network (epsilon-greedy), traces all
+// rays, and trains the network on the transitions in batches of `batch` rays (sequential optimiser steps, as the reference).
+// The live-ray count is read back once per bounce (the reference's rays_finished flag, :536).
+static int ensure_nqt(rlpt_ctx* c, int batch) {
+    const rlpt_config& g = c->cfg; const int n = g.width * g.height;
+    if (c->nqt_n == n && c->nqt_batch == batch && c->nqt.loc) return RLPT_OK;
+    CK(cudaStreamSynchronize(c->stream)); free_nqt(c);
+    NqTrainState& st = c->nqt; st.n = n;
+    CK(cudaMalloc(&st.loc, sizeof(float4) * n)); CK(cudaMalloc(&st.sloc, sizeof(float4) * n)); CK(cudaMalloc(&st.dir, sizeof(float4) * n)); CK(cudaMalloc(&st.thr, sizeof(float4) * n));
+    CK(cudaMalloc(&st.state, 4 * (size_t)n)); CK(cudaMalloc(&st.reward, 4 * (size_t)n)); CK(cudaMalloc(&st.discount, 4 * (size_t)n)); CK(cudaMalloc(&st.action, 4 * (size_t)n));
+    CK(cudaMalloc(&st.alive, 4 * (size_t)(g.max_bounces + 2)));
+    const int S = (batch + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    CK(cudaMalloc(&c->d_nqt_qcur, sizeof(float) * DQ_OUT * (size_t)n)); CK(cudaMalloc(&c->d_nqt_qnext, sizeof(float) * DQ_OUT * (size_t)S));
+    CK(cudaMalloc(&c->d_nqt_targets, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqt_loss, 4)); CK(cudaMemset(c->d_nqt_loss, 0, 4));
+    c->nqt_n = n; c->nqt_batch = batch;
+    return RLPT_OK;
+}
+static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
+    const rlpt_config& g = c->cfg; const int n = g.width * g.height;
+    int rc = ensure_nqt(c, batch); if (rc) return rc;
+    if (c->accum_pixels != n) {
+        cudaFree(c->d_accum); CK(cudaMalloc(&c->d_accum, sizeof(float4) * (size_t)n));
+        CK(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)n, c->stream)); c->accum_pixels = n;
+    }
+    FrameDyn dyn{};
+    dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
+    dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
+    dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
+    FrameParams p{};
+    p.scene = c->scene; p.accum = c->d_accum; p.stats = c->d_stats;
+    p.width = g.width; p.height = g.height; p.spp = 1; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
+    DqnFwdParams fp{}; fp.c1 = c->dq.c1; fp.m1 = c->dq.m1; fp.b2 = c->dq.b[1]; fp.b3 = c->dq.b[2]; fp.b4 = c->dq.b[3]; fp.w2p = c->dq.w2p; fp.w3p = c->dq.w3p; fp.w4p = c->dq.w4p;
+    const int grid = c->n_sm * 8;
+    const bool dist = c->allreduce && g.world_size > 1;
+    const uint32_t frame_base = (uint32_t)((c->frames_done * (uint64_t)g.world_size + (uint64_t)g.rank) * (uint64_t)g.spp);
+    const int S = (batch + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    for (int pass = 0; pass < g.spp; ++pass) {
+        dyn.sample_base = frame_base + (uint32_t)pass;
+        CK(cudaMemsetAsync(c->nqt.alive, 0, 4 * (size_t)(g.max_bounces + 2), c->stream));
+        launch_nqt_init(p, dyn, c->nqt, c->stream);
+        for (int b = 0; b < g.max_bounces; ++b) {
+            if (b > 0) {
+                fp.pos = c->nqt.loc; fp.n = n; fp.n_ptr = nullptr; fp.q = c->d_nqt_qcur; fp.q_stride = n; fp.h1t = fp.h2t = fp.h3t = nullptr;
+                int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
+                launch_nqt_sample(p, dyn, c->nqt, b, c->d_nqt_qcur, n, c->nq_epsilon, c->stream);
+            }
+            launch_nqt_trace(p, dyn, c->nqt, b, grid, c->smem_bytes, c->stream);
+            c->launches += b > 0 ? 3.0 : 1.0;
+            if (b > 0) {
+                for (int start = 0; start < n; start += batch) {
+                    const int bn = std::min(batch, n - start);
+                    fp.pos = c->nqt.loc + start; fp.n = bn; fp.q = c->d_nqt_qnext; fp.q_stride = S;
+                    int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
+                    launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
+                    frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream);
+                    if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
+                    launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
+                    c->launches += 40.0;
+                }
+            }
+            launch_nqt_respawn(p, dyn, c->nqt, b, c->stream);
+            int alive = 0;
+            CK(cudaMemcpyAsync(&alive, c->nqt.alive + b + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (alive == 0) break;
+        }
+        c->nq_epsilon = std::max(c->nq_epsilon - 0.01f, 0.05f);               // EPSILON_DECAY, EPSILON_MIN (deep_learning_settings.h:6-7)
+    }
+    float loss = 0.f; CK(cudaMemcpy(&loss, c->d_nqt_loss, 4, cudaMemcpyDeviceToHost)); CK(cudaMemset(c->d_nqt_loss, 0, 4));
+    c->nq_loss_total = loss;
+    CK(cudaGetLastError());
+    c->frames_done++;
+    return RLPT_OK;
+}
+int rlpt_render_neuralq(rlpt_ctx* c, int frames, int batch) {
+    if (!c || !c->have_scene || !c->dq.ready) return fail(RLPT_ERR_ARG, "rlpt_render_neuralq: needs a scene and a network (rlpt_dqn_init / rlpt_dqn_load_text)");
+    if (frames < 0 || batch <= 0) return fail(RLPT_ERR_ARG, "rlpt_render_neuralq: bad frame count / batch size");
+    int rc = timed_begin(c); if (rc) return rc;
+    for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_nq_training_frame(c, batch); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
+    return timed_end(c, frames);
+}
+int rlpt_neuralq_last_loss(rlpt_ctx* c, double* loss) { if (!c || !loss) return fail(RLPT_ERR_ARG, "null"); *loss = c->nq_loss_total; return RLPT_OK; }
 
 int rlpt_frame_reset(rlpt_ctx* c) {
     if (!c) return fail(RLPT_ERR_ARG, "null ctx");

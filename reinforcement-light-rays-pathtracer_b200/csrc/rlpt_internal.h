@@ -80,6 +80,25 @@ constexpr int BLOCK = 256;
 // host-visible launchers (rlpt_kernels.cu)
 void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s);
 void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+// Neural-Q training tracer state (NeuralQPathtracer, G/deep_learning/neural_q_pathtracer.cu:76-96): one slot per pixel,
+// every ray takes part in every bounce (terminated rays are re-seeded on the geometry and keep generating training data)
+struct NqTrainState {
+    float4* loc;        // (state position, as_float(surface id or -1))      ray_locations + ray_normals
+    float4* sloc;       // the state the action was taken in (network input of the training step)
+    float4* dir;        // direction to trace                                 ray_directions
+    float4* thr;        // throughput rgb                                     ray_throughputs
+    uint32_t* state;    // 0 alive, 1 terminated this bounce, 2 learning only  ray_states
+    float* reward; float* discount;                                        // ray_rewards, ray_discounts
+    uint32_t* action;   // chosen grid cell                                   directions_host
+    int* alive;         // [max_bounces + 2] alive (state 0) rays entering each bounce
+    int n;              // width * height
+};
+void launch_nqt_init(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, cudaStream_t s);
+void launch_nqt_sample(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, const float* q, int q_stride, float epsilon, cudaStream_t s);
+void launch_nqt_trace(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_nqt_targets(const NqTrainState& st, int start, int n, const float* q_next, int q_stride, float* targets, cudaStream_t s);
+void launch_nqt_respawn(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, cudaStream_t s);
+void launch_add_scalar(float* dst, const float* src, cudaStream_t s);
 // Neural-Q wavefront (rlpt_kernels.cu): trace without sampling (the direction comes from the network), and the sampler
 void launch_nq_trace(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s);
 void launch_nq_sample(const FrameParams& p, const FrameDyn& dyn, int bounce, const float* q, int q_stride, float epsilon, uint32_t* action_out, int grid, cudaStream_t s);

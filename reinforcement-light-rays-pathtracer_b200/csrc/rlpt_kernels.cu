@@ -455,11 +455,154 @@ void launch_nq_sample(const FrameParams& p, const FrameDyn& dyn, int bounce, con
     k_nq_sample<<<grid, BLOCK, 0, s>>>(p, dyn, bounce, q, q_stride, epsilon, action_out);
 }
 
+// ------------------------------------------------------------------------------------------------ Neural-Q training tracer
+// NeuralQPathtracer::render_frame (G/deep_learning/neural_q_pathtracer.cu:226-600) without the host round trips: the same
+// per-bounce sequence (sample with epsilon-greedy -> trace all rays -> TD targets -> optimiser steps -> re-seed terminated
+// rays), state in SoA float4 arrays, the network evaluated by k_dqn_forward on the rays' positions directly.
+enum { PURPOSE_NQ_RESPAWN = 3 };
+__global__ void k_nqt_init(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, NqTrainState st) {      // initialise_ray (:603-643)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    float u0, u1, u2, u3; draw4(p.seed, (uint32_t)i, dyn.sample_base, 0u, PURPOSE_CAMERA, u0, u1, u2, u3);
+    f3 d = camera_dir(i / p.height, i % p.height, u0, u1, p.width, p.height, dyn.rotated != 0, dyn.cy, dyn.sy, dyn.cx, dyn.sx);
+    st.loc[i] = make_float4(dyn.cam_x, dyn.cam_y, dyn.cam_z, __int_as_float(-1)); st.sloc[i] = st.loc[i];
+    st.dir[i] = make_float4(d.x, d.y, d.z, 0.f); st.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    st.state[i] = 0u; st.reward[i] = 0.f; st.discount[i] = 1.f; st.action[i] = 0u;
+    atomicAdd(&p.accum[i].w, 1.f);
+    if (i == 0) st.alive[0] = st.n;
+}
+void launch_nqt_init(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, cudaStream_t s) { k_nqt_init<<<(st.n + 255) / 256, 256, 0, s>>>(p, dyn, st); }
+
+// sample_batch_ray_directions_epsilon_greedy (nn_rendering_helpers.cu:330-389) for every ray; only alive rays carry throughput
+__global__ void __launch_bounds__(BLOCK) k_nqt_sample(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, NqTrainState st, int bounce,
+                                                      const float* __restrict__ q, int q_stride, float epsilon) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n) return;
+    const float4 a = st.loc[i]; const int gid = __float_as_int(a.w);
+    st.sloc[i] = a;
+    if (gid < 0) return;                                                       // cannot happen after bounce 0 (terminated rays are re-seeded on a surface)
+    float4 sN = __ldg(p.scene.shade + 4 * gid), sT = __ldg(p.scene.shade + 4 * gid + 1), sB = __ldg(p.scene.shade + 4 * gid + 2);
+    f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
+    float u0, u1, u2, u3; draw4(p.seed, (uint32_t)i, dyn.sample_base, (uint32_t)bounce, PURPOSE_NQ, u0, u1, u2, u3);
+    int cell; float pdf;
+    if (u3 <= epsilon) { cell = min((int)(u0 * (float)CELLS), CELLS - 1); pdf = RHO; }
+    else {
+        float total = 0.f;
+        for (int k = 0; k < CELLS; ++k) total += __ldg(q + (size_t)k * q_stride + i) * c_cell_cos[k];
+        const bool dead = !(total > 0.f);
+        if (dead) { total = 0.f; for (int k = 0; k < CELLS; ++k) total += c_cell_cos[k]; }
+        const float r = u0 * total; float run = 0.f, w = 0.f; cell = -1; int last = 0; float last_w = 0.f;
+        for (int k = 0; k < CELLS; ++k) {
+            w = (dead ? 1.f : __ldg(q + (size_t)k * q_stride + i)) * c_cell_cos[k]; run += w;
+            if (w > 0.f) { last = k; last_w = w; }
+            if (run > r && w > 0.f) { cell = k; break; }
+        }
+        if (cell < 0) { cell = last; w = last_w; }
+        pdf = RHO * ((w / total) / GRID_RHO);
+    }
+    f3 nd = grid_to_direction((float)(cell / GRID) + u1, (float)(cell % GRID) + u2, T, N, B);
+    st.dir[i] = make_float4(nd.x, nd.y, nd.z, 0.f); st.action[i] = (uint32_t)cell;
+    if (st.state[i] == 0u) {
+        const float scale = (N.x * nd.x + N.y * nd.y + N.z * nd.z) / pdf;
+        float4 c = st.thr[i]; st.thr[i] = make_float4(c.x * scale, c.y * scale, c.z * scale, 0.f);
+    }
+}
+void launch_nqt_sample(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, const float* q, int q_stride, float epsilon, cudaStream_t s) {
+    k_nqt_sample<<<(st.n + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(p, dyn, st, bounce, q, q_stride, epsilon);
+}
+
+// trace_ray (neural_q_pathtracer.cu:646-752): every ray, alive or learning-only
+template <bool STAGED>
+__global__ void __launch_bounds__(BLOCK) k_nqt_trace(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, NqTrainState st, int bounce) {
+    SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0, n_alive = 0;
+    const float H = (float)p.height;
+    const int n_round = (st.n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < st.n;
+        if (valid) {
+            const float4 a = st.loc[i], b = st.dir[i]; const uint32_t state = st.state[i];
+            const float ox = RLPT_FMA(RAY_EPS, b.x, a.x), oy = RLPT_FMA(RAY_EPS, b.y, a.y), oz = RLPT_FMA(RAY_EPS, b.z, a.z);
+            const f3 nn = normalize_ref(f3{ b.x, b.y, b.z });
+            float t, sdx, sdy, sdz; int gid;
+            closest_hit<STAGED, true>(v, ox, oy, oz, nn.x, nn.y, nn.z, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+            float4 c = st.thr[i];
+            if (gid < 0 || gid >= v.n_surf) {                                  // NOTHING / AREA_LIGHT: terminal
+                float lr = p.env, lg = p.env, lb = p.env, reward = 0.f;
+                if (gid >= 0) { float4 e = v.shade(4 * gid + 3); lr = e.x; lg = e.y; lb = e.z; reward = v.shade(4 * gid).w * 200.f; }     // luminance * 200 (:693)
+                st.reward[i] = reward; st.discount[i] = 0.f;
+                if (state == 0u) {
+                    lr *= c.x; lg *= c.y; lb *= c.z;
+                    st.thr[i] = make_float4(lr, lg, lb, 0.f);
+                    if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + i, make_float4(lr, lg, lb, 0.f));
+                    st_len += (unsigned)bounce + 1u; st_term++;
+                    if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;
+                }
+                st.state[i] = 1u;
+            } else {                                                           // SURFACE
+                const float4 sC = v.shade(4 * gid + 3);
+                st.loc[i] = make_float4(RLPT_FMA(sdx, t, ox), RLPT_FMA(sdy, t, oy), RLPT_FMA(sdz, t, oz), __int_as_float(gid));
+                st.reward[i] = 0.f; st.discount[i] = sC.w;                     // luminance of the surface (:724-737)
+                if (state == 0u) {
+                    if (bounce + 1 >= p.max_bounces) { st_len += (unsigned)p.max_bounces; st_term++; st_zero++; st.state[i] = 2u; }     // out of bounces: contributes nothing
+                    else { st.thr[i] = make_float4(c.x * sC.x, c.y * sC.y, c.z * sC.z, 0.f); n_alive++; }
+                }
+            }
+        }
+    }
+    n_alive = __reduce_add_sync(full, n_alive);
+    if (lane == 0 && n_alive) atomicAdd(st.alive + bounce + 1, (int)n_alive);
+    st_len = __reduce_add_sync(full, st_len); st_zero = __reduce_add_sync(full, st_zero); st_term = __reduce_add_sync(full, st_term);
+    if (lane == 0 && st_term) { atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term); }
+    n_tri = __reduce_add_sync(full, n_tri); n_box = __reduce_add_sync(full, n_box);
+    if (lane == 0 && (n_tri | n_box)) { atomicAdd(p.stats + 3, (unsigned long long)n_tri); atomicAdd(p.stats + 4, (unsigned long long)n_box); }
+}
+void launch_nqt_trace(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, int grid, size_t smem, cudaStream_t s) {
+    const SceneDev& sc = p.scene;
+    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    if (staged) k_nqt_trace<true><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce); else k_nqt_trace<false><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce);
+}
+
+// compute_td_targets (nn_rendering_helpers.cu:91-140): reward + discount * max_a Q(s', a) cos(theta_a); terminal: the reward
+__global__ void k_nqt_targets(NqTrainState st, int start, int n, const float* __restrict__ q_next, int q_stride, float* __restrict__ targets) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = start + j;
+    float target = st.reward[i];
+    if (st.state[i] != 1u) {
+        float best = 0.f;
+        for (int k = 0; k < CELLS; ++k) best = fmaxf(best, __ldg(q_next + (size_t)k * q_stride + j) * c_cell_cos[k]);
+        target += best * st.discount[i];
+    }
+    targets[j] = target;
+}
+void launch_nqt_targets(const NqTrainState& st, int start, int n, const float* q_next, int q_stride, float* targets, cudaStream_t s) {
+    k_nqt_targets<<<(n + 127) / 128, 128, 0, s>>>(st, start, n, q_next, q_stride, targets);
+}
+
+// sample_random_scene_pos_for_terminated_rays (nn_rendering_helpers.cu:241-277): a uniformly chosen surface, a uniform point
+// on it. Fixed here (DESIGN.md deviation 9): the index cannot reach n_surfaces, and y / z are not swapped.
+__global__ void k_nqt_respawn(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, NqTrainState st, int bounce) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.n || st.state[i] != 1u) return;
+    float u0, u1, u2, u3; draw4(p.seed, (uint32_t)i, dyn.sample_base, (uint32_t)bounce, PURPOSE_NQ_RESPAWN, u0, u1, u2, u3);
+    const int gid = min((int)(u0 * (float)p.scene.n_surf), p.scene.n_surf - 1);
+    if (u1 + u2 > 1.f) { u1 = 1.f - u1; u2 = 1.f - u2; }
+    const float4 t0 = __ldg(p.scene.tri + 3 * gid), t1 = __ldg(p.scene.tri + 3 * gid + 1), t2 = __ldg(p.scene.tri + 3 * gid + 2);
+    st.loc[i] = make_float4(t0.x + u1 * t0.w + u2 * t1.z, t0.y + u1 * t1.x + u2 * t1.w, t0.z + u1 * t1.y + u2 * t2.x, __int_as_float(gid));
+    st.state[i] = 2u;
+}
+void launch_nqt_respawn(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, cudaStream_t s) { k_nqt_respawn<<<(st.n + 255) / 256, 256, 0, s>>>(p, dyn, st, bounce); }
+__global__ void k_add_scalar(float* dst, const float* src) { *dst += *src; }
+void launch_add_scalar(float* dst, const float* src, cudaStream_t s) { k_add_scalar<<<1, 1, 0, s>>>(dst, src); }
+
 int kernels_set_smem_limit(size_t bytes) {
     cudaError_t e = cudaSuccess;
 #define RLPT_SET(k) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
     RLPT_SET((k_bounce<true, true, true>)); RLPT_SET((k_bounce<true, true, false>)); RLPT_SET((k_bounce<true, false, true>)); RLPT_SET((k_bounce<true, false, false>));
     RLPT_SET((k_bounce<false, true, true>)); RLPT_SET((k_bounce<false, true, false>)); RLPT_SET((k_bounce<false, false, true>)); RLPT_SET((k_bounce<false, false, false>));
+    RLPT_SET((k_nqt_trace<true>)); RLPT_SET((k_nqt_trace<false>));
     RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));
 #undef RLPT_SET

@@ -45,7 +45,7 @@ SYMBOLS = [
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
     "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
-    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_get_grads",
+    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_get_grads", "rlpt_render_neuralq", "rlpt_neuralq_last_loss",
 ]
 
 _lib = None
@@ -227,6 +227,12 @@ class Context:
 
     def render_pretrained(self, frames=1):
         self._ck(self.L.rlpt_render_pretrained(self.h, int(frames)))
+
+    def render_neuralq(self, frames=1, batch=4096):
+        self._ck(self.L.rlpt_render_neuralq(self.h, int(frames), int(batch)))
+        loss = ctypes.c_double()
+        self._ck(self.L.rlpt_neuralq_last_loss(self.h, ctypes.byref(loss)))
+        return loss.value
 
     def render_sarsa_frozen(self, frames=1):
         self._ck(self.L.rlpt_render_sarsa_frozen(self.h, int(frames)))

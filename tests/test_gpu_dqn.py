@@ -174,3 +174,32 @@ def test_adam_training_tracks_numpy_and_reduces_loss(ctx, golden_scenes, dqn_gol
     # Adam moves every parameter by about lr per step: after 20 steps the two trajectories stay within a few lr of each other
     moved = np.abs(p - p0); assert moved.max() <= 20 * 1.05e-3 + 1e-6 and moved.mean() > 1e-3
     assert np.mean(np.abs(p - p_ref) <= 6e-3) >= 0.9
+
+
+def test_neuralq_training_tracer_learns_and_stays_unbiased(ctx, golden_scenes):
+    """NeuralQPathtracer from a freshly initialised network on the Cornell box: the parameters move, the TD loss falls, fewer
+    paths end with zero contribution than under uniform sampling, and the image stays close to the default tracer's.
+    Closeness, not equality: with ReLU on the output layer (N/dq_network.cu:17) a cell whose Q is exactly 0 is only ever
+    reached by the 5% exploration branch, whose weight 1/RHO is not divided by epsilon -- the reference's estimator loses that
+    energy, and so does this one (measured -4% with a fresh network; the trained network of the pretrained test is within 1.5%)."""
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    ctx.configure(width=128, height=128, spp=4, max_bounces=80); ctx.camera_set((0, 0, -3))
+    ctx.render_default(8); base = ctx.frame_download().copy(); st0 = ctx.stats()
+    ctx.frame_reset(); ctx.stats_reset()
+    ctx.dqn_init(seed=1984)
+    p0 = ctx.dqn_get_params()
+    losses, zero = [], []
+    for f in range(4):
+        ctx.stats_reset()
+        losses.append(ctx.render_neuralq(1, batch=2048)); st = ctx.stats()
+        assert st["paths"] == 128 * 128 * 4
+        zero.append(st["zero_contribution_paths"] / st["paths"])
+    img = ctx.frame_download()
+    p1 = ctx.dqn_get_params()
+    assert np.isfinite(img).all() and np.isfinite(p1).all() and np.isfinite(losses).all()
+    assert np.abs(p1 - p0).max() > 1e-3
+    assert np.allclose(img.mean(0), base.mean(0), rtol=0.1) and np.all(img.mean(0) <= base.mean(0) * 1.03), (img.mean(0), base.mean(0))
+    assert losses[-1] < losses[0], losses
+    assert zero[-1] < st0["zero_contribution_paths"] / st0["paths"], (zero, st0["zero_contribution_paths"] / st0["paths"])
+    print("neural-q training: losses", losses, "zero-contribution", zero, "default", st0["zero_contribution_paths"] / st0["paths"])
