@@ -306,6 +306,42 @@ void RadianceMap::save_selected_radiance_volumes_vals(std::string fpath) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ Neural-Q drivers
+static void upload_with_vertices(Renderer& r, const Scene& scene) {
+    r.upload(scene);
+    if (scene.vertices_count == 9 * (scene.surfaces_count + scene.area_light_count))       // the network's input order is Scene::vertices (G/main.cu:171-176)
+        r.check(rlpt_dqn_set_vertices(r.ctx(), scene.vertices, scene.vertices_count));
+}
+NeuralQPathtracer::NeuralQPathtracer(unsigned int frames, int batch_size, SDLScreen& screen, Renderer& r, Scene& scene, Camera& camera, int, char**,
+                                     const char* load_model, const char* save_model, const char* stats_file, const char* image) {
+    upload_with_vertices(r, scene); r.set_camera(camera);
+    bool loaded = false;
+    if (load_model) { FILE* f = fopen(load_model, "r"); if (f) { fclose(f); r.check(rlpt_dqn_load_text(r.ctx(), load_model)); loaded = true; } }
+    if (!loaded) r.check(rlpt_dqn_init(r.ctx(), 1984u));
+    for (unsigned int f = 0; f < frames; ++f) {
+        r.reset_frame(); r.check(rlpt_stats_reset(r.ctx()));
+        r.check(rlpt_render_neuralq(r.ctx(), 1, batch_size));
+        r.check(rlpt_neuralq_last_loss(r.ctx(), &last_loss));
+        if (stats_file) {                                                      // "avg_path_length loss zero_contribution_paths" (neural_q_pathtracer.cu:578-583)
+            rlpt_stats_t st = r.stats(); std::ofstream out(stats_file, std::ios::app);
+            out << (st.paths > 0 ? st.path_length_sum / st.paths : 0.0) << " " << last_loss << " " << (long long)st.zero_contribution_paths << "\n";
+        }
+        r.present(screen); screen.SDL_Renderframe();
+        if (save_model) r.check(rlpt_dqn_save_text(r.ctx(), save_model));    // after every frame (:191-196)
+    }
+    if (image) screen.SDL_SaveImage(image);
+}
+PretrainedPathtracer::PretrainedPathtracer(unsigned int frames, int, SDLScreen& screen, Renderer& r, Scene& scene, Camera& camera, int, char**, const char* model, const char* image) {
+    FILE* f = model ? fopen(model, "r") : nullptr;
+    if (!f) return;
+    fclose(f);
+    upload_with_vertices(r, scene); r.set_camera(camera);
+    r.check(rlpt_dqn_load_text(r.ctx(), model));
+    for (unsigned int fr = 0; fr < frames; ++fr) { r.reset_frame(); r.check(rlpt_render_pretrained(r.ctx(), 1)); r.present(screen); screen.SDL_Renderframe(); }
+    if (image) screen.SDL_SaveImage(image);
+    rendered = true;
+}
+
 }  // namespace rlpt_host
 
 // ------------------------------------------------------------------------------------------------ C entry points for tests

@@ -116,6 +116,24 @@ public:
 private:
     Renderer& r_;
 };
+// G/deep_learning/neural_q_pathtracer.cuh:88-96. The reference's constructor does everything (initialise DyNet, optionally
+// load the model, render `frames` frames with training, save the model after every frame, save the image). Same here, over
+// rlpt_render_neuralq; argc/argv (DyNet flags) are accepted and ignored.
+class NeuralQPathtracer {
+public:
+    NeuralQPathtracer(unsigned int frames, int batch_size, SDLScreen& screen, Renderer& renderer, Scene& scene, Camera& camera, int argc = 0, char** argv = nullptr,
+                      const char* load_model = nullptr /* LOAD_MODEL */, const char* save_model = "../Radiance_Map_Data/deep_q_learning_12_12.model" /* SAVE_MODEL */,
+                      const char* stats_file = "../Radiance_Map_Data/nn_training_stats.txt", const char* image = "../Images/render.bmp");
+    double last_loss = 0.0;
+};
+// G/deep_learning/pre_trained_pathtracer.cuh:92-100: render with a trained network, no learning; returns silently when the
+// model file is missing, as the reference does (pre_trained_pathtracer.cu:50-53)
+class PretrainedPathtracer {
+public:
+    PretrainedPathtracer(unsigned int frames, int batch_size, SDLScreen& screen, Renderer& renderer, Scene& scene, Camera& camera, int argc = 0, char** argv = nullptr,
+                         const char* model = "../Radiance_Map_Data/deep_q_learning_12_12.model", const char* image = "../Images/render.bmp");
+    bool rendered = false;
+};
 // G/utils/hemisphere_helpers.cu:230-281: "px py pz nx ny nz" per line
 bool read_hemisphere_locations_and_normals(const std::string& path, std::vector<vec3>& locations, std::vector<vec3>& normals);
 
