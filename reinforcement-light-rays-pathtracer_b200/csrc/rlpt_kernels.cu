@@ -77,6 +77,25 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
     const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
     best_t = T_MISS; best_gid = -1;
     if (v.brute) {
+        if (v.n_tri <= 64) {
+            // two phases: (1) a branch-free pass over every triangle marks the candidates no early out can reject,
+            // (2) the full solve with its divisions runs on the marked ones only, in primitive order (so "first lowest id
+            // wins a tie" is kept). Lanes disagree about WHICH triangles are candidates, so solving inline would make the
+            // whole warp walk the division path at most iterations; here it walks it max-over-lanes(#candidates) times.
+            unsigned long long mask = 0ull;
+#pragma unroll 2
+            for (int gid = 0; gid < v.n_tri; ++gid) {
+                TriRec r = load_tri(v, gid);
+                if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << gid;
+            }
+            if (COUNT) n_tri += (unsigned)v.n_tri;
+            while (mask) {
+                const int gid = __ffsll((long long)mask) - 1; mask &= mask - 1ull;
+                TriRec r = load_tri(v, gid); float t;
+                if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && t < best_t) { best_t = t; best_gid = gid; }
+            }
+            return;
+        }
         for (int gid = 0; gid < v.n_tri; ++gid) {
             TriRec r = load_tri(v, gid); float t;
             if (COUNT) n_tri++;
