@@ -47,7 +47,7 @@ struct rlpt_ctx {
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
     float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
     int *d_grid_start = nullptr, *d_grid_vol = nullptr; float4* d_grid_posn = nullptr; float grid_h = 0.f;
-    float *d_q = nullptr, *d_cdf = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
+    float *d_q = nullptr, *d_cdf = nullptr, *d_cdf_rows = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
@@ -74,7 +74,7 @@ static void free_scene(rlpt_ctx* c) {
 }
 static void free_rmap(rlpt_ctx* c) {
     cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
-    cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt);
+    cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt); cudaFree(c->d_cdf_rows); c->d_cdf_rows = nullptr;
     cudaFree(c->d_grid_start); cudaFree(c->d_grid_vol); cudaFree(c->d_grid_posn); c->d_grid_start = c->d_grid_vol = nullptr; c->d_grid_posn = nullptr;
     c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
     c->have_rmap = false; c->rm = RadianceDev{};
@@ -353,7 +353,7 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     }
     const size_t cells = (size_t)nv * CELLS;
     CK(cudaMalloc(&c->d_kd, sizeof(float4) * kd.size())); CK(cudaMalloc(&c->d_posn, sizeof(float4) * nv)); CK(cudaMalloc(&c->d_vol_surface, sizeof(int) * nv));
-    CK(cudaMalloc(&c->d_q, 4 * cells)); CK(cudaMalloc(&c->d_cdf, 4 * cells)); CK(cudaMalloc(&c->d_visits, 4 * cells)); CK(cudaMalloc(&c->d_irr, 4 * (size_t)nv));
+    CK(cudaMalloc(&c->d_q, 4 * cells)); CK(cudaMalloc(&c->d_cdf, 4 * cells)); CK(cudaMalloc(&c->d_cdf_rows, 4 * (size_t)nv * GRID)); CK(cudaMalloc(&c->d_visits, 4 * cells)); CK(cudaMalloc(&c->d_irr, 4 * (size_t)nv));
     CK(cudaMalloc(&c->d_acc_sum, 4 * cells)); CK(cudaMalloc(&c->d_acc_cnt, 4 * cells));
     CK(cudaMemcpy(c->d_kd, kd.data(), sizeof(float4) * kd.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_posn, posn.data(), sizeof(float4) * nv, cudaMemcpyHostToDevice));
@@ -365,7 +365,7 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     CK(cudaMemcpy(c->d_q, q0.data(), 4 * cells, cudaMemcpyHostToDevice));
     CK(cudaMemset(c->d_visits, 0, 4 * cells)); CK(cudaMemset(c->d_acc_sum, 0, 4 * cells)); CK(cudaMemset(c->d_acc_cnt, 0, 4 * cells));
     RadianceDev& rm = c->rm;
-    rm.kd_inner = c->d_kd; rm.vol_posn = c->d_posn; rm.vol_surface = c->d_vol_surface; rm.q = c->d_q; rm.cdf = c->d_cdf; rm.visits = c->d_visits;
+    rm.kd_inner = c->d_kd; rm.vol_posn = c->d_posn; rm.vol_surface = c->d_vol_surface; rm.q = c->d_q; rm.cdf = c->d_cdf; rm.cdf_rows = c->d_cdf_rows; rm.visits = c->d_visits;
     rm.irradiance = c->d_irr; rm.acc_sum = c->d_acc_sum; rm.acc_cnt = c->d_acc_cnt; rm.n_vol = nv; rm.n_inner = n_inner;
     rm.root = child_word(0);
     rm.root_px = c->h_tree[0].pos[0]; rm.root_py = c->h_tree[0].pos[1]; rm.root_pz = c->h_tree[0].pos[2];

@@ -235,6 +235,37 @@ RLPT_HD int sample_sector(Load load, float r, float& pdf) {
     return k;
 }
 
+// Two-level form of sample_sector with the same result: `rows` = cdf[12 j + 11] (12 values, written next to the CDF by the
+// merge kernel) selects the grid row, then the row's 12 entries select the cell -- two rounds of independent 16-byte
+// loads instead of a chain of ~10 dependent 4-byte probes. row(j, out[12]) loads cdf[12 j .. 12 j + 11].
+template <class LoadRows, class LoadRow, class Load>
+RLPT_HD int sample_sector_2level(LoadRows load_rows, LoadRow load_row, Load load, float r, float& pdf) {
+    float e[12]; load_rows(e);
+    int j = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 11; ++i) j += (e[i] <= r) ? 1 : 0;           // first row whose end exceeds r (monotone), capped at the last row
+    float c[12]; load_row(j, c);
+    const float prev_end = j > 0 ? e[j - 1] : 0.f;
+    if (j == 0 && r <= c[0]) { pdf = RHO * (c[0] / GRID_RHO); return 0; }
+    int n = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 12; ++i) n += (c[i] <= r) ? 1 : 0;           // entries not exceeding r
+    if (n < 12) {
+        float hi_v = c[0], lo_v = prev_end;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 1; i < 12; ++i) { if (i == n) { hi_v = c[i]; lo_v = c[i - 1]; } }
+        pdf = RHO * ((hi_v - lo_v) / GRID_RHO);
+        return 12 * j + n;
+    }
+    return sample_sector(load, r, pdf);                              // r at or past the end of the table: the clamping path
+}
+
 // ---------------------------------------------------------------- nearest radiance volume
 // RadianceMap::find_closest_radiance_volume_iterative (G/radiance_volumes/radiance_map.cu:150-203) over the reference's
 // own kd-tree, re-laid-out: inner nodes only, one float4 each (split, left, right, dim) with leaf children encoded

@@ -33,6 +33,7 @@ struct RadianceDev {
     const int* vol_surface;
     float* q;                 // [n_vol][144]  Q(x, omega)                      radiance_grid
     float* cdf;               // [n_vol][144]  inclusive CDF frozen per frame  radiance_distribution
+    float* cdf_rows;          // [n_vol][12]   cdf[12 j + 11]: first level of the two-level sector search
     uint32_t* visits;         // [n_vol][144]
     float* irradiance;        // [n_vol]       sum_k Q_k cos_k lum/pi           irradiance_accum
     float* acc_sum;           // [n_vol][144]  sum of TD targets this iteration

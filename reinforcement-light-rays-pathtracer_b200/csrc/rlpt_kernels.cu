@@ -226,7 +226,13 @@ __device__ __forceinline__ void td_accumulate(const RadianceDev& rm, bool active
 // ------------------------------------------------------------------------------------------------ wavefront kernels
 // One bounce of one path. PRIMARY: the path is generated here (raygen fused with the first cast).
 template <bool STAGED, bool SARSA, bool PRIMARY>
-__global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+#ifndef RLPT_MINBLOCKS
+#define RLPT_MINBLOCKS 1
+#endif
+#ifndef RLPT_CDF_2LEVEL
+#define RLPT_CDF_2LEVEL 1
+#endif
+__global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
@@ -296,7 +302,16 @@ __global__ void __launch_bounds__(BLOCK) k_bounce(const __grid_constant__ FrameP
                 if (SARSA) {
                     // importance_sample_ray_direction -> sample_direction_from_radiance_distribution (radiance_volume.cu:192-244)
                     const float* __restrict__ row = p.rm.cdf + (size_t)nv * CELLS;
+                    const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(p.rm.cdf_rows + (size_t)nv * GRID);
+                    const float4* __restrict__ row4 = reinterpret_cast<const float4*>(row);
+#if RLPT_CDF_2LEVEL
+                    float pdf; int sector = sample_sector_2level(
+                        [&](float (&e)[12]) { float4 a = __ldg(rows4), b = __ldg(rows4 + 1), c = __ldg(rows4 + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
+                        [&](int j, float (&e)[12]) { float4 a = __ldg(row4 + 3 * j), b = __ldg(row4 + 3 * j + 1), c = __ldg(row4 + 3 * j + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
+                        [&](int k) { return __ldg(row + k); }, u0, pdf);
+#else
                     float pdf; int sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
+#endif
                     nd = grid_to_direction((float)(sector / GRID) + u1, (float)(sector % GRID) + u2, T, N, B);
                     float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;                       // reinforcement_path_tracing.cu:107
                     scale = cos_theta / pdf;
@@ -673,7 +688,7 @@ __global__ void __launch_bounds__(BLOCK) k_merge_cdf(RadianceDev rm, const float
             for (int o = 1; o < 32; o <<= 1) { float y = __shfl_up_sync(full, x, o); if (lane >= o) x += y; }
             x += carry;
             int k = c * 32 + lane;
-            if (k < CELLS) rm.cdf[base + k] = x;
+            if (k < CELLS) { rm.cdf[base + k] = x; if (k % GRID == GRID - 1) rm.cdf_rows[(size_t)vol * GRID + k / GRID] = x; }
             carry = __shfl_sync(full, x, 31);
         }
         if (lane == 0) rm.irradiance[vol] = irr * __ldg(surf_lum_over_pi + __ldg(rm.vol_surface + vol));

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librlpt.so")
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", os.environ.get("RLPT_LIB_NAME", "librlpt.so"))
 CELLS = 144
 
 HIT_NOTHING, HIT_AREA_LIGHT, HIT_SURFACE = 0, 1, 2
