@@ -174,6 +174,7 @@ typedef struct rlpt_stats_t {
     double box_tests;             /* ray-AABB slab tests executed (18 flop each) */
     double trace_seconds;         /* device seconds inside the per-bounce tracing kernels (CUDA events) */
     double merge_seconds;         /* device seconds inside all-reduce + Q merge + CDF rebuild */
+    double kd_fallbacks;          /* nearest-volume queries the candidate cells could not decide (answered by the reference's kd search) */
 } rlpt_stats_t;
 int rlpt_stats(rlpt_ctx* ctx, rlpt_stats_t* out);
 int rlpt_stats_reset(rlpt_ctx* ctx);

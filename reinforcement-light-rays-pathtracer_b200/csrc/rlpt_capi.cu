@@ -46,7 +46,7 @@ struct rlpt_ctx {
     bool have_rmap = false;
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
     float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
-    int *d_grid_start = nullptr, *d_grid_vol = nullptr; float4* d_grid_posn = nullptr; float grid_h = 0.f;
+    int4* d_vc_table = nullptr; float4* d_vc_cand = nullptr; float vc_built_accept = 0.f; size_t vc_keys = 0, vc_listed = 0;   // nearest-volume candidate cells
     float *d_q = nullptr, *d_cdf = nullptr, *d_cdf_rows = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // Neural-Q network
@@ -56,12 +56,19 @@ struct rlpt_ctx {
     float nq_epsilon = 0.05f; double nq_loss_total = 0.0;     // EPSILON_START (G/constants/deep_learning_settings.h:5)
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
-    struct Lane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; };
+    struct Lane {
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; float2* d_hit = nullptr;
+        // live-path counts of recent frames, copied back asynchronously: the launch plan of a frame (where the per-bounce
+        // launches stop and the run-to-completion kernel takes over) is read off the newest snapshot that has arrived
+        static constexpr int SNAPS = 4;
+        int* h_counts = nullptr; cudaEvent_t snap_ev[SNAPS] = {}; int snap_tag[SNAPS] = {}; uint64_t snap_seq = 0;   // tag = max_bounces the snapshot was taken under (0: none)
+    };
     std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; cudaEvent_t ev_fork = nullptr;
     float4* d_accum = nullptr; int accum_pixels = 0;
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
     size_t smem_bytes = 0; int grid = 148;
+    int pipe_split = 1, pipe_tail = 65536;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
     void* d_stage = nullptr; size_t stage_bytes = 0;     // device staging for frame downloads (kept across calls)
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
     double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;
@@ -75,14 +82,16 @@ static void free_scene(rlpt_ctx* c) {
 static void free_rmap(rlpt_ctx* c) {
     cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
     cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt); cudaFree(c->d_cdf_rows); c->d_cdf_rows = nullptr;
-    cudaFree(c->d_grid_start); cudaFree(c->d_grid_vol); cudaFree(c->d_grid_posn); c->d_grid_start = c->d_grid_vol = nullptr; c->d_grid_posn = nullptr;
+    cudaFree(c->d_vc_table); cudaFree(c->d_vc_cand); c->d_vc_table = nullptr; c->d_vc_cand = nullptr;
     c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
     c->have_rmap = false; c->rm = RadianceDev{};
 }
 static void free_lanes(rlpt_ctx* c) {
     for (auto& l : c->lanes) {
         for (int k = 0; k < 2; ++k) { cudaFree(l.q[k].o); cudaFree(l.q[k].d); cudaFree(l.q[k].thr); cudaFree(l.q[k].meta); }
-        cudaFree(l.d_counts); if (l.done) cudaEventDestroy(l.done); if (l.stream) cudaStreamDestroy(l.stream);
+        cudaFree(l.d_counts); cudaFree(l.d_hit); if (l.h_counts) cudaFreeHost(l.h_counts);
+        for (auto& e : l.snap_ev) if (e) cudaEventDestroy(e);
+        if (l.done) cudaEventDestroy(l.done); if (l.stream) cudaStreamDestroy(l.stream);
     }
     c->lanes.clear(); c->lane_capacity = 0; c->counts_len = 0; c->lane_spp = 0;
 }
@@ -105,7 +114,6 @@ static float within_abs_of(float max_dist) {
     for (float n = std::nextafterf(f, INFINITY); (double)n * (double)n < md; n = std::nextafterf(f, INFINITY)) f = n;
     return f;
 }
-static float grid_accept_r(float h, float within_abs) { return std::min(h * (1.f - 1e-3f), within_abs * (1.f - 1e-5f)); }
 
 static int ensure_stage(rlpt_ctx* c, size_t bytes) {
     if (bytes <= c->stage_bytes) return RLPT_OK;
@@ -139,6 +147,8 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     rlpt_ctx* c = new rlpt_ctx; c->device = device;
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
+    if (const char* e = getenv("RLPT_SPLIT")) c->pipe_split = atoi(e) != 0;
+    if (const char* e = getenv("RLPT_TAIL")) c->pipe_tail = std::max(0, atoi(e));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -203,7 +213,7 @@ int rlpt_config_set(rlpt_ctx* c, const rlpt_config* cfg) {
     CK(cudaSetDevice(c->device));
     if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); for (auto& l : c->lanes) if (l.stream) CK(cudaStreamSynchronize(l.stream)); free_frame(c); }
     if (c->have_scene) { int rc = choose_traversal(c, 0); if (rc) return rc; }
-    if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.grid.accept_r = grid_accept_r(c->grid_h, c->rm.within_abs); }
+    if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.vc.accept_r = std::min(c->vc_built_accept, c->rm.within_abs * (1.f - 1e-5f)); }   // lists were built for vc_built_accept: valid for any smaller radius
     return RLPT_OK;
 }
 
@@ -371,50 +381,19 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     rm.root_px = c->h_tree[0].pos[0]; rm.root_py = c->h_tree[0].pos[1]; rm.root_pz = c->h_tree[0].pos[2];
     rm.within_abs = within_abs_of(c->cfg.max_dist);
     {
-        // uniform grid over the volume positions, one empty cell of padding all round; cell size just above the kd search
-        // radius (or coarser for very large scenes: at most 254 cells per axis)
-        float lo[3] = { 3e38f, 3e38f, 3e38f }, hi[3] = { -3e38f, -3e38f, -3e38f };
-        for (int i = 0; i < nv; ++i) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], c->h_vol[i].pos[k]); hi[k] = std::max(hi[k], c->h_vol[i].pos[k]); }
-        float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-        float h = std::max(std::max(rm.within_abs, 0.f) * 1.01f, std::max(ext / 254.f, 1e-6f));
-        VolGrid g{}; g.inv_h = 1.f / h; g.ox = lo[0] - h; g.oy = lo[1] - h; g.oz = lo[2] - h;
-        g.nx = (int)grid_coord(hi[0], g.ox, g.inv_h) + 2; g.ny = (int)grid_coord(hi[1], g.oy, g.inv_h) + 2; g.nz = (int)grid_coord(hi[2], g.oz, g.inv_h) + 2;
-        c->grid_h = h; g.accept_r = grid_accept_r(h, rm.within_abs);
-        const size_t ncell = (size_t)g.nx * g.ny * g.nz;
-        // own-cell buckets first, then each cell's candidate list = the volumes of its 27-cell neighbourhood
-        std::vector<int> own(ncell + 1, 0), cell_of(nv), sorted(nv);
-        for (int i = 0; i < nv; ++i) {
-            const float* p = c->h_vol[i].pos;
-            int cx = (int)grid_coord(p[0], g.ox, g.inv_h), cy = (int)grid_coord(p[1], g.oy, g.inv_h), cz = (int)grid_coord(p[2], g.oz, g.inv_h);
-            cell_of[i] = (cz * g.ny + cy) * g.nx + cx; own[cell_of[i] + 1]++;
-        }
-        for (size_t k = 0; k < ncell; ++k) own[k + 1] += own[k];
-        { std::vector<int> fill(own.begin(), own.end() - 1); for (int i = 0; i < nv; ++i) sorted[fill[cell_of[i]]++] = i; }
-        std::vector<int> start(ncell + 1, 0);
-        auto neighbourhood = [&](int x, int y, int z, auto&& visit) {
-            for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
-                int xx = x + dx, yy = y + dy, zz = z + dz;
-                if (xx < 0 || yy < 0 || zz < 0 || xx >= g.nx || yy >= g.ny || zz >= g.nz) continue;
-                visit((size_t)(zz * g.ny + yy) * g.nx + xx);
-            }
-        };
-        size_t total = 0;
-        for (int z = 0; z < g.nz; ++z) for (int y = 0; y < g.ny; ++y) for (int x = 0; x < g.nx; ++x) {
-            size_t cell = (size_t)(z * g.ny + y) * g.nx + x; start[cell] = (int)total;
-            neighbourhood(x, y, z, [&](size_t nb) { total += (size_t)(own[nb + 1] - own[nb]); });
-            if (total > 0x7fffffffu) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_radiance_map_build: nearest-volume candidate lists exceed 2^31 entries");
-        }
-        start[ncell] = (int)total;
-        std::vector<int> gvol(std::max<size_t>(total, 1)); std::vector<float4> gposn(std::max<size_t>(total, 1));
-        for (int z = 0; z < g.nz; ++z) for (int y = 0; y < g.ny; ++y) for (int x = 0; x < g.nx; ++x) {
-            size_t cell = (size_t)(z * g.ny + y) * g.nx + x; size_t w = (size_t)start[cell];
-            neighbourhood(x, y, z, [&](size_t nb) { for (int k = own[nb]; k < own[nb + 1]; ++k) { gvol[w] = sorted[k]; gposn[w] = posn[sorted[k]]; ++w; } });
-        }
-        CK(cudaMalloc(&c->d_grid_start, sizeof(int) * (ncell + 1))); CK(cudaMalloc(&c->d_grid_vol, sizeof(int) * gvol.size())); CK(cudaMalloc(&c->d_grid_posn, sizeof(float4) * gposn.size()));
-        CK(cudaMemcpy(c->d_grid_start, start.data(), sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_grid_vol, gvol.data(), sizeof(int) * gvol.size(), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_grid_posn, gposn.data(), sizeof(float4) * gposn.size(), cudaMemcpyHostToDevice));
-        rm.grid = g; rm.grid_start = c->d_grid_start; rm.grid_vol = c->d_grid_vol; rm.grid_posn = c->d_grid_posn;
+        // candidate cells for the nearest-volume search: cell size = a fraction of the volume spacing sqrt(AREA_PER_SAMPLE)
+        float factor = 0.4f; if (const char* e = getenv("RLPT_VCELL")) factor = std::max(0.05f, (float)atof(e));
+        const float accept = rm.within_abs * (1.f - 1e-5f);
+        std::vector<int> vclass(nv); for (int i = 0; i < nv; ++i) vclass[i] = c->h_surf_class[c->h_vol[i].surface];
+        HostVCells hv;
+        host_build_vcells(c->h_surf_v.data(), c->h_surf_class.data(), c->n_surf, c->h_vol, vclass, factor * std::sqrt(std::max(c->cfg.area_per_sample, 1e-12f)), accept, hv);
+        CK(cudaMalloc(&c->d_vc_table, sizeof(int) * hv.table.size())); CK(cudaMalloc(&c->d_vc_cand, sizeof(float) * hv.cand.size()));
+        CK(cudaMemcpy(c->d_vc_table, hv.table.data(), sizeof(int) * hv.table.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_vc_cand, hv.cand.data(), sizeof(float) * hv.cand.size(), cudaMemcpyHostToDevice));
+        VCells g{}; g.ox = hv.ox; g.oy = hv.oy; g.oz = hv.oz; g.inv_h = 1.f / hv.h; g.nx = hv.nx; g.ny = hv.ny; g.nz = hv.nz;
+        g.mask = (uint32_t)(hv.table.size() / 4 - 1); g.accept_r = accept; c->vc_built_accept = accept;
+        c->vc_keys = hv.keys; c->vc_listed = hv.listed;
+        rm.vc = g; rm.vc_table = c->d_vc_table; rm.vc_cand = c->d_vc_cand;
     }
     c->have_rmap = true;
     launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
@@ -678,7 +657,9 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
                 CK(cudaMalloc(&l.q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * paths));
                 CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * paths));
             }
-            CK(cudaMalloc(&l.d_counts, sizeof(int) * (g.max_bounces + 2)));
+            CK(cudaMalloc(&l.d_counts, sizeof(int) * (g.max_bounces + 2))); CK(cudaMalloc(&l.d_hit, sizeof(float2) * paths));
+            CK(cudaHostAlloc(&l.h_counts, sizeof(int) * (size_t)(g.max_bounces + 2) * rlpt_ctx::Lane::SNAPS, cudaHostAllocDefault));
+            for (auto& e : l.snap_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         c->lane_capacity = paths; c->counts_len = g.max_bounces + 2;
     }
@@ -707,19 +688,47 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n;
     p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
     const int grid = c->n_sm * 8;
+    const int split = c->pipe_split, tail_thr = c->pipe_tail;
+    const int len = g.max_bounces + 2;
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t li = 0; li < c->lanes.size(); ++li) {
         rlpt_ctx::Lane& l = c->lanes[li];
         CK(cudaStreamWaitEvent(l.stream, c->ev_fork, 0));
-        CK(cudaMemsetAsync(l.d_counts, 0, sizeof(int) * (g.max_bounces + 2), l.stream));
-        p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts;
+        CK(cudaMemsetAsync(l.d_counts, 0, sizeof(int) * len, l.stream));
+        p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts; p.hit = l.d_hit;
         dyn.sample_base = frame_base + (uint32_t)li * (uint32_t)c->lane_spp;
-        launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream);
-        for (int b = 1; b < g.max_bounces; ++b) launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream);
+        // launch plan: per-bounce launches up to b_tail, then one run-to-completion launch. b_tail = the first bounce the
+        // newest arrived snapshot of this lane entered with at most tail_thr live paths (no snapshot yet: every bounce gets
+        // its launch). Only speed depends on the choice; the run-to-completion kernel is correct for any count.
+        int b_tail = g.max_bounces;
+        if (tail_thr > 0 && c->cap_bounce < 0) {
+            for (uint64_t k = 0; k < rlpt_ctx::Lane::SNAPS && k < l.snap_seq; ++k) {
+                const int slot = (int)((l.snap_seq - 1 - k) % rlpt_ctx::Lane::SNAPS);
+                if (cudaEventQuery(l.snap_ev[slot]) != cudaSuccess) continue;
+                if (l.snap_tag[slot] != g.max_bounces) break;         // taken under another configuration
+                const int* hc = l.h_counts + (size_t)slot * len;
+                for (int b = 1; b < g.max_bounces; ++b) if (hc[b] <= tail_thr) { b_tail = b; break; }
+                break;
+            }
+            (void)cudaGetLastError();
+        }
+        int launches = 0;
+        if (split) { launch_isect(p, dyn, 0, grid, c->smem_bytes, l.stream); launch_shade(p, dyn, method, 0, grid, l.stream); launches += 2; }
+        else { launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream); launches += 1; }
+        for (int b = 1; b < b_tail; ++b) {
+            if (split) { launch_isect(p, dyn, b, grid, c->smem_bytes, l.stream); launch_shade(p, dyn, method, b, grid, l.stream); launches += 2; }
+            else { launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream); launches += 1; }
+        }
+        if (b_tail < g.max_bounces) { launch_tail(p, dyn, method, b_tail, grid, c->smem_bytes, l.stream); launches += 1; }
+        c->launches += (double)launches;
+        {   // snapshot of this frame's counts
+            const int slot = (int)(l.snap_seq % rlpt_ctx::Lane::SNAPS);
+            CK(cudaMemcpyAsync(l.h_counts + (size_t)slot * len, l.d_counts, sizeof(int) * len, cudaMemcpyDeviceToHost, l.stream));
+            CK(cudaEventRecord(l.snap_ev[slot], l.stream)); l.snap_tag[slot] = g.max_bounces; l.snap_seq++;
+        }
         CK(cudaEventRecord(l.done, l.stream));
         CK(cudaStreamWaitEvent(c->stream, l.done, 0));
     }
-    c->launches += (double)g.max_bounces * (double)c->lanes.size();
     CK(cudaGetLastError());
     c->frames_done++;
     c->cap_bounce = -1;
@@ -993,6 +1002,7 @@ int rlpt_stats(rlpt_ctx* c, rlpt_stats_t* out) {
     out->path_length_sum = (double)h[0]; out->zero_contribution_paths = (double)h[1]; out->paths = (double)h[2];
     out->ray_casts = (double)h[0]; out->device_seconds = c->device_seconds; out->frames = c->frames_rendered; out->kernel_launches = c->launches;
     out->triangle_tests = (double)h[3]; out->box_tests = (double)h[4]; out->trace_seconds = c->trace_seconds; out->merge_seconds = c->merge_seconds;
+    out->kd_fallbacks = (double)h[5];
     return RLPT_OK;
 }
 int rlpt_stats_reset(rlpt_ctx* c) {

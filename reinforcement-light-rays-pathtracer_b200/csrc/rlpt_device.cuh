@@ -304,55 +304,65 @@ RLPT_HD int kd_find(LoadInner load_inner, LoadVol load_vol, uint32_t root, float
     return best;
 }
 
-// Uniform-grid front end of the nearest-volume search (DESIGN.md "Nearest volume"). The kd search above visits every
+// Candidate-cell front end of the nearest-volume search (DESIGN.md "Nearest volume"). The kd search above visits every
 // leaf whose position differs from the query by at most within_abs in every coordinate (a far child is entered when
 // the query is within within_abs of the split plane, and the split lies between query and leaf), keeps the closest
 // same-normal leaf with strict <, and starts from (volume 0, |query - root.position|). Hence: if the closest same-normal
-// volume N among ALL volumes within one grid cell of the query (the 27-cell neighbourhood) has distance
-// r <= accept_r (accept_r < min(cell size, within_abs)), N is also the kd search's winner among leaves, and the kd answer
-// is r < d0 ? N : 0. Anything else -- no candidate, r > accept_r, two candidates whose rounded distances tie (the kd
-// answer then depends on visit order), a query outside the grid -- returns -1 and the caller runs the kd search itself.
-// Layout: dense nx*ny*nz array of start offsets (x fastest) into per-cell candidate lists; the list of a cell holds
-// every volume of its 27-cell neighbourhood as (position, normal class), so a query reads ONE contiguous range.
-// cell(x) = floor((x - origin) / h). Candidates are ranked on the squared distance (the argument of the reference's
-// sqrt, same rounding sequence); only the winner and the runner-up are square-rooted, to detect ties after rounding.
-struct VolGrid { float ox, oy, oz, inv_h, accept_r; int nx, ny, nz; };
+// volume N among ALL volumes has distance r <= accept_r (accept_r < within_abs), the ball of radius r lies inside the
+// visited box, N is the kd search's winner among leaves, and the kd answer is r < d0 ? N : 0.
+// The closest same-normal volume is found from a precomputed list: a fine uniform grid (cells a fraction of the volume
+// spacing) over the surfaces; for each (cell, normal class) the host lists every volume that can be the closest one
+// within accept_r of some point of the cell (rlpt_radiance_host.cpp, host_build_vcells) -- a handful instead of the whole
+// neighbourhood. (cell, class) -> list goes through an open-addressing hash table, one 16-byte entry per pair.
+// Anything else -- no entry, no candidate within accept_r, two candidates whose rounded distances tie (the kd answer then
+// depends on visit order), a query outside the grid -- returns -1 and the caller runs the kd search itself.
+// Candidates are ranked on the squared distance (the argument of the reference's sqrt, same rounding sequence); only
+// the winner and the runner-up are square-rooted, to detect ties after rounding.
+struct VCells { float ox, oy, oz, inv_h, accept_r; int nx, ny, nz; uint32_t mask; };
 RLPT_HD float grid_coord(float x, float o, float inv_h) { return floorf(RLPT_MUL(RLPT_SUB(x, o), inv_h)); }
 RLPT_HD float kd_distance2(float px, float py, float pz, float qx, float qy, float qz) {
     float dx = RLPT_SUB(qx, px), dy = RLPT_SUB(qy, py), dz = RLPT_SUB(qz, pz);
     return RLPT_FMA(dz, dz, RLPT_FMA(dx, dx, RLPT_MUL(dy, dy)));
 }
-template <class LoadStart, class LoadCand>
-RLPT_HD int grid_find(const VolGrid& g, LoadStart load_start, LoadCand load_cand, float px, float py, float pz, int normal_class,
-                      float d0, int& best_slot) {
+RLPT_HD uint32_t vcell_hash(uint32_t cell, uint32_t cls) {
+    uint32_t h = (cell * 0x9E3779B1u) ^ (cls * 0x85EBCA77u);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+// load_entry(slot, cell, cls, start, n4) reads one table slot; load_cand(i, x, y, z, vol) one candidate (vol = -1: padding)
+template <class LoadEntry, class LoadCand>
+RLPT_HD int vcell_find(const VCells& g, LoadEntry load_entry, LoadCand load_cand, float px, float py, float pz, int normal_class, float d0) {
     float ux = grid_coord(px, g.ox, g.inv_h), uy = grid_coord(py, g.oy, g.inv_h), uz = grid_coord(pz, g.oz, g.inv_h);
     if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz)) return -1;
     const int cell = ((int)uz * g.ny + (int)uy) * g.nx + (int)ux;
-    const int s = load_start(cell), e = load_start(cell + 1);
+    uint32_t slot = vcell_hash((uint32_t)cell, (uint32_t)normal_class) & g.mask;
+    int start = 0, n4 = 0;
+    for (int probe = 0; ; ++probe) {
+        int ec, ek; load_entry(slot, ec, ek, start, n4);
+        if (ec == cell && ek == normal_class) break;
+        if (ec < 0 || probe >= 32) return -1;
+        slot = (slot + 1) & g.mask;
+    }
     float best2 = 3.0e38f, second2 = 3.0e38f; int best = -1;
-    // four candidates per trip: the loads are issued together (independent addresses), then ranked in list order
-    for (int i = s; i < e; i += 4) {
-        float vx[4], vy[4], vz[4]; int cls[4];
+    for (int i = 0; i < n4; ++i) {
+        float vx[4], vy[4], vz[4]; int vol[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int k = 0; k < 4; ++k) { int j = i + k < e ? i + k : e - 1; load_cand(j, vx[k], vy[k], vz[k], cls[k]); }
+        for (int k = 0; k < 4; ++k) load_cand(4 * (start + i) + k, vx[k], vy[k], vz[k], vol[k]);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int k = 0; k < 4; ++k) {
             float d2 = kd_distance2(px, py, pz, vx[k], vy[k], vz[k]);
-            if (i + k < e && cls[k] == normal_class) {
-                second2 = fminf(second2, fmaxf(d2, best2));
-                if (d2 < best2) { best2 = d2; best = i + k; }
-            }
+            second2 = fminf(second2, fmaxf(d2, best2));
+            if (d2 < best2) { best2 = d2; best = vol[k]; }
         }
     }
     if (best < 0) return -1;
     const float best_d = RLPT_SQRT(best2);
     if (!(best_d <= g.accept_r) || RLPT_SQRT(second2) == best_d) return -1;
-    best_slot = best;
-    return best_d < d0 ? 1 : 0;          // 1: the volume in slot `best_slot` wins; 0: volume 0 stays
+    return best_d < d0 ? best : 0;
 }
 
 }  // namespace rlpt

@@ -42,11 +42,10 @@ struct RadianceDev {
     uint32_t root;            // KD child word of the root
     float root_px, root_py, root_pz;   // radiance_array[0].position as the reference initialises its search with
     float within_abs;         // exact float form of the reference's pow(delta,2) < MAX_DIST test (rlpt_device.cuh, kd_find)
-    // uniform-grid front end of the nearest-volume search (rlpt_device.cuh, grid_find)
-    VolGrid grid;
-    const int* grid_start;    // [nx*ny*nz + 1]
-    const float4* grid_posn;  // [n_cand] per-cell candidate lists: (position, as_float(normal class)) of the 27-cell neighbourhood
-    const int* grid_vol;      // [n_cand] volume index of each candidate slot
+    // candidate-cell front end of the nearest-volume search (rlpt_device.cuh, vcell_find)
+    VCells vc;
+    const int4* vc_table;     // [vc.mask + 1] (cell, class, first candidate group, groups of 4); cell = -1: empty
+    const float4* vc_cand;    // (position, as_float(volume index)); lists padded to groups of 4 with volume -1
 };
 
 // ---- wavefront path state, SoA, one slot per live path (two queues, ping-pong per bounce)
@@ -67,9 +66,10 @@ struct FrameParams {
     SceneDev scene;
     RadianceDev rm;
     PathQueue q[2];
+    float2* hit;                    // split pipeline: (t, as_float(primitive id)) per slot of the current queue
     int* counts;                    // [max_bounces + 1] live paths entering each bounce (this lane)
     float4* accum;                  // [W*H] radiance sums (rgb) + sample count in w
-    unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests
+    unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests, [5] kd-search fallbacks
     float4* capture_o; float4* capture_d; int* capture_n;
     int width, height, spp, max_bounces;     // spp = samples per pixel traced by this lane
     uint32_t seed;
@@ -81,6 +81,9 @@ constexpr int BLOCK = 256;
 // host-visible launchers (rlpt_kernels.cu)
 void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s);
 void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_tail(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_isect(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s);
+void launch_shade(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, cudaStream_t s);
 // Neural-Q training tracer state (NeuralQPathtracer, G/deep_learning/neural_q_pathtracer.cu:76-96): one slot per pixel,
 // every ray takes part in every bounce (terminated rays are re-seeded on the geometry and keep generating training data)
 struct NqTrainState {

@@ -33,12 +33,12 @@ struct SceneView {
 };
 
 // Every CTA copies what fits of the scene into shared memory once (vectorised 16-byte loads, coalesced).
-template <bool STAGED>
+template <bool STAGED, bool SHADE = true>
 __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     SceneView<STAGED> v;
     v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute;
     float4* p = s_scene;
-    int nt = 3 * sc.smem_tris, ns = sc.smem_shade ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
+    int nt = 3 * sc.smem_tris, ns = (SHADE && sc.smem_shade) ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
     v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
     for (int i = threadIdx.x; i < nt; i += blockDim.x) p[i] = __ldg(sc.tri + i);
     for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
@@ -139,7 +139,7 @@ template <bool STAGED, bool COUNT>
 __global__ void __launch_bounds__(BLOCK) k_closest_hit(SceneDev sc, const float* __restrict__ org, const float* __restrict__ dir, int n, float H,
                                                        int* __restrict__ type, int* __restrict__ index, float* __restrict__ t_out,
                                                        unsigned long long* __restrict__ counters) {
-    SceneView<STAGED> v = stage_scene<STAGED>(sc);
+    SceneView<STAGED> v = stage_scene<STAGED, false>(sc);
     unsigned nt = 0, nb = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         f3 d = normalize_ref(f3{ dir[3 * i], dir[3 * i + 1], dir[3 * i + 2] });
@@ -169,19 +169,18 @@ void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, 
 }
 
 // ------------------------------------------------------------------------------------------------ nearest volume
-__device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, float py, float pz, int cls) {
+__device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, float py, float pz, int cls, unsigned& n_kd) {
     const float4* __restrict__ inner = rm.kd_inner; const float4* __restrict__ posn = rm.vol_posn;
-    if (rm.grid_start) {
-        const int* __restrict__ gs = rm.grid_start; const float4* __restrict__ gp = rm.grid_posn;
+    if (rm.vc_table) {
+        const int4* __restrict__ tb = rm.vc_table; const float4* __restrict__ cd = rm.vc_cand;
         const float d0 = kd_distance(px, py, pz, rm.root_px, rm.root_py, rm.root_pz);
-        int slot = 0;
-        int r = grid_find(rm.grid, [&](int i) { return __ldg(gs + i); },
-                          [&](int i, float& x, float& y, float& z, int& c) { float4 p = __ldg(gp + i); x = p.x; y = p.y; z = p.z; c = __float_as_int(p.w); },
-                          px, py, pz, cls, d0, slot);
-        if (r == 1) return __ldg(rm.grid_vol + slot);
-        if (r == 0) return 0;
+        int r = vcell_find(rm.vc, [&](uint32_t i, int& c, int& k, int& s, int& n) { int4 e = __ldg(tb + i); c = e.x; k = e.y; s = e.z; n = e.w; },
+                           [&](int i, float& x, float& y, float& z, int& v) { float4 p = __ldg(cd + i); x = p.x; y = p.y; z = p.z; v = __float_as_int(p.w); },
+                           px, py, pz, cls, d0);
+        if (r >= 0) return r;
     }
-    // exact reference search: the rare queries the grid cannot decide (far from every volume, distance ties)
+    // exact reference search: the rare queries the candidate cells cannot decide (far from every volume, distance ties)
+    n_kd++;
     return kd_find(
         [&](uint32_t idx, float& split, uint32_t& l, uint32_t& r, int& dim) {
             float4 n = __ldg(inner + idx); split = n.x; l = __float_as_uint(n.y); r = __float_as_uint(n.z); dim = __float_as_int(n.w);
@@ -192,7 +191,8 @@ __device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, floa
 
 __global__ void __launch_bounds__(BLOCK) k_find_closest(RadianceDev rm, const float* __restrict__ pos, const int* __restrict__ cls, int n, int* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = find_volume(rm, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], cls[i]);
+    unsigned n_kd = 0;
+    if (i < n) out[i] = find_volume(rm, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], cls[i], n_kd);
 }
 void launch_find_closest(const RadianceDev& rm, const SceneDev&, const float* pos, const float* cls_as_float, int n, int* out, cudaStream_t s) {
     k_find_closest<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(rm, pos, reinterpret_cast<const int*>(cls_as_float), n, out);
@@ -224,146 +224,273 @@ __device__ __forceinline__ void td_accumulate(const RadianceDev& rm, bool active
 }
 
 // ------------------------------------------------------------------------------------------------ wavefront kernels
-// One bounce of one path. PRIMARY: the path is generated here (raygen fused with the first cast).
-template <bool STAGED, bool SARSA, bool PRIMARY>
+// Two pipelines trace a frame (DESIGN.md "Wavefront"):
+//   split  per bounce k_isect (closest hit only: ~40 registers, every warp slot of the SM filled, FP32-pipe bound) writes
+//          (t, primitive) per queue slot, then k_shade (nearest volume, TD target, direction sampling, compaction:
+//          L2-latency bound, no triangle data) consumes it
+//   fused  k_bounce does both in one launch; with TAIL it keeps every path in its thread until it terminates -- used once
+//          the live-path count is below one wave, where a launch per bounce would only add its latency
 #ifndef RLPT_MINBLOCKS
 #define RLPT_MINBLOCKS 1
 #endif
 #ifndef RLPT_CDF_2LEVEL
 #define RLPT_CDF_2LEVEL 1
 #endif
-__global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
-    SceneView<STAGED> v = stage_scene<STAGED>(p.scene);
+#ifndef RLPT_SHADE_MINBLOCKS
+#define RLPT_SHADE_MINBLOCKS 4
+#endif
+#ifndef RLPT_ISECT_MINBLOCKS
+#define RLPT_ISECT_MINBLOCKS 6
+#endif
+
+struct PathState {
+    float ox, oy, oz, dx, dy, dz, tr, tg, tb, cur_brdf;
+    uint32_t pixel, sample, volsec;
+};
+
+// camera sample `i` of this lane: Ray::sample_ray_through_pixel (G/rays/ray.cu:144-172) with Philox counters (pixel, sample)
+__device__ __forceinline__ void primary_state(const FrameParams& p, const FrameDyn& dyn, int i, PathState& s) {
+    s.pixel = (uint32_t)(i / p.spp); s.sample = dyn.sample_base + (uint32_t)(i % p.spp);
+    float u0, u1, u2, u3; draw4(p.seed, s.pixel, s.sample, 0u, PURPOSE_CAMERA, u0, u1, u2, u3);
+    f3 d = camera_dir((int)(s.pixel / (uint32_t)p.height), (int)(s.pixel % (uint32_t)p.height), u0, u1, p.width, p.height, dyn.rotated != 0, dyn.cy, dyn.sy, dyn.cx, dyn.sx);
+    s.ox = dyn.cam_x; s.oy = dyn.cam_y; s.oz = dyn.cam_z; s.dx = d.x; s.dy = d.y; s.dz = d.z;
+    s.tr = s.tg = s.tb = 1.f; s.cur_brdf = 0.f; s.volsec = 0u;
+}
+__device__ __forceinline__ void load_state(const PathQueue& q, int i, PathState& s) {
+    float4 a = q.o[i], b = q.d[i], c = q.thr[i]; uint32_t m = q.meta[i];
+    s.ox = a.x; s.oy = a.y; s.oz = a.z; s.pixel = __float_as_uint(a.w);
+    s.dx = b.x; s.dy = b.y; s.dz = b.z; s.cur_brdf = b.w;
+    s.tr = c.x; s.tg = c.y; s.tb = c.z; s.volsec = __float_as_uint(c.w); s.sample = m >> 8;
+}
+__device__ __forceinline__ void store_state(const PathQueue& q, int slot, const PathState& s, int bounce) {
+    q.o[slot] = make_float4(s.ox, s.oy, s.oz, __uint_as_float(s.pixel));
+    q.d[slot] = make_float4(s.dx, s.dy, s.dz, s.cur_brdf);
+    q.thr[slot] = make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec));
+    q.meta[slot] = (s.sample << 8) | (uint32_t)bounce;
+}
+// wavefront compaction: survivors are packed densely into the next bounce's queue (one atomicAdd per warp)
+__device__ __forceinline__ void compact_store(const FrameParams& p, const PathQueue& qo, int bounce, bool alive, const PathState& s) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    unsigned bal = __ballot_sync(full, alive);
+    if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p.counts + bounce + 1, __popc(bal));
+        base = __shfl_sync(full, base, 0);
+        if (alive) store_state(qo, base + __popc(bal & lanemask_lt()), s, bounce + 1);
+    }
+}
+
+// Everything of one bounce after the closest hit (t, gid) of path `s` is known: TD target of the previous (volume,
+// sector), termination into the frame buffer, or the next direction. Returns true when the path goes on; `s` then holds
+// the next ray. Called by whole warps (td_accumulate is a warp collective); `valid` marks the lanes that hold a path.
+// path_trace_iterative (G/path_tracing/default_path_tracing.cu:36-88) / path_trace_reinforcement_iterative
+// (G/path_tracing/reinforcement_path_tracing.cu:48-120).
+template <bool SARSA, bool TD_PREV, class ShadeLoad>
+__device__ __forceinline__ bool shade_step(const FrameParams& p, const FrameDyn& dyn, const ShadeLoad& shade, int n_surf, int bounce, bool valid,
+                                           PathState& s, float t, int gid, unsigned& st_len, unsigned& st_zero, unsigned& st_term, unsigned& n_kd) {
+    const bool surface = valid && gid >= 0 && gid < n_surf;
+    const bool light = valid && gid >= n_surf;
+    float hx = 0, hy = 0, hz = 0; float4 sN = make_float4(0, 1, 0, 0), sT = make_float4(1, 0, 0, 0);
+    int nv = 0;
+    if (surface) {
+        const float H = (float)p.height;
+        const float sdx = RLPT_MUL(s.dx, H), sdy = RLPT_MUL(s.dy, H), sdz = RLPT_MUL(s.dz, H);      // dir * SCREEN_HEIGHT (ray.cu:53)
+        hx = RLPT_FMA(sdx, t, s.ox); hy = RLPT_FMA(sdy, t, s.oy); hz = RLPT_FMA(sdz, t, s.oz);      // position = start + t*dir (ray.cu:65)
+        sN = shade(4 * gid); sT = shade(4 * gid + 1);
+        if (SARSA) nv = find_volume(p.rm, hx, hy, hz, __float_as_int(sT.w), n_kd);
+    }
+    if (SARSA && TD_PREV) {
+        // RadianceMap::temporal_difference_update_radiance_volume_sector (radiance_map.cu:111-146): target by hit type
+        float target = 0.f;
+        if (surface) target = __ldg(p.rm.irradiance + nv) * ((2.f * PI_F) / 144.f) * s.cur_brdf;   // get_irradiance_estimate (radiance_volume.cu:305-307)
+        else if (light) target = s.cur_brdf * shade(4 * gid).w;
+        else target = s.cur_brdf * p.env;
+        td_accumulate(p.rm, valid && dyn.learn, (s.volsec >> 8) * (uint32_t)CELLS + (s.volsec & 0xffu), target);
+    }
+    if (valid && !surface) {
+        // NOTHING: throughput * ENVIRONMENT_LIGHT; AREA_LIGHT: throughput * diffuse_p (default_path_tracing.cu:52-63)
+        float lr = p.env, lg = p.env, lb = p.env;
+        if (light) { float4 e = shade(4 * gid + 3); lr = e.x; lg = e.y; lb = e.z; }
+        lr *= s.tr; lg *= s.tg; lb *= s.tb;
+        if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + s.pixel, make_float4(lr, lg, lb, 0.f));
+        st_len += (unsigned)bounce + 1u; st_term++;
+        if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;                                         // THROUGHPUT_THRESHOLD
+        return false;
+    }
+    if (!surface) return false;
+    if (bounce + 1 >= p.max_bounces) {            // the reference's loop ends here and returns vec3(0), path_length = MAX_RAY_BOUNCES
+        st_len += (unsigned)p.max_bounces; st_term++; st_zero++;
+        return false;
+    }
+    float4 sB = shade(4 * gid + 2), sC = shade(4 * gid + 3);
+    f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
+    float u0, u1, u2, u3; draw4(p.seed, s.pixel, s.sample, (uint32_t)bounce, PURPOSE_BOUNCE, u0, u1, u2, u3);
+    f3 nd; float scale;
+    if (SARSA) {
+        // importance_sample_ray_direction -> sample_direction_from_radiance_distribution (radiance_volume.cu:192-244)
+        const float* __restrict__ row = p.rm.cdf + (size_t)nv * CELLS;
+#if RLPT_CDF_2LEVEL
+        const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(p.rm.cdf_rows + (size_t)nv * GRID);
+        const float4* __restrict__ row4 = reinterpret_cast<const float4*>(row);
+        float pdf; int sector = sample_sector_2level(
+            [&](float (&e)[12]) { float4 a = __ldg(rows4), b = __ldg(rows4 + 1), c = __ldg(rows4 + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
+            [&](int j, float (&e)[12]) { float4 a = __ldg(row4 + 3 * j), b = __ldg(row4 + 3 * j + 1), c = __ldg(row4 + 3 * j + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
+            [&](int k) { return __ldg(row + k); }, u0, pdf);
+#else
+        float pdf; int sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
+#endif
+        nd = grid_to_direction((float)(sector / GRID) + u1, (float)(sector % GRID) + u2, T, N, B);
+        float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;                       // reinforcement_path_tracing.cu:107
+        scale = cos_theta / pdf;
+        s.volsec = ((uint32_t)nv << 8) | (uint32_t)sector;
+        s.cur_brdf = sN.w;                                                            // material.luminance / pi (:109)
+    } else {
+        nd = uniform_hemisphere(u0, u1, T, N, B);                                     // cos_theta = u0, pdf = RHO
+        scale = u0 / RHO;
+    }
+    s.tr *= sC.x * scale; s.tg *= sC.y * scale; s.tb *= sC.z * scale;
+    s.ox = RLPT_FMA(RAY_EPS, nd.x, hx); s.oy = RLPT_FMA(RAY_EPS, nd.y, hy); s.oz = RLPT_FMA(RAY_EPS, nd.z, hz);
+    f3 nn = normalize_ref(nd); s.dx = nn.x; s.dy = nn.y; s.dz = nn.z;
+    return true;
+}
+
+__device__ __forceinline__ void flush_path_stats(const FrameParams& p, unsigned st_len, unsigned st_zero, unsigned st_term, unsigned n_kd) {
     const unsigned full = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31;
-    const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
+    st_len = __reduce_add_sync(full, st_len); st_zero = __reduce_add_sync(full, st_zero); st_term = __reduce_add_sync(full, st_term); n_kd = __reduce_add_sync(full, n_kd);
+    if ((threadIdx.x & 31) == 0 && n_kd) atomicAdd(p.stats + 5, (unsigned long long)n_kd);
+    if ((threadIdx.x & 31) == 0 && st_term) {
+        atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term);
+    }
+}
+// work counters for the roofline: triangle tests and box tests actually executed; two integer adds per
+// test next to ~72 / ~18 FP32 operations, so they stay on in the product build
+__device__ __forceinline__ void flush_work_counters(const FrameParams& p, unsigned n_tri, unsigned n_box) {
+    const unsigned full = 0xffffffffu;
+    n_tri = __reduce_add_sync(full, n_tri); n_box = __reduce_add_sync(full, n_box);
+    if ((threadIdx.x & 31) == 0 && (n_tri | n_box)) { atomicAdd(p.stats + 3, (unsigned long long)n_tri); atomicAdd(p.stats + 4, (unsigned long long)n_box); }
+}
+__device__ __forceinline__ void capture_ray(const FrameParams& p, const FrameDyn& dyn, int bounce, bool valid, const PathState& s) {
+    if (dyn.capture_max > 0 && bounce == dyn.capture_bounce && valid) {
+        int slot = atomicAdd(p.capture_n, 1);
+        if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(s.ox, s.oy, s.oz, 0.f); p.capture_d[slot] = make_float4(s.dx, s.dy, s.dz, 0.f); }
+    }
+}
+
+// Fused: one bounce of one path per thread (PRIMARY: the path is generated here), or with TAIL every remaining bounce.
+template <bool STAGED, bool SARSA, bool PRIMARY, bool TAIL>
+__global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0;
-    const float H = (float)p.height;
     const int n_round = (n_in + 31) & ~31;                        // whole warps stay together for the collectives
+    if ((int)(blockIdx.x * blockDim.x) >= n_round) return;        // nothing for this CTA: do not even stage the scene
+    SceneView<STAGED> v = stage_scene<STAGED, true>(p.scene);
+    const unsigned full = 0xffffffffu;
+    const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
+    unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0, n_kd = 0;
+    const float H = (float)p.height;
+    auto shade = [&](int k) { return v.shade(k); };
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool valid = i < n_in;
-        float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1, tr = 1, tg = 1, tb = 1, cur_brdf = 0;
-        uint32_t pixel = 0, sample = 0, volsec = 0;
-        if (valid) {
+        bool live = i < n_in;
+        PathState s{};
+        if (live) {
             if (PRIMARY) {
-                pixel = (uint32_t)(i / p.spp); sample = dyn.sample_base + (uint32_t)(i % p.spp);
-                float u0, u1, u2, u3; draw4(p.seed, pixel, sample, 0u, PURPOSE_CAMERA, u0, u1, u2, u3);
-                f3 d = camera_dir((int)(pixel / (uint32_t)p.height), (int)(pixel % (uint32_t)p.height), u0, u1, p.width, p.height, dyn.rotated != 0, dyn.cy, dyn.sy, dyn.cx, dyn.sx);
-                ox = dyn.cam_x; oy = dyn.cam_y; oz = dyn.cam_z; dx = d.x; dy = d.y; dz = d.z;
-                if (i % p.spp == 0) atomicAdd(&p.accum[pixel].w, (float)p.spp);          // samples accumulated for this pixel
-            } else {
-                float4 a = qi.o[i], b = qi.d[i], c = qi.thr[i]; uint32_t m = qi.meta[i];
-                ox = a.x; oy = a.y; oz = a.z; pixel = __float_as_uint(a.w);
-                dx = b.x; dy = b.y; dz = b.z; cur_brdf = b.w;
-                tr = c.x; tg = c.y; tb = c.z; volsec = __float_as_uint(c.w); sample = m >> 8;
-            }
+                primary_state(p, dyn, i, s);
+                if (i % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);          // samples accumulated for this pixel
+            } else load_state(qi, i, s);
         }
-        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce && valid) {
+        int b = bounce;
+        while (true) {
+            capture_ray(p, dyn, b, live, s);
+            float t = T_MISS, sdx, sdy, sdz; int gid = -1;
+            if (live) closest_hit<STAGED, true>(v, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+            if (PRIMARY) live = shade_step<SARSA, false>(p, dyn, shade, v.n_surf, b, live, s, t, gid, st_len, st_zero, st_term, n_kd);
+            else live = shade_step<SARSA, true>(p, dyn, shade, v.n_surf, b, live, s, t, gid, st_len, st_zero, st_term, n_kd);
+            if (!TAIL) break;
+            ++b;
+            if (!__any_sync(full, live)) break;
+        }
+        if (!TAIL) compact_store(p, qo, bounce, live, s);
+    }
+    flush_path_stats(p, st_len, st_zero, st_term, n_kd);
+    flush_work_counters(p, n_tri, n_box);
+}
+
+// Split, first half: the closest hit of every ray of queue `bounce` -> hit[slot] = (t, as_float(primitive id))
+template <bool STAGED, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
+    if ((int)(blockIdx.x * blockDim.x) >= n_in) return;
+    SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
+    const PathQueue qi = p.q[bounce & 1];
+    unsigned n_tri = 0, n_box = 0;
+    const float H = (float)p.height;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+        float ox, oy, oz, dx, dy, dz;
+        if (PRIMARY) {
+            PathState s; primary_state(p, dyn, i, s);
+            ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz;
+        } else {
+            float4 a = qi.o[i], b = qi.d[i];
+            ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z;
+        }
+        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
             int slot = atomicAdd(p.capture_n, 1);
             if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
         }
-        float t = T_MISS, sdx = 0, sdy = 0, sdz = 0; int gid = -1;
-        if (valid) closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
-        const bool surface = valid && gid >= 0 && gid < v.n_surf;
-        const bool light = valid && gid >= v.n_surf;
-        float hx = 0, hy = 0, hz = 0; float4 sN = make_float4(0, 1, 0, 0), sT = make_float4(1, 0, 0, 0);
-        int nv = 0;
-        if (surface) {
-            hx = RLPT_FMA(sdx, t, ox); hy = RLPT_FMA(sdy, t, oy); hz = RLPT_FMA(sdz, t, oz);   // position = start + t*dir (ray.cu:65)
-            sN = v.shade(4 * gid); sT = v.shade(4 * gid + 1);
-            if (SARSA) nv = find_volume(p.rm, hx, hy, hz, __float_as_int(sT.w));
-        }
-        if (SARSA && !PRIMARY) {
-            // RadianceMap::temporal_difference_update_radiance_volume_sector (radiance_map.cu:111-146): target by hit type
-            float target = 0.f;
-            if (surface) target = __ldg(p.rm.irradiance + nv) * ((2.f * PI_F) / 144.f) * cur_brdf;   // get_irradiance_estimate (radiance_volume.cu:305-307)
-            else if (light) target = cur_brdf * v.shade(4 * gid).w;
-            else target = cur_brdf * p.env;
-            td_accumulate(p.rm, valid && dyn.learn, (volsec >> 8) * (uint32_t)CELLS + (volsec & 0xffu), target);
-        }
-        bool alive = false;
-        if (valid && !surface) {
-            // NOTHING: throughput * ENVIRONMENT_LIGHT; AREA_LIGHT: throughput * diffuse_p (default_path_tracing.cu:52-63)
-            float lr = p.env, lg = p.env, lb = p.env;
-            if (light) { float4 e = v.shade(4 * gid + 3); lr = e.x; lg = e.y; lb = e.z; }
-            lr *= tr; lg *= tg; lb *= tb;
-            if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + pixel, make_float4(lr, lg, lb, 0.f));
-            st_len += (unsigned)bounce + 1u; st_term++;
-            if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;                                         // THROUGHPUT_THRESHOLD
-        } else if (surface) {
-            if (bounce + 1 >= p.max_bounces) {            // the reference's loop ends here and returns vec3(0), path_length = MAX_RAY_BOUNCES
-                st_len += (unsigned)p.max_bounces; st_term++; st_zero++;
-            } else {
-                float4 sB = v.shade(4 * gid + 2), sC = v.shade(4 * gid + 3);
-                f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
-                float u0, u1, u2, u3; draw4(p.seed, pixel, sample, (uint32_t)bounce, PURPOSE_BOUNCE, u0, u1, u2, u3);
-                f3 nd; float scale;
-                if (SARSA) {
-                    // importance_sample_ray_direction -> sample_direction_from_radiance_distribution (radiance_volume.cu:192-244)
-                    const float* __restrict__ row = p.rm.cdf + (size_t)nv * CELLS;
-                    const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(p.rm.cdf_rows + (size_t)nv * GRID);
-                    const float4* __restrict__ row4 = reinterpret_cast<const float4*>(row);
-#if RLPT_CDF_2LEVEL
-                    float pdf; int sector = sample_sector_2level(
-                        [&](float (&e)[12]) { float4 a = __ldg(rows4), b = __ldg(rows4 + 1), c = __ldg(rows4 + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
-                        [&](int j, float (&e)[12]) { float4 a = __ldg(row4 + 3 * j), b = __ldg(row4 + 3 * j + 1), c = __ldg(row4 + 3 * j + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
-                        [&](int k) { return __ldg(row + k); }, u0, pdf);
-#else
-                    float pdf; int sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
-#endif
-                    nd = grid_to_direction((float)(sector / GRID) + u1, (float)(sector % GRID) + u2, T, N, B);
-                    float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;                       // reinforcement_path_tracing.cu:107
-                    scale = cos_theta / pdf;
-                    volsec = ((uint32_t)nv << 8) | (uint32_t)sector;
-                    cur_brdf = sN.w;                                                              // material.luminance / pi (:109)
-                } else {
-                    nd = uniform_hemisphere(u0, u1, T, N, B);                                     // cos_theta = u0, pdf = RHO
-                    scale = u0 / RHO;
-                }
-                tr *= sC.x * scale; tg *= sC.y * scale; tb *= sC.z * scale;
-                ox = RLPT_FMA(RAY_EPS, nd.x, hx); oy = RLPT_FMA(RAY_EPS, nd.y, hy); oz = RLPT_FMA(RAY_EPS, nd.z, hz);
-                f3 nn = normalize_ref(nd); dx = nn.x; dy = nn.y; dz = nn.z;
-                alive = true;
-            }
-        }
-        // wavefront compaction: survivors are packed densely into the next bounce's queue
-        unsigned bal = __ballot_sync(full, alive);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(p.counts + bounce + 1, __popc(bal));
-            base = __shfl_sync(full, base, 0);
-            if (alive) {
-                int slot = base + __popc(bal & lanemask_lt());
-                qo.o[slot] = make_float4(ox, oy, oz, __uint_as_float(pixel));
-                qo.d[slot] = make_float4(dx, dy, dz, cur_brdf);
-                qo.thr[slot] = make_float4(tr, tg, tb, __uint_as_float(volsec));
-                qo.meta[slot] = (sample << 8) | (uint32_t)(bounce + 1);
-            }
-        }
+        float t, sdx, sdy, sdz; int gid;
+        closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        p.hit[i] = make_float2(t, __int_as_float(gid));
     }
-    st_len = __reduce_add_sync(full, st_len); st_zero = __reduce_add_sync(full, st_zero); st_term = __reduce_add_sync(full, st_term);
-    if (lane == 0 && st_term) {
-        atomicAdd(p.stats + 0, (unsigned long long)st_len); atomicAdd(p.stats + 1, (unsigned long long)st_zero); atomicAdd(p.stats + 2, (unsigned long long)st_term);
-    }
-    // work counters for the roofline: triangle tests and box tests actually executed; two integer adds per
-    // test next to ~72 / ~18 FP32 operations, so they stay on in the product build
-    n_tri = __reduce_add_sync(full, n_tri); n_box = __reduce_add_sync(full, n_box);
-    if (lane == 0 && (n_tri | n_box)) { atomicAdd(p.stats + 3, (unsigned long long)n_tri); atomicAdd(p.stats + 4, (unsigned long long)n_box); }
+    flush_work_counters(p, n_tri, n_box);
 }
 
+// Split, second half: shading records come through the read-only path (2.4 KB for Cornell: L1-resident), no staging
 template <bool SARSA, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
+    const int n_round = (n_in + 31) & ~31;
+    const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
+    unsigned st_len = 0, st_zero = 0, st_term = 0, n_kd = 0;
+    const float4* __restrict__ shade_g = p.scene.shade;
+    auto shade = [&](int k) { return __ldg(shade_g + k); };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool live = i < n_in;
+        PathState s{}; float t = T_MISS; int gid = -1;
+        if (live) {
+            if (PRIMARY) {
+                primary_state(p, dyn, i, s);
+                if (i % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);
+            } else load_state(qi, i, s);
+            float2 h = p.hit[i]; t = h.x; gid = __float_as_int(h.y);
+        }
+        live = shade_step<SARSA, !PRIMARY>(p, dyn, shade, p.scene.n_surf, bounce, live, s, t, gid, st_len, st_zero, st_term, n_kd);
+        compact_store(p, qo, bounce, live, s);
+    }
+    flush_path_stats(p, st_len, st_zero, st_term, n_kd);
+}
+
+static bool scene_staged(const SceneDev& sc) { return sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes; }
+template <bool SARSA, bool PRIMARY, bool TAIL>
 static void launch_bounce_t(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
-    const SceneDev& sc = p.scene;
-    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
-    if (staged) k_bounce<true, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
-    else k_bounce<false, SARSA, PRIMARY><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
+    if (scene_staged(p.scene)) k_bounce<true, SARSA, PRIMARY, TAIL><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
+    else k_bounce<false, SARSA, PRIMARY, TAIL><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
 }
 void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s) {
-    if (method == 1) launch_bounce_t<true, true>(p, dyn, 0, grid, smem, s); else launch_bounce_t<false, true>(p, dyn, 0, grid, smem, s);
+    if (method == 1) launch_bounce_t<true, true, false>(p, dyn, 0, grid, smem, s); else launch_bounce_t<false, true, false>(p, dyn, 0, grid, smem, s);
 }
 void launch_bounce(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s) {
-    if (method == 1) launch_bounce_t<true, false>(p, dyn, bounce, grid, smem, s); else launch_bounce_t<false, false>(p, dyn, bounce, grid, smem, s);
+    if (method == 1) launch_bounce_t<true, false, false>(p, dyn, bounce, grid, smem, s); else launch_bounce_t<false, false, false>(p, dyn, bounce, grid, smem, s);
+}
+void launch_tail(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, size_t smem, cudaStream_t s) {
+    if (method == 1) launch_bounce_t<true, false, true>(p, dyn, bounce, grid, smem, s); else launch_bounce_t<false, false, true>(p, dyn, bounce, grid, smem, s);
+}
+void launch_isect(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
+    const bool staged = scene_staged(p.scene);
+    if (bounce == 0) { if (staged) k_isect<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_isect<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
+    else { if (staged) k_isect<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_isect<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
+}
+void launch_shade(const FrameParams& p, const FrameDyn& dyn, int method, int bounce, int grid, cudaStream_t s) {
+    if (method == 1) { if (bounce == 0) k_shade<true, true><<<grid, BLOCK, 0, s>>>(p, dyn, 0); else k_shade<true, false><<<grid, BLOCK, 0, s>>>(p, dyn, bounce); }
+    else { if (bounce == 0) k_shade<false, true><<<grid, BLOCK, 0, s>>>(p, dyn, 0); else k_shade<false, false><<<grid, BLOCK, 0, s>>>(p, dyn, bounce); }
 }
 
 // ------------------------------------------------------------------------------------------------ Neural-Q wavefront
@@ -634,8 +761,10 @@ void launch_add_scalar(float* dst, const float* src, cudaStream_t s) { k_add_sca
 int kernels_set_smem_limit(size_t bytes) {
     cudaError_t e = cudaSuccess;
 #define RLPT_SET(k) if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
-    RLPT_SET((k_bounce<true, true, true>)); RLPT_SET((k_bounce<true, true, false>)); RLPT_SET((k_bounce<true, false, true>)); RLPT_SET((k_bounce<true, false, false>));
-    RLPT_SET((k_bounce<false, true, true>)); RLPT_SET((k_bounce<false, true, false>)); RLPT_SET((k_bounce<false, false, true>)); RLPT_SET((k_bounce<false, false, false>));
+    RLPT_SET((k_bounce<true, true, true, false>)); RLPT_SET((k_bounce<true, true, false, false>)); RLPT_SET((k_bounce<true, false, true, false>)); RLPT_SET((k_bounce<true, false, false, false>));
+    RLPT_SET((k_bounce<false, true, true, false>)); RLPT_SET((k_bounce<false, true, false, false>)); RLPT_SET((k_bounce<false, false, true, false>)); RLPT_SET((k_bounce<false, false, false, false>));
+    RLPT_SET((k_bounce<true, true, false, true>)); RLPT_SET((k_bounce<true, false, false, true>)); RLPT_SET((k_bounce<false, true, false, true>)); RLPT_SET((k_bounce<false, false, false, true>));
+    RLPT_SET((k_isect<true, true>)); RLPT_SET((k_isect<true, false>)); RLPT_SET((k_isect<false, true>)); RLPT_SET((k_isect<false, false>));
     RLPT_SET((k_nqt_trace<true>)); RLPT_SET((k_nqt_trace<false>));
     RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));

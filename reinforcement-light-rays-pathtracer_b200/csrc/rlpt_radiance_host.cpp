@@ -10,6 +10,8 @@
 //   RadianceTree::RadianceTree / convert_to_array    G/radiance_volumes/radiance_tree.cu:12-62,135-196 (std::sort per level)
 // Built with -ffp-contract=off: one rounding per operator, as in the reference's -O0 host code.
 #include "rlpt_radiance_host.h"
+#include "rlpt_device.cuh"
+#include <unordered_map>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -104,6 +106,147 @@ void host_build_radiance_map(const float* surface_v, const float* surface_nrm, i
     HostTreeElement r0{}; r0.dim = root->dim; r0.data = root->median;
     tree.push_back(r0);
     if (nv > 0) b.flatten(root, 0);
+}
+
+
+// ------------------------------------------------------------------------------------------------ candidate cells
+// Why the lists are sufficient (DESIGN.md "Nearest volume"): let B be the cell's box (inflated by a rounding margin), v any
+// volume of the class. Every point p of B has its closest same-class volume within R = min_v maxdist(v, B), so that
+// volume has mindist(., B) <= R. Volumes farther than accept_r are never accepted by vcell_find, so only volumes with
+// mindist <= min(R, accept_r) (plus slack for the float rounding of the device's distances, which also keeps every
+// volume whose rounded distance could tie with the winner's) are listed.
+namespace {
+struct P3 { double x, y, z; };
+static inline P3 sub(P3 a, P3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+static inline double dotd(P3 a, P3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// squared distance from p to triangle abc (Ericson, Real-Time Collision Detection 5.1.5)
+static double point_triangle_dist2(P3 p, P3 a, P3 b, P3 c) {
+    P3 ab = sub(b, a), ac = sub(c, a), ap = sub(p, a);
+    double d1 = dotd(ab, ap), d2 = dotd(ac, ap);
+    auto d2to = [&](P3 q) { P3 d = sub(p, q); return dotd(d, d); };
+    if (d1 <= 0 && d2 <= 0) return d2to(a);
+    P3 bp = sub(p, b); double d3 = dotd(ab, bp), d4 = dotd(ac, bp);
+    if (d3 >= 0 && d4 <= d3) return d2to(b);
+    double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { double v = d1 / (d1 - d3); return d2to({ a.x + v * ab.x, a.y + v * ab.y, a.z + v * ab.z }); }
+    P3 cp = sub(p, c); double d5 = dotd(ab, cp), d6 = dotd(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return d2to(c);
+    double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { double w = d2 / (d2 - d6); return d2to({ a.x + w * ac.x, a.y + w * ac.y, a.z + w * ac.z }); }
+    double va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        return d2to({ b.x + w * (c.x - b.x), b.y + w * (c.y - b.y), b.z + w * (c.z - b.z) });
+    }
+    double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+    return d2to({ a.x + ab.x * v + ac.x * w, a.y + ab.y * v + ac.y * w, a.z + ab.z * v + ac.z * w });
+}
+}  // namespace
+
+void host_build_vcells(const float* sv, const int* sclass, int ns, const std::vector<HostVolume>& vol, const std::vector<int>& vclass,
+                       float cell_h, float accept_r, HostVCells& out) {
+    out = HostVCells{};
+    const int nv = (int)vol.size();
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (int i = 0; i < nv; ++i) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], (double)vol[i].pos[k]); hi[k] = std::max(hi[k], (double)vol[i].pos[k]); }
+    for (int i = 0; i < 9 * ns; ++i) { int k = i % 3; lo[k] = std::min(lo[k], (double)sv[i]); hi[k] = std::max(hi[k], (double)sv[i]); }
+    const double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
+    float h = std::max(cell_h, (float)(ext / 1000.0));                 // at most ~1000 cells per axis: the linear cell index stays below 2^31
+    if (!(h > 0.f)) h = 1e-3f;
+    out.h = h; out.ox = (float)lo[0] - h; out.oy = (float)lo[1] - h; out.oz = (float)lo[2] - h;
+    const float inv_h = 1.f / h;
+    out.nx = (int)grid_coord((float)hi[0], out.ox, inv_h) + 2; out.ny = (int)grid_coord((float)hi[1], out.oy, inv_h) + 2; out.nz = (int)grid_coord((float)hi[2], out.oz, inv_h) + 2;
+    if (nv == 0 || !(accept_r > 0.f)) { out.table.assign(4 * 2, -1); out.cand.assign(16, 0.f); return; }
+    const double scale = std::max(ext, 1.0), margin = 1e-5 * scale;      // box inflation: a point whose cell is decided by float rounding
+    const double reach = (double)accept_r * (1.0 + 1e-4) + 1e-6 * scale;
+    // coarse buckets of the volumes, cell size >= reach + box size, so a 3x3x3 block covers everything within reach of a box
+    const double cs = std::max(reach + 2.0 * margin + (double)h, ext / 256.0);
+    const int cnx = (int)std::floor((hi[0] - lo[0]) / cs) + 1, cny = (int)std::floor((hi[1] - lo[1]) / cs) + 1, cnz = (int)std::floor((hi[2] - lo[2]) / cs) + 1;
+    auto ccell = [&](double x, int k, int n) { int c = (int)std::floor((x - lo[k]) / cs); return std::min(std::max(c, 0), n - 1); };
+    std::vector<int> cstart((size_t)cnx * cny * cnz + 1, 0), corder(nv);
+    {
+        std::vector<int> cof(nv);
+        for (int i = 0; i < nv; ++i) { cof[i] = (ccell(vol[i].pos[2], 2, cnz) * cny + ccell(vol[i].pos[1], 1, cny)) * cnx + ccell(vol[i].pos[0], 0, cnx); cstart[cof[i] + 1]++; }
+        for (size_t k = 0; k + 1 < cstart.size(); ++k) cstart[k + 1] += cstart[k];
+        std::vector<int> fill(cstart.begin(), cstart.end() - 1);
+        for (int i = 0; i < nv; ++i) corder[fill[cof[i]]++] = i;
+    }
+    // (cell, class) pairs: every fine cell whose centre is within half a cell diagonal (+ margin) of a surface of that class
+    std::unordered_map<uint64_t, int> keys;
+    const double half_diag = 0.5 * std::sqrt(3.0) * (double)h + margin + 1e-4 * scale;
+    for (int s = 0; s < ns; ++s) {
+        const float* t = sv + 9 * (size_t)s;
+        P3 a = { t[0], t[1], t[2] }, b = { t[3], t[4], t[5] }, c = { t[6], t[7], t[8] };
+        int c0[3], c1[3];
+        for (int k = 0; k < 3; ++k) {
+            double mn = std::min(t[k], std::min(t[3 + k], t[6 + k])) - half_diag, mx = std::max(t[k], std::max(t[3 + k], t[6 + k])) + half_diag;
+            const double o = k == 0 ? out.ox : (k == 1 ? out.oy : out.oz); const int n = k == 0 ? out.nx : (k == 1 ? out.ny : out.nz);
+            c0[k] = std::max(0, (int)std::floor((mn - o) / h)); c1[k] = std::min(n - 1, (int)std::floor((mx - o) / h));
+        }
+        for (int z = c0[2]; z <= c1[2]; ++z) for (int y = c0[1]; y <= c1[1]; ++y) for (int x = c0[0]; x <= c1[0]; ++x) {
+            P3 ctr = { out.ox + (x + 0.5) * (double)h, out.oy + (y + 0.5) * (double)h, out.oz + (z + 0.5) * (double)h };
+            if (point_triangle_dist2(ctr, a, b, c) > half_diag * half_diag) continue;
+            const uint64_t cell = (uint64_t)((size_t)(z * out.ny + y) * out.nx + x);
+            keys.emplace((cell << 32) | (uint32_t)sclass[s], 0);
+        }
+    }
+    // candidate lists
+    std::vector<uint64_t> order; order.reserve(keys.size());
+    for (auto& kv : keys) order.push_back(kv.first);
+    std::sort(order.begin(), order.end());
+    struct Entry { int cell, cls, start, n4; };
+    std::vector<Entry> entries; entries.reserve(order.size());
+    std::vector<std::pair<double, int>> near;   // (mindist, volume)
+    for (uint64_t key : order) {
+        const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
+        const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
+        const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
+        const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
+        int k0[3], k1[3];
+        k0[0] = ccell(blo[0] - reach, 0, cnx); k1[0] = ccell(bhi[0] + reach, 0, cnx);
+        k0[1] = ccell(blo[1] - reach, 1, cny); k1[1] = ccell(bhi[1] + reach, 1, cny);
+        k0[2] = ccell(blo[2] - reach, 2, cnz); k1[2] = ccell(bhi[2] + reach, 2, cnz);
+        near.clear(); double R = 1e300;
+        for (int cz = k0[2]; cz <= k1[2]; ++cz) for (int cy = k0[1]; cy <= k1[1]; ++cy) for (int cx = k0[0]; cx <= k1[0]; ++cx) {
+            const size_t cc = (size_t)(cz * cny + cy) * cnx + cx;
+            for (int j = cstart[cc]; j < cstart[cc + 1]; ++j) {
+                const int v = corder[j]; if (vclass[v] != cls) continue;
+                double mn2 = 0, mx2 = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const double q = vol[v].pos[k];
+                    const double dlo = blo[k] - q, dhi = q - bhi[k];
+                    const double dmin = std::max(0.0, std::max(dlo, dhi)), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
+                    mn2 += dmin * dmin; mx2 += dmax * dmax;
+                }
+                const double mn = std::sqrt(mn2), mx = std::sqrt(mx2);
+                R = std::min(R, mx);
+                if (mn <= reach) near.push_back({ mn, v });
+            }
+        }
+        if (near.empty()) continue;                       // nothing within accept_r of this cell: its queries go to the kd search
+        const double lim = std::min(R * (1.0 + 1e-4) + 1e-6 * scale, reach);
+        Entry e{ cell, cls, (int)(out.cand.size() / 16), 0 };      // first group of 4 candidates
+        std::sort(near.begin(), near.end(), [](const std::pair<double, int>& p, const std::pair<double, int>& q) { return p.second < q.second; });
+        int n = 0;
+        for (auto& pr : near) if (pr.first <= lim) {
+            const int v = pr.second; float w; memcpy(&w, &v, 4);
+            out.cand.push_back(vol[v].pos[0]); out.cand.push_back(vol[v].pos[1]); out.cand.push_back(vol[v].pos[2]); out.cand.push_back(w); ++n;
+        }
+        if (n == 0) continue;
+        out.listed += (size_t)n;
+        for (; n % 4 != 0; ++n) { const int v = -1; float w; memcpy(&w, &v, 4); out.cand.push_back(1e18f); out.cand.push_back(1e18f); out.cand.push_back(1e18f); out.cand.push_back(w); }
+        e.n4 = n / 4; entries.push_back(e);
+    }
+    if (out.cand.empty()) out.cand.assign(16, 0.f);
+    out.keys = entries.size();
+    size_t slots = 8; while (slots < 2 * entries.size() + 2) slots <<= 1;
+    out.table.assign(4 * slots, -1);
+    const uint32_t mask = (uint32_t)(slots - 1);
+    for (const Entry& e : entries) {
+        uint32_t hs = vcell_hash((uint32_t)e.cell, (uint32_t)e.cls) & mask;
+        while (out.table[4 * (size_t)hs] >= 0) hs = (hs + 1) & mask;
+        out.table[4 * (size_t)hs] = e.cell; out.table[4 * (size_t)hs + 1] = e.cls; out.table[4 * (size_t)hs + 2] = e.start; out.table[4 * (size_t)hs + 3] = e.n4;
+    }
 }
 
 }  // namespace rlpt

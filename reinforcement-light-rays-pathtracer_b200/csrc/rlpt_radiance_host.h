@@ -9,4 +9,16 @@ float host_triangle_area(const float* v9);
 void host_triangle_normal(const float* v9, float* n3);
 void host_build_radiance_map(const float* surface_v, const float* surface_nrm, int n_surfaces, float area_per_sample,
                              std::vector<HostVolume>& volumes, std::vector<HostTreeElement>& tree);
+
+// Nearest-volume candidate cells (rlpt_device.cuh, vcell_find): a fine uniform grid over the surfaces; for every
+// (cell, normal class) pair that a surface of that class passes through, the list of volumes that can be the closest
+// same-class volume of some point of the cell. Hash table entries are (cell, class, first candidate, groups of 4).
+struct HostVCells {
+    float ox, oy, oz, h; int nx, ny, nz;
+    std::vector<int> table;          // 4 ints per slot; cell = -1 marks an empty slot; size is a power of two
+    std::vector<float> cand;         // 4 floats per candidate: position + volume index (as int bits), padded per list to groups of 4
+    size_t keys = 0, listed = 0;
+};
+void host_build_vcells(const float* surface_v, const int* surface_class, int n_surfaces, const std::vector<HostVolume>& volumes,
+                       const std::vector<int>& volume_class, float cell_h, float accept_r, HostVCells& out);
 }  // namespace rlpt

@@ -1,0 +1,69 @@
+// tests/devfn_host.cpp -- host instantiation of the product's per-ray device functions (rlpt_device.cuh) and of the
+// host-side radiance-map construction, for CPU tests of the host logic. TEST INFRASTRUCTURE: nothing in the product
+// library runs these on the host. Built by tests/test_vcells_cpu.py with g++ -ffp-contract=off.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <array>
+#include <vector>
+#include <random>
+#include "rlpt_radiance_host.h"
+#include "rlpt_device.cuh"
+using namespace rlpt;
+
+static float within_abs_of(float max_dist) {
+    const double md = (double)max_dist; float f = (float)std::sqrt(md);
+    while (f > 0.f && (double)f * (double)f >= md) f = std::nextafterf(f, 0.f);
+    for (float n = std::nextafterf(f, INFINITY); (double)n * (double)n < md; n = std::nextafterf(f, INFINITY)) f = n;
+    return f;
+}
+
+// Builds the radiance map of the given surfaces, then answers `nq` seeded queries (points on the surfaces, jittered off
+// them by `jitter`) twice: through the candidate cells (with the kd fallback, as find_volume does) and by the kd search
+// alone. out[0] = mismatches, out[1] = queries decided by the cells, out[2] = volumes, out[3] = (cell, class) keys,
+// out[4] = listed candidates, out[5] = table slots
+extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample, float max_dist, float cell_factor, int nq, unsigned seed, float jitter, double* out) {
+    std::vector<float> nrm(3 * (size_t)ns); std::vector<int> scls(ns);
+    std::map<std::array<uint32_t, 3>, int> classes;
+    for (int g = 0; g < ns; ++g) {
+        host_triangle_normal(sv + 9 * (size_t)g, &nrm[3 * (size_t)g]);
+        std::array<uint32_t, 3> key; for (int k = 0; k < 3; ++k) { float f = nrm[3 * g + k] == 0.f ? 0.f : nrm[3 * g + k]; memcpy(&key[k], &f, 4); }
+        auto it = classes.find(key); if (it == classes.end()) it = classes.emplace(key, (int)classes.size()).first; scls[g] = it->second;
+    }
+    std::vector<HostVolume> vol; std::vector<HostTreeElement> tree;
+    host_build_radiance_map(sv, nrm.data(), ns, area_per_sample, vol, tree);
+    const int nv = (int)vol.size(), nt = (int)tree.size();
+    std::vector<int> inner_of(nt, -1); int n_inner = 0;
+    for (int i = 0; i < nt; ++i) if (!tree[i].leaf) inner_of[i] = n_inner++;
+    auto child_word = [&](unsigned idx) -> uint32_t { return tree[idx].leaf ? (KD_LEAF | (uint32_t)(int)tree[idx].data) : (uint32_t)inner_of[idx]; };
+    struct Inner { float split; uint32_t l, r; int dim; };
+    std::vector<Inner> kd(std::max(n_inner, 1));
+    for (int i = 0; i < nt; ++i) if (!tree[i].leaf) kd[inner_of[i]] = Inner{ tree[i].data, child_word(tree[i].left), child_word(tree[i].right), tree[i].dim };
+    std::vector<int> vcls(nv); for (int i = 0; i < nv; ++i) vcls[i] = scls[vol[i].surface];
+    const float within = within_abs_of(max_dist), accept = within * (1.f - 1e-5f);
+    HostVCells hv; host_build_vcells(sv, scls.data(), ns, vol, vcls, cell_factor * std::sqrt(area_per_sample), accept, hv);
+    VCells g{}; g.ox = hv.ox; g.oy = hv.oy; g.oz = hv.oz; g.inv_h = 1.f / hv.h; g.nx = hv.nx; g.ny = hv.ny; g.nz = hv.nz; g.mask = (uint32_t)(hv.table.size() / 4 - 1); g.accept_r = accept;
+    const uint32_t root = child_word(0); const float rx = tree[0].pos[0], ry = tree[0].pos[1], rz = tree[0].pos[2];
+    auto kd_only = [&](float px, float py, float pz, int cls) {
+        return kd_find([&](uint32_t idx, float& split, uint32_t& l, uint32_t& r, int& dim) { split = kd[idx].split; l = kd[idx].l; r = kd[idx].r; dim = kd[idx].dim; },
+                       [&](int v, float& x, float& y, float& z, int& c) { x = vol[v].pos[0]; y = vol[v].pos[1]; z = vol[v].pos[2]; c = vcls[v]; },
+                       root, rx, ry, rz, px, py, pz, cls, within);
+    };
+    std::mt19937 rng(seed); std::uniform_real_distribution<float> U(0.f, 1.f); std::normal_distribution<float> Nrm(0.f, 1.f);
+    double mism = 0, decided = 0;
+    for (int q = 0; q < nq; ++q) {
+        const int s = (int)(rng() % (unsigned)ns); const float* t = sv + 9 * (size_t)s;
+        float u = U(rng), v = U(rng); if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
+        float p[3]; for (int k = 0; k < 3; ++k) p[k] = t[k] + u * (t[3 + k] - t[k]) + v * (t[6 + k] - t[k]) + jitter * Nrm(rng);
+        const int cls = scls[s];
+        const float d0 = kd_distance(p[0], p[1], p[2], rx, ry, rz);
+        int a = vcell_find(g, [&](uint32_t i, int& c, int& k, int& st, int& n) { c = hv.table[4 * (size_t)i]; k = hv.table[4 * (size_t)i + 1]; st = hv.table[4 * (size_t)i + 2]; n = hv.table[4 * (size_t)i + 3]; },
+                           [&](int i, float& x, float& y, float& z, int& vv) { x = hv.cand[4 * (size_t)i]; y = hv.cand[4 * (size_t)i + 1]; z = hv.cand[4 * (size_t)i + 2]; memcpy(&vv, &hv.cand[4 * (size_t)i + 3], 4); },
+                           p[0], p[1], p[2], cls, d0);
+        const int b = kd_only(p[0], p[1], p[2], cls);
+        if (a >= 0) { decided += 1; if (a != b) mism += 1; }
+    }
+    out[0] = mism; out[1] = decided; out[2] = nv; out[3] = (double)hv.keys; out[4] = (double)hv.listed; out[5] = (double)(hv.table.size() / 4);
+    return 0;
+}

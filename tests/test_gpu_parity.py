@@ -114,6 +114,13 @@ def test_nearest_volume_bit_exact(ctx, oracle, golden_scenes, golden_rmap):
     pos[::97] = rs.uniform(-3, 3, (len(pos[::97]), 3))
     nrm = d["nrm"][idx]
     assert np.array_equal(ctx.find_closest(pos, nrm), oracle.find_closest(pos, nrm, 1))
+    # points ON the surfaces (what the tracer asks for): these are decided by the candidate cells, not the kd fallback
+    sv = np.asarray(s["sv"], dtype=np.float32).reshape(-1, 3, 3)
+    tri = sv[d["surface"][idx]]
+    u, v = rs.rand(len(idx)).astype(np.float32), rs.rand(len(idx)).astype(np.float32)
+    flip = u + v > 1; u[flip], v[flip] = 1 - u[flip], 1 - v[flip]
+    pos = (tri[:, 0] + u[:, None] * (tri[:, 1] - tri[:, 0]) + v[:, None] * (tri[:, 2] - tri[:, 0])).astype(np.float32)
+    assert np.array_equal(ctx.find_closest(pos, nrm), oracle.find_closest(pos, nrm, 1))
 
 
 def test_nearest_volume_vs_reference_kernels(ctx, ref_cuda, golden_scenes, golden_rmap):
@@ -125,6 +132,12 @@ def test_nearest_volume_vs_reference_kernels(ctx, ref_cuda, golden_scenes, golde
     idx = rs.randint(0, ctx.n_vol, 1 << 18)
     pos = d["pos"][idx] + rs.randn(len(idx), 3).astype(np.float32) * np.float32(0.03)
     nrm = d["nrm"][idx]
+    assert np.array_equal(ctx.find_closest(pos, nrm), ref_cuda.find_closest(pos, nrm, on_device=True))
+    sv = np.asarray(s["sv"], dtype=np.float32).reshape(-1, 3, 3)
+    tri = sv[d["surface"][idx]]
+    u, v = rs.rand(len(idx)).astype(np.float32), rs.rand(len(idx)).astype(np.float32)
+    flip = u + v > 1; u[flip], v[flip] = 1 - u[flip], 1 - v[flip]
+    pos = (tri[:, 0] + u[:, None] * (tri[:, 1] - tri[:, 0]) + v[:, None] * (tri[:, 2] - tri[:, 0])).astype(np.float32)
     assert np.array_equal(ctx.find_closest(pos, nrm), ref_cuda.find_closest(pos, nrm, on_device=True))
 
 

@@ -1,0 +1,39 @@
+"""Host logic of the nearest-volume candidate cells (rlpt_radiance_host.cpp host_build_vcells + rlpt_device.cuh vcell_find):
+whenever the cells decide a query, the answer is the reference kd search's (RadianceMap::find_closest_radiance_volume_iterative,
+G/radiance_volumes/radiance_map.cu:150-203, restated by kd_find). Runs the product's own functions instantiated for the host
+(tests/devfn_host.cpp); the GPU parity tests repeat the comparison on the device against the oracle and the reference."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "reinforcement-light-rays-pathtracer_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "_build")
+
+
+@pytest.fixture(scope="module")
+def devfn():
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libdevfn_host.so")
+    srcs = [os.path.join(ROOT, "tests", "devfn_host.cpp"), os.path.join(CSRC, "rlpt_radiance_host.cpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs + [os.path.join(CSRC, "rlpt_device.cuh")]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-I", CSRC, "-o", so] + srcs)
+    lib = ctypes.CDLL(so)
+    lib.devfn_check_vcells.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_void_p]
+    return lib
+
+
+@pytest.mark.parametrize("scene,jitter,min_decided", [("cornell", 0.0, 0.97), ("cornell", 1e-6, 0.97), ("cornell", 0.02, 0.05), ("door_room", 0.0, 0.95), ("archway", 1e-6, 0.9)])
+def test_candidate_cells_agree_with_kd_search(devfn, golden_scenes, scene, jitter, min_decided):
+    sv = np.ascontiguousarray(golden_scenes[scene]["sv"], dtype=np.float32).reshape(-1, 9)
+    out = np.zeros(6, dtype=np.float64)
+    nq = 200000
+    rc = devfn.devfn_check_vcells(sv.ctypes.data, len(sv), 0.001, 0.003, 0.4, nq, 7, jitter, out.ctypes.data)
+    assert rc == 0
+    mism, decided, nv, keys, listed, slots = out
+    print(scene, jitter, dict(mismatches=mism, decided=decided / nq, volumes=nv, keys=keys, mean_list=listed / max(keys, 1), slots=slots))
+    assert mism == 0
+    assert decided / nq >= min_decided
