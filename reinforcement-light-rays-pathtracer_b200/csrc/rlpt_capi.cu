@@ -157,7 +157,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     rlpt_config_default(&c->cfg);
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
     upload_cell_cos(cs);
-    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin);
+    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 1024);     // the kernels also hold a little static shared memory (compaction scratch)
     if (!lim) lim = dqn_set_smem_limit();
     if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
     *out = c;
@@ -199,6 +199,18 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
         sc.smem_nodes = (int)(top / 64);
     }
     c->smem_bytes = scene_smem_bytes(sc);
+    {   // |detA| = |a . (e1 x e2)| <= SCREEN_HEIGHT |e1| |e2|: below 2^23 for every primitive -> the guard-free candidate pass applies
+        double worst = 0.0;
+        auto scan = [&](const std::vector<float>& v) {
+            for (size_t g = 0; g + 9 <= v.size(); g += 9) {
+                double e1 = 0, e2 = 0;
+                for (int k = 0; k < 3; ++k) { double a = (double)v[g + 3 + k] - v[g + k], b = (double)v[g + 6 + k] - v[g + k]; e1 += a * a; e2 += b * b; }
+                worst = std::max(worst, std::sqrt(e1) * std::sqrt(e2));
+            }
+        };
+        scan(c->h_surf_v); scan(c->h_light_v);
+        sc.det_small = (std::isfinite(worst) && (double)c->cfg.height * worst * 1.001 < 8388608.0) ? 1 : 0;
+    }
     return RLPT_OK;
 }
 

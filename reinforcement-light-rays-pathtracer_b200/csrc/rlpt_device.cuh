@@ -159,6 +159,26 @@ RLPT_HD bool tri_candidate(const TriRec& r, float ox, float oy, float oz, float 
     return detA != 0.f && !sign_out && !sum_out;
 }
 
+// tri_candidate without its two guards, for scenes where they cannot fire (checked on the host, SceneDev::det_small):
+//   * |detA| < 2^23 always: detA = a . (e1 x e2) with |a| = SCREEN_HEIGHT |dir|, so |detA| <= H |e1| |e2| (1 + 1e-6)
+//   * detA == 0: then dy detA = dz detA = 0, no sign early-out fires, and the triangle is at worst a false candidate that
+//     tri_solve rejects -- conservative, never wrong
+RLPT_HD bool tri_candidate_small(const TriRec& r, float ox, float oy, float oz, float a0, float a1, float a2) {
+    float T2 = RLPT_FMA(r.e2z, a1, -RLPT_MUL(r.e2y, a2));
+    float T3 = RLPT_FMA(r.e1z, a1, -RLPT_MUL(r.e1y, a2));
+    float detA = RLPT_FMA(r.e2x, T3, RLPT_FMA(a0, r.T1, -RLPT_MUL(r.e1x, T2)));
+    float bx = RLPT_SUB(ox, r.v0x), by = RLPT_SUB(oy, r.v0y), bz = RLPT_SUB(oz, r.v0z);
+    float p75 = RLPT_MUL(r.e1z, by), p80 = RLPT_MUL(r.e1y, bz);
+    float U2 = RLPT_FMA(r.e2z, by, -RLPT_MUL(r.e2y, bz));
+    float V3 = RLPT_FMA(a1, bz, -RLPT_MUL(a2, by));
+    float dy = RLPT_FMA(r.e2x, V3, RLPT_FMA(a0, U2, -RLPT_MUL(T2, bx)));
+    float dz = RLPT_FMA(T3, bx, RLPT_FMA(a0, RLPT_SUB(p80, p75), -RLPT_MUL(r.e1x, V3)));
+    const float kTiny = -7.888609052210118e-31f;   // -2^-100
+    const bool sign_out = fminf(RLPT_MUL(dy, detA), RLPT_MUL(dz, detA)) < kTiny;
+    const bool sum_out = fabsf(RLPT_ADD(dy, dz)) > RLPT_MUL(fabsf(detA), 1.000001f);
+    return !(sign_out || sum_out);
+}
+
 // ---------------------------------------------------------------- hemisphere helpers (G/utils/hemisphere_helpers.cu)
 // create_normal_coordinate_system (:31-44); evaluated once per surface at upload, kept beside the triangle.
 RLPT_HD void tangent_frame(f3 n, f3& T, f3& B) {

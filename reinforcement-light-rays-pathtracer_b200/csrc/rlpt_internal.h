@@ -24,6 +24,7 @@ struct SceneDev {
     int smem_tris;      // primitives staged in shared memory (all of them, or 0 when they do not fit)
     int smem_nodes;     // BVH nodes staged in shared memory (BFS order, so this is the top of the tree)
     int smem_shade;     // 1 when the shading records are staged too
+    int det_small;      // 1 when SCREEN_HEIGHT * max |e1| |e2| < 2^23: no determinant of this scene can reach the range where tri_candidate's sign test needs its guard
 };
 
 // ---- radiance map in HBM (SoA; the reference keeps one 1832-byte AoS record per volume, radiance_volume.cuh:40-49)

@@ -23,7 +23,7 @@ template <bool STAGED>
 struct SceneView {
     const float4* tri_s; const float4* shade_s; const float4* nodes_s;
     const float4* tri_g; const float4* shade_g; const float4* nodes_g;
-    int n_tri, n_surf, smem_nodes, brute;
+    int n_tri, n_surf, smem_nodes, brute, det_small;
     __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
     __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
     __device__ __forceinline__ float4 node(int i) const {
@@ -36,7 +36,7 @@ struct SceneView {
 template <bool STAGED, bool SHADE = true>
 __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     SceneView<STAGED> v;
-    v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute;
+    v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute; v.det_small = sc.det_small;
     float4* p = s_scene;
     int nt = 3 * sc.smem_tris, ns = (SHADE && sc.smem_shade) ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
     v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
@@ -83,10 +83,29 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
             // wins a tie" is kept). Lanes disagree about WHICH triangles are candidates, so solving inline would make the
             // whole warp walk the division path at most iterations; here it walks it max-over-lanes(#candidates) times.
             unsigned long long mask = 0ull;
+            if (v.det_small) {
+                // groups of four: the candidate bits are set at compile-time positions (one predicated LOP3 each) and
+                // shifted into the 64-bit mask once per group
+                int gid = 0;
+                for (; gid + 4 <= v.n_tri; gid += 4) {
+                    unsigned bits = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        TriRec r = load_tri(v, gid + k);
+                        if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) bits |= 1u << k;
+                    }
+                    mask |= (unsigned long long)bits << gid;
+                }
+                for (; gid < v.n_tri; ++gid) {
+                    TriRec r = load_tri(v, gid);
+                    if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << gid;
+                }
+            } else {
 #pragma unroll 2
-            for (int gid = 0; gid < v.n_tri; ++gid) {
-                TriRec r = load_tri(v, gid);
-                if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << gid;
+                for (int gid = 0; gid < v.n_tri; ++gid) {
+                    TriRec r = load_tri(v, gid);
+                    if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << gid;
+                }
             }
             if (COUNT) n_tri += (unsigned)v.n_tri;
             while (mask) {
@@ -268,16 +287,25 @@ __device__ __forceinline__ void store_state(const PathQueue& q, int slot, const 
     q.thr[slot] = make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec));
     q.meta[slot] = (s.sample << 8) | (uint32_t)bounce;
 }
-// wavefront compaction: survivors are packed densely into the next bounce's queue (one atomicAdd per warp)
-__device__ __forceinline__ void compact_store(const FrameParams& p, const PathQueue& qo, int bounce, bool alive, const PathState& s) {
-    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
-    unsigned bal = __ballot_sync(full, alive);
-    if (bal) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(p.counts + bounce + 1, __popc(bal));
-        base = __shfl_sync(full, base, 0);
-        if (alive) store_state(qo, base + __popc(bal & lanemask_lt()), s, bounce + 1);
+// wavefront compaction: survivors are packed densely into the next bounce's queue. The slot counter is ONE address, and
+// same-address atomics serialise in L2 (a quarter of k_shade's stall samples with one atomicAdd per warp): the CTA's warps
+// pool their counts through shared memory and one thread reserves the CTA's range -- 8x fewer atomics. Called by every
+// thread of the CTA the same number of times (`iter` = the call's index, selects the double-buffered scratch).
+__device__ __forceinline__ void compact_store(const FrameParams& p, const PathQueue& qo, int bounce, bool alive, const PathState& s, int iter) {
+    __shared__ int s_cnt[2][BLOCK / 32]; __shared__ int s_base[2];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int buf = iter & 1;
+    const unsigned bal = __ballot_sync(full, alive);
+    if (lane == 0) s_cnt[buf][warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; ++w) { int c = s_cnt[buf][w]; s_cnt[buf][w] = total; total += c; }
+        s_base[buf] = total ? atomicAdd(p.counts + bounce + 1, total) : 0;
     }
+    __syncthreads();
+    if (alive) store_state(qo, s_base[buf] + s_cnt[buf][warp] + __popc(bal & lanemask_lt()), s, bounce + 1);
 }
 
 // Everything of one bounce after the closest hit (t, gid) of path `s` is known: TD target of the previous (volume,
@@ -380,7 +408,7 @@ __device__ __forceinline__ void capture_ray(const FrameParams& p, const FrameDyn
 template <bool STAGED, bool SARSA, bool PRIMARY, bool TAIL>
 __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    const int n_round = (n_in + 31) & ~31;                        // whole warps stay together for the collectives
+    const int n_round = (n_in + BLOCK - 1) / BLOCK * BLOCK;       // whole CTAs stay together for the collectives
     if ((int)(blockIdx.x * blockDim.x) >= n_round) return;        // nothing for this CTA: do not even stage the scene
     SceneView<STAGED> v = stage_scene<STAGED, true>(p.scene);
     const unsigned full = 0xffffffffu;
@@ -388,7 +416,8 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
     unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0, n_kd = 0;
     const float H = (float)p.height;
     auto shade = [&](int k) { return v.shade(k); };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    int iter = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x, ++iter) {
         bool live = i < n_in;
         PathState s{};
         if (live) {
@@ -408,7 +437,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
             ++b;
             if (!__any_sync(full, live)) break;
         }
-        if (!TAIL) compact_store(p, qo, bounce, live, s);
+        if (!TAIL) compact_store(p, qo, bounce, live, s, iter);
     }
     flush_path_stats(p, st_len, st_zero, st_term, n_kd);
     flush_work_counters(p, n_tri, n_box);
@@ -447,12 +476,13 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 template <bool SARSA, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    const int n_round = (n_in + 31) & ~31;
+    const int n_round = (n_in + BLOCK - 1) / BLOCK * BLOCK;
     const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
     unsigned st_len = 0, st_zero = 0, st_term = 0, n_kd = 0;
     const float4* __restrict__ shade_g = p.scene.shade;
     auto shade = [&](int k) { return __ldg(shade_g + k); };
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    int iter = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x, ++iter) {
         bool live = i < n_in;
         PathState s{}; float t = T_MISS; int gid = -1;
         if (live) {
@@ -463,7 +493,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __g
             float2 h = p.hit[i]; t = h.x; gid = __float_as_int(h.y);
         }
         live = shade_step<SARSA, !PRIMARY>(p, dyn, shade, p.scene.n_surf, bounce, live, s, t, gid, st_len, st_zero, st_term, n_kd);
-        compact_store(p, qo, bounce, live, s);
+        compact_store(p, qo, bounce, live, s, iter);
     }
     flush_path_stats(p, st_len, st_zero, st_term, n_kd);
 }
