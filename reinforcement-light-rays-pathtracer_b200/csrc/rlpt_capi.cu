@@ -714,6 +714,9 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
         // its launch). Only speed depends on the choice; the run-to-completion kernel is correct for any count.
         int b_tail = g.max_bounces;
         if (tail_thr > 0 && c->cap_bounce < 0) {
+            // stay at most two frames ahead of the device, so that a recent snapshot has always arrived (two frames of
+            // queued work keep the GPU busy; an unbounded lead would plan every frame of a long render call blind)
+            if (l.snap_seq >= 2) CK(cudaEventSynchronize(l.snap_ev[(l.snap_seq - 2) % rlpt_ctx::Lane::SNAPS]));
             for (uint64_t k = 0; k < rlpt_ctx::Lane::SNAPS && k < l.snap_seq; ++k) {
                 const int slot = (int)((l.snap_seq - 1 - k) % rlpt_ctx::Lane::SNAPS);
                 if (cudaEventQuery(l.snap_ev[slot]) != cudaSuccess) continue;
