@@ -266,6 +266,7 @@ def main():
                        "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 52 * 2 / 1e9, nv * 144 * 20 / 1e6)},
             "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "mray_casts_per_s": st["ray_casts"] * world / dev_s / 1e6,
             "zero_contribution_fraction": st["zero_contribution_paths"] / max(st["paths"], 1),
+            "kd_search_fallback_fraction": st.get("kd_fallbacks", 0.0) / max(st["ray_casts"], 1),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timed": "wall clock around K x (camera_set, render 1 frame, frame download to pinned host memory, stats read-back), synchronised on both sides"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"kernel": "k_bounce (closest hit + shade + SARSA step + compaction)", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",

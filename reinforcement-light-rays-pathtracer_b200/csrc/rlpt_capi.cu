@@ -46,7 +46,7 @@ struct rlpt_ctx {
     bool have_rmap = false;
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
     float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
-    int4* d_vc_table = nullptr; float4* d_vc_cand = nullptr; float vc_built_accept = 0.f; size_t vc_keys = 0, vc_listed = 0;   // nearest-volume candidate cells
+    int4* d_vc_table = nullptr; float4* d_vc_cand = nullptr; int4* d_vx_table = nullptr; float4* d_vx_cand = nullptr; float vx_built_within = 0.f; float vc_built_accept = 0.f; size_t vc_keys = 0, vc_listed = 0;   // nearest-volume candidate cells
     float *d_q = nullptr, *d_cdf = nullptr, *d_cdf_rows = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // Neural-Q network
@@ -83,6 +83,7 @@ static void free_rmap(rlpt_ctx* c) {
     cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
     cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt); cudaFree(c->d_cdf_rows); c->d_cdf_rows = nullptr;
     cudaFree(c->d_vc_table); cudaFree(c->d_vc_cand); c->d_vc_table = nullptr; c->d_vc_cand = nullptr;
+    cudaFree(c->d_vx_table); cudaFree(c->d_vx_cand); c->d_vx_table = nullptr; c->d_vx_cand = nullptr;
     c->d_kd = c->d_posn = nullptr; c->d_vol_surface = nullptr; c->d_q = c->d_cdf = c->d_irr = c->d_acc_sum = nullptr; c->d_visits = c->d_acc_cnt = nullptr;
     c->have_rmap = false; c->rm = RadianceDev{};
 }
@@ -225,7 +226,8 @@ int rlpt_config_set(rlpt_ctx* c, const rlpt_config* cfg) {
     CK(cudaSetDevice(c->device));
     if (geometry_changed && c->d_accum) { CK(cudaStreamSynchronize(c->stream)); for (auto& l : c->lanes) if (l.stream) CK(cudaStreamSynchronize(l.stream)); free_frame(c); }
     if (c->have_scene) { int rc = choose_traversal(c, 0); if (rc) return rc; }
-    if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.vc.accept_r = std::min(c->vc_built_accept, c->rm.within_abs * (1.f - 1e-5f)); }   // lists were built for vc_built_accept: valid for any smaller radius
+    if (c->have_rmap) { c->rm.within_abs = within_abs_of(cfg->max_dist); c->rm.vc.accept_r = std::min(c->vc_built_accept, c->rm.within_abs * (1.f - 1e-5f));   // lists were built for vc_built_accept: valid for any smaller radius
+                        c->rm.vx_table = c->rm.within_abs == c->vx_built_within ? c->d_vx_table : nullptr; }          // the second level's lists hold for the search radius they were built with only
     return RLPT_OK;
 }
 
@@ -398,7 +400,7 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
         const float accept = rm.within_abs * (1.f - 1e-5f);
         std::vector<int> vclass(nv); for (int i = 0; i < nv; ++i) vclass[i] = c->h_surf_class[c->h_vol[i].surface];
         HostVCells hv;
-        host_build_vcells(c->h_surf_v.data(), c->h_surf_class.data(), c->n_surf, c->h_vol, vclass, factor * std::sqrt(std::max(c->cfg.area_per_sample, 1e-12f)), accept, hv);
+        host_build_vcells(c->h_surf_v.data(), c->h_surf_class.data(), c->n_surf, c->h_vol, vclass, c->h_tree, factor * std::sqrt(std::max(c->cfg.area_per_sample, 1e-12f)), accept, rm.within_abs, hv);
         CK(cudaMalloc(&c->d_vc_table, sizeof(int) * hv.table.size())); CK(cudaMalloc(&c->d_vc_cand, sizeof(float) * hv.cand.size()));
         CK(cudaMemcpy(c->d_vc_table, hv.table.data(), sizeof(int) * hv.table.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_vc_cand, hv.cand.data(), sizeof(float) * hv.cand.size(), cudaMemcpyHostToDevice));
@@ -406,6 +408,10 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
         g.mask = (uint32_t)(hv.table.size() / 4 - 1); g.accept_r = accept; c->vc_built_accept = accept;
         c->vc_keys = hv.keys; c->vc_listed = hv.listed;
         rm.vc = g; rm.vc_table = c->d_vc_table; rm.vc_cand = c->d_vc_cand;
+        CK(cudaMalloc(&c->d_vx_table, sizeof(int) * hv.xtable.size())); CK(cudaMalloc(&c->d_vx_cand, sizeof(float) * hv.xcand.size()));
+        CK(cudaMemcpy(c->d_vx_table, hv.xtable.data(), sizeof(int) * hv.xtable.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_vx_cand, hv.xcand.data(), sizeof(float) * hv.xcand.size(), cudaMemcpyHostToDevice));
+        rm.vx_table = c->d_vx_table; rm.vx_cand = c->d_vx_cand; rm.vx_mask = (uint32_t)(hv.xtable.size() / 4 - 1); c->vx_built_within = rm.within_abs;
     }
     c->have_rmap = true;
     launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);

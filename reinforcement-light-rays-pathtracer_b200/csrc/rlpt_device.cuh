@@ -385,4 +385,37 @@ RLPT_HD int vcell_find(const VCells& g, LoadEntry load_entry, LoadCand load_cand
     return best_d < d0 ? best : 0;
 }
 
+// Second level, for the queries the first cannot decide because no same-class volume lies within accept_r: the kd search
+// reaches leaf l from p exactly when fl(p_k - lo_k) >= -within_abs and fl(p_k - hi_k) <= within_abs in every dimension,
+// [lo, hi] being l's kd cell (rlpt_radiance_host.cpp derives this from kd_find's far-child rule). The list of the query's
+// (cell, class) holds every volume that can pass this test from the cell, so the closest one that does is the search's
+// winner; an empty visited set leaves volume 0. Ties after rounding depend on the visit order: -1, the caller runs kd_find.
+// load_cand(i, x, y, z, vol, lo[3], hi[3]).
+template <class LoadEntry, class LoadCand>
+RLPT_HD int vext_find(const VCells& g, uint32_t xmask, LoadEntry load_entry, LoadCand load_cand, float px, float py, float pz, int normal_class, float d0, float within_abs) {
+    float ux = grid_coord(px, g.ox, g.inv_h), uy = grid_coord(py, g.oy, g.inv_h), uz = grid_coord(pz, g.oz, g.inv_h);
+    if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz)) return -1;
+    const int cell = ((int)uz * g.ny + (int)uy) * g.nx + (int)ux;
+    uint32_t slot = vcell_hash((uint32_t)cell, (uint32_t)normal_class) & xmask;
+    int start = 0, n = 0;
+    for (int probe = 0; ; ++probe) {
+        int ec, ek; load_entry(slot, ec, ek, start, n);
+        if (ec == cell && ek == normal_class) break;
+        if (ec < 0 || probe >= 32) return -1;
+        slot = (slot + 1) & xmask;
+    }
+    float best2 = 3.0e38f, second2 = 3.0e38f; int best = -1;
+    for (int i = 0; i < n; ++i) {
+        float vx, vy, vz, lo[3], hi[3]; int vol; load_cand(start + i, vx, vy, vz, vol, lo, hi);
+        const bool visited = RLPT_SUB(px, lo[0]) >= -within_abs && RLPT_SUB(px, hi[0]) <= within_abs && RLPT_SUB(py, lo[1]) >= -within_abs &&
+                             RLPT_SUB(py, hi[1]) <= within_abs && RLPT_SUB(pz, lo[2]) >= -within_abs && RLPT_SUB(pz, hi[2]) <= within_abs;
+        const float d2 = kd_distance2(px, py, pz, vx, vy, vz);
+        if (visited) { second2 = fminf(second2, fmaxf(d2, best2)); if (d2 < best2) { best2 = d2; best = vol; } }
+    }
+    if (best < 0) return 0;
+    const float best_d = RLPT_SQRT(best2);
+    if (RLPT_SQRT(second2) == best_d) return -1;
+    return best_d < d0 ? best : 0;
+}
+
 }  // namespace rlpt

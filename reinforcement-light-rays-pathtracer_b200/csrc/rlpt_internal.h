@@ -47,6 +47,9 @@ struct RadianceDev {
     VCells vc;
     const int4* vc_table;     // [vc.mask + 1] (cell, class, first candidate group, groups of 4); cell = -1: empty
     const float4* vc_cand;    // (position, as_float(volume index)); lists padded to groups of 4 with volume -1
+    const int4* vx_table;     // second level (rlpt_device.cuh, vext_find): same slot format, 4th word = candidates
+    const float4* vx_cand;    // 3 float4 per candidate: (position, volume) (kd-cell lo, hi.x) (hi.yz, -, -)
+    uint32_t vx_mask;
 };
 
 // ---- wavefront path state, SoA, one slot per live path (two queues, ping-pong per bounce)

@@ -197,8 +197,17 @@ __device__ __forceinline__ int find_volume(const RadianceDev& rm, float px, floa
                            [&](int i, float& x, float& y, float& z, int& v) { float4 p = __ldg(cd + i); x = p.x; y = p.y; z = p.z; v = __float_as_int(p.w); },
                            px, py, pz, cls, d0);
         if (r >= 0) return r;
+        if (rm.vx_table) {
+            const int4* __restrict__ xt = rm.vx_table; const float4* __restrict__ xc = rm.vx_cand;
+            r = vext_find(rm.vc, rm.vx_mask, [&](uint32_t i, int& c, int& k, int& s, int& n) { int4 e = __ldg(xt + i); c = e.x; k = e.y; s = e.z; n = e.w; },
+                          [&](int i, float& x, float& y, float& z, int& v, float (&lo)[3], float (&hi)[3]) {
+                              float4 a = __ldg(xc + 3 * i), b = __ldg(xc + 3 * i + 1), c = __ldg(xc + 3 * i + 2);
+                              x = a.x; y = a.y; z = a.z; v = __float_as_int(a.w); lo[0] = b.x; lo[1] = b.y; lo[2] = b.z; hi[0] = b.w; hi[1] = c.x; hi[2] = c.y;
+                          }, px, py, pz, cls, d0, rm.within_abs);
+            if (r >= 0) return r;
+        }
     }
-    // exact reference search: the rare queries the candidate cells cannot decide (far from every volume, distance ties)
+    // exact reference search: what neither level decides (distance ties, points away from every surface)
     n_kd++;
     return kd_find(
         [&](uint32_t idx, float& split, uint32_t& l, uint32_t& r, int& dim) {

@@ -144,9 +144,10 @@ static double point_triangle_dist2(P3 p, P3 a, P3 b, P3 c) {
 }  // namespace
 
 void host_build_vcells(const float* sv, const int* sclass, int ns, const std::vector<HostVolume>& vol, const std::vector<int>& vclass,
-                       float cell_h, float accept_r, HostVCells& out) {
+                       const std::vector<HostTreeElement>& tree, float cell_h, float accept_r, float within_abs, HostVCells& out) {
     out = HostVCells{};
     const int nv = (int)vol.size();
+    out.xtable.assign(4 * 2, -1); out.xcand.assign(12, 0.f);
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
     for (int i = 0; i < nv; ++i) for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], (double)vol[i].pos[k]); hi[k] = std::max(hi[k], (double)vol[i].pos[k]); }
     for (int i = 0; i < 9 * ns; ++i) { int k = i % 3; lo[k] = std::min(lo[k], (double)sv[i]); hi[k] = std::max(hi[k], (double)sv[i]); }
@@ -197,6 +198,7 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
     struct Entry { int cell, cls, start, n4; };
     std::vector<Entry> entries; entries.reserve(order.size());
     std::vector<std::pair<double, int>> near;   // (mindist, volume)
+    std::vector<uint64_t> xkeys;
     for (uint64_t key : order) {
         const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
         const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
@@ -223,7 +225,8 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
                 if (mn <= reach) near.push_back({ mn, v });
             }
         }
-        if (near.empty()) continue;                       // nothing within accept_r of this cell: its queries go to the kd search
+        if (near.empty() || R >= (double)accept_r * 0.999 - margin) xkeys.push_back(key);     // some point of the cell may have no same-class volume within accept_r
+        if (near.empty()) continue;
         const double lim = std::min(R * (1.0 + 1e-4) + 1e-6 * scale, reach);
         Entry e{ cell, cls, (int)(out.cand.size() / 16), 0 };      // first group of 4 candidates
         std::sort(near.begin(), near.end(), [](const std::pair<double, int>& p, const std::pair<double, int>& q) { return p.second < q.second; });
@@ -239,6 +242,82 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
     }
     if (out.cand.empty()) out.cand.assign(16, 0.f);
     out.keys = entries.size();
+    // ---- second level. The kd search (kd_find) reaches leaf l from query p exactly when, for every ancestor whose split
+    // separates them, |fl(p_k - split)| <= within_abs; per dimension the binding ancestor is the nearest bound of l's kd cell
+    // [lo, hi] (lo = largest split with l in the right subtree, hi = smallest with l in the left), so
+    //     visited(l, p)  <=>  for k = x, y, z:  fl(p_k - lo_k) >= -within_abs  and  fl(p_k - hi_k) <= within_abs.
+    // A pair's list holds every same-class volume whose widened kd cell meets the cell's box, cut at the distance bound given
+    // by a volume that is visited from EVERY point of the box.
+    if (!xkeys.empty() && !tree.empty()) {
+        std::vector<float> klo(3 * (size_t)nv, -INFINITY), khi(3 * (size_t)nv, INFINITY);
+        {
+            struct Item { unsigned idx; float lo[3], hi[3]; };
+            std::vector<Item> stack; Item root{ 0u, { -INFINITY, -INFINITY, -INFINITY }, { INFINITY, INFINITY, INFINITY } }; stack.push_back(root);
+            while (!stack.empty()) {
+                Item it = stack.back(); stack.pop_back();
+                const HostTreeElement& e = tree[it.idx];
+                if (e.leaf) { const int v = (int)e.data; if (v >= 0 && v < nv) for (int k = 0; k < 3; ++k) { klo[3 * (size_t)v + k] = it.lo[k]; khi[3 * (size_t)v + k] = it.hi[k]; } continue; }
+                Item l = it, r = it; l.idx = e.left; r.idx = e.right;
+                l.hi[e.dim] = std::min(l.hi[e.dim], e.data); r.lo[e.dim] = std::max(r.lo[e.dim], e.data);
+                stack.push_back(l); stack.push_back(r);
+            }
+        }
+        int ncls = 0; for (int i = 0; i < nv; ++i) ncls = std::max(ncls, vclass[i] + 1);
+        std::vector<std::vector<int>> by_class(std::max(ncls, 1));
+        for (int i = 0; i < nv; ++i) if (vclass[i] >= 0) by_class[vclass[i]].push_back(i);
+        const double w = (double)within_abs;
+        struct XEntry { int cell, cls, start, n; };
+        std::vector<XEntry> xent; xent.reserve(xkeys.size());
+        out.xcand.clear();
+        struct XC { double mn, mx; int v; bool always; };
+        std::vector<XC> poss;
+        for (uint64_t key : xkeys) {
+            const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
+            if (cls < 0 || cls >= ncls) continue;
+            const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
+            const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
+            const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
+            poss.clear(); double Rx = 1e300;
+            for (int v : by_class[cls]) {
+                bool possible = true, always = true;
+                for (int k = 0; k < 3 && possible; ++k) {
+                    const double lo = klo[3 * (size_t)v + k], hi = khi[3 * (size_t)v + k];
+                    if (bhi[k] - lo < -w - margin || blo[k] - hi > w + margin) possible = false;
+                    if (!(blo[k] - lo >= -w + margin && bhi[k] - hi <= w - margin)) always = false;
+                }
+                if (!possible) continue;
+                double mn2 = 0, mx2 = 0;
+                for (int k = 0; k < 3; ++k) {
+                    const double q = vol[v].pos[k];
+                    const double dmin = std::max(0.0, std::max(blo[k] - q, q - bhi[k])), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
+                    mn2 += dmin * dmin; mx2 += dmax * dmax;
+                }
+                XC c{ std::sqrt(mn2), std::sqrt(mx2), v, always };
+                if (always) Rx = std::min(Rx, c.mx);
+                poss.push_back(c);
+            }
+            const double lim = Rx < 1e299 ? Rx * (1.0 + 1e-4) + 1e-6 * scale : 1e300;
+            XEntry e{ cell, cls, (int)(out.xcand.size() / 12), 0 };
+            for (const XC& c : poss) if (c.mn <= lim) {
+                const int v = c.v; float wv; memcpy(&wv, &v, 4);
+                const float rec[12] = { vol[v].pos[0], vol[v].pos[1], vol[v].pos[2], wv, klo[3 * (size_t)v], klo[3 * (size_t)v + 1], klo[3 * (size_t)v + 2], khi[3 * (size_t)v],
+                                        khi[3 * (size_t)v + 1], khi[3 * (size_t)v + 2], 0.f, 0.f };
+                out.xcand.insert(out.xcand.end(), rec, rec + 12); ++e.n;
+            }
+            out.xlisted += (size_t)e.n;
+            xent.push_back(e);                             // an empty list is an answer too: nothing of the class can be visited -> volume 0
+        }
+        if (out.xcand.empty()) out.xcand.assign(12, 0.f);
+        out.xkeys = xent.size();
+        size_t xs = 8; while (xs < 2 * xent.size() + 2) xs <<= 1;
+        out.xtable.assign(4 * xs, -1);
+        const uint32_t xmask = (uint32_t)(xs - 1);
+        for (const XEntry& e : xent) {
+            uint32_t hs = vcell_hash((uint32_t)e.cell, (uint32_t)e.cls) & xmask;
+            while (out.xtable[4 * (size_t)hs] >= 0) hs = (hs + 1) & xmask;
+            out.xtable[4 * (size_t)hs] = e.cell; out.xtable[4 * (size_t)hs + 1] = e.cls; out.xtable[4 * (size_t)hs + 2] = e.start; out.xtable[4 * (size_t)hs + 3] = e.n;
+        }
+    }
     size_t slots = 8; while (slots < 2 * entries.size() + 2) slots <<= 1;
     out.table.assign(4 * slots, -1);
     const uint32_t mask = (uint32_t)(slots - 1);

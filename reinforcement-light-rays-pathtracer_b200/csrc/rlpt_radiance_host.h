@@ -18,7 +18,13 @@ struct HostVCells {
     std::vector<int> table;          // 4 ints per slot; cell = -1 marks an empty slot; size is a power of two
     std::vector<float> cand;         // 4 floats per candidate: position + volume index (as int bits), padded per list to groups of 4
     size_t keys = 0, listed = 0;
+    // second level, only for the pairs where a query can fail the first (no same-class volume within accept_r): every
+    // same-class volume the reference's kd search can visit from some point of the cell, with its kd-cell bounds.
+    std::vector<int> xtable;         // same slot format; the 4th int is the number of candidates
+    std::vector<float> xcand;        // 12 floats per candidate: (position, volume index) (lo.xyz, hi.x) (hi.yz, 0, 0)
+    size_t xkeys = 0, xlisted = 0;
 };
 void host_build_vcells(const float* surface_v, const int* surface_class, int n_surfaces, const std::vector<HostVolume>& volumes,
-                       const std::vector<int>& volume_class, float cell_h, float accept_r, HostVCells& out);
+                       const std::vector<int>& volume_class, const std::vector<HostTreeElement>& tree, float cell_h, float accept_r, float within_abs,
+                       HostVCells& out);
 }  // namespace rlpt

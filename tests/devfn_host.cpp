@@ -22,7 +22,7 @@ static float within_abs_of(float max_dist) {
 // Builds the radiance map of the given surfaces, then answers `nq` seeded queries (points on the surfaces, jittered off
 // them by `jitter`) twice: through the candidate cells (with the kd fallback, as find_volume does) and by the kd search
 // alone. out[0] = mismatches, out[1] = queries decided by the cells, out[2] = volumes, out[3] = (cell, class) keys,
-// out[4] = listed candidates, out[5] = table slots
+// out[4] = listed candidates, out[5] = table slots, out[6] = queries decided by the second level, out[7] / out[8] = its keys / candidates
 extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample, float max_dist, float cell_factor, int nq, unsigned seed, float jitter, double* out) {
     std::vector<float> nrm(3 * (size_t)ns); std::vector<int> scls(ns);
     std::map<std::array<uint32_t, 3>, int> classes;
@@ -42,7 +42,8 @@ extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample
     for (int i = 0; i < nt; ++i) if (!tree[i].leaf) kd[inner_of[i]] = Inner{ tree[i].data, child_word(tree[i].left), child_word(tree[i].right), tree[i].dim };
     std::vector<int> vcls(nv); for (int i = 0; i < nv; ++i) vcls[i] = scls[vol[i].surface];
     const float within = within_abs_of(max_dist), accept = within * (1.f - 1e-5f);
-    HostVCells hv; host_build_vcells(sv, scls.data(), ns, vol, vcls, cell_factor * std::sqrt(area_per_sample), accept, hv);
+    HostVCells hv; host_build_vcells(sv, scls.data(), ns, vol, vcls, tree, cell_factor * std::sqrt(area_per_sample), accept, within, hv);
+    const uint32_t xmask = (uint32_t)(hv.xtable.size() / 4 - 1);
     VCells g{}; g.ox = hv.ox; g.oy = hv.oy; g.oz = hv.oz; g.inv_h = 1.f / hv.h; g.nx = hv.nx; g.ny = hv.ny; g.nz = hv.nz; g.mask = (uint32_t)(hv.table.size() / 4 - 1); g.accept_r = accept;
     const uint32_t root = child_word(0); const float rx = tree[0].pos[0], ry = tree[0].pos[1], rz = tree[0].pos[2];
     auto kd_only = [&](float px, float py, float pz, int cls) {
@@ -51,7 +52,7 @@ extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample
                        root, rx, ry, rz, px, py, pz, cls, within);
     };
     std::mt19937 rng(seed); std::uniform_real_distribution<float> U(0.f, 1.f); std::normal_distribution<float> Nrm(0.f, 1.f);
-    double mism = 0, decided = 0;
+    double mism = 0, decided = 0, decided2 = 0;
     for (int q = 0; q < nq; ++q) {
         const int s = (int)(rng() % (unsigned)ns); const float* t = sv + 9 * (size_t)s;
         float u = U(rng), v = U(rng); if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
@@ -61,9 +62,18 @@ extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample
         int a = vcell_find(g, [&](uint32_t i, int& c, int& k, int& st, int& n) { c = hv.table[4 * (size_t)i]; k = hv.table[4 * (size_t)i + 1]; st = hv.table[4 * (size_t)i + 2]; n = hv.table[4 * (size_t)i + 3]; },
                            [&](int i, float& x, float& y, float& z, int& vv) { x = hv.cand[4 * (size_t)i]; y = hv.cand[4 * (size_t)i + 1]; z = hv.cand[4 * (size_t)i + 2]; memcpy(&vv, &hv.cand[4 * (size_t)i + 3], 4); },
                            p[0], p[1], p[2], cls, d0);
+        if (a < 0) {
+            a = vext_find(g, xmask, [&](uint32_t i, int& c, int& k, int& st, int& n) { c = hv.xtable[4 * (size_t)i]; k = hv.xtable[4 * (size_t)i + 1]; st = hv.xtable[4 * (size_t)i + 2]; n = hv.xtable[4 * (size_t)i + 3]; },
+                          [&](int i, float& x, float& y, float& z, int& vv, float (&lo)[3], float (&hi)[3]) {
+                              const float* r = &hv.xcand[12 * (size_t)i]; x = r[0]; y = r[1]; z = r[2]; memcpy(&vv, &r[3], 4);
+                              lo[0] = r[4]; lo[1] = r[5]; lo[2] = r[6]; hi[0] = r[7]; hi[1] = r[8]; hi[2] = r[9];
+                          }, p[0], p[1], p[2], cls, d0, within);
+            if (a >= 0) decided2 += 1;
+        }
         const int b = kd_only(p[0], p[1], p[2], cls);
         if (a >= 0) { decided += 1; if (a != b) mism += 1; }
     }
     out[0] = mism; out[1] = decided; out[2] = nv; out[3] = (double)hv.keys; out[4] = (double)hv.listed; out[5] = (double)(hv.table.size() / 4);
+    out[6] = decided2; out[7] = (double)hv.xkeys; out[8] = (double)hv.xlisted;
     return 0;
 }
