@@ -396,7 +396,7 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     rm.within_abs = within_abs_of(c->cfg.max_dist);
     {
         // candidate cells for the nearest-volume search: cell size = a fraction of the volume spacing sqrt(AREA_PER_SAMPLE)
-        float factor = 0.4f; if (const char* e = getenv("RLPT_VCELL")) factor = std::max(0.05f, (float)atof(e));
+        float factor = 0.6f; if (const char* e = getenv("RLPT_VCELL")) factor = std::max(0.05f, (float)atof(e));
         const float accept = rm.within_abs * (1.f - 1e-5f);
         std::vector<int> vclass(nv); for (int i = 0; i < nv; ++i) vclass[i] = c->h_surf_class[c->h_vol[i].surface];
         HostVCells hv;

@@ -284,17 +284,20 @@ __device__ __forceinline__ void primary_state(const FrameParams& p, const FrameD
     s.ox = dyn.cam_x; s.oy = dyn.cam_y; s.oz = dyn.cam_z; s.dx = d.x; s.dy = d.y; s.dz = d.z;
     s.tr = s.tg = s.tb = 1.f; s.cur_brdf = 0.f; s.volsec = 0u;
 }
+// The path queues are write-once / read-once streams of ~0.9 GB per frame; they go through L2 with the evict-first
+// policy (ld/st.global.cs) so that they do not push out what is re-read at random: the nearest-volume tables, the CDFs
+// and the TD accumulators (~90 MB for Cornell, inside the 126 MB L2).
 __device__ __forceinline__ void load_state(const PathQueue& q, int i, PathState& s) {
-    float4 a = q.o[i], b = q.d[i], c = q.thr[i]; uint32_t m = q.meta[i];
+    float4 a = __ldcs(q.o + i), b = __ldcs(q.d + i), c = __ldcs(q.thr + i); uint32_t m = __ldcs(q.meta + i);
     s.ox = a.x; s.oy = a.y; s.oz = a.z; s.pixel = __float_as_uint(a.w);
     s.dx = b.x; s.dy = b.y; s.dz = b.z; s.cur_brdf = b.w;
     s.tr = c.x; s.tg = c.y; s.tb = c.z; s.volsec = __float_as_uint(c.w); s.sample = m >> 8;
 }
 __device__ __forceinline__ void store_state(const PathQueue& q, int slot, const PathState& s, int bounce) {
-    q.o[slot] = make_float4(s.ox, s.oy, s.oz, __uint_as_float(s.pixel));
-    q.d[slot] = make_float4(s.dx, s.dy, s.dz, s.cur_brdf);
-    q.thr[slot] = make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec));
-    q.meta[slot] = (s.sample << 8) | (uint32_t)bounce;
+    __stcs(q.o + slot, make_float4(s.ox, s.oy, s.oz, __uint_as_float(s.pixel)));
+    __stcs(q.d + slot, make_float4(s.dx, s.dy, s.dz, s.cur_brdf));
+    __stcs(q.thr + slot, make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec)));
+    __stcs(q.meta + slot, (s.sample << 8) | (uint32_t)bounce);
 }
 // wavefront compaction: survivors are packed densely into the next bounce's queue. The slot counter is ONE address, and
 // same-address atomics serialise in L2 (a quarter of k_shade's stall samples with one atomicAdd per warp): the CTA's warps
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
             PathState s; primary_state(p, dyn, i, s);
             ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz;
         } else {
-            float4 a = qi.o[i], b = qi.d[i];
+            float4 a = __ldcs(qi.o + i), b = __ldcs(qi.d + i);
             ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z;
         }
         if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
         }
         float t, sdx, sdy, sdz; int gid;
         closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
-        p.hit[i] = make_float2(t, __int_as_float(gid));
+        __stcs(p.hit + i, make_float2(t, __int_as_float(gid)));
     }
     flush_work_counters(p, n_tri, n_box);
 }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __g
                 primary_state(p, dyn, i, s);
                 if (i % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);
             } else load_state(qi, i, s);
-            float2 h = p.hit[i]; t = h.x; gid = __float_as_int(h.y);
+            float2 h = __ldcs(p.hit + i); t = h.x; gid = __float_as_int(h.y);
         }
         live = shade_step<SARSA, !PRIMARY>(p, dyn, shade, p.scene.n_surf, bounce, live, s, t, gid, st_len, st_zero, st_term, n_kd);
         compact_store(p, qo, bounce, live, s, iter);
