@@ -58,6 +58,9 @@ struct rlpt_ctx {
     // wavefront state
     struct Lane {
         cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; float2* d_hit = nullptr;
+        // the primary closest-hit pass needs nothing of the previous frame's results, only the hit buffer: it runs on `pre`
+        // as soon as the previous frame's last k_shade has read that buffer, underneath that frame's tail kernel and merge
+        cudaStream_t pre = nullptr; cudaEvent_t hit_free = nullptr, pre_done = nullptr; bool hit_free_valid = false;
         // live-path counts of recent frames, copied back asynchronously: the launch plan of a frame (where the per-bounce
         // launches stop and the run-to-completion kernel takes over) is read off the newest snapshot that has arrived
         static constexpr int SNAPS = 4;
@@ -68,7 +71,7 @@ struct rlpt_ctx {
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
     size_t smem_bytes = 0; int grid = 148;
-    int pipe_split = 1, pipe_tail = 65536;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
+    int pipe_split = 1, pipe_tail = 65536, pipe_pre = 1;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
     void* d_stage = nullptr; size_t stage_bytes = 0;     // device staging for frame downloads (kept across calls)
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
     double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;
@@ -93,6 +96,7 @@ static void free_lanes(rlpt_ctx* c) {
         cudaFree(l.d_counts); cudaFree(l.d_hit); if (l.h_counts) cudaFreeHost(l.h_counts);
         for (auto& e : l.snap_ev) if (e) cudaEventDestroy(e);
         if (l.done) cudaEventDestroy(l.done); if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.hit_free) cudaEventDestroy(l.hit_free); if (l.pre_done) cudaEventDestroy(l.pre_done); if (l.pre) cudaStreamDestroy(l.pre);
     }
     c->lanes.clear(); c->lane_capacity = 0; c->counts_len = 0; c->lane_spp = 0;
 }
@@ -150,6 +154,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     c->n_sm = prop.multiProcessorCount;
     if (const char* e = getenv("RLPT_SPLIT")) c->pipe_split = atoi(e) != 0;
     if (const char* e = getenv("RLPT_TAIL")) c->pipe_tail = std::max(0, atoi(e));
+    if (const char* e = getenv("RLPT_PRE")) c->pipe_pre = atoi(e) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -670,7 +675,10 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
         free_lanes(c);
         c->lanes.resize(L);
         for (auto& l : c->lanes) {
-            CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+            int prio_lo = 0, prio_hi = 0; CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CK(cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, prio_hi)); CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+            CK(cudaStreamCreateWithPriority(&l.pre, cudaStreamNonBlocking, prio_lo));
+            CK(cudaEventCreateWithFlags(&l.hit_free, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&l.pre_done, cudaEventDisableTiming));
             for (int k = 0; k < 2; ++k) {
                 CK(cudaMalloc(&l.q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * paths));
                 CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * paths));
@@ -734,12 +742,19 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
             (void)cudaGetLastError();
         }
         int launches = 0;
-        if (split) { launch_isect(p, dyn, 0, grid, c->smem_bytes, l.stream); launch_shade(p, dyn, method, 0, grid, l.stream); launches += 2; }
-        else { launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream); launches += 1; }
+        if (split) {
+            if (c->pipe_pre) {
+                if (l.hit_free_valid) CK(cudaStreamWaitEvent(l.pre, l.hit_free, 0));
+                launch_isect(p, dyn, 0, grid, c->smem_bytes, l.pre);
+                CK(cudaEventRecord(l.pre_done, l.pre)); CK(cudaStreamWaitEvent(l.stream, l.pre_done, 0));
+            } else launch_isect(p, dyn, 0, grid, c->smem_bytes, l.stream);
+            launch_shade(p, dyn, method, 0, grid, l.stream); launches += 2;
+        } else { launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream); launches += 1; }
         for (int b = 1; b < b_tail; ++b) {
             if (split) { launch_isect(p, dyn, b, grid, c->smem_bytes, l.stream); launch_shade(p, dyn, method, b, grid, l.stream); launches += 2; }
             else { launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream); launches += 1; }
         }
+        if (split) { CK(cudaEventRecord(l.hit_free, l.stream)); l.hit_free_valid = true; }
         if (b_tail < g.max_bounces) { launch_tail(p, dyn, method, b_tail, grid, c->smem_bytes, l.stream); launches += 1; }
         c->launches += (double)launches;
         {   // snapshot of this frame's counts
