@@ -251,10 +251,25 @@ def main():
     d2h = args.width * args.height * 3 * 4 + 8 * 8          # frame buffer + statistics block
 
     if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         flops = st["triangle_tests"] * F_TRI + st["box_tests"] * F_AABB
-        trace_s = max(st["trace_seconds"], 1e-12)
-        bounce_launches = st["kernel_launches"] - (st["frames"] if method == 1 else 0)
-        achieved = flops / trace_s / 1e12
+        split = st["isect_launches"] > 0
+        # closest-hit kernel: k_isect when the split pipeline runs (its own event pairs), else the fused k_bounce (trace phase)
+        hit_s = max(st["isect_seconds"] if split else st["trace_seconds"], 1e-12)
+        hit_n = st["isect_launches"] if split else st["kernel_launches"] - (st["frames"] if method == 1 else 0)
+        tail_flop_share = 0.0
+        if split and st["tail_launches"] > 0:
+            # the run-to-completion launches execute triangle tests too; their flops are taken out in proportion to ray casts
+            tail_flop_share = min(1.0, st["tail_seconds"] / max(st["tail_seconds"] + st["isect_seconds"] + st["shade_seconds"], 1e-12))
+        hit_flops = flops * (1.0 - tail_flop_share)
+        achieved = hit_flops / hit_s / 1e12
+        kernel_total = max(st["isect_seconds"] + st["shade_seconds"] + st["tail_seconds"], 1e-12)
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -263,31 +278,42 @@ def main():
                        "method": "Expected SARSA radiance volumes, train + render" if method == 1 else "default path tracer",
                        "width": args.width, "height": args.height, "spp_per_frame": args.spp, "frames": args.steps, "spp_total_per_gpu": args.spp * args.steps,
                        "radiance_volumes": nv, "grid": "12x12", "max_bounces": 80, "partition": "samples (rank r traces samples r*spp..(r+1)*spp-1 of each global frame)",
-                       "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 52 * 2 / 1e9, nv * 144 * 20 / 1e6)},
+                       "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 60 * 2 / 1e9, nv * 144 * 20 / 1e6)},
             "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "mray_casts_per_s": st["ray_casts"] * world / dev_s / 1e6,
             "zero_contribution_fraction": st["zero_contribution_paths"] / max(st["paths"], 1),
             "kd_search_fallback_fraction": st.get("kd_fallbacks", 0.0) / max(st["ray_casts"], 1),
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timed": "wall clock around K x (camera_set, render 1 frame, frame download to pinned host memory, stats read-back), synchronised on both sides"},
             "gpu_launches": int(st["kernel_launches"]),
-            "roofline": {"kernel": "k_bounce (closest hit + shade + SARSA step + compaction)", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+            "roofline": {"kernel": "k_isect (closest hit of every live ray, one launch per bounce)" if split else "k_bounce (closest hit + shade + SARSA step + compaction)",
+                         "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None,
+                         "traffic": None,
+                         "note": "bound is the FP32 pipe (SURVEY 8d; not hbm/tensor): algorithmic flop = ray-triangle tests x 72 + ray-box tests x 18, counted in the kernel; duration = CUDA event pairs "
+                                 "around every launch on its stream inside the timed region (launches of the two sample lanes overlap, so a launch's duration includes sharing the SMs)",
                          "peak_source": "FP32 FMA microbenchmark run by this bench on this GPU (MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
-                         "flop_per_launch": flops / max(bounce_launches, 1), "avg_launch_ms": trace_s / max(bounce_launches, 1) * 1e3,
-                         "triangle_tests": st["triangle_tests"], "box_tests": st["box_tests"], "trace_seconds": st["trace_seconds"], "merge_seconds": st["merge_seconds"],
-                         "trace_share_of_step": st["trace_seconds"] / max(st["device_seconds"], 1e-12)},
+                         "flop_per_launch": hit_flops / max(hit_n, 1), "avg_launch_ms": hit_s / max(hit_n, 1) * 1e3, "launches": hit_n,
+                         "triangle_tests": st["triangle_tests"], "box_tests": st["box_tests"],
+                         "share_of_kernel_time": (st["isect_seconds"] / kernel_total) if split else 1.0},
             "clocks": clk,
         }
+        if split and st["shade_launches"] > 0:
+            casts = st["ray_casts"] * (1.0 - tail_flop_share)
+            survive = max(0.0, 1.0 - st["paths"] / max(st["ray_casts"], 1))
+            per_ray = 60.0 + 52.0 * survive + (16.0 + 100.0 + 80.0 if method == 1 else 0.0) + 16.0 * (1.0 - survive)
+            shade_bytes = casts * per_ray
+            line["roofline_shade"] = {"kernel": "k_shade (nearest volume, TD target, direction sampling, compaction)", "bound": "hbm",
+                                      "achieved": shade_bytes / max(st["shade_seconds"], 1e-12) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": shade_bytes / max(st["shade_seconds"], 1e-12) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                      "bytes_per_ray": per_ray, "avg_launch_ms": st["shade_seconds"] / st["shade_launches"] * 1e3, "launches": st["shade_launches"],
+                                      "note": "algorithmic bytes per ray: 60 path state + hit in, 52 x survival out, 16 TD accumulate, 100 CDF (row ends, one row, irradiance), 80 nearest-volume "
+                                              "(one table slot + 4 candidates), 16 x termination frame-buffer add; the tables are L2-resident, so measured DRAM traffic is lower (profiles/)",
+                                      "share_of_kernel_time": st["shade_seconds"] / kernel_total}
+            line["tail"] = {"kernel": "k_bounce run-to-completion (paths left after the planned per-bounce launches)", "seconds": st["tail_seconds"], "launches": st["tail_launches"],
+                            "share_of_kernel_time": st["tail_seconds"] / kernel_total}
         if method == 1 and st["merge_seconds"] > 0:
-            peaks = {}
-            try:
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except (OSError, ValueError):
-                pass
-            hbm_peak = peaks.get("hbm_gbs", 6650.0)
             merge_bytes = nv * 144 * 4 * 4.0                 # per frame: read Q + accumulator counts, write Q-derived CDF (+ sums/visits for touched cells): >= 4 arrays
             line["roofline_merge"] = {"kernel": "k_merge_cdf", "bound": "hbm", "achieved": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None,
-                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}
+                                      "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src}
         if world == 1 and not args.no_cpu_baseline:
             v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}

@@ -175,6 +175,12 @@ typedef struct rlpt_stats_t {
     double trace_seconds;         /* device seconds inside the per-bounce tracing kernels (CUDA events) */
     double merge_seconds;         /* device seconds inside all-reduce + Q merge + CDF rebuild */
     double kd_fallbacks;          /* nearest-volume queries the candidate cells could not decide (answered by the reference's kd search) */
+    double isect_seconds;         /* device seconds inside k_isect launches (event pairs on the launching streams, taken on every fourth frame and scaled to all launches) and their number */
+    double isect_launches;
+    double shade_seconds;         /* the same for k_shade */
+    double shade_launches;
+    double tail_seconds;          /* the same for the run-to-completion k_bounce launches */
+    double tail_launches;
 } rlpt_stats_t;
 int rlpt_stats(rlpt_ctx* ctx, rlpt_stats_t* out);
 int rlpt_stats_reset(rlpt_ctx* ctx);

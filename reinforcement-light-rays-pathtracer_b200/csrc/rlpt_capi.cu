@@ -76,6 +76,11 @@ struct rlpt_ctx {
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
     double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;
     std::vector<cudaEvent_t> phase_ev; size_t phase_used = 0;      // per-frame phase marks of the current render call
+    // per-kernel device times (roofline denominators): event pairs around the k_isect / k_shade / tail launches, on the
+    // streams they are launched on; resolved into the sums below once the work has finished (rlpt_stats / end of a render call)
+    struct KPair { cudaEvent_t a, b; int kind; };
+    std::vector<cudaEvent_t> kev_pool; size_t kev_used = 0; std::vector<KPair> kev_pending;
+    double k_seconds[3] = { 0.0, 0.0, 0.0 }, k_launches[3] = { 0.0, 0.0, 0.0 }, k_all[3] = { 0.0, 0.0, 0.0 };     // 0 k_isect, 1 k_shade, 2 run-to-completion k_bounce; timed launches / all launches
 };
 
 static void free_scene(rlpt_ctx* c) {
@@ -177,6 +182,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq); dqn_train_free(c->dq_train); cudaFree(c->d_nq_q);
     cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->kev_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
     delete c;
     return RLPT_OK;
@@ -697,6 +703,23 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
     return RLPT_OK;
 }
 
+static cudaEvent_t kev_next(rlpt_ctx* c) {
+    if (c->kev_used == c->kev_pool.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return nullptr; c->kev_pool.push_back(e); }
+    return c->kev_pool[c->kev_used++];
+}
+static bool kev_room(rlpt_ctx* c) { return c->kev_pending.size() < 16384; }      // beyond that the timings cover a sample of the launches
+static cudaEvent_t kev_mark(rlpt_ctx* c, cudaStream_t s) { cudaEvent_t e = kev_next(c); if (e) cudaEventRecord(e, s); return e; }
+static void kev_pair(rlpt_ctx* c, cudaEvent_t a, cudaEvent_t b, int kind) { if (a && b) c->kev_pending.push_back({ a, b, kind }); }
+// call only when every stream of the context has drained
+static void kev_resolve(rlpt_ctx* c) {
+    for (const auto& p : c->kev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { c->k_seconds[p.kind] += ms * 1e-3; c->k_launches[p.kind] += 1.0; }
+    }
+    (void)cudaGetLastError();
+    c->kev_pending.clear(); c->kev_used = 0;
+}
+
 // Enqueue one frame of `method` (0 default, 1 SARSA): per lane, primary cast + (max_bounces-1) bounce launches, all
 // asynchronous; the live-ray count of every bounce stays on the device. The lanes fork from and join back into the
 // context stream with events, so callers still see one ordered stream.
@@ -742,20 +765,32 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
             (void)cudaGetLastError();
         }
         int launches = 0;
-        if (split) {
-            if (c->pipe_pre) {
-                if (l.hit_free_valid) CK(cudaStreamWaitEvent(l.pre, l.hit_free, 0));
-                launch_isect(p, dyn, 0, grid, c->smem_bytes, l.pre);
-                CK(cudaEventRecord(l.pre_done, l.pre)); CK(cudaStreamWaitEvent(l.stream, l.pre_done, 0));
-            } else launch_isect(p, dyn, 0, grid, c->smem_bytes, l.stream);
-            launch_shade(p, dyn, method, 0, grid, l.stream); launches += 2;
-        } else { launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream); launches += 1; }
-        for (int b = 1; b < b_tail; ++b) {
-            if (split) { launch_isect(p, dyn, b, grid, c->smem_bytes, l.stream); launch_shade(p, dyn, method, b, grid, l.stream); launches += 2; }
-            else { launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream); launches += 1; }
+        const bool timed = kev_room(c) && (c->frames_done % 4) == 0;        // every fourth frame: enough for the averages, no event traffic on the rest
+        for (int b = 0; b < b_tail; ++b) {
+            if (split) {
+                cudaStream_t s1 = l.stream;
+                if (b == 0 && c->pipe_pre) { s1 = l.pre; if (l.hit_free_valid) CK(cudaStreamWaitEvent(l.pre, l.hit_free, 0)); }
+                cudaEvent_t e0 = timed ? kev_mark(c, s1) : nullptr;
+                launch_isect(p, dyn, b, grid, c->smem_bytes, s1);
+                cudaEvent_t e1 = timed ? kev_mark(c, s1) : nullptr;
+                if (s1 != l.stream) { CK(cudaEventRecord(l.pre_done, l.pre)); CK(cudaStreamWaitEvent(l.stream, l.pre_done, 0)); }
+                cudaEvent_t e2 = (timed && s1 != l.stream) ? kev_mark(c, l.stream) : e1;
+                launch_shade(p, dyn, method, b, grid, l.stream);
+                cudaEvent_t e3 = timed ? kev_mark(c, l.stream) : nullptr;
+                kev_pair(c, e0, e1, 0); kev_pair(c, e2, e3, 1); c->k_all[0] += 1.0; c->k_all[1] += 1.0;
+                launches += 2;
+            } else {
+                if (b == 0) launch_primary(p, dyn, method, grid, c->smem_bytes, l.stream); else launch_bounce(p, dyn, method, b, grid, c->smem_bytes, l.stream);
+                launches += 1;
+            }
         }
         if (split) { CK(cudaEventRecord(l.hit_free, l.stream)); l.hit_free_valid = true; }
-        if (b_tail < g.max_bounces) { launch_tail(p, dyn, method, b_tail, grid, c->smem_bytes, l.stream); launches += 1; }
+        if (b_tail < g.max_bounces) {
+            cudaEvent_t e0 = timed ? kev_mark(c, l.stream) : nullptr;
+            launch_tail(p, dyn, method, b_tail, grid, c->smem_bytes, l.stream); launches += 1;
+            cudaEvent_t e1 = timed ? kev_mark(c, l.stream) : nullptr;
+            kev_pair(c, e0, e1, 2); c->k_all[2] += 1.0;
+        }
         c->launches += (double)launches;
         {   // snapshot of this frame's counts
             const int slot = (int)(l.snap_seq % rlpt_ctx::Lane::SNAPS);
@@ -803,6 +838,7 @@ static int timed_end(rlpt_ctx* c, int frames) {
         if (per >= 3) { CK(cudaEventElapsedTime(&b, c->phase_ev[f * per + 1], c->phase_ev[f * per + 2])); c->merge_seconds += b * 1e-3; }
     }
     c->phase_used = 0;
+    kev_resolve(c);
     CK(cudaGetLastError());
     return RLPT_OK;
 }
@@ -1034,11 +1070,16 @@ int rlpt_frame_save_bmp(rlpt_ctx* c, const char* path) {
 int rlpt_stats(rlpt_ctx* c, rlpt_stats_t* out) {
     if (!c || !out) return fail(RLPT_ERR_ARG, "rlpt_stats: null");
     CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    kev_resolve(c);
     unsigned long long h[8]; CK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
     out->path_length_sum = (double)h[0]; out->zero_contribution_paths = (double)h[1]; out->paths = (double)h[2];
     out->ray_casts = (double)h[0]; out->device_seconds = c->device_seconds; out->frames = c->frames_rendered; out->kernel_launches = c->launches;
     out->triangle_tests = (double)h[3]; out->box_tests = (double)h[4]; out->trace_seconds = c->trace_seconds; out->merge_seconds = c->merge_seconds;
     out->kd_fallbacks = (double)h[5];
+    // event pairs are recorded on every fourth frame; the sums are scaled to all launches of the period
+    auto scaled = [&](int k) { return c->k_launches[k] > 0.0 ? c->k_seconds[k] * (c->k_all[k] / c->k_launches[k]) : 0.0; };
+    out->isect_seconds = scaled(0); out->isect_launches = c->k_all[0]; out->shade_seconds = scaled(1); out->shade_launches = c->k_all[1];
+    out->tail_seconds = scaled(2); out->tail_launches = c->k_all[2];
     return RLPT_OK;
 }
 int rlpt_stats_reset(rlpt_ctx* c) {
@@ -1046,6 +1087,8 @@ int rlpt_stats_reset(rlpt_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * 8, c->stream));
     c->device_seconds = 0.0; c->frames_rendered = 0.0; c->launches = 0.0; c->trace_seconds = 0.0; c->merge_seconds = 0.0;
+    CK(cudaStreamSynchronize(c->stream)); kev_resolve(c);
+    for (int k = 0; k < 3; ++k) { c->k_seconds[k] = 0.0; c->k_launches[k] = 0.0; c->k_all[k] = 0.0; }
     return RLPT_OK;
 }
 

@@ -30,7 +30,8 @@ class Config(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in ("paths", "path_length_sum", "zero_contribution_paths", "ray_casts", "device_seconds", "frames", "kernel_launches",
-                                           "triangle_tests", "box_tests", "trace_seconds", "merge_seconds", "kd_fallbacks")]
+                                           "triangle_tests", "box_tests", "trace_seconds", "merge_seconds", "kd_fallbacks",
+                                           "isect_seconds", "isect_launches", "shade_seconds", "shade_launches", "tail_seconds", "tail_launches")]
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
