@@ -66,7 +66,7 @@ struct rlpt_ctx {
         static constexpr int SNAPS = 4;
         int* h_counts = nullptr; cudaEvent_t snap_ev[SNAPS] = {}; int snap_tag[SNAPS] = {}; uint64_t snap_seq = 0;   // tag = max_bounces the snapshot was taken under (0: none)
     };
-    std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; cudaEvent_t ev_fork = nullptr;
+    std::vector<Lane> lanes; size_t lane_capacity = 0; int counts_len = 0; int lane_spp = 0; int sub_cap = 0; cudaEvent_t ev_fork = nullptr;
     float4* d_accum = nullptr; int accum_pixels = 0;
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
@@ -675,6 +675,9 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
     const rlpt_config& g = c->cfg;
     const int L = choose_lanes(g), lane_spp = g.spp / L;
     const size_t paths = (size_t)g.width * g.height * lane_spp;
+    // NSUB sub-queues of sub_cap slots each (rlpt_kernels.cu "Sub-queues"); counters: one 32-byte sector per (bounce, sub-queue)
+    const size_t sub_cap = ((paths + NSUB - 1) / NSUB + 31) / 32 * 32, slots = sub_cap * NSUB;
+    const size_t counts_ints = (size_t)(g.max_bounces + 2) * NSUB * COUNT_STRIDE;
     if ((int)c->lanes.size() != L || paths > c->lane_capacity || c->counts_len < g.max_bounces + 2) {
         CK(cudaStreamSynchronize(c->stream));
         for (auto& l : c->lanes) if (l.stream) CK(cudaStreamSynchronize(l.stream));
@@ -686,16 +689,16 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
             CK(cudaStreamCreateWithPriority(&l.pre, cudaStreamNonBlocking, prio_lo));
             CK(cudaEventCreateWithFlags(&l.hit_free, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&l.pre_done, cudaEventDisableTiming));
             for (int k = 0; k < 2; ++k) {
-                CK(cudaMalloc(&l.q[k].o, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * paths));
-                CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * paths)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * paths));
+                CK(cudaMalloc(&l.q[k].o, sizeof(float4) * slots)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * slots));
+                CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * slots)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * slots));
             }
-            CK(cudaMalloc(&l.d_counts, sizeof(int) * (g.max_bounces + 2))); CK(cudaMalloc(&l.d_hit, sizeof(float2) * paths));
-            CK(cudaHostAlloc(&l.h_counts, sizeof(int) * (size_t)(g.max_bounces + 2) * rlpt_ctx::Lane::SNAPS, cudaHostAllocDefault));
+            CK(cudaMalloc(&l.d_counts, sizeof(int) * counts_ints)); CK(cudaMalloc(&l.d_hit, sizeof(float2) * slots));
+            CK(cudaHostAlloc(&l.h_counts, sizeof(int) * counts_ints * rlpt_ctx::Lane::SNAPS, cudaHostAllocDefault));
             for (auto& e : l.snap_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         c->lane_capacity = paths; c->counts_len = g.max_bounces + 2;
     }
-    c->lane_spp = lane_spp;
+    c->lane_spp = lane_spp; c->sub_cap = (int)sub_cap;
     if (c->accum_pixels != g.width * g.height) {
         cudaFree(c->d_accum); CK(cudaMalloc(&c->d_accum, sizeof(float4) * (size_t)g.width * g.height));
         CK(cudaMemsetAsync(c->d_accum, 0, sizeof(float4) * (size_t)g.width * g.height, c->stream)); c->accum_pixels = g.width * g.height;
@@ -736,9 +739,10 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats;
     p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n;
     p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
-    const int grid = c->n_sm * 8;
+    const int grid = (c->n_sm * 8 + NSUB - 1) / NSUB * NSUB;              // a whole number of CTAs per sub-queue
     const int split = c->pipe_split, tail_thr = c->pipe_tail;
-    const int len = g.max_bounces + 2;
+    const int len = (g.max_bounces + 2) * NSUB * COUNT_STRIDE;
+    p.sub_cap = c->sub_cap;
     CK(cudaEventRecord(c->ev_fork, c->stream));
     for (size_t li = 0; li < c->lanes.size(); ++li) {
         rlpt_ctx::Lane& l = c->lanes[li];
@@ -759,7 +763,10 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
                 if (cudaEventQuery(l.snap_ev[slot]) != cudaSuccess) continue;
                 if (l.snap_tag[slot] != g.max_bounces) break;         // taken under another configuration
                 const int* hc = l.h_counts + (size_t)slot * len;
-                for (int b = 1; b < g.max_bounces; ++b) if (hc[b] <= tail_thr) { b_tail = b; break; }
+                for (int b = 1; b < g.max_bounces; ++b) {
+                    long long live = 0; for (int k = 0; k < NSUB; ++k) live += hc[(b * NSUB + k) * COUNT_STRIDE];
+                    if (live <= tail_thr) { b_tail = b; break; }
+                }
                 break;
             }
             (void)cudaGetLastError();

@@ -71,7 +71,8 @@ struct FrameParams {
     RadianceDev rm;
     PathQueue q[2];
     float2* hit;                    // split pipeline: (t, as_float(primitive id)) per slot of the current queue
-    int* counts;                    // [max_bounces + 1] live paths entering each bounce (this lane)
+    int* counts;                    // live paths entering each bounce: sub-queue k of bounce b at [(b * NSUB + k) * COUNT_STRIDE] (the Neural-Q tracers keep one queue: [b])
+    int sub_cap;                    // slots per sub-queue
     float4* accum;                  // [W*H] radiance sums (rgb) + sample count in w
     unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests, [5] kd-search fallbacks
     float4* capture_o; float4* capture_d; int* capture_n;
@@ -81,6 +82,8 @@ struct FrameParams {
 };
 
 constexpr int BLOCK = 256;
+constexpr int NSUB = 32;            // sub-queues per lane (rlpt_kernels.cu, "Sub-queues"); the tracing grids are multiples of it
+constexpr int COUNT_STRIDE = 8;     // ints between two sub-queue counters: one 32-byte sector each
 
 // host-visible launchers (rlpt_kernels.cu)
 void launch_primary(const FrameParams& p, const FrameDyn& dyn, int method, int grid, size_t smem, cudaStream_t s);

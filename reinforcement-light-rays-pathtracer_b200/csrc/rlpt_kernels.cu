@@ -299,25 +299,34 @@ __device__ __forceinline__ void store_state(const PathQueue& q, int slot, const 
     __stcs(q.thr + slot, make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec)));
     __stcs(q.meta + slot, (s.sample << 8) | (uint32_t)bounce);
 }
-// wavefront compaction: survivors are packed densely into the next bounce's queue. The slot counter is ONE address, and
-// same-address atomics serialise in L2 (a quarter of k_shade's stall samples with one atomicAdd per warp): the CTA's warps
-// pool their counts through shared memory and one thread reserves the CTA's range -- 8x fewer atomics. Called by every
-// thread of the CTA the same number of times (`iter` = the call's index, selects the double-buffered scratch).
-__device__ __forceinline__ void compact_store(const FrameParams& p, const PathQueue& qo, int bounce, bool alive, const PathState& s, int iter) {
-    __shared__ int s_cnt[2][BLOCK / 32]; __shared__ int s_base[2];
-    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int buf = iter & 1;
+// Sub-queues. A lane's path queue is NSUB independent queues side by side (slots [k * sub_cap, (k + 1) * sub_cap)), each
+// with its own live-path counter per bounce and its own family of CTAs (blockIdx % NSUB == k) that both drains it and
+// refills its successor. A single queue has a single slot counter, and same-address atomics serialise in L2: with one
+// atomicAdd per warp that was a quarter of k_shade's stall samples, with one per CTA the two barriers it needs were a
+// fifth. NSUB counters in separate 32-byte sectors take 1/NSUB of the traffic each and need no barrier. Survivors of
+// family k never outnumber its inputs, so sub_cap = its share of the primary paths bounds every later bounce.
+struct SubQueue { int base; int n; int first; int stride; int* next_count; };
+template <bool PRIMARY>
+__device__ __forceinline__ SubQueue sub_queue(const FrameParams& p, int bounce) {
+    SubQueue q;
+    const int k = (int)(blockIdx.x % NSUB), j = (int)(blockIdx.x / NSUB), fam = (int)(gridDim.x / NSUB);
+    q.base = k * p.sub_cap;
+    if (PRIMARY) { const int total = p.width * p.height * p.spp; q.n = min(p.sub_cap, max(0, total - q.base)); }
+    else q.n = p.counts[(bounce * NSUB + k) * COUNT_STRIDE];
+    q.first = j * BLOCK + (int)threadIdx.x; q.stride = fam * BLOCK;
+    q.next_count = p.counts + ((bounce + 1) * NSUB + k) * COUNT_STRIDE;
+    return q;
+}
+// wavefront compaction: survivors are packed densely into the sub-queue's successor (one atomicAdd per warp)
+__device__ __forceinline__ void compact_store(const SubQueue& sq, const PathQueue& qo, int bounce, bool alive, const PathState& s) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
     const unsigned bal = __ballot_sync(full, alive);
-    if (lane == 0) s_cnt[buf][warp] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int total = 0;
-#pragma unroll
-        for (int w = 0; w < BLOCK / 32; ++w) { int c = s_cnt[buf][w]; s_cnt[buf][w] = total; total += c; }
-        s_base[buf] = total ? atomicAdd(p.counts + bounce + 1, total) : 0;
+    if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(sq.next_count, __popc(bal));
+        base = __shfl_sync(full, base, 0);
+        if (alive) store_state(qo, sq.base + base + __popc(bal & lanemask_lt()), s, bounce + 1);
     }
-    __syncthreads();
-    if (alive) store_state(qo, s_base[buf] + s_cnt[buf][warp] + __popc(bal & lanemask_lt()), s, bounce + 1);
 }
 
 // Everything of one bounce after the closest hit (t, gid) of path `s` is known: TD target of the previous (volume,
@@ -419,24 +428,23 @@ __device__ __forceinline__ void capture_ray(const FrameParams& p, const FrameDyn
 // Fused: one bounce of one path per thread (PRIMARY: the path is generated here), or with TAIL every remaining bounce.
 template <bool STAGED, bool SARSA, bool PRIMARY, bool TAIL>
 __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
-    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    const int n_round = (n_in + BLOCK - 1) / BLOCK * BLOCK;       // whole CTAs stay together for the collectives
-    if ((int)(blockIdx.x * blockDim.x) >= n_round) return;        // nothing for this CTA: do not even stage the scene
+    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
+    const int n_round = (sq.n + 31) & ~31;                        // whole warps stay together for the collectives
+    if ((int)(blockIdx.x / NSUB) * BLOCK >= n_round) return;      // nothing for this CTA: do not even stage the scene
     SceneView<STAGED> v = stage_scene<STAGED, true>(p.scene);
     const unsigned full = 0xffffffffu;
     const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
     unsigned st_len = 0, st_zero = 0, st_term = 0, n_tri = 0, n_box = 0, n_kd = 0;
     const float H = (float)p.height;
     auto shade = [&](int k) { return v.shade(k); };
-    int iter = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x, ++iter) {
-        bool live = i < n_in;
+    for (int i = sq.first; i < n_round; i += sq.stride) {
+        bool live = i < sq.n;
         PathState s{};
         if (live) {
             if (PRIMARY) {
-                primary_state(p, dyn, i, s);
-                if (i % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);          // samples accumulated for this pixel
-            } else load_state(qi, i, s);
+                primary_state(p, dyn, sq.base + i, s);
+                if ((sq.base + i) % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);          // samples accumulated for this pixel
+            } else load_state(qi, sq.base + i, s);
         }
         int b = bounce;
         while (true) {
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
             ++b;
             if (!__any_sync(full, live)) break;
         }
-        if (!TAIL) compact_store(p, qo, bounce, live, s, iter);
+        if (!TAIL) compact_store(sq, qo, bounce, live, s);
     }
     flush_path_stats(p, st_len, st_zero, st_term, n_kd);
     flush_work_counters(p, n_tri, n_box);
@@ -458,19 +466,19 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
 // Split, first half: the closest hit of every ray of queue `bounce` -> hit[slot] = (t, as_float(primitive id))
 template <bool STAGED, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
-    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    if ((int)(blockIdx.x * blockDim.x) >= n_in) return;
+    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
+    if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
     SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
     const PathQueue qi = p.q[bounce & 1];
     unsigned n_tri = 0, n_box = 0;
     const float H = (float)p.height;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+    for (int i = sq.first; i < sq.n; i += sq.stride) {
         float ox, oy, oz, dx, dy, dz;
         if (PRIMARY) {
-            PathState s; primary_state(p, dyn, i, s);
+            PathState s; primary_state(p, dyn, sq.base + i, s);
             ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz;
         } else {
-            float4 a = __ldcs(qi.o + i), b = __ldcs(qi.d + i);
+            float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i);
             ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z;
         }
         if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
         }
         float t, sdx, sdy, sdz; int gid;
         closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
-        __stcs(p.hit + i, make_float2(t, __int_as_float(gid)));
+        __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(gid)));
     }
     flush_work_counters(p, n_tri, n_box);
 }
@@ -487,25 +495,24 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 // Split, second half: shading records come through the read-only path (2.4 KB for Cornell: L1-resident), no staging
 template <bool SARSA, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
-    const int n_in = PRIMARY ? p.width * p.height * p.spp : p.counts[bounce];
-    const int n_round = (n_in + BLOCK - 1) / BLOCK * BLOCK;
+    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
+    const int n_round = (sq.n + 31) & ~31;
     const PathQueue qi = p.q[bounce & 1], qo = p.q[(bounce + 1) & 1];
     unsigned st_len = 0, st_zero = 0, st_term = 0, n_kd = 0;
     const float4* __restrict__ shade_g = p.scene.shade;
     auto shade = [&](int k) { return __ldg(shade_g + k); };
-    int iter = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x, ++iter) {
-        bool live = i < n_in;
+    for (int i = sq.first; i < n_round; i += sq.stride) {
+        bool live = i < sq.n;
         PathState s{}; float t = T_MISS; int gid = -1;
         if (live) {
             if (PRIMARY) {
-                primary_state(p, dyn, i, s);
-                if (i % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);
-            } else load_state(qi, i, s);
-            float2 h = __ldcs(p.hit + i); t = h.x; gid = __float_as_int(h.y);
+                primary_state(p, dyn, sq.base + i, s);
+                if ((sq.base + i) % p.spp == 0) atomicAdd(&p.accum[s.pixel].w, (float)p.spp);
+            } else load_state(qi, sq.base + i, s);
+            float2 h = __ldcs(p.hit + sq.base + i); t = h.x; gid = __float_as_int(h.y);
         }
         live = shade_step<SARSA, !PRIMARY>(p, dyn, shade, p.scene.n_surf, bounce, live, s, t, gid, st_len, st_zero, st_term, n_kd);
-        compact_store(p, qo, bounce, live, s, iter);
+        compact_store(sq, qo, bounce, live, s);
     }
     flush_path_stats(p, st_len, st_zero, st_term, n_kd);
 }

@@ -49,9 +49,14 @@ def test_mape_parity_cornell(ctx, ref_cuda, golden_scenes):
     mean_rel = float(np.abs(p1024.mean(0) - np.nan_to_num(gt_f).mean(0)).max() / np.nan_to_num(gt_f).mean())
 
     # Expected SARSA, 8 training frames of 32 spp; the reference's frame 0 is NaN-poisoned (initial exclusive CDF), skip it there
-    ref_cuda.rmap_build()
-    rmean, rlast, rst = ref_cuda.render_sarsa(9, 1)
-    mape_ref_sarsa = mape_score(gt, _img8(rmean, w, h))
+    # The reference's own result varies from run to run (its TD update is a racy read-modify-write, radiance_volume.cu:283-301:
+    # 0.524 .. 0.561 over five runs on one B200, the product 0.502 .. 0.506), so the reference side is the median of three runs.
+    ref_runs = []
+    for _ in range(3):
+        ref_cuda.rmap_build()
+        rmean, rlast, rst = ref_cuda.render_sarsa(9, 1)
+        ref_runs.append(mape_score(gt, _img8(rmean, w, h)))
+    mape_ref_sarsa = float(np.median(ref_runs))
     ref_sarsa_mpaths = w * h * spp / (rst[1:, 2].mean() * 1e-3) / 1e6
     ctx.frame_reset(); ctx.stats_reset(); ctx.radiance_map_build()
     ctx.render_sarsa(1); ctx.frame_reset(); ctx.stats_reset()                # same protocol: drop frame 0 from the image
@@ -59,7 +64,7 @@ def test_mape_parity_cornell(ctx, ref_cuda, golden_scenes):
     mape_prod_sarsa = mape_score(gt, _img8(ctx.frame_download(), w, h))
     st_s = ctx.stats()
     out = dict(mape_ref_default_32spp=mape_ref_default, mape_prod_default_32spp=mape_prod_default, mape_refB_1024spp=mape_refb, mape_prod_default_1024spp=mape_converged,
-               mean_rel_diff_1024spp=mean_rel, mape_ref_sarsa_8x32spp=mape_ref_sarsa, mape_prod_sarsa_8x32spp=mape_prod_sarsa,
+               mean_rel_diff_1024spp=mean_rel, mape_ref_sarsa_8x32spp=mape_ref_sarsa, mape_ref_sarsa_runs=ref_runs, mape_prod_sarsa_8x32spp=mape_prod_sarsa,
                ref_kernels_default_mpaths_s=ref_default_mpaths, ref_kernels_sarsa_mpaths_s=ref_sarsa_mpaths,
                prod_sarsa_mpaths_s=st_s["paths"] / st_s["device_seconds"] / 1e6,
                ref_sarsa_avg_path_length_int_truncated=float(rst[1:, 0].mean()), prod_sarsa_avg_path_length=st_s["path_length_sum"] / st_s["paths"],
