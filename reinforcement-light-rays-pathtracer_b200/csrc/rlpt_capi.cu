@@ -36,7 +36,7 @@ struct rlpt_ctx {
     // scene
     bool have_scene = false;
     int n_surf = 0, n_light = 0, bvh_depth = 0;
-    float4 *d_tri = nullptr, *d_shade = nullptr, *d_bvh = nullptr; float* d_surf_lum_over_pi = nullptr;
+    float4 *d_tri = nullptr, *d_shade = nullptr, *d_bvh = nullptr, *d_scan = nullptr; int* d_scan_gid = nullptr; float* d_surf_lum_over_pi = nullptr;
     std::vector<float> h_surf_v, h_surf_nrm, h_surf_rgb, h_light_v, h_light_rgb;
     std::vector<int> h_surf_class;
     SceneDev scene{};
@@ -84,7 +84,7 @@ struct rlpt_ctx {
 };
 
 static void free_scene(rlpt_ctx* c) {
-    cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_surf_lum_over_pi);
+    cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_surf_lum_over_pi); cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
     c->d_tri = c->d_shade = c->d_bvh = nullptr; c->d_surf_lum_over_pi = nullptr; c->have_scene = false;
 }
 static void free_rmap(rlpt_ctx* c) {
@@ -223,6 +223,22 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
         scan(c->h_surf_v); scan(c->h_light_v);
         sc.det_small = (std::isfinite(worst) && (double)c->cfg.height * worst * 1.001 < 8388608.0) ? 1 : 0;
     }
+    // scan units of the conservative pre-test (rlpt_device.cuh, unit_candidates): parallelogram pairs, then single triangles
+    cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
+    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
+    if (sc.brute && n_tri <= 64 && !getenv("RLPT_NO_UNITS")) {
+        std::vector<float> verts(c->h_surf_v); verts.insert(verts.end(), c->h_light_v.begin(), c->h_light_v.end());
+        HostScanUnits hu; host_build_scan_units(verts.data(), n_tri, hu);
+        if (hu.n_pairs > 0 && (int)hu.slot_gid.size() == n_tri) {
+            while (hu.slot_gid.size() % 4) hu.slot_gid.push_back(0);             // staged four at a time
+            CK(cudaMalloc(&c->d_scan, sizeof(float) * hu.scan.size())); CK(cudaMalloc(&c->d_scan_gid, sizeof(int) * hu.slot_gid.size()));
+            CK(cudaMemcpy(c->d_scan, hu.scan.data(), sizeof(float) * hu.scan.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->d_scan_gid, hu.slot_gid.data(), sizeof(int) * hu.slot_gid.size(), cudaMemcpyHostToDevice));
+            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs;
+            sc.k1 = hu.k1; sc.k2 = hu.k2; sc.k3 = hu.k3; sc.vmax = hu.vmax;
+            c->smem_bytes = scene_smem_bytes(sc);
+        }
+    }
     return RLPT_OK;
 }
 
@@ -328,10 +344,11 @@ int rlpt_closest_hit_device(rlpt_ctx* c, const float* d_org, const float* d_dir,
     if (n < 0) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: negative ray count");
     if (n == 0) return RLPT_OK;
     CK(cudaSetDevice(c->device));
-    SceneDev saved = c->scene; size_t saved_smem = c->smem_bytes;
-    if (traversal) { int rc = choose_traversal(c, traversal); if (rc) { c->scene = saved; c->smem_bytes = saved_smem; return rc; } }
+    // a traversal override lasts for this call: choose_traversal owns device buffers (scan units), so the configured mode
+    // is re-established by calling it again rather than by restoring a saved copy of the scene descriptor
+    if (traversal) { int rc = choose_traversal(c, traversal); if (rc) { (void)choose_traversal(c, 0); return rc; } }
     launch_closest_hit(c->scene, d_org, d_dir, n, (float)c->cfg.height, d_type, d_index, d_t, d_counters, c->smem_bytes, c->stream);
-    c->scene = saved; c->smem_bytes = saved_smem;
+    if (traversal) { CK(cudaStreamSynchronize(c->stream)); int rc = choose_traversal(c, 0); if (rc) return rc; }
     CK(cudaGetLastError());
     return RLPT_OK;
 }

@@ -179,6 +179,40 @@ RLPT_HD bool tri_candidate_small(const TriRec& r, float ox, float oy, float oz, 
     return !(sign_out || sum_out);
 }
 
+// Conservative pre-test of one scan unit: a triangle A = (v0; e1, e2) and optionally the triangle B that completes the
+// parallelogram v0 + u e1 + v e2, u, v in [0, 1] (B = {v0 + e1, v0 + e2, v0 + e1 + e2}). With a = -(dir * SCREEN_HEIGHT),
+// b = o - v0, n = e1 x e2 and c = a x b, Cramer's numerators of the reference's system (G/rays/ray.cu:39-74,115-141) are
+//     D = det[a e1 e2] = a . n      X = det[b e1 e2] = b . n (t)      Y = det[a b e2] = e2 . c (u)      Z = det[a e1 b] = -(e1 . c) (v)
+// -- 21 multiply-adds for BOTH triangles instead of the reference's expression tree per triangle. They are NOT the
+// reference's roundings, so they decide nothing: they only discard triangles that the exact solve (tri_solve) is certain to
+// reject. Error bounds (u = 2^-24; A = max |a_i|, E = largest |edge component| of the scene, Bm = max |o_i| + largest
+// |vertex coordinate|): the reference's own dy, dz are within 36 u A E Bm of the exact values, these Y, Z too; detA and D
+// within 30 u A E^2; dx and X within 36 u E^2 Bm. del = 2e-5 A E (Bm + E) and delx = 4e-5 E^2 Bm are more than twice
+// the sums (plus the slack of a parallelogram whose fourth vertex is off by up to 1e-6 of the scene size). A triangle is
+// kept unless, by more than these bounds, t < 0, or a barycentric numerator has the wrong sign, or u + v is on the wrong
+// side of 1 (all with the one threshold 3 del); when |D| <= del the orientation itself is uncertain and everything is kept.
+// Returns bit 0 = A, bit 1 = B. Triangles without a parallelogram partner go through tri_candidate(_small) instead.
+// The partner B shares an edge of A and completes a parallelogram; which edge decides where B lies in A's (u, v):
+//   apex v0 (shares v1 v2): u <= 1, v <= 1, u + v >= 1      apex v1 (shares v0 v2): u <= 0, v <= 1, u + v >= 0
+//   apex v2 (shares v0 v1): u <= 1, v <= 0, u + v >= 0      -- i.e. u <= pu, v <= pv, u + v >= ps with (pu, pv, ps) in {0, 1}
+struct UnitRec { float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz, pu, pv, ps; };
+// Branch-free: each triangle's three conditions and the t >= 0 condition (scaled by kx = 3 del / delx so that it shares the
+// threshold) go through one minimum; when the orientation is uncertain the threshold becomes -infinity (everything is kept).
+RLPT_HD unsigned unit_candidates(const UnitRec& r, float ox, float oy, float oz, float a0, float a1, float a2, float del, float kx) {
+    const float bx = ox - r.v0x, by = oy - r.v0y, bz = oz - r.v0z;
+    const float cx = a1 * bz - a2 * by, cy = a2 * bx - a0 * bz, cz = a0 * by - a1 * bx;
+    const float D = a0 * r.nx + a1 * r.ny + a2 * r.nz;
+    const float X = bx * r.nx + by * r.ny + bz * r.nz;
+    const float Y = r.e2x * cx + r.e2y * cy + r.e2z * cz;
+    const float Z = -(r.e1x * cx + r.e1y * cy + r.e1z * cz);
+    const float sg = D < 0.f ? -1.f : 1.f;
+    const float Ds = fabsf(D), Xk = X * (sg * kx), Ys = Y * sg, Zs = Z * sg, S = Ys + Zs;
+    const float thr = Ds > del ? -3.f * del : -3.0e38f;     // NaN compares false: kept
+    const float mA = fminf(fminf(Ys, Zs), fminf(Ds - S, Xk));
+    const float mB = fminf(fminf(r.pu * Ds - Ys, r.pv * Ds - Zs), fminf(S - r.ps * Ds, Xk));
+    return (!(mA < thr) ? 1u : 0u) | (!(mB < thr) ? 2u : 0u);
+}
+
 // ---------------------------------------------------------------- hemisphere helpers (G/utils/hemisphere_helpers.cu)
 // create_normal_coordinate_system (:31-44); evaluated once per surface at upload, kept beside the triangle.
 RLPT_HD void tangent_frame(f3 n, f3& T, f3& B) {

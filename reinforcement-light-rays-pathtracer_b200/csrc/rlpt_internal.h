@@ -24,6 +24,12 @@ struct SceneDev {
     int smem_tris;      // primitives staged in shared memory (all of them, or 0 when they do not fit)
     int smem_nodes;     // BVH nodes staged in shared memory (BFS order, so this is the top of the tree)
     int smem_shade;     // 1 when the shading records are staged too
+    // conservative pre-test of the brute-force scan (rlpt_device.cuh, unit_candidates): pairs of triangles that form a
+    // parallelogram are tested together, 4 float4 per pair: (v0, e1.x) (e1.yz, e2.xy) (e2.z, n) (pu, pv, ps, -) with n = e1 x e2
+    // and (pu, pv, ps) placing the second triangle in the first one's (u, v). slot_gid[slot] = primitive id: slots 2u, 2u+1 are
+    // pair u, the unpaired primitives follow (n_tri slots in all, padded to a multiple of 4).
+    const float4* scan; const int* slot_gid; int n_units;
+    float k1, k2, k3, vmax;   // error-bound coefficients of the pre-test (host: choose_traversal), largest |vertex coordinate|
     int det_small;      // 1 when SCREEN_HEIGHT * max |e1| |e2| < 2^23: no determinant of this scene can reach the range where tri_candidate's sign test needs its guard
 };
 

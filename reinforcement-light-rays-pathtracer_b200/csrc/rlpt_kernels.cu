@@ -21,9 +21,10 @@ extern __shared__ float4 s_scene[];
 
 template <bool STAGED>
 struct SceneView {
-    const float4* tri_s; const float4* shade_s; const float4* nodes_s;
+    const float4* tri_s; const float4* shade_s; const float4* nodes_s; const float4* scan_s; const int* gid_s;
     const float4* tri_g; const float4* shade_g; const float4* nodes_g;
-    int n_tri, n_surf, smem_nodes, brute, det_small;
+    int n_tri, n_surf, smem_nodes, brute, det_small, n_units;
+    float k1, k2, k3, vmax;
     __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
     __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
     __device__ __forceinline__ float4 node(int i) const {
@@ -37,18 +38,24 @@ template <bool STAGED, bool SHADE = true>
 __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     SceneView<STAGED> v;
     v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute; v.det_small = sc.det_small;
+    v.n_units = sc.n_units; v.k1 = sc.k1; v.k2 = sc.k2; v.k3 = sc.k3; v.vmax = sc.vmax;
     float4* p = s_scene;
     int nt = 3 * sc.smem_tris, ns = (SHADE && sc.smem_shade) ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
     v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
     for (int i = threadIdx.x; i < nt; i += blockDim.x) p[i] = __ldg(sc.tri + i);
     for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
     for (int i = threadIdx.x; i < nn; i += blockDim.x) p[nt + ns + i] = __ldg(sc.bvh + i);
+    // brute-force scenes: the parallelogram units of the conservative pre-test (4 float4 each), then the slot -> primitive table
+    const int nu = 4 * sc.n_units, ng = sc.n_units > 0 ? (sc.n_tri + 3) / 4 : 0;
+    v.scan_s = p + nt + ns + nn; v.gid_s = reinterpret_cast<const int*>(p + nt + ns + nn + nu);
+    for (int i = threadIdx.x; i < nu; i += blockDim.x) p[nt + ns + nn + i] = __ldg(sc.scan + i);
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) p[nt + ns + nn + nu + i] = __ldg(reinterpret_cast<const float4*>(sc.slot_gid) + i);
     __syncthreads();
     return v;
 }
 
 size_t scene_smem_bytes(const SceneDev& sc) {
-    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes);
+    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes + (size_t)4 * sc.n_units + (sc.n_units > 0 ? (size_t)(sc.n_tri + 3) / 4 : 0));
 }
 
 // ------------------------------------------------------------------------------------------------ closest hit
@@ -77,6 +84,61 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
     const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
     best_t = T_MISS; best_gid = -1;
     if (v.brute) {
+        if (v.n_units > 0) {
+            // phase 1 marks candidates in SLOT order: slots 2u, 2u+1 = the two triangles of parallelogram u (one conservative
+            // pre-test for both, unit_candidates), then one slot per remaining triangle (tri_candidate). phase 2: the exact solve
+            // of the marked slots; slots are not in primitive order, so ties go to the lower id explicitly (the reference's
+            // scan order with strict <).
+            const float A_ = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
+            const float Bm = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + v.vmax;
+            const float del = A_ * (v.k1 * Bm + v.k2), kx = (3.f * del) / (v.k3 * Bm);
+            unsigned long long mask = 0ull;
+            int u = 0;
+            for (; u + 2 <= v.n_units; u += 2) {
+                unsigned bits = 0u;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float4 q0 = v.scan_s[4 * (u + k)], q1 = v.scan_s[4 * (u + k) + 1], q2 = v.scan_s[4 * (u + k) + 2], q3 = v.scan_s[4 * (u + k) + 3];
+                    const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
+                    bits |= unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * k);
+                }
+                mask |= (unsigned long long)bits << (2 * u);
+            }
+            for (; u < v.n_units; ++u) {
+                const float4 q0 = v.scan_s[4 * u], q1 = v.scan_s[4 * u + 1], q2 = v.scan_s[4 * u + 2], q3 = v.scan_s[4 * u + 3];
+                const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
+                mask |= (unsigned long long)unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * u);
+            }
+            int slot = 2 * v.n_units;
+            if (v.det_small) {
+                for (; slot + 4 <= v.n_tri; slot += 4) {
+                    unsigned bits = 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        TriRec r = load_tri(v, v.gid_s[slot + k]);
+                        if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) bits |= 1u << k;
+                    }
+                    mask |= (unsigned long long)bits << slot;
+                }
+                for (; slot < v.n_tri; ++slot) {
+                    TriRec r = load_tri(v, v.gid_s[slot]);
+                    if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
+                }
+            } else {
+                for (; slot < v.n_tri; ++slot) {
+                    TriRec r = load_tri(v, v.gid_s[slot]);
+                    if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
+                }
+            }
+            if (COUNT) n_tri += (unsigned)v.n_tri;
+            while (mask) {
+                const int sl = __ffsll((long long)mask) - 1; mask &= mask - 1ull;
+                const int gid = v.gid_s[sl];
+                TriRec r = load_tri(v, gid); float t;
+                if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+            }
+            return;
+        }
         if (v.n_tri <= 64) {
             // two phases: (1) a branch-free pass over every triangle marks the candidates no early out can reject,
             // (2) the full solve with its divisions runs on the marked ones only, in primitive order (so "first lowest id

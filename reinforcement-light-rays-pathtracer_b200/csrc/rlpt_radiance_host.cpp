@@ -329,4 +329,54 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
     }
 }
 
+
+void host_build_scan_units(const float* verts, int n_tri, HostScanUnits& out) {
+    out = HostScanUnits{};
+    auto vert = [&](int g) { return verts + 9 * (size_t)g; };
+    double emax = 0.0, vmax = 0.0;
+    for (int g = 0; g < n_tri; ++g) {
+        const float* v = vert(g);
+        for (int k = 0; k < 9; ++k) vmax = std::max(vmax, (double)std::fabs(v[k]));
+        for (int k = 0; k < 3; ++k) { emax = std::max(emax, (double)std::fabs(v[3 + k] - v[k])); emax = std::max(emax, (double)std::fabs(v[6 + k] - v[k])); }
+    }
+    if (!std::isfinite(emax) || !std::isfinite(vmax)) return;
+    const double tau = 1e-6 * std::max(1.0, vmax);          // how far a partner's vertices may be from the exact parallelogram
+    std::vector<int> partner(n_tri, -1), apex(n_tri, 0); std::vector<char> used(n_tri, 0);
+    for (int i = 0; i < n_tri; ++i) {
+        if (used[i]) continue;
+        const float* a = vert(i);
+        for (int ap = 0; ap < 3 && partner[i] < 0; ++ap) {
+            // the partner's vertices: the two of A other than the apex, and their sum minus the apex
+            const int s1 = (ap + 1) % 3, s2 = (ap + 2) % 3;
+            double want[3][3];
+            for (int k = 0; k < 3; ++k) { want[0][k] = a[3 * s1 + k]; want[1][k] = a[3 * s2 + k]; want[2][k] = (double)a[3 * s1 + k] + (double)a[3 * s2 + k] - (double)a[3 * ap + k]; }
+            for (int j = i + 1; j < n_tri && partner[i] < 0; ++j) {
+                if (used[j]) continue;
+                const float* b = vert(j);
+                int hit = 0; bool taken[3] = { false, false, false };
+                for (int w = 0; w < 3; ++w) for (int q = 0; q < 3; ++q) {
+                    if (taken[q]) continue;
+                    if (std::fabs(b[3 * q] - want[w][0]) <= tau && std::fabs(b[3 * q + 1] - want[w][1]) <= tau && std::fabs(b[3 * q + 2] - want[w][2]) <= tau) { taken[q] = true; ++hit; break; }
+                }
+                if (hit == 3) { partner[i] = j; apex[i] = ap; used[i] = used[j] = 1; }
+            }
+        }
+    }
+    for (int i = 0; i < n_tri; ++i) {
+        if (partner[i] < 0) continue;
+        const float* v = vert(i);
+        const float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+        const double n[3] = { (double)e1[1] * e2[2] - (double)e1[2] * e2[1], (double)e1[2] * e2[0] - (double)e1[0] * e2[2], (double)e1[0] * e2[1] - (double)e1[1] * e2[0] };
+        // where the partner lies in (u, v): u <= pu, v <= pv, u + v >= ps  (rlpt_device.cuh, unit_candidates)
+        const float pu = apex[i] == 1 ? 0.f : 1.f, pv = apex[i] == 2 ? 0.f : 1.f, ps = apex[i] == 0 ? 1.f : 0.f;
+        const float rec[16] = { v[0], v[1], v[2], e1[0], e1[1], e1[2], e2[0], e2[1], e2[2], (float)n[0], (float)n[1], (float)n[2], pu, pv, ps, 0.f };
+        out.scan.insert(out.scan.end(), rec, rec + 16);
+        out.slot_gid.push_back(i); out.slot_gid.push_back(partner[i]);
+    }
+    out.n_pairs = (int)(out.scan.size() / 16);
+    for (int i = 0; i < n_tri; ++i) if (!used[i]) out.slot_gid.push_back(i);
+    // error-bound coefficients of unit_candidates: del = A (k1 Bm + k2), delx = k3 Bm
+    out.k1 = (float)(2e-5 * emax); out.k2 = (float)(2e-5 * emax * emax + 8.0 * tau * emax); out.k3 = (float)(4e-5 * emax * emax); out.vmax = (float)vmax;
+}
+
 }  // namespace rlpt

@@ -77,3 +77,56 @@ extern "C" int devfn_check_vcells(const float* sv, int ns, float area_per_sample
     out[6] = decided2; out[7] = (double)hv.xkeys; out[8] = (double)hv.xlisted;
     return 0;
 }
+
+// Conservativeness of the brute-force pre-test (unit_candidates): `nr` seeded rays (origins on the surfaces or at the camera,
+// directions uniform on the sphere); every primitive the exact solve (tri_solve, the reference's arithmetic) accepts must be
+// marked. out[0] = accepted-but-unmarked (must be 0), out[1] = marked per ray, out[2] = accepted per ray, out[3] = units,
+// out[4] = parallelogram pairs
+extern "C" int devfn_check_units(const float* verts, int n_tri, int nr, unsigned seed, float H, const float* cam, double* out) {
+    HostScanUnits hu; host_build_scan_units(verts, n_tri, hu);
+    const int nu = hu.n_pairs;
+    if ((int)hu.slot_gid.size() != n_tri) return 1;
+    std::mt19937 rng(seed); std::uniform_real_distribution<float> U(0.f, 1.f); std::normal_distribution<float> Nrm(0.f, 1.f);
+    double missed = 0, marked = 0, accepted = 0, pairs = nu;
+    for (int q = 0; q < nr; ++q) {
+        float o[3], d[3];
+        if (q % 4 == 0) { o[0] = cam[0]; o[1] = cam[1]; o[2] = cam[2]; }
+        else {
+            const float* t = verts + 9 * (size_t)(rng() % (unsigned)n_tri);
+            float u = U(rng), v = U(rng); if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
+            for (int k = 0; k < 3; ++k) o[k] = t[k] + u * (t[3 + k] - t[k]) + v * (t[6 + k] - t[k]);
+        }
+        for (int k = 0; k < 3; ++k) d[k] = Nrm(rng);
+        if (q % 7 == 0) d[rng() % 3] = 0.f;                  // axis-aligned planes: grazing and edge-on rays
+        f3 dn = normalize_ref(f3{ d[0], d[1], d[2] });
+        if (q % 4 != 0) for (int k = 0; k < 3; ++k) o[k] = fmaf(RAY_EPS, (&dn.x)[k], o[k]);
+        const float sdx = dn.x * H, sdy = dn.y * H, sdz = dn.z * H, a0 = 0.f - sdx, a1 = 0.f - sdy, a2 = 0.f - sdz;
+        const float A_ = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2))), Bm = fmaxf(fabsf(o[0]), fmaxf(fabsf(o[1]), fabsf(o[2]))) + hu.vmax;
+        const float del = A_ * (hu.k1 * Bm + hu.k2), kx = (3.f * del) / (hu.k3 * Bm);
+        std::vector<char> mark(n_tri, 0);
+        for (int u = 0; u < nu; ++u) {
+            const float* r = &hu.scan[16 * (size_t)u];
+            UnitRec rec{ r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14] };
+            unsigned bits = unit_candidates(rec, o[0], o[1], o[2], a0, a1, a2, del, kx);
+            if (bits & 1u) mark[hu.slot_gid[2 * u]] = 1;
+            if (bits & 2u) mark[hu.slot_gid[2 * u + 1]] = 1;
+        }
+        for (int sl = 2 * nu; sl < n_tri; ++sl) {
+            const int g = hu.slot_gid[sl]; const float* v = verts + 9 * (size_t)g;
+            const float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+            TriRec tr{ v[0], v[1], v[2], e1[0], e1[1], e1[2], e2[0], e2[1], e2[2], fmaf(e1[1], e2[2], -(e1[2] * e2[1])) };
+            if (tri_candidate_small(tr, o[0], o[1], o[2], a0, a1, a2)) mark[g] = 1;
+        }
+        for (int g = 0; g < n_tri; ++g) {
+            const float* v = verts + 9 * (size_t)g;
+            const float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+            TriRec tr{ v[0], v[1], v[2], e1[0], e1[1], e1[2], e2[0], e2[1], e2[2], fmaf(e1[1], e2[2], -(e1[2] * e2[1])) };
+            float t;
+            const bool acc = tri_solve(tr, o[0], o[1], o[2], a0, a1, a2, T_MISS, t);
+            if (mark[g]) marked += 1;
+            if (acc) { accepted += 1; if (!mark[g]) missed += 1; }
+        }
+    }
+    out[0] = missed; out[1] = marked / nr; out[2] = accepted / nr; out[3] = nu; out[4] = pairs;
+    return 0;
+}

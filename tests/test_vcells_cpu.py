@@ -38,3 +38,20 @@ def test_candidate_cells_agree_with_kd_search(devfn, golden_scenes, scene, jitte
                               xkeys=xkeys, mean_xlist=xlisted / max(xkeys, 1)))
     assert mism == 0
     assert decided / nq >= min_decided
+
+
+@pytest.mark.parametrize("scene,cam", [("cornell", (0.0, 0.0, -3.0)), ("door_room", (0.0, 0.5, -0.9)), ("archway", (-1.0, 0.2, -0.99))])
+def test_scan_unit_pretest_is_conservative(devfn, golden_scenes, scene, cam):
+    """unit_candidates (the brute-force scan's pre-test over triangles / parallelogram pairs) never discards a primitive that
+    the exact solve with the reference's arithmetic (tri_solve <- G/rays/ray.cu:39-74,115-141) accepts."""
+    s = golden_scenes[scene]
+    verts = np.ascontiguousarray(np.concatenate([np.asarray(s["sv"], np.float32).reshape(-1, 9), np.asarray(s["lv"], np.float32).reshape(-1, 9)]))
+    camv = np.asarray(cam, np.float32)
+    out = np.zeros(5, dtype=np.float64)
+    devfn.devfn_check_units.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    nr = 400000
+    assert devfn.devfn_check_units(verts.ctypes.data, len(verts), nr, 11, 512.0, camv.ctypes.data, out.ctypes.data) == 0
+    missed, marked, accepted, units, pairs = out
+    print(scene, dict(missed=missed, marked_per_ray=marked, accepted_per_ray=accepted, units=units, pairs=pairs))
+    assert missed == 0
+    assert accepted > 0.5 and marked < 6.0 * accepted + 2.0        # the pre-test is tight: besides the hits it keeps lines through a triangle behind the origin (single triangles) and the plane the ray starts on
