@@ -38,14 +38,23 @@ WORKLOADS = {
     # name: (scene in tests/golden/scenes.npz, method, camera, env_light)
     "cornell_sarsa": ("cornell", 1, (0.0, 0.0, -3.0), 0.0),
     "cornell_default": ("cornell", 0, (0.0, 0.0, -3.0), 0.0),
-    "door_room_sarsa": ("door_room", 1, (0.0, 0.5, -0.9), 0.0),
+    # BASELINE.json configs[2]: door_room.obj with its own light quad and colours (tests/golden/make_presets.py)
+    "door_room_sarsa": ("door_room_lit", 1, (0.0, 0.5, -0.9), 0.0),
     "archway_sarsa": ("archway", 1, (-1.0, 0.2, -0.99), 0.0),
+    # BASELINE.json configs[3]: the large mesh through the BVH. The reference has no preset for it: the
+    # importer's commented normalisation (tests/golden/make_presets.py), lit by ENVIRONMENT_LIGHT = 1
+    "medieval_default": ("medieval_norm", 0, (0.0, 0.0, -3.0), 1.0),
+    "medieval_sarsa": ("medieval_norm", 1, (0.0, 0.0, -3.0), 1.0),
 }
 
 
 def load_scene(name):
-    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes.npz"))
-    return {k.split("/")[1]: z[k] for k in z.files if k.startswith(name + "/")}
+    for f in ("scenes.npz", "scene_presets.npz"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", f))
+        s = {k.split("/")[1]: z[k] for k in z.files if k.startswith(name + "/")}
+        if s:
+            return s
+    raise SystemExit("bench.py: no scene %r in tests/golden" % name)
 
 
 class ClockSampler:
