@@ -71,7 +71,7 @@ struct rlpt_ctx {
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
     size_t smem_bytes = 0; int grid = 148;
-    int pipe_split = 1, pipe_tail = 65536, pipe_pre = 1;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
+    int pipe_split = 1, pipe_tail = 32768, pipe_pre = 1;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
     void* d_stage = nullptr; size_t stage_bytes = 0;     // device staging for frame downloads (kept across calls)
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
     double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;

@@ -301,7 +301,6 @@ RLPT_HD int sample_sector_2level(LoadRows load_rows, LoadRow load_row, Load load
 #endif
     for (int i = 0; i < 11; ++i) j += (e[i] <= r) ? 1 : 0;           // first row whose end exceeds r (monotone), capped at the last row
     float c[12]; load_row(j, c);
-    const float prev_end = j > 0 ? e[j - 1] : 0.f;
     if (j == 0 && r <= c[0]) { pdf = RHO * (c[0] / GRID_RHO); return 0; }
     int n = 0;
 #if defined(__CUDA_ARCH__)
@@ -309,13 +308,12 @@ RLPT_HD int sample_sector_2level(LoadRows load_rows, LoadRow load_row, Load load
 #endif
     for (int i = 0; i < 12; ++i) n += (c[i] <= r) ? 1 : 0;           // entries not exceeding r
     if (n < 12) {
-        float hi_v = c[0], lo_v = prev_end;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int i = 1; i < 12; ++i) { if (i == n) { hi_v = c[i]; lo_v = c[i - 1]; } }
+        // the two CDF entries around the chosen cell are re-read by index (the row's line is in L1) rather than selected out
+        // of the 24 registers with a chain of conditional moves
+        const int k = 12 * j + n;
+        const float hi_v = load(k), lo_v = k > 0 ? load(k - 1) : 0.f;
         pdf = RHO * ((hi_v - lo_v) / GRID_RHO);
-        return 12 * j + n;
+        return k;
     }
     return sample_sector(load, r, pdf);                              // r at or past the end of the table: the clamping path
 }
