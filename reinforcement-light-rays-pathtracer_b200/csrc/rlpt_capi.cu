@@ -71,7 +71,7 @@ struct rlpt_ctx {
     unsigned long long* d_stats = nullptr;
     float4 *d_cap_o = nullptr, *d_cap_d = nullptr; int* d_cap_n = nullptr; int cap_max = 0, cap_bounce = -1;
     size_t smem_bytes = 0; int grid = 148;
-    int pipe_split = 1, pipe_tail = 32768, pipe_pre = 1;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
+    int pipe_split = 1, pipe_tail = 32768, pipe_pre = 1; int per_sm_isect = 0, per_sm_shade = 0; size_t resident_smem = (size_t)-1;   // tracing pipeline (DESIGN.md "Wavefront"): split launches, run-to-completion threshold
     void* d_stage = nullptr; size_t stage_bytes = 0;     // device staging for frame downloads (kept across calls)
     uint64_t frames_done = 0;            // global frame counter: sample_base = (frames_done*world + rank)*spp
     double device_seconds = 0.0, frames_rendered = 0.0, launches = 0.0, trace_seconds = 0.0, merge_seconds = 0.0;
@@ -757,6 +757,12 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n;
     p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
     const int grid = (c->n_sm * 8 + NSUB - 1) / NSUB * NSUB;              // a whole number of CTAs per sub-queue
+    // the split kernels run as one resident wave each (whole CTAs per sub-queue, rounded down)
+    if (c->resident_smem != c->smem_bytes || c->per_sm_isect <= 0) { kernels_resident_ctas(c->smem_bytes, &c->per_sm_isect, &c->per_sm_shade); c->resident_smem = c->smem_bytes; }
+    const int per_sm_isect = c->per_sm_isect, per_sm_shade = c->per_sm_shade;
+    int grid_isect = std::max(1, c->n_sm * per_sm_isect / NSUB) * NSUB, grid_shade = std::max(1, c->n_sm * per_sm_shade / NSUB) * NSUB;
+    if (const char* e = getenv("RLPT_GRID_ISECT")) grid_isect = std::max(1, atoi(e)) * NSUB;
+    if (const char* e = getenv("RLPT_GRID_SHADE")) grid_shade = std::max(1, atoi(e)) * NSUB;
     const int split = c->pipe_split, tail_thr = c->pipe_tail;
     const int len = (g.max_bounces + 2) * NSUB * COUNT_STRIDE;
     p.sub_cap = c->sub_cap;
@@ -795,11 +801,11 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
                 cudaStream_t s1 = l.stream;
                 if (b == 0 && c->pipe_pre) { s1 = l.pre; if (l.hit_free_valid) CK(cudaStreamWaitEvent(l.pre, l.hit_free, 0)); }
                 cudaEvent_t e0 = timed ? kev_mark(c, s1) : nullptr;
-                launch_isect(p, dyn, b, grid, c->smem_bytes, s1);
+                launch_isect(p, dyn, b, grid_isect, c->smem_bytes, s1);
                 cudaEvent_t e1 = timed ? kev_mark(c, s1) : nullptr;
                 if (s1 != l.stream) { CK(cudaEventRecord(l.pre_done, l.pre)); CK(cudaStreamWaitEvent(l.stream, l.pre_done, 0)); }
                 cudaEvent_t e2 = (timed && s1 != l.stream) ? kev_mark(c, l.stream) : e1;
-                launch_shade(p, dyn, method, b, grid, l.stream);
+                launch_shade(p, dyn, method, b, grid_shade, l.stream);
                 cudaEvent_t e3 = timed ? kev_mark(c, l.stream) : nullptr;
                 kev_pair(c, e0, e1, 0); kev_pair(c, e2, e3, 1); c->k_all[0] += 1.0; c->k_all[1] += 1.0;
                 launches += 2;

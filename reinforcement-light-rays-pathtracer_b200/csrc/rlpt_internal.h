@@ -129,6 +129,7 @@ void launch_fp32_peak(float* out, int iters, int grid, cudaStream_t s);
 size_t scene_smem_bytes(const SceneDev& sc);
 void upload_cell_cos(const float* cos144);
 int kernels_set_smem_limit(size_t bytes);
+void kernels_resident_ctas(size_t isect_smem, int* isect_per_sm, int* shade_per_sm);
 
 // rlpt_bvh.cu: builds the BVH on the GPU from the tri buffer; returns node count and depth; d_bvh is allocated by the callee
 int bvh_build_gpu(const float4* d_tri, int n_tri, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s);
