@@ -279,6 +279,15 @@ def main():
         hit_flops = flops * (1.0 - tail_flop_share)
         achieved = hit_flops / hit_s / 1e12
         kernel_total = max(st["isect_seconds"] + st["shade_seconds"] + st["tail_seconds"], 1e-12)
+        # measured DRAM traffic per ray from the committed ncu --set full capture (profiles/r1_traffic.json), scaled to this run's average launch
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        rays_per_launch = st["ray_casts"] * (1.0 - tail_flop_share) / max(hit_n, 1)
+        def traffic_of(kernel):
+            return traffic[kernel]["bytes_per_ray"] * rays_per_launch if (split and kernel in traffic and args.workload == "cornell_sarsa") else None
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -296,7 +305,7 @@ def main():
             "roofline": {"kernel": "k_isect (closest hit of every live ray, one launch per bounce)" if split else "k_bounce (closest hit + shade + SARSA step + compaction)",
                          "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": None,
+                         "traffic": traffic_of("k_isect"),
                          "note": "bound is the FP32 pipe (SURVEY 8d; not hbm/tensor): algorithmic flop = ray-triangle tests x 72 + ray-box tests x 18, counted in the kernel; duration = CUDA event pairs "
                                  "around every launch on its stream inside the timed region (launches of the two sample lanes overlap, so a launch's duration includes sharing the SMs)",
                          "peak_source": "FP32 FMA microbenchmark run by this bench on this GPU (MEASURED_PEAKS.json has no FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
@@ -312,10 +321,10 @@ def main():
             shade_bytes = casts * per_ray
             line["roofline_shade"] = {"kernel": "k_shade (nearest volume, TD target, direction sampling, compaction)", "bound": "hbm",
                                       "achieved": shade_bytes / max(st["shade_seconds"], 1e-12) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": shade_bytes / max(st["shade_seconds"], 1e-12) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                      "frac": shade_bytes / max(st["shade_seconds"], 1e-12) / 1e9 / hbm_peak, "traffic": traffic_of("k_shade"), "peak_source": hbm_src,
                                       "bytes_per_ray": per_ray, "avg_launch_ms": st["shade_seconds"] / st["shade_launches"] * 1e3, "launches": st["shade_launches"],
                                       "note": "algorithmic bytes per ray: 60 path state + hit in, 52 x survival out, 16 TD accumulate, 100 CDF (row ends, one row, irradiance), 80 nearest-volume "
-                                              "(one table slot + 4 candidates), 16 x termination frame-buffer add; the tables are L2-resident, so measured DRAM traffic is lower (profiles/)",
+                                              "(one table slot + 4 candidates), 16 x termination frame-buffer add; traffic = DRAM bytes per launch from the ncu capture in profiles/ (lower: the tables stay in L2)",
                                       "share_of_kernel_time": st["shade_seconds"] / kernel_total}
             line["tail"] = {"kernel": "k_bounce run-to-completion (paths left after the planned per-bounce launches)", "seconds": st["tail_seconds"], "launches": st["tail_launches"],
                             "share_of_kernel_time": st["tail_seconds"] / kernel_total}
