@@ -2,11 +2,14 @@
 // Expected-SARSA sampling / TD accumulation, Q merge + CDF rebuild, pixel accumulation.
 //
 // Design (DESIGN.md has the long form):
-//  * one thread per live path per bounce; the scene (SoA float4 triangles, shading records, BVH nodes) is staged in
-//    shared memory by every CTA with vectorised float4 loads; B200 has no RT cores, traversal is FP32-pipe work
-//  * persistent grids sized in multiples of the SM count; the live-path count of each bounce lives in device memory
-//    (counts[b]) so a whole frame is a fixed launch sequence with no host round trip, captured in a CUDA graph
-//  * live rays are compacted every bounce with ballot/popc + one atomicAdd per warp (wavefront-style compaction)
+//  * per bounce two kernels: k_isect (closest hit only, 40 registers, issue-bound on the FP32 pipes) and k_shade (nearest
+//    radiance volume, TD target, direction sampling, compaction: latency-bound, no triangle data); the scene (SoA float4
+//    triangles, parallelogram scan units, BVH nodes) is staged in shared memory by every k_isect CTA with vectorised float4
+//    loads; B200 has no RT cores, traversal is FP32-pipe work
+//  * one resident wave per kernel; the live-path count of each bounce lives in device memory (counts[bounce][sub-queue]),
+//    so a frame is a launch sequence with no host round trip; once few paths are left one run-to-completion launch
+//    (k_bounce<TAIL>) finishes them
+//  * live rays are compacted every bounce with ballot/popc + one atomicAdd per warp into 32 independent sub-queues
 //  * TD targets are accumulated as (sum, count) per (volume, sector) with __match_any_sync warp aggregation
 //  * radiance is accumulated into a float4-per-pixel buffer in HBM with one vector RED per terminated path
 #include "rlpt_internal.h"
