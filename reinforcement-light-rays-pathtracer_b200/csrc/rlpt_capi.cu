@@ -57,7 +57,7 @@ struct rlpt_ctx {
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
     struct Lane {
-        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; float2* d_hit = nullptr;
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; PathQueue q[2]{}; int* d_counts = nullptr; int* d_cursor = nullptr; float2* d_hit = nullptr;
         // the primary closest-hit pass needs nothing of the previous frame's results, only the hit buffer: it runs on `pre`
         // as soon as the previous frame's last k_shade has read that buffer, underneath that frame's tail kernel and merge
         cudaStream_t pre = nullptr; cudaEvent_t hit_free = nullptr, pre_done = nullptr; bool hit_free_valid = false;
@@ -98,7 +98,7 @@ static void free_rmap(rlpt_ctx* c) {
 static void free_lanes(rlpt_ctx* c) {
     for (auto& l : c->lanes) {
         for (int k = 0; k < 2; ++k) { cudaFree(l.q[k].o); cudaFree(l.q[k].d); cudaFree(l.q[k].thr); cudaFree(l.q[k].meta); }
-        cudaFree(l.d_counts); cudaFree(l.d_hit); if (l.h_counts) cudaFreeHost(l.h_counts);
+        cudaFree(l.d_counts); cudaFree(l.d_cursor); cudaFree(l.d_hit); if (l.h_counts) cudaFreeHost(l.h_counts);
         for (auto& e : l.snap_ev) if (e) cudaEventDestroy(e);
         if (l.done) cudaEventDestroy(l.done); if (l.stream) cudaStreamDestroy(l.stream);
         if (l.hit_free) cudaEventDestroy(l.hit_free); if (l.pre_done) cudaEventDestroy(l.pre_done); if (l.pre) cudaStreamDestroy(l.pre);
@@ -709,7 +709,7 @@ static int ensure_frame_buffers(rlpt_ctx* c) {
                 CK(cudaMalloc(&l.q[k].o, sizeof(float4) * slots)); CK(cudaMalloc(&l.q[k].d, sizeof(float4) * slots));
                 CK(cudaMalloc(&l.q[k].thr, sizeof(float4) * slots)); CK(cudaMalloc(&l.q[k].meta, sizeof(uint32_t) * slots));
             }
-            CK(cudaMalloc(&l.d_counts, sizeof(int) * counts_ints)); CK(cudaMalloc(&l.d_hit, sizeof(float2) * slots));
+            CK(cudaMalloc(&l.d_counts, sizeof(int) * counts_ints)); CK(cudaMalloc(&l.d_cursor, sizeof(int) * counts_ints)); CK(cudaMalloc(&l.d_hit, sizeof(float2) * slots));
             CK(cudaHostAlloc(&l.h_counts, sizeof(int) * counts_ints * rlpt_ctx::Lane::SNAPS, cudaHostAllocDefault));
             for (auto& e : l.snap_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
@@ -758,7 +758,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
     const int grid = (c->n_sm * 8 + NSUB - 1) / NSUB * NSUB;              // a whole number of CTAs per sub-queue
     // the split kernels run as one resident wave each (whole CTAs per sub-queue, rounded down)
-    if (c->resident_smem != c->smem_bytes || c->per_sm_isect <= 0) { kernels_resident_ctas(c->smem_bytes, &c->per_sm_isect, &c->per_sm_shade); c->resident_smem = c->smem_bytes; }
+    if (c->resident_smem != c->smem_bytes || c->per_sm_isect <= 0) { kernels_resident_ctas(c->smem_bytes, c->scene.brute, c->scene.smem_tris == c->scene.n_tri && c->scene.smem_nodes == c->scene.n_nodes, &c->per_sm_isect, &c->per_sm_shade); c->resident_smem = c->smem_bytes; }
     const int per_sm_isect = c->per_sm_isect, per_sm_shade = c->per_sm_shade;
     int grid_isect = std::max(1, c->n_sm * per_sm_isect / NSUB) * NSUB, grid_shade = std::max(1, c->n_sm * per_sm_shade / NSUB) * NSUB;
     if (const char* e = getenv("RLPT_GRID_ISECT")) grid_isect = std::max(1, atoi(e)) * NSUB;
@@ -771,7 +771,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
         rlpt_ctx::Lane& l = c->lanes[li];
         CK(cudaStreamWaitEvent(l.stream, c->ev_fork, 0));
         CK(cudaMemsetAsync(l.d_counts, 0, sizeof(int) * len, l.stream));
-        p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts; p.hit = l.d_hit;
+        p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts; p.hit = l.d_hit; p.cursor = l.d_cursor;
         dyn.sample_base = frame_base + (uint32_t)li * (uint32_t)c->lane_spp;
         // launch plan: per-bounce launches up to b_tail, then one run-to-completion launch. b_tail = the first bounce the
         // newest arrived snapshot of this lane entered with at most tail_thr live paths (no snapshot yet: every bounce gets
@@ -800,6 +800,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
             if (split) {
                 cudaStream_t s1 = l.stream;
                 if (b == 0 && c->pipe_pre) { s1 = l.pre; if (l.hit_free_valid) CK(cudaStreamWaitEvent(l.pre, l.hit_free, 0)); }
+                if (b == 0 && !c->scene.brute) CK(cudaMemsetAsync(l.d_cursor, 0, sizeof(int) * len, s1));       // ray-fetch cursors of k_isect_bvh (free once the previous frame's last k_isect is done)
                 cudaEvent_t e0 = timed ? kev_mark(c, s1) : nullptr;
                 launch_isect(p, dyn, b, grid_isect, c->smem_bytes, s1);
                 cudaEvent_t e1 = timed ? kev_mark(c, s1) : nullptr;

@@ -79,6 +79,7 @@ struct FrameParams {
     float2* hit;                    // split pipeline: (t, as_float(primitive id)) per slot of the current queue
     int* counts;                    // live paths entering each bounce: sub-queue k of bounce b at [(b * NSUB + k) * COUNT_STRIDE] (the Neural-Q tracers keep one queue: [b])
     int sub_cap;                    // slots per sub-queue
+    int* cursor;                    // same layout as counts: next unclaimed ray of each (bounce, sub-queue), for k_isect_bvh's dynamic ray fetch
     float4* accum;                  // [W*H] radiance sums (rgb) + sample count in w
     unsigned long long* stats;      // [0] path-length sum, [1] zero-contribution paths, [2] terminated paths, [3] tri tests, [4] box tests, [5] kd-search fallbacks
     float4* capture_o; float4* capture_d; int* capture_n;
@@ -129,7 +130,7 @@ void launch_fp32_peak(float* out, int iters, int grid, cudaStream_t s);
 size_t scene_smem_bytes(const SceneDev& sc);
 void upload_cell_cos(const float* cos144);
 int kernels_set_smem_limit(size_t bytes);
-void kernels_resident_ctas(size_t isect_smem, int* isect_per_sm, int* shade_per_sm);
+void kernels_resident_ctas(size_t isect_smem, int brute, int staged, int* isect_per_sm, int* shade_per_sm);
 
 // rlpt_bvh.cu: builds the BVH on the GPU from the tri buffer; returns node count and depth; d_bvh is allocated by the callee
 int bvh_build_gpu(const float4* d_tri, int n_tri, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s);

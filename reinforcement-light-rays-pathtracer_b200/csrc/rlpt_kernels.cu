@@ -77,6 +77,40 @@ __device__ __forceinline__ void slab(float lox, float loy, float loz, float hix,
     tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
 }
 
+// One node of the ordered BVH traversal: both child boxes, the exact solve of any leaf child that is hit, then the nearer
+// inner child (the other one goes on the stack). Returns false when the traversal is finished.
+template <bool STAGED, bool COUNT>
+__device__ __forceinline__ bool bvh_visit(const SceneView<STAGED>& v, float ox, float oy, float oz, float a0, float a1, float a2, float ix, float iy, float iz,
+                                          float& best_t, int& best_gid, int& cur, int& top, int* stack, unsigned& n_tri, unsigned& n_box) {
+    float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
+    float tn0, tf0, tn1, tf1;
+    slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
+    slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
+    if (COUNT) n_box += 2;
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
+    if (h0 && c0 < 0) {
+        int gid = ~c0; TriRec r = load_tri(v, gid); float t;
+        if (COUNT) n_tri++;
+        if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+        h0 = false;
+    }
+    if (h1 && c1 < 0) {
+        int gid = ~c1; TriRec r = load_tri(v, gid); float t;
+        if (COUNT) n_tri++;
+        if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+        h1 = false;
+    }
+    if (h0 && h1) {
+        bool swap = tn1 < tn0;
+        if (top < 32) stack[top++] = swap ? c0 : c1;
+        cur = swap ? c1 : c0;
+    } else if (h0) cur = c0;
+    else if (h1) cur = c1;
+    else { if (top == 0) return false; cur = stack[--top]; }
+    return true;
+}
+
 // Closest hit of one ray: Ray::closest_intersection (G/rays/ray.cu:16-36). (dx,dy,dz) is the normalised direction;
 // H = SCREEN_HEIGHT. Result: best_t in the reference's units and the primitive id (-1 = NOTHING). The winner is the
 // lexicographic minimum of (t, gid), which is what the reference's scan order with strict < produces.
@@ -189,34 +223,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
     }
     const float ix = 1.f / sdx, iy = 1.f / sdy, iz = 1.f / sdz;
     int stack[32]; int top = 0; int cur = 0;
-    while (true) {
-        float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
-        float tn0, tf0, tn1, tf1;
-        slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
-        slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
-        if (COUNT) n_box += 2;
-        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
-        if (h0 && c0 < 0) {
-            int gid = ~c0; TriRec r = load_tri(v, gid); float t;
-            if (COUNT) n_tri++;
-            if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
-            h0 = false;
-        }
-        if (h1 && c1 < 0) {
-            int gid = ~c1; TriRec r = load_tri(v, gid); float t;
-            if (COUNT) n_tri++;
-            if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
-            h1 = false;
-        }
-        if (h0 && h1) {
-            bool swap = tn1 < tn0;
-            if (top < 32) stack[top++] = swap ? c0 : c1;
-            cur = swap ? c1 : c0;
-        } else if (h0) cur = c0;
-        else if (h1) cur = c1;
-        else { if (top == 0) break; cur = stack[--top]; }
-    }
+    while (bvh_visit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, ix, iy, iz, best_t, best_gid, cur, top, stack, n_tri, n_box)) {}
 }
 
 template <bool STAGED, bool COUNT>
@@ -557,6 +564,62 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
     flush_work_counters(p, n_tri, n_box);
 }
 
+// k_isect for scenes traversed through the BVH. Traversal lengths differ wildly between the rays of a warp (a ray that
+// leaves the mesh is done after a few nodes, one that grazes it visits hundreds): with one ray per thread per pass the
+// bounce-1 launch of Medieval_House ran with 5 of 32 lanes active. Here a lane whose ray is finished takes the next ray of
+// the sub-queue (one atomicAdd on the sub-queue's cursor per refill, for all idle lanes of the warp at once) while its
+// neighbours keep traversing; the warp checks for idle lanes every BVH_BATCH node visits.
+constexpr int BVH_BATCH = 8, BVH_REFILL = 8;
+template <bool STAGED, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
+    if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
+    SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
+    const PathQueue qi = p.q[bounce & 1];
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    int* cursor = p.cursor + (bounce * NSUB + (int)(blockIdx.x % NSUB)) * COUNT_STRIDE;
+    unsigned n_tri = 0, n_box = 0;
+    const float H = (float)p.height;
+    bool have = false, exhausted = false;
+    int i = 0, cur = 0, top = 0, best_gid = -1; float best_t = T_MISS;
+    float ox = 0, oy = 0, oz = 0, a0 = 0, a1 = 0, a2 = 0, ix = 0, iy = 0, iz = 0;
+    int stack[32];
+    while (true) {
+        const unsigned idle = __ballot_sync(full, !have);
+        if (!exhausted && (idle == full || __popc(idle) >= BVH_REFILL)) {
+            const int leader = __ffs(idle) - 1; int base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
+            base = __shfl_sync(full, base, leader);
+            exhausted = base + __popc(idle) >= sq.n;
+            if (!have) {
+                i = base + __popc(idle & lanemask_lt());
+                if (i < sq.n) {
+                    float dx, dy, dz;
+                    if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
+                    else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
+                    if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
+                        int slot = atomicAdd(p.capture_n, 1);
+                        if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+                    }
+                    const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
+                    a0 = RLPT_SUB(0.f, sdx); a1 = RLPT_SUB(0.f, sdy); a2 = RLPT_SUB(0.f, sdz);
+                    ix = 1.f / sdx; iy = 1.f / sdy; iz = 1.f / sdz;
+                    best_t = T_MISS; best_gid = -1; cur = 0; top = 0; have = true;
+                }
+            }
+        }
+        if (!__any_sync(full, have)) break;
+#pragma unroll 1
+        for (int step = 0; step < BVH_BATCH; ++step) {
+            if (have && !bvh_visit<STAGED, true>(v, ox, oy, oz, a0, a1, a2, ix, iy, iz, best_t, best_gid, cur, top, stack, n_tri, n_box)) {
+                __stcs(p.hit + sq.base + i, make_float2(best_t, __int_as_float(best_gid)));
+                have = false;
+            }
+        }
+    }
+    flush_work_counters(p, n_tri, n_box);
+}
+
 // Split, second half: shading records come through the read-only path (2.4 KB for Cornell: L1-resident), no staging
 template <bool SARSA, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
@@ -599,6 +662,11 @@ void launch_tail(const FrameParams& p, const FrameDyn& dyn, int method, int boun
 }
 void launch_isect(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     const bool staged = scene_staged(p.scene);
+    if (!p.scene.brute && p.cursor) {
+        if (bounce == 0) { if (staged) k_isect_bvh<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_isect_bvh<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
+        else { if (staged) k_isect_bvh<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_isect_bvh<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
+        return;
+    }
     if (bounce == 0) { if (staged) k_isect<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_isect<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
     else { if (staged) k_isect<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_isect<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
 }
@@ -874,9 +942,13 @@ void launch_add_scalar(float* dst, const float* src, cudaStream_t s) { k_add_sca
 
 // CTAs of k_isect / k_shade that are resident per SM (occupancy API): the split pipeline launches exactly one wave of each,
 // so no CTA starts when most of the grid has already finished (+4.8 % over 8 CTAs per SM for both)
-void kernels_resident_ctas(size_t isect_smem, int* isect_per_sm, int* shade_per_sm) {
+void kernels_resident_ctas(size_t isect_smem, int brute, int staged, int* isect_per_sm, int* shade_per_sm) {
     int a = 0, b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect<true, false>, BLOCK, isect_smem) != cudaSuccess) a = 0;
+    cudaError_t e;
+    if (brute) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect<true, false>, BLOCK, isect_smem);
+    else if (staged) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<true, false>, BLOCK, isect_smem);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<false, false>, BLOCK, isect_smem);
+    if (e != cudaSuccess) a = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<true, false>, BLOCK, 0) != cudaSuccess) b = 0;
     (void)cudaGetLastError();
     *isect_per_sm = a > 0 ? a : 6; *shade_per_sm = b > 0 ? b : 4;
@@ -889,6 +961,7 @@ int kernels_set_smem_limit(size_t bytes) {
     RLPT_SET((k_bounce<false, true, true, false>)); RLPT_SET((k_bounce<false, true, false, false>)); RLPT_SET((k_bounce<false, false, true, false>)); RLPT_SET((k_bounce<false, false, false, false>));
     RLPT_SET((k_bounce<true, true, false, true>)); RLPT_SET((k_bounce<true, false, false, true>)); RLPT_SET((k_bounce<false, true, false, true>)); RLPT_SET((k_bounce<false, false, false, true>));
     RLPT_SET((k_isect<true, true>)); RLPT_SET((k_isect<true, false>)); RLPT_SET((k_isect<false, true>)); RLPT_SET((k_isect<false, false>));
+    RLPT_SET((k_isect_bvh<true, true>)); RLPT_SET((k_isect_bvh<true, false>)); RLPT_SET((k_isect_bvh<false, true>)); RLPT_SET((k_isect_bvh<false, false>));
     RLPT_SET((k_nqt_trace<true>)); RLPT_SET((k_nqt_trace<false>));
     RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));

@@ -209,6 +209,28 @@ def test_default_render_matches_oracle_same_paths(ctx, oracle, golden_scenes):
     assert abs(st["zero_contribution_paths"] - ost["zero_contribution"]) <= 2e-3 * ost["paths"]
 
 
+def test_default_render_through_the_bvh(ctx, oracle, golden_scenes):
+    """archway (102 primitives) is traversed through the BVH by k_isect_bvh (lanes refill from the sub-queue as their rays
+    finish). Closest hits are bit-exact, so the image must equal the one rendered with the linear scan up to the order of the
+    frame-buffer additions. Against the oracle only most pixels agree: with a mean path length of 43 bounces the last-bit
+    differences between the device's and the host's sincos send ~0.3 % of the paths elsewhere (the linear scan shows the
+    identical 97 pixels), so that comparison is on the image mean and on 96 % of the pixels."""
+    import rlpt
+    s = golden_scenes["archway"]
+    img, oimg, st, ost = _render_pair(ctx, oracle, s, 0, 64, 64, 8, 2, 80, (-1.0, 0.2, -0.99))
+    assert st["box_tests"] > 0 and st["paths"] == ost["paths"] == 64 * 64 * 16
+    _assert_images_close(img, oimg, frac=0.96)
+    assert abs(st["path_length_sum"] - ost["total_path_length"]) <= 2e-3 * ost["total_path_length"]
+    lin = rlpt.Context(0, width=64, height=64, spp=8, max_bounces=80, traversal=rlpt.TRAVERSAL_BRUTE)
+    try:
+        load_scene(lin, s); lin.camera_set((-1.0, 0.2, -0.99)); lin.render_default(2)
+        ref = lin.frame_download(); lst = lin.stats()
+    finally:
+        lin.close()
+    assert lst["box_tests"] == 0 and lst["path_length_sum"] == st["path_length_sum"]
+    assert np.allclose(img, ref, rtol=1e-5, atol=1e-7)
+
+
 def test_sarsa_first_frame_accumulators_match_oracle(ctx, oracle, golden_scenes):
     """one training iteration from the initial table: same paths => same (volume, sector) visit counts"""
     s = golden_scenes["cornell"]
