@@ -89,17 +89,16 @@ __device__ __forceinline__ bool bvh_visit(const SceneView<STAGED>& v, float ox, 
     if (COUNT) n_box += 2;
     int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
     bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
-    if (h0 && c0 < 0) {
-        int gid = ~c0; TriRec r = load_tri(v, gid); float t;
+    // leaf children that are hit: one instance of the exact solve serves both (lanes whose first and lanes whose second child
+    // is the leaf run it together)
+    int pend0 = (h0 && c0 < 0) ? ~c0 : -1, pend1 = (h1 && c1 < 0) ? ~c1 : -1;
+    if (pend0 < 0) { pend0 = pend1; pend1 = -1; }
+    h0 = h0 && c0 >= 0; h1 = h1 && c1 >= 0;
+    while (pend0 >= 0) {
+        const int gid = pend0; pend0 = pend1; pend1 = -1;
+        TriRec r = load_tri(v, gid); float t;
         if (COUNT) n_tri++;
         if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
-        h0 = false;
-    }
-    if (h1 && c1 < 0) {
-        int gid = ~c1; TriRec r = load_tri(v, gid); float t;
-        if (COUNT) n_tri++;
-        if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
-        h1 = false;
     }
     if (h0 && h1) {
         bool swap = tn1 < tn0;
