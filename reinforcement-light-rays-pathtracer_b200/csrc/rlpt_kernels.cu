@@ -568,7 +568,13 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 // bounce-1 launch of Medieval_House ran with 5 of 32 lanes active. Here a lane whose ray is finished takes the next ray of
 // the sub-queue (one atomicAdd on the sub-queue's cursor per refill, for all idle lanes of the warp at once) while its
 // neighbours keep traversing; the warp checks for idle lanes every BVH_BATCH node visits.
-constexpr int BVH_BATCH = 8, BVH_REFILL = 8;
+#ifndef RLPT_BVH_BATCH
+#define RLPT_BVH_BATCH 8
+#endif
+#ifndef RLPT_BVH_REFILL
+#define RLPT_BVH_REFILL 8
+#endif
+constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
 template <bool STAGED, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
