@@ -147,6 +147,9 @@ int rlpt_sarsa_trace(rlpt_ctx* ctx);
 int rlpt_sarsa_merge(rlpt_ctx* ctx);
 /* render with the learned distributions frozen (no TD accumulation, no merge): train once, render many */
 int rlpt_render_sarsa_frozen(rlpt_ctx* ctx, int frames);
+/* replaces: the VORONOI debug view (G/main.cu:413-470, G/path_tracing/voronoi_trace.cu:4-45): one camera sample per pixel,
+ * surface hits painted with the colour of their nearest radiance volume, everything else white. Sets the frame buffer. */
+int rlpt_render_voronoi(rlpt_ctx* ctx);
 
 /* replaces: cudaMemset(device_buffer, 0, ...) (G/main.cu:241,359) -- and resets the sample counter */
 int rlpt_frame_reset(rlpt_ctx* ctx);
@@ -210,6 +213,10 @@ int rlpt_dqn_forward(rlpt_ctx* ctx, const float* pos3, int n, float* q);
  * backward, AdamTrainer::update (DyNet defaults). apply_update = 0 computes loss and gradients only. loss may be NULL. */
 int rlpt_dqn_train_batch(rlpt_ctx* ctx, const float* pos3, const uint32_t* actions, const float* targets, int n, int apply_update, float* loss);
 /* gradients of the last rlpt_dqn_train_batch in parameter order (tests) */
+/* replaces: the training step of the offline trainer (NN_Q_Value_Trainer/Source/main.cu:67-135): fit the network to saved Q
+ * tables. targets144 = n*144 floats (ray-major); loss = sum over the batch of the squared distance over all 144 outputs; one
+ * Adam step when apply_update != 0. */
+int rlpt_dqn_train_supervised(rlpt_ctx* ctx, const float* pos3, const float* targets144, int n, int apply_update, float* loss);
 int rlpt_dqn_get_grads(rlpt_ctx* ctx, float* grads, int count);
 
 /* replaces: PretrainedPathtracer(frames, batch, screen, scene, camera, ...) (G/deep_learning/pre_trained_pathtracer.cu:10-491):

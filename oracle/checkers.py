@@ -364,7 +364,7 @@ def bf16_round(a):
     return u.astype(np.uint32).view(np.float32).reshape(np.shape(a))
 
 
-def dqn_loss_and_grads_numpy(params, vertices, pos, actions, targets, bf16=False):
+def dqn_loss_and_grads_numpy(params, vertices, pos, actions, targets, bf16=False, all_outputs=False):
     """G/deep_learning/neural_q_pathtracer.cu:476-512 in float64 numpy: loss = sum_b (target_b - Q(s_b)[a_b])^2 and its
     gradient w.r.t. every parameter (flat, parameter order). ReLU follows every layer, the output included.
     bf16=True rounds exactly what the tensor-core path rounds (weights of layers 2-4, hidden activations, deltas, the query
@@ -381,14 +381,23 @@ def dqn_loss_and_grads_numpy(params, vertices, pos, actions, targets, bf16=False
             pre = pre.astype(np.float32).astype(np.float64)
         h = np.maximum(pre, 0.0)
         hs.append(r(h).astype(np.float64) if l < 3 else h.astype(np.float32).astype(np.float64) if bf16 else h)
-    q = hs[-1]; n = len(pos); idx = np.arange(n); a = np.asarray(actions, np.int64); t = np.asarray(targets, np.float64)
-    qa = q[idx, a]
-    loss = float(((t - qa) ** 2).sum())
-    g = 2.0 * (qa - t) * (qa > 0)
+    q = hs[-1]; n = len(pos); idx = np.arange(n); t = np.asarray(targets, np.float64)
     W4 = layers[3][0]
-    gw4 = np.zeros_like(W4); gb4 = np.zeros(W4.shape[0])
-    np.add.at(gw4, a, g[:, None] * hs[3] * (hs[3] > 0)); np.add.at(gb4, a, g)
-    d3 = r(g[:, None] * W4[a] * (hs[3] > 0)).astype(np.float64)
+    if all_outputs:
+        # NN_Q_Value_Trainer/Source/main.cu:110-117: sum_batches squared_distance(targets [144], Q(s)); targets is [n][144]
+        t = t.reshape(n, -1)
+        loss = float(((t - q) ** 2).sum())
+        G = 2.0 * (q - t) * (q > 0)
+        gw4, gb4 = G.T @ hs[3], G.sum(0)
+        d3 = r((G @ W4) * (hs[3] > 0)).astype(np.float64)
+    else:
+        a = np.asarray(actions, np.int64)
+        qa = q[idx, a]
+        loss = float(((t - qa) ** 2).sum())
+        g = 2.0 * (qa - t) * (qa > 0)
+        gw4 = np.zeros_like(W4); gb4 = np.zeros(W4.shape[0])
+        np.add.at(gw4, a, g[:, None] * hs[3] * (hs[3] > 0)); np.add.at(gb4, a, g)
+        d3 = r(g[:, None] * W4[a] * (hs[3] > 0)).astype(np.float64)
     d2 = r((d3 @ r(layers[2][0]).astype(np.float64)) * (hs[2] > 0)).astype(np.float64)
     d1 = r((d2 @ r(layers[1][0]).astype(np.float64)) * (hs[1] > 0)).astype(np.float64)
     gw3, gb3 = d3.T @ hs[2], d3.sum(0)

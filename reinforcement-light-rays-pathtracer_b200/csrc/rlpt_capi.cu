@@ -664,6 +664,28 @@ int rlpt_dqn_train_batch(rlpt_ctx* c, const float* pos3, const uint32_t* actions
     if (loss) *loss = h_loss;
     return RLPT_OK;
 }
+// replaces: the training step of NN_Q_Value_Trainer/Source/main.cu:67-135 (fit the network to saved Q tables: squared distance
+// over all 144 outputs, summed over the batch, Adam)
+int rlpt_dqn_train_supervised(rlpt_ctx* c, const float* pos3, const float* targets144, int n, int apply_update, float* loss) {
+    if (!c || !c->dq.ready) return fail(RLPT_ERR_ARG, "rlpt_dqn_train_supervised: no network");
+    if (n <= 0 || !pos3 || !targets144) return fail(RLPT_ERR_ARG, "rlpt_dqn_train_supervised: bad arguments");
+    CK(cudaSetDevice(c->device));
+    std::vector<float4> h_pos(n); for (int i = 0; i < n; ++i) h_pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 0.f);
+    float4* d_pos = nullptr; float* d_tgt = nullptr;
+    CK(cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); CK(cudaMalloc(&d_tgt, 4 * (size_t)n * DQ_OUT));
+    CK(cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_tgt, targets144, 4 * (size_t)n * DQ_OUT, cudaMemcpyHostToDevice, c->stream));
+    const bool dist = c->allreduce && c->cfg.world_size > 1;
+    int rc = dqn_train_batch(c->dq, c->dq_train, d_pos, nullptr, d_tgt, n, apply_update != 0, dist ? dqn_hook : nullptr, c, c->stream, true);
+    float h_loss = 0.f;
+    if (!rc) { CK(cudaMemcpyAsync(&h_loss, c->dq_train.scalars, 4, cudaMemcpyDeviceToHost, c->stream)); }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_pos); cudaFree(d_tgt);
+    if (rc) return fail(rc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, rc == -2 ? "gradient all-reduce hook failed" : std::string("rlpt_dqn_train_supervised: ") + cudaGetErrorString((cudaError_t)rc));
+    if (e != cudaSuccess) return fail(RLPT_ERR_CUDA, std::string("rlpt_dqn_train_supervised: ") + cudaGetErrorString(e));
+    if (loss) *loss = h_loss;
+    return RLPT_OK;
+}
 int rlpt_dqn_get_grads(rlpt_ctx* c, float* grads, int count) {
     if (!c || !c->dq.ready || !c->dq_train.gw[0] || !grads) return fail(RLPT_ERR_ARG, "rlpt_dqn_get_grads: no gradients (call rlpt_dqn_train_batch first)");
     CK(cudaSetDevice(c->device));
@@ -904,6 +926,24 @@ int rlpt_render_sarsa(rlpt_ctx* c, int frames) {
         rc = phase_mark(c); if (rc) return rc;
     }
     return timed_end(c, frames);
+}
+// replaces: the VORONOI method of main (G/main.cu:413-470) -> draw_voronoi_trace (G/path_tracing/voronoi_trace.cu:4-45)
+int rlpt_render_voronoi(rlpt_ctx* c) {
+    if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_voronoi: needs a scene and a radiance map");
+    CK(cudaSetDevice(c->device));
+    int rc = ensure_frame_buffers(c); if (rc) return rc;
+    const rlpt_config& g = c->cfg;
+    FrameDyn dyn{};
+    dyn.sample_base = (uint32_t)c->frames_done; dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
+    dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
+    dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
+    FrameParams p{};
+    p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats;
+    p.width = g.width; p.height = g.height; p.spp = 1; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
+    launch_voronoi(p, dyn, c->n_sm * 8, c->smem_bytes, c->stream);
+    c->launches += 1; c->frames_done++;
+    CK(cudaGetLastError());
+    return RLPT_OK;
 }
 int rlpt_render_sarsa_frozen(rlpt_ctx* c, int frames) {
     if (!c || !c->have_scene || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_render_sarsa_frozen: needs a scene and a radiance map");

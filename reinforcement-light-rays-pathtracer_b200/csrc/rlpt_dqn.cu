@@ -480,6 +480,36 @@ __global__ void k_delta3(const float* __restrict__ q, const uint32_t* __restrict
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
     if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(scalars, loss);
 }
+// Supervised variant (NN_Q_Value_Trainer/Source/main.cu:110-117: loss = sum_batches squared_distance(targets, Q(s)) over ALL
+// 144 outputs): the output-layer gradient is dense. g[i][a] = 2 (q_a - y_a) relu'(q_a); one thread per (ray, action).
+__global__ void k_g4_full(const float* __restrict__ q, const float* __restrict__ targets, int n, int S, float* __restrict__ g4, float* __restrict__ scalars) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    float loss = 0.f, g = 0.f;
+    if (i < n) { const float qa = q[(size_t)a * S + i], diff = qa - targets[(size_t)i * DQ_OUT + a]; loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f; }
+    if (i < S) g4[(size_t)a * S + i] = g;
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(scalars, loss);
+}
+// delta3[i][j] = relu'(h3[i][j]) sum_a g[i][a] W4[a][j]; one thread per (ray, hidden unit)
+__global__ void k_delta3_full(const float* __restrict__ g4, const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, int n, int S,
+                              __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= S) return;
+    float d = 0.f;
+    if (i < n && j < DQ_H3 && __bfloat162float(h3t[(size_t)j * S + i]) > 0.f)
+        for (int a = 0; a < DQ_OUT; ++a) d += g4[(size_t)a * S + i] * __ldg(w4 + (size_t)a * DQ_H3 + j);
+    const __nv_bfloat16 db = __float2bfloat16_rn(d);
+    d3[(size_t)i * DQ_K4 + j] = db; d3t[(size_t)j * S + i] = db;
+}
+// dW4[a][j] = sum_i g[i][a] h3[i][j], db4[a] = sum_i g[i][a]; one warp per (a, j), j == DQ_H3 is the bias
+__global__ void k_dw4_full(const float* __restrict__ g4, const __nv_bfloat16* __restrict__ h3t, int n, int S, float* __restrict__ gw4, float* __restrict__ gb4) {
+    const int a = blockIdx.y, j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j > DQ_H3) return;
+    float acc = 0.f;
+    for (int i = lane; i < n; i += 32) acc += g4[(size_t)a * S + i] * (j < DQ_H3 ? __bfloat162float(h3t[(size_t)j * S + i]) : 1.f);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) { if (j < DQ_H3) gw4[(size_t)a * DQ_H3 + j] = acc; else gb4[a] = acc; }
+}
 // hidden-layer delta: d = pre * relu'(h); written ray-major (next data GEMM's A) and feature-major (weight-gradient GEMM's A)
 __global__ void k_delta_hidden(const float* __restrict__ pre, int ld_pre, const __nv_bfloat16* __restrict__ ht, int S, int n_feat, int k_pad,
                                __nv_bfloat16* __restrict__ d_ray, __nv_bfloat16* __restrict__ d_feat) {
@@ -530,7 +560,7 @@ __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float
 void dqn_train_free(DqnTrain& t) {
     for (int l = 0; l < 4; ++l) { cudaFree(t.gw[l]); cudaFree(t.gb[l]); cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
-    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars);
+    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
     t = DqnTrain{};
 }
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
@@ -565,7 +595,7 @@ static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
 }
 
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s) {
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs) {
     if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
     int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
@@ -580,7 +610,13 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     rc = dqn_forward(d, fp, s); if (rc) return rc;
     k_train_prepare<<<(S + 127) / 128, 128, 0, s>>>(pos, n, S, t.xt, t.h1t, t.h2t, t.h3t);
     // backward: data path
-    k_delta3<<<(S + 127) / 128, 128, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+    if (all_outputs) {            // targets: [n][144]
+        if (S > t.g4_capacity) { cudaFree(t.g4); t.g4 = nullptr; t.g4_capacity = 0; DQ_CK(cudaMalloc(&t.g4, 4 * (size_t)DQ_OUT * S)); t.g4_capacity = S; }
+        k_g4_full<<<dim3((S + 127) / 128, DQ_OUT), 128, 0, s>>>(t.q, targets, n, S, t.g4, t.scalars);
+        k_delta3_full<<<dim3((S + 127) / 128, DQ_K4), 128, 0, s>>>(t.g4, d.w[3], t.h3t, n, S, t.d3, t.d3t);
+        k_dw4_full<<<dim3((DQ_H3 + 1 + 7) / 8, DQ_OUT), 256, 0, s>>>(t.g4, t.h3t, n, S, t.gw[3], t.gb[3]);
+    } else
+        k_delta3<<<(S + 127) / 128, 128, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
     rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, DQ_N2, S, DQ_N2, DQ_K4, 1, s); if (rc) return rc;                  // [S x 208] x [304 x 208]^T
     k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, DQ_N2, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
     rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, DQ_N3, S, DQ_N3, DQ_K3, 1, s); if (rc) return rc;                  // [S x 304] x [208 x 304]^T

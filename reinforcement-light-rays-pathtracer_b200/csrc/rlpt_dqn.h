@@ -62,6 +62,7 @@ struct DqnTrain {
     float *p2 = nullptr, *p1 = nullptr;             // pre-activation deltas [S][304], [S][208] (fp32 GEMM outputs)
     float* q = nullptr;                             // [144][S] predictions of the batch
     float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm
+    float* g4 = nullptr; int g4_capacity = 0;       // supervised step: dense output-layer gradient [144][S]
     unsigned long long step = 0;
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
 };
@@ -72,7 +73,7 @@ void dqn_train_free(DqnTrain& t);
 // all-reduce hook (may be null): sums the gradient buffers across ranks before the update.
 typedef int (*dqn_allreduce_fn)(void* d_buf, uint64_t count, int dtype, void* cuda_stream, void* user);
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s);
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs = false);   // all_outputs: targets is [n][144], the supervised loss over every output (actions unused)
 int dqn_alloc(DqnDev& d, int k_in);
 void dqn_free(DqnDev& d);
 int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s);       // copies parameters, derives operands

@@ -124,6 +124,7 @@ void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float th
 void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
                         unsigned long long* counters, size_t smem, cudaStream_t s);
 void launch_find_closest(const RadianceDev& rm, const SceneDev& sc, const float* pos, const float* nrm, int n, int* out, cudaStream_t s);
+void launch_voronoi(const FrameParams& p, const FrameDyn& dyn, int grid, size_t smem, cudaStream_t s);
 void launch_frame_mean(const float4* accum, float* rgb, int n, cudaStream_t s);
 void launch_pack_argb(const float4* accum, uint32_t* argb, int width, int height, cudaStream_t s);
 void launch_fp32_peak(float* out, int iters, int grid, cudaStream_t s);

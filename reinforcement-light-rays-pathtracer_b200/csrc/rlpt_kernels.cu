@@ -650,6 +650,35 @@ __global__ void __launch_bounds__(BLOCK, RLPT_SHADE_MINBLOCKS) k_shade(const __g
     flush_path_stats(p, st_len, st_zero, st_term, n_kd);
 }
 
+// Debug view of the radiance map: draw_voronoi_trace (G/path_tracing/voronoi_trace.cu:4-45): one jittered camera ray per
+// pixel; a surface hit is painted with the colour of its nearest radiance volume, anything else white. The reference gives
+// every volume a host rand() colour (radiance_volume.cu:311-318); here the colour is Philox(seed, volume) -- arbitrary in
+// both. The frame buffer is SET (weight 1), not accumulated.
+template <bool STAGED>
+__global__ void __launch_bounds__(BLOCK) k_voronoi(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn) {
+    SceneView<STAGED> v = stage_scene<STAGED, true>(p.scene);
+    const int n = p.width * p.height;
+    unsigned n_tri = 0, n_box = 0, n_kd = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        PathState s; primary_state(p, dyn, i, s);                       // p.spp == 1 here: path index = pixel
+        float t, sdx, sdy, sdz; int gid;
+        closest_hit<STAGED, true>(v, s.ox, s.oy, s.oz, s.dx, s.dy, s.dz, (float)p.height, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        float4 c = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gid >= 0 && gid < v.n_surf) {
+            const float hx = RLPT_FMA(sdx, t, s.ox), hy = RLPT_FMA(sdy, t, s.oy), hz = RLPT_FMA(sdz, t, s.oz);
+            const int nv = find_volume(p.rm, hx, hy, hz, __float_as_int(v.shade(4 * gid + 1).w), n_kd);
+            float u0, u1, u2, u3; draw4(p.seed, (uint32_t)nv, 0x766f726fu, 0u, 7u, u0, u1, u2, u3);
+            c = make_float4(u0, u1, u2, 1.f);
+        }
+        p.accum[i] = c;
+    }
+}
+void launch_voronoi(const FrameParams& p, const FrameDyn& dyn, int grid, size_t smem, cudaStream_t s) {
+    const SceneDev& sc = p.scene;
+    if (sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes) k_voronoi<true><<<grid, BLOCK, smem, s>>>(p, dyn);
+    else k_voronoi<false><<<grid, BLOCK, smem, s>>>(p, dyn);
+}
+
 static bool scene_staged(const SceneDev& sc) { return sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes; }
 template <bool SARSA, bool PRIMARY, bool TAIL>
 static void launch_bounce_t(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
@@ -969,6 +998,7 @@ int kernels_set_smem_limit(size_t bytes) {
     RLPT_SET((k_isect_bvh<true, true>)); RLPT_SET((k_isect_bvh<true, false>)); RLPT_SET((k_isect_bvh<false, true>)); RLPT_SET((k_isect_bvh<false, false>));
     RLPT_SET((k_nqt_trace<true>)); RLPT_SET((k_nqt_trace<false>));
     RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
+    RLPT_SET((k_voronoi<true>)); RLPT_SET((k_voronoi<false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));
 #undef RLPT_SET
     return (int)e;

@@ -46,7 +46,7 @@ SYMBOLS = [
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
     "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
-    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_get_grads", "rlpt_render_neuralq", "rlpt_neuralq_last_loss",
+    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_train_supervised", "rlpt_render_voronoi", "rlpt_dqn_get_grads", "rlpt_render_neuralq", "rlpt_neuralq_last_loss",
 ]
 
 _lib = None
@@ -235,6 +235,9 @@ class Context:
         self._ck(self.L.rlpt_neuralq_last_loss(self.h, ctypes.byref(loss)))
         return loss.value
 
+    def render_voronoi(self):
+        self._ck(self.L.rlpt_render_voronoi(self.h))
+
     def render_sarsa_frozen(self, frames=1):
         self._ck(self.L.rlpt_render_sarsa_frozen(self.h, int(frames)))
 
@@ -319,6 +322,12 @@ class Context:
         loss = ctypes.c_float()
         self._ck(self.L.rlpt_dqn_train_batch(self.h, _p(pos), _p(a), _p(t), len(pos), int(bool(apply_update)), ctypes.byref(loss)))
         return loss.value
+
+    def dqn_train_supervised(self, pos, targets144, apply_update=True):
+        pos = _f32(pos).reshape(-1, 3); t = _f32(targets144).reshape(len(pos), 144)
+        loss = ctypes.c_float()
+        self._ck(self.L.rlpt_dqn_train_supervised(self.h, _p(pos), _p(t), len(pos), int(apply_update), ctypes.byref(loss)))
+        return float(loss.value)
 
     def dqn_get_grads(self):
         n, _ = self.dqn_param_count()

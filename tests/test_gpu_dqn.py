@@ -151,6 +151,37 @@ def test_training_step_gradients_match_numpy(ctx, golden_scenes, dqn_golden):
     assert np.array_equal(ctx.dqn_get_params(), dqn_golden["params"])              # apply_update=False left the weights alone
 
 
+def test_supervised_step_matches_numpy_and_fits_a_q_table(ctx, golden_scenes, dqn_golden):
+    """The offline trainer's step (NN_Q_Value_Trainer/Source/main.cu:67-135): squared distance over all 144 outputs. Gradients
+    against the numpy restatement (same bars as the TD step), then a few hundred Adam steps on a fixed batch of 128 (the
+    reference's batch size) must fit the targets."""
+    from checkers import dqn_loss_and_grads_numpy
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s)
+    vertices = np.concatenate([s["sv"].ravel(), s["lv"].ravel()])
+    ctx.dqn_set_params(dqn_golden["params"])
+    rs = np.random.RandomState(3)
+    for n in (128, 1000):
+        pos = dqn_golden["pos"][rs.randint(0, len(dqn_golden["pos"]), n)]
+        targets = (rs.rand(n, 144) * 800).astype(np.float32)
+        loss = ctx.dqn_train_supervised(pos, targets, apply_update=False)
+        g = ctx.dqn_get_grads()
+        b_loss, b_g = dqn_loss_and_grads_numpy(dqn_golden["params"], vertices, pos, None, targets, bf16=True, all_outputs=True)
+        assert abs(loss - b_loss) <= 5e-3 * b_loss, (loss, b_loss)
+        rep = _tensor_report(g, b_g, 342)
+        assert all(c >= 0.9995 and r <= 2e-2 for c, r in rep), rep
+        ref_loss, ref_g = dqn_loss_and_grads_numpy(dqn_golden["params"], vertices, pos, None, targets, all_outputs=True)
+        rep = _tensor_report(g, ref_g, 342)
+        assert all(c >= 0.99 and r <= 0.15 for c, r in rep), rep
+    assert np.array_equal(ctx.dqn_get_params(), dqn_golden["params"])
+    # fit: targets = a normalised "Q table" per position (what save_q_vals_to_file holds), batch 128
+    ctx.dqn_init(seed=9)
+    pos = dqn_golden["pos"][:128]
+    targets = (1.0 + np.sin(np.arange(144)[None, :] * 0.2 + pos[:, :1] * 3.0)).astype(np.float32)
+    losses = [ctx.dqn_train_supervised(pos, targets) for _ in range(300)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.1 * losses[0], (losses[0], losses[-1])
+
+
 def test_adam_training_tracks_numpy_and_reduces_loss(ctx, golden_scenes, dqn_golden):
     from checkers import AdamNumpy, dqn_loss_and_grads_numpy
     s = golden_scenes["cornell"]

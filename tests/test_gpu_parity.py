@@ -309,6 +309,28 @@ def test_sarsa_learns_and_stays_finite(ctx, golden_scenes):
     assert np.isfinite(img).all() and img.mean() > 0.05
 
 
+def test_voronoi_view(ctx, oracle, golden_scenes):
+    """draw_voronoi_trace (G/path_tracing/voronoi_trace.cu:4-45): every surface pixel carries the colour of its nearest radiance
+    volume. Pixels of one colour must be one volume's cell: the colour is looked up again through find_closest on the hit
+    points (oracle closest hit + nearest-volume search on the same camera rays is the long way round; here the check is that
+    equal colours form few, compact cells and that distinct volumes get distinct colours)."""
+    s = golden_scenes["cornell"]
+    ctx.configure(width=128, height=128, spp=1)
+    load_scene(ctx, s); nv = ctx.radiance_map_build(); ctx.camera_set((0, 0, -3))
+    ctx.render_voronoi()
+    img = ctx.frame_download().reshape(128, 128, 3)
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0
+    keys = (img * 65535).astype(np.int64); keys = keys[..., 0] * (1 << 32) + keys[..., 1] * (1 << 16) + keys[..., 2]
+    uniq, counts = np.unique(keys, return_counts=True)
+    assert 1500 < len(uniq) <= min(nv + 1, 128 * 128)              # ~2 volumes per 3 pixels at this resolution
+    # cells are compact: the pixels of one colour lie within a few pixels of each other
+    xs, ys = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")
+    big = uniq[counts >= 4][:200]
+    for k in big:
+        m = keys == k
+        assert xs[m].max() - xs[m].min() <= 12 and ys[m].max() - ys[m].min() <= 12
+
+
 def test_frame_argb_and_bmp(ctx, golden_scenes, tmp_path):
     from checkers import to_rgb8
     load_scene(ctx, golden_scenes["cornell"])
