@@ -53,6 +53,9 @@ struct rlpt_ctx {
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
     DqnTrain dq_train;
     NqTrainState nqt{}; int nqt_n = 0; float *d_nqt_qcur = nullptr, *d_nqt_qnext = nullptr, *d_nqt_targets = nullptr, *d_nqt_loss = nullptr; int nqt_batch = 0;
+    // CUDA graph of one full-batch optimiser step + fixed staging buffers for the batch's slice of the ray arrays
+    int nq_graphs = 1; cudaGraphExec_t nq_graph_exec = nullptr; int nq_graph_batch = 0;
+    float4 *d_nqg_loc = nullptr, *d_nqg_sloc = nullptr; uint32_t *d_nqg_action = nullptr, *d_nqg_state = nullptr; float *d_nqg_reward = nullptr, *d_nqg_discount = nullptr; int nqg_capacity = 0;
     float nq_epsilon = 0.05f; double nq_loss_total = 0.0;     // EPSILON_START (G/constants/deep_learning_settings.h:5)
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
@@ -105,7 +108,11 @@ static void free_lanes(rlpt_ctx* c) {
     }
     c->lanes.clear(); c->lane_capacity = 0; c->counts_len = 0; c->lane_spp = 0;
 }
+static void nq_graph_reset(rlpt_ctx* c) { if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; } c->nq_graph_batch = 0; }
 static void free_nqt(rlpt_ctx* c) {
+    nq_graph_reset(c);
+    cudaFree(c->d_nqg_loc); cudaFree(c->d_nqg_sloc); cudaFree(c->d_nqg_action); cudaFree(c->d_nqg_state); cudaFree(c->d_nqg_reward); cudaFree(c->d_nqg_discount);
+    c->d_nqg_loc = c->d_nqg_sloc = nullptr; c->d_nqg_action = c->d_nqg_state = nullptr; c->d_nqg_reward = c->d_nqg_discount = nullptr;
     cudaFree(c->nqt.loc); cudaFree(c->nqt.sloc); cudaFree(c->nqt.dir); cudaFree(c->nqt.thr); cudaFree(c->nqt.state); cudaFree(c->nqt.reward); cudaFree(c->nqt.discount);
     cudaFree(c->nqt.action); cudaFree(c->nqt.alive); cudaFree(c->d_nqt_qcur); cudaFree(c->d_nqt_qnext); cudaFree(c->d_nqt_targets); cudaFree(c->d_nqt_loss);
     c->nqt = NqTrainState{}; c->nqt_n = 0; c->nqt_batch = 0; c->d_nqt_qcur = c->d_nqt_qnext = c->d_nqt_targets = c->d_nqt_loss = nullptr;
@@ -160,6 +167,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     if (const char* e = getenv("RLPT_SPLIT")) c->pipe_split = atoi(e) != 0;
     if (const char* e = getenv("RLPT_TAIL")) c->pipe_tail = std::max(0, atoi(e));
     if (const char* e = getenv("RLPT_PRE")) c->pipe_pre = atoi(e) != 0;
+    if (const char* e = getenv("RLPT_NQ_GRAPH")) c->nq_graphs = atoi(e) != 0;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -562,7 +570,7 @@ static const std::vector<float>& dqn_vertices(rlpt_ctx* c) {
 static int dqn_push(rlpt_ctx* c) {          // host parameters -> device, operands derived
     const std::vector<float>& v = dqn_vertices(c);
     if ((int)v.size() != c->dq_host.k_in) return fail(RLPT_ERR_ARG, "DQN input width " + std::to_string(c->dq_host.k_in) + " does not match the scene (" + std::to_string(v.size()) + " vertex floats)");
-    dqn_train_free(c->dq_train);                     // new parameters: fresh optimiser state
+    nq_graph_reset(c); dqn_train_free(c->dq_train);  // new parameters: fresh optimiser state (and the captured step points into the old buffers)
     int rc = dqn_upload(c->dq, c->dq_host, v.data(), c->stream);
     if (rc) return fail(RLPT_ERR_CUDA, std::string("DQN upload failed: ") + cudaGetErrorString((cudaError_t)rc));
     return RLPT_OK;
@@ -1014,6 +1022,8 @@ static int ensure_nqt(rlpt_ctx* c, int batch) {
     const int S = (batch + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     CK(cudaMalloc(&c->d_nqt_qcur, sizeof(float) * DQ_OUT * (size_t)n)); CK(cudaMalloc(&c->d_nqt_qnext, sizeof(float) * DQ_OUT * (size_t)S));
     CK(cudaMalloc(&c->d_nqt_targets, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqt_loss, 4)); CK(cudaMemset(c->d_nqt_loss, 0, 4));
+    CK(cudaMalloc(&c->d_nqg_loc, sizeof(float4) * (size_t)S)); CK(cudaMalloc(&c->d_nqg_sloc, sizeof(float4) * (size_t)S)); CK(cudaMalloc(&c->d_nqg_action, 4 * (size_t)S));
+    CK(cudaMalloc(&c->d_nqg_state, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqg_reward, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqg_discount, 4 * (size_t)S));
     c->nqt_n = n; c->nqt_batch = batch;
     return RLPT_OK;
 }
@@ -1051,12 +1061,40 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
             if (b > 0) {
                 for (int start = 0; start < n; start += batch) {
                     const int bn = std::min(batch, n - start);
-                    fp.pos = c->nqt.loc + start; fp.n = bn; fp.q = c->d_nqt_qnext; fp.q_stride = S;
-                    int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
-                    launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                    frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream);
-                    if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
-                    launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
+                    // One optimiser step is ~40 small launches (forward of the next states, TD targets, forward + backward GEMMs,
+                    // Adam, operand repacking): launch-bound. Full batches replay a CUDA graph captured once; the batch's slice of
+                    // the ray arrays is copied into fixed staging buffers first, so the graph holds no per-batch address.
+                    const bool use_graph = c->nq_graphs && !dist && bn == batch;
+                    if (use_graph) {
+                        launch_nqt_stage(c->nqt, start, bn, c->d_nqg_loc, c->d_nqg_sloc, c->d_nqg_action, c->d_nqg_state, c->d_nqg_reward, c->d_nqg_discount, c->stream);
+                        if (!c->nq_graph_exec || c->nq_graph_batch != batch) {
+                            if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; }
+                            int arc = dqn_train_alloc(c->dq_train, c->dq, batch); if (arc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
+                            NqTrainState gs = c->nqt; gs.state = c->d_nqg_state; gs.reward = c->d_nqg_reward; gs.discount = c->d_nqg_discount;
+                            cudaGraph_t graph = nullptr;
+                            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                            DqnFwdParams gp = fp; gp.pos = c->d_nqg_loc; gp.n = bn; gp.q = c->d_nqt_qnext; gp.q_stride = S;
+                            int frc = dqn_forward(c->dq, gp, c->stream);
+                            launch_nqt_targets(gs, 0, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
+                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream);
+                            launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
+                            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                            if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(RLPT_ERR_CUDA, "Neural-Q training step: graph capture failed"); }
+                            ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
+                            cudaGraphDestroy(graph);
+                            if (ce != cudaSuccess) { c->nq_graph_exec = nullptr; return fail(RLPT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+                            c->nq_graph_batch = batch;
+                        }
+                        CK(cudaGraphLaunch(c->nq_graph_exec, c->stream));
+                        c->dq_train.step++;
+                    } else {
+                        fp.pos = c->nqt.loc + start; fp.n = bn; fp.q = c->d_nqt_qnext; fp.q_stride = S;
+                        int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
+                        launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
+                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream);
+                        if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
+                        launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
+                    }
                     c->launches += 40.0;
                 }
             }

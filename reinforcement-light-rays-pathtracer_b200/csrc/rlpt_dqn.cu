@@ -546,10 +546,17 @@ __global__ void k_sqnorm(const float* __restrict__ g, int n, float* __restrict__
 }
 // Adam as DyNet's AdamTrainer applies it: gradient scaled by min(1, clip / ||g||), m and v updated, step size
 // lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
+// The step counter lives on the device (scalars[3], advanced once per step by k_adam_tick, which also derives the bias-corrected
+// step size into scalars[2]), so that a captured optimiser step can be replayed as a CUDA graph without any host value in it.
+__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2) {
+    const float t = scalars[3] + 1.f; scalars[3] = t;
+    scalars[2] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
+}
 __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n, const float* __restrict__ scalars,
-                       float clip, float beta1, float beta2, float eps, float step_size) {
+                       float clip, float beta1, float beta2, float eps) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float step_size = scalars[2];
     const float norm = sqrtf(scalars[1]); const float scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
     const float gi = g[i] * scale;
     const float mi = beta1 * m[i] + (1.f - beta1) * gi, vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
@@ -575,7 +582,7 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
             DQ_CK(cudaMemset(t.mw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.mb[l], 0, 4 * nb)); DQ_CK(cudaMemset(t.vw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.vb[l], 0, 4 * nb));
         }
         DQ_CK(cudaMalloc(&t.dw3x, 4 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.dw2x, 4 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.dg, 4 * (size_t)DQ_K2 * 16));
-        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4));
+        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4)); DQ_CK(cudaMemset(t.scalars, 0, 4 * 4));
         t.step = 0;
     }
     if (S > t.capacity) {
@@ -603,7 +610,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     if (t.step == 0 || true) { rc = refresh_transposes(d, t, s); if (rc) return rc; }
     for (int l = 0; l < 4; ++l) { DQ_CK(cudaMemsetAsync(t.gw[l], 0, 4 * (size_t)DqnHost::rows(l) * shape.cols(l), s)); DQ_CK(cudaMemsetAsync(t.gb[l], 0, 4 * (size_t)DqnHost::rows(l), s)); }
     DQ_CK(cudaMemsetAsync(t.dw3x, 0, 4 * (size_t)DQ_N3 * DQ_K3, s)); DQ_CK(cudaMemsetAsync(t.dw2x, 0, 4 * (size_t)DQ_N2 * DQ_K2, s)); DQ_CK(cudaMemsetAsync(t.dg, 0, 4 * (size_t)DQ_K2 * 16, s));
-    DQ_CK(cudaMemsetAsync(t.scalars, 0, 4 * 4, s));
+    DQ_CK(cudaMemsetAsync(t.scalars, 0, 4 * 2, s));            // loss and gradient norm; [2] step size and [3] step count persist
     // forward, activations kept
     DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
     fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
@@ -638,11 +645,11 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     if (!apply_update) return (int)cudaGetLastError();
     for (int l = 0; l < 4; ++l) { k_sqnorm<<<64, 256, 0, s>>>(t.gw[l], DqnHost::rows(l) * shape.cols(l), t.scalars + 1); k_sqnorm<<<1, 256, 0, s>>>(t.gb[l], DqnHost::rows(l), t.scalars + 1); }
     t.step++;
-    const float step_size = t.lr * std::sqrt(1.f - std::pow(t.beta2, (float)t.step)) / (1.f - std::pow(t.beta1, (float)t.step));
+    k_adam_tick<<<1, 1, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2);
     for (int l = 0; l < 4; ++l) {
         const int nw = DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
-        k_adam<<<(nw + 255) / 256, 256, 0, s>>>(d.w[l], t.gw[l], t.mw[l], t.vw[l], nw, t.scalars, t.clip, t.beta1, t.beta2, t.eps, step_size);
-        k_adam<<<(nb + 255) / 256, 256, 0, s>>>(d.b[l], t.gb[l], t.mb[l], t.vb[l], nb, t.scalars, t.clip, t.beta1, t.beta2, t.eps, step_size);
+        k_adam<<<(nw + 255) / 256, 256, 0, s>>>(d.w[l], t.gw[l], t.mw[l], t.vw[l], nw, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
+        k_adam<<<(nb + 255) / 256, 256, 0, s>>>(d.b[l], t.gb[l], t.mb[l], t.vb[l], nb, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
     }
     rc = dqn_refresh_operands(d, s); if (rc) return rc;
     return (int)cudaGetLastError();

@@ -61,7 +61,7 @@ struct DqnTrain {
     __nv_bfloat16 *d3 = nullptr, *d2 = nullptr, *d3t = nullptr, *d2t = nullptr, *d1t = nullptr;
     float *p2 = nullptr, *p1 = nullptr;             // pre-activation deltas [S][304], [S][208] (fp32 GEMM outputs)
     float* q = nullptr;                             // [144][S] predictions of the batch
-    float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm
+    float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm, [2] Adam step size, [3] Adam step count (kept on the device: graph replay)
     float* g4 = nullptr; int g4_capacity = 0;       // supervised step: dense output-layer gradient [144][S]
     unsigned long long step = 0;
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;

@@ -954,6 +954,17 @@ __global__ void k_nqt_targets(NqTrainState st, int start, int n, const float* __
     }
     targets[j] = target;
 }
+// the batch's slice of the ray arrays -> fixed staging buffers (the captured optimiser step reads only those)
+__global__ void k_nqt_stage(NqTrainState st, int start, int n, float4* __restrict__ loc, float4* __restrict__ sloc, uint32_t* __restrict__ action,
+                            uint32_t* __restrict__ state, float* __restrict__ reward, float* __restrict__ discount) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = start + j;
+    loc[j] = st.loc[i]; sloc[j] = st.sloc[i]; action[j] = st.action[i]; state[j] = st.state[i]; reward[j] = st.reward[i]; discount[j] = st.discount[i];
+}
+void launch_nqt_stage(const NqTrainState& st, int start, int n, float4* loc, float4* sloc, uint32_t* action, uint32_t* state, float* reward, float* discount, cudaStream_t s) {
+    k_nqt_stage<<<(n + 255) / 256, 256, 0, s>>>(st, start, n, loc, sloc, action, state, reward, discount);
+}
 void launch_nqt_targets(const NqTrainState& st, int start, int n, const float* q_next, int q_stride, float* targets, cudaStream_t s) {
     k_nqt_targets<<<(n + 127) / 128, 128, 0, s>>>(st, start, n, q_next, q_stride, targets);
 }
