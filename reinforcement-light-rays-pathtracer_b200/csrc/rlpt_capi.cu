@@ -1095,7 +1095,7 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
                         launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
                     }
-                    c->launches += 40.0;
+                    c->launches += 22.0;       // kernels of one optimiser step (staging, 2 forwards, targets, zeroing, 5 GEMMs, deltas, collect, norm, Adam, operand refresh)
                 }
             }
             launch_nqt_respawn(p, dyn, c->nqt, b, c->stream);

@@ -564,6 +564,72 @@ __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float
     x[i] -= step_size * mi / (sqrtf(vi) + eps);
 }
 
+// The eight parameter arrays (W1 b1 .. W4 b4) are separate allocations; the per-step element-wise passes run over all of them
+// in ONE launch each (segment table passed by value) instead of eight: the optimiser step is a chain of ~40 tiny kernels and
+// every node costs a few microseconds of dependency latency.
+struct ParamSegs { float* x[8]; float* g[8]; float* m[8]; float* v[8]; int start[9]; };
+__device__ __forceinline__ int seg_of(const ParamSegs& t, int i) { int s = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += i >= t.start[k] ? 1 : 0;
+    return s; }
+__global__ void k_zero_grads(ParamSegs t, float* a, int na, float* b, int nb, float* c, int nc, float* scalars) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, total = t.start[8];
+    if (i < total) { const int s = seg_of(t, i); t.g[s][i - t.start[s]] = 0.f; return; }
+    int j = i - total;
+    if (j < na) { a[j] = 0.f; return; } j -= na;
+    if (j < nb) { b[j] = 0.f; return; } j -= nb;
+    if (j < nc) { c[j] = 0.f; return; } j -= nc;
+    if (j < 2) scalars[j] = 0.f;                               // loss and gradient norm; [2] step size and [3] step count persist
+}
+__global__ void k_sqnorm_all(ParamSegs t, float* __restrict__ out) {
+    float acc = 0.f; const int total = t.start[8];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { const int s = seg_of(t, i); const float g = t.g[s][i - t.start[s]]; acc += g * g; }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+__global__ void k_adam_all(ParamSegs t, const float* __restrict__ scalars, float clip, float beta1, float beta2, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.start[8]) return;
+    const int s = seg_of(t, i), j = i - t.start[s];
+    const float step_size = scalars[2];
+    const float norm = sqrtf(scalars[1]); const float scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
+    const float gi = t.g[s][j] * scale;
+    const float mi = beta1 * t.m[s][j] + (1.f - beta1) * gi, vi = beta2 * t.v[s][j] + (1.f - beta2) * gi * gi;
+    t.m[s][j] = mi; t.v[s][j] = vi;
+    t.x[s][j] -= step_size * mi / (sqrtf(vi) + eps);
+}
+static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
+    ParamSegs p{}; DqnHost shape; shape.k_in = d.k_in; int at = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int nw = DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
+        p.x[2 * l] = d.w[l]; p.g[2 * l] = t.gw[l]; p.m[2 * l] = t.mw[l]; p.v[2 * l] = t.vw[l]; p.start[2 * l] = at; at += nw;
+        p.x[2 * l + 1] = d.b[l]; p.g[2 * l + 1] = t.gb[l]; p.m[2 * l + 1] = t.mb[l]; p.v[2 * l + 1] = t.vb[l]; p.start[2 * l + 1] = at; at += nb;
+    }
+    p.start[8] = at;
+    return p;
+}
+// packed bf16 operands of layers 2-4 and the two transposes of the backward pass, one launch
+__global__ void k_pack_all(const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w3p,
+                           __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n2 = DQ_N2 * DQ_K2, n3 = DQ_N3 * DQ_K3, n4 = DQ_N4 * DQ_K4;
+    auto pack = [](const float* w, int n, int k, int k_pad, __nv_bfloat16* out, int idx) {
+        const int row = idx / k_pad, col = idx % k_pad;
+        const float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + operand_offset(row, col, k_pad)) = __float2bfloat16_rn(v);
+    };
+    auto transpose = [](const float* w, int rows, int cols, int out_cols_pad, __nv_bfloat16* out, int idx) {      // out[c][r] = w[r][c]
+        const int c = idx / out_cols_pad, r = idx % out_cols_pad;
+        out[idx] = __float2bfloat16_rn((c < cols && r < rows) ? w[(size_t)r * cols + c] : 0.f);
+    };
+    if (i < n2) { pack(w2, DQ_H2, DQ_H1, DQ_K2, w2p, i); return; } i -= n2;
+    if (i < n3) { pack(w3, DQ_H3, DQ_H2, DQ_K3, w3p, i); return; } i -= n3;
+    if (i < n4) { pack(w4, DQ_OUT, DQ_H3, DQ_K4, w4p, i); return; } i -= n4;
+    if (!w3t) return;
+    if (i < DQ_N2 * DQ_K2) { transpose(w3, DQ_H3, DQ_H2, DQ_K2, w3t, i); return; } i -= DQ_N2 * DQ_K2;
+    if (i < DQ_N3 * DQ_K3) transpose(w2, DQ_H2, DQ_H1, DQ_K3, w2t, i);
+}
+
 void dqn_train_free(DqnTrain& t) {
     for (int l = 0; l < 4; ++l) { cudaFree(t.gw[l]); cudaFree(t.gb[l]); cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
@@ -607,10 +673,12 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     DqnHost shape; shape.k_in = d.k_in;
-    if (t.step == 0 || true) { rc = refresh_transposes(d, t, s); if (rc) return rc; }
-    for (int l = 0; l < 4; ++l) { DQ_CK(cudaMemsetAsync(t.gw[l], 0, 4 * (size_t)DqnHost::rows(l) * shape.cols(l), s)); DQ_CK(cudaMemsetAsync(t.gb[l], 0, 4 * (size_t)DqnHost::rows(l), s)); }
-    DQ_CK(cudaMemsetAsync(t.dw3x, 0, 4 * (size_t)DQ_N3 * DQ_K3, s)); DQ_CK(cudaMemsetAsync(t.dw2x, 0, 4 * (size_t)DQ_N2 * DQ_K2, s)); DQ_CK(cudaMemsetAsync(t.dg, 0, 4 * (size_t)DQ_K2 * 16, s));
-    DQ_CK(cudaMemsetAsync(t.scalars, 0, 4 * 2, s));            // loss and gradient norm; [2] step size and [3] step count persist
+    const ParamSegs segs = param_segs(d, t);
+    if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }       // afterwards k_pack_all keeps them current
+    {
+        const int na = DQ_N3 * DQ_K3, nb = DQ_N2 * DQ_K2, nc = DQ_K2 * 16, total = segs.start[8] + na + nb + nc + 2;
+        k_zero_grads<<<(total + 255) / 256, 256, 0, s>>>(segs, t.dw3x, na, t.dw2x, nb, t.dg, nc, t.scalars);
+    }
     // forward, activations kept
     DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
     fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
@@ -643,15 +711,16 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
     }
     if (!apply_update) return (int)cudaGetLastError();
-    for (int l = 0; l < 4; ++l) { k_sqnorm<<<64, 256, 0, s>>>(t.gw[l], DqnHost::rows(l) * shape.cols(l), t.scalars + 1); k_sqnorm<<<1, 256, 0, s>>>(t.gb[l], DqnHost::rows(l), t.scalars + 1); }
+    k_sqnorm_all<<<128, 256, 0, s>>>(segs, t.scalars + 1);
     t.step++;
     k_adam_tick<<<1, 1, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2);
-    for (int l = 0; l < 4; ++l) {
-        const int nw = DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
-        k_adam<<<(nw + 255) / 256, 256, 0, s>>>(d.w[l], t.gw[l], t.mw[l], t.vw[l], nw, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
-        k_adam<<<(nb + 255) / 256, 256, 0, s>>>(d.b[l], t.gb[l], t.mb[l], t.vb[l], nb, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
+    k_adam_all<<<(segs.start[8] + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
+    // operands for the next forward / backward: layer-1 rank-3 form, packed bf16 weights, the two transposes
+    k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);
+    {
+        const int total = DQ_N2 * DQ_K2 + DQ_N3 * DQ_K3 + DQ_N4 * DQ_K4 + DQ_N2 * DQ_K2 + DQ_N3 * DQ_K3;
+        k_pack_all<<<(total + 255) / 256, 256, 0, s>>>(d.w[1], d.w[2], d.w[3], d.w2p, d.w3p, d.w4p, t.w3t, t.w2t);
     }
-    rc = dqn_refresh_operands(d, s); if (rc) return rc;
     return (int)cudaGetLastError();
 }
 

@@ -64,6 +64,7 @@ struct DqnTrain {
     float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm, [2] Adam step size, [3] Adam step count (kept on the device: graph replay)
     float* g4 = nullptr; int g4_capacity = 0;       // supervised step: dense output-layer gradient [144][S]
     unsigned long long step = 0;
+    bool transposes_fresh = false;                  // W3^T / W2^T match the current parameters (k_pack_all refreshes them after every update)
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
 };
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
