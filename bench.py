@@ -212,8 +212,14 @@ def main():
     ctx.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"])
     ctx.camera_set(cam)
     nv = ctx.radiance_map_build() if method == 1 else 0
+    exchange = "none"
     if world > 1:
         ctx.set_allreduce(torch_allreduce_hook(local))
+        exchange = "nccl all-reduce of the Q accumulators (torch.distributed), then the merge kernel"
+        if method == 1 and os.environ.get("RLPT_EXCHANGE", "p2p") == "p2p":
+            from rlpt.dist import p2p_setup
+            p2p_setup(ctx)
+            exchange = "fused exchange + merge kernel over peer memory (CUDA IPC, P2P loads/stores over NVLink); no collective call per frame"
     fp32_peak = ctx.measure_fp32_peak()
     render = ctx.render_sarsa if method == 1 else ctx.render_default
 
@@ -295,7 +301,7 @@ def main():
             "config": {"workload": args.workload, "scene": "%s (%d surfaces + %d area lights)" % (scene_name, len(s["sv"]), len(s["lv"])),
                        "method": "Expected SARSA radiance volumes, train + render" if method == 1 else "default path tracer",
                        "width": args.width, "height": args.height, "spp_per_frame": args.spp, "frames": args.steps, "spp_total_per_gpu": args.spp * args.steps,
-                       "radiance_volumes": nv, "grid": "12x12", "max_bounces": 80, "partition": "samples (rank r traces samples r*spp..(r+1)*spp-1 of each global frame)",
+                       "radiance_volumes": nv, "grid": "12x12", "max_bounces": 80, "partition": "samples (rank r traces samples r*spp..(r+1)*spp-1 of each global frame)", "exchange": exchange,
                        "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 60 * 2 / 1e9, nv * 144 * 20 / 1e6)},
             "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "mray_casts_per_s": st["ray_casts"] * world / dev_s / 1e6,
             "zero_contribution_fraction": st["zero_contribution_paths"] / max(st["paths"], 1),

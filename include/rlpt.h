@@ -114,6 +114,15 @@ int rlpt_closest_hit_device(rlpt_ctx* ctx, const float* d_org, const float* d_di
  * device storage is SoA (DESIGN.md "Q-table layout"). */
 int rlpt_radiance_map_build(rlpt_ctx* ctx);
 int rlpt_radiance_map_info(rlpt_ctx* ctx, int* n_volumes, int* n_tree_nodes);
+/* Peer-memory exchange for N > 1 ranks on one node (one process per GPU). Without it the Q accumulators are all-reduced
+ * through the rlpt_set_allreduce hook and merged afterwards; with it ONE kernel per rank reduces its slice of the volumes
+ * straight out of every rank's accumulators (P2P loads over NVLink), merges, rebuilds the CDFs and stores the results into
+ * every rank's tables (P2P stores). Call on every rank after rlpt_radiance_map_build: export this rank's blob
+ * (rlpt_p2p_blob_bytes() bytes of CUDA IPC handles), gather all ranks' blobs in rank order by any means, import them.
+ * rlpt_config.rank / world_size select the slice. The reference has no multi-GPU code. */
+int rlpt_p2p_blob_bytes(void);
+int rlpt_p2p_export(rlpt_ctx* ctx, void* blob);
+int rlpt_p2p_import(rlpt_ctx* ctx, const void* blobs, int world_size);
 /* flattened kd-tree exactly as the reference's std::vector<RadianceTreeElement> (G/radiance_volumes/radiance_tree.cuh:19-27) */
 int rlpt_radiance_map_tree(rlpt_ctx* ctx, int* dim, int* leaf, unsigned* left, unsigned* right, float* data, float* pos3, float* nrm3);
 /* replaces: RadianceMap::find_closest_radiance_volume_iterative (radiance_map.cu:150-203) for a batch of points */

@@ -49,6 +49,9 @@ struct rlpt_ctx {
     int4* d_vc_table = nullptr; float4* d_vc_cand = nullptr; int4* d_vx_table = nullptr; float4* d_vx_cand = nullptr; float vx_built_within = 0.f; float vc_built_accept = 0.f; size_t vc_keys = 0, vc_listed = 0;   // nearest-volume candidate cells
     float *d_q = nullptr, *d_cdf = nullptr, *d_cdf_rows = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
+    // peer-memory exchange (rlpt_p2p_export / rlpt_p2p_import): every rank's exchange buffers opened through CUDA IPC
+    PeerTables peers{}; bool p2p_ready = false; unsigned p2p_epoch = 0; unsigned* d_p2p_flags = nullptr; unsigned* d_p2p_done = nullptr;
+    std::vector<void*> p2p_opened;
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
     DqnTrain dq_train;
@@ -90,7 +93,13 @@ static void free_scene(rlpt_ctx* c) {
     cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_surf_lum_over_pi); cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
     c->d_tri = c->d_shade = c->d_bvh = nullptr; c->d_surf_lum_over_pi = nullptr; c->have_scene = false;
 }
+static void p2p_close(rlpt_ctx* c) {
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear(); c->p2p_ready = false; c->peers = PeerTables{};
+    cudaFree(c->d_p2p_flags); cudaFree(c->d_p2p_done); c->d_p2p_flags = c->d_p2p_done = nullptr; c->p2p_epoch = 0;
+}
 static void free_rmap(rlpt_ctx* c) {
+    p2p_close(c);
     cudaFree(c->d_kd); cudaFree(c->d_posn); cudaFree(c->d_vol_surface); cudaFree(c->d_q); cudaFree(c->d_cdf); cudaFree(c->d_irr);
     cudaFree(c->d_acc_sum); cudaFree(c->d_visits); cudaFree(c->d_acc_cnt); cudaFree(c->d_cdf_rows); c->d_cdf_rows = nullptr;
     cudaFree(c->d_vc_table); cudaFree(c->d_vc_cand); c->d_vc_table = nullptr; c->d_vc_cand = nullptr;
@@ -453,6 +462,54 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     c->have_rmap = true;
     launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    return RLPT_OK;
+}
+
+// ---- peer-memory exchange setup. Blob: n_volumes (int, padded to 8 bytes) + 8 cudaIpcMemHandle_t
+// (acc_sum, acc_cnt, q, cdf, cdf_rows, visits, irradiance, flags).
+static const int P2P_HANDLES = 8;
+int rlpt_p2p_blob_bytes(void) { return 8 + P2P_HANDLES * (int)sizeof(cudaIpcMemHandle_t); }
+int rlpt_p2p_export(rlpt_ctx* c, void* blob) {
+    if (!c || !c->have_rmap || !blob) return fail(RLPT_ERR_ARG, "rlpt_p2p_export: build the radiance map first");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    if (!c->d_p2p_flags) {
+        CK(cudaMalloc(&c->d_p2p_flags, sizeof(unsigned) * 2 * MAX_PEERS)); CK(cudaMemset(c->d_p2p_flags, 0, sizeof(unsigned) * 2 * MAX_PEERS));
+        CK(cudaMalloc(&c->d_p2p_done, sizeof(unsigned))); CK(cudaMemset(c->d_p2p_done, 0, sizeof(unsigned)));
+    }
+    unsigned char* out = (unsigned char*)blob; memset(out, 0, 8);
+    const int nv = c->rm.n_vol; memcpy(out, &nv, 4);
+    void* ptrs[P2P_HANDLES] = { c->d_acc_sum, c->d_acc_cnt, c->d_q, c->d_cdf, c->d_cdf_rows, c->d_visits, c->d_irr, c->d_p2p_flags };
+    for (int i = 0; i < P2P_HANDLES; ++i) { cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, ptrs[i])); memcpy(out + 8 + i * sizeof h, &h, sizeof h); }
+    return RLPT_OK;
+}
+int rlpt_p2p_import(rlpt_ctx* c, const void* blobs, int world_size) {
+    if (!c || !c->have_rmap || !blobs || !c->d_p2p_flags) return fail(RLPT_ERR_ARG, "rlpt_p2p_import: call rlpt_p2p_export first");
+    if (world_size != c->cfg.world_size || world_size < 2 || world_size > MAX_PEERS) return fail(RLPT_ERR_ARG, "rlpt_p2p_import: world size must equal rlpt_config.world_size and be 2..8");
+    CK(cudaSetDevice(c->device));
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear(); c->p2p_ready = false;
+    PeerTables pt{}; pt.world = world_size; pt.rank = c->cfg.rank;
+    const size_t stride = (size_t)rlpt_p2p_blob_bytes();
+    for (int r = 0; r < world_size; ++r) {
+        const unsigned char* in = (const unsigned char*)blobs + (size_t)r * stride;
+        int nv = 0; memcpy(&nv, in, 4);
+        if (nv != c->rm.n_vol) return fail(RLPT_ERR_ARG, "rlpt_p2p_import: rank " + std::to_string(r) + " has a different radiance map");
+        void* ptrs[P2P_HANDLES];
+        if (r == c->cfg.rank) {
+            void* own[P2P_HANDLES] = { c->d_acc_sum, c->d_acc_cnt, c->d_q, c->d_cdf, c->d_cdf_rows, c->d_visits, c->d_irr, c->d_p2p_flags };
+            memcpy(ptrs, own, sizeof own);
+        } else {
+            for (int i = 0; i < P2P_HANDLES; ++i) {
+                cudaIpcMemHandle_t h; memcpy(&h, in + 8 + i * sizeof h, sizeof h);
+                cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], h, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) return fail(RLPT_ERR_CUDA, std::string("rlpt_p2p_import: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                c->p2p_opened.push_back(ptrs[i]);
+            }
+        }
+        pt.acc_sum[r] = (float*)ptrs[0]; pt.acc_cnt[r] = (uint32_t*)ptrs[1]; pt.q[r] = (float*)ptrs[2]; pt.cdf[r] = (float*)ptrs[3]; pt.cdf_rows[r] = (float*)ptrs[4];
+        pt.visits[r] = (uint32_t*)ptrs[5]; pt.irradiance[r] = (float*)ptrs[6]; pt.flags[r] = (unsigned*)ptrs[7];
+    }
+    c->peers = pt; c->p2p_ready = true;
     return RLPT_OK;
 }
 
@@ -869,6 +926,12 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
 }
 
 static int enqueue_merge(rlpt_ctx* c) {
+    if (c->p2p_ready && c->cfg.world_size > 1) {
+        launch_merge_p2p(c->rm, c->peers, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, ++c->p2p_epoch, c->d_p2p_done, c->stream);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        return RLPT_OK;
+    }
     if (c->allreduce && c->cfg.world_size > 1) {
         const uint64_t cells = (uint64_t)c->rm.n_vol * CELLS;
         if (c->allreduce(c->d_acc_sum, cells, 0, (void*)c->stream, c->allreduce_user)) return fail(RLPT_ERR_COLLECTIVE, "all-reduce hook failed (target sums)");

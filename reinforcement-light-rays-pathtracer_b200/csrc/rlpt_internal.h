@@ -122,6 +122,17 @@ void launch_add_scalar(float* dst, const float* src, cudaStream_t s);
 void launch_nq_trace(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s);
 void launch_nq_sample(const FrameParams& p, const FrameDyn& dyn, int bounce, const float* q, int q_stride, float epsilon, uint32_t* action_out, int grid, cudaStream_t s);
 void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float threshold, int rebuild_only, cudaStream_t s);
+// Peer-memory exchange (one process per GPU of one node, buffers opened through CUDA IPC): the same arrays on every rank.
+// flags: [2][MAX_PEERS] unsigned per rank -- [0][r] = rank r's accumulators of epoch e are complete, [1][r] = rank r has
+// stored its slice of epoch e into my tables (and is done with my accumulators).
+constexpr int MAX_PEERS = 8;
+struct PeerTables {
+    float* acc_sum[MAX_PEERS]; uint32_t* acc_cnt[MAX_PEERS];
+    float* q[MAX_PEERS]; float* cdf[MAX_PEERS]; float* cdf_rows[MAX_PEERS]; uint32_t* visits[MAX_PEERS]; float* irradiance[MAX_PEERS];
+    unsigned* flags[MAX_PEERS];
+    int world, rank;
+};
+void launch_merge_p2p(const RadianceDev& rm, const PeerTables& pt, const float* surf_lum_over_pi, float threshold, unsigned epoch, unsigned* done_counter, cudaStream_t s);
 void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
                         unsigned long long* counters, size_t smem, cudaStream_t s);
 void launch_find_closest(const RadianceDev& rm, const SceneDev& sc, const float* pos, const float* nrm, int n, int* out, cudaStream_t s);

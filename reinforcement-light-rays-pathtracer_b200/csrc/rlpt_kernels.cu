@@ -1072,6 +1072,107 @@ void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float th
     k_merge_cdf<<<grid, BLOCK, 0, s>>>(rm, surf_lum_over_pi, threshold, rebuild_only);
 }
 
+// ------------------------------------------------------------------------------------------------ exchange + merge over peer memory
+// Multi-GPU form of k_merge_cdf: instead of all-reducing the accumulators (1152 B per volume) with a collective library and
+// merging afterwards, every rank reduces ITS slice of the volumes straight out of all ranks' accumulators (P2P loads over
+// NVLink / NVSwitch), merges, rebuilds the CDFs of the slice and stores the results into every rank's tables (P2P stores):
+// reduce-scatter, the merge and the all-gather in one kernel, 1/N of the all-reduce's traffic per GPU on the way in, only
+// the volumes that were actually visited on the way out. Replicas end bit-identical by construction (one owner computes
+// each volume; the sum runs over the ranks in rank order). Synchronisation is two flag rounds in peer memory:
+//   start  block 0 announces "my accumulators of this epoch are complete" (the kernel is stream-ordered after the tracing)
+//          to every rank; every CTA waits until all ranks have announced
+//   end    the last CTA to finish announces "my slice is stored everywhere"; k_wait_peers (next in the stream) waits for
+//          all ranks' announcements, after which the local tables are complete and nobody reads the local accumulators
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__global__ void __launch_bounds__(BLOCK) k_merge_cdf_p2p(RadianceDev rm, const __grid_constant__ PeerTables pt, const float* __restrict__ surf_lum_over_pi, float threshold,
+                                                         unsigned epoch, unsigned* done_counter) {
+    const unsigned full = 0xffffffffu;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) { __threadfence_system(); for (int r = 0; r < pt.world; ++r) st_release_sys(pt.flags[r] + pt.rank, epoch); }
+        const unsigned* mine = pt.flags[pt.rank];
+        for (int r = 0; r < pt.world; ++r) while ((int)(ld_acquire_sys(mine + r) - epoch) < 0) __nanosleep(200);
+    }
+    __syncthreads();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int v0 = (int)((long long)rm.n_vol * pt.rank / pt.world), v1 = (int)((long long)rm.n_vol * (pt.rank + 1) / pt.world);
+    for (int vol = v0 + warp; vol < v1; vol += nwarps) {
+        const size_t base = (size_t)vol * CELLS;
+        float temp[5]; float tsum = 0.f, irr = 0.f; bool touched = false;
+        // all remote loads of the volume are issued before any is used: one NVLink round trip per volume, not one per cell and rank
+        uint32_t cn[5][MAX_PEERS]; float sm[5][MAX_PEERS];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int k = c * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r) {
+                const bool on = r < pt.world && k < CELLS;
+                cn[c][r] = on ? __ldcg(pt.acc_cnt[r] + base + k) : 0u;
+                sm[c][r] = on ? __ldcg(pt.acc_sum[r] + base + k) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int k = c * 32 + lane; temp[c] = 0.f;
+            if (k < CELLS) {
+                float q = rm.q[base + k];
+                uint32_t cnt = 0; float sum = 0.f;
+#pragma unroll
+                for (int r = 0; r < MAX_PEERS; ++r) {                     // rank order: the same sum on whichever rank owns the volume
+                    if (r < pt.world && cn[c][r]) { cnt += cn[c][r]; sum += sm[c][r]; pt.acc_cnt[r][base + k] = 0u; pt.acc_sum[r][base + k] = 0.f; }
+                }
+                if (cnt) {
+                    const float vs = (float)rm.visits[base + k];
+                    q = (vs * q + sum) / (vs + (float)cnt);
+                    q = q > threshold ? q : threshold;
+                    const uint32_t nvis = rm.visits[base + k] + cnt;
+                    for (int r = 0; r < pt.world; ++r) { pt.q[r][base + k] = q; pt.visits[r][base + k] = nvis; }
+                    touched = true;
+                }
+                const float w = q * c_cell_cos[k];
+                irr += w;
+                temp[c] = w > 0.f ? w : 0.f;
+                tsum += temp[c];
+            }
+        }
+        if (!__any_sync(full, touched)) continue;                        // nothing of this volume was visited: every rank's CDF stands
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { tsum += __shfl_xor_sync(full, tsum, o); irr += __shfl_xor_sync(full, irr, o); }
+        const float total = 0.0000000001f + tsum;
+        float carry = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            float x = temp[c] / total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { float y = __shfl_up_sync(full, x, o); if (lane >= o) x += y; }
+            x += carry;
+            const int k = c * 32 + lane;
+            if (k < CELLS) {
+                for (int r = 0; r < pt.world; ++r) { pt.cdf[r][base + k] = x; if (k % GRID == GRID - 1) pt.cdf_rows[r][(size_t)vol * GRID + k / GRID] = x; }
+            }
+            carry = __shfl_sync(full, x, 31);
+        }
+        if (lane == 0) { const float e = irr * __ldg(surf_lum_over_pi + __ldg(rm.vol_surface + vol)); for (int r = 0; r < pt.world; ++r) pt.irradiance[r][vol] = e; }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+            *done_counter = 0u; __threadfence_system();
+            for (int r = 0; r < pt.world; ++r) st_release_sys(pt.flags[r] + MAX_PEERS + pt.rank, epoch);
+        }
+    }
+}
+__global__ void k_wait_peers(const unsigned* __restrict__ flags, int world, unsigned epoch) {
+    if (threadIdx.x < (unsigned)world) while ((int)(ld_acquire_sys(flags + MAX_PEERS + threadIdx.x) - epoch) < 0) __nanosleep(200);
+}
+void launch_merge_p2p(const RadianceDev& rm, const PeerTables& pt, const float* surf_lum_over_pi, float threshold, unsigned epoch, unsigned* done_counter, cudaStream_t s) {
+    const int slice = rm.n_vol / pt.world + 1, warps_per_block = BLOCK / 32;
+    int grid = (slice + warps_per_block - 1) / warps_per_block; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    k_merge_cdf_p2p<<<grid, BLOCK, 0, s>>>(rm, pt, surf_lum_over_pi, threshold, epoch, done_counter);
+    k_wait_peers<<<1, 32, 0, s>>>(pt.flags[pt.rank], pt.world, epoch);
+}
+
 // ------------------------------------------------------------------------------------------------ frame buffer
 __global__ void k_frame_mean(const float4* __restrict__ accum, float* __restrict__ rgb, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

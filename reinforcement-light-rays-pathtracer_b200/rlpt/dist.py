@@ -41,3 +41,13 @@ def host_allreduce_hook(group=None):
         t = torch.from_numpy(a)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return hook
+
+
+def p2p_setup(ctx, group=None):
+    """Peer-memory exchange for the ranks of one node (Context.p2p_export / p2p_import): gathers every rank's CUDA IPC
+    handles with torch.distributed and opens them. After this the per-frame Q exchange needs no collective call."""
+    import torch.distributed as dist
+    blobs = [None] * dist.get_world_size(group)
+    dist.all_gather_object(blobs, ctx.p2p_export(), group=group)
+    ctx.p2p_import(blobs)
+    dist.barrier(group=group)

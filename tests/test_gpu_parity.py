@@ -358,7 +358,7 @@ def test_error_behaviour(ctx):
         ctx.scene_upload(np.zeros((0, 9)), np.zeros((0, 3)), np.zeros((0, 9)), np.zeros((0, 3)))
 
 
-def _two_gpu_worker(rank, world, port, out_dir):
+def _two_gpu_worker(rank, world, port, out_dir, p2p=False):
     import os, sys
     from conftest import ROOT
     sys.path.insert(0, os.path.join(ROOT, "reinforcement-light-rays-pathtracer_b200"))
@@ -371,11 +371,37 @@ def _two_gpu_worker(rank, world, port, out_dir):
     s = {k.split("/")[1]: z[k] for k in z.files if k.startswith("cornell/")}
     c = rlpt.Context(rank, width=64, height=64, spp=4, max_bounces=80, rank=rank, world_size=world)
     c.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"]); c.camera_set((0, 0, -3)); c.radiance_map_build()
-    c.set_allreduce(torch_allreduce_hook(rank))
+    c.set_allreduce(torch_allreduce_hook(rank))                    # frame buffer sum (and the Q exchange unless p2p)
+    if p2p:
+        from rlpt.dist import p2p_setup
+        p2p_setup(c)
     c.render_sarsa(3); c.frame_allreduce()
     d = c.radiance_map_download()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), q=d["q"], cdf=d["cdf"], vis=d["visits"], img=c.frame_download(), paths=c.stats()["paths"])
     c.close(); dist.destroy_process_group()
+
+
+def test_two_gpus_peer_memory_exchange(ctx, golden_scenes, tmp_path):
+    """the same with the fused exchange + merge kernel over peer memory (k_merge_cdf_p2p: each rank reduces its slice of the
+    volumes out of both ranks' accumulators, merges and stores into both ranks' tables; no collective call per frame)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import os
+    mp.spawn(_two_gpu_worker, args=(2, 29300 + os.getpid() % 200, str(tmp_path), True), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("q", "cdf", "vis", "img"):
+        assert np.array_equal(r0[k], r1[k]), k
+    load_scene(ctx, golden_scenes["cornell"])
+    ctx.configure(width=64, height=64, spp=8, max_bounces=80); ctx.camera_set((0, 0, -3)); ctx.radiance_map_build()
+    ctx.render_sarsa(3)
+    d = ctx.radiance_map_download(); img = ctx.frame_download()
+    assert float(r0["paths"]) * 2 == ctx.stats()["paths"]
+    assert int(r0["vis"].sum()) > 0 and np.mean(d["visits"] == r0["vis"]) >= 0.999
+    assert np.mean(np.isclose(d["q"], r0["q"], rtol=1e-3, atol=1e-6)) >= 0.999
+    assert np.mean(np.isclose(d["cdf"], r0["cdf"], rtol=1e-3, atol=1e-5)) >= 0.999
+    _assert_images_close(r0["img"], img, frac=0.99, tol=5e-3, mean_tol=5e-3)
 
 
 def test_two_gpus_equal_one_gpu(ctx, golden_scenes, tmp_path):
