@@ -218,8 +218,8 @@ def main():
         exchange = "nccl all-reduce of the Q accumulators (torch.distributed), then the merge kernel"
         if method == 1 and os.environ.get("RLPT_EXCHANGE", "p2p") == "p2p":
             from rlpt.dist import p2p_setup
-            p2p_setup(ctx)
-            exchange = "fused exchange + merge kernel over peer memory (CUDA IPC, P2P loads/stores over NVLink); no collective call per frame"
+            if p2p_setup(ctx):
+                exchange = "fused exchange + merge kernel over peer memory (CUDA IPC, P2P loads/stores over NVLink); no collective call per frame"
     fp32_peak = ctx.measure_fp32_peak()
     render = ctx.render_sarsa if method == 1 else ctx.render_default
 

@@ -123,6 +123,8 @@ int rlpt_radiance_map_info(rlpt_ctx* ctx, int* n_volumes, int* n_tree_nodes);
 int rlpt_p2p_blob_bytes(void);
 int rlpt_p2p_export(rlpt_ctx* ctx, void* blob);
 int rlpt_p2p_import(rlpt_ctx* ctx, const void* blobs, int world_size);
+/* back to the all-reduce hook (every rank must switch at the same frame boundary) */
+int rlpt_p2p_close(rlpt_ctx* ctx);
 /* flattened kd-tree exactly as the reference's std::vector<RadianceTreeElement> (G/radiance_volumes/radiance_tree.cuh:19-27) */
 int rlpt_radiance_map_tree(rlpt_ctx* ctx, int* dim, int* leaf, unsigned* left, unsigned* right, float* data, float* pos3, float* nrm3);
 /* replaces: RadianceMap::find_closest_radiance_volume_iterative (radiance_map.cu:150-203) for a batch of points */

@@ -513,6 +513,14 @@ int rlpt_p2p_import(rlpt_ctx* c, const void* blobs, int world_size) {
     return RLPT_OK;
 }
 
+int rlpt_p2p_close(rlpt_ctx* c) {
+    if (!c) return fail(RLPT_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
+    c->p2p_opened.clear(); c->p2p_ready = false;                 // the flag arrays stay: peers may still hold them open
+    return RLPT_OK;
+}
+
 int rlpt_radiance_map_info(rlpt_ctx* c, int* nv, int* nt) {
     if (!c || !c->have_rmap) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_info: no radiance map");
     if (nv) *nv = (int)c->h_vol.size(); if (nt) *nt = (int)c->h_tree.size();

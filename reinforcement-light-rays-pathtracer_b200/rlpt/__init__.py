@@ -46,7 +46,7 @@ SYMBOLS = [
     "rlpt_render_sarsa_frozen", "rlpt_frame_reset", "rlpt_frame_allreduce", "rlpt_frame_download", "rlpt_frame_download_argb", "rlpt_frame_save_bmp",
     "rlpt_stats", "rlpt_stats_reset", "rlpt_measure_fp32_peak", "rlpt_capture_rays",
     "rlpt_dqn_set_vertices", "rlpt_dqn_init", "rlpt_dqn_load_text", "rlpt_dqn_save_text", "rlpt_dqn_param_count", "rlpt_dqn_set_params", "rlpt_dqn_get_params",
-    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_train_supervised", "rlpt_render_voronoi", "rlpt_p2p_blob_bytes", "rlpt_p2p_export", "rlpt_p2p_import", "rlpt_dqn_get_grads", "rlpt_render_neuralq", "rlpt_neuralq_last_loss",
+    "rlpt_dqn_forward", "rlpt_render_pretrained", "rlpt_dqn_train_batch", "rlpt_dqn_train_supervised", "rlpt_render_voronoi", "rlpt_p2p_blob_bytes", "rlpt_p2p_export", "rlpt_p2p_import", "rlpt_p2p_close", "rlpt_dqn_get_grads", "rlpt_render_neuralq", "rlpt_neuralq_last_loss",
 ]
 
 _lib = None
@@ -145,6 +145,9 @@ class Context:
         """blobs: the p2p_export() results of all ranks in rank order"""
         data = b"".join(blobs)
         self._ck(self.L.rlpt_p2p_import(self.h, data, len(blobs)))
+
+    def p2p_close(self):
+        self._ck(self.L.rlpt_p2p_close(self.h))
 
     # ---- scene / camera
     def scene_upload(self, sv, srgb, lv, lrgb):

@@ -45,9 +45,29 @@ def host_allreduce_hook(group=None):
 
 def p2p_setup(ctx, group=None):
     """Peer-memory exchange for the ranks of one node (Context.p2p_export / p2p_import): gathers every rank's CUDA IPC
-    handles with torch.distributed and opens them. After this the per-frame Q exchange needs no collective call."""
+    handles with torch.distributed and opens them. After this the per-frame Q exchange needs no collective call.
+    All ranks agree on the outcome: if any rank cannot open its peers' buffers, every rank stays on the all-reduce hook.
+    Returns True when the peer-memory exchange is active."""
+    import torch
     import torch.distributed as dist
+    ok = 1
+    try:
+        blob = ctx.p2p_export()
+    except Exception as e:  # noqa: BLE001
+        print("rlpt p2p export failed:", e); blob = None; ok = 0
     blobs = [None] * dist.get_world_size(group)
-    dist.all_gather_object(blobs, ctx.p2p_export(), group=group)
-    ctx.p2p_import(blobs)
+    dist.all_gather_object(blobs, blob, group=group)
+    if ok and all(b is not None for b in blobs):
+        try:
+            ctx.p2p_import(blobs)
+        except Exception as e:  # noqa: BLE001
+            print("rlpt p2p import failed:", e); ok = 0
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        ctx.p2p_close()
+        return False
     dist.barrier(group=group)
+    return True
