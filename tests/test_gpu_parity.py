@@ -321,6 +321,31 @@ def test_sarsa_learns_and_stays_finite(ctx, golden_scenes):
     assert np.isfinite(img).all() and img.mean() > 0.05
 
 
+def test_q_table_file_round_trip(ctx, golden_scenes, tmp_path):
+    """RadianceMap::save_q_vals_to_file (G/radiance_volumes/radiance_map.cu:237-268): "144", then per volume
+    "px py pz q0 .. q143" as ofstream prints floats (6 significant digits); and the loader the reference lacks:
+    a trained table written and read back renders like the table it came from."""
+    s = golden_scenes["cornell"]
+    ctx.configure(width=64, height=64, spp=8)
+    load_scene(ctx, s); nv = ctx.radiance_map_build(); ctx.camera_set((0, 0, -3))
+    ctx.render_sarsa(3)
+    before = ctx.radiance_map_download()
+    path = str(tmp_path / "radiance_map_data.txt")
+    ctx.radiance_map_save_q(path)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "144" and len([l for l in lines[1:] if l]) == nv
+    row = np.array(lines[1].split(), np.float64)
+    assert len(row) == 3 + 144 and np.allclose(row[:3], before["pos"][0], rtol=1e-5) and np.allclose(row[3:], before["q"][0], rtol=1e-5)
+    ctx.radiance_map_build()                                       # fresh table (Q = 100/144 everywhere)
+    assert not np.allclose(ctx.radiance_map_download()["q"], before["q"])
+    ctx.radiance_map_load_q(path)
+    after = ctx.radiance_map_download()
+    assert np.allclose(after["q"], before["q"], rtol=1e-5, atol=1e-9)           # %g keeps 6 digits
+    assert np.abs(after["cdf"] - before["cdf"]).max() <= 1e-4                    # CDFs rebuilt from the loaded table
+    with pytest.raises(Exception):
+        ctx.radiance_map_load_q(str(tmp_path / "missing.txt"))
+
+
 def test_voronoi_view(ctx, oracle, golden_scenes):
     """draw_voronoi_trace (G/path_tracing/voronoi_trace.cu:4-45): every surface pixel carries the colour of its nearest radiance
     volume. Pixels of one colour must be one volume's cell: the colour is looked up again through find_closest on the hit
