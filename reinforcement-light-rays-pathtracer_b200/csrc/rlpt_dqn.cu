@@ -538,12 +538,6 @@ __global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __r
     i -= DQ_H2;
     if (i < DQ_H3) gb3[i] = dw3x[(size_t)i * DQ_K3 + DQ_H2];
 }
-__global__ void k_sqnorm(const float* __restrict__ g, int n, float* __restrict__ out) {
-    float acc = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += g[i] * g[i];
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
-}
 // Adam as DyNet's AdamTrainer applies it: gradient scaled by min(1, clip / ||g||), m and v updated, step size
 // lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
 // The step counter lives on the device (scalars[3], advanced once per step by k_adam_tick, which also derives the bias-corrected
@@ -552,18 +546,6 @@ __global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, 
     const float t = scalars[3] + 1.f; scalars[3] = t;
     scalars[2] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
 }
-__global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n, const float* __restrict__ scalars,
-                       float clip, float beta1, float beta2, float eps) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float step_size = scalars[2];
-    const float norm = sqrtf(scalars[1]); const float scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
-    const float gi = g[i] * scale;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi, vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    x[i] -= step_size * mi / (sqrtf(vi) + eps);
-}
-
 // The eight parameter arrays (W1 b1 .. W4 b4) are separate allocations; the per-step element-wise passes run over all of them
 // in ONE launch each (segment table passed by value) instead of eight: the optimiser step is a chain of ~40 tiny kernels and
 // every node costs a few microseconds of dependency latency.
