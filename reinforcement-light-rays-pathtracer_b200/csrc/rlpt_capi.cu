@@ -243,7 +243,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
     }
     // scan units of the conservative pre-test (rlpt_device.cuh, unit_candidates): parallelogram pairs, then single triangles
     cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
-    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
+    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.n_items = 0; sc.bundle = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
     if (sc.brute && n_tri <= 64 && !getenv("RLPT_NO_UNITS")) {
         std::vector<float> verts(c->h_surf_v); verts.insert(verts.end(), c->h_light_v.begin(), c->h_light_v.end());
         HostScanUnits hu; host_build_scan_units(verts.data(), n_tri, hu);
@@ -252,7 +252,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
             CK(cudaMalloc(&c->d_scan, sizeof(float) * hu.scan.size())); CK(cudaMalloc(&c->d_scan_gid, sizeof(int) * hu.slot_gid.size()));
             CK(cudaMemcpy(c->d_scan, hu.scan.data(), sizeof(float) * hu.scan.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c->d_scan_gid, hu.slot_gid.data(), sizeof(int) * hu.slot_gid.size(), cudaMemcpyHostToDevice));
-            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs;
+            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs; sc.n_items = hu.n_items; sc.bundle = getenv("RLPT_NO_BUNDLE") ? 0 : 1;
             sc.k1 = hu.k1; sc.k2 = hu.k2; sc.k3 = hu.k3; sc.vmax = hu.vmax;
             c->smem_bytes = scene_smem_bytes(sc);
         }

@@ -28,7 +28,7 @@ struct SceneDev {
     // parallelogram are tested together, 4 float4 per pair: (v0, e1.x) (e1.yz, e2.xy) (e2.z, n) (pu, pv, ps, -) with n = e1 x e2
     // and (pu, pv, ps) placing the second triangle in the first one's (u, v). slot_gid[slot] = primitive id: slots 2u, 2u+1 are
     // pair u, the unpaired primitives follow (n_tri slots in all, padded to a multiple of 4).
-    const float4* scan; const int* slot_gid; int n_units;
+    const float4* scan; const int* slot_gid; int n_units; int n_items; int bundle;     // bundle: camera rays are pre-tested once per warp (closest_hit_bundle)   // n_items >= n_units records: the unpaired triangles follow the pairs (bundle pre-test)
     float k1, k2, k3, vmax;   // error-bound coefficients of the pre-test (host: choose_traversal), largest |vertex coordinate|
     int det_small;      // 1 when SCREEN_HEIGHT * max |e1| |e2| < 2^23: no determinant of this scene can reach the range where tri_candidate's sign test needs its guard
 };

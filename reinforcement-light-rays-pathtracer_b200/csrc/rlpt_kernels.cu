@@ -26,7 +26,7 @@ template <bool STAGED>
 struct SceneView {
     const float4* tri_s; const float4* shade_s; const float4* nodes_s; const float4* scan_s; const int* gid_s;
     const float4* tri_g; const float4* shade_g; const float4* nodes_g;
-    int n_tri, n_surf, smem_nodes, brute, det_small, n_units;
+    int n_tri, n_surf, smem_nodes, brute, det_small, n_units, n_items;
     float k1, k2, k3, vmax;
     __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
     __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
@@ -41,7 +41,7 @@ template <bool STAGED, bool SHADE = true>
 __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     SceneView<STAGED> v;
     v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute; v.det_small = sc.det_small;
-    v.n_units = sc.n_units; v.k1 = sc.k1; v.k2 = sc.k2; v.k3 = sc.k3; v.vmax = sc.vmax;
+    v.n_units = sc.n_units; v.n_items = sc.n_items; v.k1 = sc.k1; v.k2 = sc.k2; v.k3 = sc.k3; v.vmax = sc.vmax;
     float4* p = s_scene;
     int nt = 3 * sc.smem_tris, ns = (SHADE && sc.smem_shade) ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
     v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
@@ -49,7 +49,7 @@ __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
     for (int i = threadIdx.x; i < nn; i += blockDim.x) p[nt + ns + i] = __ldg(sc.bvh + i);
     // brute-force scenes: the parallelogram units of the conservative pre-test (4 float4 each), then the slot -> primitive table
-    const int nu = 4 * sc.n_units, ng = sc.n_units > 0 ? (sc.n_tri + 3) / 4 : 0;
+    const int nu = 4 * sc.n_items, ng = sc.n_units > 0 ? (sc.n_tri + 3) / 4 : 0;
     v.scan_s = p + nt + ns + nn; v.gid_s = reinterpret_cast<const int*>(p + nt + ns + nn + nu);
     for (int i = threadIdx.x; i < nu; i += blockDim.x) p[nt + ns + nn + i] = __ldg(sc.scan + i);
     for (int i = threadIdx.x; i < ng; i += blockDim.x) p[nt + ns + nn + nu + i] = __ldg(reinterpret_cast<const float4*>(sc.slot_gid) + i);
@@ -58,7 +58,7 @@ __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
 }
 
 size_t scene_smem_bytes(const SceneDev& sc) {
-    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes + (size_t)4 * sc.n_units + (sc.n_units > 0 ? (size_t)(sc.n_tri + 3) / 4 : 0));
+    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes + (size_t)4 * sc.n_items + (sc.n_units > 0 ? (size_t)(sc.n_tri + 3) / 4 : 0));
 }
 
 // ------------------------------------------------------------------------------------------------ closest hit
@@ -225,6 +225,56 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
     while (bvh_visit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, ix, iy, iz, best_t, best_gid, cur, top, stack, n_tri, n_box)) {}
 }
 
+// Closest hit for a warp of CAMERA rays: same origin, directions within a pixel or two. Phase 1 is done once per warp instead
+// of once per ray: lane j pre-tests scan record j (a parallelogram pair or a single triangle, <= 32 records) against the
+// warp's central ray, with the thresholds of unit_candidates widened by how far any lane's direction is from the central one
+// -- with a common origin b = o - v0 is shared and Cramer's numerators are LINEAR in a:  D = a . n,  Y = a . (b x e2),
+// Z = a . (e1 x b),  so |D(a) - D(ac)| <= sum_i rho_i |n_i| etc. with rho_i = max over lanes |a_i - ac_i|. The ballots of the
+// lanes' verdicts are the warp's candidate list, and phase 2 (the exact solve) runs on it in lockstep.
+template <bool STAGED>
+__device__ __forceinline__ void closest_hit_bundle(const SceneView<STAGED>& v, bool valid, float ox, float oy, float oz, float dx, float dy, float dz, float H,
+                                                   float& best_t, int& best_gid, unsigned& n_tri) {
+    const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
+    const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
+    best_t = T_MISS; best_gid = -1;
+    const int src = __ffs(__ballot_sync(full, valid)) - 1;                     // a lane that holds a ray (callers pass whole warps with >= 1 ray)
+    const float c0 = __shfl_sync(full, a0, src), c1 = __shfl_sync(full, a1, src), c2 = __shfl_sync(full, a2, src);
+    const float r0 = __uint_as_float(__reduce_max_sync(full, __float_as_uint(valid ? fabsf(a0 - c0) : 0.f)));   // non-negative floats order like their bits
+    const float r1 = __uint_as_float(__reduce_max_sync(full, __float_as_uint(valid ? fabsf(a1 - c1) : 0.f)));
+    const float r2 = __uint_as_float(__reduce_max_sync(full, __float_as_uint(valid ? fabsf(a2 - c2) : 0.f)));
+    bool candA = false, candB = false;
+    if ((int)lane < v.n_items) {
+        const float4 q0 = v.scan_s[4 * lane], q1 = v.scan_s[4 * lane + 1], q2 = v.scan_s[4 * lane + 2], q3 = v.scan_s[4 * lane + 3];
+        const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x, nx = q2.y, ny = q2.z, nz = q2.w;
+        const float bx = ox - q0.x, by = oy - q0.y, bz = oz - q0.z;
+        const float yx = by * e2z - bz * e2y, yy = bz * e2x - bx * e2z, yz = bx * e2y - by * e2x;        // b x e2
+        const float zx = e1y * bz - e1z * by, zy = e1z * bx - e1x * bz, zz = e1x * by - e1y * bx;        // e1 x b
+        const float D = c0 * nx + c1 * ny + c2 * nz, X = bx * nx + by * ny + bz * nz;
+        const float Y = c0 * yx + c1 * yy + c2 * yz, Z = c0 * zx + c1 * zy + c2 * zz;
+        const float eD = r0 * fabsf(nx) + r1 * fabsf(ny) + r2 * fabsf(nz);
+        const float eY = r0 * fabsf(yx) + r1 * fabsf(yy) + r2 * fabsf(yz), eZ = r0 * fabsf(zx) + r1 * fabsf(zy) + r2 * fabsf(zz);
+        const float A_ = fmaxf(fabsf(c0) + r0, fmaxf(fabsf(c1) + r1, fabsf(c2) + r2));
+        const float Bm = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + v.vmax;
+        const float del = A_ * (v.k1 * Bm + v.k2), delx = v.k3 * Bm, lim = 3.f * del;
+        const float Ds = fabsf(D), Xs = D < 0.f ? -X : X, Ys = D < 0.f ? -Y : Y, Zs = D < 0.f ? -Z : Z, S = Ys + Zs;
+        const bool unsure = !(Ds > del + eD), front = Xs >= -delx;
+        const bool inA = Ys >= -(lim + eY) && Zs >= -(lim + eZ) && S <= Ds + (lim + eY + eZ + eD);
+        const bool inB = Ys <= q3.x * Ds + (lim + eY + eD) && Zs <= q3.y * Ds + (lim + eZ + eD) && S >= q3.z * Ds - (lim + eY + eZ + eD);
+        candA = unsure || (front && inA);
+        candB = (int)lane < v.n_units && (unsure || (front && inB));
+    }
+    unsigned mA = __ballot_sync(full, candA), mB = __ballot_sync(full, candB);
+    n_tri += (unsigned)v.n_tri;
+    while (mA | mB) {
+        int gid;
+        if (mA) { const int j = __ffs(mA) - 1; mA &= mA - 1u; gid = j < v.n_units ? v.gid_s[2 * j] : v.gid_s[v.n_units + j]; }     // singles: slot 2 n_units + (j - n_units)
+        else { const int j = __ffs(mB) - 1; mB &= mB - 1u; gid = v.gid_s[2 * j + 1]; }
+        TriRec r = load_tri(v, gid); float t;
+        if (valid && tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+    }
+}
+
 template <bool STAGED, bool COUNT>
 __global__ void __launch_bounds__(BLOCK) k_closest_hit(SceneDev sc, const float* __restrict__ org, const float* __restrict__ dir, int n, float H,
                                                        int* __restrict__ type, int* __restrict__ index, float* __restrict__ t_out,
@@ -341,6 +391,7 @@ __device__ __forceinline__ void td_accumulate(const RadianceDev& rm, bool active
 #ifndef RLPT_ISECT_MINBLOCKS
 #define RLPT_ISECT_MINBLOCKS 6
 #endif
+
 
 struct PathState {
     float ox, oy, oz, dx, dy, dz, tr, tg, tb, cur_brdf;
@@ -543,6 +594,24 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
     const PathQueue qi = p.q[bounce & 1];
     unsigned n_tri = 0, n_box = 0;
     const float H = (float)p.height;
+    if (PRIMARY && v.brute && p.scene.bundle && v.n_items > 0 && v.n_items <= 32) {
+        // camera rays: one pre-test per warp (closest_hit_bundle); whole warps stay together for its collectives
+        const int n_round = (sq.n + 31) & ~31;
+        for (int i = sq.first; i < n_round; i += sq.stride) {
+            const bool valid = i < sq.n;
+            PathState s{}; if (valid) primary_state(p, dyn, sq.base + i, s);
+            const float cx = dyn.cam_x, cy = dyn.cam_y, cz = dyn.cam_z;            // the shared origin (primary_state sets exactly this)
+            if (valid && dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
+                int slot = atomicAdd(p.capture_n, 1);
+                if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(cx, cy, cz, 0.f); p.capture_d[slot] = make_float4(s.dx, s.dy, s.dz, 0.f); }
+            }
+            float t; int gid;
+            closest_hit_bundle<STAGED>(v, valid, cx, cy, cz, s.dx, s.dy, s.dz, H, t, gid, n_tri);
+            if (valid) __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(gid)));
+        }
+        flush_work_counters(p, n_tri, n_box);
+        return;
+    }
     for (int i = sq.first; i < sq.n; i += sq.stride) {
         float ox, oy, oz, dx, dy, dz;
         if (PRIMARY) {

@@ -374,7 +374,17 @@ void host_build_scan_units(const float* verts, int n_tri, HostScanUnits& out) {
         out.slot_gid.push_back(i); out.slot_gid.push_back(partner[i]);
     }
     out.n_pairs = (int)(out.scan.size() / 16);
-    for (int i = 0; i < n_tri; ++i) if (!used[i]) out.slot_gid.push_back(i);
+    // the remaining triangles: their own slots, and records without a partner (used by the bundle pre-test of the primary rays)
+    for (int i = 0; i < n_tri; ++i) {
+        if (used[i]) continue;
+        out.slot_gid.push_back(i);
+        const float* v = vert(i);
+        const float e1[3] = { v[3] - v[0], v[4] - v[1], v[5] - v[2] }, e2[3] = { v[6] - v[0], v[7] - v[1], v[8] - v[2] };
+        const double n[3] = { (double)e1[1] * e2[2] - (double)e1[2] * e2[1], (double)e1[2] * e2[0] - (double)e1[0] * e2[2], (double)e1[0] * e2[1] - (double)e1[1] * e2[0] };
+        const float rec[16] = { v[0], v[1], v[2], e1[0], e1[1], e1[2], e2[0], e2[1], e2[2], (float)n[0], (float)n[1], (float)n[2], 0.f, 0.f, 0.f, 0.f };
+        out.scan.insert(out.scan.end(), rec, rec + 16);
+    }
+    out.n_items = (int)(out.scan.size() / 16);
     // error-bound coefficients of unit_candidates: del = A (k1 Bm + k2), delx = k3 Bm
     out.k1 = (float)(2e-5 * emax); out.k2 = (float)(2e-5 * emax * emax + 8.0 * tau * emax); out.k3 = (float)(4e-5 * emax * emax); out.vmax = (float)vmax;
 }

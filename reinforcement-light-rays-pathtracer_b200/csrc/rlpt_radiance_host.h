@@ -30,7 +30,8 @@ void host_build_vcells(const float* surface_v, const int* surface_class, int n_s
 
 // Scan units of the brute-force closest hit's conservative pre-test (rlpt_device.cuh, unit_candidates): pairs of primitives
 // that form a parallelogram (a triangle and the triangle that completes it across one of its edges). 16 floats per pair
-// (v0, e1, e2, n = e1 x e2, pu, pv, ps, 0); slot_gid = primitive id per scan slot: the pairs' two triangles, then the rest.
-struct HostScanUnits { std::vector<float> scan; std::vector<int> slot_gid; int n_pairs = 0; float k1 = 0.f, k2 = 0.f, k3 = 0.f, vmax = 0.f; };
+// (v0, e1, e2, n = e1 x e2, pu, pv, ps, 0), followed by one record per unpaired triangle (n_items records in all);
+// slot_gid = primitive id per scan slot: the pairs' two triangles, then the rest.
+struct HostScanUnits { std::vector<float> scan; std::vector<int> slot_gid; int n_pairs = 0, n_items = 0; float k1 = 0.f, k2 = 0.f, k3 = 0.f, vmax = 0.f; };
 void host_build_scan_units(const float* verts9, int n_primitives, HostScanUnits& out);
 }  // namespace rlpt

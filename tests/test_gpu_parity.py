@@ -243,6 +243,32 @@ def test_small_and_ragged_frames_match_oracle(ctx, oracle, golden_scenes, w, h, 
     _assert_images_close(img, oimg, frac=0.99, tol=5e-3, mean_tol=5e-3)
 
 
+def test_camera_ray_bundle_pretest_changes_no_hit(golden_scenes, monkeypatch):
+    """closest_hit_bundle pre-tests the camera rays once per warp (shared origin, thresholds widened by the warp's spread of
+    directions); the exact solve decides. With and without it the same paths must be traced: equal path-length and
+    zero-contribution totals, images equal up to the order of the frame-buffer additions. Cornell and door_room (all
+    primitives in parallelogram pairs), straight and rotated camera."""
+    import rlpt
+    for name, cam, yaw in (("cornell", (0, 0, -3), 0.0), ("cornell", (0.3, -0.2, -2.5), 0.35), ("door_room", (0, 0.5, -0.9), 0.0)):
+        out = []
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("RLPT_NO_BUNDLE", "1")
+            else:
+                monkeypatch.delenv("RLPT_NO_BUNDLE", raising=False)
+            c = rlpt.Context(0, width=256, height=192, spp=4, max_bounces=80)
+            try:
+                load_scene(c, golden_scenes[name]); c.camera_set(cam, yaw_y=yaw, yaw_x=-yaw / 2)
+                c.render_default(2)
+                st = c.stats(); out.append((c.frame_download().copy(), st["path_length_sum"], st["zero_contribution_paths"], st["paths"]))
+            finally:
+                c.close()
+        monkeypatch.delenv("RLPT_NO_BUNDLE", raising=False)
+        (a, la, za, pa), (b, lb, zb, pb) = out
+        assert pa == pb == 256 * 192 * 4 * 2 and la == lb and za == zb, (name, la, lb)
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-7), name
+
+
 def test_sarsa_first_frame_accumulators_match_oracle(ctx, oracle, golden_scenes):
     """one training iteration from the initial table: same paths => same (volume, sector) visit counts"""
     s = golden_scenes["cornell"]
