@@ -15,6 +15,8 @@
 #include <vector>
 #include <queue>
 #include <cfloat>
+#include <cstring>
+#include <cstdlib>
 
 namespace rlpt {
 
@@ -106,6 +108,142 @@ __global__ void k_fit(const Box* __restrict__ prim_boxes, const int* __restrict_
         p = parent[p];
     }
 }
+// ---- top-down binned SAH build, one CTA (scenes up to SAH_MAX_PRIMS primitives; the LBVH above serves the rest).
+// The Morton-order tree costs a ray of Medieval_House 23 node visits and 7 triangle solves on average, and single rays
+// several hundred visits -- the dependent chain that sets the floor of every small launch. The surface-area heuristic
+// (16 centroid bins per axis, all three axes, one primitive per leaf as before) is the classic cure. Nodes are processed
+// breadth-first by the whole CTA: bounds -> binning with shared-memory atomics -> 45 candidate planes costed in parallel ->
+// stable partition of the index range with a block scan. Everything that decides a split is a set operation (min, max,
+// count), so the tree does not depend on thread scheduling. It writes the LBVH's intermediate form (left/right links with
+// leaves as (n-1) + position, node boxes), so numbering and k_emit are shared.
+constexpr int SAH_T = 1024, SAH_BINS = 16, SAH_MAX_DEPTH = 29, SAH_MAX_PRIMS = 1 << 17;
+struct SahItem { int b, e, depth; };
+__device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }       // order-preserving float -> int
+__device__ __forceinline__ float o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ int sah_bin(const Box& bx, int k, float cmin, float scale) {
+    const float c = 0.5f * (bx.lo[k] + bx.hi[k]);
+    return scale > 0.f ? min(SAH_BINS - 1, max(0, (int)((c - cmin) * scale))) : 0;
+}
+__device__ __forceinline__ int levels_for(int c) { return c <= 1 ? 0 : 32 - __clz(c - 1); }                        // internal levels a median build of c primitives needs
+__device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int t = s_warp[lane];
+        for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+        s_warp[lane] = t;
+    }
+    __syncthreads();
+    const int pre = (w > 0 ? s_warp[w - 1] : 0) + x - v;
+    total = s_warp[31];
+    __syncthreads();
+    return pre;
+}
+__global__ void __launch_bounds__(SAH_T) k_sah_build(const Box* __restrict__ boxes, int n, int* __restrict__ ids, int* __restrict__ tmp, SahItem* __restrict__ queue,
+                                                     int* __restrict__ left, int* __restrict__ right, Box* __restrict__ node_boxes, int* __restrict__ depth_out) {
+    __shared__ int s_cb[6], s_nb[6];
+    __shared__ int s_cnt[3][SAH_BINS], s_lo[3][SAH_BINS][3], s_hi[3][SAH_BINS][3];
+    __shared__ float s_cost[48];
+    __shared__ int s_axis, s_split, s_nl, s_next, s_maxd, s_warp[32];
+    const int tid = threadIdx.x;
+    for (int j = tid; j < n; j += SAH_T) ids[j] = j;
+    if (tid == 0) { queue[0] = SahItem{ 0, n, 1 }; s_next = 1; s_maxd = 1; }
+    __syncthreads();
+    for (int node = 0; node < n - 1; ++node) {
+        const SahItem it = queue[node];
+        const int b = it.b, e = it.e, c = e - b;
+        if (tid < 6) { s_cb[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000; s_nb[tid] = s_cb[tid]; }
+        for (int k = tid; k < 3 * SAH_BINS; k += SAH_T) {
+            (&s_cnt[0][0])[k] = 0;
+            for (int d = 0; d < 3; ++d) { (&s_lo[0][0][0])[3 * k + d] = 0x7fffffff; (&s_hi[0][0][0])[3 * k + d] = (int)0x80000000; }
+        }
+        __syncthreads();
+        for (int j = b + tid; j < e; j += SAH_T) {
+            const Box bx = boxes[ids[j]];
+            for (int k = 0; k < 3; ++k) {
+                const int cc = f2o(0.5f * (bx.lo[k] + bx.hi[k]));
+                atomicMin(&s_cb[k], cc); atomicMax(&s_cb[3 + k], cc);
+                atomicMin(&s_nb[k], f2o(bx.lo[k])); atomicMax(&s_nb[3 + k], f2o(bx.hi[k]));
+            }
+        }
+        __syncthreads();
+        float cmin[3], scale[3];
+        for (int k = 0; k < 3; ++k) {
+            const float lo = o2f(s_cb[k]), hi = o2f(s_cb[3 + k]);
+            cmin[k] = lo; scale[k] = hi > lo ? (float)SAH_BINS / (hi - lo) : 0.f;
+        }
+        if (tid == 0) { Box m; for (int k = 0; k < 3; ++k) { m.lo[k] = o2f(s_nb[k]); m.hi[k] = o2f(s_nb[3 + k]); } node_boxes[node] = m; }
+        for (int j = b + tid; j < e; j += SAH_T) {
+            const Box bx = boxes[ids[j]];
+            for (int k = 0; k < 3; ++k) {
+                const int bin = sah_bin(bx, k, cmin[k], scale[k]);
+                atomicAdd(&s_cnt[k][bin], 1);
+                for (int d = 0; d < 3; ++d) { atomicMin(&s_lo[k][bin][d], f2o(bx.lo[d])); atomicMax(&s_hi[k][bin][d], f2o(bx.hi[d])); }
+            }
+        }
+        __syncthreads();
+        if (tid < 3 * (SAH_BINS - 1)) {
+            const int k = tid / (SAH_BINS - 1), sp = tid % (SAH_BINS - 1);          // left = bins 0..sp, right = sp+1..
+            float cost = FLT_MAX;
+            if (scale[k] > 0.f) {
+                int nl = 0, nr = 0; float llo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, lhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX }, rlo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, rhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+                for (int q = 0; q < SAH_BINS; ++q) {
+                    const int cnt = s_cnt[k][q]; if (!cnt) continue;
+                    if (q <= sp) { nl += cnt; for (int d = 0; d < 3; ++d) { llo[d] = fminf(llo[d], o2f(s_lo[k][q][d])); lhi[d] = fmaxf(lhi[d], o2f(s_hi[k][q][d])); } }
+                    else { nr += cnt; for (int d = 0; d < 3; ++d) { rlo[d] = fminf(rlo[d], o2f(s_lo[k][q][d])); rhi[d] = fmaxf(rhi[d], o2f(s_hi[k][q][d])); } }
+                }
+                if (nl > 0 && nr > 0) {
+                    const float lx = lhi[0] - llo[0], ly = lhi[1] - llo[1], lz = lhi[2] - llo[2], rx = rhi[0] - rlo[0], ry = rhi[1] - rlo[1], rz = rhi[2] - rlo[2];
+                    cost = (lx * ly + ly * lz + lz * lx) * (float)nl + (rx * ry + ry * rz + rz * rx) * (float)nr;
+                }
+            }
+            s_cost[tid] = cost;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int best = -1; float bc = FLT_MAX;
+            if (it.depth + levels_for(c - 1) <= SAH_MAX_DEPTH)                       // otherwise halve: the stack of the traversal holds 32 entries
+                for (int q = 0; q < 3 * (SAH_BINS - 1); ++q) if (s_cost[q] < bc) { bc = s_cost[q]; best = q; }
+            if (best >= 0) {
+                s_axis = best / (SAH_BINS - 1); s_split = best % (SAH_BINS - 1);
+                int nl = 0; for (int q = 0; q <= s_split; ++q) nl += s_cnt[s_axis][q];
+                s_nl = nl;
+            } else { s_axis = -1; s_nl = c / 2; }
+        }
+        __syncthreads();
+        const int axis = s_axis, split = s_split, nl = s_nl;
+        if (axis >= 0) {
+            int lpos = b, rpos = b + nl;
+            for (int cs = b; cs < e; cs += SAH_T) {
+                const int j = cs + tid; const bool valid = j < e;
+                const int id = valid ? ids[j] : 0;
+                const bool pl = valid && sah_bin(boxes[id], axis, cmin[axis], scale[axis]) <= split;
+                int total; const int off = block_excl_scan(pl ? 1 : 0, s_warp, total);
+                if (valid) { if (pl) tmp[lpos + off] = id; else tmp[rpos + (tid - off)] = id; }
+                lpos += total; rpos += min(SAH_T, e - cs) - total;
+            }
+            __syncthreads();
+            for (int j = b + tid; j < e; j += SAH_T) ids[j] = tmp[j];
+        }
+        if (tid == 0) {
+            const int m = b + nl;
+            int links[2];
+            for (int side = 0; side < 2; ++side) {
+                const int lb = side ? m : b, le = side ? e : m;
+                if (le - lb == 1) links[side] = (n - 1) + lb;
+                else { const int id = s_next++; queue[id] = SahItem{ lb, le, it.depth + 1 }; links[side] = id; if (it.depth + 1 > s_maxd) s_maxd = it.depth + 1; }
+            }
+            left[node] = links[0]; right[node] = links[1];
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += SAH_T) node_boxes[(n - 1) + j] = boxes[ids[j]];
+    if (tid == 0) *depth_out = s_maxd;
+}
+
 // emit traversal nodes; `order[k]` = LBVH internal node placed at output slot k (breadth-first), `slot_of[i]` its inverse
 __global__ void k_emit(const Box* __restrict__ node_boxes, const int* __restrict__ ids, int n, const int* __restrict__ left, const int* __restrict__ right,
                        const int* __restrict__ order, const int* __restrict__ slot_of, float4* __restrict__ out) {
@@ -129,7 +267,7 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
     int rc = 0;
     Box *boxes = nullptr, *node_boxes = nullptr; float* scene = nullptr; uint64_t *keys = nullptr, *keys_s = nullptr; int *ids = nullptr, *ids_s = nullptr;
     int *left = nullptr, *right = nullptr, *parent = nullptr, *flags = nullptr, *order = nullptr, *slot_of = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
-    float4* out = nullptr;
+    float4* out = nullptr; SahItem* sah_queue = nullptr; int* sah_depth = nullptr; bool use_sah = false;
     const int T = 128;
     *d_bvh = nullptr; *n_nodes = 0; *depth = 0;
     if (n <= 0) return 0;
@@ -148,18 +286,27 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
         BVH_CK(cudaMalloc(&out, sizeof(float4) * 4)); BVH_CK(cudaMemcpy(out, h, sizeof h, cudaMemcpyHostToDevice));
         *d_bvh = out; out = nullptr; *n_nodes = 1; *depth = 1; goto done;
     }
-    BVH_CK(cudaMalloc(&keys, sizeof(uint64_t) * n)); BVH_CK(cudaMalloc(&keys_s, sizeof(uint64_t) * n));
     BVH_CK(cudaMalloc(&ids, sizeof(int) * n)); BVH_CK(cudaMalloc(&ids_s, sizeof(int) * n));
-    k_morton<<<(n + T - 1) / T, T, 0, s>>>(boxes, n, scene, keys, ids);
-    BVH_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
-    BVH_CK(cudaMalloc(&tmp, tmp_bytes));
-    BVH_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
     BVH_CK(cudaMalloc(&left, sizeof(int) * (n - 1))); BVH_CK(cudaMalloc(&right, sizeof(int) * (n - 1)));
-    BVH_CK(cudaMalloc(&parent, sizeof(int) * (2 * n - 1))); BVH_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
-    BVH_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), s));
     BVH_CK(cudaMalloc(&node_boxes, sizeof(Box) * (2 * n - 1)));
-    k_karras<<<(n - 1 + T - 1) / T, T, 0, s>>>(keys_s, n, left, right, parent);
-    k_fit<<<(n + T - 1) / T, T, 0, s>>>(boxes, ids_s, n, left, right, parent, node_boxes, flags);
+    {
+        const char* e = getenv("RLPT_BVH_BUILD");                    // "lbvh": the Morton-order build for every size (A/B runs)
+        use_sah = n <= SAH_MAX_PRIMS && !(e && !strcmp(e, "lbvh"));
+    }
+    if (use_sah) {
+        BVH_CK(cudaMalloc(&sah_queue, sizeof(SahItem) * (n - 1))); BVH_CK(cudaMalloc(&sah_depth, sizeof(int)));
+        k_sah_build<<<1, SAH_T, 0, s>>>(boxes, n, ids_s, ids, sah_queue, left, right, node_boxes, sah_depth);
+    } else {
+        BVH_CK(cudaMalloc(&keys, sizeof(uint64_t) * n)); BVH_CK(cudaMalloc(&keys_s, sizeof(uint64_t) * n));
+        k_morton<<<(n + T - 1) / T, T, 0, s>>>(boxes, n, scene, keys, ids);
+        BVH_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
+        BVH_CK(cudaMalloc(&tmp, tmp_bytes));
+        BVH_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
+        BVH_CK(cudaMalloc(&parent, sizeof(int) * (2 * n - 1))); BVH_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
+        BVH_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), s));
+        k_karras<<<(n - 1 + T - 1) / T, T, 0, s>>>(keys_s, n, left, right, parent);
+        k_fit<<<(n + T - 1) / T, T, 0, s>>>(boxes, ids_s, n, left, right, parent, node_boxes, flags);
+    }
     {
         // breadth-first numbering of the internal nodes (host walk over the n-1 child links; O(n), one-off)
         std::vector<int> hl(n - 1), hr(n - 1), ord, slot(n - 1, -1);
@@ -186,7 +333,7 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
     *d_bvh = out; out = nullptr; *n_nodes = n - 1;
 done:
     cudaFree(boxes); cudaFree(node_boxes); cudaFree(scene); cudaFree(keys); cudaFree(keys_s); cudaFree(ids); cudaFree(ids_s);
-    cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(flags); cudaFree(order); cudaFree(slot_of); cudaFree(tmp); cudaFree(out);
+    cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(flags); cudaFree(order); cudaFree(slot_of); cudaFree(tmp); cudaFree(out); cudaFree(sah_queue); cudaFree(sah_depth);
     return rc;
 }
 

@@ -185,7 +185,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     rlpt_config_default(&c->cfg);
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
     upload_cell_cos(cs);
-    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 1024);     // the kernels also hold a little static shared memory (compaction scratch)
+    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 8192);     // the kernels also hold static shared memory (compaction scratch; k_isect_bvh: leaf queues + per-lane results, 5 KB)
     if (!lim) lim = dqn_set_smem_limit();
     if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
     *out = c;
@@ -219,7 +219,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
     sc.brute = mode == RLPT_TRAVERSAL_BRUTE;
     // shared-memory budget: leave room for >= 2 CTAs per SM when the scene is small, otherwise take what one CTA can have
     size_t tri_b = (size_t)n_tri * 48, shade_b = (size_t)n_tri * 64, node_b = (size_t)sc.n_nodes * 64;
-    size_t budget = optin > 4096 ? optin - 2048 : optin;
+    size_t budget = optin > 16384 ? optin - 8192 : optin;
     if (tri_b + shade_b + node_b <= budget) { sc.smem_tris = n_tri; sc.smem_shade = 1; sc.smem_nodes = sc.n_nodes; }
     else {
         sc.smem_tris = 0; sc.smem_shade = 0;

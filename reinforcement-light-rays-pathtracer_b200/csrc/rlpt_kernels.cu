@@ -110,6 +110,29 @@ __device__ __forceinline__ bool bvh_visit(const SceneView<STAGED>& v, float ox, 
     return true;
 }
 
+// The same visit with the leaf children handed back instead of solved (k_isect_bvh queues them for the whole warp).
+template <bool STAGED, bool COUNT>
+__device__ __forceinline__ bool bvh_visit_defer(const SceneView<STAGED>& v, float ox, float oy, float oz, float ix, float iy, float iz,
+                                                float best_t, int& cur, int& top, int* stack, int& pend0, int& pend1, unsigned& n_box) {
+    float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
+    float tn0, tf0, tn1, tf1;
+    slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
+    slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
+    if (COUNT) n_box += 2;
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
+    pend0 = (h0 && c0 < 0) ? ~c0 : -1; pend1 = (h1 && c1 < 0) ? ~c1 : -1;
+    h0 = h0 && c0 >= 0; h1 = h1 && c1 >= 0;
+    if (h0 && h1) {
+        bool swap = tn1 < tn0;
+        if (top < 32) stack[top++] = swap ? c0 : c1;
+        cur = swap ? c1 : c0;
+    } else if (h0) cur = c0;
+    else if (h1) cur = c1;
+    else { if (top == 0) return false; cur = stack[--top]; }
+    return true;
+}
+
 // Closest hit of one ray: Ray::closest_intersection (G/rays/ray.cu:16-36). (dx,dy,dz) is the normalised direction;
 // H = SCREEN_HEIGHT. Result: best_t in the reference's units and the primitive id (-1 = NOTHING). The winner is the
 // lexicographic minimum of (t, gid), which is what the reference's scan order with strict < produces.
@@ -644,51 +667,116 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 #define RLPT_BVH_REFILL 8
 #endif
 constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
+// Leaf triangles are not solved where they are found: a visit with a leaf hit in 2 or 3 of its 32 lanes made the whole warp
+// walk the exact solve (about as long as the box tests) at 1-3 active lanes -- 45 % of the kernel's issue slots. Instead each
+// leaf hit goes into a per-warp queue in shared memory as (owner lane, primitive); when 32 entries are there the warp solves
+// them at full width: lane j takes entry j, fetches the owner's ray with shuffles, and merges an accepted hit into the owner's
+// result with a 64-bit atomicMin in shared memory on  bits(|t|) << 32 | primitive << 1 | (t is -0)  -- the lexicographic
+// minimum of (t, primitive id), which is the reference's scan order with strict <, so the order of the solves is free.
+// A ray's best_t is refreshed after every solve round; between rounds the descent prunes with a stale (larger) bound, which
+// only costs box tests. A lane whose traversal is finished keeps its ray until its queued entries are solved ("draining");
+// the queue is emptied whenever the warp is about to refill idle lanes.
+constexpr int WQ_CAP = 96;                                             // < 32 left over + at most 64 new entries per visit
+constexpr unsigned long long KEY_MISS = ((unsigned long long)0x497423F0u << 32) | 0xffffffffull;    // bits(999999.f), primitive -1
+static_assert(BLOCK % 32 == 0, "whole warps");
+__device__ __forceinline__ unsigned long long hit_key(float t, int gid) {
+    const unsigned tb = __float_as_uint(t);
+    return ((unsigned long long)(tb & 0x7fffffffu) << 32) | (unsigned long long)(((unsigned)gid << 1) | (tb >> 31));
+}
+template <bool STAGED>
+__device__ __forceinline__ void wq_solve(const SceneView<STAGED>& v, const unsigned* wq, unsigned long long* best, int lo, int n, unsigned lane,
+                                         float ox, float oy, float oz, float a0, float a1, float a2, float& best_t, int& first_pos, unsigned& n_tri) {
+    const unsigned full = 0xffffffffu;
+    const bool mine = (int)lane < n;
+    const unsigned e = mine ? wq[lo + lane] : (lane << 27);
+    const int src = (int)(e >> 27), gid = (int)(e & 0x7ffffffu);
+    const float sox = __shfl_sync(full, ox, src), soy = __shfl_sync(full, oy, src), soz = __shfl_sync(full, oz, src);
+    const float sa0 = __shfl_sync(full, a0, src), sa1 = __shfl_sync(full, a1, src), sa2 = __shfl_sync(full, a2, src);
+    const float sbt = __shfl_sync(full, best_t, src);
+    if (mine) {
+        TriRec r = load_tri(v, gid); float t;
+        n_tri++;
+        if (tri_solve(r, sox, soy, soz, sa0, sa1, sa2, sbt, t) && t < T_MISS) atomicMin(best + src, hit_key(t, gid));
+    }
+    __syncwarp();
+    if (first_pos >= lo) first_pos = 0x7fffffff;                        // everything of mine at or above lo has been solved
+    best_t = __uint_as_float((unsigned)(best[lane] >> 32));
+}
 template <bool STAGED, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    __shared__ unsigned s_wq[(BLOCK / 32) * WQ_CAP];
+    __shared__ unsigned long long s_best[BLOCK];
     const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
     if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
     SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
     const PathQueue qi = p.q[bounce & 1];
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+    unsigned* wq = s_wq + (threadIdx.x >> 5) * WQ_CAP;
+    unsigned long long* best = s_best + (threadIdx.x & ~31u);
     int* cursor = p.cursor + (bounce * NSUB + (int)(blockIdx.x % NSUB)) * COUNT_STRIDE;
     unsigned n_tri = 0, n_box = 0;
     const float H = (float)p.height;
-    bool have = false, exhausted = false;
-    int i = 0, cur = 0, top = 0, best_gid = -1; float best_t = T_MISS;
+    bool have = false, drain = false, exhausted = false;
+    int i = 0, cur = 0, top = 0, count = 0, first_pos = 0x7fffffff; float best_t = T_MISS;
     float ox = 0, oy = 0, oz = 0, a0 = 0, a1 = 0, a2 = 0, ix = 0, iy = 0, iz = 0;
     int stack[32];
+    auto finish = [&]() {                                               // the ray's result: (t, primitive) from the merged key
+        const unsigned long long k = best[lane];
+        const unsigned lo = (unsigned)k;
+        const float t = __uint_as_float((unsigned)(k >> 32) | (lo == 0xffffffffu ? 0u : (lo & 1u) << 31));
+        __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(lo == 0xffffffffu ? -1 : (int)(lo >> 1))));
+    };
     while (true) {
-        const unsigned idle = __ballot_sync(full, !have);
-        if (!exhausted && (idle == full || __popc(idle) >= BVH_REFILL)) {
-            const int leader = __ffs(idle) - 1; int base = 0;
-            if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
-            base = __shfl_sync(full, base, leader);
-            exhausted = base + __popc(idle) >= sq.n;
-            if (!have) {
-                i = base + __popc(idle & lanemask_lt());
-                if (i < sq.n) {
-                    float dx, dy, dz;
-                    if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
-                    else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
-                    if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
-                        int slot = atomicAdd(p.capture_n, 1);
-                        if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+        const unsigned idle = __ballot_sync(full, !have);               // idle or draining
+        if (idle == full || __popc(idle) >= BVH_REFILL) {
+            while (count > 0) {                                         // empty the queue: draining lanes become idle
+                const int n = count < 32 ? count : 32;
+                count -= n;
+                wq_solve<STAGED>(v, wq, best, count, n, lane, ox, oy, oz, a0, a1, a2, best_t, first_pos, n_tri);
+            }
+            if (drain) { finish(); drain = false; }
+            if (!exhausted) {
+                const int leader = __ffs(idle) - 1; int base = 0;
+                if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
+                base = __shfl_sync(full, base, leader);
+                exhausted = base + __popc(idle) >= sq.n;
+                if (!have) {
+                    i = base + __popc(idle & lanemask_lt());
+                    if (i < sq.n) {
+                        float dx, dy, dz;
+                        if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
+                        else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
+                        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
+                            int slot = atomicAdd(p.capture_n, 1);
+                            if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+                        }
+                        const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
+                        a0 = RLPT_SUB(0.f, sdx); a1 = RLPT_SUB(0.f, sdy); a2 = RLPT_SUB(0.f, sdz);
+                        ix = 1.f / sdx; iy = 1.f / sdy; iz = 1.f / sdz;
+                        best_t = T_MISS; best[lane] = KEY_MISS; cur = 0; top = 0; have = true;
                     }
-                    const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
-                    a0 = RLPT_SUB(0.f, sdx); a1 = RLPT_SUB(0.f, sdy); a2 = RLPT_SUB(0.f, sdz);
-                    ix = 1.f / sdx; iy = 1.f / sdy; iz = 1.f / sdz;
-                    best_t = T_MISS; best_gid = -1; cur = 0; top = 0; have = true;
                 }
+                __syncwarp();
             }
         }
-        if (!__any_sync(full, have)) break;
+        if (!__any_sync(full, have)) break;                             // nothing traversing: the queue is empty here too
 #pragma unroll 1
         for (int step = 0; step < BVH_BATCH; ++step) {
-            if (have && !bvh_visit<STAGED, true>(v, ox, oy, oz, a0, a1, a2, ix, iy, iz, best_t, best_gid, cur, top, stack, n_tri, n_box)) {
-                __stcs(p.hit + sq.base + i, make_float2(best_t, __int_as_float(best_gid)));
-                have = false;
+            int pend0 = -1, pend1 = -1;
+            if (have && !bvh_visit_defer<STAGED, true>(v, ox, oy, oz, ix, iy, iz, best_t, cur, top, stack, pend0, pend1, n_box)) { have = false; drain = true; }
+            const unsigned m0 = __ballot_sync(full, pend0 >= 0), m1 = __ballot_sync(full, pend1 >= 0);
+            if (m0 | m1) {
+                const int pos0 = count + __popc(m0 & lanemask_lt()), pos1 = count + __popc(m0) + __popc(m1 & lanemask_lt());
+                if (pend0 >= 0) { wq[pos0] = (lane << 27) | (unsigned)pend0; first_pos = min(first_pos, pos0); }
+                if (pend1 >= 0) { wq[pos1] = (lane << 27) | (unsigned)pend1; first_pos = min(first_pos, pos1); }
+                count += __popc(m0) + __popc(m1);
+                __syncwarp();
+                while (count >= 32) {
+                    count -= 32;
+                    wq_solve<STAGED>(v, wq, best, count, 32, lane, ox, oy, oz, a0, a1, a2, best_t, first_pos, n_tri);
+                }
             }
+            if (drain && first_pos == 0x7fffffff) { finish(); drain = false; }
         }
     }
     flush_work_counters(p, n_tri, n_box);
