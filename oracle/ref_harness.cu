@@ -231,6 +231,24 @@ int ref_scene_arrays(const float* sv, const float* srgb, int ns, const float* lv
     h.surfaces = S.data(); h.area_lights = L.data(); h.vertices = V.data();
     return adopt_scene(h);
 }
+/* RadianceVolume::read_radiance_volumes_to_surfaces (G/radiance_volumes/radiance_volume.cu:499-510): saved radiance volumes as
+ * hemisphere geometry, the RENDER_SAVED_RADIANCE_VOLUMES path of Scene::load_custom_scene. Returns the surface count. */
+int ref_saved_volumes_to_surfaces(const char* path, int max_surfaces, float* sv, float* srgb, float* snrm) {
+#ifdef RLPT_REF_HOST
+    std::vector<Surface> S;
+    RadianceVolume::read_radiance_volumes_to_surfaces(std::string(path), S);
+    for (int i = 0; i < (int)S.size() && i < max_surfaces; ++i) {
+        Surface& s = S[i];
+        float v[9] = { s.v0.x, s.v0.y, s.v0.z, s.v1.x, s.v1.y, s.v1.z, s.v2.x, s.v2.y, s.v2.z };
+        memcpy(sv + 9 * i, v, sizeof v);
+        srgb[3 * i] = s.material.diffuse_c.x; srgb[3 * i + 1] = s.material.diffuse_c.y; srgb[3 * i + 2] = s.material.diffuse_c.z;
+        snrm[3 * i] = s.normal.x; snrm[3 * i + 1] = s.normal.y; snrm[3 * i + 2] = s.normal.z;
+    }
+    return (int)S.size();
+#else
+    return -1;
+#endif
+}
 int ref_scene_counts(int* ns, int* nl) { if (!g_scene) return 1; *ns = g_scene->surfaces_count; *nl = g_scene->area_light_count; return 0; }
 int ref_scene_get(float* sv, float* srgb, float* snrm, float* slum, float* lv, float* lrgb, float* lnrm, float* llum) {
     if (!g_scene) return 1;

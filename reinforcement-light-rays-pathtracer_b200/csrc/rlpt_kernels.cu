@@ -31,8 +31,7 @@ struct SceneView {
     __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
     __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
     __device__ __forceinline__ float4 node(int i) const {
-        if (STAGED) return nodes_s[i];
-        return i < smem_nodes ? nodes_s[i] : __ldg(nodes_g + i);
+        return STAGED ? nodes_s[i] : __ldg(nodes_g + i);       // a tree that does not fit is served by L1: staging its top costs a compare-and-select per load (-5 %)
     }
 };
 

@@ -183,9 +183,10 @@ void Scene::adopt(std::vector<Surface>& s, std::vector<AreaLight>& l, std::vecto
     std::copy(s.begin(), s.end(), surfaces); std::copy(l.begin(), l.end(), area_lights); std::copy(v.begin(), v.end(), vertices);
 }
 void Scene::load_cornell_box_scene() { std::vector<Surface> s; std::vector<AreaLight> l; std::vector<float> v; get_cornell_shapes(s, l, v); adopt(s, l, v); }
-bool Scene::load_custom_scene(const char* filename, bool lights_in_obj, const ImportPreset& preset) {
+bool Scene::load_custom_scene(const char* filename, bool lights_in_obj, const ImportPreset& preset, const char* saved_radiance_volumes) {
     std::vector<Surface> s; std::vector<AreaLight> l; std::vector<float> v;
     bool ok = load_scene(filename, s, l, v, lights_in_obj, preset);
+    if (saved_radiance_volumes) read_radiance_volumes_to_surfaces(saved_radiance_volumes, s);      // RENDER_SAVED_RADIANCE_VOLUMES (scene.cu:41-46); `vertices` stays the .obj's
     adopt(s, l, v);
     return ok;
 }
@@ -306,6 +307,95 @@ void RadianceMap::save_selected_radiance_volumes_vals(std::string fpath) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ saved radiance volumes as geometry
+// Shirley-Chiu concentric map of the unit square onto the hemisphere around +y (hemisphere_helpers.cu:134-226). The square is
+// cut into eight wedges by the axes and diagonals of (2x-1, 2y-1); wedge k starts at azimuth k pi/4, `r` is the distance from
+// the centre in the wedge's leading coordinate, `s` runs across the wedge. cos(theta) = 1 - r^2. Intermediate types follow the
+// reference: the wedge's start angle is a float, the azimuth is summed in double and rounded once.
+void map(float x, float y, float& x_ret, float& y_ret, float& z_ret) {
+    const float u = 2 * x - 1, v = 2 * y - 1;
+    int wedge; float r, s;
+    if (v > -u) {
+        if (v < u) { r = u; if (v > 0) { wedge = 0; s = v; } else { wedge = 7; s = u + v; } }
+        else       { r = v; if (u > 0) { wedge = 1; s = v - u; } else { wedge = 2; s = -u; } }
+    } else {
+        if (v > u) { r = -u; if (v > 0) { wedge = 3; s = -u - v; } else { wedge = 4; s = -v; } }
+        else {
+            r = -v;
+            if (u > 0) { wedge = 6; s = u; }
+            else if (v != 0) { wedge = 5; s = u - v; }
+            else { x_ret = 0.f; y_ret = 1.f; z_ret = 0.f; return; }             // the centre of the square: straight up
+        }
+    }
+    const float start = (float)((wedge * M_PI) / 4);
+    const float theta = std::acos(1 - r * r);
+    const float phi = (float)(start + (M_PI / 4) * (s / r));
+    x_ret = std::sin(theta) * std::cos(phi);
+    y_ret = std::cos(theta);
+    z_ret = std::sin(theta) * std::sin(phi);
+}
+// create_normal_coordinate_system (hemisphere_helpers.cu:31-44)
+static void normal_frame(vec3 n, vec3& t, vec3& b) {
+    t = std::fabs(n.x) > std::fabs(n.y) ? vec3(n.z, 0.f, -n.x) : vec3(0.f, -n.z, n.y);
+    const float inv = 1.f / std::sqrt((t.x * t.x + t.y * t.y) + t.z * t.z);
+    t = vec3(t.x * inv, t.y * inv, t.z * inv);
+    b = vec3(n.y * t.z - t.y * n.z, n.z * t.x - t.z * n.x, n.x * t.y - t.x * n.y);           // cross(n, t)
+}
+std::vector<std::vector<vec4>> SavedRadianceVolume::get_vertices() const {
+    const float kDiameter = 0.15f;                                                 // DIAMETER, radiance_volumes_settings.h:11
+    vec3 t, b; normal_frame(normal, t, b);
+    // the volume's local -> world matrix has columns (T, N, B, position) (create_transformation_matrix, hemisphere_helpers.cu:48-63);
+    // a mat4 * vec4 product sums its columns pairwise: (c0 x + c1 y) + (c2 z + c3 w)
+    std::vector<std::vector<vec4>> grid(RLPT_GRID_RESOLUTION + 1, std::vector<vec4>(RLPT_GRID_RESOLUTION + 1));
+    for (int gx = 0; gx <= RLPT_GRID_RESOLUTION; ++gx)
+        for (int gy = 0; gy <= RLPT_GRID_RESOLUTION; ++gy) {
+            float hx, hy, hz; map(gx / (float)RLPT_GRID_RESOLUTION, gy / (float)RLPT_GRID_RESOLUTION, hx, hy, hz);
+            hx *= kDiameter; hy *= kDiameter; hz *= kDiameter;
+            grid[gx][gy] = vec4((t.x * hx + normal.x * hy) + (b.x * hz + position.x * 1.f), (t.y * hx + normal.y * hy) + (b.y * hz + position.y * 1.f),
+                                (t.z * hx + normal.z * hy) + (b.z * hz + position.z * 1.f), (0.f * hx + 0.f * hy) + (0.f * hz + 1.f * 1.f));
+        }
+    return grid;
+}
+void SavedRadianceVolume::build_surfaces(std::vector<Surface>& surfaces) const {
+    float top = 0.f;
+    for (int k = 0; k < RLPT_GRID_CELLS; ++k) if (top < radiance_distribution[k]) top = radiance_distribution[k];
+    const std::vector<std::vector<vec4>> g = get_vertices();
+    for (int gx = 0; gx < RLPT_GRID_RESOLUTION; ++gx)
+        for (int gy = 0; gy < RLPT_GRID_RESOLUTION; ++gy) {
+            const vec4 a = g[gx][gy], bq = g[gx + 1][gy], c = g[gx][gy + 1], d = g[gx + 1][gy + 1];
+            const vec4 mid(((a.x + bq.x) + c.x + d.x) / 4.f, ((a.y + bq.y) + c.y + d.y) / 4.f, ((a.z + bq.z) + c.z + d.z) / 4.f, ((a.w + bq.w) + c.w + d.w) / 4.f);
+            const float ratio = radiance_distribution[gx * RLPT_GRID_RESOLUTION + gy] / top;
+            const Material colour(vec3(ratio, 1.f - ratio, 0.f));
+            // both triangles of the quad face away from the volume's centre: normalize(mid - position) as a vec4 (w = 0)
+            const float nx = mid.x - position.x, ny = mid.y - position.y, nz = mid.z - position.z, nw = mid.w - position.w;
+            const float inv = 1.f / std::sqrt(((nx * nx + ny * ny) + nz * nz) + nw * nw);
+            Surface s1(a, c, bq, colour), s2(bq, c, d, colour);
+            s1.normal = s2.normal = vec4(nx * inv, ny * inv, nz * inv, nw * inv);
+            surfaces.push_back(s1); surfaces.push_back(s2);
+        }
+}
+bool read_radiance_volumes_from_file(const std::string& fname, std::vector<SavedRadianceVolume>& rvs) {
+    std::ifstream in(fname);
+    if (!in.is_open()) { printf("Could not read radiance volumes.\n"); return false; }
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ss(line); std::string tok; std::vector<float> val;
+        while (std::getline(ss, tok, ' ')) if (!tok.empty()) val.push_back(std::stof(tok));
+        if (val.size() < 6 + (size_t)RLPT_GRID_CELLS) continue;                  // ragged line: skipped (the reference reads past the end of its vector)
+        SavedRadianceVolume rv;
+        rv.position = vec4(val[0], val[1], val[2], 1.f); rv.normal = vec3(val[3], val[4], val[5]);
+        for (int k = 0; k < RLPT_GRID_CELLS; ++k) rv.radiance_distribution[k] = val[6 + k];
+        rvs.push_back(rv);
+    }
+    return true;
+}
+bool read_radiance_volumes_to_surfaces(const std::string& fname, std::vector<Surface>& surfaces) {
+    std::vector<SavedRadianceVolume> rvs;
+    if (!read_radiance_volumes_from_file(fname, rvs)) return false;
+    for (const SavedRadianceVolume& rv : rvs) rv.build_surfaces(surfaces);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ Neural-Q drivers
 static void upload_with_vertices(Renderer& r, const Scene& scene) {
     r.upload(scene);
@@ -375,4 +465,17 @@ extern "C" int rlpt_host_load_scene(const char* obj_path_or_null, int lights_in_
     }
     if (vertices) std::copy(s.vertices, s.vertices + s.vertices_count, vertices);
     return 0;
+}
+extern "C" int rlpt_host_saved_volumes_to_surfaces(const char* path, int max_surfaces, float* sv, float* srgb, float* snrm) {
+    using namespace rlpt_host;
+    std::vector<Surface> S;
+    if (!read_radiance_volumes_to_surfaces(path, S)) return -1;
+    for (int i = 0; i < (int)S.size() && i < max_surfaces; ++i) {
+        const Surface& s = S[i];
+        const float v[9] = { s.v0.x, s.v0.y, s.v0.z, s.v1.x, s.v1.y, s.v1.z, s.v2.x, s.v2.y, s.v2.z };
+        memcpy(sv + 9 * i, v, sizeof v);
+        srgb[3 * i] = s.material.diffuse_c.x; srgb[3 * i + 1] = s.material.diffuse_c.y; srgb[3 * i + 2] = s.material.diffuse_c.z;
+        snrm[3 * i] = s.normal.x; snrm[3 * i + 1] = s.normal.y; snrm[3 * i + 2] = s.normal.z;
+    }
+    return (int)S.size();
 }

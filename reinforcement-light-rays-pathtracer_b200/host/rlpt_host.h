@@ -49,7 +49,8 @@ public:
     ~Scene();
     Scene(const Scene&) = delete; Scene& operator=(const Scene&) = delete;
     void load_cornell_box_scene();                                               // G/scenes/scene.cu:8-30
-    bool load_custom_scene(const char* filename, bool lights_in_obj, const ImportPreset& preset = ImportPreset::committed());   // :33-60
+    bool load_custom_scene(const char* filename, bool lights_in_obj, const ImportPreset& preset = ImportPreset::committed(),
+                           const char* saved_radiance_volumes = nullptr /* RENDER_SAVED_RADIANCE_VOLUMES: file whose volumes are appended as geometry, :41-46 */);   // :33-60
     void save_vertices_to_file(const char* path = "../Radiance_Map_Data/vertices.txt") const;   // :63-88
 private:
     void adopt(std::vector<Surface>& s, std::vector<AreaLight>& l, std::vector<float>& v);
@@ -134,6 +135,18 @@ public:
                          const char* model = "../Radiance_Map_Data/deep_q_learning_12_12.model", const char* image = "../Images/render.bmp");
     bool rendered = false;
 };
+// Saved radiance volumes drawn as geometry (RENDER_SAVED_RADIANCE_VOLUMES, G/constants/image_settings.h:15, G/scenes/scene.cu:41-46):
+// each volume of a selected_*.txt file becomes a hemisphere of 12x12 quads (two Surfaces each) of diameter DIAMETER, coloured
+// from green to red by its distribution value relative to the volume's maximum.
+struct SavedRadianceVolume {
+    vec4 position; vec3 normal; float radiance_distribution[RLPT_GRID_CELLS];
+    std::vector<std::vector<vec4>> get_vertices() const;                 // G/radiance_volumes/radiance_volume.cu:441-463
+    void build_surfaces(std::vector<Surface>& surfaces) const;           // :467-496
+};
+bool read_radiance_volumes_from_file(const std::string& fname, std::vector<SavedRadianceVolume>& rvs);       // :377-437 ("px py pz nx ny nz d0 .. d143" per line)
+bool read_radiance_volumes_to_surfaces(const std::string& fname, std::vector<Surface>& surfaces);            // :499-515
+// Shirley-Chiu square -> unit hemisphere (y up), G/utils/hemisphere_helpers.cu:134-226
+void map(float x, float y, float& x_ret, float& y_ret, float& z_ret);
 // G/utils/hemisphere_helpers.cu:230-281: "px py pz nx ny nz" per line
 bool read_hemisphere_locations_and_normals(const std::string& path, std::vector<vec3>& locations, std::vector<vec3>& normals);
 

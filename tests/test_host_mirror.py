@@ -70,3 +70,32 @@ def test_presets_and_errors(tmp_path):
     obj.write_text("o thing\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\n\nvt 0 0\ns off\nf 1/1/1 2/2/1 3/3/1 4/4/1\nf 1 2 3\nf 1 2 9\n")
     t = load(str(obj), False, preset=2)
     assert len(t["sv"]) == 3
+
+
+def saved_volume_surfaces(path, n_max=4096):
+    if not os.path.exists(LIB):
+        pytest.skip("librlpt_host.so not built")
+    L = ctypes.CDLL(LIB)
+    sv, rgb, nrm = np.zeros((n_max, 9), np.float32), np.zeros((n_max, 3), np.float32), np.zeros((n_max, 3), np.float32)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    n = L.rlpt_host_saved_volumes_to_surfaces(str(path).encode(), n_max, ptr(sv), ptr(rgb), ptr(nrm))
+    return n, sv[:max(n, 0)], rgb[:max(n, 0)], nrm[:max(n, 0)]
+
+
+def test_saved_radiance_volumes_as_geometry_match_reference(tmp_path):
+    """SURVEY 8f.4: RadianceVolume::read_radiance_volumes_to_surfaces (radiance_volume.cu:377-515: reader, get_vertices,
+    build_surfaces) in the host mirror against the reference's own output on its committed selected_sarsa.txt, bit for bit."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "saved_volumes.npz"))
+    f = tmp_path / "selected.txt"
+    f.write_bytes(g["text"].tobytes())
+    n, sv, rgb, nrm = saved_volume_surfaces(f)
+    assert n == len(g["sv"]) == 3 * 288                      # 12 x 12 quads x 2 triangles per volume
+    assert same(sv, g["sv"]) and same(rgb, g["rgb"]) and same(nrm, g["nrm"])
+    # the hemisphere has diameter 0.15 around the volume, colours run green -> red with the distribution value
+    first = np.array(f.read_text().splitlines()[0].split()[:3], np.float32)
+    assert np.all(np.linalg.norm(sv[:288].reshape(-1, 3) - first, axis=1) <= 0.15 * 1.0001)
+    assert np.allclose(rgb[:, 0] + rgb[:, 1], 1.0, atol=1e-6) and np.all(rgb[:, 2] == 0) and rgb[:, 0].max() == 1.0
+    # a missing file reports failure (the reference prints and carries on); ragged lines are skipped
+    assert saved_volume_surfaces(tmp_path / "nope.txt")[0] == -1
+    (tmp_path / "ragged.txt").write_text("0 0 0 0 1 0 0.5 0.5\n" + f.read_text().splitlines()[1] + "\n")
+    assert saved_volume_surfaces(tmp_path / "ragged.txt")[0] == 288
