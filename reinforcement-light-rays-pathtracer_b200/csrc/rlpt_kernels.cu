@@ -132,6 +132,54 @@ __device__ __forceinline__ bool bvh_visit_defer(const SceneView<STAGED>& v, floa
     return true;
 }
 
+// Phase 1 of the brute-force scan over the scan units (parallelogram pairs, then single triangles): the slots no early out can
+// reject, as a bit mask in SLOT order (slot -> primitive through gid_s). Branch-free over the whole scene.
+template <bool STAGED>
+__device__ __forceinline__ unsigned long long unit_scan_mask(const SceneView<STAGED>& v, float ox, float oy, float oz, float a0, float a1, float a2) {
+    const float A_ = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
+    const float Bm = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + v.vmax;
+    const float del = A_ * (v.k1 * Bm + v.k2), kx = (3.f * del) / (v.k3 * Bm);
+    unsigned long long mask = 0ull;
+    int u = 0;
+    for (; u + 2 <= v.n_units; u += 2) {
+        unsigned bits = 0u;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4 q0 = v.scan_s[4 * (u + k)], q1 = v.scan_s[4 * (u + k) + 1], q2 = v.scan_s[4 * (u + k) + 2], q3 = v.scan_s[4 * (u + k) + 3];
+            const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
+            bits |= unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * k);
+        }
+        mask |= (unsigned long long)bits << (2 * u);
+    }
+    for (; u < v.n_units; ++u) {
+        const float4 q0 = v.scan_s[4 * u], q1 = v.scan_s[4 * u + 1], q2 = v.scan_s[4 * u + 2], q3 = v.scan_s[4 * u + 3];
+        const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
+        mask |= (unsigned long long)unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * u);
+    }
+    int slot = 2 * v.n_units;
+    if (v.det_small) {
+        for (; slot + 4 <= v.n_tri; slot += 4) {
+            unsigned bits = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                TriRec r = load_tri(v, v.gid_s[slot + k]);
+                if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) bits |= 1u << k;
+            }
+            mask |= (unsigned long long)bits << slot;
+        }
+        for (; slot < v.n_tri; ++slot) {
+            TriRec r = load_tri(v, v.gid_s[slot]);
+            if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
+        }
+    } else {
+        for (; slot < v.n_tri; ++slot) {
+            TriRec r = load_tri(v, v.gid_s[slot]);
+            if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
+        }
+    }
+    return mask;
+}
+
 // Closest hit of one ray: Ray::closest_intersection (G/rays/ray.cu:16-36). (dx,dy,dz) is the normalised direction;
 // H = SCREEN_HEIGHT. Result: best_t in the reference's units and the primitive id (-1 = NOTHING). The winner is the
 // lexicographic minimum of (t, gid), which is what the reference's scan order with strict < produces.
@@ -147,47 +195,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
             // pre-test for both, unit_candidates), then one slot per remaining triangle (tri_candidate). phase 2: the exact solve
             // of the marked slots; slots are not in primitive order, so ties go to the lower id explicitly (the reference's
             // scan order with strict <).
-            const float A_ = fmaxf(fabsf(a0), fmaxf(fabsf(a1), fabsf(a2)));
-            const float Bm = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) + v.vmax;
-            const float del = A_ * (v.k1 * Bm + v.k2), kx = (3.f * del) / (v.k3 * Bm);
-            unsigned long long mask = 0ull;
-            int u = 0;
-            for (; u + 2 <= v.n_units; u += 2) {
-                unsigned bits = 0u;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const float4 q0 = v.scan_s[4 * (u + k)], q1 = v.scan_s[4 * (u + k) + 1], q2 = v.scan_s[4 * (u + k) + 2], q3 = v.scan_s[4 * (u + k) + 3];
-                    const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
-                    bits |= unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * k);
-                }
-                mask |= (unsigned long long)bits << (2 * u);
-            }
-            for (; u < v.n_units; ++u) {
-                const float4 q0 = v.scan_s[4 * u], q1 = v.scan_s[4 * u + 1], q2 = v.scan_s[4 * u + 2], q3 = v.scan_s[4 * u + 3];
-                const UnitRec r{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z };
-                mask |= (unsigned long long)unit_candidates(r, ox, oy, oz, a0, a1, a2, del, kx) << (2 * u);
-            }
-            int slot = 2 * v.n_units;
-            if (v.det_small) {
-                for (; slot + 4 <= v.n_tri; slot += 4) {
-                    unsigned bits = 0u;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        TriRec r = load_tri(v, v.gid_s[slot + k]);
-                        if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) bits |= 1u << k;
-                    }
-                    mask |= (unsigned long long)bits << slot;
-                }
-                for (; slot < v.n_tri; ++slot) {
-                    TriRec r = load_tri(v, v.gid_s[slot]);
-                    if (tri_candidate_small(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
-                }
-            } else {
-                for (; slot < v.n_tri; ++slot) {
-                    TriRec r = load_tri(v, v.gid_s[slot]);
-                    if (tri_candidate(r, ox, oy, oz, a0, a1, a2)) mask |= 1ull << slot;
-                }
-            }
+            unsigned long long mask = unit_scan_mask<STAGED>(v, ox, oy, oz, a0, a1, a2);
             if (COUNT) n_tri += (unsigned)v.n_tri;
             while (mask) {
                 const int sl = __ffsll((long long)mask) - 1; mask &= mask - 1ull;
@@ -607,6 +615,16 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
     flush_work_counters(p, n_tri, n_box);
 }
 
+// (t, primitive) as one 64-bit key whose unsigned order is the lexicographic order of (|t|, primitive id): results of exact solves
+// done by any lane in any order merge with atomicMin, and the minimum is what the reference's scan order with strict < keeps.
+constexpr int BQ_CAP = 512;                                            // entries of the brute-force scan's per-warp candidate list
+constexpr unsigned long long KEY_MISS = ((unsigned long long)0x497423F0u << 32) | 0xffffffffull;    // bits(999999.f), primitive -1
+static_assert(BLOCK % 32 == 0, "whole warps");
+__device__ __forceinline__ unsigned long long hit_key(float t, int gid) {
+    const unsigned tb = __float_as_uint(t);
+    return ((unsigned long long)(tb & 0x7fffffffu) << 32) | (unsigned long long)(((unsigned)gid << 1) | (tb >> 31));
+}
+
 // Split, first half: the closest hit of every ray of queue `bounce` -> hit[slot] = (t, as_float(primitive id))
 template <bool STAGED, bool PRIMARY>
 __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
@@ -630,6 +648,74 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
             float t; int gid;
             closest_hit_bundle<STAGED>(v, valid, cx, cy, cz, s.dx, s.dy, s.dz, H, t, gid, n_tri);
             if (valid) __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(gid)));
+        }
+        flush_work_counters(p, n_tri, n_box);
+        return;
+    }
+    if (STAGED && v.brute && v.n_units > 0 && p.scene.warp_solve) {
+        // Scan units: phase 1 per ray as before, phase 2 (the exact solves) for the whole warp. A ray has 0..8 candidates, so
+        // solving them lane by lane runs the division path max-over-lanes times at about half the lanes. Instead the warp's
+        // candidates go into a shared-memory list as (owner lane, slot) -- lane-major, placed with a warp prefix sum -- and are
+        // solved 32 at a time: lane j takes entry j, fetches the owner's ray with shuffles and merges an accepted hit into the
+        // owner's 64-bit (t, primitive) key with atomicMin. The few entries beyond the list's capacity stay with their owner.
+        __shared__ unsigned short s_bq[(BLOCK / 32) * BQ_CAP];
+        __shared__ unsigned long long s_bbest[BLOCK];
+        const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
+        unsigned short* bq = s_bq + (threadIdx.x >> 5) * BQ_CAP;
+        unsigned long long* best = s_bbest + (threadIdx.x & ~31u);
+        const int n_round = (sq.n + 31) & ~31;
+        for (int i = sq.first; i < n_round; i += sq.stride) {
+            const bool valid = i < sq.n;
+            float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
+            if (valid) {
+                if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
+                else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
+                if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
+                    int slot = atomicAdd(p.capture_n, 1);
+                    if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+                }
+            }
+            const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
+            const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
+            unsigned long long m = valid ? unit_scan_mask<STAGED>(v, ox, oy, oz, a0, a1, a2) : 0ull;
+            if (valid) n_tri += (unsigned)v.n_tri;
+            best[lane] = KEY_MISS;
+            const int cnt = __popcll(m);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(full, incl, d); if ((int)lane >= d) incl += y; }
+            const int total = __shfl_sync(full, incl, 31), lim = total < BQ_CAP ? total : BQ_CAP;
+            int pos = incl - cnt;
+            while (m && pos < BQ_CAP) { const int sl = __ffsll((long long)m) - 1; m &= m - 1ull; bq[pos++] = (unsigned short)((lane << 6) | (unsigned)sl); }
+            __syncwarp();
+            for (int e0 = 0; e0 < lim; e0 += 32) {
+                const bool mine = e0 + (int)lane < lim;
+                const unsigned e = mine ? bq[e0 + lane] : (lane << 6);
+                const int src = (int)(e >> 6);
+                const float sox = __shfl_sync(full, ox, src), soy = __shfl_sync(full, oy, src), soz = __shfl_sync(full, oz, src);
+                const float sa0 = __shfl_sync(full, a0, src), sa1 = __shfl_sync(full, a1, src), sa2 = __shfl_sync(full, a2, src);
+                if (mine) {
+                    const int gid = v.gid_s[e & 63u];
+                    const float sbt = __uint_as_float((unsigned)(best[src] >> 32));
+                    TriRec r = load_tri(v, gid); float t;
+                    if (tri_solve(r, sox, soy, soz, sa0, sa1, sa2, sbt, t) && t < T_MISS) atomicMin(best + src, hit_key(t, gid));
+                }
+                __syncwarp();
+            }
+            while (m) {                                                                // beyond the list's capacity: the owner's own lane
+                const int sl = __ffsll((long long)m) - 1; m &= m - 1ull;
+                const int gid = v.gid_s[sl];
+                TriRec r = load_tri(v, gid); float t;
+                if (tri_solve(r, ox, oy, oz, a0, a1, a2, __uint_as_float((unsigned)(best[lane] >> 32)), t) && t < T_MISS) atomicMin(best + lane, hit_key(t, gid));
+            }
+            __syncwarp();
+            if (valid) {
+                const unsigned long long k = best[lane];
+                const unsigned lo = (unsigned)k;
+                const float t = __uint_as_float((unsigned)(k >> 32) | (lo == 0xffffffffu ? 0u : (lo & 1u) << 31));
+                __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(lo == 0xffffffffu ? -1 : (int)(lo >> 1))));
+            }
+            __syncwarp();
         }
         flush_work_counters(p, n_tri, n_box);
         return;
@@ -676,12 +762,6 @@ constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
 // only costs box tests. A lane whose traversal is finished keeps its ray until its queued entries are solved ("draining");
 // the queue is emptied whenever the warp is about to refill idle lanes.
 constexpr int WQ_CAP = 96;                                             // < 32 left over + at most 64 new entries per visit
-constexpr unsigned long long KEY_MISS = ((unsigned long long)0x497423F0u << 32) | 0xffffffffull;    // bits(999999.f), primitive -1
-static_assert(BLOCK % 32 == 0, "whole warps");
-__device__ __forceinline__ unsigned long long hit_key(float t, int gid) {
-    const unsigned tb = __float_as_uint(t);
-    return ((unsigned long long)(tb & 0x7fffffffu) << 32) | (unsigned long long)(((unsigned)gid << 1) | (tb >> 31));
-}
 template <bool STAGED>
 __device__ __forceinline__ void wq_solve(const SceneView<STAGED>& v, const unsigned* wq, unsigned long long* best, int lo, int n, unsigned lane,
                                          float ox, float oy, float oz, float a0, float a1, float a2, float& best_t, int& first_pos, unsigned& n_tri) {
