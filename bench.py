@@ -276,7 +276,8 @@ def main():
         flops = st["triangle_tests"] * F_TRI + st["box_tests"] * F_AABB
         split = st["isect_launches"] > 0
         # closest-hit kernel: k_isect when the split pipeline runs (its own event pairs), else the fused k_bounce (trace phase)
-        hit_s = max(st["isect_seconds"] if split else st["trace_seconds"], 1e-12)
+        # (per-kernel event pairs are taken on every fourth frame: a run of fewer than four steps has none and falls back to the trace phase)
+        hit_s = max(st["isect_seconds"] if (split and st["isect_seconds"] > 0) else st["trace_seconds"], 1e-12)
         hit_n = st["isect_launches"] if split else st["kernel_launches"] - (st["frames"] if method == 1 else 0)
         tail_flop_share = 0.0
         if split and st["tail_launches"] > 0:
@@ -337,7 +338,9 @@ def main():
         if method == 1 and st["merge_seconds"] > 0:
             merge_bytes = nv * 144 * 4 * 4.0                 # per frame: read Q + accumulator counts, write Q-derived CDF (+ sums/visits for touched cells): >= 4 arrays
             line["roofline_merge"] = {"kernel": "k_merge_cdf", "bound": "hbm", "achieved": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                      "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src}
+                                      "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                      "note": "duration = the merge phase of the frame on the context stream, during which the next frame's primary k_isect runs on purpose "
+                                              "(low-priority stream); k_merge_cdf alone takes 40-48 us per launch = 1.2-1.4 TB/s (profiles/r1_launches_cornell_sarsa.csv)"}
         if world == 1 and not args.no_cpu_baseline:
             v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}

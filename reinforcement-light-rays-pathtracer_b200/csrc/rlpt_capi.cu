@@ -4,6 +4,9 @@
 // GPU rlpt_ctx_create fails and nothing else can be called.
 #include "../../include/rlpt.h"
 #include "rlpt_internal.h"
+#ifndef RLPT_WARP_SOLVE_DEFAULT
+#define RLPT_WARP_SOLVE_DEFAULT 0      // k_isect: exact solves of the brute-force scan for the whole warp at once (RLPT_WARP_SOLVE=0/1 overrides)
+#endif
 #include "rlpt_radiance_host.h"
 #include "rlpt_dqn.h"
 
@@ -250,7 +253,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
             CK(cudaMalloc(&c->d_scan, sizeof(float) * hu.scan.size())); CK(cudaMalloc(&c->d_scan_gid, sizeof(int) * hu.slot_gid.size()));
             CK(cudaMemcpy(c->d_scan, hu.scan.data(), sizeof(float) * hu.scan.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c->d_scan_gid, hu.slot_gid.data(), sizeof(int) * hu.slot_gid.size(), cudaMemcpyHostToDevice));
-            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs; sc.n_items = hu.n_items; sc.bundle = getenv("RLPT_NO_BUNDLE") ? 0 : 1; sc.warp_solve = getenv("RLPT_NO_WARP_SOLVE") ? 0 : 1;
+            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs; sc.n_items = hu.n_items; sc.bundle = getenv("RLPT_NO_BUNDLE") ? 0 : 1; { const char* e = getenv("RLPT_WARP_SOLVE"); sc.warp_solve = e ? (atoi(e) != 0) : RLPT_WARP_SOLVE_DEFAULT; }
             sc.k1 = hu.k1; sc.k2 = hu.k2; sc.k3 = hu.k3; sc.vmax = hu.vmax;
             c->smem_bytes = scene_smem_bytes(sc);
         }

@@ -94,6 +94,31 @@ def test_bvh_is_built_on_device_and_encloses_scene(ctx, golden_scenes):
         assert np.all(nodes[is_leaf][:, list(a)] <= lo[gid]) and np.all(nodes[is_leaf][:, list(b)] >= hi[gid])
 
 
+def test_sah_and_lbvh_builds_agree_on_every_hit(golden_scenes, golden_hits, monkeypatch):
+    """Both GPU builders (binned SAH, the default up to 131072 primitives; Morton-order LBVH for larger scenes, forced here with
+    RLPT_BVH_BUILD=lbvh) produce valid trees with identical closest hits; the SAH tree needs fewer box tests."""
+    import rlpt
+    s = golden_scenes["Medieval_House"]
+    org, dir = golden_hits["Medieval_House"]["org"][:1 << 16], golden_hits["Medieval_House"]["dir"][:1 << 16]
+    out = {}
+    for build in ("sah", "lbvh"):
+        monkeypatch.setenv("RLPT_BVH_BUILD", build)
+        c = rlpt.Context(0)
+        try:
+            load_scene(c, s)
+            info = c.scene_info()
+            n = info["n_surfaces"] + info["n_lights"]
+            links = c.bvh_download()[:, 12:14].view(np.int32)
+            assert info["bvh_nodes"] == n - 1 and 2 <= info["bvh_depth"] <= 30
+            assert sorted((~links[links < 0]).tolist()) == list(range(n)) and sorted(links[links >= 0].tolist()) == list(range(1, n - 1))
+            out[build] = c.closest_hit(org, dir, traversal=1, count=True)
+        finally:
+            c.close()
+    (ty0, ix0, t0, cnt0), (ty1, ix1, t1, cnt1) = out["sah"], out["lbvh"]
+    assert np.array_equal(ty0, ty1) and np.array_equal(ix0, ix1) and np.array_equal(bits(t0), bits(t1))
+    assert cnt0[1] < cnt1[1]                                   # box tests
+
+
 def test_nearest_volume_bit_exact(ctx, oracle, golden_scenes, golden_rmap):
     s = golden_scenes["cornell"]
     load_scene(ctx, s); load_scene(oracle, s)
