@@ -4,9 +4,6 @@
 // GPU rlpt_ctx_create fails and nothing else can be called.
 #include "../../include/rlpt.h"
 #include "rlpt_internal.h"
-#ifndef RLPT_WARP_SOLVE_DEFAULT
-#define RLPT_WARP_SOLVE_DEFAULT 0      // k_isect: exact solves of the brute-force scan for the whole warp at once (RLPT_WARP_SOLVE=0/1 overrides)
-#endif
 #include "rlpt_radiance_host.h"
 #include "rlpt_dqn.h"
 
@@ -188,7 +185,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     rlpt_config_default(&c->cfg);
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
     upload_cell_cos(cs);
-    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 12288);    // the kernels also hold static shared memory (compaction scratch; k_isect_bvh: leaf queues + per-lane results, 5 KB; k_isect: candidate lists + results, 10 KB)
+    int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 12288);    // the kernels also hold static shared memory (compaction scratch; k_isect_bvh: leaf lists + per-lane results, 5 KB)
     if (!lim) lim = dqn_set_smem_limit();
     if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
     *out = c;
@@ -244,7 +241,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
     }
     // scan units of the conservative pre-test (rlpt_device.cuh, unit_candidates): parallelogram pairs, then single triangles
     cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
-    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.n_items = 0; sc.bundle = 0; sc.warp_solve = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
+    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.n_items = 0; sc.bundle = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
     if (sc.brute && n_tri <= 64 && !getenv("RLPT_NO_UNITS")) {
         std::vector<float> verts(c->h_surf_v); verts.insert(verts.end(), c->h_light_v.begin(), c->h_light_v.end());
         HostScanUnits hu; host_build_scan_units(verts.data(), n_tri, hu);
@@ -253,7 +250,7 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
             CK(cudaMalloc(&c->d_scan, sizeof(float) * hu.scan.size())); CK(cudaMalloc(&c->d_scan_gid, sizeof(int) * hu.slot_gid.size()));
             CK(cudaMemcpy(c->d_scan, hu.scan.data(), sizeof(float) * hu.scan.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c->d_scan_gid, hu.slot_gid.data(), sizeof(int) * hu.slot_gid.size(), cudaMemcpyHostToDevice));
-            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs; sc.n_items = hu.n_items; sc.bundle = getenv("RLPT_NO_BUNDLE") ? 0 : 1; { const char* e = getenv("RLPT_WARP_SOLVE"); sc.warp_solve = e ? (atoi(e) != 0) : RLPT_WARP_SOLVE_DEFAULT; }
+            sc.scan = reinterpret_cast<const float4*>(c->d_scan); sc.slot_gid = c->d_scan_gid; sc.n_units = hu.n_pairs; sc.n_items = hu.n_items; sc.bundle = getenv("RLPT_NO_BUNDLE") ? 0 : 1;
             sc.k1 = hu.k1; sc.k2 = hu.k2; sc.k3 = hu.k3; sc.vmax = hu.vmax;
             c->smem_bytes = scene_smem_bytes(sc);
         }

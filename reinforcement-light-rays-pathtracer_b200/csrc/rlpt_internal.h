@@ -30,7 +30,6 @@ struct SceneDev {
     // pair u, the unpaired primitives follow (n_tri slots in all, padded to a multiple of 4).
     const float4* scan; const int* slot_gid; int n_units; int n_items; int bundle;     // bundle: camera rays are pre-tested once per warp (closest_hit_bundle)   // n_items >= n_units records: the unpaired triangles follow the pairs (bundle pre-test)
     float k1, k2, k3, vmax;   // error-bound coefficients of the pre-test (host: choose_traversal), largest |vertex coordinate|
-    int warp_solve;     // 1: k_isect solves the scan's candidates for the whole warp at once (rlpt_kernels.cu, k_isect); RLPT_WARP_SOLVE=0/1
     int det_small;      // 1 when SCREEN_HEIGHT * max |e1| |e2| < 2^23: no determinant of this scene can reach the range where tri_candidate's sign test needs its guard
 };
 

@@ -617,7 +617,6 @@ __global__ void __launch_bounds__(BLOCK, RLPT_MINBLOCKS) k_bounce(const __grid_c
 
 // (t, primitive) as one 64-bit key whose unsigned order is the lexicographic order of (|t|, primitive id): results of exact solves
 // done by any lane in any order merge with atomicMin, and the minimum is what the reference's scan order with strict < keeps.
-constexpr int BQ_CAP = 512;                                            // entries of the brute-force scan's per-warp candidate list
 constexpr unsigned long long KEY_MISS = ((unsigned long long)0x497423F0u << 32) | 0xffffffffull;    // bits(999999.f), primitive -1
 static_assert(BLOCK % 32 == 0, "whole warps");
 __device__ __forceinline__ unsigned long long hit_key(float t, int gid) {
@@ -652,74 +651,11 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
         flush_work_counters(p, n_tri, n_box);
         return;
     }
-    if (STAGED && v.brute && v.n_units > 0 && p.scene.warp_solve) {
-        // Scan units: phase 1 per ray as before, phase 2 (the exact solves) for the whole warp. A ray has 0..8 candidates, so
-        // solving them lane by lane runs the division path max-over-lanes times at about half the lanes. Instead the warp's
-        // candidates go into a shared-memory list as (owner lane, slot) -- lane-major, placed with a warp prefix sum -- and are
-        // solved 32 at a time: lane j takes entry j, fetches the owner's ray with shuffles and merges an accepted hit into the
-        // owner's 64-bit (t, primitive) key with atomicMin. The few entries beyond the list's capacity stay with their owner.
-        __shared__ unsigned short s_bq[(BLOCK / 32) * BQ_CAP];
-        __shared__ unsigned long long s_bbest[BLOCK];
-        const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
-        unsigned short* bq = s_bq + (threadIdx.x >> 5) * BQ_CAP;
-        unsigned long long* best = s_bbest + (threadIdx.x & ~31u);
-        const int n_round = (sq.n + 31) & ~31;
-        for (int i = sq.first; i < n_round; i += sq.stride) {
-            const bool valid = i < sq.n;
-            float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
-            if (valid) {
-                if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
-                else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
-                if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
-                    int slot = atomicAdd(p.capture_n, 1);
-                    if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
-                }
-            }
-            const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
-            const float a0 = RLPT_SUB(0.f, sdx), a1 = RLPT_SUB(0.f, sdy), a2 = RLPT_SUB(0.f, sdz);
-            unsigned long long m = valid ? unit_scan_mask<STAGED>(v, ox, oy, oz, a0, a1, a2) : 0ull;
-            if (valid) n_tri += (unsigned)v.n_tri;
-            best[lane] = KEY_MISS;
-            const int cnt = __popcll(m);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(full, incl, d); if ((int)lane >= d) incl += y; }
-            const int total = __shfl_sync(full, incl, 31), lim = total < BQ_CAP ? total : BQ_CAP;
-            int pos = incl - cnt;
-            while (m && pos < BQ_CAP) { const int sl = __ffsll((long long)m) - 1; m &= m - 1ull; bq[pos++] = (unsigned short)((lane << 6) | (unsigned)sl); }
-            __syncwarp();
-            for (int e0 = 0; e0 < lim; e0 += 32) {
-                const bool mine = e0 + (int)lane < lim;
-                const unsigned e = mine ? bq[e0 + lane] : (lane << 6);
-                const int src = (int)(e >> 6);
-                const float sox = __shfl_sync(full, ox, src), soy = __shfl_sync(full, oy, src), soz = __shfl_sync(full, oz, src);
-                const float sa0 = __shfl_sync(full, a0, src), sa1 = __shfl_sync(full, a1, src), sa2 = __shfl_sync(full, a2, src);
-                if (mine) {
-                    const int gid = v.gid_s[e & 63u];
-                    const float sbt = __uint_as_float((unsigned)(best[src] >> 32));
-                    TriRec r = load_tri(v, gid); float t;
-                    if (tri_solve(r, sox, soy, soz, sa0, sa1, sa2, sbt, t) && t < T_MISS) atomicMin(best + src, hit_key(t, gid));
-                }
-                __syncwarp();
-            }
-            while (m) {                                                                // beyond the list's capacity: the owner's own lane
-                const int sl = __ffsll((long long)m) - 1; m &= m - 1ull;
-                const int gid = v.gid_s[sl];
-                TriRec r = load_tri(v, gid); float t;
-                if (tri_solve(r, ox, oy, oz, a0, a1, a2, __uint_as_float((unsigned)(best[lane] >> 32)), t) && t < T_MISS) atomicMin(best + lane, hit_key(t, gid));
-            }
-            __syncwarp();
-            if (valid) {
-                const unsigned long long k = best[lane];
-                const unsigned lo = (unsigned)k;
-                const float t = __uint_as_float((unsigned)(k >> 32) | (lo == 0xffffffffu ? 0u : (lo & 1u) << 31));
-                __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(lo == 0xffffffffu ? -1 : (int)(lo >> 1))));
-            }
-            __syncwarp();
-        }
-        flush_work_counters(p, n_tri, n_box);
-        return;
-    }
+    // (Tried and dropped: the exact solves of the scan's candidates for the whole warp at once -- candidates of all 32 rays in a
+    // shared-memory list placed by a warp prefix sum, solved 32 at a time with the owner's ray fetched by shuffles and merged by
+    // the 64-bit atomicMin k_isect_bvh uses. Bit-exact, lanes per instruction in phase 2 go from 15 to ~30, but the list
+    // bookkeeping, seven shuffles per entry, the compare-and-swap loop behind a 64-bit shared-memory atomicMin and the lost
+    // "farther than the current best" early-out cost more than the idle lanes did: 2175 -> 2097 Mpaths/s.)
     for (int i = sq.first; i < sq.n; i += sq.stride) {
         float ox, oy, oz, dx, dy, dz;
         if (PRIMARY) {

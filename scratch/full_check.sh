@@ -3,8 +3,6 @@
 # list + one --set full capture of the longest secondary k_isect_bvh launch (Medieval_House); everything lands in gpurun_out/
 T=${1:-x}
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_$T.log 2>&1; tail -3 gpurun_out/pytest_gpu_$T.log
-echo "with RLPT_WARP_SOLVE=1:"; RLPT_WARP_SOLVE=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_mape.py -x -q -m gpu > gpurun_out/pytest_gpu_${T}_ws.log 2>&1; tail -3 gpurun_out/pytest_gpu_${T}_ws.log
-REPS=2 bash scratch/ab.sh "RLPT_WARP_SOLVE=0" "RLPT_WARP_SOLVE=1" > gpurun_out/ab_ws_$T.log 2>&1; REPS=1 BENCH_ARGS="--workload door_room_sarsa" bash scratch/ab.sh "RLPT_WARP_SOLVE=0" "RLPT_WARP_SOLVE=1" >> gpurun_out/ab_ws_$T.log 2>&1; cat gpurun_out/ab_ws_$T.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_$T.log 2>&1; tail -1 gpurun_out/smoke_$T.log
 python bench.py --no-cpu-baseline > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err
 for w in medieval_default medieval_sarsa archway_sarsa door_room_sarsa cornell_sarsa cornell_default; do bash scratch/kstats.sh "A=1" --workload $w; done > gpurun_out/kstats_$T.log 2>&1; cat gpurun_out/kstats_$T.log
