@@ -377,6 +377,12 @@ void launch_find_closest(const RadianceDev& rm, const SceneDev&, const float* po
     k_find_closest<<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, s>>>(rm, pos, reinterpret_cast<const int*>(cls_as_float), n, out);
 }
 
+// "zero contribution" of the reference's statistics: mean(rgb) < THROUGHPUT_THRESHOLD = 0.0001 (G/main.cu:223-229). The division by
+// three sat in the divergent termination branch (2 % of k_shade's instructions for a counter); fl(x / 3) < 0.0001f holds exactly
+// for the floats x <= 0x1.3a92ap-12 (correctly rounded division is monotonic; the boundary was found by stepping through the
+// neighbouring floats), so the comparison is made on the sum. NaN compares false in both forms.
+__device__ __forceinline__ bool zero_contribution(float lr, float lg, float lb) { return (lr + lg + lb) <= 0x1.3a92ap-12f; }
+
 // ------------------------------------------------------------------------------------------------ warp helpers
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -515,7 +521,7 @@ __device__ __forceinline__ bool shade_step(const FrameParams& p, const FrameDyn&
         lr *= s.tr; lg *= s.tg; lb *= s.tb;
         if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + s.pixel, make_float4(lr, lg, lb, 0.f));
         st_len += (unsigned)bounce + 1u; st_term++;
-        if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;                                         // THROUGHPUT_THRESHOLD
+        if (zero_contribution(lr, lg, lb)) st_zero++;                                         // THROUGHPUT_THRESHOLD
         return false;
     }
     if (!surface) return false;
@@ -926,7 +932,7 @@ __global__ void __launch_bounds__(BLOCK) k_nq_trace(const __grid_constant__ Fram
             lr *= tr; lg *= tg; lb *= tb;
             if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + pixel, make_float4(lr, lg, lb, 0.f));
             st_len += (unsigned)bounce + 1u; st_term++;
-            if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;
+            if (zero_contribution(lr, lg, lb)) st_zero++;
         } else if (surface) {
             if (bounce + 1 >= p.max_bounces) { st_len += (unsigned)p.max_bounces; st_term++; st_zero++; }     // out of bounces: contributes nothing (DESIGN.md deviation 8)
             else {
@@ -1086,7 +1092,7 @@ __global__ void __launch_bounds__(BLOCK) k_nqt_trace(const __grid_constant__ Fra
                     st.thr[i] = make_float4(lr, lg, lb, 0.f);
                     if (lr != 0.f || lg != 0.f || lb != 0.f) atomicAdd(p.accum + i, make_float4(lr, lg, lb, 0.f));
                     st_len += (unsigned)bounce + 1u; st_term++;
-                    if ((lr + lg + lb) / 3.f < 0.0001f) st_zero++;
+                    if (zero_contribution(lr, lg, lb)) st_zero++;
                 }
                 st.state[i] = 1u;
             } else {                                                           // SURFACE

@@ -318,7 +318,7 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
             out.xtable[4 * (size_t)hs] = e.cell; out.xtable[4 * (size_t)hs + 1] = e.cls; out.xtable[4 * (size_t)hs + 2] = e.start; out.xtable[4 * (size_t)hs + 3] = e.n;
         }
     }
-    double fill = 2.0; if (const char* e = getenv("RLPT_VFILL")) fill = std::max(1.1, atof(e));
+    double fill = 3.0; if (const char* e = getenv("RLPT_VFILL")) fill = std::max(1.1, atof(e));
     size_t slots = 8; while ((double)slots < fill * (double)entries.size() + 2) slots <<= 1;
     out.table.assign(4 * slots, -1);
     const uint32_t mask = (uint32_t)(slots - 1);
