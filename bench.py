@@ -250,6 +250,8 @@ def main():
     # ---- e2e: the reference's per-frame protocol through the C ABI with host buffers
     pinned = torch.empty((args.width * args.height, 3), dtype=torch.float32, pin_memory=True)
     frame_np = pinned.numpy()
+    for _ in range(2):                                      # untimed: first use of the download path (staging buffers, page faults of the pinned block)
+        ctx.camera_set(cam); render(1); ctx.frame_download(frame_np); ctx.stats()
     barrier(); ctx.stats_reset()
     e0 = time.perf_counter()
     for _ in range(args.steps):
