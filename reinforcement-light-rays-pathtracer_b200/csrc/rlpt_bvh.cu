@@ -2,10 +2,12 @@
 // The reference has no acceleration structure (brute force over every Surface and AreaLight, G/rays/ray.cu:22-35);
 // this is new work asked for by BASELINE.json north_star.
 //
-// Linear BVH (Karras 2012): 30-bit Morton code of each primitive's centroid, radix sort (CUB), one thread per
-// internal node finds its range and split from the sorted keys, AABBs are fitted bottom-up with one atomic flag per
-// node, then nodes are emitted breadth-first in the traversal layout (so "the first K nodes" is the top of the tree,
-// which is what kernels stage in shared memory when the whole tree does not fit):
+// Two builders, both on the GPU, both emitting the same traversal layout:
+//   * top-down binned SAH by one CTA (k_sah_build, below) for scenes up to SAH_MAX_PRIMS primitives -- the trees the tracing
+//     kernels actually walk for the bundled scenes;
+//   * linear BVH (Karras 2012) above that: 30-bit Morton code of each primitive's centroid, radix sort (CUB), one thread per
+//     internal node finds its range and split from the sorted keys, AABBs fitted bottom-up with one atomic flag per node.
+// Nodes are emitted breadth-first:
 //   node = 4 x float4:  (c0.min.xyz, c0.max.x) (c0.max.yz, c1.min.xy) (c1.min.z, c1.max.xyz) (as_float(c0), as_float(c1), 0, 0)
 //   child link >= 0: node index;  < 0: ~primitive id (one primitive per leaf)
 // Leaf boxes are padded (kPad * primitive extent + kAbs) so that traversal can never cull a primitive that the

@@ -22,7 +22,7 @@ struct SceneDev {
     int n_tri, n_surf, n_light, n_nodes;
     int brute;          // 1: scan all primitives in gid order from shared memory; 0: BVH traversal
     int smem_tris;      // primitives staged in shared memory (all of them, or 0 when they do not fit)
-    int smem_nodes;     // BVH nodes staged in shared memory (BFS order, so this is the top of the tree)
+    int smem_nodes;     // BVH nodes staged in shared memory: all of them or none (a partly staged tree costs a compare-and-select per node load)
     int smem_shade;     // 1 when the shading records are staged too
     // conservative pre-test of the brute-force scan (rlpt_device.cuh, unit_candidates): pairs of triangles that form a
     // parallelogram are tested together, 4 float4 per pair: (v0, e1.x) (e1.yz, e2.xy) (e2.z, n) (pu, pv, ps, -) with n = e1 x e2

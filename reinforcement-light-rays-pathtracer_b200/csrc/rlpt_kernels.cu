@@ -5,7 +5,10 @@
 //  * per bounce two kernels: k_isect (closest hit only, 40 registers, issue-bound on the FP32 pipes) and k_shade (nearest
 //    radiance volume, TD target, direction sampling, compaction: latency-bound, no triangle data); the scene (SoA float4
 //    triangles, parallelogram scan units, BVH nodes) is staged in shared memory by every k_isect CTA with vectorised float4
-//    loads; B200 has no RT cores, traversal is FP32-pipe work
+//    loads when it fits (otherwise everything comes through the read-only path and L1); B200 has no RT cores, traversal is
+//    FP32-pipe work
+//  * scenes above 64 primitives go through the BVH (k_isect_bvh): lanes take a new ray from the sub-queue as theirs finishes,
+//    and leaf triangles are solved for the whole warp from a shared-memory list, merged by a 64-bit atomicMin on (t, primitive)
 //  * one resident wave per kernel; the live-path count of each bounce lives in device memory (counts[bounce][sub-queue]),
 //    so a frame is a launch sequence with no host round trip; once few paths are left one run-to-completion launch
 //    (k_bounce<TAIL>) finishes them
