@@ -12,9 +12,11 @@ CDFs. Default workload = BASELINE.json configs[1]: Cornell box 512x512, 12x12 ra
             render, frame-buffer download to pinned host memory and the statistics read-back, every step (G/main.cu:307-349)
   roofline  dominant kernel = the per-bounce tracing kernel (k_bounce): executed ray-triangle / ray-box tests (counted in
             the kernel) x 72 / 18 flop / its device time, against the FP32 FMA rate measured on this GPU
-  cpu_baseline / --impl reference   the reference's own sources compiled for the host (oracle/_ref/libref_host_spp2.so:
-            G/path_tracing/reinforcement_path_tracing.cu etc. behind oracle/host_shim, OpenMP over pixels), same scene and
-            method, a bounded sample (2 spp per frame: resolution and spp are compile-time constants in the reference)
+  cpu_baseline   BASELINE.json configs[0]: the reference's Old_CPU_Rendering_Engine (baseline/_ref/libcpu_engine_b*.so, built by
+            oracle/cpu_engine/build.sh), built-in Cornell box, default path tracer, 16 spp, all host cores (and 6 threads as hard-coded)
+  cpu_baseline_sarsa / --impl reference   this bench's own workload on the host: the reference's GPU engine sources compiled for
+            the host (oracle/_ref/libref_host.so: G/path_tracing/reinforcement_path_tracing.cu etc. behind oracle/host_shim, OpenMP
+            over pixels), same scene, method, resolution and 32 spp per frame, all host cores (set explicitly)
 
 N > 1 (torchrun): sample-partitioned, weak scaling -- every rank traces `spp` samples of every pixel per frame
 (global frame = N*spp samples, disjoint Philox sample indices), Q accumulators are all-reduced every frame (NCCL).
@@ -45,6 +47,11 @@ WORKLOADS = {
     # importer's commented normalisation (tests/golden/make_presets.py), lit by ENVIRONMENT_LIGHT = 1
     "medieval_default": ("medieval_norm", 0, (0.0, 0.0, -3.0), 1.0),
     "medieval_sarsa": ("medieval_norm", 1, (0.0, 0.0, -3.0), 1.0),
+    # the same mesh seen from INSIDE its main room (86 % of the directions from the camera hit a wall; found with the oracle's closest
+    # hit): paths bounce ~7 times before they leave through a window, so the BVH is walked by incoherent secondary rays
+    "medieval_inside_default": ("medieval_norm", 0, (0.2, 0.3, -0.5), 1.0),
+    "medieval_inside_sarsa": ("medieval_norm", 1, (0.2, 0.3, -0.5), 1.0),
+    "complex_light_room_default": ("complex_light_room", 0, (0.0, 0.0, -0.9), 0.0),
 }
 
 
@@ -113,17 +120,29 @@ class c_stdout_to_stderr:
         os.close(self.saved)
 
 
-def cpu_reference_run(frames, warmup, want_seconds=None):
+def set_host_threads(n):
+    """OpenMP team size of the CPU arms, set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank."""
+    import ctypes
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def cpu_reference_run(frames, warmup, want_seconds=None, spp=32):
     """The reference's SARSA frame loop on the host cores. Returns (Mpaths/s, kind, cores, sample, ms_per_step)."""
     with c_stdout_to_stderr():
-        return _cpu_reference_run(frames, warmup, want_seconds)
+        return _cpu_reference_run(frames, warmup, want_seconds, spp)
 
 
-def _cpu_reference_run(frames, warmup, want_seconds=None):
+def _cpu_reference_run(frames, warmup, want_seconds=None, spp=32):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from checkers import Oracle, Reference
-    if Reference.available("host", "_spp2"):
-        R = Reference("host", "_spp2")
+    set_host_threads(os.cpu_count() or 1)
+    suffix = "" if spp == 32 else "_spp%d" % spp             # oracle/build_ref.sh: libref_host.so is the 512 x 512 x 32 spp build
+    if Reference.available("host", suffix):
+        R = Reference("host", suffix)
         R.scene_cornell(); R.camera(0.0, 0.0, -3.0)
         R.rmap_build()
         for _ in range(warmup):
@@ -135,13 +154,13 @@ def _cpu_reference_run(frames, warmup, want_seconds=None):
                 break
         dt = time.perf_counter() - t0
         paths = done * R.width * R.height * R.spp
-        sample = "%d frames x %d spp, Cornell %dx%d, Expected SARSA, after %d warm-up frames (%.2f M paths); unmodified reference sources built for the host with g++ -O2 -fopenmp" % (
-            done, R.spp, R.width, R.height, warmup, paths / 1e6)
+        sample = "%d frames x %d spp, Cornell %dx%d, Expected SARSA, after %d warm-up frames (%.2f M paths); unmodified reference sources (GPU_Rendering_Engine) built for the host with g++ -O2 -fopenmp, %d threads" % (
+            done, R.spp, R.width, R.height, warmup, paths / 1e6, R.threads())
         return paths / dt / 1e6, "reference", R.threads(), sample, dt / done * 1e3
     orc = Oracle()
     s = load_scene("cornell")
     orc.scene_set(s["sv"], s["srgb"], s["lv"], s["lrgb"]); orc.rmap_build(); orc.rmap_update_distributions(); orc.rmap_merge_frame()
-    w = h = 512; spp = 2
+    w = h = 512
     def frame(i):
         orc.render_frame(1, w, h, spp, sample0=i * spp, fma_mode=1, td_mode=1); orc.rmap_merge_frame(); orc.rmap_update_distributions()
     for i in range(warmup):
@@ -156,14 +175,38 @@ def _cpu_reference_run(frames, warmup, want_seconds=None):
     return paths / dt / 1e6, "port", orc.threads(), "%d frames x %d spp, Cornell 512x512, Expected SARSA (oracle port, OpenMP)" % (done, spp), dt / done * 1e3
 
 
+def cpu_engine_run():
+    """BASELINE.json configs[0]: the reference's Old_CPU_Rendering_Engine (restored and built by oracle/cpu_engine/build.sh into
+    baseline/_ref/), built-in Cornell box, default path tracer; std::chrono around draw_default_path_tracing only (BASELINE.md 2)."""
+    import ctypes
+    out = {}
+    ncpu = os.cpu_count() or 1
+    for key, lib, threads in (("as_committed_all_cores", "libcpu_engine_b2.so", ncpu), ("as_committed_6_threads", "libcpu_engine_b2.so", 6), ("bounces_80_all_cores", "libcpu_engine_b80.so", ncpu)):
+        path = os.path.join(ROOT, "baseline", "_ref", lib)
+        if not os.path.exists(path):
+            return None
+        L = ctypes.CDLL(path)
+        w, h, spp, b = [ctypes.c_int() for _ in range(4)]
+        L.cpu_engine_dims(*[ctypes.byref(x) for x in (w, h, spp, b)])
+        sec = np.zeros(1)
+        with c_stdout_to_stderr():
+            L.cpu_engine_render_default(1, int(threads), sec.ctypes.data_as(ctypes.c_void_p), None)
+        paths = w.value * h.value * spp.value
+        out[key] = {"value": paths / sec[0] / 1e6, "unit": "Mpaths/s", "cores": int(min(threads, ncpu)), "threads": int(threads), "seconds": float(sec[0]),
+                    "sample": "1 frame %dx%d x %d spp = %.2f M paths, MAX_RAY_BOUNCES %d, built-in Cornell box, default path tracer (uniform hemisphere sampling)" % (w.value, h.value, spp.value, paths / 1e6, b.value)}
+    return out
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    v, kind, cores, sample, ms = cpu_reference_run(args.steps, args.warmup)
+    v, kind, cores, sample, ms = cpu_reference_run(args.steps, args.warmup, want_seconds=240.0, spp=args.spp)
     line = {"impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "built-in Cornell box scene (no dataset)",
-            "config": {"workload": "cornell_sarsa", "scene": "Cornell box (36 surfaces + 2 area lights)", "width": 512, "height": 512, "spp_per_frame": 2,
-                       "radiance_volumes": 24526, "grid": "12x12", "max_bounces": 80, "note": "CPU arm: bounded sample, 2 spp per frame"},
+            "config": {"workload": "cornell_sarsa", "scene": "Cornell box (36 surfaces + 2 area lights)", "width": 512, "height": 512, "spp_per_frame": args.spp,
+                       "radiance_volumes": 24526, "grid": "12x12", "max_bounces": 80,
+                       "note": "CPU arm: the reference's GPU_Rendering_Engine sources compiled for the host (oracle/_ref/libref_host.so), same scene, method, resolution and spp per frame as the GPU arm; "
+                               "a step = one full frame; at most 240 s of timed frames"},
             "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -181,6 +224,7 @@ def main():
     ap.add_argument("--spp", type=int, default=32)
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exclusive", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -264,6 +308,23 @@ def main():
     if world > 1:
         dist.all_reduce(e1, op=dist.ReduceOp.MAX)
     e2e_value = est["paths"] * world / float(e1.item()) / 1e6
+    # ---- exclusive per-kernel times: the two sample lanes (and the next frame's primary scan) overlap on purpose, so the per-launch
+    # durations above include sharing the SMs. One short pass with a single lane and no cross-frame overlap gives each kernel's time alone.
+    excl = None
+    if rank == 0 and world == 1 and not args.no_exclusive:
+        os.environ["RLPT_LANES"] = "1"; os.environ["RLPT_PRE"] = "0"
+        cx = rlpt.Context(local, width=args.width, height=args.height, spp=args.spp, max_bounces=80, env_light=env, traversal=args.traversal)
+        cx.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"]); cx.camera_set(cam)
+        if method == 1:
+            cx.radiance_map_build()
+        rx = cx.render_sarsa if method == 1 else cx.render_default
+        rx(max(args.warmup, 4)); cx.sync(); cx.stats_reset(); rx(8); cx.sync()
+        sx = cx.stats()
+        excl = {"k_isect": sx["isect_seconds"] / 8 * 1e3, "k_shade": sx["shade_seconds"] / 8 * 1e3, "tail": sx["tail_seconds"] / 8 * 1e3,
+                "merge": sx["merge_seconds"] / 8 * 1e3, "frame": sx["device_seconds"] / 8 * 1e3,
+                "note": "8 frames traced as ONE lane with no cross-frame overlap (RLPT_LANES=1 RLPT_PRE=0): kernels run back to back, so these are exclusive times; the headline runs two overlapping lanes"}
+        cx.close()
+        del os.environ["RLPT_LANES"]; del os.environ["RLPT_PRE"]
     h2d = 48                                                # FrameDyn: camera position + rotation + sample base, staged by the render call
     d2h = args.width * args.height * 3 * 4 + 8 * 8          # frame buffer + statistics block
 
@@ -343,9 +404,38 @@ def main():
                                       "frac": merge_bytes * st["frames"] / st["merge_seconds"] / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
                                       "note": "duration = the merge phase of the frame on the context stream, during which the next frame's primary k_isect runs on purpose "
                                               "(low-priority stream); k_merge_cdf alone takes 40-48 us per launch = 1.2-1.4 TB/s (profiles/r1_launches_cornell_sarsa.csv)"}
+        # image parity and the reference's own kernels on this GPU type: recorded by tests/test_gpu_mape.py on a B200 (bench.py itself
+        # runs no checker code outside the cpu_baseline leg)
+        for name in ("r2_mape_parity.json", "r1_mape_parity.json"):
+            try:
+                mp = json.load(open(os.path.join(ROOT, "profiles", name)))
+            except (OSError, ValueError):
+                continue
+            key = "cornell" if "cornell" in mp else None
+            m = mp[key] if key else mp
+            line["mape"] = {"product_sarsa_8x32spp": m.get("mape_prod_sarsa_8x32spp"), "reference_sarsa_8x32spp": m.get("mape_ref_sarsa_8x32spp"),
+                            "product_default_1024spp": m.get("mape_prod_default_1024spp"), "reference_default_1024spp": m.get("mape_refB_1024spp"),
+                            "ground_truth": "the reference's default path tracer (its own CUDA kernels on a B200) at 1024 spp; MAPE = Graphing/mape.py:10-21 on 8-bit RGB",
+                            "source": "profiles/%s (written by tests/test_gpu_mape.py)" % name}
+            line["reference_kernels_on_b200"] = {"sarsa_mpaths_s": m.get("ref_kernels_sarsa_mpaths_s"), "default_mpaths_s": m.get("ref_kernels_default_mpaths_s"),
+                                                 "what": "GPU_Rendering_Engine's own kernels recompiled for sm_100a (oracle/_ref/libref_cuda.so), Cornell 512x512x32 spp, CUDA events around its frame loop",
+                                                 "source": "profiles/%s" % name}
+            break
+        if excl:
+            line["exclusive_kernel_ms_per_step"] = excl
         if world == 1 and not args.no_cpu_baseline:
-            v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
+            eng = cpu_engine_run()
+            v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds, spp=32)
+            sarsa = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
+            if eng:
+                a = eng["as_committed_all_cores"]
+                line["cpu_baseline"] = {"value": a["value"], "unit": "Mpaths/s", "cores": a["cores"], "kind": "reference",
+                                        "sample": "Old_CPU_Rendering_Engine (BASELINE.json configs[0]; unmodified sources + the two functions it declares but never defines, "
+                                                  "oracle/cpu_engine/, g++ -O3 -fopenmp), " + a["sample"] + ", std::chrono around draw_default_path_tracing",
+                                        "six_threads_as_hard_coded": eng["as_committed_6_threads"], "bounces_80": eng["bounces_80_all_cores"]}
+                line["cpu_baseline_sarsa"] = sarsa                 # this bench's own workload on the host: the reference's GPU engine sources behind a host shim
+            else:
+                line["cpu_baseline"] = sarsa
         emit(line)
     ctx.close()
     if world > 1:

@@ -92,6 +92,11 @@ int rlpt_scene_upload(rlpt_ctx* ctx, const float* surface_v, const float* surfac
 int rlpt_scene_info(rlpt_ctx* ctx, int* n_surfaces, int* n_lights, int* bvh_nodes, int* bvh_depth);
 /* device-built BVH, for inspection/tests: nodes as 16 floats each (see DESIGN.md "BVH node") */
 int rlpt_scene_bvh_download(rlpt_ctx* ctx, float* nodes16, int max_nodes);
+/* the 4-wide tree the tracing kernels walk (the binary tree above collapsed on the GPU; new work, the reference scans every
+ * primitive, G/rays/ray.cu:16-36): 28 floats per node = lo.x, hi.x, lo.y, hi.y, lo.z, hi.z of the four children + four links
+ * (>= 0 node, < 0 ~(first record << 3 | records), -1 = no records = unused slot); record_gid[i] = primitive id of leaf-order record i */
+int rlpt_scene_bvh4_info(rlpt_ctx* ctx, int* nodes, int* depth, int* leaf_max);
+int rlpt_scene_bvh4_download(rlpt_ctx* ctx, float* nodes28, int max_nodes, int* record_gid, int max_records);
 
 /* replaces: cudaMemcpy(device_camera, &camera, ...) each frame (G/main.cu:210,307); Camera{position,yaw_y,yaw_x} (G/camera.cuh:19-22) */
 int rlpt_camera_set(rlpt_ctx* ctx, const float position[4], float yaw_y, float yaw_x);

@@ -12,6 +12,16 @@
 //   child link >= 0: node index;  < 0: ~primitive id (one primitive per leaf)
 // Leaf boxes are padded (kPad * primitive extent + kAbs) so that traversal can never cull a primitive that the
 // reference's FP32 Cramer test would accept for a ray passing just outside the exact triangle.
+//
+// The kernels do not walk that binary tree: k_collapse4 (below) folds it, still on the GPU, into a 4-WIDE tree -- a wide node
+// absorbs the binary nodes under it (largest surface area first) until it has four children; a binary subtree of at most
+// `leaf_max` primitives becomes one leaf. Half the dependent node visits per ray, and the per-visit bookkeeping (stack, ordering,
+// loop control) is paid once per four boxes. Wide node = 7 x float4:
+//   [0] lo.x of children 0..3   [1] hi.x   [2] lo.y   [3] hi.y   [4] lo.z   [5] hi.z        (a ray picks near / far by its octant)
+//   [6] links: inner children FIRST, and their nodes are consecutive (link_k = link_0 + k), so the traversal stack and the
+//       ordering keys carry a slot number instead of a link; leaf: ~(first record << 3 | records), the records being consecutive
+//       in tri4 (the triangle buffer re-ordered by leaf, primitive id in the third float4's z); unused slot: BVH4_EMPTY (= a leaf of zero
+//       records) + an inverted box (lo = FLT_MAX, hi = -FLT_MAX) that no finite ray can enter.
 #include "rlpt_internal.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>
@@ -74,7 +84,7 @@ __device__ __forceinline__ int delta(const uint64_t* keys, int n, int i, int j) 
 }
 // Karras 2012, one thread per internal node i in [0, n-1): children/parents in the temporary "LBVH numbering":
 // internal nodes 0..n-2, leaves encoded as (n-1) + sorted position.
-__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent) {
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right, int* __restrict__ parent, int* __restrict__ rng_b, int* __restrict__ rng_e) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -90,6 +100,7 @@ __global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* __restri
     int lc = (lo == gamma) ? (n - 1) + gamma : gamma;
     int rc = (hi == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
     left[i] = lc; right[i] = rc; parent[lc] = i; parent[rc] = i;
+    rng_b[i] = lo; rng_e[i] = hi + 1;                        // the node's primitives: sorted positions [lo, hi]
     if (i == 0) parent[0] = -1;
 }
 // bottom-up AABB fit: each leaf walks up; the second thread to reach a node merges its children's boxes
@@ -145,7 +156,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int& total) {
     return pre;
 }
 __global__ void __launch_bounds__(SAH_T) k_sah_build(const Box* __restrict__ boxes, int n, int* __restrict__ ids, int* __restrict__ tmp, SahItem* __restrict__ queue,
-                                                     int* __restrict__ left, int* __restrict__ right, Box* __restrict__ node_boxes, int* __restrict__ depth_out) {
+                                                     int* __restrict__ left, int* __restrict__ right, Box* __restrict__ node_boxes, int* __restrict__ depth_out, int* __restrict__ rng_b, int* __restrict__ rng_e) {
     __shared__ int s_cb[6], s_nb[6];
     __shared__ int s_cnt[3][SAH_BINS], s_lo[3][SAH_BINS][3], s_hi[3][SAH_BINS][3];
     __shared__ float s_cost[48];
@@ -157,6 +168,7 @@ __global__ void __launch_bounds__(SAH_T) k_sah_build(const Box* __restrict__ box
     for (int node = 0; node < n - 1; ++node) {
         const SahItem it = queue[node];
         const int b = it.b, e = it.e, c = e - b;
+        if (tid == 0) { rng_b[node] = b; rng_e[node] = e; }
         if (tid < 6) { s_cb[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000; s_nb[tid] = s_cb[tid]; }
         for (int k = tid; k < 3 * SAH_BINS; k += SAH_T) {
             (&s_cnt[0][0])[k] = 0;
@@ -261,24 +273,107 @@ __global__ void k_emit(const Box* __restrict__ node_boxes, const int* __restrict
     out[4 * k + 2] = make_float4(b.lo[2], b.hi[0], b.hi[1], b.hi[2]);
     out[4 * k + 3] = make_float4(__int_as_float(l0), __int_as_float(l1), 0.f, 0.f);
 }
+
+// ---- binary -> 4-wide collapse, one CTA, level by level (the wide tree is numbered breadth-first: the children of one node get
+// consecutive slots, which the traversal relies on). Task = (binary node, wide slot). Everything that decides the topology is a
+// function of the binary tree alone; slots are handed out by a block scan, so the wide tree is the same on every run and GPU.
+constexpr int C4_T = 1024;
+struct C4Task { int bnode, wslot; };
+__device__ __forceinline__ float box_area(const Box& b) {
+    const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+    return x * y + y * z + z * x;
+}
+__global__ void __launch_bounds__(C4_T) k_collapse4(const Box* __restrict__ node_boxes, int n, const int* __restrict__ left, const int* __restrict__ right,
+                                                    const int* __restrict__ rng_b, const int* __restrict__ rng_e, int leaf_max, C4Task* __restrict__ queue,
+                                                    float4* __restrict__ out, int* __restrict__ counts /* [0] nodes, [1] depth */) {
+    __shared__ int s_warp[32];
+    __shared__ int s_begin, s_end, s_alloc, s_depth;
+    const int tid = threadIdx.x;
+    if (tid == 0) { queue[0] = C4Task{ 0, 0 }; s_begin = 0; s_end = 1; s_alloc = 1; s_depth = 0; }
+    __syncthreads();
+    auto is_inner = [&](int c) { return c < n - 1 && rng_e[c] - rng_b[c] > leaf_max; };       // becomes a wide node of its own
+    while (true) {
+        const int begin = s_begin, end = s_end;
+        if (begin >= end) break;
+        int qtail = end;
+        for (int chunk = begin; chunk < end; chunk += C4_T) {
+            const int t = chunk + tid; const bool valid = t < end;
+            int c[4] = { -1, -1, -1, -1 }; int nc = 0, n_inner = 0; C4Task task{ 0, 0 };
+            if (valid) {
+                task = queue[t];
+                c[0] = left[task.bnode]; c[1] = right[task.bnode]; nc = 2;
+                while (nc < 4) {                                                          // open the inner child with the largest box
+                    int pick = -1; float best = -1.f;
+                    for (int k = 0; k < nc; ++k) if (is_inner(c[k])) { const float a = box_area(node_boxes[c[k]]); if (a > best) { best = a; pick = k; } }
+                    if (pick < 0) break;
+                    const int o = c[pick]; c[pick] = left[o]; c[nc++] = right[o];
+                }
+                // inner children first (stable), then leaves
+                int ord[4], m = 0;
+                for (int k = 0; k < nc; ++k) if (is_inner(c[k])) ord[m++] = c[k];
+                n_inner = m;
+                for (int k = 0; k < nc; ++k) if (!is_inner(c[k])) ord[m++] = c[k];
+                for (int k = 0; k < nc; ++k) c[k] = ord[k];
+            }
+            int total; const int off = block_excl_scan(n_inner, s_warp, total);
+            const int base = s_alloc + off, qpos = qtail + off;
+            if (valid) {
+                float pl[6][4]; int link[4];
+                for (int k = 0; k < 4; ++k) {
+                    if (k < nc) {
+                        const Box b = node_boxes[c[k]];
+                        for (int d = 0; d < 3; ++d) { pl[2 * d][k] = b.lo[d]; pl[2 * d + 1][k] = b.hi[d]; }
+                        if (k < n_inner) { link[k] = base + k; queue[qpos + k] = C4Task{ c[k], base + k }; }
+                        else if (c[k] >= n - 1) link[k] = ~(((c[k] - (n - 1)) << 3) | 1);                       // one primitive: its sorted position
+                        else link[k] = ~((rng_b[c[k]] << 3) | (rng_e[c[k]] - rng_b[c[k]]));                     // a small subtree: its run of positions
+                    } else {
+                        for (int d = 0; d < 3; ++d) { pl[2 * d][k] = FLT_MAX; pl[2 * d + 1][k] = -FLT_MAX; }
+                        link[k] = BVH4_EMPTY;
+                    }
+                }
+                float4* o = out + 7 * (size_t)task.wslot;
+                for (int r = 0; r < 6; ++r) o[r] = make_float4(pl[r][0], pl[r][1], pl[r][2], pl[r][3]);
+                o[6] = make_float4(__int_as_float(link[0]), __int_as_float(link[1]), __int_as_float(link[2]), __int_as_float(link[3]));
+            }
+            __syncthreads();
+            if (tid == 0) s_alloc += total;
+            qtail += total;
+            __syncthreads();
+        }
+        if (tid == 0) { s_begin = end; s_end = qtail; s_depth++; }
+        __syncthreads();
+    }
+    if (tid == 0) { counts[0] = s_alloc; counts[1] = s_depth; }
+}
+// triangle records in leaf order, primitive id in the spare word
+__global__ void k_tri4(const float4* __restrict__ tri, const int* __restrict__ ids, int n, float4* __restrict__ tri4) {
+    int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const int gid = ids[pos];
+    float4 c = tri[3 * gid + 2]; c.z = __int_as_float(gid);
+    tri4[3 * pos] = tri[3 * gid]; tri4[3 * pos + 1] = tri[3 * gid + 1]; tri4[3 * pos + 2] = c;
+}
 }  // namespace
 
 #define BVH_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (int)e_; goto done; } } while (0)
 
-int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s) {
+int bvh_build_gpu(const float4* d_tri, int n, int leaf_max, float4** d_bvh, int* n_nodes, int* depth, float4** d_bvh4, int* n_nodes4, int* depth4, float4** d_tri4, cudaStream_t s) {
     int rc = 0;
     Box *boxes = nullptr, *node_boxes = nullptr; float* scene = nullptr; uint64_t *keys = nullptr, *keys_s = nullptr; int *ids = nullptr, *ids_s = nullptr;
     int *left = nullptr, *right = nullptr, *parent = nullptr, *flags = nullptr, *order = nullptr, *slot_of = nullptr; void* tmp = nullptr; size_t tmp_bytes = 0;
+    int *rng_b = nullptr, *rng_e = nullptr, *c4_counts = nullptr; C4Task* c4_queue = nullptr; float4 *out4 = nullptr, *tri4 = nullptr;
     float4* out = nullptr; SahItem* sah_queue = nullptr; int* sah_depth = nullptr; bool use_sah = false;
     const int T = 128;
-    *d_bvh = nullptr; *n_nodes = 0; *depth = 0;
+    *d_bvh = nullptr; *n_nodes = 0; *depth = 0; *d_bvh4 = nullptr; *n_nodes4 = 0; *depth4 = 0; *d_tri4 = nullptr;
     if (n <= 0) return 0;
+    leaf_max = leaf_max < 1 ? 1 : (leaf_max > BVH4_LEAF_MAX ? BVH4_LEAF_MAX : leaf_max);
     BVH_CK(cudaMalloc(&boxes, sizeof(Box) * n)); BVH_CK(cudaMalloc(&scene, sizeof(float) * 6));
     {
         float init[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
         BVH_CK(cudaMemcpyAsync(scene, init, sizeof init, cudaMemcpyHostToDevice, s));
     }
     k_prim_bounds<<<(n + T - 1) / T, T, 0, s>>>(d_tri, n, boxes, scene);
+    BVH_CK(cudaMalloc(&tri4, sizeof(float4) * 3 * (size_t)n));
     if (n == 1) {
         // a single primitive: one node whose second child is an empty box
         Box b; BVH_CK(cudaStreamSynchronize(s)); BVH_CK(cudaMemcpy(&b, boxes, sizeof(Box), cudaMemcpyDeviceToHost));
@@ -286,10 +381,18 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
                         make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX), make_float4(0, 0, 0, 0) };
         int l0 = ~0; memcpy(&h[3].x, &l0, 4); memcpy(&h[3].y, &l0, 4);
         BVH_CK(cudaMalloc(&out, sizeof(float4) * 4)); BVH_CK(cudaMemcpy(out, h, sizeof h, cudaMemcpyHostToDevice));
-        *d_bvh = out; out = nullptr; *n_nodes = 1; *depth = 1; goto done;
+        float4 w[7]; const int leaf = ~((0 << 3) | 1), none = BVH4_EMPTY;
+        for (int d = 0; d < 3; ++d) { w[2 * d] = make_float4(b.lo[d], FLT_MAX, FLT_MAX, FLT_MAX); w[2 * d + 1] = make_float4(b.hi[d], -FLT_MAX, -FLT_MAX, -FLT_MAX); }
+        memcpy(&w[6].x, &leaf, 4); memcpy(&w[6].y, &none, 4); memcpy(&w[6].z, &none, 4); memcpy(&w[6].w, &none, 4);
+        BVH_CK(cudaMalloc(&out4, sizeof(float4) * 7)); BVH_CK(cudaMemcpy(out4, w, sizeof w, cudaMemcpyHostToDevice));
+        BVH_CK(cudaMalloc(&ids, sizeof(int))); BVH_CK(cudaMemset(ids, 0, sizeof(int)));
+        k_tri4<<<1, T, 0, s>>>(d_tri, ids, 1, tri4);
+        BVH_CK(cudaStreamSynchronize(s)); BVH_CK(cudaGetLastError());
+        *d_bvh = out; out = nullptr; *n_nodes = 1; *depth = 1; *d_bvh4 = out4; out4 = nullptr; *n_nodes4 = 1; *depth4 = 1; *d_tri4 = tri4; tri4 = nullptr; goto done;
     }
     BVH_CK(cudaMalloc(&ids, sizeof(int) * n)); BVH_CK(cudaMalloc(&ids_s, sizeof(int) * n));
     BVH_CK(cudaMalloc(&left, sizeof(int) * (n - 1))); BVH_CK(cudaMalloc(&right, sizeof(int) * (n - 1)));
+    BVH_CK(cudaMalloc(&rng_b, sizeof(int) * (n - 1))); BVH_CK(cudaMalloc(&rng_e, sizeof(int) * (n - 1)));
     BVH_CK(cudaMalloc(&node_boxes, sizeof(Box) * (2 * n - 1)));
     {
         const char* e = getenv("RLPT_BVH_BUILD");                    // "lbvh": the Morton-order build for every size (A/B runs)
@@ -297,7 +400,7 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
     }
     if (use_sah) {
         BVH_CK(cudaMalloc(&sah_queue, sizeof(SahItem) * (n - 1))); BVH_CK(cudaMalloc(&sah_depth, sizeof(int)));
-        k_sah_build<<<1, SAH_T, 0, s>>>(boxes, n, ids_s, ids, sah_queue, left, right, node_boxes, sah_depth);
+        k_sah_build<<<1, SAH_T, 0, s>>>(boxes, n, ids_s, ids, sah_queue, left, right, node_boxes, sah_depth, rng_b, rng_e);
     } else {
         BVH_CK(cudaMalloc(&keys, sizeof(uint64_t) * n)); BVH_CK(cudaMalloc(&keys_s, sizeof(uint64_t) * n));
         k_morton<<<(n + T - 1) / T, T, 0, s>>>(boxes, n, scene, keys, ids);
@@ -306,9 +409,14 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
         BVH_CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_s, ids, ids_s, n, 0, 64, s));
         BVH_CK(cudaMalloc(&parent, sizeof(int) * (2 * n - 1))); BVH_CK(cudaMalloc(&flags, sizeof(int) * (n - 1)));
         BVH_CK(cudaMemsetAsync(flags, 0, sizeof(int) * (n - 1), s));
-        k_karras<<<(n - 1 + T - 1) / T, T, 0, s>>>(keys_s, n, left, right, parent);
+        k_karras<<<(n - 1 + T - 1) / T, T, 0, s>>>(keys_s, n, left, right, parent, rng_b, rng_e);
         k_fit<<<(n + T - 1) / T, T, 0, s>>>(boxes, ids_s, n, left, right, parent, node_boxes, flags);
     }
+    // the 4-wide tree the kernels walk, and the triangle records in its leaf order
+    BVH_CK(cudaMalloc(&c4_queue, sizeof(C4Task) * (n - 1))); BVH_CK(cudaMalloc(&c4_counts, sizeof(int) * 2));
+    BVH_CK(cudaMalloc(&out4, sizeof(float4) * 7 * (size_t)(n - 1)));
+    k_collapse4<<<1, C4_T, 0, s>>>(node_boxes, n, left, right, rng_b, rng_e, leaf_max, c4_queue, out4, c4_counts);
+    k_tri4<<<(n + T - 1) / T, T, 0, s>>>(d_tri, ids_s, n, tri4);
     {
         // breadth-first numbering of the internal nodes (host walk over the n-1 child links; O(n), one-off)
         std::vector<int> hl(n - 1), hr(n - 1), ord, slot(n - 1, -1);
@@ -332,10 +440,16 @@ int bvh_build_gpu(const float4* d_tri, int n, float4** d_bvh, int* n_nodes, int*
     k_emit<<<(n - 1 + T - 1) / T, T, 0, s>>>(node_boxes, ids_s, n, left, right, order, slot_of, out);
     BVH_CK(cudaStreamSynchronize(s));
     BVH_CK(cudaGetLastError());
-    *d_bvh = out; out = nullptr; *n_nodes = n - 1;
+    {
+        int hc[2] = { 0, 0 }; BVH_CK(cudaMemcpy(hc, c4_counts, sizeof hc, cudaMemcpyDeviceToHost));
+        if (hc[0] < 1 || hc[0] > n - 1) { rc = -2; goto done; }
+        *n_nodes4 = hc[0]; *depth4 = hc[1];
+    }
+    *d_bvh = out; out = nullptr; *n_nodes = n - 1; *d_bvh4 = out4; out4 = nullptr; *d_tri4 = tri4; tri4 = nullptr;
 done:
     cudaFree(boxes); cudaFree(node_boxes); cudaFree(scene); cudaFree(keys); cudaFree(keys_s); cudaFree(ids); cudaFree(ids_s);
     cudaFree(left); cudaFree(right); cudaFree(parent); cudaFree(flags); cudaFree(order); cudaFree(slot_of); cudaFree(tmp); cudaFree(out); cudaFree(sah_queue); cudaFree(sah_depth);
+    cudaFree(rng_b); cudaFree(rng_e); cudaFree(c4_counts); cudaFree(c4_queue); cudaFree(out4); cudaFree(tri4);
     return rc;
 }
 

@@ -36,7 +36,7 @@ struct rlpt_ctx {
     // scene
     bool have_scene = false;
     int n_surf = 0, n_light = 0, bvh_depth = 0;
-    float4 *d_tri = nullptr, *d_shade = nullptr, *d_bvh = nullptr, *d_scan = nullptr; int* d_scan_gid = nullptr; float* d_surf_lum_over_pi = nullptr;
+    float4 *d_tri = nullptr, *d_shade = nullptr, *d_bvh = nullptr, *d_bvh4 = nullptr, *d_tri4 = nullptr, *d_scan = nullptr; int n_nodes = 0, bvh4_depth = 0, bvh_leaf_max = 2; int* d_chit_cursor = nullptr; int* d_scan_gid = nullptr; float* d_surf_lum_over_pi = nullptr;
     std::vector<float> h_surf_v, h_surf_nrm, h_surf_rgb, h_light_v, h_light_rgb;
     std::vector<int> h_surf_class;
     SceneDev scene{};
@@ -50,7 +50,7 @@ struct rlpt_ctx {
     float *d_q = nullptr, *d_cdf = nullptr, *d_cdf_rows = nullptr, *d_irr = nullptr, *d_acc_sum = nullptr; uint32_t *d_visits = nullptr, *d_acc_cnt = nullptr;
     RadianceDev rm{};
     // peer-memory exchange (rlpt_p2p_export / rlpt_p2p_import): every rank's exchange buffers opened through CUDA IPC
-    PeerTables peers{}; bool p2p_ready = false; unsigned p2p_epoch = 0; unsigned* d_p2p_flags = nullptr; unsigned* d_p2p_done = nullptr;
+    PeerTables peers{}; bool p2p_ready = false; unsigned p2p_epoch = 0; unsigned* d_p2p_flags = nullptr; unsigned* d_p2p_done = nullptr; unsigned* d_p2p_error = nullptr; bool p2p_used = false;
     std::vector<void*> p2p_opened;
     // Neural-Q network
     DqnHost dq_host; DqnDev dq; std::vector<float> dq_vertices; bool dq_vertices_custom = false;
@@ -90,13 +90,31 @@ struct rlpt_ctx {
 };
 
 static void free_scene(rlpt_ctx* c) {
-    cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_surf_lum_over_pi); cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
+    cudaFree(c->d_tri); cudaFree(c->d_shade); cudaFree(c->d_bvh); cudaFree(c->d_bvh4); cudaFree(c->d_tri4); c->d_bvh4 = c->d_tri4 = nullptr; cudaFree(c->d_surf_lum_over_pi); cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
     c->d_tri = c->d_shade = c->d_bvh = nullptr; c->d_surf_lum_over_pi = nullptr; c->have_scene = false;
 }
+// Closes this rank's view of the peers. The flag arrays, the error word and the epoch counter live as long as the context: peers
+// may still hold the flags mapped (a cudaFree under them would leave dangling IPC mappings), and the epoch stays monotonic so that
+// a later export / import round (whose blobs carry every rank's epoch) resynchronises instead of restarting from 0.
 static void p2p_close(rlpt_ctx* c) {
     for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
     c->p2p_opened.clear(); c->p2p_ready = false; c->peers = PeerTables{};
-    cudaFree(c->d_p2p_flags); cudaFree(c->d_p2p_done); c->d_p2p_flags = c->d_p2p_done = nullptr; c->p2p_epoch = 0;
+}
+static void p2p_destroy(rlpt_ctx* c) {
+    p2p_close(c);
+    cudaFree(c->d_p2p_flags); cudaFree(c->d_p2p_done); cudaFree(c->d_p2p_error); c->d_p2p_flags = c->d_p2p_done = c->d_p2p_error = nullptr;
+}
+// the error word of the peer-memory merge (rlpt_kernels.cu, wait_flag): call after the stream has drained
+static int p2p_check(rlpt_ctx* c) {
+    if (!c->p2p_used || !c->d_p2p_error) return RLPT_OK;
+    unsigned e = 0;
+    if (cudaMemcpy(&e, c->d_p2p_error, sizeof e, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(RLPT_ERR_CUDA, "peer-memory exchange: cannot read the error word");
+    c->p2p_used = false;
+    if (!e) return RLPT_OK;
+    cudaMemset(c->d_p2p_error, 0, sizeof(unsigned)); cudaMemset(c->d_p2p_done, 0, sizeof(unsigned));
+    c->p2p_ready = false;                                              // broken until the ranks run rlpt_p2p_export / rlpt_p2p_import again
+    return fail(RLPT_ERR_COLLECTIVE, "peer-memory exchange timed out waiting for a rank (asymmetric rlpt_sarsa_merge calls, a failed or restarted peer); "
+                                     "radiance tables may be incomplete -- rebuild the exchange with rlpt_p2p_export / rlpt_p2p_import");
 }
 static void free_rmap(rlpt_ctx* c) {
     p2p_close(c);
@@ -182,6 +200,8 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaMalloc(&c->d_stats, sizeof(unsigned long long) * 8)); CK(cudaMemset(c->d_stats, 0, sizeof(unsigned long long) * 8));
     CK(cudaMalloc(&c->d_cap_n, sizeof(int))); CK(cudaMemset(c->d_cap_n, 0, sizeof(int)));
+    CK(cudaMalloc(&c->d_chit_cursor, sizeof(int))); CK(cudaMemset(c->d_chit_cursor, 0, sizeof(int)));
+    if (const char* e = getenv("RLPT_BVH_LEAF")) c->bvh_leaf_max = std::max(1, std::min(atoi(e), (int)BVH4_LEAF_MAX));
     rlpt_config_default(&c->cfg);
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
     upload_cell_cos(cs);
@@ -196,8 +216,8 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     if (!c) return RLPT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    free_scene(c); free_rmap(c); free_frame(c); dqn_free(c->dq); dqn_train_free(c->dq_train); cudaFree(c->d_nq_q);
-    cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n);
+    free_scene(c); free_rmap(c); p2p_destroy(c); free_frame(c); dqn_free(c->dq); dqn_train_free(c->dq_train); cudaFree(c->d_nq_q);
+    cudaFree(c->d_stage); cudaFree(c->d_stats); if (c->ev_fork) cudaEventDestroy(c->ev_fork); cudaFree(c->d_cap_o); cudaFree(c->d_cap_d); cudaFree(c->d_cap_n); cudaFree(c->d_chit_cursor);
     for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->kev_pool) cudaEventDestroy(e);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->stream);
@@ -205,7 +225,7 @@ int rlpt_ctx_destroy(rlpt_ctx* c) {
     return RLPT_OK;
 }
 
-int rlpt_sync(rlpt_ctx* c) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError()); return RLPT_OK; }
+int rlpt_sync(rlpt_ctx* c) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError()); return p2p_check(c); }
 int rlpt_stream(rlpt_ctx* c, void** s) { if (!c || !s) return fail(RLPT_ERR_ARG, "null"); *s = (void*)c->stream; return RLPT_OK; }
 int rlpt_config_get(rlpt_ctx* c, rlpt_config* cfg) { if (!c || !cfg) return fail(RLPT_ERR_ARG, "null"); *cfg = c->cfg; return RLPT_OK; }
 int rlpt_set_allreduce(rlpt_ctx* c, rlpt_allreduce_fn fn, void* user) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); c->allreduce = fn; c->allreduce_user = user; return RLPT_OK; }
@@ -217,15 +237,17 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
     int mode = traversal ? traversal : c->cfg.traversal;
     if (mode == RLPT_TRAVERSAL_AUTO) mode = n_tri <= 48 ? RLPT_TRAVERSAL_BRUTE : RLPT_TRAVERSAL_BVH;
     sc.brute = mode == RLPT_TRAVERSAL_BRUTE;
-    // shared-memory budget: leave room for >= 2 CTAs per SM when the scene is small, otherwise take what one CTA can have
-    size_t tri_b = (size_t)n_tri * 48, shade_b = (size_t)n_tri * 64, node_b = (size_t)sc.n_nodes * 64;
-    size_t budget = optin > 16384 ? optin - 12288 : optin;
-    if (tri_b + shade_b + node_b <= budget) { sc.smem_tris = n_tri; sc.smem_shade = 1; sc.smem_nodes = sc.n_nodes; }
-    else {
-        sc.smem_tris = 0; sc.smem_shade = 0;
-        if (sc.brute) return fail(RLPT_ERR_UNSUPPORTED, "brute-force traversal needs the whole scene in shared memory");
-        sc.smem_nodes = 0;                                          // nothing staged: triangles and nodes come through the read-only path (L1 hit rate 93-95 % on Medieval_House)
-    }
+    // shared-memory budget: the whole scene is staged by every CTA when it is small enough to leave room for four resident CTAs
+    // of the closest-hit kernel (BVH scenes: plus its per-warp traversal scratch); otherwise everything comes through the
+    // read-only path (L1 hit rate 93-95 % on Medieval_House)
+    cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
+    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.n_items = 0; sc.bundle = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
+    sc.staged = 1;
+    const size_t scene_b = scene_smem_bytes(sc) + (sc.brute ? (size_t)n_tri * 80 + 64 : 0);      // brute: + scan units and slot table (built below), upper bound
+    const size_t budget = optin > 16384 ? optin - 12288 : optin;
+    if (sc.brute) {
+        if (scene_b > budget) return fail(RLPT_ERR_UNSUPPORTED, "brute-force traversal needs the whole scene in shared memory");
+    } else if (scene_b > 20480 || scene_b + bvh4_scratch_bytes() > budget) sc.staged = 0;       // 20 KB: three to four CTAs of k_isect_bvh (50 KB of traversal scratch each) still fit
     c->smem_bytes = scene_smem_bytes(sc);
     {   // |detA| = |a . (e1 x e2)| <= SCREEN_HEIGHT |e1| |e2|: below 2^23 for every primitive -> the guard-free candidate pass applies
         double worst = 0.0;
@@ -240,8 +262,6 @@ static int choose_traversal(rlpt_ctx* c, int traversal) {
         sc.det_small = (std::isfinite(worst) && (double)c->cfg.height * worst * 1.001 < 8388608.0) ? 1 : 0;
     }
     // scan units of the conservative pre-test (rlpt_device.cuh, unit_candidates): parallelogram pairs, then single triangles
-    cudaFree(c->d_scan); cudaFree(c->d_scan_gid); c->d_scan = nullptr; c->d_scan_gid = nullptr;
-    sc.scan = nullptr; sc.slot_gid = nullptr; sc.n_units = 0; sc.n_items = 0; sc.bundle = 0; sc.k1 = sc.k2 = sc.k3 = sc.vmax = 0.f;
     if (sc.brute && n_tri <= 64 && !getenv("RLPT_NO_UNITS")) {
         std::vector<float> verts(c->h_surf_v); verts.insert(verts.end(), c->h_light_v.begin(), c->h_light_v.end());
         HostScanUnits hu; host_build_scan_units(verts.data(), n_tri, hu);
@@ -324,13 +344,13 @@ int rlpt_scene_upload(rlpt_ctx* c, const float* sv, const float* srgb, int ns, c
     CK(cudaMemcpyAsync(c->d_shade, shade.data(), sizeof(float4) * shade.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_surf_lum_over_pi, lum_pi.data(), sizeof(float) * lum_pi.size(), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    int n_nodes = 0, depth = 0;
-    int rc = bvh_build_gpu(c->d_tri, n, &c->d_bvh, &n_nodes, &depth, c->stream);
+    int n_nodes = 0, depth = 0, n_nodes4 = 0, depth4 = 0;
+    int rc = bvh_build_gpu(c->d_tri, n, c->bvh_leaf_max, &c->d_bvh, &n_nodes, &depth, &c->d_bvh4, &n_nodes4, &depth4, &c->d_tri4, c->stream);
     if (rc) { char b[128]; snprintf(b, sizeof b, "rlpt_scene_upload: GPU BVH build failed (%d: %s)", rc, rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "topology"); return fail(RLPT_ERR_CUDA, b); }
     if (depth > 30) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_scene_upload: BVH deeper than the traversal stack");
-    c->bvh_depth = depth;
-    c->scene = SceneDev{}; c->scene.tri = c->d_tri; c->scene.shade = c->d_shade; c->scene.bvh = c->d_bvh;
-    c->scene.n_tri = n; c->scene.n_surf = ns; c->scene.n_light = nl; c->scene.n_nodes = n_nodes;
+    c->bvh_depth = depth; c->bvh4_depth = depth4; c->n_nodes = n_nodes;
+    c->scene = SceneDev{}; c->scene.tri = c->d_tri; c->scene.shade = c->d_shade; c->scene.bvh4 = c->d_bvh4; c->scene.tri4 = c->d_tri4;
+    c->scene.n_tri = n; c->scene.n_surf = ns; c->scene.n_light = nl; c->scene.n_nodes4 = n_nodes4;
     c->have_scene = true;
     c->dq_vertices.clear(); c->dq_vertices_custom = false; c->dq.ready = false;
     return choose_traversal(c, 0);
@@ -338,14 +358,33 @@ int rlpt_scene_upload(rlpt_ctx* c, const float* sv, const float* srgb, int ns, c
 
 int rlpt_scene_info(rlpt_ctx* c, int* ns, int* nl, int* nodes, int* depth) {
     if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_scene_info: no scene");
-    if (ns) *ns = c->n_surf; if (nl) *nl = c->n_light; if (nodes) *nodes = c->scene.n_nodes; if (depth) *depth = c->bvh_depth;
+    if (ns) *ns = c->n_surf; if (nl) *nl = c->n_light; if (nodes) *nodes = c->n_nodes; if (depth) *depth = c->bvh_depth;
     return RLPT_OK;
 }
 int rlpt_scene_bvh_download(rlpt_ctx* c, float* nodes16, int max_nodes) {
     if (!c || !c->have_scene || !nodes16) return fail(RLPT_ERR_ARG, "rlpt_scene_bvh_download: no scene");
     CK(cudaSetDevice(c->device));
-    int n = std::min(max_nodes, c->scene.n_nodes);
+    int n = std::min(max_nodes, c->n_nodes);
     CK(cudaMemcpy(nodes16, c->d_bvh, sizeof(float) * 16 * (size_t)n, cudaMemcpyDeviceToHost));
+    return RLPT_OK;
+}
+// the 4-wide tree the kernels walk (rlpt_bvh.cu): 28 floats per node, and the primitive id of every leaf-order triangle record
+int rlpt_scene_bvh4_info(rlpt_ctx* c, int* nodes, int* depth, int* leaf_max) {
+    if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_scene_bvh4_info: no scene");
+    if (nodes) *nodes = c->scene.n_nodes4; if (depth) *depth = c->bvh4_depth; if (leaf_max) *leaf_max = c->bvh_leaf_max;
+    return RLPT_OK;
+}
+int rlpt_scene_bvh4_download(rlpt_ctx* c, float* nodes28, int max_nodes, int* record_gid, int max_records) {
+    if (!c || !c->have_scene || !nodes28) return fail(RLPT_ERR_ARG, "rlpt_scene_bvh4_download: no scene");
+    CK(cudaSetDevice(c->device));
+    const int n = std::min(max_nodes, c->scene.n_nodes4);
+    CK(cudaMemcpy(nodes28, c->d_bvh4, sizeof(float) * 28 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (record_gid) {
+        const int m = std::min(max_records, c->scene.n_tri);
+        std::vector<float4> rec(3 * (size_t)m);
+        CK(cudaMemcpy(rec.data(), c->d_tri4, sizeof(float4) * rec.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) memcpy(&record_gid[i], &rec[3 * (size_t)i + 2].z, 4);
+    }
     return RLPT_OK;
 }
 
@@ -363,7 +402,7 @@ int rlpt_closest_hit_device(rlpt_ctx* c, const float* d_org, const float* d_dir,
     // a traversal override lasts for this call: choose_traversal owns device buffers (scan units), so the configured mode
     // is re-established by calling it again rather than by restoring a saved copy of the scene descriptor
     if (traversal) { int rc = choose_traversal(c, traversal); if (rc) { (void)choose_traversal(c, 0); return rc; } }
-    launch_closest_hit(c->scene, d_org, d_dir, n, (float)c->cfg.height, d_type, d_index, d_t, d_counters, c->smem_bytes, c->stream);
+    launch_closest_hit(c->scene, d_org, d_dir, n, (float)c->cfg.height, d_type, d_index, d_t, d_counters, c->d_chit_cursor, c->smem_bytes, c->stream);
     if (traversal) { CK(cudaStreamSynchronize(c->stream)); int rc = choose_traversal(c, 0); if (rc) return rc; }
     CK(cudaGetLastError());
     return RLPT_OK;
@@ -473,9 +512,10 @@ int rlpt_p2p_export(rlpt_ctx* c, void* blob) {
     if (!c->d_p2p_flags) {
         CK(cudaMalloc(&c->d_p2p_flags, sizeof(unsigned) * 2 * MAX_PEERS)); CK(cudaMemset(c->d_p2p_flags, 0, sizeof(unsigned) * 2 * MAX_PEERS));
         CK(cudaMalloc(&c->d_p2p_done, sizeof(unsigned))); CK(cudaMemset(c->d_p2p_done, 0, sizeof(unsigned)));
+        CK(cudaMalloc(&c->d_p2p_error, sizeof(unsigned))); CK(cudaMemset(c->d_p2p_error, 0, sizeof(unsigned)));
     }
     unsigned char* out = (unsigned char*)blob; memset(out, 0, 8);
-    const int nv = c->rm.n_vol; memcpy(out, &nv, 4);
+    const int nv = c->rm.n_vol; memcpy(out, &nv, 4); memcpy(out + 4, &c->p2p_epoch, 4);        // the epoch this rank has reached: import resumes from the largest
     void* ptrs[P2P_HANDLES] = { c->d_acc_sum, c->d_acc_cnt, c->d_q, c->d_cdf, c->d_cdf_rows, c->d_visits, c->d_irr, c->d_p2p_flags };
     for (int i = 0; i < P2P_HANDLES; ++i) { cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, ptrs[i])); memcpy(out + 8 + i * sizeof h, &h, sizeof h); }
     return RLPT_OK;
@@ -486,11 +526,13 @@ int rlpt_p2p_import(rlpt_ctx* c, const void* blobs, int world_size) {
     CK(cudaSetDevice(c->device));
     for (void* p : c->p2p_opened) cudaIpcCloseMemHandle(p);
     c->p2p_opened.clear(); c->p2p_ready = false;
-    PeerTables pt{}; pt.world = world_size; pt.rank = c->cfg.rank;
+    PeerTables pt{}; pt.world = world_size; pt.rank = c->cfg.rank; pt.error = c->d_p2p_error;
     const size_t stride = (size_t)rlpt_p2p_blob_bytes();
+    unsigned epoch = c->p2p_epoch;
     for (int r = 0; r < world_size; ++r) {
         const unsigned char* in = (const unsigned char*)blobs + (size_t)r * stride;
         int nv = 0; memcpy(&nv, in, 4);
+        unsigned er = 0; memcpy(&er, in + 4, 4); if ((int)(er - epoch) > 0) epoch = er;
         if (nv != c->rm.n_vol) return fail(RLPT_ERR_ARG, "rlpt_p2p_import: rank " + std::to_string(r) + " has a different radiance map");
         void* ptrs[P2P_HANDLES];
         if (r == c->cfg.rank) {
@@ -507,7 +549,8 @@ int rlpt_p2p_import(rlpt_ctx* c, const void* blobs, int world_size) {
         pt.acc_sum[r] = (float*)ptrs[0]; pt.acc_cnt[r] = (uint32_t*)ptrs[1]; pt.q[r] = (float*)ptrs[2]; pt.cdf[r] = (float*)ptrs[3]; pt.cdf_rows[r] = (float*)ptrs[4];
         pt.visits[r] = (uint32_t*)ptrs[5]; pt.irradiance[r] = (float*)ptrs[6]; pt.flags[r] = (unsigned*)ptrs[7];
     }
-    c->peers = pt; c->p2p_ready = true;
+    c->peers = pt; c->p2p_ready = true; c->p2p_epoch = epoch;         // every rank continues from the same epoch
+    CK(cudaMemset(c->d_p2p_error, 0, sizeof(unsigned))); CK(cudaMemset(c->d_p2p_done, 0, sizeof(unsigned)));
     return RLPT_OK;
 }
 
@@ -725,7 +768,9 @@ int rlpt_dqn_train_batch(rlpt_ctx* c, const float* pos3, const uint32_t* actions
     CK(cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_act, actions, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream)); CK(cudaMemcpyAsync(d_tgt, targets, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     const bool dist = c->allreduce && c->cfg.world_size > 1;
+    const int cap0 = c->dq_train.capacity;
     int rc = dqn_train_batch(c->dq, c->dq_train, d_pos, d_act, d_tgt, n, apply_update != 0, dist ? dqn_hook : nullptr, c, c->stream);
+    if (c->dq_train.capacity != cap0) nq_graph_reset(c);               // the captured optimiser step points into the buffers that were just reallocated
     float h_loss = 0.f;
     if (!rc) { CK(cudaMemcpyAsync(&h_loss, c->dq_train.scalars, 4, cudaMemcpyDeviceToHost, c->stream)); }
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -747,7 +792,9 @@ int rlpt_dqn_train_supervised(rlpt_ctx* c, const float* pos3, const float* targe
     CK(cudaMemcpyAsync(d_pos, h_pos.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_tgt, targets144, 4 * (size_t)n * DQ_OUT, cudaMemcpyHostToDevice, c->stream));
     const bool dist = c->allreduce && c->cfg.world_size > 1;
+    const int cap0 = c->dq_train.capacity;
     int rc = dqn_train_batch(c->dq, c->dq_train, d_pos, nullptr, d_tgt, n, apply_update != 0, dist ? dqn_hook : nullptr, c, c->stream, true);
+    if (c->dq_train.capacity != cap0) nq_graph_reset(c);
     float h_loss = 0.f;
     if (!rc) { CK(cudaMemcpyAsync(&h_loss, c->dq_train.scalars, 4, cudaMemcpyDeviceToHost, c->stream)); }
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -852,7 +899,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     p.width = g.width; p.height = g.height; p.spp = c->lane_spp; p.max_bounces = g.max_bounces; p.seed = g.seed; p.env = g.env_light;
     const int grid = (c->n_sm * 8 + NSUB - 1) / NSUB * NSUB;              // a whole number of CTAs per sub-queue
     // the split kernels run as one resident wave each (whole CTAs per sub-queue, rounded down)
-    if (c->resident_smem != c->smem_bytes || c->per_sm_isect <= 0) { kernels_resident_ctas(c->smem_bytes, c->scene.brute, c->scene.smem_tris == c->scene.n_tri && c->scene.smem_nodes == c->scene.n_nodes, &c->per_sm_isect, &c->per_sm_shade); c->resident_smem = c->smem_bytes; }
+    if (c->resident_smem != c->smem_bytes || c->per_sm_isect <= 0) { kernels_resident_ctas(c->smem_bytes, c->scene.brute, c->scene.staged, &c->per_sm_isect, &c->per_sm_shade); c->resident_smem = c->smem_bytes; }
     const int per_sm_isect = c->per_sm_isect, per_sm_shade = c->per_sm_shade;
     int grid_isect = std::max(1, c->n_sm * per_sm_isect / NSUB) * NSUB, grid_shade = std::max(1, c->n_sm * per_sm_shade / NSUB) * NSUB;
     if (const char* e = getenv("RLPT_GRID_ISECT")) grid_isect = std::max(1, atoi(e)) * NSUB;
@@ -934,7 +981,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
 static int enqueue_merge(rlpt_ctx* c) {
     if (c->p2p_ready && c->cfg.world_size > 1) {
         launch_merge_p2p(c->rm, c->peers, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, ++c->p2p_epoch, c->d_p2p_done, c->stream);
-        c->launches += 2;
+        c->launches += 2; c->p2p_used = true;
         CK(cudaGetLastError());
         return RLPT_OK;
     }
@@ -971,7 +1018,7 @@ static int timed_end(rlpt_ctx* c, int frames) {
     c->phase_used = 0;
     kev_resolve(c);
     CK(cudaGetLastError());
-    return RLPT_OK;
+    return p2p_check(c);
 }
 
 int rlpt_render_default(rlpt_ctx* c, int frames) {
@@ -1087,7 +1134,7 @@ static int ensure_nqt(rlpt_ctx* c, int batch) {
     NqTrainState& st = c->nqt; st.n = n;
     CK(cudaMalloc(&st.loc, sizeof(float4) * n)); CK(cudaMalloc(&st.sloc, sizeof(float4) * n)); CK(cudaMalloc(&st.dir, sizeof(float4) * n)); CK(cudaMalloc(&st.thr, sizeof(float4) * n));
     CK(cudaMalloc(&st.state, 4 * (size_t)n)); CK(cudaMalloc(&st.reward, 4 * (size_t)n)); CK(cudaMalloc(&st.discount, 4 * (size_t)n)); CK(cudaMalloc(&st.action, 4 * (size_t)n));
-    CK(cudaMalloc(&st.alive, 4 * (size_t)(g.max_bounces + 2)));
+    CK(cudaMalloc(&st.alive, 4 * (size_t)(255 + 2)));               // rlpt_config_set accepts max_bounces up to 255; the buffers are reused across such changes
     const int S = (batch + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     CK(cudaMalloc(&c->d_nqt_qcur, sizeof(float) * DQ_OUT * (size_t)n)); CK(cudaMalloc(&c->d_nqt_qnext, sizeof(float) * DQ_OUT * (size_t)S));
     CK(cudaMalloc(&c->d_nqt_targets, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqt_loss, 4)); CK(cudaMemset(c->d_nqt_loss, 0, 4));

@@ -14,16 +14,17 @@ namespace rlpt {
 //   shade[4*gid+1] = (T.x, T.y, T.z, as_float(normal class))
 //   shade[4*gid+2] = (B.x, B.y, B.z, 0)
 //   shade[4*gid+3] = (diffuse_c / pi  rgb, 0)                     [lights: diffuse_p rgb]
-//   bvh[4*node+0..3]: two child boxes + two child links, see rlpt_bvh.cu
+//   bvh4[7*node+0..6]: the 4-wide traversal tree, see rlpt_bvh.cu: six plane records (lo.x, hi.x, lo.y, hi.y, lo.z, hi.z of the four
+//                      children) + four child links; tri4 = the triangle records in LEAF order (a leaf = a run of 1..BVH4_LEAF_MAX
+//                      records) with the primitive id in the third float4's z
 struct SceneDev {
     const float4* tri;
     const float4* shade;
-    const float4* bvh;
-    int n_tri, n_surf, n_light, n_nodes;
+    const float4* bvh4;
+    const float4* tri4;
+    int n_tri, n_surf, n_light, n_nodes4;
     int brute;          // 1: scan all primitives in gid order from shared memory; 0: BVH traversal
-    int smem_tris;      // primitives staged in shared memory (all of them, or 0 when they do not fit)
-    int smem_nodes;     // BVH nodes staged in shared memory: all of them or none (a partly staged tree costs a compare-and-select per node load)
-    int smem_shade;     // 1 when the shading records are staged too
+    int staged;         // 1: the scene is copied into shared memory by every CTA (brute: tri, shade, scan units; BVH: tri4, shade, bvh4); 0: read-only path / L1
     // conservative pre-test of the brute-force scan (rlpt_device.cuh, unit_candidates): pairs of triangles that form a
     // parallelogram are tested together, 4 float4 per pair: (v0, e1.x) (e1.yz, e2.xy) (e2.z, n) (pu, pv, ps, -) with n = e1 x e2
     // and (pu, pv, ps) placing the second triangle in the first one's (u, v). slot_gid[slot] = primitive id: slots 2u, 2u+1 are
@@ -130,11 +131,13 @@ struct PeerTables {
     float* acc_sum[MAX_PEERS]; uint32_t* acc_cnt[MAX_PEERS];
     float* q[MAX_PEERS]; float* cdf[MAX_PEERS]; float* cdf_rows[MAX_PEERS]; uint32_t* visits[MAX_PEERS]; float* irradiance[MAX_PEERS];
     unsigned* flags[MAX_PEERS];
+    unsigned* error;            // this rank's error word (device memory): raised when a wait for a peer times out
     int world, rank;
 };
 void launch_merge_p2p(const RadianceDev& rm, const PeerTables& pt, const float* surf_lum_over_pi, float threshold, unsigned epoch, unsigned* done_counter, cudaStream_t s);
 void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
-                        unsigned long long* counters, size_t smem, cudaStream_t s);
+                        unsigned long long* counters, int* cursor, size_t smem, cudaStream_t s);
+size_t bvh4_scratch_bytes();
 void launch_find_closest(const RadianceDev& rm, const SceneDev& sc, const float* pos, const float* nrm, int n, int* out, cudaStream_t s);
 void launch_voronoi(const FrameParams& p, const FrameDyn& dyn, int grid, size_t smem, cudaStream_t s);
 void launch_frame_mean(const float4* accum, float* rgb, int n, cudaStream_t s);
@@ -146,6 +149,10 @@ int kernels_set_smem_limit(size_t bytes);
 void kernels_resident_ctas(size_t isect_smem, int brute, int staged, int* isect_per_sm, int* shade_per_sm);
 
 // rlpt_bvh.cu: builds the BVH on the GPU from the tri buffer; returns node count and depth; d_bvh is allocated by the callee
-int bvh_build_gpu(const float4* d_tri, int n_tri, float4** d_bvh, int* n_nodes, int* depth, cudaStream_t s);
+// The binary tree (d_bvh, one primitive per leaf; kept for rlpt_scene_bvh_download) is collapsed on the GPU into the 4-wide tree the
+// kernels walk (d_bvh4, d_tri4); leaf_max = primitives per leaf of the wide tree (1..BVH4_LEAF_MAX).
+constexpr int BVH4_LEAF_MAX = 2;
+constexpr int BVH4_EMPTY = -1;                      // child link of an unused slot: reads as a leaf of zero records, so even a NaN ray (every slab test passes) finds nothing in it
+int bvh_build_gpu(const float4* d_tri, int n_tri, int leaf_max, float4** d_bvh, int* n_nodes, int* depth, float4** d_bvh4, int* n_nodes4, int* depth4, float4** d_tri4, cudaStream_t s);
 
 }  // namespace rlpt

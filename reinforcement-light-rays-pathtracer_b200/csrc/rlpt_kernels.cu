@@ -29,8 +29,9 @@ template <bool STAGED>
 struct SceneView {
     const float4* tri_s; const float4* shade_s; const float4* nodes_s; const float4* scan_s; const int* gid_s;
     const float4* tri_g; const float4* shade_g; const float4* nodes_g;
-    int n_tri, n_surf, smem_nodes, brute, det_small, n_units, n_items;
+    int n_tri, n_surf, brute, det_small, n_units, n_items;
     float k1, k2, k3, vmax;
+    // brute force: record of primitive `i`; BVH: record at leaf-order position `i` (tri4, primitive id in the third float4's z)
     __device__ __forceinline__ float4 tri(int i) const { return STAGED ? tri_s[i] : __ldg(tri_g + i); }
     __device__ __forceinline__ float4 shade(int i) const { return STAGED ? shade_s[i] : __ldg(shade_g + i); }
     __device__ __forceinline__ float4 node(int i) const {
@@ -38,29 +39,40 @@ struct SceneView {
     }
 };
 
-// Every CTA copies what fits of the scene into shared memory once (vectorised 16-byte loads, coalesced).
+// Every CTA copies the scene into shared memory once when it fits (vectorised 16-byte loads, coalesced): brute-force scenes
+// their triangles, scan units and slot table, BVH scenes the leaf-ordered triangles and the 4-wide nodes.
 template <bool STAGED, bool SHADE = true>
 __device__ __forceinline__ SceneView<STAGED> stage_scene(const SceneDev& sc) {
     SceneView<STAGED> v;
-    v.tri_g = sc.tri; v.shade_g = sc.shade; v.nodes_g = sc.bvh; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute; v.det_small = sc.det_small;
+    v.tri_g = sc.brute ? sc.tri : sc.tri4; v.shade_g = sc.shade; v.nodes_g = sc.bvh4; v.n_tri = sc.n_tri; v.n_surf = sc.n_surf; v.brute = sc.brute; v.det_small = sc.det_small;
     v.n_units = sc.n_units; v.n_items = sc.n_items; v.k1 = sc.k1; v.k2 = sc.k2; v.k3 = sc.k3; v.vmax = sc.vmax;
-    float4* p = s_scene;
-    int nt = 3 * sc.smem_tris, ns = (SHADE && sc.smem_shade) ? 4 * sc.smem_tris : 0, nn = 4 * sc.smem_nodes;
-    v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns; v.smem_nodes = 4 * sc.smem_nodes;
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) p[i] = __ldg(sc.tri + i);
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) p[nt + ns + i] = __ldg(sc.bvh + i);
-    // brute-force scenes: the parallelogram units of the conservative pre-test (4 float4 each), then the slot -> primitive table
-    const int nu = 4 * sc.n_items, ng = sc.n_units > 0 ? (sc.n_tri + 3) / 4 : 0;
-    v.scan_s = p + nt + ns + nn; v.gid_s = reinterpret_cast<const int*>(p + nt + ns + nn + nu);
-    for (int i = threadIdx.x; i < nu; i += blockDim.x) p[nt + ns + nn + i] = __ldg(sc.scan + i);
-    for (int i = threadIdx.x; i < ng; i += blockDim.x) p[nt + ns + nn + nu + i] = __ldg(reinterpret_cast<const float4*>(sc.slot_gid) + i);
-    __syncthreads();
+    v.tri_s = v.shade_s = v.nodes_s = v.scan_s = nullptr; v.gid_s = nullptr;
+    if (STAGED) {
+        float4* p = s_scene;
+        const int nt = 3 * sc.n_tri, ns = SHADE ? 4 * sc.n_tri : 0, nn = sc.brute ? 0 : 7 * sc.n_nodes4;
+        v.tri_s = p; v.shade_s = p + nt; v.nodes_s = p + nt + ns;
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) p[i] = __ldg(v.tri_g + i);
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) p[nt + i] = __ldg(sc.shade + i);
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) p[nt + ns + i] = __ldg(sc.bvh4 + i);
+        // brute-force scenes: the parallelogram units of the conservative pre-test (4 float4 each), then the slot -> primitive table
+        const int nu = sc.brute ? 4 * sc.n_items : 0, ng = (sc.brute && sc.n_units > 0) ? (sc.n_tri + 3) / 4 : 0;
+        v.scan_s = p + nt + ns + nn; v.gid_s = reinterpret_cast<const int*>(p + nt + ns + nn + nu);
+        for (int i = threadIdx.x; i < nu; i += blockDim.x) p[nt + ns + nn + i] = __ldg(sc.scan + i);
+        for (int i = threadIdx.x; i < ng; i += blockDim.x) p[nt + ns + nn + nu + i] = __ldg(reinterpret_cast<const float4*>(sc.slot_gid) + i);
+        __syncthreads();
+    }
     return v;
 }
 
+__device__ __forceinline__ size_t scene_smem_bytes_dev(const SceneDev& sc) {
+    return sizeof(float4) * ((size_t)3 * sc.n_tri + (size_t)4 * sc.n_tri + (sc.brute ? 0 : (size_t)7 * sc.n_nodes4) + (sc.brute ? (size_t)4 * sc.n_items : 0) +
+                             ((sc.brute && sc.n_units > 0) ? (size_t)(sc.n_tri + 3) / 4 : 0));
+}
+// dynamic shared memory of the staged scene (the kernels that do not stage the shading records simply leave that part unused)
 size_t scene_smem_bytes(const SceneDev& sc) {
-    return sizeof(float4) * ((size_t)3 * sc.smem_tris + (sc.smem_shade ? (size_t)4 * sc.smem_tris : 0) + (size_t)4 * sc.smem_nodes + (size_t)4 * sc.n_items + (sc.n_units > 0 ? (size_t)(sc.n_tri + 3) / 4 : 0));
+    if (!sc.staged) return 0;
+    return sizeof(float4) * ((size_t)3 * sc.n_tri + (size_t)4 * sc.n_tri + (sc.brute ? 0 : (size_t)7 * sc.n_nodes4) + (sc.brute ? (size_t)4 * sc.n_items : 0) +
+                             ((sc.brute && sc.n_units > 0) ? (size_t)(sc.n_tri + 3) / 4 : 0));
 }
 
 // ------------------------------------------------------------------------------------------------ closest hit
@@ -70,69 +82,83 @@ __device__ __forceinline__ TriRec load_tri(const SceneView<STAGED>& v, int gid) 
     return TriRec{ a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y };
 }
 
-__device__ __forceinline__ void slab(float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                     float ox, float oy, float oz, float ix, float iy, float iz, float& tn, float& tf) {
-    float x0 = (lox - ox) * ix, x1 = (hix - ox) * ix;
-    float y0 = (loy - oy) * iy, y1 = (hiy - oy) * iy;
-    float z0 = (loz - oz) * iz, z1 = (hiz - oz) * iz;
-    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
-    tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+// ---- 4-wide BVH (rlpt_bvh.cu, k_collapse4). Per-ray constants of the slab test: inv = 1 / (dir * SCREEN_HEIGHT), noi = -(o * inv)
+// and the ray's octant as record offsets (near plane = lo where the direction is non-negative). The test is the FMA form
+// t = plane * inv - o * inv: against (plane - o) * inv it moves a plane by at most |o| 2^-24 (the rounding of o * inv, seen from the
+// plane's side) -- four orders of magnitude inside the padding every leaf box carries (1e-4 + 1/128 of the primitive's extent),
+// so a primitive the exact solve accepts is still never culled. A direction component of exactly 0 gives inv = inf and NaN where
+// plane and origin have the same sign; fminf / fmaxf drop NaN operands, i.e. that axis is then ignored: conservative as well.
+struct Ray4 { float ix, iy, iz, nox, noy, noz; int sx, sy, sz; };
+__device__ __forceinline__ Ray4 ray4_setup(float ox, float oy, float oz, float sdx, float sdy, float sdz) {
+    Ray4 r; r.ix = 1.f / sdx; r.iy = 1.f / sdy; r.iz = 1.f / sdz;
+    r.nox = -(ox * r.ix); r.noy = -(oy * r.iy); r.noz = -(oz * r.iz);
+    r.sx = sdx < 0.f ? 1 : 0; r.sy = sdy < 0.f ? 1 : 0; r.sz = sdz < 0.f ? 1 : 0;
+    return r;
 }
-
-// One node of the ordered BVH traversal: both child boxes, the exact solve of any leaf child that is hit, then the nearer
-// inner child (the other one goes on the stack). Returns false when the traversal is finished.
-template <bool STAGED, bool COUNT>
-__device__ __forceinline__ bool bvh_visit(const SceneView<STAGED>& v, float ox, float oy, float oz, float a0, float a1, float a2, float ix, float iy, float iz,
-                                          float& best_t, int& best_gid, int& cur, int& top, int* stack, unsigned& n_tri, unsigned& n_box) {
-    float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
-    float tn0, tf0, tn1, tf1;
-    slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
-    slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
-    if (COUNT) n_box += 2;
-    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-    bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
-    // leaf children that are hit: one instance of the exact solve serves both (lanes whose first and lanes whose second child
-    // is the leaf run it together)
-    int pend0 = (h0 && c0 < 0) ? ~c0 : -1, pend1 = (h1 && c1 < 0) ? ~c1 : -1;
-    if (pend0 < 0) { pend0 = pend1; pend1 = -1; }
-    h0 = h0 && c0 >= 0; h1 = h1 && c1 >= 0;
-    while (pend0 >= 0) {
-        const int gid = pend0; pend0 = pend1; pend1 = -1;
-        TriRec r = load_tri(v, gid); float t;
-        if (COUNT) n_tri++;
-        if (tri_solve(r, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+// the four children of node `cur`: entry distances (clamped at 0) and hit flags; links returned as loaded
+template <bool STAGED>
+__device__ __forceinline__ void bvh4_boxes(const SceneView<STAGED>& v, int cur, const Ray4& r, float best_t, float (&tn)[4], bool (&hit)[4], int (&lk)[4]) {
+    const int b = 7 * cur;
+    const float4 nx = v.node(b + r.sx), fx = v.node(b + (r.sx ^ 1)), ny = v.node(b + 2 + r.sy), fy = v.node(b + 2 + (r.sy ^ 1));
+    const float4 nz = v.node(b + 4 + r.sz), fz = v.node(b + 4 + (r.sz ^ 1)), l = v.node(b + 6);
+    const float nxx[4] = { nx.x, nx.y, nx.z, nx.w }, fxx[4] = { fx.x, fx.y, fx.z, fx.w }, nyy[4] = { ny.x, ny.y, ny.z, ny.w }, fyy[4] = { fy.x, fy.y, fy.z, fy.w };
+    const float nzz[4] = { nz.x, nz.y, nz.z, nz.w }, fzz[4] = { fz.x, fz.y, fz.z, fz.w };
+    lk[0] = __float_as_int(l.x); lk[1] = __float_as_int(l.y); lk[2] = __float_as_int(l.z); lk[3] = __float_as_int(l.w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float a = fmaxf(fmaxf(fmaf(nxx[k], r.ix, r.nox), fmaf(nyy[k], r.iy, r.noy)), fmaxf(fmaf(nzz[k], r.iz, r.noz), 0.f));
+        const float f = fminf(fminf(fmaf(fxx[k], r.ix, r.nox), fmaf(fyy[k], r.iy, r.noy)), fminf(fmaf(fzz[k], r.iz, r.noz), best_t));
+        tn[k] = a; hit[k] = a <= f;
     }
-    if (h0 && h1) {
-        bool swap = tn1 < tn0;
-        if (top < 32) stack[top++] = swap ? c0 : c1;
-        cur = swap ? c1 : c0;
-    } else if (h0) cur = c0;
-    else if (h1) cur = c1;
-    else { if (top == 0) return false; cur = stack[--top]; }
-    return true;
 }
+// Inner children that were hit, ordered by entry distance. Key = entry distance with the slot number in its two lowest mantissa
+// bits (entry distances are >= 0, so the bit patterns order like the values; rounding the distance down by two bits only makes a
+// later cull more conservative); 0xffffffff = no child. Five compare-exchanges on integer min / max.
+__device__ __forceinline__ void bvh4_sort(unsigned (&key)[4]) {
+#define RLPT_CE(i, j) { const unsigned lo_ = min(key[i], key[j]), hi_ = max(key[i], key[j]); key[i] = lo_; key[j] = hi_; }
+    RLPT_CE(0, 1) RLPT_CE(2, 3) RLPT_CE(0, 2) RLPT_CE(1, 3) RLPT_CE(1, 2)
+#undef RLPT_CE
+}
+constexpr unsigned B4_NONE = 0xffffffffu;
 
-// The same visit with the leaf children handed back instead of solved (k_isect_bvh queues them for the whole warp).
+// Per-lane traversal of the 4-wide tree with the exact solve done where a leaf is found (stack in local memory): the generic
+// closest_hit used by the run-to-completion kernel, the Neural-Q tracers and the debug view. The wavefront's own closest-hit
+// kernel (k_isect_bvh) and the parity entry point walk the same tree warp-cooperatively (bvh4_trace_warp, below).
 template <bool STAGED, bool COUNT>
-__device__ __forceinline__ bool bvh_visit_defer(const SceneView<STAGED>& v, float ox, float oy, float oz, float ix, float iy, float iz,
-                                                float best_t, int& cur, int& top, int* stack, int& pend0, int& pend1, unsigned& n_box) {
-    float4 n0 = v.node(4 * cur), n1 = v.node(4 * cur + 1), n2 = v.node(4 * cur + 2), n3 = v.node(4 * cur + 3);
-    float tn0, tf0, tn1, tf1;
-    slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ox, oy, oz, ix, iy, iz, tn0, tf0);
-    slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ox, oy, oz, ix, iy, iz, tn1, tf1);
-    if (COUNT) n_box += 2;
-    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-    bool h0 = tn0 <= tf0 && tn0 <= best_t, h1 = tn1 <= tf1 && tn1 <= best_t;
-    pend0 = (h0 && c0 < 0) ? ~c0 : -1; pend1 = (h1 && c1 < 0) ? ~c1 : -1;
-    h0 = h0 && c0 >= 0; h1 = h1 && c1 >= 0;
-    if (h0 && h1) {
-        bool swap = tn1 < tn0;
-        if (top < 32) stack[top++] = swap ? c0 : c1;
-        cur = swap ? c1 : c0;
-    } else if (h0) cur = c0;
-    else if (h1) cur = c1;
-    else { if (top == 0) return false; cur = stack[--top]; }
-    return true;
+__device__ __forceinline__ void bvh4_closest_hit(const SceneView<STAGED>& v, float ox, float oy, float oz, float a0, float a1, float a2, float sdx, float sdy, float sdz,
+                                                 float& best_t, int& best_gid, unsigned& n_tri, unsigned& n_box) {
+    const Ray4 r = ray4_setup(ox, oy, oz, sdx, sdy, sdz);
+    uint2 stack[96]; int top = 0; int cur = 0;
+    while (true) {
+        float tn[4]; bool hit[4]; int lk[4];
+        bvh4_boxes<STAGED>(v, cur, r, best_t, tn, hit, lk);
+        unsigned key[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (COUNT) n_box += lk[k] != BVH4_EMPTY ? 1u : 0u;
+            key[k] = (hit[k] && lk[k] >= 0) ? ((__float_as_uint(tn[k]) & ~3u) | (unsigned)k) : B4_NONE;
+            if (hit[k] && lk[k] < 0) {
+                const int first = (~lk[k]) >> 3, cnt = (~lk[k]) & 7;
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 q0 = v.tri(3 * (first + j)), q1 = v.tri(3 * (first + j) + 1), q2 = v.tri(3 * (first + j) + 2);
+                    const TriRec tr{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y }; const int gid = __float_as_int(q2.z); float t;
+                    if (COUNT) n_tri++;
+                    if (tri_solve(tr, ox, oy, oz, a0, a1, a2, best_t, t) && (t < best_t || (t == best_t && gid < best_gid))) { best_t = t; best_gid = gid; }
+                }
+            }
+        }
+        bvh4_sort(key);
+        if (key[0] != B4_NONE) {
+            if (key[3] != B4_NONE && top < 96) stack[top++] = make_uint2((unsigned)lk[0] + (key[3] & 3u), key[3]);
+            if (key[2] != B4_NONE && top < 96) stack[top++] = make_uint2((unsigned)lk[0] + (key[2] & 3u), key[2]);
+            if (key[1] != B4_NONE && top < 96) stack[top++] = make_uint2((unsigned)lk[0] + (key[1] & 3u), key[1]);
+            cur = lk[0] + (int)(key[0] & 3u);
+        } else {
+            bool found = false;
+            while (top > 0) { const uint2 e = stack[--top]; if (__uint_as_float(e.y & ~3u) <= best_t) { cur = (int)e.x; found = true; break; } }
+            if (!found) return;
+        }
+    }
 }
 
 // Phase 1 of the brute-force scan over the scan units (parallelogram pairs, then single triangles): the slots no early out can
@@ -253,9 +279,7 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
         }
         return;
     }
-    const float ix = 1.f / sdx, iy = 1.f / sdy, iz = 1.f / sdz;
-    int stack[32]; int top = 0; int cur = 0;
-    while (bvh_visit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, ix, iy, iz, best_t, best_gid, cur, top, stack, n_tri, n_box)) {}
+    bvh4_closest_hit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, sdx, sdy, sdz, best_t, best_gid, n_tri, n_box);
 }
 
 // Closest hit for a warp of CAMERA rays: same origin, directions within a pixel or two. Phase 1 is done once per warp instead
@@ -325,19 +349,6 @@ __global__ void __launch_bounds__(BLOCK) k_closest_hit(SceneDev sc, const float*
     if (COUNT) {
         nt = __reduce_add_sync(0xffffffffu, nt); nb = __reduce_add_sync(0xffffffffu, nb);
         if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], (unsigned long long)nt); atomicAdd(&counters[1], (unsigned long long)nb); }
-    }
-}
-
-void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
-                        unsigned long long* counters, size_t smem, cudaStream_t s) {
-    int grid = (n + BLOCK - 1) / BLOCK; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
-    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
-    if (staged) {
-        if (counters) k_closest_hit<true, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
-        else k_closest_hit<true, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
-    } else {
-        if (counters) k_closest_hit<false, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
-        else k_closest_hit<false, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
     }
 }
 
@@ -452,13 +463,13 @@ __device__ __forceinline__ void load_state(const PathQueue& q, int i, PathState&
     float4 a = __ldcs(q.o + i), b = __ldcs(q.d + i), c = __ldcs(q.thr + i); uint32_t m = __ldcs(q.meta + i);
     s.ox = a.x; s.oy = a.y; s.oz = a.z; s.pixel = __float_as_uint(a.w);
     s.dx = b.x; s.dy = b.y; s.dz = b.z; s.cur_brdf = b.w;
-    s.tr = c.x; s.tg = c.y; s.tb = c.z; s.volsec = __float_as_uint(c.w); s.sample = m >> 8;
+    s.tr = c.x; s.tg = c.y; s.tb = c.z; s.volsec = __float_as_uint(c.w); s.sample = m;
 }
 __device__ __forceinline__ void store_state(const PathQueue& q, int slot, const PathState& s, int bounce) {
     __stcs(q.o + slot, make_float4(s.ox, s.oy, s.oz, __uint_as_float(s.pixel)));
     __stcs(q.d + slot, make_float4(s.dx, s.dy, s.dz, s.cur_brdf));
     __stcs(q.thr + slot, make_float4(s.tr, s.tg, s.tb, __uint_as_float(s.volsec)));
-    __stcs(q.meta + slot, (s.sample << 8) | (uint32_t)bounce);
+    __stcs(q.meta + slot, s.sample);          // the full 32-bit sample index: it is a Philox counter word, and frames * ranks * spp passes 2^24 within minutes
 }
 // Sub-queues. A lane's path queue is NSUB independent queues side by side (slots [k * sub_cap, (k + 1) * sub_cap)), each
 // with its own live-path counter per bounce and its own family of CTAs (blockIdx % NSUB == k) that both drains it and
@@ -685,125 +696,237 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
     flush_work_counters(p, n_tri, n_box);
 }
 
-// k_isect for scenes traversed through the BVH. Traversal lengths differ wildly between the rays of a warp (a ray that
-// leaves the mesh is done after a few nodes, one that grazes it visits hundreds): with one ray per thread per pass the
-// bounce-1 launch of Medieval_House ran with 5 of 32 lanes active. Here a lane whose ray is finished takes the next ray of
-// the sub-queue (one atomicAdd on the sub-queue's cursor per refill, for all idle lanes of the warp at once) while its
-// neighbours keep traversing; the warp checks for idle lanes every BVH_BATCH node visits.
+// ---- closest hit through the 4-wide BVH, warp-cooperative (k_isect_bvh, k_closest_hit_bvh).
+// Traversal lengths differ wildly between the rays of a warp (a ray that leaves the mesh is done after a few nodes, one that
+// grazes it visits dozens): a lane whose ray is finished takes the next ray of the pool (one atomicAdd on the pool's cursor per
+// refill, for all idle lanes of the warp at once) while its neighbours keep traversing; the warp looks for idle lanes every
+// BVH_BATCH node visits.
+// Leaf triangles are not solved where they are found: a visit finds a leaf in a few of its 32 lanes, and the exact solve (longer
+// than the four box tests) would run at those few lanes. Each leaf hit goes into a per-warp list in shared memory as
+// (owner lane, triangle record); whenever 32 entries are there the warp solves them at full width: lane j takes entry j, reads the
+// owner's ray from shared memory, and merges an accepted hit into the owner's result with a 64-bit atomicMin in shared memory on
+// bits(|t|) << 32 | primitive << 1 | (t is -0)  -- the lexicographic minimum of (t, primitive id), which is the reference's scan
+// order with strict <, so the order of the solves is free. A ray's best_t is refreshed after every solve round; between rounds
+// the descent prunes with a stale (larger) bound, which only costs box tests. A lane whose traversal is finished keeps its ray
+// until its queued entries are solved ("draining"); the list is emptied whenever the warp is about to refill idle lanes.
+// The traversal stack lives in shared memory ((node, entry-distance key) per entry, B4_STACK entries per lane; deeper entries
+// -- never seen on the bundled scenes -- spill to a local array): entries whose entry distance has meanwhile fallen behind best_t are
+// dropped at pop time without a visit.
 #ifndef RLPT_BVH_BATCH
-#define RLPT_BVH_BATCH 8
+#define RLPT_BVH_BATCH 4
 #endif
 #ifndef RLPT_BVH_REFILL
-#define RLPT_BVH_REFILL 8
+#define RLPT_BVH_REFILL 6
 #endif
 constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
-// Leaf triangles are not solved where they are found: a visit with a leaf hit in 2 or 3 of its 32 lanes made the whole warp
-// walk the exact solve (about as long as the box tests) at 1-3 active lanes -- 45 % of the kernel's issue slots. Instead each
-// leaf hit goes into a per-warp queue in shared memory as (owner lane, primitive); when 32 entries are there the warp solves
-// them at full width: lane j takes entry j, fetches the owner's ray with shuffles, and merges an accepted hit into the owner's
-// result with a 64-bit atomicMin in shared memory on  bits(|t|) << 32 | primitive << 1 | (t is -0)  -- the lexicographic
-// minimum of (t, primitive id), which is the reference's scan order with strict <, so the order of the solves is free.
-// A ray's best_t is refreshed after every solve round; between rounds the descent prunes with a stale (larger) bound, which
-// only costs box tests. A lane whose traversal is finished keeps its ray until its queued entries are solved ("draining");
-// the queue is emptied whenever the warp is about to refill idle lanes.
-constexpr int WQ_CAP = 96;                                             // < 32 left over + at most 64 new entries per visit
+constexpr int B4_STACK = 16;                                             // shared-memory stack entries per lane
+constexpr int B4_SPILL = 80;                                             // local-memory overflow: 3 x depth 30 fits in 96 entries
+constexpr int WQ_CAP = 32 + 32 * 4 * BVH4_LEAF_MAX;                      // < 32 left over + at most 4 leaves of BVH4_LEAF_MAX records per lane and visit
+// per-warp scratch in dynamic shared memory, behind the staged scene
+constexpr int B4_WARP_BYTES = B4_STACK * 32 * 8 + 32 * 8 + WQ_CAP * 4 + 6 * 32 * 4;
+constexpr size_t B4_CTA_BYTES = (size_t)(BLOCK / 32) * B4_WARP_BYTES;
+size_t bvh4_scratch_bytes() { return B4_CTA_BYTES; }
+struct B4Scratch { uint2* stack; unsigned long long* best; unsigned* wq; float* ray; };
+__device__ __forceinline__ B4Scratch b4_scratch(unsigned char* base) {
+    unsigned char* p = base + (threadIdx.x >> 5) * B4_WARP_BYTES;
+    B4Scratch w; w.stack = reinterpret_cast<uint2*>(p); p += B4_STACK * 32 * 8;
+    w.best = reinterpret_cast<unsigned long long*>(p); p += 32 * 8;
+    w.wq = reinterpret_cast<unsigned*>(p); p += WQ_CAP * 4;
+    w.ray = reinterpret_cast<float*>(p);
+    return w;
+}
 template <bool STAGED>
-__device__ __forceinline__ void wq_solve(const SceneView<STAGED>& v, const unsigned* wq, unsigned long long* best, int lo, int n, unsigned lane,
-                                         float ox, float oy, float oz, float a0, float a1, float a2, float& best_t, int& first_pos, unsigned& n_tri) {
-    const unsigned full = 0xffffffffu;
-    const bool mine = (int)lane < n;
-    const unsigned e = mine ? wq[lo + lane] : (lane << 27);
-    const int src = (int)(e >> 27), gid = (int)(e & 0x7ffffffu);
-    const float sox = __shfl_sync(full, ox, src), soy = __shfl_sync(full, oy, src), soz = __shfl_sync(full, oz, src);
-    const float sa0 = __shfl_sync(full, a0, src), sa1 = __shfl_sync(full, a1, src), sa2 = __shfl_sync(full, a2, src);
-    const float sbt = __shfl_sync(full, best_t, src);
-    if (mine) {
-        TriRec r = load_tri(v, gid); float t;
+__device__ __forceinline__ void wq_solve(const SceneView<STAGED>& v, const B4Scratch& w, int lo, int n, unsigned lane, float& best_t, int& first_pos, unsigned& n_tri) {
+    if ((int)lane < n) {
+        const unsigned e = w.wq[lo + lane];
+        const int src = (int)(e >> 27), pos = (int)(e & 0x7ffffffu);
+        const float4 q0 = v.tri(3 * pos), q1 = v.tri(3 * pos + 1), q2 = v.tri(3 * pos + 2);
+        const TriRec tr{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y }; const int gid = __float_as_int(q2.z);
+        const float bt = __uint_as_float((unsigned)(w.best[src] >> 32));
+        float t;
         n_tri++;
-        if (tri_solve(r, sox, soy, soz, sa0, sa1, sa2, sbt, t) && t < T_MISS) atomicMin(best + src, hit_key(t, gid));
+        if (tri_solve(tr, w.ray[src], w.ray[32 + src], w.ray[64 + src], w.ray[96 + src], w.ray[128 + src], w.ray[160 + src], bt, t) && t < T_MISS) atomicMin(w.best + src, hit_key(t, gid));
     }
     __syncwarp();
     if (first_pos >= lo) first_pos = 0x7fffffff;                        // everything of mine at or above lo has been solved
-    best_t = __uint_as_float((unsigned)(best[lane] >> 32));
+    best_t = __uint_as_float((unsigned)(w.best[lane] >> 32));
 }
-template <bool STAGED, bool PRIMARY>
-__global__ void __launch_bounds__(BLOCK) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
-    __shared__ unsigned s_wq[(BLOCK / 32) * WQ_CAP];
-    __shared__ unsigned long long s_best[BLOCK];
-    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
-    if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
-    SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
-    const PathQueue qi = p.q[bounce & 1];
+// Src: int n (rays in the pool), fetch(i, ox, oy, oz, dx, dy, dz) -> the normalised ray i, emit(i, t, gid) <- its closest hit
+template <bool STAGED, class Src>
+__device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, const Src& src, int* cursor, float H, unsigned char* scratch, unsigned& n_tri, unsigned& n_box) {
     const unsigned full = 0xffffffffu, lane = threadIdx.x & 31;
-    unsigned* wq = s_wq + (threadIdx.x >> 5) * WQ_CAP;
-    unsigned long long* best = s_best + (threadIdx.x & ~31u);
-    int* cursor = p.cursor + (bounce * NSUB + (int)(blockIdx.x % NSUB)) * COUNT_STRIDE;
-    unsigned n_tri = 0, n_box = 0;
-    const float H = (float)p.height;
+    const B4Scratch w = b4_scratch(scratch);
+    uint2* stack = w.stack + lane;                                      // entry k at stack[32 k]: conflict-free
+    uint2 spill[B4_SPILL];
     bool have = false, drain = false, exhausted = false;
     int i = 0, cur = 0, top = 0, count = 0, first_pos = 0x7fffffff; float best_t = T_MISS;
-    float ox = 0, oy = 0, oz = 0, a0 = 0, a1 = 0, a2 = 0, ix = 0, iy = 0, iz = 0;
-    int stack[32];
+    Ray4 r{};
     auto finish = [&]() {                                               // the ray's result: (t, primitive) from the merged key
-        const unsigned long long k = best[lane];
+        const unsigned long long k = w.best[lane];
         const unsigned lo = (unsigned)k;
         const float t = __uint_as_float((unsigned)(k >> 32) | (lo == 0xffffffffu ? 0u : (lo & 1u) << 31));
-        __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(lo == 0xffffffffu ? -1 : (int)(lo >> 1))));
+        src.emit(i, t, lo == 0xffffffffu ? -1 : (int)(lo >> 1));
     };
+    auto push = [&](unsigned node, unsigned key) { if (top < B4_STACK) stack[32 * top] = make_uint2(node, key); else if (top < B4_STACK + B4_SPILL) spill[top - B4_STACK] = make_uint2(node, key); ++top; };
     while (true) {
         const unsigned idle = __ballot_sync(full, !have);               // idle or draining
         if (idle == full || __popc(idle) >= BVH_REFILL) {
-            while (count > 0) {                                         // empty the queue: draining lanes become idle
+            while (count > 0) {                                         // empty the list: draining lanes become idle
                 const int n = count < 32 ? count : 32;
                 count -= n;
-                wq_solve<STAGED>(v, wq, best, count, n, lane, ox, oy, oz, a0, a1, a2, best_t, first_pos, n_tri);
+                wq_solve<STAGED>(v, w, count, n, lane, best_t, first_pos, n_tri);
             }
             if (drain) { finish(); drain = false; }
             if (!exhausted) {
                 const int leader = __ffs(idle) - 1; int base = 0;
                 if ((int)lane == leader) base = atomicAdd(cursor, __popc(idle));
                 base = __shfl_sync(full, base, leader);
-                exhausted = base + __popc(idle) >= sq.n;
+                exhausted = base + __popc(idle) >= src.n;
                 if (!have) {
                     i = base + __popc(idle & lanemask_lt());
-                    if (i < sq.n) {
-                        float dx, dy, dz;
-                        if (PRIMARY) { PathState s; primary_state(p, dyn, sq.base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
-                        else { float4 a = __ldcs(qi.o + sq.base + i), b = __ldcs(qi.d + sq.base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
-                        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
-                            int slot = atomicAdd(p.capture_n, 1);
-                            if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
-                        }
+                    if (i < src.n) {
+                        float ox, oy, oz, dx, dy, dz;
+                        src.fetch(i, ox, oy, oz, dx, dy, dz);
                         const float sdx = RLPT_MUL(dx, H), sdy = RLPT_MUL(dy, H), sdz = RLPT_MUL(dz, H);
-                        a0 = RLPT_SUB(0.f, sdx); a1 = RLPT_SUB(0.f, sdy); a2 = RLPT_SUB(0.f, sdz);
-                        ix = 1.f / sdx; iy = 1.f / sdy; iz = 1.f / sdz;
-                        best_t = T_MISS; best[lane] = KEY_MISS; cur = 0; top = 0; have = true;
+                        w.ray[lane] = ox; w.ray[32 + lane] = oy; w.ray[64 + lane] = oz;
+                        w.ray[96 + lane] = RLPT_SUB(0.f, sdx); w.ray[128 + lane] = RLPT_SUB(0.f, sdy); w.ray[160 + lane] = RLPT_SUB(0.f, sdz);
+                        r = ray4_setup(ox, oy, oz, sdx, sdy, sdz);
+                        best_t = T_MISS; w.best[lane] = KEY_MISS; cur = 0; top = 0; have = true;
                     }
                 }
                 __syncwarp();
             }
         }
-        if (!__any_sync(full, have)) break;                             // nothing traversing: the queue is empty here too
+        if (!__any_sync(full, have)) break;                             // nothing traversing: the list is empty here too
 #pragma unroll 1
         for (int step = 0; step < BVH_BATCH; ++step) {
-            int pend0 = -1, pend1 = -1;
-            if (have && !bvh_visit_defer<STAGED, true>(v, ox, oy, oz, ix, iy, iz, best_t, cur, top, stack, pend0, pend1, n_box)) { have = false; drain = true; }
-            const unsigned m0 = __ballot_sync(full, pend0 >= 0), m1 = __ballot_sync(full, pend1 >= 0);
-            if (m0 | m1) {
-                const int pos0 = count + __popc(m0 & lanemask_lt()), pos1 = count + __popc(m0) + __popc(m1 & lanemask_lt());
-                if (pend0 >= 0) { wq[pos0] = (lane << 27) | (unsigned)pend0; first_pos = min(first_pos, pos0); }
-                if (pend1 >= 0) { wq[pos1] = (lane << 27) | (unsigned)pend1; first_pos = min(first_pos, pos1); }
-                count += __popc(m0) + __popc(m1);
+            int lf[4] = { 0, 0, 0, 0 }; int c = 0;                      // leaf links hit by this visit (0 = none), records in them
+            if (have) {
+                float tn[4]; bool hit[4]; int lk[4];
+                bvh4_boxes<STAGED>(v, cur, r, best_t, tn, hit, lk);
+                unsigned key[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    n_box += lk[k] != BVH4_EMPTY ? 1u : 0u;
+                    key[k] = (hit[k] && lk[k] >= 0) ? ((__float_as_uint(tn[k]) & ~3u) | (unsigned)k) : B4_NONE;
+                    if (hit[k] && lk[k] < 0) { lf[k] = ~lk[k]; c += lf[k] & 7; }
+                }
+                bvh4_sort(key);
+                if (key[0] != B4_NONE) {
+                    if (key[3] != B4_NONE) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
+                    if (key[2] != B4_NONE) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
+                    if (key[1] != B4_NONE) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
+                    cur = lk[0] + (int)(key[0] & 3u);
+                } else {
+                    bool found = false;
+                    while (top > 0) {
+                        --top;
+                        const uint2 e = top < B4_STACK ? stack[32 * top] : spill[min(top - B4_STACK, B4_SPILL - 1)];
+                        if (__uint_as_float(e.y & ~3u) <= best_t) { cur = (int)e.x; found = true; break; }
+                    }
+                    if (!found) { have = false; drain = true; }
+                }
+            }
+            if (__any_sync(full, c > 0)) {
+                int pos = c;                                            // inclusive warp scan of the record counts
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(full, pos, d); if ((int)lane >= d) pos += y; }
+                const int total = __shfl_sync(full, pos, 31);
+                pos = count + pos - c;
+                if (c > 0) {
+                    first_pos = min(first_pos, pos);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int first = lf[k] >> 3, cnt = lf[k] & 7;
+#pragma unroll
+                        for (int j = 0; j < BVH4_LEAF_MAX; ++j) if (j < cnt) w.wq[pos++] = (lane << 27) | (unsigned)(first + j);
+                    }
+                }
+                count += total;
                 __syncwarp();
                 while (count >= 32) {
                     count -= 32;
-                    wq_solve<STAGED>(v, wq, best, count, 32, lane, ox, oy, oz, a0, a1, a2, best_t, first_pos, n_tri);
+                    wq_solve<STAGED>(v, w, count, 32, lane, best_t, first_pos, n_tri);
                 }
             }
             if (drain && first_pos == 0x7fffffff) { finish(); drain = false; }
         }
     }
+}
+
+template <bool PRIMARY>
+struct QueueRays {
+    const FrameParams& p; const FrameDyn& dyn; PathQueue qi; int base, n, bounce;
+    __device__ __forceinline__ void fetch(int i, float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) const {
+        if (PRIMARY) { PathState s; primary_state(p, dyn, base + i, s); ox = s.ox; oy = s.oy; oz = s.oz; dx = s.dx; dy = s.dy; dz = s.dz; }
+        else { const float4 a = __ldcs(qi.o + base + i), b = __ldcs(qi.d + base + i); ox = a.x; oy = a.y; oz = a.z; dx = b.x; dy = b.y; dz = b.z; }
+        if (dyn.capture_max > 0 && bounce == dyn.capture_bounce) {
+            const int slot = atomicAdd(p.capture_n, 1);
+            if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
+        }
+    }
+    __device__ __forceinline__ void emit(int i, float t, int gid) const { __stcs(p.hit + base + i, make_float2(t, __int_as_float(gid))); }
+};
+template <bool STAGED, bool PRIMARY>
+__global__ void __launch_bounds__(BLOCK, 3) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+    const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
+    if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
+    SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(s_scene) + (STAGED ? scene_smem_bytes_dev(p.scene) : 0);
+    int* cursor = p.cursor + (bounce * NSUB + (int)(blockIdx.x % NSUB)) * COUNT_STRIDE;
+    unsigned n_tri = 0, n_box = 0;
+    const QueueRays<PRIMARY> src{ p, dyn, p.q[bounce & 1], sq.base, sq.n, bounce };
+    bvh4_trace_warp<STAGED>(v, src, cursor, (float)p.height, scratch, n_tri, n_box);
     flush_work_counters(p, n_tri, n_box);
+}
+
+// the parity entry point rlpt_closest_hit through the same warp-cooperative traversal (scenes walked through the BVH)
+struct ArrayRays {
+    const float* org; const float* dir; int n, n_surf; int* type; int* index; float* t_out;
+    __device__ __forceinline__ void fetch(int i, float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) const {
+        const f3 d = normalize_ref(f3{ dir[3 * i], dir[3 * i + 1], dir[3 * i + 2] });
+        ox = org[3 * i]; oy = org[3 * i + 1]; oz = org[3 * i + 2]; dx = d.x; dy = d.y; dz = d.z;
+    }
+    __device__ __forceinline__ void emit(int i, float t, int gid) const {
+        type[i] = gid < 0 ? 0 : (gid < n_surf ? 2 : 1);
+        index[i] = gid < 0 ? -1 : (gid < n_surf ? gid : gid - n_surf);
+        t_out[i] = t;
+    }
+};
+template <bool STAGED>
+__global__ void __launch_bounds__(BLOCK, 3) k_closest_hit_bvh(SceneDev sc, const float* __restrict__ org, const float* __restrict__ dir, int n, float H,
+                                                              int* __restrict__ type, int* __restrict__ index, float* __restrict__ t_out,
+                                                              unsigned long long* __restrict__ counters, int* __restrict__ cursor) {
+    SceneView<STAGED> v = stage_scene<STAGED, false>(sc);
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(s_scene) + (STAGED ? scene_smem_bytes_dev(sc) : 0);
+    unsigned nt = 0, nb = 0;
+    const ArrayRays src{ org, dir, n, sc.n_surf, type, index, t_out };
+    bvh4_trace_warp<STAGED>(v, src, cursor, H, scratch, nt, nb);
+    if (counters) {
+        nt = __reduce_add_sync(0xffffffffu, nt); nb = __reduce_add_sync(0xffffffffu, nb);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], (unsigned long long)nt); atomicAdd(&counters[1], (unsigned long long)nb); }
+    }
+}
+
+void launch_closest_hit(const SceneDev& sc, const float* org, const float* dir, int n, float H, int* type, int* index, float* t,
+                        unsigned long long* counters, int* cursor, size_t smem, cudaStream_t s) {
+    int grid = (n + BLOCK - 1) / BLOCK; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    const bool staged = sc.staged != 0;
+    if (!sc.brute) {
+        // warp-cooperative traversal (the code k_isect_bvh runs): rays are handed out through `cursor` (zeroed here)
+        cudaMemsetAsync(cursor, 0, sizeof(int), s);
+        if (grid > 148 * 3) grid = 148 * 3;
+        if (staged) k_closest_hit_bvh<true><<<grid, BLOCK, smem + B4_CTA_BYTES, s>>>(sc, org, dir, n, H, type, index, t, counters, cursor);
+        else k_closest_hit_bvh<false><<<grid, BLOCK, B4_CTA_BYTES, s>>>(sc, org, dir, n, H, type, index, t, counters, cursor);
+        return;
+    }
+    if (staged) {
+        if (counters) k_closest_hit<true, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+        else k_closest_hit<true, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+    } else {
+        if (counters) k_closest_hit<false, true><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+        else k_closest_hit<false, false><<<grid, BLOCK, smem, s>>>(sc, org, dir, n, H, type, index, t, counters);
+    }
 }
 
 // Split, second half: shading records come through the read-only path (2.4 KB for Cornell: L1-resident), no staging
@@ -856,11 +979,11 @@ __global__ void __launch_bounds__(BLOCK) k_voronoi(const __grid_constant__ Frame
 }
 void launch_voronoi(const FrameParams& p, const FrameDyn& dyn, int grid, size_t smem, cudaStream_t s) {
     const SceneDev& sc = p.scene;
-    if (sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes) k_voronoi<true><<<grid, BLOCK, smem, s>>>(p, dyn);
+    if (sc.staged) k_voronoi<true><<<grid, BLOCK, smem, s>>>(p, dyn);
     else k_voronoi<false><<<grid, BLOCK, smem, s>>>(p, dyn);
 }
 
-static bool scene_staged(const SceneDev& sc) { return sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes; }
+static bool scene_staged(const SceneDev& sc) { return sc.staged != 0; }
 template <bool SARSA, bool PRIMARY, bool TAIL>
 static void launch_bounce_t(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     if (scene_staged(p.scene)) k_bounce<true, SARSA, PRIMARY, TAIL><<<grid, BLOCK, smem, s>>>(p, dyn, bounce);
@@ -878,8 +1001,9 @@ void launch_tail(const FrameParams& p, const FrameDyn& dyn, int method, int boun
 void launch_isect(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     const bool staged = scene_staged(p.scene);
     if (!p.scene.brute && p.cursor) {
-        if (bounce == 0) { if (staged) k_isect_bvh<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_isect_bvh<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
-        else { if (staged) k_isect_bvh<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_isect_bvh<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
+        const size_t sm = smem + B4_CTA_BYTES;
+        if (bounce == 0) { if (staged) k_isect_bvh<true, true><<<grid, BLOCK, sm, s>>>(p, dyn, 0); else k_isect_bvh<false, true><<<grid, BLOCK, sm, s>>>(p, dyn, 0); }
+        else { if (staged) k_isect_bvh<true, false><<<grid, BLOCK, sm, s>>>(p, dyn, bounce); else k_isect_bvh<false, false><<<grid, BLOCK, sm, s>>>(p, dyn, bounce); }
         return;
     }
     if (bounce == 0) { if (staged) k_isect<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_isect<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
@@ -920,7 +1044,7 @@ __global__ void __launch_bounds__(BLOCK) k_nq_trace(const __grid_constant__ Fram
                 if (i % p.spp == 0) atomicAdd(&p.accum[pixel].w, (float)p.spp);
             } else {
                 float4 a = qi.o[i], b = qi.d[i], c = qi.thr[i]; uint32_t m = qi.meta[i];
-                pixel = __float_as_uint(a.w); sample = m >> 8; tr = c.x; tg = c.y; tb = c.z;
+                pixel = __float_as_uint(a.w); sample = m; tr = c.x; tg = c.y; tb = c.z;
                 ox = RLPT_FMA(RAY_EPS, b.x, a.x); oy = RLPT_FMA(RAY_EPS, b.y, a.y); oz = RLPT_FMA(RAY_EPS, b.z, a.z);      // position + dir * 0.00001f (:439)
                 f3 nn = normalize_ref(f3{ b.x, b.y, b.z }); dx = nn.x; dy = nn.y; dz = nn.z;
             }
@@ -954,7 +1078,7 @@ __global__ void __launch_bounds__(BLOCK) k_nq_trace(const __grid_constant__ Fram
                 qo.o[slot] = make_float4(hx, hy, hz, __uint_as_float(pixel));
                 qo.d[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(gid));
                 qo.thr[slot] = make_float4(tr, tg, tb, 0.f);
-                qo.meta[slot] = (sample << 8) | (uint32_t)(bounce + 1);
+                qo.meta[slot] = sample;
             }
         }
     }
@@ -965,7 +1089,7 @@ __global__ void __launch_bounds__(BLOCK) k_nq_trace(const __grid_constant__ Fram
 }
 void launch_nq_trace(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     const SceneDev& sc = p.scene;
-    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    bool staged = sc.staged != 0;
     if (bounce == 0) { if (staged) k_nq_trace<true, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); else k_nq_trace<false, true><<<grid, BLOCK, smem, s>>>(p, dyn, 0); }
     else { if (staged) k_nq_trace<true, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); else k_nq_trace<false, false><<<grid, BLOCK, smem, s>>>(p, dyn, bounce); }
 }
@@ -980,7 +1104,7 @@ __global__ void __launch_bounds__(BLOCK) k_nq_sample(const __grid_constant__ Fra
     const int n = p.counts[bounce];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 a = qu.o[i], b = qu.d[i], c = qu.thr[i]; const uint32_t m = qu.meta[i];
-        const int gid = __float_as_int(b.w); const uint32_t pixel = __float_as_uint(a.w), sample = m >> 8;
+        const int gid = __float_as_int(b.w); const uint32_t pixel = __float_as_uint(a.w), sample = m;
         float4 sN = __ldg(p.scene.shade + 4 * gid), sT = __ldg(p.scene.shade + 4 * gid + 1), sB = __ldg(p.scene.shade + 4 * gid + 2);
         f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
         float u0, u1, u2, u3; draw4(p.seed, pixel, sample, (uint32_t)bounce, PURPOSE_NQ, u0, u1, u2, u3);
@@ -1118,7 +1242,7 @@ __global__ void __launch_bounds__(BLOCK) k_nqt_trace(const __grid_constant__ Fra
 }
 void launch_nqt_trace(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, int grid, size_t smem, cudaStream_t s) {
     const SceneDev& sc = p.scene;
-    bool staged = sc.smem_tris == sc.n_tri && sc.smem_shade && sc.smem_nodes == sc.n_nodes;
+    bool staged = sc.staged != 0;
     if (staged) k_nqt_trace<true><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce); else k_nqt_trace<false><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce);
 }
 
@@ -1172,8 +1296,8 @@ void kernels_resident_ctas(size_t isect_smem, int brute, int staged, int* isect_
     int a = 0, b = 0;
     cudaError_t e;
     if (brute) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect<true, false>, BLOCK, isect_smem);
-    else if (staged) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<true, false>, BLOCK, isect_smem);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<false, false>, BLOCK, isect_smem);
+    else if (staged) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<true, false>, BLOCK, isect_smem + B4_CTA_BYTES);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_isect_bvh<false, false>, BLOCK, isect_smem + B4_CTA_BYTES);
     if (e != cudaSuccess) a = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_shade<true, false>, BLOCK, 0) != cudaSuccess) b = 0;
     (void)cudaGetLastError();
@@ -1192,6 +1316,7 @@ int kernels_set_smem_limit(size_t bytes) {
     RLPT_SET((k_nq_trace<true, true>)); RLPT_SET((k_nq_trace<true, false>)); RLPT_SET((k_nq_trace<false, true>)); RLPT_SET((k_nq_trace<false, false>));
     RLPT_SET((k_voronoi<true>)); RLPT_SET((k_voronoi<false>));
     RLPT_SET((k_closest_hit<true, true>)); RLPT_SET((k_closest_hit<true, false>)); RLPT_SET((k_closest_hit<false, true>)); RLPT_SET((k_closest_hit<false, false>));
+    RLPT_SET((k_closest_hit_bvh<true>)); RLPT_SET((k_closest_hit_bvh<false>));
 #undef RLPT_SET
     return (int)e;
 }
@@ -1266,15 +1391,32 @@ void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float th
 //          all ranks' announcements, after which the local tables are complete and nobody reads the local accumulators
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// A rank that never arrives (it skipped its merge, failed before it, or rebuilt its map on its own) must not hang the others inside a
+// kernel: every wait gives up after P2P_TIMEOUT_NS of %globaltimer and raises the rank's error word (pt.error, checked by the
+// host after every merge; the exchange is then marked broken and the frame fails with RLPT_ERR_COLLECTIVE).
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ bool wait_flag(const unsigned* p, unsigned epoch, unsigned* error) {
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+        __nanosleep(200);
+        if (globaltimer_ns() - t0 > P2P_TIMEOUT_NS || *reinterpret_cast<volatile unsigned*>(error) != 0u) { atomicExch(error, 1u); return false; }
+    }
+    return true;
+}
 __global__ void __launch_bounds__(BLOCK) k_merge_cdf_p2p(RadianceDev rm, const __grid_constant__ PeerTables pt, const float* __restrict__ surf_lum_over_pi, float threshold,
                                                          unsigned epoch, unsigned* done_counter) {
     const unsigned full = 0xffffffffu;
+    __shared__ int s_ok;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) { __threadfence_system(); for (int r = 0; r < pt.world; ++r) st_release_sys(pt.flags[r] + pt.rank, epoch); }
         const unsigned* mine = pt.flags[pt.rank];
-        for (int r = 0; r < pt.world; ++r) while ((int)(ld_acquire_sys(mine + r) - epoch) < 0) __nanosleep(200);
+        bool ok = true;
+        for (int r = 0; r < pt.world && ok; ++r) ok = wait_flag(mine + r, epoch, pt.error);
+        s_ok = ok ? 1 : 0;
     }
     __syncthreads();
+    if (!s_ok) return;                                                    // a peer never announced: touch nothing of anybody's tables
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int v0 = (int)((long long)rm.n_vol * pt.rank / pt.world), v1 = (int)((long long)rm.n_vol * (pt.rank + 1) / pt.world);
     for (int vol = v0 + warp; vol < v1; vol += nwarps) {
@@ -1344,14 +1486,14 @@ __global__ void __launch_bounds__(BLOCK) k_merge_cdf_p2p(RadianceDev rm, const _
         }
     }
 }
-__global__ void k_wait_peers(const unsigned* __restrict__ flags, int world, unsigned epoch) {
-    if (threadIdx.x < (unsigned)world) while ((int)(ld_acquire_sys(flags + MAX_PEERS + threadIdx.x) - epoch) < 0) __nanosleep(200);
+__global__ void k_wait_peers(const unsigned* __restrict__ flags, int world, unsigned epoch, unsigned* error) {
+    if (threadIdx.x < (unsigned)world) wait_flag(flags + MAX_PEERS + threadIdx.x, epoch, error);
 }
 void launch_merge_p2p(const RadianceDev& rm, const PeerTables& pt, const float* surf_lum_over_pi, float threshold, unsigned epoch, unsigned* done_counter, cudaStream_t s) {
     const int slice = rm.n_vol / pt.world + 1, warps_per_block = BLOCK / 32;
     int grid = (slice + warps_per_block - 1) / warps_per_block; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
     k_merge_cdf_p2p<<<grid, BLOCK, 0, s>>>(rm, pt, surf_lum_over_pi, threshold, epoch, done_counter);
-    k_wait_peers<<<1, 32, 0, s>>>(pt.flags[pt.rank], pt.world, epoch);
+    k_wait_peers<<<1, 32, 0, s>>>(pt.flags[pt.rank], pt.world, epoch, pt.error);
 }
 
 // ------------------------------------------------------------------------------------------------ frame buffer

@@ -39,7 +39,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, 
 # every symbol include/rlpt.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
     "rlpt_last_error", "rlpt_version", "rlpt_ctx_create", "rlpt_ctx_destroy", "rlpt_sync", "rlpt_stream", "rlpt_config_default", "rlpt_config_set",
-    "rlpt_config_get", "rlpt_set_allreduce", "rlpt_scene_upload", "rlpt_scene_info", "rlpt_scene_bvh_download", "rlpt_camera_set", "rlpt_closest_hit",
+    "rlpt_config_get", "rlpt_set_allreduce", "rlpt_scene_upload", "rlpt_scene_info", "rlpt_scene_bvh_download", "rlpt_scene_bvh4_info", "rlpt_scene_bvh4_download", "rlpt_camera_set", "rlpt_closest_hit",
     "rlpt_closest_hit_device", "rlpt_radiance_map_build", "rlpt_radiance_map_info", "rlpt_radiance_map_tree", "rlpt_radiance_map_find_closest",
     "rlpt_radiance_map_set_q", "rlpt_radiance_map_update_distributions", "rlpt_radiance_map_download", "rlpt_radiance_map_delta_download",
     "rlpt_radiance_map_save_q", "rlpt_radiance_map_load_q", "rlpt_render_default", "rlpt_render_sarsa", "rlpt_sarsa_trace", "rlpt_sarsa_merge",
@@ -165,6 +165,15 @@ class Context:
         a = np.zeros((n, 16), np.float32)
         self._ck(self.L.rlpt_scene_bvh_download(self.h, _p(a), n))
         return a
+
+    def bvh4_download(self):
+        """the 4-wide tree the kernels walk: (nodes [n, 28] float32, record_gid [n_primitives] int32, depth, leaf_max)"""
+        v = [ctypes.c_int() for _ in range(3)]
+        self._ck(self.L.rlpt_scene_bvh4_info(self.h, *[ctypes.byref(x) for x in v]))
+        info = self.scene_info(); m = info["n_surfaces"] + info["n_lights"]
+        a = np.zeros((v[0].value, 28), np.float32); g = np.zeros(m, np.int32)
+        self._ck(self.L.rlpt_scene_bvh4_download(self.h, _p(a), v[0].value, _p(g), m))
+        return a, g, v[1].value, v[2].value
 
     def camera_set(self, pos, yaw_y=0.0, yaw_x=0.0):
         p = _f32(list(pos)[:3] + [1.0])

@@ -30,6 +30,20 @@ def golden_scenes():
 
 
 @pytest.fixture(scope="session")
+def all_scenes(golden_scenes):
+    """the bundled scenes plus the two presets of BASELINE.json configs[2] / [3] (tests/golden/make_presets.py): door_room_lit, medieval_norm"""
+    z = np.load(os.path.join(GOLDEN, "scene_presets.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    out = dict(golden_scenes)
+    out.update({n: {k.split("/")[1]: z[k] for k in z.files if k.startswith(n + "/")} for n in names})
+    return out
+
+
+# camera and ENVIRONMENT_LIGHT of the BASELINE.json configurations (G/main.cu:100-104; medieval: SURVEY section 7 preset)
+CONFIG_SCENES = {"cornell": ((0.0, 0.0, -3.0), 0.0), "door_room_lit": ((0.0, 0.5, -0.9), 0.0), "archway": ((-1.0, 0.2, -0.99), 0.0), "medieval_norm": ((0.0, 0.0, -3.0), 1.0)}
+
+
+@pytest.fixture(scope="session")
 def golden_hits():
     z = np.load(os.path.join(GOLDEN, "closest_hit.npz"))
     names = sorted({k.split("/")[0] for k in z.files})
@@ -62,6 +76,15 @@ def ref_cuda():
     if not Reference.available("cuda"):
         pytest.skip("oracle/_ref/libref_cuda.so not built")
     return Reference("cuda")
+
+
+@pytest.fixture(scope="session")
+def ref_cuda_env1():
+    """the reference's kernels built with ENVIRONMENT_LIGHT 1 (a compile-time constant there): oracle/build_ref.sh cuda 512 512 32 _env1 with RLPT_ORACLE_ENV=1.0f"""
+    from checkers import Reference
+    if not Reference.available("cuda", "_env1"):
+        pytest.skip("oracle/_ref/libref_cuda_env1.so not built")
+    return Reference("cuda", "_env1")
 
 
 @pytest.fixture()

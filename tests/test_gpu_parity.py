@@ -94,6 +94,51 @@ def test_bvh_is_built_on_device_and_encloses_scene(ctx, golden_scenes):
         assert np.all(nodes[is_leaf][:, list(a)] <= lo[gid]) and np.all(nodes[is_leaf][:, list(b)] >= hi[gid])
 
 
+@pytest.mark.parametrize("name", ["archway", "complex_light_room", "Medieval_House"])
+@pytest.mark.parametrize("leaf_max", [1, 2])
+def test_bvh4_collapse_is_a_valid_tree(golden_scenes, monkeypatch, name, leaf_max):
+    """The 4-wide tree the kernels walk (binary tree collapsed on the GPU, rlpt_bvh.cu k_collapse4): every node is referenced by
+    exactly one parent, inner children come first and are consecutive, every primitive sits in exactly one leaf of at most
+    leaf_max records, every child box encloses what is below it, unused slots cannot be hit."""
+    import rlpt
+    monkeypatch.setenv("RLPT_BVH_LEAF", str(leaf_max))
+    s = golden_scenes[name]
+    c = rlpt.Context(0)
+    try:
+        load_scene(c, s)
+        nodes, gid, depth, lm = c.bvh4_download()
+    finally:
+        c.close()
+    n = len(s["sv"]) + len(s["lv"])
+    assert lm == leaf_max and sorted(gid.tolist()) == list(range(n)) and 1 <= depth <= 30
+    links = nodes[:, 24:28].view(np.int32); planes = nodes[:, :24].reshape(-1, 6, 4)
+    v = np.concatenate([s["sv"], s["lv"]]).reshape(-1, 3, 3); plo, phi = v.min(1), v.max(1)
+    seen_nodes, seen_rec = np.zeros(len(nodes), int), np.zeros(n, int); seen_nodes[0] = 1
+    lo_of, hi_of = np.full((len(nodes), 3), np.inf), np.full((len(nodes), 3), -np.inf)        # bounds of everything below a node
+    for i in range(len(nodes) - 1, -1, -1):                                                  # children have larger indices (breadth-first numbering)
+        kinds = ["inner" if l >= 0 else ("empty" if l == -1 else "leaf") for l in links[i]]
+        ni = kinds.count("inner")
+        assert kinds[:ni] == ["inner"] * ni and "inner" not in kinds[ni:] and kinds.count("empty") <= 2
+        assert all(k == "empty" for k in kinds[kinds.index("empty"):]) if "empty" in kinds else True
+        for k in range(4):
+            lo, hi = planes[i, 0::2, k], planes[i, 1::2, k]
+            if kinds[k] == "empty":
+                assert np.all(lo > hi)
+                continue
+            if kinds[k] == "inner":
+                ch = links[i, k]
+                assert ch == links[i, 0] + k and ch > i
+                seen_nodes[ch] += 1; clo, chi = lo_of[ch], hi_of[ch]
+            else:
+                first, cnt = (~links[i, k]) >> 3, (~links[i, k]) & 7
+                assert 1 <= cnt <= leaf_max
+                g = gid[first:first + cnt]; seen_rec[first:first + cnt] += 1
+                clo, chi = plo[g].min(0), phi[g].max(0)
+            assert np.all(lo <= clo) and np.all(hi >= chi)
+            lo_of[i] = np.minimum(lo_of[i], lo); hi_of[i] = np.maximum(hi_of[i], hi)
+    assert np.all(seen_nodes == 1) and np.all(seen_rec == 1)
+
+
 def test_sah_and_lbvh_builds_agree_on_every_hit(golden_scenes, golden_hits, monkeypatch):
     """Both GPU builders (binned SAH, the default up to 131072 primitives; Morton-order LBVH for larger scenes, forced here with
     RLPT_BVH_BUILD=lbvh) produce valid trees with identical closest hits; the SAH tree needs fewer box tests."""
@@ -148,12 +193,17 @@ def test_nearest_volume_bit_exact(ctx, oracle, golden_scenes, golden_rmap):
     assert np.array_equal(ctx.find_closest(pos, nrm), oracle.find_closest(pos, nrm, 1))
 
 
-def test_nearest_volume_vs_reference_kernels(ctx, ref_cuda, golden_scenes, golden_rmap):
-    s = golden_scenes["cornell"]
-    load_scene(ctx, s); ctx.radiance_map_build()
-    ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"]); ref_cuda.rmap_build()
+@pytest.mark.parametrize("name", ["cornell", "door_room_lit", "archway", "medieval_norm"])
+def test_nearest_volume_vs_reference_kernels(ctx, ref_cuda, all_scenes, name):
+    """RadianceMap::find_closest_radiance_volume_iterative as the reference's own kernel runs it (radiance_map.cu:150-203), on the
+    radiance maps of all four BASELINE.json scenes: 2^18 queries near the volumes and 2^18 queries ON the surfaces"""
+    s = all_scenes[name]
+    load_scene(ctx, s); nv = ctx.radiance_map_build()
+    ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"]); assert ref_cuda.rmap_build() == nv
     rs = np.random.RandomState(11)
     d = ctx.radiance_map_download()
+    rpos, rnrm, rsurf = ref_cuda.rmap_volumes()
+    assert np.array_equal(bits(d["pos"]), bits(rpos)) and np.array_equal(d["surface"], rsurf)        # the same map on both sides
     idx = rs.randint(0, ctx.n_vol, 1 << 18)
     pos = d["pos"][idx] + rs.randn(len(idx), 3).astype(np.float32) * np.float32(0.03)
     nrm = d["nrm"][idx]
@@ -187,8 +237,9 @@ def test_cdf_within_1e5(ctx, oracle, golden_scenes, golden_rmap):
         assert np.all(np.diff(cdf, axis=1) >= 0) and np.all(np.abs(cdf[:, -1] - 1) < 1e-5)
 
 
-def test_cdf_vs_reference_kernels(ctx, ref_cuda, golden_scenes):
-    s = golden_scenes["cornell"]
+@pytest.mark.parametrize("name", ["cornell", "door_room_lit", "archway", "medieval_norm"])
+def test_cdf_vs_reference_kernels(ctx, ref_cuda, all_scenes, name):
+    s = all_scenes[name]
     load_scene(ctx, s); nv = ctx.radiance_map_build()
     ref_cuda.scene_arrays(s["sv"], s["srgb"], s["lv"], s["lrgb"]); assert ref_cuda.rmap_build() == nv
     q = np.exp(np.random.RandomState(1984).randn(nv, 144) * 2).astype(np.float32)
