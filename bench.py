@@ -52,7 +52,12 @@ WORKLOADS = {
     "medieval_inside_default": ("medieval_norm", 0, (0.2, 0.3, -0.5), 1.0),
     "medieval_inside_sarsa": ("medieval_norm", 1, (0.2, 0.3, -0.5), 1.0),
     "complex_light_room_default": ("complex_light_room", 0, (0.0, 0.0, -0.9), 0.0),
+    # BASELINE.json configs[4]: archway.obj, Neural-Q (method 3): the DQN fc_layer network (K = 918 -> 200 -> 300 -> 200 -> 144) trained online,
+    # batch 4096 (G/main.cu:116-118), one pass over the pixels per frame; a step = one training frame. cornell_neuralq: the K = 342 network
+    "archway_neuralq": ("archway", 3, (-1.0, 0.2, -0.99), 0.0),
+    "cornell_neuralq": ("cornell", 3, (0.0, 0.0, -3.0), 0.0),
 }
+DQN_FLOP_PER_RAY = {342: 434400.0, 918: 664800.0}        # dense-equivalent forward flop per ray, 2 (K 200 + 200 300 + 300 200 + 200 144)
 
 
 def load_scene(name):
@@ -212,6 +217,66 @@ def run_reference_arm(args, rank):
     emit(line)
 
 
+def run_neuralq(args, ctx, s, scene_name, cam, rank, world, local, fp32_peak):
+    """BASELINE.json configs[4]: online Neural-Q training + rendering (NeuralQPathtracer, G/deep_learning/neural_q_pathtracer.cu:226-600).
+    Single GPU here (the gradient all-reduce path is covered by the 2-GPU test)."""
+    import torch
+    batch = args.batch
+    ctx.dqn_init(seed=1984)
+    n_par, k_in = ctx.dqn_param_count()
+    for _ in range(args.warmup):
+        ctx.render_neuralq(1, batch=batch)
+    ctx.sync(); torch.cuda.synchronize(); ctx.stats_reset(); ctx.sync()
+    clocks = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    loss = ctx.render_neuralq(args.steps, batch=batch)
+    ctx.sync(); torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    st = ctx.stats()
+    clk = clocks.stop(t0, t1) if clocks else None
+    dev_s = st["device_seconds"]
+    value = st["paths"] / dev_s / 1e6
+    pinned = torch.empty((args.width * args.height, 3), dtype=torch.float32, pin_memory=True); frame_np = pinned.numpy()
+    ctx.camera_set(cam); ctx.render_neuralq(1, batch=batch); ctx.frame_download(frame_np); ctx.stats()
+    ctx.sync(); ctx.stats_reset()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.camera_set(cam); ctx.render_neuralq(1, batch=batch); ctx.frame_download(frame_np); est = ctx.stats()
+    ctx.sync(); torch.cuda.synchronize()
+    e2e_value = est["paths"] / (time.perf_counter() - e0) / 1e6
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    fl = DQN_FLOP_PER_RAY.get(k_in, 2.0 * (k_in * 200 + 200 * 300 + 300 * 200 + 200 * 144))
+    fwd_s = max(st["dqn_forward_seconds"], 1e-12)
+    achieved = st["dqn_forward_rays"] * fl / fwd_s / 1e12
+    steps_n = max(st["train_steps"], 1.0)
+    line = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 operands, f32 accumulate (network); f32 (tracing)",
+            "data": "bundled .obj geometry (no dataset); network starts from a seeded Glorot draw and is trained online by the frames themselves",
+            "config": {"workload": args.workload, "scene": "%s (%d surfaces + %d area lights)" % (scene_name, len(s["sv"]), len(s["lv"])), "method": "Neural-Q (DQN fc_layer), train + render",
+                       "width": args.width, "height": args.height, "spp_per_frame": args.spp, "frames": args.steps, "batch": batch, "dqn_inputs": k_in, "dqn_parameters": n_par, "max_bounces": 80,
+                       "l2": "the Q matrix of one bounce (144 x W*H floats = %.0f MB) exceeds L2" % (144 * args.width * args.height * 4 / 1e6)},
+            "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "loss_last_frame": loss,
+            "optimiser_steps_per_frame": steps_n / args.steps, "us_per_optimiser_step": st["train_seconds"] / steps_n * 1e6,
+            "train_share_of_frame": st["train_seconds"] / max(dev_s, 1e-12),
+            "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": args.width * args.height * 12 + 23 * 8,
+                    "timed": "wall clock around K x (camera_set, render 1 training frame, frame download to pinned host memory, stats read-back)"},
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": {"kernel": "k_dqn_forward (per-bounce network evaluation of every ray: layer 1 in fp32 as a rank-3 update, layers 2-4 tcgen05.mma bf16 -> fp32 in TMEM)",
+                         "bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if "bf16_tflops_sustained" in peaks else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)",
+                         "flop_per_launch": st["dqn_forward_rays"] * fl / max(st["dqn_forward_launches"], 1), "avg_launch_ms": fwd_s / max(st["dqn_forward_launches"], 1) * 1e3,
+                         "launches": st["dqn_forward_launches"], "share_of_step": fwd_s / max(dev_s, 1e-12),
+                         "note": "algorithmic flop = dense-equivalent forward flop per ray (SURVEY 8d: %.0f for K = %d) x rays evaluated; duration = CUDA event pairs around every per-bounce launch" % (fl, k_in)},
+            "clocks": clk}
+    emit(line)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +290,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exclusive", action="store_true")
+    ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -251,6 +317,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scene_name, method, cam, env = WORKLOADS[args.workload]
     s = load_scene(scene_name)
+    if method == 3 and args.spp == 32:
+        args.spp = 1                                           # Neural-Q: one pass over the pixels per training frame
     ctx = rlpt.Context(local, width=args.width, height=args.height, spp=args.spp, max_bounces=80, env_light=env, traversal=args.traversal,
                        rank=rank, world_size=world)
     ctx.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"])
@@ -266,6 +334,8 @@ def main():
                 exchange = "fused exchange + merge kernel over peer memory (CUDA IPC, P2P loads/stores over NVLink); no collective call per frame"
     fp32_peak = ctx.measure_fp32_peak()
     render = ctx.render_sarsa if method == 1 else ctx.render_default
+    if method == 3:
+        return run_neuralq(args, ctx, s, scene_name, cam, rank, world, local, fp32_peak)
 
     def barrier():
         ctx.sync(); torch.cuda.synchronize()
@@ -423,6 +493,12 @@ def main():
             break
         if excl:
             line["exclusive_kernel_ms_per_step"] = excl
+            if excl["k_isect"] > 0:
+                fe = hit_flops / args.steps / (excl["k_isect"] * 1e-3) / 1e12
+                line["roofline"]["frac_exclusive"] = fe / fp32_peak if fp32_peak else None
+                line["roofline"]["achieved_exclusive"] = fe
+            if "roofline_shade" in line and excl["k_shade"] > 0:
+                line["roofline_shade"]["frac_exclusive"] = shade_bytes / args.steps / (excl["k_shade"] * 1e-3) / 1e9 / hbm_peak
         if world == 1 and not args.no_cpu_baseline:
             eng = cpu_engine_run()
             v, kind, cores, sample, _ = cpu_reference_run(64, 1, want_seconds=args.cpu_seconds, spp=32)

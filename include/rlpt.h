@@ -200,6 +200,11 @@ typedef struct rlpt_stats_t {
     double shade_launches;
     double tail_seconds;          /* the same for the run-to-completion k_bounce launches */
     double tail_launches;
+    double dqn_forward_seconds;   /* Neural-Q tracers: device seconds inside the per-bounce k_dqn_forward launches over all live rays (event pairs), */
+    double dqn_forward_launches;  /*   their number, */
+    double dqn_forward_rays;      /*   and the rays they evaluated (dense-equivalent flop per ray: SURVEY 8d) */
+    double train_steps;           /* optimiser steps taken by rlpt_render_neuralq (one per batch and bounce) */
+    double train_seconds;         /* device seconds inside them (next-state forward, TD targets, forward + backward, Adam) */
 } rlpt_stats_t;
 int rlpt_stats(rlpt_ctx* ctx, rlpt_stats_t* out);
 int rlpt_stats_reset(rlpt_ctx* ctx);
@@ -245,6 +250,10 @@ int rlpt_render_pretrained(rlpt_ctx* ctx, int frames);
  * ceil(width*height / batch) sequential optimiser steps (batch = 4096 in G/main.cu:116-118). With an all-reduce hook and
  * world_size > 1 the gradients of every step are summed across ranks. */
 int rlpt_render_neuralq(rlpt_ctx* ctx, int frames, int batch);
+/* replaces: the compile-time training constants EPSILON_START / EPSILON_DECAY / EPSILON_MIN (G/constants/deep_learning_settings.h:5-7) and the
+ * learning rate handed to DyNet's AdamTrainer (G/deep_learning/neural_q_pathtracer.cu:44-53, DyNet default 0.001). epsilon_start also resets the
+ * running epsilon. learning_rate 0 freezes the network (the tracer still runs every optimiser step): what the same-path parity test uses. */
+int rlpt_neuralq_set_hyper(rlpt_ctx* ctx, float learning_rate, float epsilon_start, float epsilon_decay, float epsilon_min);
 /* the loss summed over the last frame ("loss" of nn_training_stats.txt, neural_q_pathtracer.cu:578-583) */
 int rlpt_neuralq_last_loss(rlpt_ctx* ctx, double* loss);
 

@@ -6,6 +6,7 @@
 #   libref_cuda.so   nvcc -rdc=true sm_100a  (the reference's own kernels; GPU box only)
 # Excluded on purpose: main.cu and deep_learning/* (DyNet, SDL window), sdl/sdl_screen.cpp (SDL2), voronoi (debug view).
 # usage: oracle/build_ref.sh [host|cuda|all] [W H SPP [SUFFIX]]   (resolution and spp are compile-time in the reference)
+#        RLPT_ORACLE_ENV=1.0f oracle/build_ref.sh cuda 512 512 32 _env1   (ENVIRONMENT_LIGHT is compile-time too: the Medieval_House preset)
 set -euo pipefail
 cd "$(dirname "$0")"
 WHAT="${1:-all}"; W="${2:-512}"; H="${3:-512}"; SPP="${4:-32}"; SUFFIX="${5:-}"
@@ -14,6 +15,7 @@ G="$REF/GPU_Rendering_Engine"; S="$G/Source"
 if [ ! -d "$S" ]; then echo "build_ref.sh: reference not present at $REF (nothing to build)"; exit 0; fi
 OUT=_ref; HOBJ="$OUT/hobj$SUFFIX"; COBJ="$OUT/cobj$SUFFIX"; mkdir -p "$HOBJ" "$COBJ"
 DEFS="-DRLPT_ORACLE_W=$W -DRLPT_ORACLE_H=$H -DRLPT_ORACLE_SPP=$SPP"
+if [ -n "${RLPT_ORACLE_ENV:-}" ]; then DEFS="$DEFS -DRLPT_ORACLE_ENV=$RLPT_ORACLE_ENV"; fi
 INC="-Iref_overrides -I$G/glm -I$S -I$S/constants -I$S/rays -I$S/objects -I$S/lights -I$S/scenes -I$S/utils -I$S/radiance_volumes -I$S/path_tracing -I$S/sdl"
 SRCS="rays/ray camera objects/triangle objects/material objects/surface objects/shape objects/object_importer lights/area_light
       scenes/scene scenes/cornell_box_scene utils/hemisphere_helpers utils/stack utils/printing radiance_volumes/radiance_volume

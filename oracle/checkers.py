@@ -330,6 +330,20 @@ def dqn_forward_numpy(params, vertices, pos):
     return h
 
 
+def dqn_forward_numpy_bf16(params, vertices, pos):
+    """The same network function with the roundings of the tensor-core path (rlpt_dqn.cu): layer 1 in float32; the activations entering layers 2-4 and
+    the weights of layers 2-4 rounded to bfloat16; products accumulated wide. Networks whose outputs are small differences of large terms (the committed
+    door-room network: pre-activations up to 3e5 behind outputs of order 1) lose accuracy to those roundings -- this restatement shows how much."""
+    vertices = np.asarray(vertices, np.float32).ravel(); pos = np.asarray(pos, np.float32).reshape(-1, 3)
+    layers = dqn_split(params, len(vertices))
+    h = vertices[None, :] - np.tile(pos, (1, len(vertices) // 3))
+    W, b = layers[0]
+    h = np.maximum(h @ W.T + b[None, :], np.float32(0)).astype(np.float32)
+    for W, b in layers[1:]:
+        h = np.maximum(bf16_round(h).astype(np.float64) @ bf16_round(W).T.astype(np.float64) + b[None, :], 0.0).astype(np.float32)
+    return h
+
+
 def dynet_text_load(path):
     """DyNet TextFileSaver dump -> flat parameter vector + k_in ("#Parameter# /_i {rows,cols} nbytes ZERO_GRAD", values column-major)"""
     blocks = []

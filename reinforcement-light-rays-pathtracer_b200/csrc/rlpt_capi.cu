@@ -59,7 +59,7 @@ struct rlpt_ctx {
     // CUDA graph of one full-batch optimiser step + fixed staging buffers for the batch's slice of the ray arrays
     int nq_graphs = 1; cudaGraphExec_t nq_graph_exec = nullptr; int nq_graph_batch = 0;
     float4 *d_nqg_loc = nullptr, *d_nqg_sloc = nullptr; uint32_t *d_nqg_action = nullptr, *d_nqg_state = nullptr; float *d_nqg_reward = nullptr, *d_nqg_discount = nullptr; int nqg_capacity = 0;
-    float nq_epsilon = 0.05f; double nq_loss_total = 0.0;     // EPSILON_START (G/constants/deep_learning_settings.h:5)
+    float nq_epsilon = 0.05f, nq_eps_decay = 0.01f, nq_eps_min = 0.05f, nq_lr = 1e-3f; double nq_loss_total = 0.0;     // EPSILON_START / DECAY / MIN (G/constants/deep_learning_settings.h:5-7)
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
     struct Lane {
@@ -86,7 +86,7 @@ struct rlpt_ctx {
     // streams they are launched on; resolved into the sums below once the work has finished (rlpt_stats / end of a render call)
     struct KPair { cudaEvent_t a, b; int kind; };
     std::vector<cudaEvent_t> kev_pool; size_t kev_used = 0; std::vector<KPair> kev_pending;
-    double k_seconds[3] = { 0.0, 0.0, 0.0 }, k_launches[3] = { 0.0, 0.0, 0.0 }, k_all[3] = { 0.0, 0.0, 0.0 };     // 0 k_isect, 1 k_shade, 2 run-to-completion k_bounce; timed launches / all launches
+    double k_seconds[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 }, k_launches[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 }, k_all[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 }; double dqn_rays = 0.0;     // 0 k_isect, 1 k_shade, 2 run-to-completion k_bounce, 3 per-bounce k_dqn_forward, 4 optimiser steps of one bounce; timed launches / all launches
 };
 
 static void free_scene(rlpt_ctx* c) {
@@ -1145,6 +1145,7 @@ static int ensure_nqt(rlpt_ctx* c, int batch) {
 }
 static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
     const rlpt_config& g = c->cfg; const int n = g.width * g.height;
+    c->dq_train.lr = c->nq_lr;                                 // (the optimiser state is recreated whenever new parameters are pushed)
     int rc = ensure_nqt(c, batch); if (rc) return rc;
     if (c->accum_pixels != n) {
         cudaFree(c->d_accum); CK(cudaMalloc(&c->d_accum, sizeof(float4) * (size_t)n));
@@ -1169,12 +1170,16 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
         for (int b = 0; b < g.max_bounces; ++b) {
             if (b > 0) {
                 fp.pos = c->nqt.loc; fp.n = n; fp.n_ptr = nullptr; fp.q = c->d_nqt_qcur; fp.q_stride = n; fp.h1t = fp.h2t = fp.h3t = nullptr;
+                cudaEvent_t e0 = kev_room(c) ? kev_mark(c, c->stream) : nullptr;
                 int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
+                cudaEvent_t e1 = e0 ? kev_mark(c, c->stream) : nullptr;
+                kev_pair(c, e0, e1, 3); c->k_all[3] += 1.0; c->dqn_rays += (double)n;
                 launch_nqt_sample(p, dyn, c->nqt, b, c->d_nqt_qcur, n, c->nq_epsilon, c->stream);
             }
             launch_nqt_trace(p, dyn, c->nqt, b, grid, c->smem_bytes, c->stream);
             c->launches += b > 0 ? 3.0 : 1.0;
             if (b > 0) {
+                cudaEvent_t t0 = kev_room(c) ? kev_mark(c, c->stream) : nullptr;
                 for (int start = 0; start < n; start += batch) {
                     const int bn = std::min(batch, n - start);
                     // One optimiser step is ~40 small launches (forward of the next states, TD targets, forward + backward GEMMs,
@@ -1212,7 +1217,10 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
                     }
                     c->launches += 22.0;       // kernels of one optimiser step (staging, 2 forwards, targets, zeroing, 5 GEMMs, deltas, collect, norm, Adam, operand refresh)
+                    c->k_all[4] += 1.0;
                 }
+                cudaEvent_t t1 = t0 ? kev_mark(c, c->stream) : nullptr;
+                kev_pair(c, t0, t1, 4);
             }
             launch_nqt_respawn(p, dyn, c->nqt, b, c->stream);
             int alive = 0;
@@ -1220,7 +1228,7 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
             CK(cudaStreamSynchronize(c->stream));
             if (alive == 0) break;
         }
-        c->nq_epsilon = std::max(c->nq_epsilon - 0.01f, 0.05f);               // EPSILON_DECAY, EPSILON_MIN (deep_learning_settings.h:6-7)
+        c->nq_epsilon = std::max(c->nq_epsilon - c->nq_eps_decay, c->nq_eps_min);               // EPSILON_DECAY, EPSILON_MIN (deep_learning_settings.h:6-7)
     }
     float loss = 0.f; CK(cudaMemcpy(&loss, c->d_nqt_loss, 4, cudaMemcpyDeviceToHost)); CK(cudaMemset(c->d_nqt_loss, 0, 4));
     c->nq_loss_total = loss;
@@ -1234,6 +1242,14 @@ int rlpt_render_neuralq(rlpt_ctx* c, int frames, int batch) {
     int rc = timed_begin(c); if (rc) return rc;
     for (int f = 0; f < frames; ++f) { rc = phase_mark(c); if (rc) return rc; rc = enqueue_nq_training_frame(c, batch); if (rc) return rc; rc = phase_mark(c); if (rc) return rc; }
     return timed_end(c, frames);
+}
+int rlpt_neuralq_set_hyper(rlpt_ctx* c, float lr, float eps_start, float eps_decay, float eps_min) {
+    if (!c) return fail(RLPT_ERR_ARG, "null ctx");
+    if (!(lr >= 0.f) || !(eps_start >= 0.f && eps_start <= 1.f) || !(eps_decay >= 0.f) || !(eps_min >= 0.f && eps_min <= 1.f)) return fail(RLPT_ERR_ARG, "rlpt_neuralq_set_hyper: learning rate >= 0, epsilons in [0, 1]");
+    CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
+    nq_graph_reset(c);                                     // the captured optimiser step carries the learning rate by value
+    c->nq_lr = lr; c->dq_train.lr = lr; c->nq_epsilon = eps_start; c->nq_eps_decay = eps_decay; c->nq_eps_min = eps_min;
+    return RLPT_OK;
 }
 int rlpt_neuralq_last_loss(rlpt_ctx* c, double* loss) { if (!c || !loss) return fail(RLPT_ERR_ARG, "null"); *loss = c->nq_loss_total; return RLPT_OK; }
 
@@ -1306,6 +1322,8 @@ int rlpt_stats(rlpt_ctx* c, rlpt_stats_t* out) {
     auto scaled = [&](int k) { return c->k_launches[k] > 0.0 ? c->k_seconds[k] * (c->k_all[k] / c->k_launches[k]) : 0.0; };
     out->isect_seconds = scaled(0); out->isect_launches = c->k_all[0]; out->shade_seconds = scaled(1); out->shade_launches = c->k_all[1];
     out->tail_seconds = scaled(2); out->tail_launches = c->k_all[2];
+    out->dqn_forward_seconds = scaled(3); out->dqn_forward_launches = c->k_all[3]; out->dqn_forward_rays = c->dqn_rays;
+    out->train_seconds = c->k_seconds[4]; out->train_steps = c->k_all[4];
     return RLPT_OK;
 }
 int rlpt_stats_reset(rlpt_ctx* c) {
@@ -1314,7 +1332,8 @@ int rlpt_stats_reset(rlpt_ctx* c) {
     CK(cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * 8, c->stream));
     c->device_seconds = 0.0; c->frames_rendered = 0.0; c->launches = 0.0; c->trace_seconds = 0.0; c->merge_seconds = 0.0;
     CK(cudaStreamSynchronize(c->stream)); kev_resolve(c);
-    for (int k = 0; k < 3; ++k) { c->k_seconds[k] = 0.0; c->k_launches[k] = 0.0; c->k_all[k] = 0.0; }
+    for (int k = 0; k < 5; ++k) { c->k_seconds[k] = 0.0; c->k_launches[k] = 0.0; c->k_all[k] = 0.0; }
+    c->dqn_rays = 0.0;
     return RLPT_OK;
 }
 

@@ -88,19 +88,20 @@ __device__ __forceinline__ TriRec load_tri(const SceneView<STAGED>& v, int gid) 
 // plane's side) -- four orders of magnitude inside the padding every leaf box carries (1e-4 + 1/128 of the primitive's extent),
 // so a primitive the exact solve accepts is still never culled. A direction component of exactly 0 gives inv = inf and NaN where
 // plane and origin have the same sign; fminf / fmaxf drop NaN operands, i.e. that axis is then ignored: conservative as well.
-struct Ray4 { float ix, iy, iz, nox, noy, noz; int sx, sy, sz; };
+struct Ray4 { float ix, iy, iz, nox, noy, noz; unsigned sx, sy, sz; };        // sx, sy, sz: record offset of the NEAR plane (0 = lo, 1 = hi)
 __device__ __forceinline__ Ray4 ray4_setup(float ox, float oy, float oz, float sdx, float sdy, float sdz) {
     Ray4 r; r.ix = 1.f / sdx; r.iy = 1.f / sdy; r.iz = 1.f / sdz;
     r.nox = -(ox * r.ix); r.noy = -(oy * r.iy); r.noz = -(oz * r.iz);
-    r.sx = sdx < 0.f ? 1 : 0; r.sy = sdy < 0.f ? 1 : 0; r.sz = sdz < 0.f ? 1 : 0;
+    r.sx = sdx < 0.f ? 1u : 0u; r.sy = sdy < 0.f ? 1u : 0u; r.sz = sdz < 0.f ? 1u : 0u;
     return r;
 }
 // the four children of node `cur`: entry distances (clamped at 0) and hit flags; links returned as loaded
 template <bool STAGED>
 __device__ __forceinline__ void bvh4_boxes(const SceneView<STAGED>& v, int cur, const Ray4& r, float best_t, float (&tn)[4], bool (&hit)[4], int (&lk)[4]) {
-    const int b = 7 * cur;
-    const float4 nx = v.node(b + r.sx), fx = v.node(b + (r.sx ^ 1)), ny = v.node(b + 2 + r.sy), fy = v.node(b + 2 + (r.sy ^ 1));
-    const float4 nz = v.node(b + 4 + r.sz), fz = v.node(b + 4 + (r.sz ^ 1)), l = v.node(b + 6);
+    const float4* __restrict__ nb = (STAGED ? v.nodes_s : v.nodes_g) + 7u * (unsigned)cur;          // one 64-bit address; the records are 32-bit offsets from it
+    auto rec = [&](unsigned i) { return STAGED ? nb[i] : __ldg(nb + i); };
+    const float4 nx = rec(r.sx), fx = rec(r.sx ^ 1u), ny = rec(2u + r.sy), fy = rec(2u + (r.sy ^ 1u));
+    const float4 nz = rec(4u + r.sz), fz = rec(4u + (r.sz ^ 1u)), l = rec(6u);
     const float nxx[4] = { nx.x, nx.y, nx.z, nx.w }, fxx[4] = { fx.x, fx.y, fx.z, fx.w }, nyy[4] = { ny.x, ny.y, ny.z, ny.w }, fyy[4] = { fy.x, fy.y, fy.z, fy.w };
     const float nzz[4] = { nz.x, nz.y, nz.z, nz.w }, fzz[4] = { fz.x, fz.y, fz.z, fz.w };
     lk[0] = __float_as_int(l.x); lk[1] = __float_as_int(l.y); lk[2] = __float_as_int(l.z); lk[3] = __float_as_int(l.w);
@@ -111,6 +112,8 @@ __device__ __forceinline__ void bvh4_boxes(const SceneView<STAGED>& v, int cur, 
         tn[k] = a; hit[k] = a <= f;
     }
 }
+// children of a node: the first two slots are always used, unused slots come last (k_collapse4)
+__device__ __forceinline__ unsigned bvh4_children(const int (&lk)[4]) { return 2u + (lk[2] != BVH4_EMPTY ? 1u : 0u) + (lk[3] != BVH4_EMPTY ? 1u : 0u); }
 // Inner children that were hit, ordered by entry distance. Key = entry distance with the slot number in its two lowest mantissa
 // bits (entry distances are >= 0, so the bit patterns order like the values; rounding the distance down by two bits only makes a
 // later cull more conservative); 0xffffffff = no child. Five compare-exchanges on integer min / max.
@@ -132,10 +135,10 @@ __device__ __forceinline__ void bvh4_closest_hit(const SceneView<STAGED>& v, flo
     while (true) {
         float tn[4]; bool hit[4]; int lk[4];
         bvh4_boxes<STAGED>(v, cur, r, best_t, tn, hit, lk);
+        if (COUNT) n_box += bvh4_children(lk);
         unsigned key[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (COUNT) n_box += lk[k] != BVH4_EMPTY ? 1u : 0u;
             key[k] = (hit[k] && lk[k] >= 0) ? ((__float_as_uint(tn[k]) & ~3u) | (unsigned)k) : B4_NONE;
             if (hit[k] && lk[k] < 0) {
                 const int first = (~lk[k]) >> 3, cnt = (~lk[k]) & 7;
@@ -713,39 +716,48 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 // -- never seen on the bundled scenes -- spill to a local array): entries whose entry distance has meanwhile fallen behind best_t are
 // dropped at pop time without a visit.
 #ifndef RLPT_BVH_BATCH
-#define RLPT_BVH_BATCH 4
+#define RLPT_BVH_BATCH 8
 #endif
 #ifndef RLPT_BVH_REFILL
-#define RLPT_BVH_REFILL 6
+#define RLPT_BVH_REFILL 8
+#endif
+#ifndef RLPT_BVH_UNIFIED_POP
+#define RLPT_BVH_UNIFIED_POP 0
 #endif
 constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
-constexpr int B4_STACK = 16;                                             // shared-memory stack entries per lane
-constexpr int B4_SPILL = 80;                                             // local-memory overflow: 3 x depth 30 fits in 96 entries
-constexpr int WQ_CAP = 32 + 32 * 4 * BVH4_LEAF_MAX;                      // < 32 left over + at most 4 leaves of BVH4_LEAF_MAX records per lane and visit
+constexpr int B4_STACK = 8;                                              // shared-memory stack entries per lane (kept small: the L1 that serves the nodes shares the SM's 256 KB with it)
+constexpr int B4_SPILL = 88;                                             // local-memory overflow: 3 x depth 30 fits in 96 entries
+constexpr int WQ_CAP = 32 + 32 * 4;                                      // < 32 left over + at most 4 leaves per lane and visit
 // per-warp scratch in dynamic shared memory, behind the staged scene
-constexpr int B4_WARP_BYTES = B4_STACK * 32 * 8 + 32 * 8 + WQ_CAP * 4 + 6 * 32 * 4;
+constexpr int B4_WARP_BYTES = B4_STACK * 32 * 8 + 32 * 8 + WQ_CAP * 4 + 6 * 32 * 4 + 16;
 constexpr size_t B4_CTA_BYTES = (size_t)(BLOCK / 32) * B4_WARP_BYTES;
 size_t bvh4_scratch_bytes() { return B4_CTA_BYTES; }
-struct B4Scratch { uint2* stack; unsigned long long* best; unsigned* wq; float* ray; };
+struct B4Scratch { uint2* stack; unsigned long long* best; unsigned* wq; float* ray; int* count; };
 __device__ __forceinline__ B4Scratch b4_scratch(unsigned char* base) {
     unsigned char* p = base + (threadIdx.x >> 5) * B4_WARP_BYTES;
     B4Scratch w; w.stack = reinterpret_cast<uint2*>(p); p += B4_STACK * 32 * 8;
     w.best = reinterpret_cast<unsigned long long*>(p); p += 32 * 8;
     w.wq = reinterpret_cast<unsigned*>(p); p += WQ_CAP * 4;
-    w.ray = reinterpret_cast<float*>(p);
+    w.ray = reinterpret_cast<float*>(p); p += 6 * 32 * 4;
+    w.count = reinterpret_cast<int*>(p);
     return w;
 }
+// list entry = owner lane << 27 | leaf word (first record << 3 | records): the solving lane walks the leaf's 1..BVH4_LEAF_MAX records
 template <bool STAGED>
 __device__ __forceinline__ void wq_solve(const SceneView<STAGED>& v, const B4Scratch& w, int lo, int n, unsigned lane, float& best_t, int& first_pos, unsigned& n_tri) {
     if ((int)lane < n) {
         const unsigned e = w.wq[lo + lane];
-        const int src = (int)(e >> 27), pos = (int)(e & 0x7ffffffu);
-        const float4 q0 = v.tri(3 * pos), q1 = v.tri(3 * pos + 1), q2 = v.tri(3 * pos + 2);
-        const TriRec tr{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y }; const int gid = __float_as_int(q2.z);
-        const float bt = __uint_as_float((unsigned)(w.best[src] >> 32));
-        float t;
-        n_tri++;
-        if (tri_solve(tr, w.ray[src], w.ray[32 + src], w.ray[64 + src], w.ray[96 + src], w.ray[128 + src], w.ray[160 + src], bt, t) && t < T_MISS) atomicMin(w.best + src, hit_key(t, gid));
+        const int src = (int)(e >> 27), first = (int)((e & 0x7ffffffu) >> 3), cnt = (int)(e & 7u);
+        const float ox = w.ray[src], oy = w.ray[32 + src], oz = w.ray[64 + src], a0 = w.ray[96 + src], a1 = w.ray[128 + src], a2 = w.ray[160 + src];
+        float bt = __uint_as_float((unsigned)(w.best[src] >> 32));
+        for (int j = 0; j < cnt; ++j) {
+            const int pos = first + j;
+            const float4 q0 = v.tri(3 * pos), q1 = v.tri(3 * pos + 1), q2 = v.tri(3 * pos + 2);
+            const TriRec tr{ q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y }; const int gid = __float_as_int(q2.z);
+            float t;
+            n_tri++;
+            if (tri_solve(tr, ox, oy, oz, a0, a1, a2, bt, t) && t < T_MISS) { atomicMin(w.best + src, hit_key(t, gid)); bt = fminf(bt, t); }
+        }
     }
     __syncwarp();
     if (first_pos >= lo) first_pos = 0x7fffffff;                        // everything of mine at or above lo has been solved
@@ -761,6 +773,8 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
     bool have = false, drain = false, exhausted = false;
     int i = 0, cur = 0, top = 0, count = 0, first_pos = 0x7fffffff; float best_t = T_MISS;
     Ray4 r{};
+    if (lane == 0) *w.count = 0;
+    __syncwarp();
     auto finish = [&]() {                                               // the ray's result: (t, primitive) from the merged key
         const unsigned long long k = w.best[lane];
         const unsigned lo = (unsigned)k;
@@ -768,14 +782,19 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
         src.emit(i, t, lo == 0xffffffffu ? -1 : (int)(lo >> 1));
     };
     auto push = [&](unsigned node, unsigned key) { if (top < B4_STACK) stack[32 * top] = make_uint2(node, key); else if (top < B4_STACK + B4_SPILL) spill[top - B4_STACK] = make_uint2(node, key); ++top; };
+    auto solve_down_to = [&](int keep) {                                // solve rounds of up to 32 entries from the top of the list until at most `keep` are left
+        while (count > keep) {
+            const int n = count < 32 ? count : 32;
+            count -= n;
+            wq_solve<STAGED>(v, w, count, n, lane, best_t, first_pos, n_tri);
+        }
+        if (lane == 0) *w.count = count;
+        __syncwarp();
+    };
     while (true) {
         const unsigned idle = __ballot_sync(full, !have);               // idle or draining
         if (idle == full || __popc(idle) >= BVH_REFILL) {
-            while (count > 0) {                                         // empty the list: draining lanes become idle
-                const int n = count < 32 ? count : 32;
-                count -= n;
-                wq_solve<STAGED>(v, w, count, n, lane, best_t, first_pos, n_tri);
-            }
+            if (count > 0) solve_down_to(0);                            // empty the list: draining lanes become idle
             if (drain) { finish(); drain = false; }
             if (!exhausted) {
                 const int leader = __ffs(idle) - 1; int base = 0;
@@ -800,18 +819,42 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
         if (!__any_sync(full, have)) break;                             // nothing traversing: the list is empty here too
 #pragma unroll 1
         for (int step = 0; step < BVH_BATCH; ++step) {
-            int lf[4] = { 0, 0, 0, 0 }; int c = 0;                      // leaf links hit by this visit (0 = none), records in them
+            bool leafs = false;
             if (have) {
                 float tn[4]; bool hit[4]; int lk[4];
                 bvh4_boxes<STAGED>(v, cur, r, best_t, tn, hit, lk);
-                unsigned key[4];
+                n_box += bvh4_children(lk);
+                unsigned key[4]; bool lh[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    n_box += lk[k] != BVH4_EMPTY ? 1u : 0u;
                     key[k] = (hit[k] && lk[k] >= 0) ? ((__float_as_uint(tn[k]) & ~3u) | (unsigned)k) : B4_NONE;
-                    if (hit[k] && lk[k] < 0) { lf[k] = ~lk[k]; c += lf[k] & 7; }
+                    lh[k] = hit[k] && lk[k] < -1;                       // a leaf with records (BVH4_EMPTY = -1 has none)
+                }
+                leafs = lh[0] || lh[1] || lh[2] || lh[3];
+                if (leafs) {                                            // this lane's leaf hits -> the warp's list (slots claimed with one shared-memory atomic)
+                    int pos = atomicAdd(w.count, (int)lh[0] + (int)lh[1] + (int)lh[2] + (int)lh[3]);
+                    first_pos = min(first_pos, pos);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (lh[k]) w.wq[pos++] = (lane << 27) | (unsigned)(~lk[k]);
                 }
                 bvh4_sort(key);
+#if RLPT_BVH_UNIFIED_POP
+                // every inner hit goes on the stack (farthest first) and the next node is popped from it: one code path for "descend" and
+                // "backtrack" instead of two that the warp's lanes would walk one after the other
+                if (key[3] != B4_NONE) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
+                if (key[2] != B4_NONE) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
+                if (key[1] != B4_NONE) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
+                if (key[0] != B4_NONE) push((unsigned)lk[0] + (key[0] & 3u), key[0]);
+                {
+                    bool found = false;
+                    while (top > 0) {
+                        --top;
+                        const uint2 e = top < B4_STACK ? stack[32 * top] : spill[min(top - B4_STACK, B4_SPILL - 1)];
+                        if (__uint_as_float(e.y & ~3u) <= best_t) { cur = (int)e.x; found = true; break; }
+                    }
+                    if (!found) { have = false; drain = true; }
+                }
+#else
                 if (key[0] != B4_NONE) {
                     if (key[3] != B4_NONE) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
                     if (key[2] != B4_NONE) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
@@ -826,28 +869,12 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
                     }
                     if (!found) { have = false; drain = true; }
                 }
+#endif
             }
-            if (__any_sync(full, c > 0)) {
-                int pos = c;                                            // inclusive warp scan of the record counts
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(full, pos, d); if ((int)lane >= d) pos += y; }
-                const int total = __shfl_sync(full, pos, 31);
-                pos = count + pos - c;
-                if (c > 0) {
-                    first_pos = min(first_pos, pos);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int first = lf[k] >> 3, cnt = lf[k] & 7;
-#pragma unroll
-                        for (int j = 0; j < BVH4_LEAF_MAX; ++j) if (j < cnt) w.wq[pos++] = (lane << 27) | (unsigned)(first + j);
-                    }
-                }
-                count += total;
-                __syncwarp();
-                while (count >= 32) {
-                    count -= 32;
-                    wq_solve<STAGED>(v, w, count, 32, lane, best_t, first_pos, n_tri);
-                }
+            if (__any_sync(full, leafs)) {
+                __syncwarp();                                           // the list writes above are visible to the solving lanes
+                count = *w.count;
+                if (count >= 32) solve_down_to(31);
             }
             if (drain && first_pos == 0x7fffffff) { finish(); drain = false; }
         }
@@ -867,8 +894,11 @@ struct QueueRays {
     }
     __device__ __forceinline__ void emit(int i, float t, int gid) const { __stcs(p.hit + base + i, make_float2(t, __int_as_float(gid))); }
 };
+#ifndef RLPT_BVH_MINBLOCKS
+#define RLPT_BVH_MINBLOCKS 4
+#endif
 template <bool STAGED, bool PRIMARY>
-__global__ void __launch_bounds__(BLOCK, 3) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
+__global__ void __launch_bounds__(BLOCK, RLPT_BVH_MINBLOCKS) k_isect_bvh(const __grid_constant__ FrameParams p, const __grid_constant__ FrameDyn dyn, int bounce) {
     const SubQueue sq = sub_queue<PRIMARY>(p, bounce);
     if ((int)(blockIdx.x / NSUB) * BLOCK >= sq.n) return;
     SceneView<STAGED> v = stage_scene<STAGED, false>(p.scene);

@@ -51,7 +51,7 @@ def test_config_defaults_are_the_reference_settings():
     assert (c.width, c.height, c.spp, c.max_bounces, c.seed) == (512, 512, 32, 80, 1984)
     assert abs(c.area_per_sample - 0.001) < 1e-9 and abs(c.max_dist - 0.003) < 1e-9
     assert abs(c.initial_radiance - 100.0 / 144.0) < 1e-6 and abs(c.radiance_threshold - 0.8 / 144.0) < 1e-8
-    assert ctypes.sizeof(rlpt.Config) == 13 * 4 and ctypes.sizeof(rlpt.Stats) == 18 * 8
+    assert ctypes.sizeof(rlpt.Config) == 13 * 4 and ctypes.sizeof(rlpt.Stats) == 23 * 8
 
 
 def test_no_cpu_fallback():

@@ -47,6 +47,58 @@ def test_forward_matches_numpy_on_reference_weights(ctx, golden_scenes, dqn_gold
     assert np.median(e2) <= 3e-3 and np.quantile(e2, 0.999) <= 5e-2 and e2.max() <= 0.2, (float(np.median(e2)), float(np.quantile(e2, 0.999)), float(e2.max()))
 
 
+@pytest.mark.parametrize("fixture,scene", [("dqn_cornell_no_decay.npz", "cornell"), ("dqn_door_room.npz", "door_room_lit")])
+def test_forward_on_the_other_committed_networks(ctx, all_scenes, fixture, scene):
+    """Radiance_Map_Data/cornell_no_decay.model and door_room_12_12.model (SURVEY 8f row f1 asks for all three committed networks).
+    These two networks cancel heavily (door room: pre-activations up to 3e5 behind outputs of order 1..1e4), so bf16 operands cost more
+    than on the Cornell network: against the float32 restatement the bar is on quantiles (median 0.2 %, 99 % of the entries 3 % of the
+    row's largest Q, greedy action kept on >= 90 % of the points); the largest single deviation (26 % / 57 % of a row maximum) is what
+    bf16 rounding of weights and activations gives by itself -- the numpy restatement WITH those roundings
+    (checkers.dqn_forward_numpy_bf16) shows the same figure, and the kernel must match that restatement tightly."""
+    from checkers import dqn_forward_numpy_bf16
+    g = dict(np.load(os.path.join(GOLDEN, fixture)))
+    s = all_scenes[scene]
+    load_scene(ctx, s)
+    n, k = ctx.dqn_param_count()
+    assert (n, k) == (218044, 342) and n == len(g["params"])
+    ctx.dqn_set_params(g["params"])
+    q = ctx.dqn_forward(g["pos"]); ref = g["q"]
+    scale = np.maximum(ref.max(1, keepdims=True), 1.0)
+    err = np.abs(q - ref) / scale
+    assert np.median(err) <= 2e-3 and np.quantile(err, 0.99) <= 3e-2, (float(np.median(err)), float(np.quantile(err, 0.99)), float(err.max()))
+    assert np.mean(np.argmax(q, 1) == np.argmax(ref, 1)) >= 0.9
+    emu = dqn_forward_numpy_bf16(g["params"], np.concatenate([s["sv"].ravel(), s["lv"].ravel()]), g["pos"])
+    e2 = np.abs(q - emu) / scale
+    assert np.quantile(e2, 0.999) <= 2e-3 and e2.max() <= 2e-2, (float(np.quantile(e2, 0.999)), float(e2.max()))
+
+
+def test_forward_k918_matches_numpy(ctx, oracle, golden_scenes, golden_hits):
+    """BASELINE.json configs[4]'s shape: archway, K = 918 inputs, 333 244 parameters. No trained archway network is committed (the
+    reference's deep_q_learning_12_12.model is a missing blob), so the weights are a seeded Glorot draw scaled like a trained network;
+    the float32 numpy restatement of the network function is evaluated here on archway hit points."""
+    from checkers import dqn_forward_numpy, dqn_shapes
+    s = golden_scenes["archway"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    n, k = ctx.dqn_param_count()
+    assert (n, k) == (333244, 918)
+    rs = np.random.RandomState(918)
+    parts = []
+    for r, c in dqn_shapes(918):
+        lim = np.sqrt(6.0 / (r + c))
+        parts += [rs.uniform(-lim, lim, r * c).astype(np.float32), rs.uniform(0.0, 0.1, r).astype(np.float32)]
+    params = np.concatenate(parts)
+    ctx.dqn_set_params(params)
+    ty, _, _, pos = oracle.closest_hit(golden_hits["archway"]["org"], golden_hits["archway"]["dir"], 512, 1)
+    pos = pos[ty == 2][:2000].astype(np.float32)
+    vertices = np.concatenate([s["sv"].ravel(), s["lv"].ravel()])
+    ref = dqn_forward_numpy(params, vertices, pos)
+    q = ctx.dqn_forward(pos)
+    assert ref.max() > 0 and np.isfinite(q).all()
+    err = np.abs(q - ref) / np.maximum(ref.max(1, keepdims=True), 1e-3)
+    assert err.max() <= 3e-2 and np.median(err) <= 3e-3, (float(err.max()), float(np.median(err)))
+    assert np.array_equal(ctx.dqn_forward(pos[:129]), q[:129])
+
+
 def test_dynet_text_round_trip(ctx, golden_scenes, dqn_golden, tmp_path):
     from checkers import dynet_text_load, dynet_text_save
     load_scene(ctx, golden_scenes["cornell"])
