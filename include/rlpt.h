@@ -163,6 +163,11 @@ int rlpt_sarsa_trace(rlpt_ctx* ctx);
 int rlpt_sarsa_merge(rlpt_ctx* ctx);
 /* render with the learned distributions frozen (no TD accumulation, no merge): train once, render many */
 int rlpt_render_sarsa_frozen(rlpt_ctx* ctx, int frames);
+/* replaces: the greedy debug samplers the reference swaps in by hand -- RadianceVolume::sample_max_direction_from_radiance_distribution
+ * (G/radiance_volumes/radiance_volume.cu:248-278) for the radiance-volume tracer, sample_max_direction (G/deep_learning/nn_rendering_helpers.cu:492-553)
+ * for the pretrained Neural-Q tracer: the next direction is a random point of the cell with the largest Q. on != 0 switches rlpt_render_sarsa,
+ * rlpt_render_sarsa_frozen and rlpt_render_pretrained to it until switched off. */
+int rlpt_set_max_direction(rlpt_ctx* ctx, int on);
 /* replaces: the VORONOI debug view (G/main.cu:413-470, G/path_tracing/voronoi_trace.cu:4-45): one camera sample per pixel,
  * surface hits painted with the colour of their nearest radiance volume, everything else white. Sets the frame buffer. */
 int rlpt_render_voronoi(rlpt_ctx* ctx);

@@ -41,6 +41,9 @@ class Oracle:
     def threads(self):
         return self.L.orc_threads()
 
+    def set_max_direction(self, on):
+        self.L.orc_set_max_direction(int(bool(on)))
+
     def philox(self, seed, pixel, sample, bounce, purpose):
         u = np.zeros(4, np.float32)
         self.L.orc_philox(ctypes.c_uint32(seed), ctypes.c_uint32(pixel), ctypes.c_uint32(sample), ctypes.c_uint32(bounce), ctypes.c_uint32(purpose), _p(u))

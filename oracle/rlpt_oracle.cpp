@@ -431,6 +431,7 @@ static void merge_frame() {
     }
 }
 
+static int g_max_direction = 0;      /* orc_set_max_direction: greedy debug sampling (the thesis' 1-spp figures) */
 /* path_trace_reinforcement_iterative (G/path_tracing/reinforcement_path_tracing.cu:48-120) +
  * RadianceMap::temporal_difference_update_radiance_volume_sector (radiance_map.cu:111-146) */
 static V3 trace_sarsa(const Cfg& c, uint32_t pixel, int px, int py, uint32_t sample, int& len, bool& failed) {
@@ -459,8 +460,19 @@ static V3 trace_sarsa(const Cfg& c, uint32_t pixel, int px, int py, uint32_t sam
         draw4(c.seed, pixel, sample, (uint32_t)i, PURPOSE_BOUNCE, u);
         const float* cdf = &g_rm.cdf[(size_t)cur_vol * A];
         float pdf = 0.f;
-        int sector = sample_sector(cdf, u[0], pdf);
-        if (sector < 0 && c.clamp_last_bin) sector = sample_sector_fallback(cdf, u[0], pdf);
+        int sector;
+        if (g_max_direction) {
+            /* RadianceVolume::sample_max_direction_from_radiance_distribution (radiance_volume.cu:248-278): the first cell holding the largest Q;
+             * pdf from the width of its CDF bin. (The reference takes cdf[0] - cdf[0] = 0 for cell 0; the proper width cdf[0] is used here, the same
+             * repair as the clamped last bin.) */
+            const float* q = &g_rm.q[(size_t)cur_vol * A];
+            sector = 0; float mx = q[0];
+            for (int k = 0; k < A; ++k) if (mx < q[k]) { mx = q[k]; sector = k; }
+            pdf = RHO * ((cdf[sector] - (sector ? cdf[sector - 1] : 0.f)) / GRID_RHO);
+        } else {
+            sector = sample_sector(cdf, u[0], pdf);
+            if (sector < 0 && c.clamp_last_bin) sector = sample_sector_fallback(cdf, u[0], pdf);
+        }
         V3 nd;
         if (sector < 0) { failed = true; nd = { 0.f, 0.f, 0.f }; }
         else {
@@ -483,6 +495,7 @@ static V3 trace_sarsa(const Cfg& c, uint32_t pixel, int px, int py, uint32_t sam
 
 extern "C" {
 
+void orc_set_max_direction(int on) { g_max_direction = on; }
 int orc_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

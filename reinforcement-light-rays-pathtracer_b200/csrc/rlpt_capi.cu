@@ -41,7 +41,7 @@ struct rlpt_ctx {
     std::vector<int> h_surf_class;
     SceneDev scene{};
     // camera / per-frame
-    float cam[3] = { 0.f, 0.f, -3.f }; float yaw_y = 0.f, yaw_x = 0.f;
+    float cam[3] = { 0.f, 0.f, -3.f }; float yaw_y = 0.f, yaw_x = 0.f; int max_dir = 0;
     // radiance map
     bool have_rmap = false;
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
@@ -393,6 +393,10 @@ int rlpt_camera_set(rlpt_ctx* c, const float position[4], float yaw_y, float yaw
     c->cam[0] = position[0]; c->cam[1] = position[1]; c->cam[2] = position[2]; c->yaw_y = yaw_y; c->yaw_x = yaw_x;
     return RLPT_OK;
 }
+
+// replaces: the greedy samplers RadianceVolume::sample_max_direction_from_radiance_distribution (G/radiance_volumes/radiance_volume.cu:248-278) and
+// sample_max_direction (G/deep_learning/nn_rendering_helpers.cu:492-553), which the reference swaps in by hand for its 1-spp "what has been learned" figures
+int rlpt_set_max_direction(rlpt_ctx* c, int on) { if (!c) return fail(RLPT_ERR_ARG, "null ctx"); c->max_dir = on ? 1 : 0; return RLPT_OK; }
 
 int rlpt_closest_hit_device(rlpt_ctx* c, const float* d_org, const float* d_dir, int n, int traversal, int* d_type, int* d_index, float* d_t, unsigned long long* d_counters) {
     if (!c || !c->have_scene) return fail(RLPT_ERR_ARG, "rlpt_closest_hit: upload a scene first");
@@ -892,7 +896,7 @@ static int enqueue_trace(rlpt_ctx* c, int method, int learn) {
     dyn.learn = learn; dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
     dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
     dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
-    dyn.capture_bounce = c->cap_bounce; dyn.capture_max = c->cap_bounce >= 0 ? c->cap_max : 0;
+    dyn.capture_bounce = c->cap_bounce; dyn.capture_max = c->cap_bounce >= 0 ? c->cap_max : 0; dyn.max_dir = c->max_dir;
     FrameParams p{};
     p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats;
     p.capture_o = c->d_cap_o; p.capture_d = c->d_cap_d; p.capture_n = c->d_cap_n;
@@ -1091,6 +1095,7 @@ static int enqueue_nq_inference(rlpt_ctx* c) {
     dyn.cam_x = c->cam[0]; dyn.cam_y = c->cam[1]; dyn.cam_z = c->cam[2];
     dyn.cy = cosf(c->yaw_y); dyn.sy = sinf(c->yaw_y); dyn.cx = cosf(c->yaw_x); dyn.sx = sinf(c->yaw_x);
     dyn.rotated = (c->yaw_y != 0.f || c->yaw_x != 0.f) ? 1 : 0;
+    dyn.max_dir = c->max_dir;
     rlpt_ctx::Lane& l = c->lanes[0];
     FrameParams p{};
     p.scene = c->scene; p.rm = c->rm; p.accum = c->d_accum; p.stats = c->d_stats; p.q[0] = l.q[0]; p.q[1] = l.q[1]; p.counts = l.d_counts;
@@ -1190,15 +1195,14 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         launch_nqt_stage(c->nqt, start, bn, c->d_nqg_loc, c->d_nqg_sloc, c->d_nqg_action, c->d_nqg_state, c->d_nqg_reward, c->d_nqg_discount, c->stream);
                         if (!c->nq_graph_exec || c->nq_graph_batch != batch) {
                             if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; }
-                            int arc = dqn_train_alloc(c->dq_train, c->dq, batch); if (arc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
+                            int arc = dqn_train_prepare(c->dq, c->dq_train, batch, c->stream); if (arc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
                             NqTrainState gs = c->nqt; gs.state = c->d_nqg_state; gs.reward = c->d_nqg_reward; gs.discount = c->d_nqg_discount;
                             cudaGraph_t graph = nullptr;
                             CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                             DqnFwdParams gp = fp; gp.pos = c->d_nqg_loc; gp.n = bn; gp.q = c->d_nqt_qnext; gp.q_stride = S;
                             int frc = dqn_forward(c->dq, gp, c->stream);
                             launch_nqt_targets(gs, 0, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream);
-                            launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
+                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss);
                             cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
                             if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(RLPT_ERR_CUDA, "Neural-Q training step: graph capture failed"); }
                             ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
@@ -1212,9 +1216,8 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         fp.pos = c->nqt.loc + start; fp.n = bn; fp.q = c->d_nqt_qnext; fp.q_stride = S;
                         int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
                         launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream);
+                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss);
                         if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
-                        launch_add_scalar(c->d_nqt_loss, c->dq_train.scalars, c->stream);
                     }
                     c->launches += 22.0;       // kernels of one optimiser step (staging, 2 forwards, targets, zeroing, 5 GEMMs, deltas, collect, norm, Adam, operand refresh)
                     c->k_all[4] += 1.0;

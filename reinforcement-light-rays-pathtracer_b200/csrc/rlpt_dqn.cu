@@ -458,27 +458,40 @@ __global__ void k_train_prepare(const float4* __restrict__ pos, int n, int S, __
     }
 }
 // output-layer delta (one action per ray): g = d/dq (target - q_a)^2 * relu'(q_a); delta3 = g W4[a, :] relu'(h3);
-// dW4[a, :] += g h3, db4[a] += g; loss accumulated. One thread per ray.
-__global__ void k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, const float* __restrict__ targets, int n, int S,
-                         const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t,
-                         float* __restrict__ gw4, float* __restrict__ gb4, float* __restrict__ scalars) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    float g = 0.f; int a = 0; float loss = 0.f;
-    if (i < n) {
-        a = (int)actions[i]; const float qa = q[(size_t)a * S + i], diff = qa - targets[i];
-        loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f;
+// dW4[a, :] += g h3, db4[a] += g; loss accumulated. One CTA per 32 rays x all 208 hidden units: the feature-major arrays (h3t, d3t) are
+// walked with the ray index fastest, the ray-major d3 is written from a shared-memory tile with the unit index fastest -- every access
+// coalesced. (One thread per ray walking 208 units, the first form of this kernel, took 125 us of a 270 us optimiser step.)
+constexpr int D3_RAYS = 32;
+__global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, const float* __restrict__ targets, int n, int S,
+                                                const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t,
+                                                float* __restrict__ gw4, float* __restrict__ gb4, float* __restrict__ scalars) {
+    __shared__ __nv_bfloat16 tile[D3_RAYS][DQ_K4 + 2];                   // + 2: rows 105 words apart, conflict-free column writes
+    __shared__ float s_g[D3_RAYS]; __shared__ int s_a[D3_RAYS];
+    const int i0 = blockIdx.x * D3_RAYS, tid = threadIdx.x;
+    if (tid < D3_RAYS) {
+        const int i = i0 + tid; float g = 0.f, loss = 0.f; int a = 0;
+        if (i < n) {
+            a = (int)actions[i]; const float qa = q[(size_t)a * S + i], diff = qa - targets[i];
+            loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f;
+            if (g != 0.f) atomicAdd(gb4 + a, g);
+        }
+        s_g[tid] = g; s_a[tid] = a;
+        for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+        if (tid == 0 && loss != 0.f) atomicAdd(scalars, loss);
     }
-    for (int j = 0; j < DQ_K4; ++j) {
-        float h = (i < n && j < DQ_H3) ? __bfloat162float(h3t[(size_t)j * S + i]) : 0.f;
-        float d = (g != 0.f && h > 0.f) ? g * __ldg(w4 + (size_t)a * DQ_H3 + j) : 0.f;
-        __nv_bfloat16 db = __float2bfloat16_rn(d);
-        d3[(size_t)i * DQ_K4 + j] = db; d3t[(size_t)j * S + i] = db;
-        if (g != 0.f && h > 0.f) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
+    __syncthreads();
+    const int ii = tid & 31, jj = tid >> 5, i = i0 + ii;
+    const float g = s_g[ii]; const int a = s_a[ii];
+    for (int j = jj; j < DQ_K4; j += 8) {
+        const float h = (i < n && j < DQ_H3) ? __bfloat162float(h3t[(size_t)j * S + i]) : 0.f;
+        const bool on = g != 0.f && h > 0.f;
+        const __nv_bfloat16 db = __float2bfloat16_rn(on ? g * __ldg(w4 + (size_t)a * DQ_H3 + j) : 0.f);
+        if (i < S) d3t[(size_t)j * S + i] = db;
+        tile[ii][j] = db;
+        if (on) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
     }
-    if (g != 0.f) atomicAdd(gb4 + a, g);
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(scalars, loss);
+    __syncthreads();
+    for (int r = 0; r < D3_RAYS; ++r) if (tid < DQ_K4 && i0 + r < S) d3[(size_t)(i0 + r) * DQ_K4 + tid] = tile[r][tid];
 }
 // Supervised variant (NN_Q_Value_Trainer/Source/main.cu:110-117: loss = sum_batches squared_distance(targets, Q(s)) over ALL
 // 144 outputs): the output-layer gradient is dense. g[i][a] = 2 (q_a - y_a) relu'(q_a); one thread per (ray, action).
@@ -542,7 +555,8 @@ __global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __r
 // lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
 // The step counter lives on the device (scalars[3], advanced once per step by k_adam_tick, which also derives the bias-corrected
 // step size into scalars[2]), so that a captured optimiser step can be replayed as a CUDA graph without any host value in it.
-__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2) {
+__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2, float* __restrict__ loss_total) {
+    if (loss_total) *loss_total += scalars[0];                          // running loss of the frame (was a kernel of its own)
     const float t = scalars[3] + 1.f; scalars[3] = t;
     scalars[2] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
 }
@@ -613,9 +627,12 @@ __global__ void k_pack_all(const float* __restrict__ w2, const float* __restrict
 }
 
 void dqn_train_free(DqnTrain& t) {
-    for (int l = 0; l < 4; ++l) { cudaFree(t.gw[l]); cudaFree(t.gb[l]); cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
+    cudaFree(t.gall);
+    for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
     cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
+    if (t.side) cudaStreamDestroy(t.side);
+    for (cudaEvent_t e : t.ev) if (e) cudaEventDestroy(e);
     t = DqnTrain{};
 }
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
@@ -623,9 +640,15 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
     DqnHost shape; shape.k_in = d.k_in;
     const bool fresh = t.gw[0] == nullptr;
     if (fresh) {
+        // the eight gradient arrays live in ONE block (W1 b1 .. W4 b4, each 16-byte aligned): a multi-GPU step sums them with a single all-reduce
+        size_t gtotal = 0;
+        for (int l = 0; l < 4; ++l) gtotal += ((size_t)DqnHost::rows(l) * shape.cols(l) + 3) / 4 * 4 + ((size_t)DqnHost::rows(l) + 3) / 4 * 4;
+        DQ_CK(cudaMalloc(&t.gall, 4 * gtotal)); DQ_CK(cudaMemset(t.gall, 0, 4 * gtotal)); t.gall_count = gtotal;
+        float* gp = t.gall;
         for (int l = 0; l < 4; ++l) {
             const size_t nw = (size_t)DqnHost::rows(l) * shape.cols(l), nb = DqnHost::rows(l);
-            DQ_CK(cudaMalloc(&t.gw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.gb[l], 4 * nb)); DQ_CK(cudaMalloc(&t.mw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.mb[l], 4 * nb));
+            t.gw[l] = gp; gp += (nw + 3) / 4 * 4; t.gb[l] = gp; gp += (nb + 3) / 4 * 4;
+            DQ_CK(cudaMalloc(&t.mw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.mb[l], 4 * nb));
             DQ_CK(cudaMalloc(&t.vw[l], 4 * nw)); DQ_CK(cudaMalloc(&t.vb[l], 4 * nb));
             DQ_CK(cudaMemset(t.mw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.mb[l], 0, 4 * nb)); DQ_CK(cudaMemset(t.vw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.vb[l], 0, 4 * nb));
         }
@@ -649,14 +672,22 @@ static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
-int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs) {
-    if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
+int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {           // everything a captured step must not contain: allocations, the first transposes, the side stream
     int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
+    if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }
+    if (!t.side) {
+        DQ_CK(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : t.ev) DQ_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    return 0;
+}
+int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs, float* loss_total) {
+    if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
+    int rc = dqn_train_prepare(d, t, n, s); if (rc) return rc;               // (afterwards k_pack_all keeps the transposes current)
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     DqnHost shape; shape.k_in = d.k_in;
     const ParamSegs segs = param_segs(d, t);
-    if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }       // afterwards k_pack_all keeps them current
     {
         const int na = DQ_N3 * DQ_K3, nb = DQ_N2 * DQ_K2, nc = DQ_K2 * 16, total = segs.start[8] + na + nb + nc + 2;
         k_zero_grads<<<(total + 255) / 256, 256, 0, s>>>(segs, t.dw3x, na, t.dw2x, nb, t.dg, nc, t.scalars);
@@ -673,29 +704,31 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         k_delta3_full<<<dim3((S + 127) / 128, DQ_K4), 128, 0, s>>>(t.g4, d.w[3], t.h3t, n, S, t.d3, t.d3t);
         k_dw4_full<<<dim3((DQ_H3 + 1 + 7) / 8, DQ_OUT), 256, 0, s>>>(t.g4, t.h3t, n, S, t.gw[3], t.gb[3]);
     } else
-        k_delta3<<<(S + 127) / 128, 128, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+        k_delta3<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+    // The weight-gradient products need only the deltas of their own layer, not the rest of the data path: they run on a side stream
+    // (forked and joined with events, which also works inside a stream capture: the captured graph gets the parallel branches), so
+    // the chain the step waits for is  d3 -> p2 -> d2 -> p1 -> d1 -> dG  with dW3, dW2 beside it.
+    const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
+    DQ_CK(cudaEventRecord(t.ev[0], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[0], 0));
+    rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, t.side); if (rc) return rc;                 // [208 x S] x [304 x S]^T
     rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, DQ_N2, S, DQ_N2, DQ_K4, 1, s); if (rc) return rc;                  // [S x 208] x [304 x 208]^T
     k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, DQ_N2, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
+    DQ_CK(cudaEventRecord(t.ev[1], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[1], 0));
+    rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, t.side); if (rc) return rc;                 // [304 x S] x [208 x S]^T
     rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, DQ_N3, S, DQ_N3, DQ_K3, 1, s); if (rc) return rc;                  // [S x 304] x [208 x 304]^T
     k_delta_hidden<<<dim3((S + 127) / 128, DQ_K2), 128, 0, s>>>(t.p1, DQ_N3, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
-    // backward: weight gradients, K = the batch, split over CTAs
-    const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
-    rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, s); if (rc) return rc;                      // [208 x S] x [304 x S]^T
-    rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, s); if (rc) return rc;                      // [304 x S] x [208 x S]^T
     rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
+    DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
     const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
     k_collect_grads<<<(n_collect + 255) / 256, 256, 0, s>>>(t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.gw[0], t.gb[0], t.gw[1], t.gb[1], t.gw[2], t.gb[2]);
     if (allreduce) {
-        for (int l = 0; l < 4; ++l) {
-            if (allreduce(t.gw[l], (uint64_t)DqnHost::rows(l) * shape.cols(l), 0, (void*)s, allreduce_user)) return -2;
-            if (allreduce(t.gb[l], (uint64_t)DqnHost::rows(l), 0, (void*)s, allreduce_user)) return -2;
-        }
+        if (allreduce(t.gall, (uint64_t)t.gall_count, 0, (void*)s, allreduce_user)) return -2;            // all eight gradient arrays at once (padding words are zero)
         if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
     }
     if (!apply_update) return (int)cudaGetLastError();
     k_sqnorm_all<<<128, 256, 0, s>>>(segs, t.scalars + 1);
     t.step++;
-    k_adam_tick<<<1, 1, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2);
+    k_adam_tick<<<1, 1, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2, loss_total);
     k_adam_all<<<(segs.start[8] + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
     // operands for the next forward / backward: layer-1 rank-3 form, packed bf16 weights, the two transposes
     k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);

@@ -52,7 +52,8 @@ struct DqnFwdParams {
 //   d3 [S][208], d2 [S][304] ray-major and d3t [208][S], d2t [304][S], d1t [208][S] feature-major deltas (bf16)
 struct DqnTrain {
     int capacity = 0;                               // S the buffers were allocated for
-    float *gw[4] = { nullptr, nullptr, nullptr, nullptr }, *gb[4] = { nullptr, nullptr, nullptr, nullptr };      // gradients
+    float *gw[4] = { nullptr, nullptr, nullptr, nullptr }, *gb[4] = { nullptr, nullptr, nullptr, nullptr };      // gradients: views into gall
+    float* gall = nullptr; size_t gall_count = 0;   // one block holding all eight gradient arrays
     float *mw[4] = { nullptr, nullptr, nullptr, nullptr }, *mb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam first moments
     float *vw[4] = { nullptr, nullptr, nullptr, nullptr }, *vb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam second moments
     float *dw3x = nullptr, *dw2x = nullptr, *dg = nullptr;      // GEMM outputs: [208][304] (col 300 = db3), [304][208] (col 200 = db2), [208][16] (cols 0-2 = G, col 3 = db1)
@@ -66,6 +67,7 @@ struct DqnTrain {
     unsigned long long step = 0;
     bool transposes_fresh = false;                  // W3^T / W2^T match the current parameters (k_pack_all refreshes them after every update)
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
+    cudaStream_t side = nullptr; cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };      // the weight-gradient GEMMs run beside the data path
 };
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
 void dqn_train_free(DqnTrain& t);
@@ -74,7 +76,9 @@ void dqn_train_free(DqnTrain& t);
 // all-reduce hook (may be null): sums the gradient buffers across ranks before the update.
 typedef int (*dqn_allreduce_fn)(void* d_buf, uint64_t count, int dtype, void* cuda_stream, void* user);
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs = false);   // all_outputs: targets is [n][144], the supervised loss over every output (actions unused)
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs = false,    // all_outputs: targets is [n][144], the supervised loss over every output (actions unused)
+                    float* loss_total = nullptr);                                                                  // device scalar the step's loss is added to (may be null)
+int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s);                     // allocations, first transposes, side stream: call before capturing a step
 int dqn_alloc(DqnDev& d, int k_in);
 void dqn_free(DqnDev& d);
 int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s);       // copies parameters, derives operands

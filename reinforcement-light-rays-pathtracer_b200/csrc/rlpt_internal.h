@@ -69,6 +69,7 @@ struct FrameDyn {
     uint32_t sample_base; int learn;
     float cam_x, cam_y, cam_z, cy, sy, cx, sx; int rotated;
     int capture_bounce, capture_max;
+    int max_dir;                    // 1: greedy debug sampling (sample_max_direction_from_radiance_distribution / sample_max_direction)
 };
 
 // One lane = one slice of a frame's samples traced on its own stream with its own queues, so that the latency-bound

@@ -553,16 +553,26 @@ __device__ __forceinline__ bool shade_step(const FrameParams& p, const FrameDyn&
     if (SARSA) {
         // importance_sample_ray_direction -> sample_direction_from_radiance_distribution (radiance_volume.cu:192-244)
         const float* __restrict__ row = p.rm.cdf + (size_t)nv * CELLS;
+        float pdf; int sector;
+        if (dyn.max_dir) {
+            // RadianceVolume::sample_max_direction_from_radiance_distribution (radiance_volume.cu:248-278): the first cell holding the largest Q,
+            // pdf from the width of its CDF bin (cell 0: its proper width cdf[0]; the reference subtracts cdf[0] from itself there)
+            const float* __restrict__ qrow = p.rm.q + (size_t)nv * CELLS;
+            sector = 0; float mx = __ldg(qrow);
+            for (int k = 1; k < CELLS; ++k) { const float qk = __ldg(qrow + k); if (mx < qk) { mx = qk; sector = k; } }
+            pdf = RHO * ((__ldg(row + sector) - (sector ? __ldg(row + sector - 1) : 0.f)) / GRID_RHO);
+        } else {
 #if RLPT_CDF_2LEVEL
         const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(p.rm.cdf_rows + (size_t)nv * GRID);
         const float4* __restrict__ row4 = reinterpret_cast<const float4*>(row);
-        float pdf; int sector = sample_sector_2level(
+        sector = sample_sector_2level(
             [&](float (&e)[12]) { float4 a = __ldg(rows4), b = __ldg(rows4 + 1), c = __ldg(rows4 + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
             [&](int j, float (&e)[12]) { float4 a = __ldg(row4 + 3 * j), b = __ldg(row4 + 3 * j + 1), c = __ldg(row4 + 3 * j + 2); e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w; },
             [&](int k) { return __ldg(row + k); }, u0, pdf);
 #else
-        float pdf; int sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
+        sector = sample_sector([&](int k) { return __ldg(row + k); }, u0, pdf);
 #endif
+        }
         nd = grid_to_direction((float)(sector / GRID) + u1, (float)(sector % GRID) + u2, T, N, B);
         float cos_theta = N.x * nd.x + N.y * nd.y + N.z * nd.z;                       // reinforcement_path_tracing.cu:107
         scale = cos_theta / pdf;
@@ -1139,7 +1149,13 @@ __global__ void __launch_bounds__(BLOCK) k_nq_sample(const __grid_constant__ Fra
         f3 N = { sN.x, sN.y, sN.z }, T = { sT.x, sT.y, sT.z }, B = { sB.x, sB.y, sB.z };
         float u0, u1, u2, u3; draw4(p.seed, pixel, sample, (uint32_t)bounce, PURPOSE_NQ, u0, u1, u2, u3);
         int cell; float pdf;
-        if (u3 <= epsilon) {                                                   // explore: a uniformly chosen cell, pdf = RHO (:366-387, :30-36)
+        if (dyn.max_dir) {
+            // sample_max_direction (nn_rendering_helpers.cu:492-553): the first cell with the largest Q (cell 0 when none is positive), a random point
+            // inside it, and the reference's constant pdf 2 RHO
+            cell = 0; float mq = 0.f;
+            for (int k = 0; k < CELLS; ++k) { const float qk = __ldg(q + (size_t)k * q_stride + i); if (qk > mq) { mq = qk; cell = k; } }
+            pdf = RHO * 2.f;
+        } else if (u3 <= epsilon) {                                            // explore: a uniformly chosen cell, pdf = RHO (:366-387, :30-36)
             cell = min((int)(u0 * (float)CELLS), CELLS - 1); pdf = RHO;
         } else {
             float total = 0.f;

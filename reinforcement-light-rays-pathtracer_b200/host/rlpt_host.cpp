@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <sstream>
 
 namespace rlpt_host {
@@ -430,6 +431,92 @@ PretrainedPathtracer::PretrainedPathtracer(unsigned int frames, int, SDLScreen& 
     for (unsigned int fr = 0; fr < frames; ++fr) { r.reset_frame(); r.check(rlpt_render_pretrained(r.ctx(), 1)); r.present(screen); screen.SDL_Renderframe(); }
     if (image) screen.SDL_SaveImage(image);
     rendered = true;
+}
+
+
+// ---- NN_Q_Value_Trainer/Source/main.cu: the offline supervised trainer over the C ABI
+static bool read_float_lines(const std::string& path, std::vector<std::vector<float>>& rows) {
+    std::ifstream in(path);
+    if (!in.is_open()) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        std::vector<float> v; const char* sp = line.c_str(); char* end = nullptr;
+        for (;;) { float f = strtof(sp, &end); if (end == sp) break; v.push_back(f); sp = end; }
+        rows.push_back(v);
+    }
+    return true;
+}
+bool load_radiance_map_data(const std::string& path, std::vector<std::vector<float>>& data, int& action_count) {
+    std::vector<std::vector<float>> rows;
+    if (!read_float_lines(path, rows) || rows.empty() || rows[0].size() != 1) { printf("Radiance Map Data file could not be opened.\n"); return false; }
+    action_count = (int)rows[0][0];
+    for (size_t i = 1; i < rows.size(); ++i) if (!rows[i].empty()) data.push_back(rows[i]);
+    return true;
+}
+bool load_vertices(const std::string& path, std::vector<float>& vertices) {
+    std::vector<std::vector<float>> rows;
+    if (!read_float_lines(path, rows)) { printf("Scene Data file could not be opened.\n"); return false; }
+    for (const auto& r : rows) vertices.insert(vertices.end(), r.begin(), r.end());
+    return true;
+}
+QValueTrainerResult train_q_value_network(Renderer& renderer, const std::string& data_path, const std::string& vertices_path, int epochs, int batch_size,
+                                          const char* save_model, const char* load_model, unsigned shuffle_seed, bool verbose) {
+    QValueTrainerResult res;
+    std::vector<std::vector<float>> data; int action_count = 0;
+    if (!load_radiance_map_data(data_path, data, action_count)) return res;
+    // std::random_shuffle (main.cu:126) is gone from C++17; a Fisher-Yates shuffle on a seeded LCG takes its place (any permutation serves)
+    { uint64_t st = 0x9E3779B97F4A7C15ull ^ shuffle_seed; for (size_t i = data.size(); i > 1; --i) { st = st * 6364136223846793005ull + 1442695040888963407ull; std::swap(data[i - 1], data[(size_t)((st >> 33) % i)]); } }
+    std::vector<float> vertices;
+    if (!load_vertices(vertices_path, vertices)) return res;
+    res.lines = (int)data.size(); res.vertices = (int)vertices.size() / 3; res.action_count = action_count;
+    if (verbose) { std::cout << "Read " << data.size() << " lines of radiance_map data." << std::endl << "Action count: " << action_count << std::endl << "Read " << vertices.size() / 3 << " vertices." << std::endl; }
+    if (action_count != RLPT_GRID_CELLS || vertices.size() % 9 != 0 || vertices.empty()) throw RenderError{ RLPT_ERR_ARG, "train_q_value_network: expected 144 actions and 9 floats per triangle in vertices.txt" };
+    std::vector<const std::vector<float>*> training, test;
+    for (const auto& line : data) {
+        if (line.size() != (size_t)(3 + action_count)) throw RenderError{ RLPT_ERR_IO, "train_q_value_network: a data line does not hold 3 + action_count values" };
+        const double rv = (double)rand() / (RAND_MAX);                       // main.cu:147
+        (rv < 0.8 ? training : test).push_back(&line);
+    }
+    res.train = (int)training.size(); res.test = (int)test.size();
+    if (verbose) { std::cout << "Training data set size: " << training.size() << std::endl << "Test data set size: " << test.size() << std::endl; }
+    // the network's input is every scene vertex minus the query point: the scene behind vertices.txt is uploaded as plain geometry
+    rlpt_ctx* ctx = renderer.ctx();
+    {
+        const int n_tri = (int)vertices.size() / 9; std::vector<float> rgb(3 * (size_t)n_tri, 0.75f);
+        renderer.check(rlpt_scene_upload(ctx, vertices.data(), rgb.data(), n_tri, nullptr, nullptr, 0));
+        renderer.check(rlpt_dqn_set_vertices(ctx, vertices.data(), (int)vertices.size()));
+    }
+    if (load_model) renderer.check(rlpt_dqn_load_text(ctx, load_model)); else renderer.check(rlpt_dqn_init(ctx, 1984u));
+    const size_t num_batches = (training.size() + (size_t)batch_size - 1) / (size_t)batch_size;
+    std::vector<float> pos, tgt, q;
+    for (int e = 0; e < epochs; ++e) {
+        float loss = 0.f;
+        for (size_t b = 0; b < num_batches; ++b) {
+            const size_t sidx = b * (size_t)batch_size, n = std::min(training.size() - sidx, (size_t)batch_size);
+            pos.resize(3 * n); tgt.resize((size_t)action_count * n);
+            for (size_t k = 0; k < n; ++k) {
+                const std::vector<float>& l = *training[sidx + k];
+                std::copy(l.begin(), l.begin() + 3, pos.begin() + 3 * k); std::copy(l.begin() + 3, l.end(), tgt.begin() + (size_t)action_count * k);
+            }
+            float bl = 0.f;
+            renderer.check(rlpt_dqn_train_supervised(ctx, pos.data(), tgt.data(), (int)n, 1, &bl));
+            loss += bl;
+        }
+        float error = 0.f;
+        if (!test.empty()) {
+            pos.resize(3 * test.size()); q.resize((size_t)action_count * test.size());
+            for (size_t t = 0; t < test.size(); ++t) std::copy(test[t]->begin(), test[t]->begin() + 3, pos.begin() + 3 * t);
+            renderer.check(rlpt_dqn_forward(ctx, pos.data(), (int)test.size(), q.data()));
+            for (size_t t = 0; t < test.size(); ++t) for (int a = 0; a < action_count; ++a) { const float d = (*test[t])[3 + a] - q[t * (size_t)action_count + a]; error += d * d; }
+        }
+        res.loss.push_back(loss); res.error.push_back(error);
+        if (verbose) {
+            std::cout << "---------------- " << e + 1 << " ----------------" << std::endl << "      Loss: " << loss << std::endl << "      Error: " << error << std::endl
+                      << "-------------------------------------" << std::endl << std::endl;
+        }
+    }
+    if (save_model) renderer.check(rlpt_dqn_save_text(ctx, save_model));
+    return res;
 }
 
 }  // namespace rlpt_host

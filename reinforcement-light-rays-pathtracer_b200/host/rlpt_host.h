@@ -135,6 +135,18 @@ public:
                          const char* model = "../Radiance_Map_Data/deep_q_learning_12_12.model", const char* image = "../Images/render.bmp");
     bool rendered = false;
 };
+// NN_Q_Value_Trainer/Source/main.cu:118-295 -- the offline supervised trainer: fit the network to a saved Q table. Reads the two files
+// the engine writes (radiance_map_data.txt: "144" then "px py pz q0 .. q143" per volume, RadianceMap::save_q_vals_to_file; vertices.txt,
+// Scene::save_vertices_to_file), shuffles, splits ~80 / 20 with rand() (:143-155), trains EPOCHS x ceil(train / BATCH_SIZE) Adam steps on the
+// summed squared distance over all outputs (:186-238, rlpt_dqn_train_supervised), evaluates the test error after every epoch (:240-279),
+// prints the reference's per-epoch block and saves the DyNet text model (:287-292). settings.cuh: BATCH_SIZE 128, EPOCHS 100.
+struct QValueTrainerResult { int lines = 0, vertices = 0, train = 0, test = 0, action_count = 0; std::vector<float> loss, error; };
+bool load_radiance_map_data(const std::string& path, std::vector<std::vector<float>>& radiance_map_data, int& action_count);      // main.cu:72-116
+bool load_vertices(const std::string& path, std::vector<float>& vertices);                                                          // main.cu:39-69
+QValueTrainerResult train_q_value_network(Renderer& renderer, const std::string& radiance_map_data = "../Radiance_Map_Data/radiance_map_data.txt",
+                                          const std::string& vertices = "../Radiance_Map_Data/vertices.txt", int epochs = 100, int batch_size = 128,
+                                          const char* save_model = "../Radiance_Map_Data/radiance_map_model.model", const char* load_model = nullptr,
+                                          unsigned shuffle_seed = 0, bool verbose = true);
 // Saved radiance volumes drawn as geometry (RENDER_SAVED_RADIANCE_VOLUMES, G/constants/image_settings.h:15, G/scenes/scene.cu:41-46):
 // each volume of a selected_*.txt file becomes a hemisphere of 12x12 quads (two Surfaces each) of diameter DIAMETER, coloured
 // from green to red by its distribution value relative to the volume's maximum.

@@ -286,3 +286,83 @@ def test_neuralq_training_tracer_learns_and_stays_unbiased(ctx, golden_scenes):
     assert losses[-1] < losses[0], losses
     assert zero[-1] < st0["zero_contribution_paths"] / st0["paths"], (zero, st0["zero_contribution_paths"] / st0["paths"])
     print("neural-q training: losses", losses, "zero-contribution", zero, "default", st0["zero_contribution_paths"] / st0["paths"])
+
+
+@pytest.mark.parametrize("network", ["trained", "glorot"])
+def test_neuralq_training_tracer_matches_oracle_same_paths(ctx, oracle, golden_scenes, dqn_golden, network):
+    """the training tracer (k_nqt_init / k_nqt_sample / k_nqt_trace / k_nqt_targets / k_nqt_respawn and the frame loop of
+    rlpt_render_neuralq) against oracle/nq_tracer_oracle.py, the numpy restatement of NeuralQPathtracer::render_frame tracing the same Philox
+    paths. The network is frozen (learning rate 0: every optimiser step still runs, the weights must not move) and the oracle evaluates Q through
+    the library's own forward, so the comparison isolates the tracer: epsilon-greedy sampling, rewards, discounts, TD targets (through the loss),
+    re-seeding of terminated rays, frame-buffer accumulation, path statistics. "glorot" is an untrained network whose output ReLUs zero most rows:
+    the cosine-weighted fallback for dead rows."""
+    from nq_tracer_oracle import nq_training_pass
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    w = h = 64; bounces = 80; eps = 0.2; batch = 1024; cam = (0.0, 0.0, -3.0)
+    ctx.configure(width=w, height=h, spp=1, max_bounces=bounces); ctx.camera_set(cam)
+    if network == "trained":
+        ctx.dqn_set_params(dqn_golden["params"])
+    else:
+        ctx.dqn_init(seed=11)
+    before = ctx.dqn_get_params().copy()
+    ctx.neuralq_set_hyper(learning_rate=0.0, epsilon_start=eps, epsilon_decay=0.0, epsilon_min=eps)
+    loss = ctx.render_neuralq(1, batch=batch)
+    img = ctx.frame_download().copy(); st = ctx.stats()
+    assert np.array_equal(ctx.dqn_get_params(), before)                           # frozen
+    o = nq_training_pass(oracle, s, lambda p: ctx.dqn_forward(p), w, h, 1984, 0, bounces, eps, 0.0, cam, batch)
+    assert st["paths"] == o["terminated"] == w * h
+    assert abs(st["path_length_sum"] - o["path_length_sum"]) <= 5e-3 * o["path_length_sum"], (st["path_length_sum"], o["path_length_sum"])
+    assert abs(st["zero_contribution_paths"] - o["zero_contribution"]) <= 5e-3 * w * h
+    assert st["train_steps"] == o["steps"]
+    oimg = o["accum"].astype(np.float32)
+    err = np.abs(img - oimg).max(1) / np.maximum(np.abs(oimg).max(1), 1e-2)
+    assert np.mean(err <= 5e-3) >= 0.99, (float(np.mean(err <= 5e-3)), float(err.max()))
+    assert abs(float(img.mean()) - float(oimg.mean())) <= 1e-2 * max(float(oimg.mean()), 1e-6)
+    assert abs(loss - o["loss"]) <= 5e-3 * max(o["loss"], 1e-6), (loss, o["loss"])
+
+
+def _two_gpu_nq_worker(rank, world, port, out_dir):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "reinforcement-light-rays-pathtracer_b200"))
+    import torch, torch.distributed as dist
+    import rlpt
+    from rlpt.dist import torch_allreduce_hook
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes.npz"))
+    s = {k.split("/")[1]: z[k] for k in z.files if k.startswith("cornell/")}
+    c = rlpt.Context(rank, width=32, height=32, spp=1, max_bounces=12, rank=rank, world_size=world)
+    c.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"]); c.camera_set((0, 0, -3))
+    c.dqn_init(seed=3)                                             # the same draw on every rank
+    p0 = c.dqn_get_params().copy()
+    # (1) one batch per rank, different data: local gradients, then the all-reduced ones
+    rs = np.random.RandomState(100 + rank)
+    pos = rs.uniform(-1, 1, (300, 3)).astype(np.float32); act = rs.randint(0, 144, 300).astype(np.uint32); tgt = rs.uniform(0, 2, 300).astype(np.float32)
+    c.dqn_train_batch(pos, act, tgt, apply_update=False); g_local = c.dqn_get_grads().copy()
+    c.set_allreduce(torch_allreduce_hook(rank))
+    c.dqn_train_batch(pos, act, tgt, apply_update=False); g_sum = c.dqn_get_grads().copy()
+    # (2) a training frame with the gradient all-reduce in every optimiser step: the replicas must stay identical
+    loss = c.render_neuralq(1, batch=256)
+    np.savez(os.path.join(out_dir, "nq_rank%d.npz" % rank), p0=p0, p1=c.dqn_get_params(), g_local=g_local, g_sum=g_sum, loss=loss, steps=c.stats()["train_steps"])
+    c.close(); dist.destroy_process_group()
+
+
+def test_two_gpus_neuralq_gradient_allreduce(tmp_path):
+    """rlpt_render_neuralq with world_size 2: every optimiser step sums the gradients of both ranks' batches (one all-reduce over the
+    block holding all eight gradient arrays) before Adam, so the two replicas of the network must remain bit-identical while training on different
+    samples; and the all-reduced gradient of one step must be the sum of the two local ones."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_two_gpu_nq_worker, args=(2, 29500 + os.getpid() % 200, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "nq_rank0.npz"), np.load(tmp_path / "nq_rank1.npz")
+    assert np.array_equal(r0["p0"], r1["p0"])
+    assert np.array_equal(r0["g_sum"], r1["g_sum"])
+    want = r0["g_local"].astype(np.float64) + r1["g_local"].astype(np.float64)
+    assert np.abs(r0["g_sum"] - want).max() <= 1e-4 * max(np.abs(want).max(), 1e-6)
+    assert not np.array_equal(r0["g_local"], r1["g_local"])
+    assert np.array_equal(r0["p1"], r1["p1"]) and not np.array_equal(r0["p1"], r0["p0"])      # trained, and in lock step
+    assert np.isfinite(r0["loss"]) and r0["steps"] == r1["steps"] > 0

@@ -470,6 +470,59 @@ def test_voronoi_view(ctx, oracle, golden_scenes):
         assert xs[m].max() - xs[m].min() <= 12 and ys[m].max() - ys[m].min() <= 12
 
 
+def test_voronoi_colours_are_the_nearest_volumes(ctx, oracle, golden_scenes):
+    """Every pixel of the Voronoi view against the long way round: the same jittered camera ray (Philox counters (pixel, frame)), the oracle's
+    closest hit, the oracle's nearest-volume search on that hit point, and the colour the view assigns to that volume (Philox(seed, volume))."""
+    from nq_tracer_oracle import camera_dir, draw4
+    s = golden_scenes["cornell"]
+    w = h = 96
+    ctx.configure(width=w, height=h, spp=1)
+    load_scene(ctx, s); load_scene(oracle, s); nv = ctx.radiance_map_build(); assert oracle.rmap_build() == nv
+    ctx.camera_set((0, 0, -3))
+    ctx.render_voronoi()
+    img = ctx.frame_download()
+    pix = np.arange(w * h, dtype=np.uint32)
+    u = draw4(1984, pix, 0, 0, 0)
+    d = camera_dir((pix // h).astype(np.int64), (pix % h).astype(np.int64), u[0], u[1], w, h)
+    org = np.tile(np.array([[0, 0, -3]], np.float32), (w * h, 1))
+    ty, ix, t, pos = oracle.closest_hit(org, d, h, 1)
+    sn = oracle.scene_normals()[0]
+    surf = ty == 2
+    vol = oracle.find_closest(pos[surf], sn[ix[surf]], 1)
+    c = draw4(1984, vol.astype(np.uint32), 0x766f726f, 0, 7)
+    exp = np.ones((w * h, 3), np.float32)
+    exp[surf] = np.stack([c[0], c[1], c[2]], 1)
+    assert np.mean(np.all(img == exp, 1)) >= 0.999              # (a camera ray on a triangle edge may resolve differently in the last bit of sincos-free code: none expected)
+
+
+def test_sarsa_max_direction_matches_oracle_same_paths(ctx, oracle, golden_scenes):
+    """The greedy debug sampler (RadianceVolume::sample_max_direction_from_radiance_distribution, radiance_volume.cu:248-278): after one ordinary
+    training frame (tables synchronised to the oracle's), a frame sampled towards each volume's largest Q must trace the oracle's paths."""
+    s = golden_scenes["cornell"]
+    load_scene(ctx, s); load_scene(oracle, s)
+    w = h = 48; spp = 4
+    ctx.configure(width=w, height=h, spp=spp, max_bounces=80); ctx.camera_set((0, 0, -3))
+    ctx.radiance_map_build(); oracle.rmap_build(); oracle.rmap_update_distributions(); oracle.rmap_merge_frame()
+    ctx.render_sarsa(1)
+    oracle.render_frame(1, w, h, spp, sample0=0, max_bounces=80, cam=(0, 0, -3), fma_mode=1, td_mode=1)
+    oracle.rmap_merge_frame(); oracle.rmap_update_distributions()
+    oq, ocdf, ovis, oirr = oracle.rmap_state()
+    ctx.radiance_map_set_q(oq, ovis); ctx.radiance_map_update_distributions(); ctx.sync()
+    ctx.frame_reset(); ctx.stats_reset()
+    ctx.set_max_direction(True); oracle.set_max_direction(True)
+    try:
+        ctx.render_sarsa(1)
+        img, st = ctx.frame_download(), ctx.stats()
+        o, ost = oracle.render_frame(1, w, h, spp, sample0=spp, max_bounces=80, cam=(0, 0, -3), fma_mode=1, td_mode=1)
+    finally:
+        ctx.set_max_direction(False); oracle.set_max_direction(False)
+    _assert_images_close(img, o / spp, frac=0.99, tol=5e-3, mean_tol=1e-2)
+    assert st["paths"] == ost["paths"]
+    assert abs(st["path_length_sum"] - ost["total_path_length"]) <= 5e-3 * ost["total_path_length"]
+    # greedy sampling differs from CDF sampling: the same frame sampled from the distributions gives another image
+    ctx.frame_reset(); ctx.radiance_map_set_q(oq, ovis); ctx.radiance_map_update_distributions()
+
+
 def test_frame_argb_and_bmp(ctx, golden_scenes, tmp_path):
     from checkers import to_rgb8
     load_scene(ctx, golden_scenes["cornell"])
