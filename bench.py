@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exclusive", action="store_true")
     ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --spp is the GLOBAL frame's samples per pixel, each rank traces spp / N of them")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -319,6 +320,11 @@ def main():
     s = load_scene(scene_name)
     if method == 3 and args.spp == 32:
         args.spp = 1                                           # Neural-Q: one pass over the pixels per training frame
+    global_spp = args.spp * world if args.scaling == "weak" else args.spp
+    if args.scaling == "strong":
+        if args.spp % world:
+            raise SystemExit("bench.py --scaling strong: --spp must be a multiple of the GPU count")
+        args.spp //= world                                     # this rank's share of the global frame
     ctx = rlpt.Context(local, width=args.width, height=args.height, spp=args.spp, max_bounces=80, env_light=env, traversal=args.traversal,
                        rank=rank, world_size=world)
     ctx.scene_upload(s["sv"], s["srgb"], s["lv"], s["lrgb"])
@@ -430,13 +436,14 @@ def main():
             return traffic[kernel]["bytes_per_ray"] * rays_per_launch if (split and kernel in traffic and args.workload == "cornell_sarsa") else None
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "built-in Cornell box scene / bundled .obj geometry (no dataset); radiance volumes start untrained, trained by the %d warm-up frames" % args.warmup,
             "config": {"workload": args.workload, "scene": "%s (%d surfaces + %d area lights)" % (scene_name, len(s["sv"]), len(s["lv"])),
                        "method": "Expected SARSA radiance volumes, train + render" if method == 1 else "default path tracer",
-                       "width": args.width, "height": args.height, "spp_per_frame": args.spp, "frames": args.steps, "spp_total_per_gpu": args.spp * args.steps,
+                       "width": args.width, "height": args.height, "spp_per_frame": args.spp, "spp_per_global_frame": global_spp, "frames": args.steps, "spp_total_per_gpu": args.spp * args.steps,
                        "radiance_volumes": nv, "grid": "12x12", "max_bounces": 80, "partition": "samples (rank r traces samples r*spp..(r+1)*spp-1 of each global frame)", "exchange": exchange,
                        "l2": "inputs larger than L2: path queues %.2f GB + Q-table %.0f MB per GPU" % (args.width * args.height * args.spp * 60 * 2 / 1e9, nv * 144 * 20 / 1e6)},
+            "radiance_map_build_ms": ({k: v * 1e3 for k, v in ctx.radiance_map_build_seconds().items()} if method == 1 else None),
             "mean_path_length": st["path_length_sum"] / max(st["paths"], 1), "mray_casts_per_s": st["ray_casts"] * world / dev_s / 1e6,
             "zero_contribution_fraction": st["zero_contribution_paths"] / max(st["paths"], 1),
             "kd_search_fallback_fraction": st.get("kd_fallbacks", 0.0) / max(st["ray_casts"], 1),

@@ -118,6 +118,9 @@ int rlpt_closest_hit_device(rlpt_ctx* ctx, const float* d_org, const float* d_di
  * (G/main.cu:274-289). Volumes and tree are identical to the reference's (same rand() stream, same std::sort);
  * device storage is SoA (DESIGN.md "Q-table layout"). */
 int rlpt_radiance_map_build(rlpt_ctx* ctx);
+/* wall-clock seconds of the last build: [0] volume sampling + kd-tree (host; the reference's RadianceMap constructor, G/radiance_volumes/radiance_map.cu:8-54),
+ * [1] nearest-volume candidate cells (host), [2] uploads and the first CDF build (device), [3] total */
+int rlpt_radiance_map_build_seconds(rlpt_ctx* ctx, double* seconds4);
 int rlpt_radiance_map_info(rlpt_ctx* ctx, int* n_volumes, int* n_tree_nodes);
 /* Peer-memory exchange for N > 1 ranks on one node (one process per GPU). Without it the Q accumulators are all-reduced
  * through the rlpt_set_allreduce hook and merged afterwards; with it ONE kernel per rank reduces its slice of the volumes

@@ -12,7 +12,7 @@ pids=()
 for f in rlpt_kernels rlpt_bvh rlpt_capi rlpt_dqn; do
   $NVCC $FLAGS -c csrc/$f.cu -o build/$f.o 2> build/$f.ptxas.log & pids+=($!)
 done
-g++ -std=c++17 -O2 -fPIC -ffp-contract=off -fno-fast-math -c csrc/rlpt_radiance_host.cpp -o build/rlpt_radiance_host.o & pids+=($!)
+g++ -std=c++17 -O2 -fPIC -fopenmp -ffp-contract=off -fno-fast-math -c csrc/rlpt_radiance_host.cpp -o build/rlpt_radiance_host.o & pids+=($!)
 for p in "${pids[@]}"; do wait $p || { cat build/*.ptxas.log | grep -iE "error|fatal" -A3 | head -60; exit 1; }; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -ccbin g++ -o lib/${RLPT_LIB_NAME:-librlpt.so} build/rlpt_kernels.o build/rlpt_bvh.o build/rlpt_capi.o build/rlpt_dqn.o build/rlpt_radiance_host.o -lcudart
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -ccbin g++ -o lib/${RLPT_LIB_NAME:-librlpt.so} build/rlpt_kernels.o build/rlpt_bvh.o build/rlpt_capi.o build/rlpt_dqn.o build/rlpt_radiance_host.o -lcudart -lgomp
 echo "built $(pwd)/lib/librlpt.so"

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <array>
+#include <chrono>
 
 using namespace rlpt;
 
@@ -43,7 +44,7 @@ struct rlpt_ctx {
     // camera / per-frame
     float cam[3] = { 0.f, 0.f, -3.f }; float yaw_y = 0.f, yaw_x = 0.f; int max_dir = 0;
     // radiance map
-    bool have_rmap = false;
+    bool have_rmap = false; double rmap_build_s[4] = { 0.0, 0.0, 0.0, 0.0 };     // volumes + kd-tree (host), candidate cells (host), uploads + first CDF build (device), total
     std::vector<HostVolume> h_vol; std::vector<HostTreeElement> h_tree;
     float4 *d_kd = nullptr, *d_posn = nullptr; int* d_vol_surface = nullptr;
     int4* d_vc_table = nullptr; float4* d_vc_cand = nullptr; int4* d_vx_table = nullptr; float4* d_vx_cand = nullptr; float vx_built_within = 0.f; float vc_built_accept = 0.f; size_t vc_keys = 0, vc_listed = 0;   // nearest-volume candidate cells
@@ -442,7 +443,10 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     if (c->n_surf == 0) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build: scene has no surfaces");
     CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream));
     free_rmap(c);
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     host_build_radiance_map(c->h_surf_v.data(), c->h_surf_nrm.data(), c->n_surf, c->cfg.area_per_sample, c->h_vol, c->h_tree);
+    c->rmap_build_s[0] = since(t_begin); c->rmap_build_s[1] = 0.0;
     const int nv = (int)c->h_vol.size(), nt = (int)c->h_tree.size();
     if (nv == 0) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build: no radiance volumes (surfaces smaller than area_per_sample)");
     if (nv >= (1 << 24)) return fail(RLPT_ERR_UNSUPPORTED, "rlpt_radiance_map_build: more than 2^24 radiance volumes");
@@ -487,7 +491,9 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
         const float accept = rm.within_abs * (1.f - 1e-5f);
         std::vector<int> vclass(nv); for (int i = 0; i < nv; ++i) vclass[i] = c->h_surf_class[c->h_vol[i].surface];
         HostVCells hv;
+        const auto t_vc = std::chrono::steady_clock::now();
         host_build_vcells(c->h_surf_v.data(), c->h_surf_class.data(), c->n_surf, c->h_vol, vclass, c->h_tree, factor * std::sqrt(std::max(c->cfg.area_per_sample, 1e-12f)), accept, rm.within_abs, hv);
+        c->rmap_build_s[1] = since(t_vc);
         CK(cudaMalloc(&c->d_vc_table, sizeof(int) * hv.table.size())); CK(cudaMalloc(&c->d_vc_cand, sizeof(float) * hv.cand.size()));
         CK(cudaMemcpy(c->d_vc_table, hv.table.data(), sizeof(int) * hv.table.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_vc_cand, hv.cand.data(), sizeof(float) * hv.cand.size(), cudaMemcpyHostToDevice));
@@ -503,6 +509,12 @@ int rlpt_radiance_map_build(rlpt_ctx* c) {
     c->have_rmap = true;
     launch_merge(rm, c->d_surf_lum_over_pi, c->cfg.radiance_threshold, 1, c->stream);
     CK(cudaStreamSynchronize(c->stream)); CK(cudaGetLastError());
+    c->rmap_build_s[3] = since(t_begin); c->rmap_build_s[2] = c->rmap_build_s[3] - c->rmap_build_s[0] - c->rmap_build_s[1];
+    return RLPT_OK;
+}
+int rlpt_radiance_map_build_seconds(rlpt_ctx* c, double* seconds4) {
+    if (!c || !c->have_rmap || !seconds4) return fail(RLPT_ERR_ARG, "rlpt_radiance_map_build_seconds: no radiance map");
+    for (int k = 0; k < 4; ++k) seconds4[k] = c->rmap_build_s[k];
     return RLPT_OK;
 }
 
@@ -1199,10 +1211,12 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                             NqTrainState gs = c->nqt; gs.state = c->d_nqg_state; gs.reward = c->d_nqg_reward; gs.discount = c->d_nqg_discount;
                             cudaGraph_t graph = nullptr;
                             CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                            DqnFwdParams gp = fp; gp.pos = c->d_nqg_loc; gp.n = bn; gp.q = c->d_nqt_qnext; gp.q_stride = S;
+                            // one launch evaluates the batch's states (activations kept for the backward pass) and its next states (Q only, for the TD targets)
+                            DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->d_nqg_sloc, bn);
+                            gp.pos2 = c->d_nqg_loc; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
                             int frc = dqn_forward(c->dq, gp, c->stream);
                             launch_nqt_targets(gs, 0, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss);
+                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss, true);
                             cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
                             if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(RLPT_ERR_CUDA, "Neural-Q training step: graph capture failed"); }
                             ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
@@ -1213,13 +1227,15 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         CK(cudaGraphLaunch(c->nq_graph_exec, c->stream));
                         c->dq_train.step++;
                     } else {
-                        fp.pos = c->nqt.loc + start; fp.n = bn; fp.q = c->d_nqt_qnext; fp.q_stride = S;
-                        int frc = dqn_forward(c->dq, fp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
+                        int frc = dqn_train_prepare(c->dq, c->dq_train, bn, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
+                        DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->nqt.sloc + start, bn);
+                        gp.pos2 = c->nqt.loc + start; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
+                        frc = dqn_forward(c->dq, gp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
                         launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss);
+                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true);
                         if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
                     }
-                    c->launches += 22.0;       // kernels of one optimiser step (staging, 2 forwards, targets, zeroing, 5 GEMMs, deltas, collect, norm, Adam, operand refresh)
+                    c->launches += 19.0;       // kernels of one optimiser step (staging, forward of both batches, targets, zeroing, prepare, 5 GEMMs, 3 deltas, collect, norm, tick, Adam, 2 operand refreshes)
                     c->k_all[4] += 1.0;
                 }
                 cudaEvent_t t1 = t0 ? kev_mark(c, c->stream) : nullptr;

@@ -168,12 +168,18 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's 32 lanes
 
     LayerPipe lp; uint32_t done_uses = 0;
-    const int n_rays = p.n_ptr ? min(*p.n_ptr, p.n) : p.n;
-    const int n_tiles = (n_rays + DQ_TILE - 1) / DQ_TILE;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n_rays1 = p.n_ptr ? min(*p.n_ptr, p.n) : p.n;
+    const int n_tiles1 = (n_rays1 + DQ_TILE - 1) / DQ_TILE, n_tiles = n_tiles1 + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
+    for (int tile_all = blockIdx.x; tile_all < n_tiles; tile_all += gridDim.x) {
+        // the second batch (next states of a training step: Q only) rides in the same launch, its tiles after the first batch's
+        const bool second = tile_all >= n_tiles1;
+        const int tile = second ? tile_all - n_tiles1 : tile_all, n_rays = second ? p.n2 : n_rays1;
+        const float4* __restrict__ pos = second ? p.pos2 : p.pos;
+        float* __restrict__ q_out = second ? p.q2 : p.q; const int q_stride = second ? p.q_stride2 : p.q_stride;
+        __nv_bfloat16* const k1 = second ? nullptr : p.h1t; __nv_bfloat16* const k2 = second ? nullptr : p.h2t; __nv_bfloat16* const k3 = second ? nullptr : p.h3t;
         const int ray = tile * DQ_TILE + t; const bool valid = ray < n_rays;
         // ---- layer 1 (fp32): h1 = relu(c1 - M1 x), 8 outputs per 16-byte store into the A operand
-        float4 x = valid ? p.pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = valid ? pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j0 = 0; j0 < DQ_K2; j0 += 8) {
             __nv_bfloat162 pk[4];
 #pragma unroll
@@ -184,21 +190,21 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
                 pk[j] = __floats2bfloat162_rn(ha, hb);
             }
             *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(t, j0, DQ_K2)) = *reinterpret_cast<uint4*>(&pk[0]);
-            if (p.h1t && valid) {
+            if (k1 && valid) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { p.h1t[(size_t)(j0 + 2 * j) * p.h_stride + ray] = pk[j].x; p.h1t[(size_t)(j0 + 2 * j + 1) * p.h_stride + ray] = pk[j].y; }
+                for (int j = 0; j < 4; ++j) { k1[(size_t)(j0 + 2 * j) * p.h_stride + ray] = pk[j].x; k1[(size_t)(j0 + 2 * j + 1) * p.h_stride + ray] = pk[j].y; }
             }
         }
         fence_proxy_async(); tc_fence_before(); __syncthreads();
         // ---- layer 2: 200 -> 300
         if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K2, p.w2p, DQ_N2, tmem_base, 0); }
         mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
-        hidden_epilogue(smem, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, t, p.h2t, p.h_stride, ray, valid);
+        hidden_epilogue(smem, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, t, k2, p.h_stride, ray, valid);
         fence_proxy_async(); tc_fence_before(); __syncthreads();
         // ---- layer 3: 300 -> 200
         if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A2, DQ_K3, p.w3p, DQ_N3, tmem_base, DQ_N2); }
         mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
-        hidden_epilogue(smem, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, t, p.h3t, p.h_stride, ray, valid);
+        hidden_epilogue(smem, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, t, k3, p.h_stride, ray, valid);
         fence_proxy_async(); tc_fence_before(); __syncthreads();
         // ---- layer 4: 200 -> 144, ReLU on the output as well (N/dq_network.cu:17)
         if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K4, p.w4p, DQ_N4, tmem_base, 0); }
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constan
             uint32_t r[16]; tmem_ld16(tmem_lane + (uint32_t)c0, r);
             if (valid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) p.q[(size_t)(c0 + j) * p.q_stride + ray] = fmaxf(__uint_as_float(r[j]) + s_b4[c0 + j], 0.f);
+                for (int j = 0; j < 16; ++j) q_out[(size_t)(c0 + j) * q_stride + ray] = fmaxf(__uint_as_float(r[j]) + s_b4[c0 + j], 0.f);
             }
         }
         tc_fence_before(); __syncthreads();       // TMEM and A1 are reused by the next tile
@@ -222,7 +228,7 @@ int dqn_set_smem_limit() { int rc = (int)cudaFuncSetAttribute(k_dqn_forward, cud
 int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
     if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
     int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE;
+    const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
     k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_TILE, SM_TOTAL, s>>>(p);
     return (int)cudaGetLastError();
 }
@@ -366,8 +372,10 @@ namespace rlpt {
 constexpr int GM_KC = 64, GM_BN = 160;
 constexpr uint32_t GM_A = 0, GM_B = GM_A + 2 * DQ_TILE * GM_KC * 2, GM_BAR = GM_B + 2 * GM_BN * GM_KC * 2, GM_TOTAL = GM_BAR + 64;
 
+// c_t != 0: C is stored transposed, C[n][m] with row length ldc -- the CTA's 128 threads (one output row each) then write consecutive addresses,
+// and the consumer of the backward data path (k_delta_hidden, feature-major) reads them the same way.
 __global__ void __launch_bounds__(DQ_TILE, 1) k_gemm_bf16_tn(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                              int M, int N, int K, int k_per_split) {
+                                                              int M, int N, int K, int k_per_split, int c_t) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_BAR);          // [0,1]: stage free (MMAs done), [2]: all done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
@@ -419,19 +427,20 @@ __global__ void __launch_bounds__(DQ_TILE, 1) k_gemm_bf16_tn(const __nv_bfloat16
     for (int c0 = 0; c0 < bn; c0 += 16) {
         uint32_t r[16]; tmem_ld16(lane_addr + (uint32_t)c0, r);
         if (m < M && chunk > 0) {
-            float* dst = C + (size_t)m * ldc + n0 + c0;
+            float* dst = c_t ? C + (size_t)(n0 + c0) * ldc + m : C + (size_t)m * ldc + n0 + c0;
+            const size_t step = c_t ? (size_t)ldc : 1;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j, __uint_as_float(r[j])); else dst[j] = __uint_as_float(r[j]); }
+            for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j * step, __uint_as_float(r[j])); else dst[j * step] = __uint_as_float(r[j]); }
         }
     }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
-static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s) {
+static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s, int c_t = 0) {
     int k_per = ((K + k_splits - 1) / k_splits + GM_KC - 1) / GM_KC * GM_KC; if (k_per < GM_KC) k_per = GM_KC;
     const int zs = (K + k_per - 1) / k_per;
     dim3 grid((M + DQ_TILE - 1) / DQ_TILE, (N + GM_BN - 1) / GM_BN, zs);
-    k_gemm_bf16_tn<<<grid, DQ_TILE, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per);
+    k_gemm_bf16_tn<<<grid, DQ_TILE, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per, c_t);
     return (int)cudaGetLastError();
 }
 
@@ -529,7 +538,7 @@ __global__ void k_delta_hidden(const float* __restrict__ pre, int ld_pre, const 
     int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= S) return;
     float d = 0.f;
-    if (j < n_feat) { float h = __bfloat162float(ht[(size_t)j * S + i]); d = h > 0.f ? pre[(size_t)i * ld_pre + j] : 0.f; }
+    if (j < n_feat) { float h = __bfloat162float(ht[(size_t)j * S + i]); d = h > 0.f ? pre[(size_t)j * ld_pre + i] : 0.f; }       // pre is feature-major (the GEMM stores it transposed)
     __nv_bfloat16 db = __float2bfloat16_rn(d);
     if (d_ray) d_ray[(size_t)i * k_pad + j] = db;
     d_feat[(size_t)j * S + i] = db;
@@ -555,7 +564,14 @@ __global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __r
 // lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
 // The step counter lives on the device (scalars[3], advanced once per step by k_adam_tick, which also derives the bias-corrected
 // step size into scalars[2]), so that a captured optimiser step can be replayed as a CUDA graph without any host value in it.
-__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2, float* __restrict__ loss_total) {
+constexpr int SQN_BLOCKS = 128;        // k_sqnorm_all's grid: that many partial sums, added in order by k_adam_tick
+__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2, float* __restrict__ loss_total, const float* __restrict__ sq_partial) {
+    // one warp; the summation order is fixed (lane l adds partials 4l .. 4l+3, then a butterfly), so every rank derives the same bits
+    const int l = threadIdx.x;
+    float n2 = (sq_partial[4 * l] + sq_partial[4 * l + 1]) + (sq_partial[4 * l + 2] + sq_partial[4 * l + 3]);
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    if (l) return;
+    scalars[1] = n2;
     if (loss_total) *loss_total += scalars[0];                          // running loss of the frame (was a kernel of its own)
     const float t = scalars[3] + 1.f; scalars[3] = t;
     scalars[2] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
@@ -577,11 +593,17 @@ __global__ void k_zero_grads(ParamSegs t, float* a, int na, float* b, int nb, fl
     if (j < nc) { c[j] = 0.f; return; } j -= nc;
     if (j < 2) scalars[j] = 0.f;                               // loss and gradient norm; [2] step size and [3] step count persist
 }
-__global__ void k_sqnorm_all(ParamSegs t, float* __restrict__ out) {
+// squared gradient norm, in a FIXED summation order (per-thread strided sums -> block tree -> 128 partials added by one thread): after a gradient
+// all-reduce every rank holds the same gradients, and the clipping factor derived from this norm must then be the same bits on every rank, or the
+// replicas of the network drift apart in the last place. (A float atomicAdd per warp, the first form, sums in arrival order.)
+__global__ void __launch_bounds__(256) k_sqnorm_all(ParamSegs t, float* __restrict__ partial) {
+    __shared__ float s_w[8];
     float acc = 0.f; const int total = t.start[8];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) { const int s = seg_of(t, i); const float g = t.g[s][i - t.start[s]]; acc += g * g; }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float b = 0.f; for (int w = 0; w < 8; ++w) b += s_w[w]; partial[blockIdx.x] = b; }
 }
 __global__ void k_adam_all(ParamSegs t, const float* __restrict__ scalars, float clip, float beta1, float beta2, float eps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -627,7 +649,7 @@ __global__ void k_pack_all(const float* __restrict__ w2, const float* __restrict
 }
 
 void dqn_train_free(DqnTrain& t) {
-    cudaFree(t.gall);
+    cudaFree(t.gall); cudaFree(t.sq_partial);
     for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
     cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
@@ -653,7 +675,7 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
             DQ_CK(cudaMemset(t.mw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.mb[l], 0, 4 * nb)); DQ_CK(cudaMemset(t.vw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.vb[l], 0, 4 * nb));
         }
         DQ_CK(cudaMalloc(&t.dw3x, 4 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.dw2x, 4 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.dg, 4 * (size_t)DQ_K2 * 16));
-        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4)); DQ_CK(cudaMemset(t.scalars, 0, 4 * 4));
+        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4)); DQ_CK(cudaMemset(t.scalars, 0, 4 * 4)); DQ_CK(cudaMalloc(&t.sq_partial, 4 * 128));
         t.step = 0;
     }
     if (S > t.capacity) {
@@ -672,6 +694,12 @@ static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+DqnFwdParams dqn_train_forward_params(const DqnDev& d, DqnTrain& t, const float4* pos, int n) {
+    const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
+    fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
+    return fp;
+}
 int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {           // everything a captured step must not contain: allocations, the first transposes, the side stream
     int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
     if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }
@@ -682,7 +710,7 @@ int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {          
     return 0;
 }
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs, float* loss_total) {
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs, float* loss_total, bool forward_done) {
     if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
     int rc = dqn_train_prepare(d, t, n, s); if (rc) return rc;               // (afterwards k_pack_all keeps the transposes current)
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
@@ -693,9 +721,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         k_zero_grads<<<(total + 255) / 256, 256, 0, s>>>(segs, t.dw3x, na, t.dw2x, nb, t.dg, nc, t.scalars);
     }
     // forward, activations kept
-    DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
-    fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
-    rc = dqn_forward(d, fp, s); if (rc) return rc;
+    if (!forward_done) { const DqnFwdParams fp = dqn_train_forward_params(d, t, pos, n); rc = dqn_forward(d, fp, s); if (rc) return rc; }
     k_train_prepare<<<(S + 127) / 128, 128, 0, s>>>(pos, n, S, t.xt, t.h1t, t.h2t, t.h3t);
     // backward: data path
     if (all_outputs) {            // targets: [n][144]
@@ -711,12 +737,13 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
     DQ_CK(cudaEventRecord(t.ev[0], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[0], 0));
     rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, t.side); if (rc) return rc;                 // [208 x S] x [304 x S]^T
-    rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, DQ_N2, S, DQ_N2, DQ_K4, 1, s); if (rc) return rc;                  // [S x 208] x [304 x 208]^T
-    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, DQ_N2, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
+    rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, S, S, DQ_N2, DQ_K4, 1, s, 1); if (rc) return rc;                    // [S x 208] x [304 x 208]^T, stored [304][S]
+    // (the mask + bf16 conversion stays a launch of its own: fused into the GEMM's epilogue it ran on the GEMM's 64 CTAs instead of ~10 k blocks, 141 -> 191 us per step)
+    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, S, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
     DQ_CK(cudaEventRecord(t.ev[1], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[1], 0));
     rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, t.side); if (rc) return rc;                 // [304 x S] x [208 x S]^T
-    rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, DQ_N3, S, DQ_N3, DQ_K3, 1, s); if (rc) return rc;                  // [S x 304] x [208 x 304]^T
-    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K2), 128, 0, s>>>(t.p1, DQ_N3, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
+    rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, S, S, DQ_N3, DQ_K3, 1, s, 1); if (rc) return rc;                    // [S x 304] x [208 x 304]^T, stored [208][S]
+    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K2), 128, 0, s>>>(t.p1, S, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
     rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
     DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
     const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
@@ -726,9 +753,9 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
     }
     if (!apply_update) return (int)cudaGetLastError();
-    k_sqnorm_all<<<128, 256, 0, s>>>(segs, t.scalars + 1);
+    k_sqnorm_all<<<SQN_BLOCKS, 256, 0, s>>>(segs, t.sq_partial);
     t.step++;
-    k_adam_tick<<<1, 1, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2, loss_total);
+    k_adam_tick<<<1, 32, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2, loss_total, t.sq_partial);
     k_adam_all<<<(segs.start[8] + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
     // operands for the next forward / backward: layer-1 rank-3 form, packed bf16 weights, the two transposes
     k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);

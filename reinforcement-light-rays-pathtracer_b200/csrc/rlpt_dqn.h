@@ -43,6 +43,7 @@ struct DqnFwdParams {
     const __nv_bfloat16 *w2p, *w3p, *w4p;
     float* q; int q_stride;                         // out: [144][q_stride], action-major (coalesced for producer and consumers)
     __nv_bfloat16 *h1t, *h2t, *h3t; int h_stride;   // optional: activations kept for the backward pass, feature-major [K_pad][h_stride]
+    const float4* pos2; int n2; float* q2; int q_stride2;       // optional second batch evaluated by the same launch (no activations kept): tiles follow the first batch's
 };
 
 // Training state: gradients, Adam moments (DyNet AdamTrainer defaults: lr 1e-3, beta1 0.9, beta2 0.999, eps 1e-8, gradient
@@ -54,6 +55,7 @@ struct DqnTrain {
     int capacity = 0;                               // S the buffers were allocated for
     float *gw[4] = { nullptr, nullptr, nullptr, nullptr }, *gb[4] = { nullptr, nullptr, nullptr, nullptr };      // gradients: views into gall
     float* gall = nullptr; size_t gall_count = 0;   // one block holding all eight gradient arrays
+    float* sq_partial = nullptr;                    // [128] per-block partial sums of the squared gradient norm (summed in a fixed order)
     float *mw[4] = { nullptr, nullptr, nullptr, nullptr }, *mb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam first moments
     float *vw[4] = { nullptr, nullptr, nullptr, nullptr }, *vb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam second moments
     float *dw3x = nullptr, *dw2x = nullptr, *dg = nullptr;      // GEMM outputs: [208][304] (col 300 = db3), [304][208] (col 200 = db2), [208][16] (cols 0-2 = G, col 3 = db1)
@@ -77,7 +79,9 @@ void dqn_train_free(DqnTrain& t);
 typedef int (*dqn_allreduce_fn)(void* d_buf, uint64_t count, int dtype, void* cuda_stream, void* user);
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
                     dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs = false,    // all_outputs: targets is [n][144], the supervised loss over every output (actions unused)
-                    float* loss_total = nullptr);                                                                  // device scalar the step's loss is added to (may be null)
+                    float* loss_total = nullptr,                                                                   // device scalar the step's loss is added to (may be null)
+                    bool forward_done = false);                                                                    // the caller already ran the kept-activation forward into t.q / t.h*t (dqn_train_forward_params)
+DqnFwdParams dqn_train_forward_params(const DqnDev& d, DqnTrain& t, const float4* pos, int n);   // the forward a training step starts with, for callers that merge it with another batch                                                                  // device scalar the step's loss is added to (may be null)
 int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s);                     // allocations, first transposes, side stream: call before capturing a step
 int dqn_alloc(DqnDev& d, int k_in);
 void dqn_free(DqnDev& d);

@@ -17,6 +17,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace rlpt {
 
@@ -172,6 +175,8 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
         std::vector<int> fill(cstart.begin(), cstart.end() - 1);
         for (int i = 0; i < nv; ++i) corder[fill[cof[i]]++] = i;
     }
+    const bool vc_timing = getenv("RLPT_VC_TIMING") != nullptr; auto vc_t0 = std::chrono::steady_clock::now();
+    auto vc_mark = [&](const char* what) { if (vc_timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "vcells %s: %.3f s\n", what, std::chrono::duration<double>(t - vc_t0).count()); vc_t0 = t; } };
     // (cell, class) pairs: every fine cell whose centre is within half a cell diagonal (+ margin) of a surface of that class
     std::unordered_map<uint64_t, int> keys;
     const double half_diag = 0.5 * std::sqrt(3.0) * (double)h + margin + 1e-4 * scale;
@@ -191,55 +196,76 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
             keys.emplace((cell << 32) | (uint32_t)sclass[s], 0);
         }
     }
+    vc_mark("keys");
     // candidate lists
     std::vector<uint64_t> order; order.reserve(keys.size());
     for (auto& kv : keys) order.push_back(kv.first);
     std::sort(order.begin(), order.end());
     struct Entry { int cell, cls, start, n4; };
     std::vector<Entry> entries; entries.reserve(order.size());
-    std::vector<std::pair<double, int>> near;   // (mindist, volume)
     std::vector<uint64_t> xkeys;
-    for (uint64_t key : order) {
-        const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
-        const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
-        const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
-        const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
-        int k0[3], k1[3];
-        k0[0] = ccell(blo[0] - reach, 0, cnx); k1[0] = ccell(bhi[0] + reach, 0, cnx);
-        k0[1] = ccell(blo[1] - reach, 1, cny); k1[1] = ccell(bhi[1] + reach, 1, cny);
-        k0[2] = ccell(blo[2] - reach, 2, cnz); k1[2] = ccell(bhi[2] + reach, 2, cnz);
-        near.clear(); double R = 1e300;
-        for (int cz = k0[2]; cz <= k1[2]; ++cz) for (int cy = k0[1]; cy <= k1[1]; ++cy) for (int cx = k0[0]; cx <= k1[0]; ++cx) {
-            const size_t cc = (size_t)(cz * cny + cy) * cnx + cx;
-            for (int j = cstart[cc]; j < cstart[cc + 1]; ++j) {
-                const int v = corder[j]; if (vclass[v] != cls) continue;
-                double mn2 = 0, mx2 = 0;
-                for (int k = 0; k < 3; ++k) {
-                    const double q = vol[v].pos[k];
-                    const double dlo = blo[k] - q, dhi = q - bhi[k];
-                    const double dmin = std::max(0.0, std::max(dlo, dhi)), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
-                    mn2 += dmin * dmin; mx2 += dmax * dmax;
+    // The lists of different (cell, class) pairs are independent: they are computed by all host threads (OpenMP) into per-pair vectors and
+    // concatenated in key order afterwards, so the tables do not depend on the thread count. (Single-threaded this loop was 6.2 s of archway's
+    // 6.5 s radiance-map build.)
+    vc_mark("sort keys");
+    const size_t nk = order.size();
+    std::vector<std::vector<int>> lists(nk); std::vector<char> is_x(nk, 0);
+#pragma omp parallel
+    {
+        std::vector<std::pair<double, int>> near;   // (mindist, volume)
+#pragma omp for schedule(dynamic, 256)
+        for (long long qi = 0; qi < (long long)nk; ++qi) {
+            const uint64_t key = order[(size_t)qi];
+            const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
+            const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
+            const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
+            const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
+            int k0[3], k1[3];
+            k0[0] = ccell(blo[0] - reach, 0, cnx); k1[0] = ccell(bhi[0] + reach, 0, cnx);
+            k0[1] = ccell(blo[1] - reach, 1, cny); k1[1] = ccell(bhi[1] + reach, 1, cny);
+            k0[2] = ccell(blo[2] - reach, 2, cnz); k1[2] = ccell(bhi[2] + reach, 2, cnz);
+            near.clear(); double R = 1e300;
+            for (int cz = k0[2]; cz <= k1[2]; ++cz) for (int cy = k0[1]; cy <= k1[1]; ++cy) for (int cx = k0[0]; cx <= k1[0]; ++cx) {
+                const size_t cc = (size_t)(cz * cny + cy) * cnx + cx;
+                for (int j = cstart[cc]; j < cstart[cc + 1]; ++j) {
+                    const int v = corder[j]; if (vclass[v] != cls) continue;
+                    double mn2 = 0, mx2 = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        const double q = vol[v].pos[k];
+                        const double dlo = blo[k] - q, dhi = q - bhi[k];
+                        const double dmin = std::max(0.0, std::max(dlo, dhi)), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
+                        mn2 += dmin * dmin; mx2 += dmax * dmax;
+                    }
+                    const double mn = std::sqrt(mn2), mx = std::sqrt(mx2);
+                    R = std::min(R, mx);
+                    if (mn <= reach) near.push_back({ mn, v });
                 }
-                const double mn = std::sqrt(mn2), mx = std::sqrt(mx2);
-                R = std::min(R, mx);
-                if (mn <= reach) near.push_back({ mn, v });
             }
+            if (near.empty() || R >= (double)accept_r * 0.999 - margin) is_x[(size_t)qi] = 1;     // some point of the cell may have no same-class volume within accept_r
+            if (near.empty()) continue;
+            const double lim = std::min(R * (1.0 + 1e-4) + 1e-6 * scale, reach);
+            std::sort(near.begin(), near.end(), [](const std::pair<double, int>& p, const std::pair<double, int>& q) { return p.second < q.second; });
+            std::vector<int>& l = lists[(size_t)qi];
+            for (auto& pr : near) if (pr.first <= lim) l.push_back(pr.second);
         }
-        if (near.empty() || R >= (double)accept_r * 0.999 - margin) xkeys.push_back(key);     // some point of the cell may have no same-class volume within accept_r
-        if (near.empty()) continue;
-        const double lim = std::min(R * (1.0 + 1e-4) + 1e-6 * scale, reach);
-        Entry e{ cell, cls, (int)(out.cand.size() / 16), 0 };      // first group of 4 candidates
-        std::sort(near.begin(), near.end(), [](const std::pair<double, int>& p, const std::pair<double, int>& q) { return p.second < q.second; });
+    }
+    vc_mark("lists (parallel)");
+    for (size_t qi = 0; qi < nk; ++qi) {
+        const uint64_t key = order[qi];
+        if (is_x[qi]) xkeys.push_back(key);
+        const std::vector<int>& l = lists[qi];
+        if (l.empty()) continue;
+        Entry e{ (int)(key >> 32), (int)(uint32_t)key, (int)(out.cand.size() / 16), 0 };      // first group of 4 candidates
         int n = 0;
-        for (auto& pr : near) if (pr.first <= lim) {
-            const int v = pr.second; float w; memcpy(&w, &v, 4);
+        for (int v : l) {
+            float w; memcpy(&w, &v, 4);
             out.cand.push_back(vol[v].pos[0]); out.cand.push_back(vol[v].pos[1]); out.cand.push_back(vol[v].pos[2]); out.cand.push_back(w); ++n;
         }
-        if (n == 0) continue;
         out.listed += (size_t)n;
         for (; n % 4 != 0; ++n) { const int v = -1; float w; memcpy(&w, &v, 4); out.cand.push_back(1e18f); out.cand.push_back(1e18f); out.cand.push_back(1e18f); out.cand.push_back(w); }
         e.n4 = n / 4; entries.push_back(e);
     }
+    vc_mark("concatenate");
     if (out.cand.empty()) out.cand.assign(16, 0.f);
     out.keys = entries.size();
     // ---- second level. The kd search (kd_find) reaches leaf l from query p exactly when, for every ancestor whose split
@@ -270,36 +296,50 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
         std::vector<XEntry> xent; xent.reserve(xkeys.size());
         out.xcand.clear();
         struct XC { double mn, mx; int v; bool always; };
-        std::vector<XC> poss;
-        for (uint64_t key : xkeys) {
-            const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
-            if (cls < 0 || cls >= ncls) continue;
-            const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
-            const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
-            const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
-            poss.clear(); double Rx = 1e300;
-            for (int v : by_class[cls]) {
-                bool possible = true, always = true;
-                for (int k = 0; k < 3 && possible; ++k) {
-                    const double lo = klo[3 * (size_t)v + k], hi = khi[3 * (size_t)v + k];
-                    if (bhi[k] - lo < -w - margin || blo[k] - hi > w + margin) possible = false;
-                    if (!(blo[k] - lo >= -w + margin && bhi[k] - hi <= w - margin)) always = false;
+        // independent per pair as well: all host threads, results concatenated in key order (2.8 of archway's remaining 3.9 s single-threaded)
+        const size_t nx = xkeys.size();
+        std::vector<std::vector<int>> xlists(nx); std::vector<char> xvalid(nx, 0);
+#pragma omp parallel
+        {
+            std::vector<XC> poss;
+#pragma omp for schedule(dynamic, 16)
+            for (long long xi = 0; xi < (long long)nx; ++xi) {
+                const uint64_t key = xkeys[(size_t)xi];
+                const int cell = (int)(key >> 32), cls = (int)(uint32_t)key;
+                if (cls < 0 || cls >= ncls) continue;
+                xvalid[(size_t)xi] = 1;
+                const int x = cell % out.nx, y = (cell / out.nx) % out.ny, z = cell / (out.nx * out.ny);
+                const double blo[3] = { out.ox + x * (double)h - margin, out.oy + y * (double)h - margin, out.oz + z * (double)h - margin };
+                const double bhi[3] = { blo[0] + h + 2 * margin, blo[1] + h + 2 * margin, blo[2] + h + 2 * margin };
+                poss.clear(); double Rx = 1e300;
+                for (int v : by_class[cls]) {
+                    bool possible = true, always = true;
+                    for (int k = 0; k < 3 && possible; ++k) {
+                        const double lo = klo[3 * (size_t)v + k], hi = khi[3 * (size_t)v + k];
+                        if (bhi[k] - lo < -w - margin || blo[k] - hi > w + margin) possible = false;
+                        if (!(blo[k] - lo >= -w + margin && bhi[k] - hi <= w - margin)) always = false;
+                    }
+                    if (!possible) continue;
+                    double mn2 = 0, mx2 = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        const double q = vol[v].pos[k];
+                        const double dmin = std::max(0.0, std::max(blo[k] - q, q - bhi[k])), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
+                        mn2 += dmin * dmin; mx2 += dmax * dmax;
+                    }
+                    XC c{ std::sqrt(mn2), std::sqrt(mx2), v, always };
+                    if (always) Rx = std::min(Rx, c.mx);
+                    poss.push_back(c);
                 }
-                if (!possible) continue;
-                double mn2 = 0, mx2 = 0;
-                for (int k = 0; k < 3; ++k) {
-                    const double q = vol[v].pos[k];
-                    const double dmin = std::max(0.0, std::max(blo[k] - q, q - bhi[k])), dmax = std::max(std::fabs(q - blo[k]), std::fabs(q - bhi[k]));
-                    mn2 += dmin * dmin; mx2 += dmax * dmax;
-                }
-                XC c{ std::sqrt(mn2), std::sqrt(mx2), v, always };
-                if (always) Rx = std::min(Rx, c.mx);
-                poss.push_back(c);
+                const double lim = Rx < 1e299 ? Rx * (1.0 + 1e-4) + 1e-6 * scale : 1e300;
+                for (const XC& c : poss) if (c.mn <= lim) xlists[(size_t)xi].push_back(c.v);
             }
-            const double lim = Rx < 1e299 ? Rx * (1.0 + 1e-4) + 1e-6 * scale : 1e300;
-            XEntry e{ cell, cls, (int)(out.xcand.size() / 12), 0 };
-            for (const XC& c : poss) if (c.mn <= lim) {
-                const int v = c.v; float wv; memcpy(&wv, &v, 4);
+        }
+        for (size_t xi = 0; xi < nx; ++xi) {
+            if (!xvalid[xi]) continue;
+            const uint64_t key = xkeys[xi];
+            XEntry e{ (int)(key >> 32), (int)(uint32_t)key, (int)(out.xcand.size() / 12), 0 };
+            for (int v : xlists[xi]) {
+                float wv; memcpy(&wv, &v, 4);
                 const float rec[12] = { vol[v].pos[0], vol[v].pos[1], vol[v].pos[2], wv, klo[3 * (size_t)v], klo[3 * (size_t)v + 1], klo[3 * (size_t)v + 2], khi[3 * (size_t)v],
                                         khi[3 * (size_t)v + 1], khi[3 * (size_t)v + 2], 0.f, 0.f };
                 out.xcand.insert(out.xcand.end(), rec, rec + 12); ++e.n;
@@ -318,6 +358,7 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
             out.xtable[4 * (size_t)hs] = e.cell; out.xtable[4 * (size_t)hs + 1] = e.cls; out.xtable[4 * (size_t)hs + 2] = e.start; out.xtable[4 * (size_t)hs + 3] = e.n;
         }
     }
+    vc_mark("second level");
     double fill = 3.0; if (const char* e = getenv("RLPT_VFILL")) fill = std::max(1.1, atof(e));
     size_t slots = 8; while ((double)slots < fill * (double)entries.size() + 2) slots <<= 1;
     out.table.assign(4 * slots, -1);
@@ -327,6 +368,7 @@ void host_build_vcells(const float* sv, const int* sclass, int ns, const std::ve
         while (out.table[4 * (size_t)hs] >= 0) hs = (hs + 1) & mask;
         out.table[4 * (size_t)hs] = e.cell; out.table[4 * (size_t)hs + 1] = e.cls; out.table[4 * (size_t)hs + 2] = e.start; out.table[4 * (size_t)hs + 3] = e.n4;
     }
+    vc_mark("hash table");
 }
 
 

@@ -40,7 +40,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, 
 # every symbol include/rlpt.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
     "rlpt_last_error", "rlpt_version", "rlpt_ctx_create", "rlpt_ctx_destroy", "rlpt_sync", "rlpt_stream", "rlpt_config_default", "rlpt_config_set",
-    "rlpt_config_get", "rlpt_set_allreduce", "rlpt_scene_upload", "rlpt_scene_info", "rlpt_scene_bvh_download", "rlpt_scene_bvh4_info", "rlpt_scene_bvh4_download", "rlpt_neuralq_set_hyper", "rlpt_set_max_direction", "rlpt_camera_set", "rlpt_closest_hit",
+    "rlpt_config_get", "rlpt_set_allreduce", "rlpt_scene_upload", "rlpt_scene_info", "rlpt_scene_bvh_download", "rlpt_scene_bvh4_info", "rlpt_scene_bvh4_download", "rlpt_neuralq_set_hyper", "rlpt_set_max_direction", "rlpt_radiance_map_build_seconds", "rlpt_camera_set", "rlpt_closest_hit",
     "rlpt_closest_hit_device", "rlpt_radiance_map_build", "rlpt_radiance_map_info", "rlpt_radiance_map_tree", "rlpt_radiance_map_find_closest",
     "rlpt_radiance_map_set_q", "rlpt_radiance_map_update_distributions", "rlpt_radiance_map_download", "rlpt_radiance_map_delta_download",
     "rlpt_radiance_map_save_q", "rlpt_radiance_map_load_q", "rlpt_render_default", "rlpt_render_sarsa", "rlpt_sarsa_trace", "rlpt_sarsa_merge",
@@ -260,6 +260,11 @@ class Context:
 
     def neuralq_set_hyper(self, learning_rate=1e-3, epsilon_start=0.05, epsilon_decay=0.01, epsilon_min=0.05):
         self._ck(self.L.rlpt_neuralq_set_hyper(self.h, ctypes.c_float(learning_rate), ctypes.c_float(epsilon_start), ctypes.c_float(epsilon_decay), ctypes.c_float(epsilon_min)))
+
+    def radiance_map_build_seconds(self):
+        v = (ctypes.c_double * 4)()
+        self._ck(self.L.rlpt_radiance_map_build_seconds(self.h, v))
+        return dict(volumes_and_kd_tree_host=v[0], candidate_cells_host=v[1], upload_and_first_cdf_device=v[2], total=v[3])
 
     def set_max_direction(self, on):
         self._ck(self.L.rlpt_set_max_direction(self.h, int(bool(on))))
