@@ -77,146 +77,334 @@ __host__ __device__ __forceinline__ size_t operand_offset(int row, int k, int k_
     return (size_t)(row >> 3) * ((size_t)k_pad * 16) + (size_t)(k >> 3) * 128 + (size_t)(row & 7) * 16 + (size_t)(k & 7) * 2;
 }
 
+// Packed weights of a layer as k_dqn_forward streams them (B operands): the layer's output rows are cut into N parts (layer 2: rows [0,160) and
+// [160,304), so that the epilogue of the first part runs under the MMAs of the second; layers 3 and 4: one part), each part into K chunks of 64
+// inputs; a chunk is one contiguous block = one bulk copy = the B operand of kw / 16 MMAs with N = the part's rows (large N: an SS-mode MMA re-reads
+// its 4 KB of A from shared memory, so N = 64 pieces are shared-memory-bound and issue-bound). Inside a chunk: canonical K-major no-swizzle form,
+// 8x8 core matrices of 128 bytes, K-adjacent ones 128 bytes apart (LBO), 8-row groups kw * 16 bytes apart (SBO).
+#ifndef RLPT_DQN_KC
+#define RLPT_DQN_KC 64
+#endif
+#ifndef RLPT_DQN_STAGES
+#define RLPT_DQN_STAGES 3
+#endif
+#ifndef RLPT_DQN_PIECES
+#define RLPT_DQN_PIECES 1
+#endif
+constexpr int DQ_KC = RLPT_DQN_KC;                                          // inputs per weight chunk
+constexpr int DQ_L2_SPLIT = 160;                                           // layer 2's first N part
+__host__ __device__ __forceinline__ size_t wpack_offset(int n_split, int row, int k, int n_pad, int k_pad) {
+    const int n0 = (n_split > 0 && row >= n_split) ? n_split : 0, rows = n_split > 0 ? (row >= n_split ? n_pad - n_split : n_split) : n_pad;
+    const int kc = k / DQ_KC, kw = min(DQ_KC, k_pad - kc * DQ_KC), r = row - n0, kk = k - kc * DQ_KC;
+    return (size_t)n0 * k_pad * 2 + (size_t)rows * DQ_KC * 2 * kc + (size_t)(r >> 3) * ((size_t)kw * 16) + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+}
+
 // ------------------------------------------------------------------------------------------------ forward kernel
+constexpr int DQ_STAGES = RLPT_DQN_STAGES;
+constexpr uint32_t DQ_STAGE_BYTES = DQ_N3 * DQ_KC * 2;                     // largest chunk: layer 3, 208 rows x 64 inputs
+static_assert(DQ_L2_SPLIT * DQ_KC * 2 <= DQ_STAGE_BYTES && DQ_N4 * DQ_KC * 2 <= DQ_STAGE_BYTES, "chunk fits a stage");
 constexpr uint32_t SM_A1 = 0;                                             // 128 x 208 bf16: layer-2 A, later layer-4 A
 constexpr uint32_t SM_A2 = SM_A1 + DQ_TILE * DQ_K2 * 2;                   // 128 x 304 bf16: layer-3 A
-constexpr uint32_t SM_B0 = SM_A2 + DQ_TILE * DQ_K3 * 2;                   // 64 x 304 bf16 (largest chunk)
-constexpr uint32_t SM_B1 = SM_B0 + DQ_CHUNK * DQ_K3 * 2;
-constexpr uint32_t SM_C1 = SM_B1 + DQ_CHUNK * DQ_K3 * 2;                  // fp32 constants
+constexpr uint32_t SM_B0 = SM_A2 + DQ_TILE * DQ_K3 * 2;                   // DQ_STAGES weight chunks
+constexpr uint32_t SM_C1 = SM_B0 + DQ_STAGES * DQ_STAGE_BYTES;            // fp32 constants
 constexpr uint32_t SM_M1 = SM_C1 + DQ_K2 * 4;
 constexpr uint32_t SM_BIAS2 = SM_M1 + DQ_K2 * 3 * 4;
 constexpr uint32_t SM_BIAS3 = SM_BIAS2 + DQ_N2 * 4;
 constexpr uint32_t SM_BIAS4 = SM_BIAS3 + DQ_N3 * 4;
-constexpr uint32_t SM_BAR = SM_BIAS4 + DQ_N4 * 4;                         // 5 mbarriers + the TMEM base address
-constexpr uint32_t SM_TOTAL = SM_BAR + 64;
+constexpr uint32_t SM_BAR = SM_BIAS4 + DQ_N4 * 4;                         // 8 mbarriers + the TMEM base address
+constexpr uint32_t SM_TABLE = SM_BAR + 160;                                // chunk table (17 x 40 bytes)
+constexpr uint32_t SM_TOTAL = SM_TABLE + 17 * 40;
 static_assert(SM_TOTAL <= 227 * 1024, "shared-memory budget");
-static_assert(SM_BAR % 8 == 0, "mbarrier alignment");
+static_assert(SM_BAR % 8 == 0 && SM_B0 % 128 == 0 && DQ_STAGE_BYTES % 128 == 0, "alignment");
 
-struct LayerPipe {            // bookkeeping of the elected thread: which buffer a chunk uses and how often each barrier fired
-    uint32_t chunk = 0; uint32_t full_uses[2] = { 0, 0 }, free_uses[2] = { 0, 0 };
-};
+#ifndef RLPT_DQN_STAGGER
+#define RLPT_DQN_STAGGER 0         // cycles of start-up delay per CTA (blockIdx % 8): tried 3000 -- 215 -> 236 us per full-frame forward
+#endif
+#ifndef RLPT_DQN_EPI_GROUPS
+#define RLPT_DQN_EPI_GROUPS 4
+#endif
+// Warp roles (round 2): DQ_EPI_GROUPS warpgroups of epilogue / layer-1 threads (thread t works on ray t & 127; TMEM lane quarter = warp & 3, the
+// warpgroups take 32-column blocks in turn), then one MMA warp and one copy warp (one lane each). A tile's weights are a fixed stream of
+// 17 chunks (wpack_offset): layer 2 = 2 N parts x 4 K chunks, layer 3 = 5 K chunks, layer 4 = 4 K chunks, described by a table in shared memory.
+// The copy lane runs free of the layer structure: it refills a stage as soon as the MMAs that read it have completed (three stages; the next layer's
+// and the next tile's first chunks included -- weights do not depend on activations). The MMA lane commits every N part to its own mbarrier, so
+// layer 2's first part is converted (TMEM -> +bias, ReLU -> bf16 A operand of layer 3) under the MMAs of its second part. (One lane doing both, with
+// the chunk geometry recomputed per chunk, spent ~1000 cycles of dependent scalar instructions per chunk -- three times the chunk's MMA time.)
+constexpr int DQ_NKC2 = (DQ_K2 + DQ_KC - 1) / DQ_KC, DQ_NKC3 = (DQ_K3 + DQ_KC - 1) / DQ_KC, DQ_NKC4 = (DQ_K4 + DQ_KC - 1) / DQ_KC;       // K chunks per layer (4, 5, 4 at 64 inputs per chunk)
+constexpr int DQ_EPI_GROUPS = RLPT_DQN_EPI_GROUPS, DQ_EPI_THREADS = 128 * DQ_EPI_GROUPS, DQ_CHUNKS_PER_TILE = 2 * DQ_NKC2 + DQ_NKC3 + DQ_NKC4;
+constexpr int DQ_COMPUTE_THREADS = DQ_EPI_THREADS + 32, DQ_THREADS = DQ_EPI_THREADS + 64;        // epilogue warps + MMA warp (named barrier 1) + copy warp
+#ifdef RLPT_DQN_TRACE           // debug build: phase timestamps of CTA 0's second tile (epilogue thread 0 and the issuer lane), printed at kernel end
+#define DQ_TR_DECL long long tr_[24]; int ntr_ = 0; const bool tr_on_ = blockIdx.x == 0;
+#define DQ_TR(it) do { if (tr_on_ && (it) == 1 && ntr_ < 24) tr_[ntr_++] = clock64(); } while (0)
+#define DQ_TR_PRINT(who) do { if (tr_on_ && ntr_ > 1) { printf("%s:", who); for (int i_ = 1; i_ < ntr_; ++i_) printf(" %lld", tr_[i_] - tr_[0]); printf("\n"); } } while (0)
+#else
+#define DQ_TR_DECL
+#define DQ_TR(it) do {} while (0)
+#define DQ_TR_PRINT(who) do {} while (0)
+#endif
 
-// One dense layer on the tensor cores: D[128 x n_pad] = A[128 x k_pad] * W[n_pad x k_pad]^T into TMEM columns [tmem_col, +n_pad).
-// Called by thread 0 only. Chunk c+1 is copied while chunk c multiplies.
-__device__ __forceinline__ void issue_layer(LayerPipe& lp, uint8_t* smem, uint64_t* b_full, uint64_t* b_free, uint64_t* layer_done,
-                                            uint32_t a_off, int k_pad, const __nv_bfloat16* wp, int n_pad, uint32_t tmem_base, uint32_t tmem_col) {
-    const int n_chunks = (n_pad + DQ_CHUNK - 1) / DQ_CHUNK;
-    auto copy = [&](int c) {
-        const uint32_t g = lp.chunk + (uint32_t)c, buf = g & 1u;
-        if (lp.free_uses[buf]) mbar_wait(&b_free[buf], (lp.free_uses[buf] - 1u) & 1u);       // the MMAs that read this buffer last have finished
-        const int rows = min(DQ_CHUNK, n_pad - c * DQ_CHUNK);
-        const uint32_t bytes = (uint32_t)rows * (uint32_t)k_pad * 2u;
-        mbar_expect_tx(&b_full[buf], bytes);
-        bulk_copy_g2s(smem + (buf ? SM_B1 : SM_B0), reinterpret_cast<const uint8_t*>(wp) + (size_t)c * DQ_CHUNK * k_pad * 2, bytes, &b_full[buf]);
-    };
-    copy(0);
-    for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t g = lp.chunk + (uint32_t)c, buf = g & 1u;
-        if (c + 1 < n_chunks) copy(c + 1);
-        mbar_wait(&b_full[buf], lp.full_uses[buf] & 1u); lp.full_uses[buf]++;
-        tc_fence_after();
-        const int rows = min(DQ_CHUNK, n_pad - c * DQ_CHUNK);
-        const uint32_t idesc = idesc_bf16(DQ_TILE, rows);
-        const uint32_t a_addr = smem_u32(smem + a_off), b_addr = smem_u32(smem + (buf ? SM_B1 : SM_B0));
-        const uint32_t d_addr = tmem_base + tmem_col + (uint32_t)c * DQ_CHUNK;
-        for (int k = 0; k < k_pad / 16; ++k)
-            umma_bf16(d_addr, smem_desc(a_addr + (uint32_t)k * 256u, 128u, (uint32_t)k_pad * 16u), smem_desc(b_addr + (uint32_t)k * 256u, 128u, (uint32_t)k_pad * 16u), idesc, k > 0);
-        umma_commit(&b_free[buf]); lp.free_uses[buf]++;
+struct ChunkInfo { const __nv_bfloat16* src; int rows, kw, kc, last, part; uint32_t a_off, a_kpad, tmem_col; };
+__device__ __forceinline__ ChunkInfo chunk_info(const DqnFwdParams& p, int s) {          // s = position in the tile's stream, 0..16
+    ChunkInfo ci;
+    if (s < 2 * DQ_NKC2) {
+        const int part = s >= DQ_NKC2 ? 1 : 0, kc = s - part * DQ_NKC2, n0 = part ? DQ_L2_SPLIT : 0;
+        ci.rows = part ? DQ_N2 - DQ_L2_SPLIT : DQ_L2_SPLIT; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K2 - kc * DQ_KC); ci.last = kc == DQ_NKC2 - 1; ci.part = part;
+        ci.src = p.w2p + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
+    } else if (s < 2 * DQ_NKC2 + DQ_NKC3) {
+        const int kc = s - 2 * DQ_NKC2;
+        ci.rows = DQ_N3; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K3 - kc * DQ_KC); ci.last = kc == DQ_NKC3 - 1; ci.part = 0;
+        ci.src = p.w3p + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
+    } else {
+        const int kc = s - 2 * DQ_NKC2 - DQ_NKC3;
+        ci.rows = DQ_N4; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K4 - kc * DQ_KC); ci.last = kc == DQ_NKC4 - 1; ci.part = 0;
+        ci.src = p.w4p + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
     }
-    umma_commit(layer_done);
-    lp.chunk += (uint32_t)n_chunks;
+    return ci;
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the MMA with its two shared-memory descriptors given as (low, high) words: the K step only moves the start address (low word, 16-byte units)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// chunk table entry (shared memory, built once per CTA from chunk_info)
+struct ChunkRow { uint32_t src_lo, src_hi, bytes, a_lo, a_hi, b_hi, idesc, tmem_col, n_mma, flags; };        // flags: bit 0 = first chunk of its accumulator, bit 1 = last, bit 2 = N part
+constexpr uint32_t SM_TABLE_BYTES = DQ_CHUNKS_PER_TILE * sizeof(ChunkRow);
 
-// Epilogue of a hidden layer: TMEM -> (+bias, ReLU) -> bf16 A operand of the next layer; optionally also kept in HBM
-// feature-major for the backward pass. Thread t owns TMEM lane t = ray t of the tile.
-__device__ __forceinline__ void hidden_epilogue(uint8_t* smem, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad, const float* bias, uint32_t a_next_off, int k_pad_next,
-                                                int row, __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
-    for (int c0 = 0; c0 < n_pad; c0 += 16) {
-        uint32_t r[16]; tmem_ld16(tmem_lane_addr + tmem_col + (uint32_t)c0, r);
-        __nv_bfloat162 pk[8];
+// 32 (or 16) accumulator columns of one ray: + bias, ReLU, bf16; written as the next layer's A operand and optionally kept feature-major in HBM
+template <int NC>
+__device__ __forceinline__ void hidden_block(uint8_t* smem, const uint32_t* r, int c0, const float* bias, uint32_t a_next_off, int k_pad_next, int row,
+                                             __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float a = fmaxf(__uint_as_float(r[2 * j]) + bias[c0 + 2 * j], 0.f), b = fmaxf(__uint_as_float(r[2 * j + 1]) + bias[c0 + 2 * j + 1], 0.f);
+    for (int q = 0; q < NC / 8; ++q) {
+        __nv_bfloat162 pk[4];
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q), b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4);       // (16-byte aligned: c0 is a multiple of 16)
+        const float bb[8] = { b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = fmaxf(__uint_as_float(r[8 * q + 2 * j]) + bb[2 * j], 0.f), b = fmaxf(__uint_as_float(r[8 * q + 2 * j + 1]) + bb[2 * j + 1], 0.f);
             pk[j] = __floats2bfloat162_rn(a, b);
         }
-        *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[0]);
-        *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0 + 8, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[4]);
+        *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0 + 8 * q, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[0]);
         if (keep && ray_valid) {
+            __nv_bfloat16* kp = keep + (size_t)(c0 + 8 * q) * keep_stride + ray;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { keep[(size_t)(c0 + 2 * j) * keep_stride + ray] = pk[j].x; keep[(size_t)(c0 + 2 * j + 1) * keep_stride + ray] = pk[j].y; }
+            for (int j = 0; j < 4; ++j) { kp[0] = pk[j].x; kp[keep_stride] = pk[j].y; kp += 2 * (size_t)keep_stride; }
+        }
+    }
+}
+// Epilogue of a hidden layer for one epilogue thread: its warpgroup's 32-column blocks (alternating with the other warpgroup's), each as soon
+// as the N part that holds it is complete (n_split: first column of the second part, 0 = one part). Bit c of done_par = parity of the
+// completions of part_done[c] before this layer.
+__device__ __forceinline__ void hidden_epilogue(uint8_t* smem, uint64_t* part_done, uint32_t done_par, int n_split, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad,
+                                                const float* bias, uint32_t a_next_off, int k_pad_next, int row, int half, __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
+    const int n_blocks = (n_pad + 31) / 32;
+    for (int b = half; b < n_blocks; b += DQ_EPI_GROUPS) {
+        const int c0 = 32 * b, c = (n_split > 0 && c0 >= n_split) ? 1 : 0;
+        mbar_wait(&part_done[c], (done_par >> c) & 1u); tc_fence_after();
+        uint32_t r[32];
+        if (c0 + 32 <= n_pad) {
+            tmem_ld32_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait();
+            hidden_block<32>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid);
+        } else {
+            tmem_ld16_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait();
+            hidden_block<16>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid);
         }
     }
 }
 
-__global__ void __launch_bounds__(DQ_TILE, 1) k_dqn_forward(const __grid_constant__ DqnFwdParams p) {
+__global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_constant__ DqnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    float* s_c1 = reinterpret_cast<float*>(smem + SM_C1); float* s_m1 = reinterpret_cast<float*>(smem + SM_M1);
+    const float4* s_l1c = reinterpret_cast<const float4*>(smem + SM_C1); float4* s_l1 = reinterpret_cast<float4*>(smem + SM_C1);
     float* s_b2 = reinterpret_cast<float*>(smem + SM_BIAS2); float* s_b3 = reinterpret_cast<float*>(smem + SM_BIAS3); float* s_b4 = reinterpret_cast<float*>(smem + SM_BIAS4);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    uint64_t *b_full = bars, *b_free = bars + 2, *layer_done = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t *b_full = bars, *b_free = bars + DQ_STAGES, *part_done = bars + 2 * DQ_STAGES;       // [3], [3], [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DQ_STAGES + 2);
     const int t = threadIdx.x, warp = t >> 5;
 
-    for (int i = t; i < DQ_K2; i += DQ_TILE) { s_c1[i] = i < DQ_H1 ? p.c1[i] : 0.f; for (int d = 0; d < 3; ++d) s_m1[3 * i + d] = i < DQ_H1 ? p.m1[3 * i + d] : 0.f; }
-    for (int i = t; i < DQ_N2; i += DQ_TILE) s_b2[i] = i < DQ_H2 ? p.b2[i] : 0.f;
-    for (int i = t; i < DQ_N3; i += DQ_TILE) s_b3[i] = i < DQ_H3 ? p.b3[i] : 0.f;
-    for (int i = t; i < DQ_N4; i += DQ_TILE) s_b4[i] = i < DQ_OUT ? p.b4[i] : 0.f;
-    if (t == 0) { mbar_init(&b_full[0], 1); mbar_init(&b_full[1], 1); mbar_init(&b_free[0], 1); mbar_init(&b_free[1], 1); mbar_init(layer_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    // layer-1 constants as one float4 (c1, M1 row) per output: the shared-memory pipe takes one instruction per cycle, broadcast or not
+    for (int i = t; i < DQ_K2; i += DQ_THREADS) s_l1[i] = i < DQ_H1 ? make_float4(p.c1[i], p.m1[3 * i], p.m1[3 * i + 1], p.m1[3 * i + 2]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < DQ_N2; i += DQ_THREADS) s_b2[i] = i < DQ_H2 ? p.b2[i] : 0.f;
+    for (int i = t; i < DQ_N3; i += DQ_THREADS) s_b3[i] = i < DQ_H3 ? p.b3[i] : 0.f;
+    for (int i = t; i < DQ_N4; i += DQ_THREADS) s_b4[i] = i < DQ_OUT ? p.b4[i] : 0.f;
+    ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
+    if (t < DQ_CHUNKS_PER_TILE) {
+        const ChunkInfo ci = chunk_info(p, t);
+        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.kc * (DQ_KC * 16u);
+        ChunkRow cr;
+        cr.src_lo = (uint32_t)reinterpret_cast<uint64_t>(ci.src); cr.src_hi = (uint32_t)(reinterpret_cast<uint64_t>(ci.src) >> 32); cr.bytes = (uint32_t)ci.rows * (uint32_t)ci.kw * 2u;
+        cr.a_lo = ((a_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); cr.a_hi = ((ci.a_kpad * 16u) >> 4) | (1u << 14); cr.b_hi = (((uint32_t)ci.kw * 16u) >> 4) | (1u << 14);
+        cr.idesc = idesc_bf16(DQ_TILE, ci.rows); cr.tmem_col = ci.tmem_col; cr.n_mma = (uint32_t)ci.kw / 16u;
+        cr.flags = (ci.kc == 0 ? 1u : 0u) | (ci.last ? 2u : 0u) | ((uint32_t)ci.part << 2);
+        table[t] = cr;
+    }
+    if (t == 0) { for (int i = 0; i < 2 * DQ_STAGES + 2; ++i) mbar_init(&bars[i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's 32 lanes
+    const uint32_t b_lo0 = ((smem_u32(smem + SM_B0) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);       // B descriptor, low word, stage 0
+    auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(DQ_COMPUTE_THREADS) : "memory"); };       // epilogue warps + MMA warp
 
-    LayerPipe lp; uint32_t done_uses = 0;
     const int n_rays1 = p.n_ptr ? min(*p.n_ptr, p.n) : p.n;
     const int n_tiles1 = (n_rays1 + DQ_TILE - 1) / DQ_TILE, n_tiles = n_tiles1 + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
-    for (int tile_all = blockIdx.x; tile_all < n_tiles; tile_all += gridDim.x) {
-        // the second batch (next states of a training step: Q only) rides in the same launch, its tiles after the first batch's
-        const bool second = tile_all >= n_tiles1;
-        const int tile = second ? tile_all - n_tiles1 : tile_all, n_rays = second ? p.n2 : n_rays1;
-        const float4* __restrict__ pos = second ? p.pos2 : p.pos;
-        float* __restrict__ q_out = second ? p.q2 : p.q; const int q_stride = second ? p.q_stride2 : p.q_stride;
-        __nv_bfloat16* const k1 = second ? nullptr : p.h1t; __nv_bfloat16* const k2 = second ? nullptr : p.h2t; __nv_bfloat16* const k3 = second ? nullptr : p.h3t;
-        const int ray = tile * DQ_TILE + t; const bool valid = ray < n_rays;
-        // ---- layer 1 (fp32): h1 = relu(c1 - M1 x), 8 outputs per 16-byte store into the A operand
-        float4 x = valid ? pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j0 = 0; j0 < DQ_K2; j0 += 8) {
-            __nv_bfloat162 pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int a = j0 + 2 * j, b = a + 1;
-                float ha = fmaxf(s_c1[a] - (s_m1[3 * a] * x.x + s_m1[3 * a + 1] * x.y + s_m1[3 * a + 2] * x.z), 0.f);
-                float hb = fmaxf(s_c1[b] - (s_m1[3 * b] * x.x + s_m1[3 * b + 1] * x.y + s_m1[3 * b + 2] * x.z), 0.f);
-                pk[j] = __floats2bfloat162_rn(ha, hb);
-            }
-            *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(t, j0, DQ_K2)) = *reinterpret_cast<uint4*>(&pk[0]);
-            if (k1 && valid) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { k1[(size_t)(j0 + 2 * j) * p.h_stride + ray] = pk[j].x; k1[(size_t)(j0 + 2 * j + 1) * p.h_stride + ray] = pk[j].y; }
+    const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == DQ_EPI_THREADS / 32 + 1) {
+        // ---- copy warp (one lane): the weight stream, DQ_STAGES - 1 chunks ahead of the MMAs at most; it takes no part in the layer barriers
+        if ((t & 31) == 0) {
+            const uint32_t total = (uint32_t)my_tiles * DQ_CHUNKS_PER_TILE;
+            uint32_t stage = 0, par = 1, srow = 0;                          // par: parity to wait for on b_free (first pass: the stages have never been used)
+            for (uint32_t g = 0; g < total; ++g) {
+                if (g >= DQ_STAGES) mbar_wait(&b_free[stage], par);
+                const ChunkRow& cr = table[srow];
+                const uint32_t bytes = cr.bytes;
+                mbar_expect_tx(&b_full[stage], bytes);
+                bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES, reinterpret_cast<const void*>(((uint64_t)cr.src_hi << 32) | cr.src_lo), bytes, &b_full[stage]);
+                if (++srow == DQ_CHUNKS_PER_TILE) srow = 0;
+                if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
             }
         }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- layer 2: 200 -> 300
-        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K2, p.w2p, DQ_N2, tmem_base, 0); }
-        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
-        hidden_epilogue(smem, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, t, k2, p.h_stride, ray, valid);
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- layer 3: 300 -> 200
-        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A2, DQ_K3, p.w3p, DQ_N3, tmem_base, DQ_N2); }
-        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
-        hidden_epilogue(smem, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, t, k3, p.h_stride, ray, valid);
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        // ---- layer 4: 200 -> 144, ReLU on the output as well (N/dq_network.cu:17)
-        if (t == 0) { tc_fence_after(); issue_layer(lp, smem, b_full, b_free, layer_done, SM_A1, DQ_K4, p.w4p, DQ_N4, tmem_base, 0); }
-        mbar_wait(layer_done, done_uses & 1u); done_uses++; tc_fence_after();
-        for (int c0 = 0; c0 < DQ_N4; c0 += 16) {
-            uint32_t r[16]; tmem_ld16(tmem_lane + (uint32_t)c0, r);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) q_out[(size_t)(c0 + j) * q_stride + ray] = fmaxf(__uint_as_float(r[j]) + s_b4[c0 + j], 0.f);
+        __syncwarp();
+    } else if (warp == DQ_EPI_THREADS / 32) {
+        // ---- MMA warp: lane 0 works, the warp reconverges before every barrier of the compute group
+        const bool lead = (t & 31) == 0;
+        DQ_TR_DECL
+        uint32_t stage = 0, par = 0, srow = 0;
+        auto run = [&](int n) {
+            for (int i = 0; i < n; ++i) {
+                mbar_wait(&b_full[stage], par);
+                tc_fence_after();
+                const ChunkRow cr = table[srow];
+                uint32_t a_lo = cr.a_lo, b_lo = b_lo0 + stage * (DQ_STAGE_BYTES >> 4);
+                const uint32_t d_addr = tmem_base + cr.tmem_col, first = cr.flags & 1u;
+                for (uint32_t k = 0; k < cr.n_mma; ++k, a_lo += 16u, b_lo += 16u)
+                    umma_bf16_lohi(d_addr, a_lo, cr.a_hi, b_lo, cr.b_hi, cr.idesc, (first ^ 1u) | k);
+                umma_commit(&b_free[stage]);
+                if (cr.flags & 2u) umma_commit(&part_done[(cr.flags >> 2) & 1u]);
+                if (++srow == DQ_CHUNKS_PER_TILE) srow = 0;
+                if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
             }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            if (lead) DQ_TR(it);
+            compute_sync();                                                // layer-1 activations are in A1, the previous tile's accumulators have been read
+            if (lead) { DQ_TR(it); tc_fence_after(); run(2 * DQ_NKC2); DQ_TR(it); }
+            __syncwarp(); compute_sync();                                  // A2 written
+            if (lead) { DQ_TR(it); tc_fence_after(); run(DQ_NKC3); DQ_TR(it); }
+            __syncwarp(); compute_sync();                                  // A1 (layer-4 operand) written
+            if (lead) { DQ_TR(it); tc_fence_after(); run(DQ_NKC4); DQ_TR(it); }
+            __syncwarp();
         }
-        tc_fence_before(); __syncthreads();       // TMEM and A1 are reused by the next tile
+        if (lead) DQ_TR_PRINT("issuer  [sync1 | L2 issued | sync2 | L3 issued | sync3 | L4 issued]");
+        __syncwarp();
+    } else {
+        // ---- epilogue warps
+        const int row = t & (DQ_TILE - 1), half = t >> 7;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);        // this warp's quarter of the 128 TMEM lanes
+        uint32_t done_par = 0;                                                  // bit c: parity of part_done[c]'s completed phases
+        float4 x_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        // CTAs that run many tiles start staggered: in lockstep all 148 stream the same weight chunk from L2 and write their Q tiles to HBM at the
+        // same moment, and each of those bursts ran at the L2 / HBM limit while the average traffic is a tenth of it
+        if (RLPT_DQN_STAGGER && my_tiles >= 4) { const long long t0 = clock64(), d = (long long)(blockIdx.x % 8u) * RLPT_DQN_STAGGER; while (clock64() - t0 < d) { } }
+        DQ_TR_DECL
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile_all = (int)blockIdx.x + it * (int)gridDim.x;
+            // the second batch (next states of a training step: Q only) rides in the same launch, its tiles after the first batch's
+            const bool second = tile_all >= n_tiles1;
+            const int tile = second ? tile_all - n_tiles1 : tile_all, n_rays = second ? p.n2 : n_rays1;
+            const float4* __restrict__ pos = second ? p.pos2 : p.pos;
+            float* __restrict__ q_out = second ? p.q2 : p.q; const int q_stride = second ? p.q_stride2 : p.q_stride;
+            __nv_bfloat16* const k1 = second ? nullptr : p.h1t; __nv_bfloat16* const k2 = second ? nullptr : p.h2t; __nv_bfloat16* const k3 = second ? nullptr : p.h3t;
+            const int ray = tile * DQ_TILE + row; const bool valid = ray < n_rays;
+            if (t == 0) DQ_TR(it);
+            // ---- layer 1 (fp32): h1 = relu(c1 - M1 x), 8 outputs per 16-byte store into the A operand; the warpgroups take the 26 groups of 8 in turn
+            const float4 x = it == 0 ? (valid ? pos[ray] : make_float4(0.f, 0.f, 0.f, 0.f)) : x_next;
+            {   // the next tile's position is fetched now: a DRAM round trip at the head of every tile was a tenth of the tile time
+                const int ta = tile_all + (int)gridDim.x;
+                if (ta < n_tiles) {
+                    const bool sec = ta >= n_tiles1; const int r2 = (sec ? ta - n_tiles1 : ta) * DQ_TILE + row;
+                    x_next = r2 < (sec ? p.n2 : n_rays1) ? (sec ? p.pos2 : p.pos)[r2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            for (int j0 = 8 * half; j0 < DQ_K2; j0 += 8 * DQ_EPI_GROUPS) {
+                __nv_bfloat162 pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int a = j0 + 2 * j, b = a + 1;
+                    const float4 ca = s_l1c[a], cb = s_l1c[b];
+                    float ha = fmaxf(ca.x - (ca.y * x.x + ca.z * x.y + ca.w * x.z), 0.f);
+                    float hb = fmaxf(cb.x - (cb.y * x.x + cb.z * x.y + cb.w * x.z), 0.f);
+                    pk[j] = __floats2bfloat162_rn(ha, hb);
+                }
+                *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(row, j0, DQ_K2)) = *reinterpret_cast<uint4*>(&pk[0]);
+                if (k1 && valid) {
+                    __nv_bfloat16* kp = k1 + (size_t)j0 * p.h_stride + ray;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { kp[0] = pk[j].x; kp[p.h_stride] = pk[j].y; kp += 2 * (size_t)p.h_stride; }
+                }
+            }
+            if (t == 0) DQ_TR(it);
+            fence_proxy_async(); tc_fence_before(); compute_sync();
+            if (t == 0) DQ_TR(it);
+            // ---- layer 2: 200 -> 300 (TMEM columns [0, 304), two N parts)
+#ifdef RLPT_DQN_TRACE
+            if (t == 0) { mbar_wait(&part_done[0], done_par & 1u); DQ_TR(it); }
+#endif
+            hidden_epilogue(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, row, half, k2, p.h_stride, ray, valid);
+            done_par ^= 3u;
+            if (t == 0) DQ_TR(it);
+            fence_proxy_async(); tc_fence_before(); compute_sync();
+            if (t == 0) DQ_TR(it);
+            // ---- layer 3: 300 -> 200 (columns [304, 512))
+#ifdef RLPT_DQN_TRACE
+            if (t == 0) { mbar_wait(&part_done[0], done_par & 1u); DQ_TR(it); }
+#endif
+            hidden_epilogue(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, row, half, k3, p.h_stride, ray, valid);
+            done_par ^= 1u;
+            if (t == 0) DQ_TR(it);
+            fence_proxy_async(); tc_fence_before(); compute_sync();
+            if (t == 0) DQ_TR(it);
+            // ---- layer 4: 200 -> 144 (columns [0, 144)), ReLU on the output as well (N/dq_network.cu:17)
+            mbar_wait(&part_done[0], done_par & 1u); tc_fence_after();     // (also: layer 4's MMAs have all read A1 before the next tile's layer 1 rewrites it)
+            done_par ^= 1u;
+            if (t == 0) DQ_TR(it);
+            for (int b = half; b < (DQ_N4 + 31) / 32; b += DQ_EPI_GROUPS) {
+                const int c0 = 32 * b;
+                uint32_t r[32];
+                if (c0 + 32 <= DQ_N4) { tmem_ld32_issue(tmem_lane + (uint32_t)c0, r); tmem_ld_wait(); } else { tmem_ld16_issue(tmem_lane + (uint32_t)c0, r); tmem_ld_wait(); }
+                const int nc = min(32, DQ_N4 - c0);
+                if (valid) {
+                    float* qp = q_out + (size_t)c0 * q_stride + ray;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) if (4 * j4 < nc) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(s_b4 + c0 + 4 * j4);
+                        qp[0] = fmaxf(__uint_as_float(r[4 * j4]) + b4.x, 0.f); qp[q_stride] = fmaxf(__uint_as_float(r[4 * j4 + 1]) + b4.y, 0.f);
+                        qp[2 * (size_t)q_stride] = fmaxf(__uint_as_float(r[4 * j4 + 2]) + b4.z, 0.f); qp[3 * (size_t)q_stride] = fmaxf(__uint_as_float(r[4 * j4 + 3]) + b4.w, 0.f);
+                        qp += 4 * (size_t)q_stride;
+                    }
+                }
+            }
+            tc_fence_before();                                              // (the next tile's first CTA barrier orders these TMEM reads before its MMAs)
+            if (t == 0) DQ_TR(it);
+        }
+        if (t == 0) DQ_TR_PRINT("epilogue [L1 done | sync1 | L2 part0 ready | E2 done | sync2 | L3 ready | E3 done | sync3 | L4 ready | E4 done]");
     }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -229,18 +417,18 @@ int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
     if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
     int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
-    k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_TILE, SM_TOTAL, s>>>(p);
+    k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
     return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ operands from parameters
 // one thread per packed element: bf16 copy of W [n][k] (row-major fp32, n x k) into the canonical [n_pad][k_pad] operand, zero padding
-__global__ void k_pack_weights(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, __nv_bfloat16* __restrict__ out) {
+__global__ void k_pack_weights(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * k_pad) return;
     int row = i / k_pad, col = i % k_pad;
     float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + operand_offset(row, col, k_pad)) = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + wpack_offset(n_split, row, col, n_pad, k_pad)) = __float2bfloat16_rn(v);
 }
 // c1 = b1 + W1 v, M1[:, d] = sum_{i % 3 == d} W1[:, i]; one warp per output row, fp32 with pairwise lane sums
 __global__ void k_layer1_operands(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ v, int k_in, float* __restrict__ c1, float* __restrict__ m1) {
@@ -254,9 +442,9 @@ __global__ void k_layer1_operands(const float* __restrict__ w1, const float* __r
 
 int dqn_refresh_operands(DqnDev& d, cudaStream_t s) {
     k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);
-    k_pack_weights<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N2, DQ_K2, d.w2p);
-    k_pack_weights<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N3, DQ_K3, d.w3p);
-    k_pack_weights<<<(DQ_N4 * DQ_K4 + 255) / 256, 256, 0, s>>>(d.w[3], DQ_OUT, DQ_H3, DQ_N4, DQ_K4, d.w4p);
+    k_pack_weights<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N2, DQ_K2, DQ_L2_SPLIT, d.w2p);
+    k_pack_weights<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N3, DQ_K3, 0, d.w3p);
+    k_pack_weights<<<(DQ_N4 * DQ_K4 + 255) / 256, 256, 0, s>>>(d.w[3], DQ_OUT, DQ_H3, DQ_N4, DQ_K4, 0, d.w4p);
     return (int)cudaGetLastError();
 }
 
@@ -631,18 +819,18 @@ __global__ void k_pack_all(const float* __restrict__ w2, const float* __restrict
                            __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n2 = DQ_N2 * DQ_K2, n3 = DQ_N3 * DQ_K3, n4 = DQ_N4 * DQ_K4;
-    auto pack = [](const float* w, int n, int k, int k_pad, __nv_bfloat16* out, int idx) {
+    auto pack = [](const float* w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* out, int idx) {
         const int row = idx / k_pad, col = idx % k_pad;
         const float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
-        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + operand_offset(row, col, k_pad)) = __float2bfloat16_rn(v);
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + wpack_offset(n_split, row, col, n_pad, k_pad)) = __float2bfloat16_rn(v);
     };
     auto transpose = [](const float* w, int rows, int cols, int out_cols_pad, __nv_bfloat16* out, int idx) {      // out[c][r] = w[r][c]
         const int c = idx / out_cols_pad, r = idx % out_cols_pad;
         out[idx] = __float2bfloat16_rn((c < cols && r < rows) ? w[(size_t)r * cols + c] : 0.f);
     };
-    if (i < n2) { pack(w2, DQ_H2, DQ_H1, DQ_K2, w2p, i); return; } i -= n2;
-    if (i < n3) { pack(w3, DQ_H3, DQ_H2, DQ_K3, w3p, i); return; } i -= n3;
-    if (i < n4) { pack(w4, DQ_OUT, DQ_H3, DQ_K4, w4p, i); return; } i -= n4;
+    if (i < n2) { pack(w2, DQ_H2, DQ_H1, DQ_N2, DQ_K2, DQ_L2_SPLIT, w2p, i); return; } i -= n2;
+    if (i < n3) { pack(w3, DQ_H3, DQ_H2, DQ_N3, DQ_K3, 0, w3p, i); return; } i -= n3;
+    if (i < n4) { pack(w4, DQ_OUT, DQ_H3, DQ_N4, DQ_K4, 0, w4p, i); return; } i -= n4;
     if (!w3t) return;
     if (i < DQ_N2 * DQ_K2) { transpose(w3, DQ_H3, DQ_H2, DQ_K2, w3t, i); return; } i -= DQ_N2 * DQ_K2;
     if (i < DQ_N3 * DQ_K3) transpose(w2, DQ_H2, DQ_H1, DQ_K3, w2t, i);

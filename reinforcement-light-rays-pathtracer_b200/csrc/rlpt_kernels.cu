@@ -734,18 +734,21 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
 #ifndef RLPT_BVH_UNIFIED_POP
 #define RLPT_BVH_UNIFIED_POP 0
 #endif
+#ifndef RLPT_BVH_FAST_PUSH
+#define RLPT_BVH_FAST_PUSH 0      // branch-free pushes (unconditional stores + conditional increments): measured -0.5 % (medieval_inside), with the unified pop -2.5 %
+#endif
 constexpr int BVH_BATCH = RLPT_BVH_BATCH, BVH_REFILL = RLPT_BVH_REFILL;
 constexpr int B4_STACK = 8;                                              // shared-memory stack entries per lane (kept small: the L1 that serves the nodes shares the SM's 256 KB with it)
 constexpr int B4_SPILL = 88;                                             // local-memory overflow: 3 x depth 30 fits in 96 entries
 constexpr int WQ_CAP = 32 + 32 * 4;                                      // < 32 left over + at most 4 leaves per lane and visit
 // per-warp scratch in dynamic shared memory, behind the staged scene
-constexpr int B4_WARP_BYTES = B4_STACK * 32 * 8 + 32 * 8 + WQ_CAP * 4 + 6 * 32 * 4 + 16;
+constexpr int B4_WARP_BYTES = (B4_STACK + 1) * 32 * 8 + 32 * 8 + WQ_CAP * 4 + 6 * 32 * 4 + 16;   // stack: B4_STACK entries + one scratch slot per lane (branch-free pushes)
 constexpr size_t B4_CTA_BYTES = (size_t)(BLOCK / 32) * B4_WARP_BYTES;
 size_t bvh4_scratch_bytes() { return B4_CTA_BYTES; }
 struct B4Scratch { uint2* stack; unsigned long long* best; unsigned* wq; float* ray; int* count; };
 __device__ __forceinline__ B4Scratch b4_scratch(unsigned char* base) {
     unsigned char* p = base + (threadIdx.x >> 5) * B4_WARP_BYTES;
-    B4Scratch w; w.stack = reinterpret_cast<uint2*>(p); p += B4_STACK * 32 * 8;
+    B4Scratch w; w.stack = reinterpret_cast<uint2*>(p); p += (B4_STACK + 1) * 32 * 8;
     w.best = reinterpret_cast<unsigned long long*>(p); p += 32 * 8;
     w.wq = reinterpret_cast<unsigned*>(p); p += WQ_CAP * 4;
     w.ray = reinterpret_cast<float*>(p); p += 6 * 32 * 4;
@@ -850,12 +853,21 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
                 bvh4_sort(key);
 #if RLPT_BVH_UNIFIED_POP
                 // every inner hit goes on the stack (farthest first) and the next node is popped from it: one code path for "descend" and
-                // "backtrack" instead of two that the warp's lanes would walk one after the other
-                if (key[3] != B4_NONE) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
-                if (key[2] != B4_NONE) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
-                if (key[1] != B4_NONE) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
-                if (key[0] != B4_NONE) push((unsigned)lk[0] + (key[0] & 3u), key[0]);
+                // "backtrack" instead of two that the warp's lanes would walk one after the other. Pushes are branch-free while the shared-memory
+                // stack has room: four unconditional stores (slot B4_STACK is a scratch slot) and conditional increments.
                 {
+                    const int p0 = key[0] != B4_NONE, p1 = key[1] != B4_NONE, p2 = key[2] != B4_NONE, p3 = key[3] != B4_NONE;
+                    if (top + p0 + p1 + p2 + p3 <= B4_STACK) {
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[3] & 3u), key[3]); top += p3;
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[2] & 3u), key[2]); top += p2;
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[1] & 3u), key[1]); top += p1;
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[0] & 3u), key[0]); top += p0;
+                    } else {
+                        if (p3) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
+                        if (p2) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
+                        if (p1) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
+                        if (p0) push((unsigned)lk[0] + (key[0] & 3u), key[0]);
+                    }
                     bool found = false;
                     while (top > 0) {
                         --top;
@@ -866,9 +878,16 @@ __device__ __forceinline__ void bvh4_trace_warp(const SceneView<STAGED>& v, cons
                 }
 #else
                 if (key[0] != B4_NONE) {
-                    if (key[3] != B4_NONE) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
-                    if (key[2] != B4_NONE) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
-                    if (key[1] != B4_NONE) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
+                    const int p1 = key[1] != B4_NONE, p2 = key[2] != B4_NONE, p3 = key[3] != B4_NONE;
+                    if (RLPT_BVH_FAST_PUSH && top + p1 + p2 + p3 <= B4_STACK) {     // branch-free: unconditional stores (slot B4_STACK is scratch), conditional increments
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[3] & 3u), key[3]); top += p3;
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[2] & 3u), key[2]); top += p2;
+                        stack[32 * top] = make_uint2((unsigned)lk[0] + (key[1] & 3u), key[1]); top += p1;
+                    } else {
+                        if (p3) push((unsigned)lk[0] + (key[3] & 3u), key[3]);
+                        if (p2) push((unsigned)lk[0] + (key[2] & 3u), key[2]);
+                        if (p1) push((unsigned)lk[0] + (key[1] & 3u), key[1]);
+                    }
                     cur = lk[0] + (int)(key[0] & 3u);
                 } else {
                     bool found = false;

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+RLPT_LIB_NAME=librlpt_trace.so timeout 120 python scratch/dqn_trace.py 2>&1 | tail -3
+timeout 400 python -m pytest tests/test_gpu_dqn.py -m gpu -x -q > gpurun_out/r2_pytest_dqn18.log 2>&1; echo "pytest dqn rc=$?"; tail -3 gpurun_out/r2_pytest_dqn18.log | cut -c1-600
+for w in cornell_neuralq archway_neuralq; do
+  timeout 300 python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_${w}_18.json 2> gpurun_out/r2_bench_${w}_18.err; echo "$w rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/r2_bench_${w}_18.json')); print({k:d[k] for k in ('value','ms_per_step','us_per_optimiser_step','train_share_of_frame')}, d['roofline']['frac'], d['roofline']['avg_launch_ms'])"
+done
