@@ -205,7 +205,7 @@ int rlpt_ctx_create(int device, rlpt_ctx** out) {
     if (const char* e = getenv("RLPT_BVH_LEAF")) c->bvh_leaf_max = std::max(1, std::min(atoi(e), (int)BVH4_LEAF_MAX));
     rlpt_config_default(&c->cfg);
     float cs[CELLS]; for (int k = 0; k < CELLS; ++k) cs[k] = cell_centre_cos(k);
-    upload_cell_cos(cs);
+    upload_cell_cos(cs); dqn_upload_cell_cos(cs);
     int lim = kernels_set_smem_limit((size_t)prop.sharedMemPerBlockOptin - 12288);    // the kernels also hold static shared memory (compaction scratch; k_isect_bvh: leaf lists + per-lane results, 5 KB)
     if (!lim) lim = dqn_set_smem_limit();
     if (lim) { delete c; return fail(RLPT_ERR_CUDA, "rlpt_ctx_create: cudaFuncSetAttribute failed (kernel image missing for this GPU? built for sm_100a only)"); }
@@ -1211,12 +1211,14 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                             NqTrainState gs = c->nqt; gs.state = c->d_nqg_state; gs.reward = c->d_nqg_reward; gs.discount = c->d_nqg_discount;
                             cudaGraph_t graph = nullptr;
                             CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                            // one launch evaluates the batch's states (activations kept for the backward pass) and its next states (Q only, for the TD targets)
+                            // the step's zeroing runs beside the forward launch, which evaluates the batch's states (activations kept for the backward pass) and its
+                            // next states (Q only); the TD targets are derived from those inside the output-layer delta kernel
+                            int frc = dqn_train_begin(c->dq, c->dq_train, c->d_nqg_sloc, bn, true, c->stream);
                             DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->d_nqg_sloc, bn);
                             gp.pos2 = c->d_nqg_loc; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
-                            int frc = dqn_forward(c->dq, gp, c->stream);
-                            launch_nqt_targets(gs, 0, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss, true);
+                            if (!frc) frc = dqn_forward(c->dq, gp, c->stream);
+                            const DqnTdParams td{ c->d_nqt_qnext, S, gs.state, gs.reward, gs.discount };
+                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss, true, &td);
                             cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
                             if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(RLPT_ERR_CUDA, "Neural-Q training step: graph capture failed"); }
                             ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
@@ -1227,15 +1229,15 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         CK(cudaGraphLaunch(c->nq_graph_exec, c->stream));
                         c->dq_train.step++;
                     } else {
-                        int frc = dqn_train_prepare(c->dq, c->dq_train, bn, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
+                        int frc = dqn_train_begin(c->dq, c->dq_train, c->nqt.sloc + start, bn, true, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
                         DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->nqt.sloc + start, bn);
                         gp.pos2 = c->nqt.loc + start; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
                         frc = dqn_forward(c->dq, gp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
-                        launch_nqt_targets(c->nqt, start, bn, c->d_nqt_qnext, S, c->d_nqt_targets, c->stream);
-                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true);
+                        const DqnTdParams td{ c->d_nqt_qnext, S, c->nqt.state + start, c->nqt.reward + start, c->nqt.discount + start };
+                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true, &td);
                         if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
                     }
-                    c->launches += 19.0;       // kernels of one optimiser step (staging, forward of both batches, targets, zeroing, prepare, 5 GEMMs, 3 deltas, collect, norm, tick, Adam, 2 operand refreshes)
+                    c->launches += 13.0;       // kernels of one optimiser step (staging, step begin, forward of both batches, 5 GEMMs, 3 deltas, collect + norm, Adam + operand refresh)
                     c->k_all[4] += 1.0;
                 }
                 cudaEvent_t t1 = t0 ? kev_mark(c, c->stream) : nullptr;

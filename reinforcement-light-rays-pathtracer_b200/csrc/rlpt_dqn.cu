@@ -240,8 +240,10 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
     const int t = threadIdx.x, warp = t >> 5;
 
     // layer-1 constants as one float4 (c1, M1 row) per output: the shared-memory pipe takes one instruction per cycle, broadcast or not
-    for (int i = t; i < DQ_K2; i += DQ_THREADS) s_l1[i] = i < DQ_H1 ? make_float4(p.c1[i], p.m1[3 * i], p.m1[3 * i + 1], p.m1[3 * i + 2]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = t; i < DQ_N2; i += DQ_THREADS) s_b2[i] = i < DQ_H2 ? p.b2[i] : 0.f;
+    // Unit DQ_H1 of layer 1 and unit DQ_H2 of layer 2 (padding: their weights are zero in both directions) are constant one: the kept activations then carry
+    // the "ones" row that makes the weight-gradient GEMMs of the backward pass produce the bias gradients as well.
+    for (int i = t; i < DQ_K2; i += DQ_THREADS) s_l1[i] = i < DQ_H1 ? make_float4(p.c1[i], p.m1[3 * i], p.m1[3 * i + 1], p.m1[3 * i + 2]) : make_float4(i == DQ_H1 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < DQ_N2; i += DQ_THREADS) s_b2[i] = i < DQ_H2 ? p.b2[i] : (i == DQ_H2 ? 1.f : 0.f);
     for (int i = t; i < DQ_N3; i += DQ_THREADS) s_b3[i] = i < DQ_H3 ? p.b3[i] : 0.f;
     for (int i = t; i < DQ_N4; i += DQ_THREADS) s_b4[i] = i < DQ_OUT ? p.b4[i] : 0.f;
     ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
@@ -555,80 +557,78 @@ namespace rlpt {
 
 // ------------------------------------------------------------------------------------------------ generic tcgen05 GEMM
 // C[M x N] (+)= A[M x K] * B[N x K]^T; A, B bf16 with K contiguous (row strides lda, ldb, multiples of 8), C fp32 row-major.
-// CTA tile 128 x BN (BN <= 160, multiple of 16), K in chunks of 64 through two shared-memory stages; grid.z splits K,
-// partial tiles are combined with atomicAdd (C zeroed by the caller) -- used for the backward pass, where M or K is the batch.
-constexpr int GM_KC = 64, GM_BN = 160;
-constexpr uint32_t GM_A = 0, GM_B = GM_A + 2 * DQ_TILE * GM_KC * 2, GM_BAR = GM_B + 2 * GM_BN * GM_KC * 2, GM_TOTAL = GM_BAR + 64;
+// CTA tile 128 x BN (BN <= 160, multiple of 16); grid.z splits K into pieces of at most GM_KMAX, partial tiles are combined with atomicAdd
+// (C zeroed by the caller) -- used for the backward pass, where M or K is the batch.
+// Single shot: a CTA's whole K piece of both operands (<= 128 x 304 + 160 x 304 bf16 = 175 KB) goes into shared memory with one wave of 16-byte
+// cp.async copies (zero-filled past the edges), one thread then issues all K / 16 MMAs, and 8 warps read the accumulator out of TMEM. The backward
+// pass is a chain of these on <= 64 CTAs each: what counts is latency, and this form pays the global-memory round trip once instead of once per
+// K chunk (the first form staged 64-wide chunks through registers: 15-18 us per launch).
+constexpr int GM_BN = 160, GM_KMAX = 304, GM_THREADS = 256;
+constexpr uint32_t GM_A = 0, GM_B = GM_A + DQ_TILE * GM_KMAX * 2, GM_BAR = GM_B + GM_BN * GM_KMAX * 2, GM_TOTAL = GM_BAR + 64;
+static_assert(GM_TOTAL <= 227 * 1024, "shared-memory budget");
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
 
-// c_t != 0: C is stored transposed, C[n][m] with row length ldc -- the CTA's 128 threads (one output row each) then write consecutive addresses,
+// c_t != 0: C is stored transposed, C[n][m] with row length ldc -- a warp's 32 threads (one output row each) then write consecutive addresses,
 // and the consumer of the backward data path (k_delta_hidden, feature-major) reads them the same way.
-__global__ void __launch_bounds__(DQ_TILE, 1) k_gemm_bf16_tn(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                              int M, int N, int K, int k_per_split, int c_t) {
+__global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_bf16_tn(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                                 int M, int N, int K, int k_per_split, int c_t) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_BAR);          // [0,1]: stage free (MMAs done), [2]: all done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GM_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int t = threadIdx.x, warp = t >> 5;
     const int m0 = blockIdx.x * DQ_TILE, n0 = blockIdx.y * GM_BN, bn = min(GM_BN, N - n0);
     const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
-    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
-    tc_fence_before(); __syncthreads(); tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    uint32_t uses[2] = { 0, 0 };
-    const uint32_t idesc = idesc_bf16(DQ_TILE, bn);
-    int chunk = 0;
-    for (int k0 = k_begin; k0 < k_end; k0 += GM_KC, ++chunk) {
-        const int st = chunk & 1;
-        if (uses[st]) mbar_wait(&bars[st], (uses[st] - 1u) & 1u);         // the MMAs that read this stage have completed
-        uint8_t* sa = smem + GM_A + st * (DQ_TILE * GM_KC * 2); uint8_t* sb = smem + GM_B + st * (GM_BN * GM_KC * 2);
-        {   // A: thread t stages row m0 + t, 64 k-values = 8 x 16 bytes
-            const int m = m0 + t; const bool ok = m < M;
-            const uint4* src = reinterpret_cast<const uint4*>(A + (size_t)(ok ? m : 0) * lda + k0);
-#pragma unroll
-            for (int j = 0; j < GM_KC / 8; ++j) {
-                uint4 v = (ok && k0 + 8 * j < k_end) ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sa + operand_offset(t, 8 * j, GM_KC)) = v;
-            }
-        }
-        for (int r = t; r < bn; r += DQ_TILE) {
-            const uint4* src = reinterpret_cast<const uint4*>(B + (size_t)(n0 + r) * ldb + k0);
-#pragma unroll
-            for (int j = 0; j < GM_KC / 8; ++j) {
-                uint4 v = (k0 + 8 * j < k_end) ? __ldg(src + j) : make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sb + operand_offset(r, 8 * j, GM_KC)) = v;
-            }
-        }
-        fence_proxy_async(); tc_fence_before(); __syncthreads();
-        if (t == 0) {
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
-            for (int k = 0; k < GM_KC / 16; ++k)
-                umma_bf16(tmem_base, smem_desc(a_addr + (uint32_t)k * 256u, 128u, GM_KC * 16u), smem_desc(b_addr + (uint32_t)k * 256u, 128u, GM_KC * 16u), idesc, (chunk | k) != 0);
-            umma_commit(&bars[st]);
-        }
-        uses[st]++;
+    const int kk = (k_end - k_begin + 15) & ~15, pk = kk >> 3;            // this CTA's K, padded to the MMA's K step; 16-byte pieces per row
+    uint8_t* sa = smem + GM_A; uint8_t* sb = smem + GM_B;
+    for (int idx = t; idx < DQ_TILE * pk; idx += GM_THREADS) {
+        const int row = idx / pk, j = idx - row * pk, m = m0 + row, k = k_begin + 8 * j;
+        const bool ok = m < M && k < k_end;
+        cp_async16(sa + operand_offset(row, 8 * j, kk), ok ? A + (size_t)m * lda + k : A, ok);
     }
-    if (t == 0) umma_commit(&bars[2]);
-    mbar_wait(&bars[2], 0); tc_fence_after();
-    const int m = m0 + t; const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool split = gridDim.z > 1;
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-        uint32_t r[16]; tmem_ld16(lane_addr + (uint32_t)c0, r);
-        if (m < M && chunk > 0) {
-            float* dst = c_t ? C + (size_t)(n0 + c0) * ldc + m : C + (size_t)m * ldc + n0 + c0;
-            const size_t step = c_t ? (size_t)ldc : 1;
+    for (int idx = t; idx < bn * pk; idx += GM_THREADS) {
+        const int row = idx / pk, j = idx - row * pk, k = k_begin + 8 * j;
+        const bool ok = k < k_end;
+        cp_async16(sb + operand_offset(row, 8 * j, kk), ok ? B + (size_t)(n0 + row) * ldb + k : B, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async(); tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (t == 0 && kk > 0) {
+        const uint32_t idesc = idesc_bf16(DQ_TILE, bn);
+        uint32_t a_lo = ((smem_u32(sa) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16), b_lo = ((smem_u32(sb) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+        const uint32_t hi = (uint32_t)kk | (1u << 14);                     // SBO = kk * 16 bytes, in 16-byte units
+        for (int k = 0; k < kk / 16; ++k, a_lo += 16u, b_lo += 16u) umma_bf16_lohi(tmem_base, a_lo, hi, b_lo, hi, idesc, (uint32_t)k);
+        umma_commit(bar);
+    }
+    if (kk > 0) {
+        mbar_wait(bar, 0); tc_fence_after();
+        const int m = m0 + (t & (DQ_TILE - 1)); const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const bool split = gridDim.z > 1;
+        for (int c0 = 16 * (warp >> 2); c0 < bn; c0 += 32) {               // the two warpgroups take the 16-column blocks in turn
+            uint32_t r[16]; tmem_ld16(lane_addr + (uint32_t)c0, r);
+            if (m < M) {
+                float* dst = c_t ? C + (size_t)(n0 + c0) * ldc + m : C + (size_t)m * ldc + n0 + c0;
+                const size_t step = c_t ? (size_t)ldc : 1;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j * step, __uint_as_float(r[j])); else dst[j * step] = __uint_as_float(r[j]); }
+                for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j * step, __uint_as_float(r[j])); else dst[j * step] = __uint_as_float(r[j]); }
+            }
         }
     }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s, int c_t = 0) {
-    int k_per = ((K + k_splits - 1) / k_splits + GM_KC - 1) / GM_KC * GM_KC; if (k_per < GM_KC) k_per = GM_KC;
+    const int k_cap = 256;                                                 // K per CTA when K has to be split (<= GM_KMAX)
+    if (k_splits < (K + GM_KMAX - 1) / GM_KMAX) k_splits = (K + k_cap - 1) / k_cap;
+    int k_per = ((K + k_splits - 1) / k_splits + 15) / 16 * 16; if (k_per > GM_KMAX) k_per = k_cap; if (k_per < 16) k_per = 16;
     const int zs = (K + k_per - 1) / k_per;
     dim3 grid((M + DQ_TILE - 1) / DQ_TILE, (N + GM_BN - 1) / GM_BN, zs);
-    k_gemm_bf16_tn<<<grid, DQ_TILE, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per, c_t);
+    k_gemm_bf16_tn<<<grid, GM_THREADS, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per, c_t);
     return (int)cudaGetLastError();
 }
 
@@ -639,36 +639,46 @@ __global__ void k_transpose_bf16(const float* __restrict__ w, int rows, int cols
     int c = i / out_cols_pad, r = i % out_cols_pad;
     out[i] = __float2bfloat16_rn((c < cols && r < rows) ? w[(size_t)r * cols + c] : 0.f);
 }
-// batch inputs for the gradient GEMMs: xt rows (x, y, z, 1), the "ones" rows of h1t / h2t, zero padding rows
-__global__ void k_train_prepare(const float4* __restrict__ pos, int n, int S, __nv_bfloat16* __restrict__ xt, __nv_bfloat16* __restrict__ h1t, __nv_bfloat16* __restrict__ h2t, __nv_bfloat16* __restrict__ h3t) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    const bool ok = i < n; float4 x = ok ? pos[i] : make_float4(0, 0, 0, 0);
-    const __nv_bfloat16 one = __float2bfloat16_rn(ok ? 1.f : 0.f), zero = __float2bfloat16_rn(0.f);
-    xt[i] = __float2bfloat16_rn(x.x); xt[(size_t)S + i] = __float2bfloat16_rn(x.y); xt[(size_t)2 * S + i] = __float2bfloat16_rn(x.z); xt[(size_t)3 * S + i] = one;
-    for (int r = 4; r < 16; ++r) xt[(size_t)r * S + i] = zero;
-    if (!ok) {                                                             // rays past n are not written by the forward kernel
-        for (int r = 0; r < DQ_K2; ++r) { h1t[(size_t)r * S + i] = zero; h3t[(size_t)r * S + i] = zero; }
-        for (int r = 0; r < DQ_K3; ++r) h2t[(size_t)r * S + i] = zero;
-    } else {
-        h1t[(size_t)DQ_H1 * S + i] = one; h2t[(size_t)DQ_H2 * S + i] = one;
-    }
-}
+// (k_step_begin, below the parameter segment table, prepares a step: zeroing + the batch inputs of the gradient GEMMs)
 // output-layer delta (one action per ray): g = d/dq (target - q_a)^2 * relu'(q_a); delta3 = g W4[a, :] relu'(h3);
 // dW4[a, :] += g h3, db4[a] += g; loss accumulated. One CTA per 32 rays x all 208 hidden units: the feature-major arrays (h3t, d3t) are
 // walked with the ray index fastest, the ray-major d3 is written from a shared-memory tile with the unit index fastest -- every access
 // coalesced. (One thread per ray walking 208 units, the first form of this kernel, took 125 us of a 270 us optimiser step.)
 constexpr int D3_RAYS = 32;
-__global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, const float* __restrict__ targets, int n, int S,
+__constant__ float c_dq_cos[DQ_OUT];                                     // cos(theta) of the 144 grid cells (the tracer's table; dqn_upload_cell_cos)
+void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos144, sizeof(float) * DQ_OUT); }
+// With tdp.q_next set the kernel first derives the batch's TD targets itself (compute_td_targets, nn_rendering_helpers.cu:91-140:
+// reward + discount * max_a Q(s', a) cos(theta_a); terminal: the reward) -- eight warps x 18 cells per ray, combined through shared memory --
+// instead of reading them from a kernel of its own (8 us of a 130 us optimiser step).
+__global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, float* __restrict__ targets, DqnTdParams tdp, int n, int S,
                                                 const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t,
                                                 float* __restrict__ gw4, float* __restrict__ gb4, float* __restrict__ scalars) {
     __shared__ __nv_bfloat16 tile[D3_RAYS][DQ_K4 + 2];                   // + 2: rows 105 words apart, conflict-free column writes
-    __shared__ float s_g[D3_RAYS]; __shared__ int s_a[D3_RAYS];
+    __shared__ float s_g[D3_RAYS]; __shared__ int s_a[D3_RAYS]; __shared__ float s_best[8][D3_RAYS];
     const int i0 = blockIdx.x * D3_RAYS, tid = threadIdx.x;
-    if (tid < D3_RAYS) {
-        const int i = i0 + tid; float g = 0.f, loss = 0.f; int a = 0;
+    const int ii = tid & 31, jj = tid >> 5, i = i0 + ii;
+    if (tdp.q_next) {
+        float best = 0.f;
         if (i < n) {
-            a = (int)actions[i]; const float qa = q[(size_t)a * S + i], diff = qa - targets[i];
+#pragma unroll
+            for (int k = jj * 18; k < jj * 18 + 18; ++k) best = fmaxf(best, __ldg(tdp.q_next + (size_t)k * tdp.q_stride + i) * c_dq_cos[k]);
+        }
+        s_best[jj][ii] = best;
+        __syncthreads();
+    }
+    if (tid < D3_RAYS) {
+        float g = 0.f, loss = 0.f; int a = 0;
+        if (i < n) {
+            float target;
+            if (tdp.q_next) {
+                float best = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) best = fmaxf(best, s_best[w][ii]);
+                target = tdp.reward[i];
+                if (tdp.state[i] != 1u) target += best * tdp.discount[i];
+                targets[i] = target;
+            } else target = targets[i];
+            a = (int)actions[i]; const float qa = q[(size_t)a * S + i], diff = qa - target;
             loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f;
             if (g != 0.f) atomicAdd(gb4 + a, g);
         }
@@ -677,8 +687,8 @@ __global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, con
         if (tid == 0 && loss != 0.f) atomicAdd(scalars, loss);
     }
     __syncthreads();
-    const int ii = tid & 31, jj = tid >> 5, i = i0 + ii;
     const float g = s_g[ii]; const int a = s_a[ii];
+#pragma unroll 13
     for (int j = jj; j < DQ_K4; j += 8) {
         const float h = (i < n && j < DQ_H3) ? __bfloat162float(h3t[(size_t)j * S + i]) : 0.f;
         const bool on = g != 0.f && h > 0.f;
@@ -720,16 +730,32 @@ __global__ void k_dw4_full(const float* __restrict__ g4, const __nv_bfloat16* __
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) { if (j < DQ_H3) gw4[(size_t)a * DQ_H3 + j] = acc; else gb4[a] = acc; }
 }
-// hidden-layer delta: d = pre * relu'(h); written ray-major (next data GEMM's A) and feature-major (weight-gradient GEMM's A)
-__global__ void k_delta_hidden(const float* __restrict__ pre, int ld_pre, const __nv_bfloat16* __restrict__ ht, int S, int n_feat, int k_pad,
-                               __nv_bfloat16* __restrict__ d_ray, __nv_bfloat16* __restrict__ d_feat) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i >= S) return;
-    float d = 0.f;
-    if (j < n_feat) { float h = __bfloat162float(ht[(size_t)j * S + i]); d = h > 0.f ? pre[(size_t)j * ld_pre + i] : 0.f; }       // pre is feature-major (the GEMM stores it transposed)
-    __nv_bfloat16 db = __float2bfloat16_rn(d);
-    if (d_ray) d_ray[(size_t)i * k_pad + j] = db;
-    d_feat[(size_t)j * S + i] = db;
+// hidden-layer delta: d = pre * relu'(h); written feature-major (weight-gradient GEMM's A) and, for the layer that has one below it, ray-major (next data
+// GEMM's A). One CTA = 32 rays x 64 features: all global reads and the feature-major store walk the ray index (coalesced); the ray-major copy goes
+// through a shared-memory tile and leaves as 128-byte rows. (One thread per element with a 2-byte store at stride k_pad was 14 us of the step.)
+constexpr int DH_RAYS = 32, DH_FEATS = 64;
+__global__ void __launch_bounds__(256) k_delta_hidden(const float* __restrict__ pre, int ld_pre, const __nv_bfloat16* __restrict__ ht, int S, int n_feat, int k_pad,
+                                                      __nv_bfloat16* __restrict__ d_ray, __nv_bfloat16* __restrict__ d_feat) {
+    __shared__ __nv_bfloat16 tile[DH_RAYS][DH_FEATS + 2];                // rows 33 words apart: conflict-free both ways
+    const int i0 = blockIdx.x * DH_RAYS, f0 = blockIdx.y * DH_FEATS, lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = i0 + lane;
+#pragma unroll
+    for (int q = 0; q < DH_FEATS / 8; ++q) {
+        const int fl = w + 8 * q, j = f0 + fl;
+        float d = 0.f;
+        if (i < S && j < n_feat) { const float h = __bfloat162float(ht[(size_t)j * S + i]); d = h > 0.f ? pre[(size_t)j * ld_pre + i] : 0.f; }       // pre is feature-major (the GEMM stores it transposed)
+        const __nv_bfloat16 db = __float2bfloat16_rn(d);
+        if (i < S && j < k_pad) d_feat[(size_t)j * S + i] = db;
+        tile[lane][fl] = db;
+    }
+    if (!d_ray) return;
+    __syncthreads();
+    const uint32_t* tw = reinterpret_cast<const uint32_t*>(&tile[0][0]);
+#pragma unroll
+    for (int q = 0; q < DH_RAYS / 8; ++q) {
+        const int r = w + 8 * q;                                           // ray of the tile; lane = pair of features
+        if (i0 + r < S && f0 + 2 * lane < k_pad)
+            reinterpret_cast<uint32_t*>(d_ray + (size_t)(i0 + r) * k_pad + f0)[lane] = tw[r * ((DH_FEATS + 2) / 2) + lane];
+    }
 }
 // gather the gradient of every parameter from the GEMM outputs; W1 through the rank-3 identity dW1[j][i] = db1_j v_i - G[j][i % 3]
 __global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __restrict__ dw2x, const float* __restrict__ dg, const float* __restrict__ v, int k_in,
@@ -750,20 +776,9 @@ __global__ void k_collect_grads(const float* __restrict__ dw3x, const float* __r
 }
 // Adam as DyNet's AdamTrainer applies it: gradient scaled by min(1, clip / ||g||), m and v updated, step size
 // lr sqrt(1 - beta2^t) / (1 - beta1^t), x -= step * m / (sqrt(v) + eps)
-// The step counter lives on the device (scalars[3], advanced once per step by k_adam_tick, which also derives the bias-corrected
+// The step counter lives on the device (scalars[3], advanced once per step by k_step_begin; k_adam_fused derives the bias-corrected
 // step size into scalars[2]), so that a captured optimiser step can be replayed as a CUDA graph without any host value in it.
-constexpr int SQN_BLOCKS = 128;        // k_sqnorm_all's grid: that many partial sums, added in order by k_adam_tick
-__global__ void k_adam_tick(float* __restrict__ scalars, float lr, float beta1, float beta2, float* __restrict__ loss_total, const float* __restrict__ sq_partial) {
-    // one warp; the summation order is fixed (lane l adds partials 4l .. 4l+3, then a butterfly), so every rank derives the same bits
-    const int l = threadIdx.x;
-    float n2 = (sq_partial[4 * l] + sq_partial[4 * l + 1]) + (sq_partial[4 * l + 2] + sq_partial[4 * l + 3]);
-    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-    if (l) return;
-    scalars[1] = n2;
-    if (loss_total) *loss_total += scalars[0];                          // running loss of the frame (was a kernel of its own)
-    const float t = scalars[3] + 1.f; scalars[3] = t;
-    scalars[2] = lr * sqrtf(1.f - powf(beta2, t)) / (1.f - powf(beta1, t));
-}
+constexpr int SQN_BLOCKS = 128;        // k_sqnorm_all's / k_collect_norm's grid: that many partial sums, added in a fixed order by k_adam_fused
 // The eight parameter arrays (W1 b1 .. W4 b4) are separate allocations; the per-step element-wise passes run over all of them
 // in ONE launch each (segment table passed by value) instead of eight: the optimiser step is a chain of ~40 tiny kernels and
 // every node costs a few microseconds of dependency latency.
@@ -772,14 +787,29 @@ __device__ __forceinline__ int seg_of(const ParamSegs& t, int i) { int s = 0;
 #pragma unroll
     for (int k = 1; k < 8; ++k) s += i >= t.start[k] ? 1 : 0;
     return s; }
-__global__ void k_zero_grads(ParamSegs t, float* a, int na, float* b, int nb, float* c, int nc, float* scalars) {
+// Start of an optimiser step (runs beside the forward pass): gradients, GEMM outputs and the step's scalars zeroed, Adam's step count advanced, the
+// batch inputs of the layer-1 gradient GEMM xt = rows (x, y, z, 1), and zero activations for the padding rays of a partial batch (the forward pass
+// writes valid rays only; its "ones" units take care of the bias rows).
+__global__ void k_step_begin(ParamSegs t, float* a, int na, float* b, int nb, float* c, int nc, float* scalars, int advance,
+                             const float4* __restrict__ pos, int n, int S, __nv_bfloat16* __restrict__ xt, __nv_bfloat16* __restrict__ h1t, __nv_bfloat16* __restrict__ h2t, __nv_bfloat16* __restrict__ h3t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, total = t.start[8];
+    if (i < S) {
+        const bool ok = i < n; const float4 x = ok ? pos[i] : make_float4(0, 0, 0, 0);
+        const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+        xt[i] = __float2bfloat16_rn(x.x); xt[(size_t)S + i] = __float2bfloat16_rn(x.y); xt[(size_t)2 * S + i] = __float2bfloat16_rn(x.z); xt[(size_t)3 * S + i] = __float2bfloat16_rn(ok ? 1.f : 0.f);
+        for (int r = 4; r < 16; ++r) xt[(size_t)r * S + i] = zero;
+        if (!ok) {
+            for (int r = 0; r < DQ_K2; ++r) { h1t[(size_t)r * S + i] = zero; h3t[(size_t)r * S + i] = zero; }
+            for (int r = 0; r < DQ_K3; ++r) h2t[(size_t)r * S + i] = zero;
+        }
+    }
     if (i < total) { const int s = seg_of(t, i); t.g[s][i - t.start[s]] = 0.f; return; }
     int j = i - total;
     if (j < na) { a[j] = 0.f; return; } j -= na;
     if (j < nb) { b[j] = 0.f; return; } j -= nb;
     if (j < nc) { c[j] = 0.f; return; } j -= nc;
-    if (j < 2) scalars[j] = 0.f;                               // loss and gradient norm; [2] step size and [3] step count persist
+    if (j < 2) scalars[j] = 0.f;                               // loss and gradient norm; [2] step size persists
+    if (j == 2 && advance) scalars[3] += 1.f;                  // Adam's step count t of THIS step (nothing else writes it)
 }
 // squared gradient norm, in a FIXED summation order (per-thread strided sums -> block tree -> 128 partials added by one thread): after a gradient
 // all-reduce every rank holds the same gradients, and the clipping factor derived from this norm must then be the same bits on every rank, or the
@@ -793,16 +823,114 @@ __global__ void __launch_bounds__(256) k_sqnorm_all(ParamSegs t, float* __restri
     __syncthreads();
     if (threadIdx.x == 0) { float b = 0.f; for (int w = 0; w < 8; ++w) b += s_w[w]; partial[blockIdx.x] = b; }
 }
-__global__ void k_adam_all(ParamSegs t, const float* __restrict__ scalars, float clip, float beta1, float beta2, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= t.start[8]) return;
-    const int s = seg_of(t, i), j = i - t.start[s];
-    const float step_size = scalars[2];
-    const float norm = sqrtf(scalars[1]); const float scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
-    const float gi = t.g[s][j] * scale;
-    const float mi = beta1 * t.m[s][j] + (1.f - beta1) * gi, vi = beta2 * t.v[s][j] + (1.f - beta2) * gi * gi;
-    t.m[s][j] = mi; t.v[s][j] = vi;
-    t.x[s][j] -= step_size * mi / (sqrtf(vi) + eps);
+// k_collect_grads + k_sqnorm_all in one pass (single-GPU step; with a gradient all-reduce between them the two stay separate): every thread derives
+// the gradients it is responsible for from the GEMM outputs (W4 / b4 are already in place, accumulated by k_delta3), stores them and sums their
+// squares in k_sqnorm_all's order, so the norm has the same bits either way.
+__global__ void __launch_bounds__(1024) k_collect_norm(ParamSegs t, const float* __restrict__ dw3x, const float* __restrict__ dw2x, const float* __restrict__ dg, const float* __restrict__ v, int k_in,
+                                                      float* __restrict__ partial) {
+    __shared__ float s_w[32];
+    float acc = 0.f; const int total = t.start[8];
+#pragma unroll 2
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int s = seg_of(t, i), j = i - t.start[s];
+        float g;
+        switch (s) {
+            case 0: { const int r = j / k_in, c = j - r * k_in; g = dg[r * 16 + 3] * v[c] - dg[r * 16 + c % 3]; break; }
+            case 1: g = dg[j * 16 + 3]; break;
+            case 2: { const int r = j / DQ_H1, c = j - r * DQ_H1; g = dw2x[(size_t)r * DQ_K2 + c]; break; }
+            case 3: g = dw2x[(size_t)j * DQ_K2 + DQ_H1]; break;
+            case 4: { const int r = j / DQ_H2, c = j - r * DQ_H2; g = dw3x[(size_t)r * DQ_K3 + c]; break; }
+            case 5: g = dw3x[(size_t)j * DQ_K3 + DQ_H2]; break;
+            default: g = t.g[s][j]; break;
+        }
+        if (s < 6) t.g[s][j] = g;
+        acc += g * g;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float b = 0.f; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b += s_w[w]; partial[blockIdx.x] = b; }
+}
+// k_adam_tick + k_adam_all + k_layer1_operands + k_pack_all in one launch. Every CTA derives the clipping factor (the 128 partial sums, added in
+// k_adam_tick's order by its first warp) and the bias-corrected step size (step count t = scalars[3], advanced by k_step_begin) for itself.
+// CTAs [0, 200): one CTA per row of W1 -- Adam on the row and on b1, then the row's layer-1 operands c1 = b1 + W1 v, M1 = column sums by coordinate.
+// The other CTAs: Adam element-wise on W2 b2 W3 b3 W4 b4, each updated weight written straight into its bf16 operand copies (the forward pass's
+// packed B operands, and the transposes the backward data path multiplies by; their padding stays zero from the first pack).
+constexpr int ADAM_ROW_BLOCKS = DQ_H1, ADAM_ROW_ITEMS = 4;                // one CTA per row of W1; the first 4 x 256 inputs of the row are requested before the norm is known
+__global__ void __launch_bounds__(256) k_adam_fused(ParamSegs t, float* __restrict__ scalars, const float* __restrict__ sq_partial, float* __restrict__ loss_total,
+                                                    float lr, float clip, float beta1, float beta2, float eps, const float* __restrict__ v, int k_in, float* __restrict__ c1, float* __restrict__ m1,
+                                                    __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w3p, __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t) {
+    __shared__ float s_n2; __shared__ float s_red[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool rows = blockIdx.x < ADAM_ROW_BLOCKS;
+    // this thread's elements: their gradient and moments are requested before the CTA turns to the norm (everything here is latency)
+    int seg[ADAM_ROW_ITEMS], idx[ADAM_ROW_ITEMS]; float g[ADAM_ROW_ITEMS], mm[ADAM_ROW_ITEMS], vv[ADAM_ROW_ITEMS], xx[ADAM_ROW_ITEMS], vin[ADAM_ROW_ITEMS];
+    int n_items = 0;
+    if (rows) {
+#pragma unroll
+        for (int q = 0; q < ADAM_ROW_ITEMS; ++q) { const int i = threadIdx.x + 256 * q; if (i < k_in) { seg[q] = 0; idx[q] = blockIdx.x * k_in + i; vin[q] = v[i]; n_items = q + 1; } else { seg[q] = -1; idx[q] = 0; vin[q] = 0.f; } }
+    } else {
+        const int i = t.start[2] + (blockIdx.x - ADAM_ROW_BLOCKS) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < ADAM_ROW_ITEMS; ++q) { seg[q] = -1; idx[q] = 0; vin[q] = 0.f; }
+        if (i < t.start[8]) { seg[0] = seg_of(t, i); idx[0] = i - t.start[seg[0]]; n_items = 1; }
+    }
+#pragma unroll
+    for (int q = 0; q < ADAM_ROW_ITEMS; ++q) if (seg[q] >= 0) { g[q] = t.g[seg[q]][idx[q]]; mm[q] = t.m[seg[q]][idx[q]]; vv[q] = t.v[seg[q]][idx[q]]; xx[q] = t.x[seg[q]][idx[q]]; }
+    float gb = 0.f, mb = 0.f, vb = 0.f, xb1 = 0.f;                          // the row's bias b1 (thread 0 of a row CTA)
+    if (rows && threadIdx.x == 0) { gb = t.g[1][blockIdx.x]; mb = t.m[1][blockIdx.x]; vb = t.v[1][blockIdx.x]; xb1 = t.x[1][blockIdx.x]; }
+    if (warp == 0) {
+        float n2 = (sq_partial[4 * lane] + sq_partial[4 * lane + 1]) + (sq_partial[4 * lane + 2] + sq_partial[4 * lane + 3]);
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        if (lane == 0) s_n2 = n2;
+    }
+    __syncthreads();
+    const float n2 = s_n2, tt = scalars[3];
+    const float step_size = lr * sqrtf(1.f - powf(beta2, tt)) / (1.f - powf(beta1, tt));
+    const float norm = sqrtf(n2), scale = (clip > 0.f && norm > clip) ? clip / norm : 1.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scalars[1] = n2; scalars[2] = step_size; if (loss_total) *loss_total += scalars[0]; }
+    auto adam = [&](float gi, float& mi, float& vi, float x) {
+        gi *= scale;
+        mi = beta1 * mi + (1.f - beta1) * gi; vi = beta2 * vi + (1.f - beta2) * gi * gi;
+        return x - step_size * mi / (sqrtf(vi) + eps);
+    };
+    if (rows) {
+        // Adam on the row of W1 and on b1, then the row's layer-1 operands c1 = b1 + W1 v, M1 = column sums by coordinate
+        float acc = 0.f, m[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int q = 0; q < ADAM_ROW_ITEMS; ++q) if (seg[q] >= 0) {
+            const float w = adam(g[q], mm[q], vv[q], xx[q]);
+            t.m[0][idx[q]] = mm[q]; t.v[0][idx[q]] = vv[q]; t.x[0][idx[q]] = w;
+            acc += w * vin[q]; const int d = (threadIdx.x + 256 * q) % 3; m[0] += d == 0 ? w : 0.f; m[1] += d == 1 ? w : 0.f; m[2] += d == 2 ? w : 0.f;
+        }
+        for (int i = threadIdx.x + 256 * ADAM_ROW_ITEMS; i < k_in; i += 256) {          // rows wider than 1024 inputs (large scenes): the rest, plainly
+            const int e = blockIdx.x * k_in + i; float mi = t.m[0][e], vi = t.v[0][e];
+            const float w = adam(t.g[0][e], mi, vi, t.x[0][e]);
+            t.m[0][e] = mi; t.v[0][e] = vi; t.x[0][e] = w;
+            acc += w * v[i]; const int d = i % 3; m[0] += d == 0 ? w : 0.f; m[1] += d == 1 ? w : 0.f; m[2] += d == 2 ? w : 0.f;
+        }
+        for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); for (int d = 0; d < 3; ++d) m[d] += __shfl_xor_sync(0xffffffffu, m[d], o); }
+        if (lane == 0) { s_red[warp][0] = acc; s_red[warp][1] = m[0]; s_red[warp][2] = m[1]; s_red[warp][3] = m[2]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float r4[4] = { 0.f, 0.f, 0.f, 0.f };
+            for (int w = 0; w < 8; ++w) for (int d = 0; d < 4; ++d) r4[d] += s_red[w][d];
+            const int row = blockIdx.x;
+            const float b = adam(gb, mb, vb, xb1);
+            t.m[1][row] = mb; t.v[1][row] = vb; t.x[1][row] = b;
+            c1[row] = b + r4[0]; m1[3 * row] = r4[1]; m1[3 * row + 1] = r4[2]; m1[3 * row + 2] = r4[3];
+        }
+        return;
+    }
+    if (n_items == 0) return;
+    // element-wise on W2 b2 W3 b3 W4 b4; each updated weight goes straight into its bf16 operand copies (padding stays zero from the first pack)
+    const int s = seg[0], j = idx[0];
+    const float x = adam(g[0], mm[0], vv[0], xx[0]);
+    t.m[s][j] = mm[0]; t.v[s][j] = vv[0]; t.x[s][j] = x;
+    const __nv_bfloat16 xb = __float2bfloat16_rn(x);
+    if (s == 2) { const int r = j / DQ_H1, c = j - r * DQ_H1; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2p) + wpack_offset(DQ_L2_SPLIT, r, c, DQ_N2, DQ_K2)) = xb; if (w2t) w2t[(size_t)c * DQ_K3 + r] = xb; }
+    else if (s == 4) { const int r = j / DQ_H2, c = j - r * DQ_H2; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3p) + wpack_offset(0, r, c, DQ_N3, DQ_K3)) = xb; if (w3t) w3t[(size_t)c * DQ_K2 + r] = xb; }
+    else if (s == 6) { const int r = j / DQ_H3, c = j - r * DQ_H3; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w4p) + wpack_offset(0, r, c, DQ_N4, DQ_K4)) = xb; }
 }
 static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
     ParamSegs p{}; DqnHost shape; shape.k_in = d.k_in; int at = 0;
@@ -814,28 +942,6 @@ static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
     p.start[8] = at;
     return p;
 }
-// packed bf16 operands of layers 2-4 and the two transposes of the backward pass, one launch
-__global__ void k_pack_all(const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w3p,
-                           __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n2 = DQ_N2 * DQ_K2, n3 = DQ_N3 * DQ_K3, n4 = DQ_N4 * DQ_K4;
-    auto pack = [](const float* w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* out, int idx) {
-        const int row = idx / k_pad, col = idx % k_pad;
-        const float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
-        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + wpack_offset(n_split, row, col, n_pad, k_pad)) = __float2bfloat16_rn(v);
-    };
-    auto transpose = [](const float* w, int rows, int cols, int out_cols_pad, __nv_bfloat16* out, int idx) {      // out[c][r] = w[r][c]
-        const int c = idx / out_cols_pad, r = idx % out_cols_pad;
-        out[idx] = __float2bfloat16_rn((c < cols && r < rows) ? w[(size_t)r * cols + c] : 0.f);
-    };
-    if (i < n2) { pack(w2, DQ_H2, DQ_H1, DQ_N2, DQ_K2, DQ_L2_SPLIT, w2p, i); return; } i -= n2;
-    if (i < n3) { pack(w3, DQ_H3, DQ_H2, DQ_N3, DQ_K3, 0, w3p, i); return; } i -= n3;
-    if (i < n4) { pack(w4, DQ_OUT, DQ_H3, DQ_N4, DQ_K4, 0, w4p, i); return; } i -= n4;
-    if (!w3t) return;
-    if (i < DQ_N2 * DQ_K2) { transpose(w3, DQ_H3, DQ_H2, DQ_K2, w3t, i); return; } i -= DQ_N2 * DQ_K2;
-    if (i < DQ_N3 * DQ_K3) transpose(w2, DQ_H2, DQ_H1, DQ_K3, w2t, i);
-}
-
 void dqn_train_free(DqnTrain& t) {
     cudaFree(t.gall); cudaFree(t.sq_partial);
     for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
@@ -897,28 +1003,40 @@ int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {          
     }
     return 0;
 }
-int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
-                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs, float* loss_total, bool forward_done) {
+// Start of a step, beside whatever the caller enqueues next on `s` (the forward pass): zeroing and the batch inputs on the side stream.
+int dqn_train_begin(DqnDev& d, DqnTrain& t, const float4* pos, int n, bool advance, cudaStream_t s) {
     if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
-    int rc = dqn_train_prepare(d, t, n, s); if (rc) return rc;               // (afterwards k_pack_all keeps the transposes current)
+    int rc = dqn_train_prepare(d, t, n, s); if (rc) return rc;               // (afterwards k_adam_fused keeps operands and transposes current)
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
-    DqnHost shape; shape.k_in = d.k_in;
     const ParamSegs segs = param_segs(d, t);
-    {
-        const int na = DQ_N3 * DQ_K3, nb = DQ_N2 * DQ_K2, nc = DQ_K2 * 16, total = segs.start[8] + na + nb + nc + 2;
-        k_zero_grads<<<(total + 255) / 256, 256, 0, s>>>(segs, t.dw3x, na, t.dw2x, nb, t.dg, nc, t.scalars);
-    }
+    const int na = DQ_N3 * DQ_K3, nb = DQ_N2 * DQ_K2, nc = DQ_K2 * 16; int total = segs.start[8] + na + nb + nc + 3; if (total < S) total = S;
+    DQ_CK(cudaEventRecord(t.ev[3], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[3], 0));
+    k_step_begin<<<(total + 255) / 256, 256, 0, t.side>>>(segs, t.dw3x, na, t.dw2x, nb, t.dg, nc, t.scalars, advance ? 1 : 0, pos, n, S, t.xt, t.h1t, t.h2t, t.h3t);
+    DQ_CK(cudaEventRecord(t.ev[4], t.side));
+    t.begun = true;
+    return (int)cudaGetLastError();
+}
+int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
+                    dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs, float* loss_total, bool forward_done, const DqnTdParams* tdp) {
+    if (!d.ready || n <= 0) return n == 0 ? 0 : -1;
+    int rc = 0;
+    if (!t.begun) { rc = dqn_train_begin(d, t, pos, n, apply_update, s); if (rc) return rc; }
+    t.begun = false;
+    const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
+    const ParamSegs segs = param_segs(d, t);
     // forward, activations kept
     if (!forward_done) { const DqnFwdParams fp = dqn_train_forward_params(d, t, pos, n); rc = dqn_forward(d, fp, s); if (rc) return rc; }
-    k_train_prepare<<<(S + 127) / 128, 128, 0, s>>>(pos, n, S, t.xt, t.h1t, t.h2t, t.h3t);
+    DQ_CK(cudaStreamWaitEvent(s, t.ev[4], 0));                              // the zeroing and the batch inputs are in place
     // backward: data path
     if (all_outputs) {            // targets: [n][144]
         if (S > t.g4_capacity) { cudaFree(t.g4); t.g4 = nullptr; t.g4_capacity = 0; DQ_CK(cudaMalloc(&t.g4, 4 * (size_t)DQ_OUT * S)); t.g4_capacity = S; }
         k_g4_full<<<dim3((S + 127) / 128, DQ_OUT), 128, 0, s>>>(t.q, targets, n, S, t.g4, t.scalars);
         k_delta3_full<<<dim3((S + 127) / 128, DQ_K4), 128, 0, s>>>(t.g4, d.w[3], t.h3t, n, S, t.d3, t.d3t);
         k_dw4_full<<<dim3((DQ_H3 + 1 + 7) / 8, DQ_OUT), 256, 0, s>>>(t.g4, t.h3t, n, S, t.gw[3], t.gb[3]);
-    } else
-        k_delta3<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, s>>>(t.q, actions, targets, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+    } else {
+        DqnTdParams td{}; if (tdp) td = *tdp;
+        k_delta3<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, s>>>(t.q, actions, const_cast<float*>(targets), td, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+    }
     // The weight-gradient products need only the deltas of their own layer, not the rest of the data path: they run on a side stream
     // (forked and joined with events, which also works inside a stream capture: the captured graph gets the parallel branches), so
     // the chain the step waits for is  d3 -> p2 -> d2 -> p1 -> d1 -> dG  with dW3, dW2 beside it.
@@ -926,30 +1044,29 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     DQ_CK(cudaEventRecord(t.ev[0], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[0], 0));
     rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, t.side); if (rc) return rc;                 // [208 x S] x [304 x S]^T
     rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, S, S, DQ_N2, DQ_K4, 1, s, 1); if (rc) return rc;                    // [S x 208] x [304 x 208]^T, stored [304][S]
-    // (the mask + bf16 conversion stays a launch of its own: fused into the GEMM's epilogue it ran on the GEMM's 64 CTAs instead of ~10 k blocks, 141 -> 191 us per step)
-    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K3), 128, 0, s>>>(t.p2, S, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
+    // (the mask + bf16 conversion stays a launch of its own: fused into the GEMM's epilogue it ran on the GEMM's 64 CTAs, 141 -> 191 us per step)
+    k_delta_hidden<<<dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K3 + DH_FEATS - 1) / DH_FEATS), 256, 0, s>>>(t.p2, S, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
     DQ_CK(cudaEventRecord(t.ev[1], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[1], 0));
     rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, t.side); if (rc) return rc;                 // [304 x S] x [208 x S]^T
     rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, S, S, DQ_N3, DQ_K3, 1, s, 1); if (rc) return rc;                    // [S x 304] x [208 x 304]^T, stored [208][S]
-    k_delta_hidden<<<dim3((S + 127) / 128, DQ_K2), 128, 0, s>>>(t.p1, S, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
+    k_delta_hidden<<<dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K2 + DH_FEATS - 1) / DH_FEATS), 256, 0, s>>>(t.p1, S, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
     rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
     DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
-    const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
-    k_collect_grads<<<(n_collect + 255) / 256, 256, 0, s>>>(t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.gw[0], t.gb[0], t.gw[1], t.gb[1], t.gw[2], t.gb[2]);
     if (allreduce) {
+        const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
+        k_collect_grads<<<(n_collect + 255) / 256, 256, 0, s>>>(t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.gw[0], t.gb[0], t.gw[1], t.gb[1], t.gw[2], t.gb[2]);
         if (allreduce(t.gall, (uint64_t)t.gall_count, 0, (void*)s, allreduce_user)) return -2;            // all eight gradient arrays at once (padding words are zero)
         if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
-    }
+        if (apply_update) k_sqnorm_all<<<SQN_BLOCKS, 256, 0, s>>>(segs, t.sq_partial);
+    } else
+        k_collect_norm<<<SQN_BLOCKS, 1024, 0, s>>>(segs, t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.sq_partial);
     if (!apply_update) return (int)cudaGetLastError();
-    k_sqnorm_all<<<SQN_BLOCKS, 256, 0, s>>>(segs, t.sq_partial);
     t.step++;
-    k_adam_tick<<<1, 32, 0, s>>>(t.scalars, t.lr, t.beta1, t.beta2, loss_total, t.sq_partial);
-    k_adam_all<<<(segs.start[8] + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.clip, t.beta1, t.beta2, t.eps);
-    // operands for the next forward / backward: layer-1 rank-3 form, packed bf16 weights, the two transposes
-    k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);
+    // Adam on all parameters; operands for the next forward / backward refreshed in the same launch (layer-1 rank-3 form, packed bf16 weights, the two transposes)
     {
-        const int total = DQ_N2 * DQ_K2 + DQ_N3 * DQ_K3 + DQ_N4 * DQ_K4 + DQ_N2 * DQ_K2 + DQ_N3 * DQ_K3;
-        k_pack_all<<<(total + 255) / 256, 256, 0, s>>>(d.w[1], d.w[2], d.w[3], d.w2p, d.w3p, d.w4p, t.w3t, t.w2t);
+        const int rest = segs.start[8] - segs.start[2];
+        k_adam_fused<<<ADAM_ROW_BLOCKS + (rest + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.sq_partial, loss_total, t.lr, t.clip, t.beta1, t.beta2, t.eps, d.vertices, d.k_in, d.c1, d.m1,
+                                                                          d.w2p, d.w3p, d.w4p, t.w3t, t.w2t);
     }
     return (int)cudaGetLastError();
 }

@@ -69,10 +69,14 @@ struct DqnTrain {
     unsigned long long step = 0;
     bool transposes_fresh = false;                  // W3^T / W2^T match the current parameters (k_pack_all refreshes them after every update)
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
-    cudaStream_t side = nullptr; cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };      // the weight-gradient GEMMs run beside the data path
+    cudaStream_t side = nullptr; cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };      // the weight-gradient GEMMs and the step's zeroing run beside the data path
+    bool begun = false;                             // dqn_train_begin has been enqueued for the step dqn_train_batch is about to run
 };
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
 void dqn_train_free(DqnTrain& t);
+// TD targets derived inside the output-layer delta kernel (q_next null: targets are read from the array instead)
+struct DqnTdParams { const float* q_next; int q_stride; const uint32_t* state; const float* reward; const float* discount; };
+void dqn_upload_cell_cos(const float* cos144);
 // One optimiser step on a batch (G/deep_learning/neural_q_pathtracer.cu:476-512): forward with kept activations, loss
 // sum_b (target_b - Q(s_b)[a_b])^2, backward, Adam update, operands refreshed. pos/actions/targets are device pointers.
 // all-reduce hook (may be null): sums the gradient buffers across ranks before the update.
@@ -80,7 +84,9 @@ typedef int (*dqn_allreduce_fn)(void* d_buf, uint64_t count, int dtype, void* cu
 int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* actions, const float* targets, int n, bool apply_update,
                     dqn_allreduce_fn allreduce, void* allreduce_user, cudaStream_t s, bool all_outputs = false,    // all_outputs: targets is [n][144], the supervised loss over every output (actions unused)
                     float* loss_total = nullptr,                                                                   // device scalar the step's loss is added to (may be null)
-                    bool forward_done = false);                                                                    // the caller already ran the kept-activation forward into t.q / t.h*t (dqn_train_forward_params)
+                    bool forward_done = false,                                                                     // the caller already ran the kept-activation forward into t.q / t.h*t (dqn_train_forward_params)
+                    const DqnTdParams* tdp = nullptr);                                                             // TD targets from the next states' Q values, computed in the step (targets: where they are stored)
+int dqn_train_begin(DqnDev& d, DqnTrain& t, const float4* pos, int n, bool advance, cudaStream_t s);              // optional: the step's zeroing / batch inputs enqueued beside the caller's own forward launch
 DqnFwdParams dqn_train_forward_params(const DqnDev& d, DqnTrain& t, const float4* pos, int n);   // the forward a training step starts with, for callers that merge it with another batch                                                                  // device scalar the step's loss is added to (may be null)
 int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s);                     // allocations, first transposes, side stream: call before capturing a step
 int dqn_alloc(DqnDev& d, int k_in);
