@@ -26,6 +26,10 @@ namespace rlpt {
 
 #define DQ_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+// Programmatic dependent launch (the optimiser step is a chain of small kernels): a kernel launched with the programmatic-serialisation attribute
+// may become resident while its predecessor still runs; it waits here before it touches anything the predecessor produces, and only then lets
+// ITS successor in (so at most two kernels of the chain hold SM resources at a time). Without the attribute both instructions fall through.
+#define RLPT_PDL_SYNC() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
     const int t = threadIdx.x, warp = t >> 5;
 
     // layer-1 constants as one float4 (c1, M1 row) per output: the shared-memory pipe takes one instruction per cycle, broadcast or not
+    RLPT_PDL_SYNC();
     // Unit DQ_H1 of layer 1 and unit DQ_H2 of layer 2 (padding: their weights are zero in both directions) are constant one: the kept activations then carry
     // the "ones" row that makes the weight-gradient GEMMs of the backward pass produce the bias gradients as well.
     for (int i = t; i < DQ_K2; i += DQ_THREADS) s_l1[i] = i < DQ_H1 ? make_float4(p.c1[i], p.m1[3 * i], p.m1[3 * i + 1], p.m1[3 * i + 2]) : make_float4(i == DQ_H1 ? 1.f : 0.f, 0.f, 0.f, 0.f);
@@ -573,15 +578,16 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool vali
 // c_t != 0: C is stored transposed, C[n][m] with row length ldc -- a warp's 32 threads (one output row each) then write consecutive addresses,
 // and the consumer of the backward data path (k_delta_hidden, feature-major) reads them the same way.
 __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_bf16_tn(const __nv_bfloat16* __restrict__ A, int lda, const __nv_bfloat16* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                                 int M, int N, int K, int k_per_split, int c_t) {
+                                                                 int M, int N, int K, int k_per_split, int c_t, int bn_tile) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GM_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int t = threadIdx.x, warp = t >> 5;
-    const int m0 = blockIdx.x * DQ_TILE, n0 = blockIdx.y * GM_BN, bn = min(GM_BN, N - n0);
+    const int m0 = blockIdx.x * DQ_TILE, n0 = blockIdx.y * bn_tile, bn = min(bn_tile, N - n0);
     const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
     const int kk = (k_end - k_begin + 15) & ~15, pk = kk >> 3;            // this CTA's K, padded to the MMA's K step; 16-byte pieces per row
     uint8_t* sa = smem + GM_A; uint8_t* sb = smem + GM_B;
+    RLPT_PDL_SYNC();
     for (int idx = t; idx < DQ_TILE * pk; idx += GM_THREADS) {
         const int row = idx / pk, j = idx - row * pk, m = m0 + row, k = k_begin + 8 * j;
         const bool ok = m < M && k < k_end;
@@ -614,22 +620,34 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_gemm_bf16_tn(const __nv_bfloa
             if (m < M) {
                 float* dst = c_t ? C + (size_t)(n0 + c0) * ldc + m : C + (size_t)m * ldc + n0 + c0;
                 const size_t step = c_t ? (size_t)ldc : 1;
+                if (split && !c_t) {                                         // 16 consecutive floats of one row: four 16-byte vector reductions instead of sixteen scalar ones
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j * step, __uint_as_float(r[j])); else dst[j * step] = __uint_as_float(r[j]); }
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { if (split) atomicAdd(dst + j * step, __uint_as_float(r[j])); else dst[j * step] = __uint_as_float(r[j]); }
+                }
             }
         }
     }
     tc_fence_before(); __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
-static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s, int c_t = 0) {
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{}; cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+static int gemm_tn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, float* C, int ldc, int M, int N, int K, int k_splits, cudaStream_t s, int c_t = 0, bool pdl = false, int bn_tile = GM_BN) {
     const int k_cap = 256;                                                 // K per CTA when K has to be split (<= GM_KMAX)
     if (k_splits < (K + GM_KMAX - 1) / GM_KMAX) k_splits = (K + k_cap - 1) / k_cap;
     int k_per = ((K + k_splits - 1) / k_splits + 15) / 16 * 16; if (k_per > GM_KMAX) k_per = k_cap; if (k_per < 16) k_per = 16;
     const int zs = (K + k_per - 1) / k_per;
-    dim3 grid((M + DQ_TILE - 1) / DQ_TILE, (N + GM_BN - 1) / GM_BN, zs);
-    k_gemm_bf16_tn<<<grid, GM_THREADS, GM_TOTAL, s>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per, c_t);
-    return (int)cudaGetLastError();
+    dim3 grid((M + DQ_TILE - 1) / DQ_TILE, (N + bn_tile - 1) / bn_tile, zs);
+    return (int)launch_ex(pdl, k_gemm_bf16_tn, grid, dim3(GM_THREADS), GM_TOTAL, s, A, lda, B, ldb, C, ldc, M, N, K, k_per, c_t, bn_tile);
 }
 
 // ------------------------------------------------------------------------------------------------ element-wise pieces
@@ -641,7 +659,7 @@ __global__ void k_transpose_bf16(const float* __restrict__ w, int rows, int cols
 }
 // (k_step_begin, below the parameter segment table, prepares a step: zeroing + the batch inputs of the gradient GEMMs)
 // output-layer delta (one action per ray): g = d/dq (target - q_a)^2 * relu'(q_a); delta3 = g W4[a, :] relu'(h3);
-// dW4[a, :] += g h3, db4[a] += g; loss accumulated. One CTA per 32 rays x all 208 hidden units: the feature-major arrays (h3t, d3t) are
+// db4[a] += g; loss accumulated (dW4: k_dw4_rank1). One CTA per 32 rays x all 208 hidden units: the feature-major arrays (h3t, d3t) are
 // walked with the ray index fastest, the ray-major d3 is written from a shared-memory tile with the unit index fastest -- every access
 // coalesced. (One thread per ray walking 208 units, the first form of this kernel, took 125 us of a 270 us optimiser step.)
 constexpr int D3_RAYS = 32;
@@ -652,11 +670,12 @@ void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos
 // instead of reading them from a kernel of its own (8 us of a 130 us optimiser step).
 __global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, const uint32_t* __restrict__ actions, float* __restrict__ targets, DqnTdParams tdp, int n, int S,
                                                 const float* __restrict__ w4, const __nv_bfloat16* __restrict__ h3t, __nv_bfloat16* __restrict__ d3, __nv_bfloat16* __restrict__ d3t,
-                                                float* __restrict__ gw4, float* __restrict__ gb4, float* __restrict__ scalars) {
+                                                float* __restrict__ g_out, float* __restrict__ gb4, float* __restrict__ scalars) {
     __shared__ __nv_bfloat16 tile[D3_RAYS][DQ_K4 + 2];                   // + 2: rows 105 words apart, conflict-free column writes
     __shared__ float s_g[D3_RAYS]; __shared__ int s_a[D3_RAYS]; __shared__ float s_best[8][D3_RAYS];
     const int i0 = blockIdx.x * D3_RAYS, tid = threadIdx.x;
     const int ii = tid & 31, jj = tid >> 5, i = i0 + ii;
+    RLPT_PDL_SYNC();
     if (tdp.q_next) {
         float best = 0.f;
         if (i < n) {
@@ -683,6 +702,7 @@ __global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, con
             if (g != 0.f) atomicAdd(gb4 + a, g);
         }
         s_g[tid] = g; s_a[tid] = a;
+        if (i < S) g_out[i] = g;
         for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
         if (tid == 0 && loss != 0.f) atomicAdd(scalars, loss);
     }
@@ -695,10 +715,23 @@ __global__ void __launch_bounds__(256) k_delta3(const float* __restrict__ q, con
         const __nv_bfloat16 db = __float2bfloat16_rn(on ? g * __ldg(w4 + (size_t)a * DQ_H3 + j) : 0.f);
         if (i < S) d3t[(size_t)j * S + i] = db;
         tile[ii][j] = db;
-        if (on) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
     }
     __syncthreads();
     for (int r = 0; r < D3_RAYS; ++r) if (tid < DQ_K4 && i0 + r < S) d3[(size_t)(i0 + r) * DQ_K4 + tid] = tile[r][tid];
+}
+// dW4[a, :] += g h3 (rank-1 per ray, scatter-added): off the step's critical path -- it runs beside the data path and is only needed when the
+// gradients are collected. g_in: the per-ray output-layer gradient k_delta3 left behind.
+__global__ void __launch_bounds__(256) k_dw4_rank1(const float* __restrict__ g_in, const uint32_t* __restrict__ actions, int n, int S, const __nv_bfloat16* __restrict__ h3t, float* __restrict__ gw4) {
+    const int i = blockIdx.x * D3_RAYS + (threadIdx.x & 31), jj = threadIdx.x >> 5;
+    if (i >= n) return;
+    const float g = g_in[i];
+    if (g == 0.f) return;
+    const int a = (int)actions[i];
+#pragma unroll 5
+    for (int j = jj; j < DQ_H3; j += 8) {
+        const float h = __bfloat162float(h3t[(size_t)j * S + i]);
+        if (h > 0.f) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
+    }
 }
 // Supervised variant (NN_Q_Value_Trainer/Source/main.cu:110-117: loss = sum_batches squared_distance(targets, Q(s)) over ALL
 // 144 outputs): the output-layer gradient is dense. g[i][a] = 2 (q_a - y_a) relu'(q_a); one thread per (ray, action).
@@ -738,6 +771,7 @@ __global__ void __launch_bounds__(256) k_delta_hidden(const float* __restrict__ 
                                                       __nv_bfloat16* __restrict__ d_ray, __nv_bfloat16* __restrict__ d_feat) {
     __shared__ __nv_bfloat16 tile[DH_RAYS][DH_FEATS + 2];                // rows 33 words apart: conflict-free both ways
     const int i0 = blockIdx.x * DH_RAYS, f0 = blockIdx.y * DH_FEATS, lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = i0 + lane;
+    RLPT_PDL_SYNC();
 #pragma unroll
     for (int q = 0; q < DH_FEATS / 8; ++q) {
         const int fl = w + 8 * q, j = f0 + fl;
@@ -830,6 +864,7 @@ __global__ void __launch_bounds__(1024) k_collect_norm(ParamSegs t, const float*
                                                       float* __restrict__ partial) {
     __shared__ float s_w[32];
     float acc = 0.f; const int total = t.start[8];
+    RLPT_PDL_SYNC();
 #pragma unroll 2
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int s = seg_of(t, i), j = i - t.start[s];
@@ -863,6 +898,7 @@ __global__ void __launch_bounds__(256) k_adam_fused(ParamSegs t, float* __restri
     __shared__ float s_n2; __shared__ float s_red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool rows = blockIdx.x < ADAM_ROW_BLOCKS;
+    RLPT_PDL_SYNC();
     // this thread's elements: their gradient and moments are requested before the CTA turns to the norm (everything here is latency)
     int seg[ADAM_ROW_ITEMS], idx[ADAM_ROW_ITEMS]; float g[ADAM_ROW_ITEMS], mm[ADAM_ROW_ITEMS], vv[ADAM_ROW_ITEMS], xx[ADAM_ROW_ITEMS], vin[ADAM_ROW_ITEMS];
     int n_items = 0;
@@ -946,7 +982,7 @@ void dqn_train_free(DqnTrain& t) {
     cudaFree(t.gall); cudaFree(t.sq_partial);
     for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
-    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
+    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
     if (t.side) cudaStreamDestroy(t.side);
     for (cudaEvent_t e : t.ev) if (e) cudaEventDestroy(e);
     t = DqnTrain{};
@@ -973,10 +1009,10 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
         t.step = 0;
     }
     if (S > t.capacity) {
-        cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt); cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q);
+        cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt); cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q);
         DQ_CK(cudaMalloc(&t.h1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.h2t, 2 * (size_t)DQ_K3 * S)); DQ_CK(cudaMalloc(&t.h3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.xt, 2 * (size_t)16 * S));
         DQ_CK(cudaMalloc(&t.d3, 2 * (size_t)S * DQ_K4)); DQ_CK(cudaMalloc(&t.d2, 2 * (size_t)S * DQ_K3)); DQ_CK(cudaMalloc(&t.d3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.d2t, 2 * (size_t)DQ_K3 * S));
-        DQ_CK(cudaMalloc(&t.d1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.p2, 4 * (size_t)S * DQ_N2)); DQ_CK(cudaMalloc(&t.p1, 4 * (size_t)S * DQ_N3)); DQ_CK(cudaMalloc(&t.q, 4 * (size_t)DQ_OUT * S));
+        DQ_CK(cudaMalloc(&t.d1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.g3, 4 * (size_t)S)); DQ_CK(cudaMalloc(&t.p2, 4 * (size_t)S * DQ_N2)); DQ_CK(cudaMalloc(&t.p1, 4 * (size_t)S * DQ_N3)); DQ_CK(cudaMalloc(&t.q, 4 * (size_t)DQ_OUT * S));
         t.capacity = S;
     }
     return 0;
@@ -998,6 +1034,7 @@ int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {          
     int rc = dqn_train_alloc(t, d, n); if (rc) return rc;
     if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }
     if (!t.side) {
+        if (const char* e = getenv("RLPT_NQ_PDL")) t.pdl = atoi(e) != 0;
         DQ_CK(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking));
         for (cudaEvent_t& e : t.ev) DQ_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
@@ -1024,6 +1061,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     t.begun = false;
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     const ParamSegs segs = param_segs(d, t);
+    const bool pdl = t.pdl && !all_outputs;
     // forward, activations kept
     if (!forward_done) { const DqnFwdParams fp = dqn_train_forward_params(d, t, pos, n); rc = dqn_forward(d, fp, s); if (rc) return rc; }
     DQ_CK(cudaStreamWaitEvent(s, t.ev[4], 0));                              // the zeroing and the batch inputs are in place
@@ -1035,22 +1073,25 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         k_dw4_full<<<dim3((DQ_H3 + 1 + 7) / 8, DQ_OUT), 256, 0, s>>>(t.g4, t.h3t, n, S, t.gw[3], t.gb[3]);
     } else {
         DqnTdParams td{}; if (tdp) td = *tdp;
-        k_delta3<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, s>>>(t.q, actions, const_cast<float*>(targets), td, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.gw[3], t.gb[3], t.scalars);
+        DQ_CK(launch_ex(pdl, k_delta3, dim3((S + D3_RAYS - 1) / D3_RAYS), dim3(256), 0, s, t.q, actions, const_cast<float*>(targets), td, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.g3, t.gb[3], t.scalars));
     }
     // The weight-gradient products need only the deltas of their own layer, not the rest of the data path: they run on a side stream
     // (forked and joined with events, which also works inside a stream capture: the captured graph gets the parallel branches), so
     // the chain the step waits for is  d3 -> p2 -> d2 -> p1 -> d1 -> dG  with dW3, dW2 beside it.
     const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
+    static const int bn_env = getenv("RLPT_GM_BN") ? atoi(getenv("RLPT_GM_BN")) : 80;     // output columns per CTA of the two data-path GEMMs (80: 128 CTAs at batch 4096)
+    const int bn_data = (bn_env >= 16 && bn_env <= GM_BN && bn_env % 16 == 0) ? bn_env : GM_BN;
     DQ_CK(cudaEventRecord(t.ev[0], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[0], 0));
+    if (!all_outputs) k_dw4_rank1<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, t.side>>>(t.g3, actions, n, S, t.h3t, t.gw[3]);
     rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, t.side); if (rc) return rc;                 // [208 x S] x [304 x S]^T
-    rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, S, S, DQ_N2, DQ_K4, 1, s, 1); if (rc) return rc;                    // [S x 208] x [304 x 208]^T, stored [304][S]
+    rc = gemm_tn(t.d3, DQ_K4, t.w3t, DQ_K2, t.p2, S, S, DQ_N2, DQ_K4, 1, s, 1, pdl, bn_data); if (rc) return rc;                    // [S x 208] x [304 x 208]^T, stored [304][S]
     // (the mask + bf16 conversion stays a launch of its own: fused into the GEMM's epilogue it ran on the GEMM's 64 CTAs, 141 -> 191 us per step)
-    k_delta_hidden<<<dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K3 + DH_FEATS - 1) / DH_FEATS), 256, 0, s>>>(t.p2, S, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t);
+    DQ_CK(launch_ex(pdl, k_delta_hidden, dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K3 + DH_FEATS - 1) / DH_FEATS), dim3(256), 0, s, t.p2, S, t.h2t, S, DQ_H2, DQ_K3, t.d2, t.d2t));
     DQ_CK(cudaEventRecord(t.ev[1], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[1], 0));
     rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, t.side); if (rc) return rc;                 // [304 x S] x [208 x S]^T
-    rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, S, S, DQ_N3, DQ_K3, 1, s, 1); if (rc) return rc;                    // [S x 304] x [208 x 304]^T, stored [208][S]
-    k_delta_hidden<<<dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K2 + DH_FEATS - 1) / DH_FEATS), 256, 0, s>>>(t.p1, S, t.h1t, S, DQ_H1, DQ_K2, nullptr, t.d1t);
-    rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
+    rc = gemm_tn(t.d2, DQ_K3, t.w2t, DQ_K3, t.p1, S, S, DQ_N3, DQ_K3, 1, s, 1, pdl, bn_data); if (rc) return rc;                    // [S x 304] x [208 x 304]^T, stored [208][S]
+    DQ_CK(launch_ex(pdl, k_delta_hidden, dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K2 + DH_FEATS - 1) / DH_FEATS), dim3(256), 0, s, t.p1, S, t.h1t, S, DQ_H1, DQ_K2, (__nv_bfloat16*)nullptr, t.d1t));
+    rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s, 0, pdl); if (rc) return rc;                                // [208 x S] x [16 x S]^T
     DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
     if (allreduce) {
         const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
@@ -1059,14 +1100,14 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         if (allreduce(t.scalars, 1, 0, (void*)s, allreduce_user)) return -2;
         if (apply_update) k_sqnorm_all<<<SQN_BLOCKS, 256, 0, s>>>(segs, t.sq_partial);
     } else
-        k_collect_norm<<<SQN_BLOCKS, 1024, 0, s>>>(segs, t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.sq_partial);
+        DQ_CK(launch_ex(pdl, k_collect_norm, dim3(SQN_BLOCKS), dim3(1024), 0, s, segs, t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.sq_partial));
     if (!apply_update) return (int)cudaGetLastError();
     t.step++;
     // Adam on all parameters; operands for the next forward / backward refreshed in the same launch (layer-1 rank-3 form, packed bf16 weights, the two transposes)
     {
         const int rest = segs.start[8] - segs.start[2];
-        k_adam_fused<<<ADAM_ROW_BLOCKS + (rest + 255) / 256, 256, 0, s>>>(segs, t.scalars, t.sq_partial, loss_total, t.lr, t.clip, t.beta1, t.beta2, t.eps, d.vertices, d.k_in, d.c1, d.m1,
-                                                                          d.w2p, d.w3p, d.w4p, t.w3t, t.w2t);
+        DQ_CK(launch_ex(pdl, k_adam_fused, dim3(ADAM_ROW_BLOCKS + (rest + 255) / 256), dim3(256), 0, s, segs, t.scalars, t.sq_partial, loss_total, t.lr, t.clip, t.beta1, t.beta2, t.eps, d.vertices, d.k_in, d.c1, d.m1,
+                        d.w2p, d.w3p, d.w4p, t.w3t, t.w2t));
     }
     return (int)cudaGetLastError();
 }

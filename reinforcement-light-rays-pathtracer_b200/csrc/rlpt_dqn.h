@@ -62,6 +62,7 @@ struct DqnTrain {
     __nv_bfloat16 *w3t = nullptr, *w2t = nullptr;   // transposed bf16 copies: W3^T [304][208], W2^T [208][304]
     __nv_bfloat16 *h1t = nullptr, *h2t = nullptr, *h3t = nullptr, *xt = nullptr;
     __nv_bfloat16 *d3 = nullptr, *d2 = nullptr, *d3t = nullptr, *d2t = nullptr, *d1t = nullptr;
+    float* g3 = nullptr;                            // [S] per-ray output-layer gradient of the TD step (k_delta3 -> k_dw4_rank1)
     float *p2 = nullptr, *p1 = nullptr;             // pre-activation deltas [S][304], [S][208] (fp32 GEMM outputs)
     float* q = nullptr;                             // [144][S] predictions of the batch
     float* scalars = nullptr;                       // [0] loss sum, [1] squared gradient norm, [2] Adam step size, [3] Adam step count (kept on the device: graph replay)
@@ -70,6 +71,7 @@ struct DqnTrain {
     bool transposes_fresh = false;                  // W3^T / W2^T match the current parameters (k_pack_all refreshes them after every update)
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
     cudaStream_t side = nullptr; cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };      // the weight-gradient GEMMs and the step's zeroing run beside the data path
+    bool pdl = false;                               // programmatic dependent launch along the step's main chain (RLPT_NQ_PDL=1; measured: 100.9 -> 102.4 us per step, off)
     bool begun = false;                             // dqn_train_begin has been enqueued for the step dqn_train_batch is about to run
 };
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
