@@ -97,6 +97,14 @@ __host__ __device__ __forceinline__ size_t operand_offset(int row, int k, int k_
 #endif
 constexpr int DQ_KC = RLPT_DQN_KC;                                          // inputs per weight chunk
 constexpr int DQ_L2_SPLIT = 160;                                           // layer 2's first N part
+// The packed weights exist DQ_REPLICAS times in global memory (replica r at byte offset r * stride): CTA b streams replica b % DQ_REPLICAS. All CTAs of a
+// full-frame forward walk the chunk stream in step, so without replicas 148 SMs ask the same 128-byte lines of the same L2 slices at the same moment
+// (an A/B switch: it made no difference).
+#ifndef RLPT_DQN_REPLICAS
+#define RLPT_DQN_REPLICAS 1          // measured with 8: 186.3 vs 186.6 us per full-frame forward -- L2 line contention is not what paces the weight stream
+#endif
+constexpr int DQ_REPLICAS = RLPT_DQN_REPLICAS;
+constexpr size_t DQ_W2P_STRIDE = 2 * (size_t)DQ_N2 * DQ_K2 + 128 * 3, DQ_W3P_STRIDE = 2 * (size_t)DQ_N3 * DQ_K3 + 128 * 5, DQ_W4P_STRIDE = 2 * (size_t)DQ_N4 * DQ_K4 + 128 * 7;       // bytes; odd multiples of a line apart
 __host__ __device__ __forceinline__ size_t wpack_offset(int n_split, int row, int k, int n_pad, int k_pad) {
     const int n0 = (n_split > 0 && row >= n_split) ? n_split : 0, rows = n_split > 0 ? (row >= n_split ? n_pad - n_split : n_split) : n_pad;
     const int kc = k / DQ_KC, kw = min(DQ_KC, k_pad - kc * DQ_KC), r = row - n0, kk = k - kc * DQ_KC;
@@ -149,19 +157,19 @@ constexpr int DQ_COMPUTE_THREADS = DQ_EPI_THREADS + 32, DQ_THREADS = DQ_EPI_THRE
 
 struct ChunkInfo { const __nv_bfloat16* src; int rows, kw, kc, last, part; uint32_t a_off, a_kpad, tmem_col; };
 __device__ __forceinline__ ChunkInfo chunk_info(const DqnFwdParams& p, int s) {          // s = position in the tile's stream, 0..16
-    ChunkInfo ci;
+    ChunkInfo ci; const size_t rep = blockIdx.x % DQ_REPLICAS;       // (strides are in bytes, pointers in bf16)
     if (s < 2 * DQ_NKC2) {
         const int part = s >= DQ_NKC2 ? 1 : 0, kc = s - part * DQ_NKC2, n0 = part ? DQ_L2_SPLIT : 0;
         ci.rows = part ? DQ_N2 - DQ_L2_SPLIT : DQ_L2_SPLIT; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K2 - kc * DQ_KC); ci.last = kc == DQ_NKC2 - 1; ci.part = part;
-        ci.src = p.w2p + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
+        ci.src = p.w2p + rep * (DQ_W2P_STRIDE / 2) + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
     } else if (s < 2 * DQ_NKC2 + DQ_NKC3) {
         const int kc = s - 2 * DQ_NKC2;
         ci.rows = DQ_N3; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K3 - kc * DQ_KC); ci.last = kc == DQ_NKC3 - 1; ci.part = 0;
-        ci.src = p.w3p + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
+        ci.src = p.w3p + rep * (DQ_W3P_STRIDE / 2) + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
     } else {
         const int kc = s - 2 * DQ_NKC2 - DQ_NKC3;
         ci.rows = DQ_N4; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K4 - kc * DQ_KC); ci.last = kc == DQ_NKC4 - 1; ci.part = 0;
-        ci.src = p.w4p + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
+        ci.src = p.w4p + rep * (DQ_W4P_STRIDE / 2) + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
     }
     return ci;
 }
@@ -430,12 +438,13 @@ int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ operands from parameters
 // one thread per packed element: bf16 copy of W [n][k] (row-major fp32, n x k) into the canonical [n_pad][k_pad] operand, zero padding
-__global__ void k_pack_weights(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* __restrict__ out) {
+__global__ void k_pack_weights(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* __restrict__ out, size_t rep_stride) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad * k_pad) return;
     int row = i / k_pad, col = i % k_pad;
     float v = (row < n && col < k) ? w[(size_t)row * k + col] : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + wpack_offset(n_split, row, col, n_pad, k_pad)) = __float2bfloat16_rn(v);
+    const size_t off = wpack_offset(n_split, row, col, n_pad, k_pad);
+    for (int r = 0; r < DQ_REPLICAS; ++r) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + r * rep_stride + off) = __float2bfloat16_rn(v);
 }
 // c1 = b1 + W1 v, M1[:, d] = sum_{i % 3 == d} W1[:, i]; one warp per output row, fp32 with pairwise lane sums
 __global__ void k_layer1_operands(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ v, int k_in, float* __restrict__ c1, float* __restrict__ m1) {
@@ -449,9 +458,9 @@ __global__ void k_layer1_operands(const float* __restrict__ w1, const float* __r
 
 int dqn_refresh_operands(DqnDev& d, cudaStream_t s) {
     k_layer1_operands<<<(DQ_H1 + 7) / 8, 256, 0, s>>>(d.w[0], d.b[0], d.vertices, d.k_in, d.c1, d.m1);
-    k_pack_weights<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N2, DQ_K2, DQ_L2_SPLIT, d.w2p);
-    k_pack_weights<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N3, DQ_K3, 0, d.w3p);
-    k_pack_weights<<<(DQ_N4 * DQ_K4 + 255) / 256, 256, 0, s>>>(d.w[3], DQ_OUT, DQ_H3, DQ_N4, DQ_K4, 0, d.w4p);
+    k_pack_weights<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N2, DQ_K2, DQ_L2_SPLIT, d.w2p, DQ_W2P_STRIDE);
+    k_pack_weights<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N3, DQ_K3, 0, d.w3p, DQ_W3P_STRIDE);
+    k_pack_weights<<<(DQ_N4 * DQ_K4 + 255) / 256, 256, 0, s>>>(d.w[3], DQ_OUT, DQ_H3, DQ_N4, DQ_K4, 0, d.w4p, DQ_W4P_STRIDE);
     return (int)cudaGetLastError();
 }
 
@@ -466,7 +475,7 @@ int dqn_alloc(DqnDev& d, int k_in) {
     DqnHost shape; shape.k_in = k_in;
     for (int l = 0; l < 4; ++l) { DQ_CK(cudaMalloc(&d.w[l], sizeof(float) * (size_t)DqnHost::rows(l) * shape.cols(l))); DQ_CK(cudaMalloc(&d.b[l], sizeof(float) * DqnHost::rows(l))); }
     DQ_CK(cudaMalloc(&d.vertices, sizeof(float) * (size_t)k_in)); DQ_CK(cudaMalloc(&d.c1, sizeof(float) * DQ_H1)); DQ_CK(cudaMalloc(&d.m1, sizeof(float) * DQ_H1 * 3));
-    DQ_CK(cudaMalloc(&d.w2p, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&d.w3p, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&d.w4p, 2 * (size_t)DQ_N4 * DQ_K4));
+    DQ_CK(cudaMalloc(&d.w2p, DQ_REPLICAS * DQ_W2P_STRIDE)); DQ_CK(cudaMalloc(&d.w3p, DQ_REPLICAS * DQ_W3P_STRIDE)); DQ_CK(cudaMalloc(&d.w4p, DQ_REPLICAS * DQ_W4P_STRIDE));
     return 0;
 }
 int dqn_upload(DqnDev& d, const DqnHost& h, const float* vertices, cudaStream_t s) {
@@ -964,9 +973,9 @@ __global__ void __launch_bounds__(256) k_adam_fused(ParamSegs t, float* __restri
     const float x = adam(g[0], mm[0], vv[0], xx[0]);
     t.m[s][j] = mm[0]; t.v[s][j] = vv[0]; t.x[s][j] = x;
     const __nv_bfloat16 xb = __float2bfloat16_rn(x);
-    if (s == 2) { const int r = j / DQ_H1, c = j - r * DQ_H1; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2p) + wpack_offset(DQ_L2_SPLIT, r, c, DQ_N2, DQ_K2)) = xb; if (w2t) w2t[(size_t)c * DQ_K3 + r] = xb; }
-    else if (s == 4) { const int r = j / DQ_H2, c = j - r * DQ_H2; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3p) + wpack_offset(0, r, c, DQ_N3, DQ_K3)) = xb; if (w3t) w3t[(size_t)c * DQ_K2 + r] = xb; }
-    else if (s == 6) { const int r = j / DQ_H3, c = j - r * DQ_H3; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w4p) + wpack_offset(0, r, c, DQ_N4, DQ_K4)) = xb; }
+    if (s == 2) { const int r = j / DQ_H1, c = j - r * DQ_H1; { const size_t o = wpack_offset(DQ_L2_SPLIT, r, c, DQ_N2, DQ_K2); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2p) + q * DQ_W2P_STRIDE + o) = xb; } if (w2t) w2t[(size_t)c * DQ_K3 + r] = xb; }
+    else if (s == 4) { const int r = j / DQ_H2, c = j - r * DQ_H2; { const size_t o = wpack_offset(0, r, c, DQ_N3, DQ_K3); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3p) + q * DQ_W3P_STRIDE + o) = xb; } if (w3t) w3t[(size_t)c * DQ_K2 + r] = xb; }
+    else if (s == 6) { const int r = j / DQ_H3, c = j - r * DQ_H3; { const size_t o = wpack_offset(0, r, c, DQ_N4, DQ_K4); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w4p) + q * DQ_W4P_STRIDE + o) = xb; } }
 }
 static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
     ParamSegs p{}; DqnHost shape; shape.k_in = d.k_in; int at = 0;
