@@ -111,6 +111,8 @@ __host__ __device__ __forceinline__ size_t wpack_offset(int n_split, int row, in
     return (size_t)n0 * k_pad * 2 + (size_t)rows * DQ_KC * 2 * kc + (size_t)(r >> 3) * ((size_t)kw * 16) + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
 }
 
+__constant__ float c_dq_cos[DQ_OUT];                                     // cos(theta) of the 144 grid cells (the tracer's table; dqn_upload_cell_cos)
+void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos144, sizeof(float) * DQ_OUT); }
 // ------------------------------------------------------------------------------------------------ forward kernel
 constexpr int DQ_STAGES = RLPT_DQN_STAGES;
 constexpr uint32_t DQ_STAGE_BYTES = DQ_N3 * DQ_KC * 2;                     // largest chunk: layer 3, 208 rows x 64 inputs
@@ -156,20 +158,20 @@ constexpr int DQ_COMPUTE_THREADS = DQ_EPI_THREADS + 32, DQ_THREADS = DQ_EPI_THRE
 #endif
 
 struct ChunkInfo { const __nv_bfloat16* src; int rows, kw, kc, last, part; uint32_t a_off, a_kpad, tmem_col; };
-__device__ __forceinline__ ChunkInfo chunk_info(const DqnFwdParams& p, int s) {          // s = position in the tile's stream, 0..16
+__device__ __forceinline__ ChunkInfo chunk_info(const __nv_bfloat16* w2p, const __nv_bfloat16* w3p, const __nv_bfloat16* w4p, int s) {          // s = position in the tile's stream, 0..16
     ChunkInfo ci; const size_t rep = blockIdx.x % DQ_REPLICAS;       // (strides are in bytes, pointers in bf16)
     if (s < 2 * DQ_NKC2) {
         const int part = s >= DQ_NKC2 ? 1 : 0, kc = s - part * DQ_NKC2, n0 = part ? DQ_L2_SPLIT : 0;
         ci.rows = part ? DQ_N2 - DQ_L2_SPLIT : DQ_L2_SPLIT; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K2 - kc * DQ_KC); ci.last = kc == DQ_NKC2 - 1; ci.part = part;
-        ci.src = p.w2p + rep * (DQ_W2P_STRIDE / 2) + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
+        ci.src = w2p + rep * (DQ_W2P_STRIDE / 2) + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
     } else if (s < 2 * DQ_NKC2 + DQ_NKC3) {
         const int kc = s - 2 * DQ_NKC2;
         ci.rows = DQ_N3; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K3 - kc * DQ_KC); ci.last = kc == DQ_NKC3 - 1; ci.part = 0;
-        ci.src = p.w3p + rep * (DQ_W3P_STRIDE / 2) + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
+        ci.src = w3p + rep * (DQ_W3P_STRIDE / 2) + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
     } else {
         const int kc = s - 2 * DQ_NKC2 - DQ_NKC3;
         ci.rows = DQ_N4; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K4 - kc * DQ_KC); ci.last = kc == DQ_NKC4 - 1; ci.part = 0;
-        ci.src = p.w4p + rep * (DQ_W4P_STRIDE / 2) + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
+        ci.src = w4p + rep * (DQ_W4P_STRIDE / 2) + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
     }
     return ci;
 }
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
     for (int i = t; i < DQ_N4; i += DQ_THREADS) s_b4[i] = i < DQ_OUT ? p.b4[i] : 0.f;
     ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
     if (t < DQ_CHUNKS_PER_TILE) {
-        const ChunkInfo ci = chunk_info(p, t);
+        const ChunkInfo ci = chunk_info(p.w2p, p.w3p, p.w4p, t);
         const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.kc * (DQ_KC * 16u);
         ChunkRow cr;
         cr.src_lo = (uint32_t)reinterpret_cast<uint64_t>(ci.src); cr.src_hi = (uint32_t)(reinterpret_cast<uint64_t>(ci.src) >> 32); cr.bytes = (uint32_t)ci.rows * (uint32_t)ci.kw * 2u;
@@ -426,13 +428,219 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
 }
 
 int dqn_gemm_set_smem_limit();
-int dqn_set_smem_limit() { int rc = (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); return rc ? rc : dqn_gemm_set_smem_limit(); }
+__global__ void k_dqn_backward(const __grid_constant__ DqnBwdParams p);
+int dqn_set_smem_limit() {
+    int rc = (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_dqn_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    return rc ? rc : dqn_gemm_set_smem_limit();
+}
 
 int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
     if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
     int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
     k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ backward data path, one kernel
+// The TD step's backward data path for a tile of 128 rays, in k_dqn_forward's own shape (same warp roles, chunk stream, stages, barriers):
+//   phase 0   TD target (max over the next state's Q cos(theta), four threads per ray), output-layer gradient g, delta3 = g W4[a, :] relu'(h3) written as
+//             the bf16 A operand (and feature-major to HBM for the weight-gradient GEMM), dW4 / db4 / loss scatter-added
+//   P2        delta3 [128 x 208] x (W3^T)^T on the tensor cores (W3^T packed like the forward's layer 2: two N parts x four K chunks) -> TMEM [0, 304)
+//             epilogue: relu'(h2) mask -> bf16 A operand of the next product + d2t in HBM
+//   P1        delta2 [128 x 304] x (W2^T)^T (packed like the forward's layer 3) -> TMEM [304, 512); epilogue: relu'(h1) mask -> d1t in HBM
+// It replaces k_delta3, two data GEMMs and two mask kernels (43 us of a 92 us optimiser step) -- the activations never leave the SM between the products.
+constexpr int DQ_BWD_CHUNKS = 2 * DQ_NKC2 + DQ_NKC3;
+static_assert(DQ_REPLICAS == 1, "the packed transposes of k_dqn_backward have no replicas");
+template <int NC>
+__device__ __forceinline__ void bwd_block(uint8_t* smem, const uint32_t* r, uint32_t mbits, int c0, bool write_a, uint32_t a_next_off, int k_pad_next, int row, __nv_bfloat16* out, int S, int ray) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        __nv_bfloat162 pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = ((mbits >> (8 * q + 2 * j)) & 1u) ? __uint_as_float(r[8 * q + 2 * j]) : 0.f, b = ((mbits >> (8 * q + 2 * j + 1)) & 1u) ? __uint_as_float(r[8 * q + 2 * j + 1]) : 0.f;
+            pk[j] = __floats2bfloat162_rn(a, b);
+        }
+        if (write_a) *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0 + 8 * q, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[0]);
+        __nv_bfloat16* op = out + (size_t)(c0 + 8 * q) * S + ray;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { op[0] = pk[j].x; op[S] = pk[j].y; op += 2 * (size_t)S; }
+    }
+}
+__device__ __forceinline__ void bwd_epilogue(uint8_t* smem, uint64_t* part_done, uint32_t done_par, int n_split, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad, int n_feat,
+                                             const __nv_bfloat16* __restrict__ mask_src, bool write_a, uint32_t a_next_off, int k_pad_next, int row, int grp, __nv_bfloat16* out, int S, int ray) {
+    const int n_blocks = (n_pad + 31) / 32;
+    for (int b = grp; b < n_blocks; b += DQ_EPI_GROUPS) {
+        const int c0 = 32 * b, c = (n_split > 0 && c0 >= n_split) ? 1 : 0, nc = min(32, n_pad - c0);
+        uint32_t mbits = 0;                                                // relu'(h) of this block's units, requested before the product is waited for
+        {   // all 32 loads first, then the bits: with load and test in one loop the compiler chained them (one memory round trip per unit: 62 us per launch)
+            const unsigned short* ms = reinterpret_cast<const unsigned short*>(mask_src) + (size_t)c0 * S + ray;
+            unsigned short hb[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) hb[e] = (e < nc && c0 + e < n_feat) ? __ldg(ms + (size_t)e * S) : (unsigned short)0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mbits |= (hb[e] != 0 && hb[e] < 0x8000u) ? (1u << e) : 0u;
+        }
+        mbar_wait(&part_done[c], (done_par >> c) & 1u); tc_fence_after();
+        uint32_t r[32];
+        if (nc == 32) { tmem_ld32_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait(); bwd_block<32>(smem, r, mbits, c0, write_a, a_next_off, k_pad_next, row, out, S, ray); }
+        else { tmem_ld16_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait(); bwd_block<16>(smem, r, mbits, c0, write_a, a_next_off, k_pad_next, row, out, S, ray); }
+    }
+}
+__global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_constant__ DqnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* s_best = reinterpret_cast<float*>(smem + SM_C1);               // [4][128] partial maxima of the TD target
+    float* s_g = reinterpret_cast<float*>(smem + SM_BIAS2); int* s_a = reinterpret_cast<int*>(smem + SM_BIAS2 + 4 * DQ_TILE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t *b_full = bars, *b_free = bars + DQ_STAGES, *part_done = bars + 2 * DQ_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * DQ_STAGES + 2);
+    const int t = threadIdx.x, warp = t >> 5;
+    RLPT_PDL_SYNC();
+    ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
+    if (t < DQ_BWD_CHUNKS) {
+        const ChunkInfo ci = chunk_info(p.w3tp, p.w2tp, nullptr, t);
+        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.kc * (DQ_KC * 16u);
+        ChunkRow cr;
+        cr.src_lo = (uint32_t)reinterpret_cast<uint64_t>(ci.src); cr.src_hi = (uint32_t)(reinterpret_cast<uint64_t>(ci.src) >> 32); cr.bytes = (uint32_t)ci.rows * (uint32_t)ci.kw * 2u;
+        cr.a_lo = ((a_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); cr.a_hi = ((ci.a_kpad * 16u) >> 4) | (1u << 14); cr.b_hi = (((uint32_t)ci.kw * 16u) >> 4) | (1u << 14);
+        cr.idesc = idesc_bf16(DQ_TILE, ci.rows); cr.tmem_col = ci.tmem_col; cr.n_mma = (uint32_t)ci.kw / 16u;
+        cr.flags = (ci.kc == 0 ? 1u : 0u) | (ci.last ? 2u : 0u) | ((uint32_t)ci.part << 2);
+        table[t] = cr;
+    }
+    if (t == 0) { for (int i = 0; i < 2 * DQ_STAGES + 2; ++i) mbar_init(&bars[i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t b_lo0 = ((smem_u32(smem + SM_B0) & 0x3FFFFu) >> 4) | ((128u >> 4) << 16);
+    auto compute_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(DQ_COMPUTE_THREADS) : "memory"); };       // epilogue warps + MMA warp
+    auto epi_sync = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(DQ_EPI_THREADS) : "memory"); };               // epilogue warps only
+    const int S = p.S, n_tiles = S / DQ_TILE;
+    const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == DQ_EPI_THREADS / 32 + 1) {
+        if ((t & 31) == 0) {
+            const uint32_t total = (uint32_t)my_tiles * DQ_BWD_CHUNKS;
+            uint32_t stage = 0, par = 1, srow = 0;
+            for (uint32_t g = 0; g < total; ++g) {
+                if (g >= DQ_STAGES) mbar_wait(&b_free[stage], par);
+                const ChunkRow& cr = table[srow];
+                const uint32_t bytes = cr.bytes;
+                mbar_expect_tx(&b_full[stage], bytes);
+                bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES, reinterpret_cast<const void*>(((uint64_t)cr.src_hi << 32) | cr.src_lo), bytes, &b_full[stage]);
+                if (++srow == DQ_BWD_CHUNKS) srow = 0;
+                if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == DQ_EPI_THREADS / 32) {
+        const bool lead = (t & 31) == 0;
+        uint32_t stage = 0, par = 0, srow = 0;
+        auto run = [&](int n) {
+            for (int i = 0; i < n; ++i) {
+                mbar_wait(&b_full[stage], par);
+                tc_fence_after();
+                const ChunkRow cr = table[srow];
+                uint32_t a_lo = cr.a_lo, b_lo = b_lo0 + stage * (DQ_STAGE_BYTES >> 4);
+                const uint32_t d_addr = tmem_base + cr.tmem_col, first = cr.flags & 1u;
+                for (uint32_t k = 0; k < cr.n_mma; ++k, a_lo += 16u, b_lo += 16u)
+                    umma_bf16_lohi(d_addr, a_lo, cr.a_hi, b_lo, cr.b_hi, cr.idesc, (first ^ 1u) | k);
+                umma_commit(&b_free[stage]);
+                if (cr.flags & 2u) umma_commit(&part_done[(cr.flags >> 2) & 1u]);
+                if (++srow == DQ_BWD_CHUNKS) srow = 0;
+                if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
+            }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+            compute_sync();                                                // delta3 is in A1
+            if (lead) { tc_fence_after(); run(2 * DQ_NKC2); }
+            __syncwarp(); compute_sync();                                  // delta2 is in A2
+            if (lead) { tc_fence_after(); run(DQ_NKC3); }
+            __syncwarp();
+        }
+    } else {
+        const int row = t & (DQ_TILE - 1), grp = t >> 7;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t done_par = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x, ray = tile * DQ_TILE + row; const bool valid = ray < p.n;
+            // ---- phase 0: TD target, output-layer gradient, delta3
+            if (p.td.q_next) {
+                float best = 0.f;
+                if (valid) {
+#pragma unroll 12
+                    for (int k = grp * (DQ_OUT / DQ_EPI_GROUPS); k < (grp + 1) * (DQ_OUT / DQ_EPI_GROUPS); ++k) best = fmaxf(best, __ldg(p.td.q_next + (size_t)k * p.td.q_stride + ray) * c_dq_cos[k]);
+                }
+                s_best[grp * DQ_TILE + row] = best;
+                epi_sync();
+            }
+            if (grp == 0) {
+                float g = 0.f, loss = 0.f; int a = 0;
+                if (valid) {
+                    float target;
+                    if (p.td.q_next) {
+                        float best = 0.f;
+#pragma unroll
+                        for (int w = 0; w < DQ_EPI_GROUPS; ++w) best = fmaxf(best, s_best[w * DQ_TILE + row]);
+                        target = p.td.reward[ray];
+                        if (p.td.state[ray] != 1u) target += best * p.td.discount[ray];
+                        p.targets[ray] = target;
+                    } else target = p.targets[ray];
+                    a = (int)p.actions[ray]; const float qa = p.q[(size_t)a * S + ray], diff = qa - target;
+                    loss = diff * diff; g = qa > 0.f ? 2.f * diff : 0.f;
+                    if (g != 0.f) atomicAdd(p.gb4 + a, g);
+                }
+                s_g[row] = g; s_a[row] = a; p.g_out[ray] = g;
+                for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+                if ((t & 31) == 0 && loss != 0.f) atomicAdd(p.scalars, loss);
+            }
+            epi_sync();
+            {
+                const float g = s_g[row]; const int a = s_a[row];
+                const unsigned short* h3 = reinterpret_cast<const unsigned short*>(p.h3t) + ray;       // read-only path: the loads of several iterations may then be in flight together
+#pragma unroll 4
+                for (int j0 = 8 * grp; j0 < DQ_K4; j0 += 8 * DQ_EPI_GROUPS) {
+                    float h[8], w[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = (valid && j0 + e < DQ_H3) ? __uint_as_float((uint32_t)__ldg(h3 + (size_t)(j0 + e) * S) << 16) : 0.f;
+                    if (g != 0.f && j0 < DQ_H3) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w4 + (size_t)a * DQ_H3 + j0)), w1 = __ldg(reinterpret_cast<const float4*>(p.w4 + (size_t)a * DQ_H3 + j0 + 4));
+                        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[e] = 0.f;
+                    }
+                    __nv_bfloat162 pk[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const bool on0 = g != 0.f && h[e] > 0.f, on1 = g != 0.f && h[e + 1] > 0.f;
+                        pk[e >> 1] = __floats2bfloat162_rn(on0 ? g * w[e] : 0.f, on1 ? g * w[e + 1] : 0.f);       // (dW4's scatter-adds: k_dw4_rank1 beside the GEMMs -- from these 32 SMs they took 45 us)
+                    }
+                    *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(row, j0, DQ_K4)) = *reinterpret_cast<uint4*>(&pk[0]);
+                    __nv_bfloat16* op = p.d3t + (size_t)j0 * S + ray;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { op[0] = pk[e].x; op[S] = pk[e].y; op += 2 * (size_t)S; }
+                }
+            }
+            fence_proxy_async(); tc_fence_before(); compute_sync();
+            // ---- P2 = delta3 W3 -> relu'(h2) -> delta2 (A operand + d2t)
+            bwd_epilogue(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, DQ_H2, p.h2t, true, SM_A2, DQ_K3, row, grp, p.d2t, S, ray);
+            done_par ^= 3u;
+            fence_proxy_async(); tc_fence_before(); compute_sync();
+            // ---- P1 = delta2 W2 -> relu'(h1) -> d1t
+            bwd_epilogue(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, DQ_H1, p.h1t, false, 0, 0, row, grp, p.d1t, S, ray);
+            done_par ^= 1u;
+            tc_fence_before();
+        }
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+int dqn_backward(const DqnBwdParams& p, cudaStream_t s) {
+    int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int n_tiles = p.S / DQ_TILE;
+    k_dqn_backward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -672,8 +880,6 @@ __global__ void k_transpose_bf16(const float* __restrict__ w, int rows, int cols
 // walked with the ray index fastest, the ray-major d3 is written from a shared-memory tile with the unit index fastest -- every access
 // coalesced. (One thread per ray walking 208 units, the first form of this kernel, took 125 us of a 270 us optimiser step.)
 constexpr int D3_RAYS = 32;
-__constant__ float c_dq_cos[DQ_OUT];                                     // cos(theta) of the 144 grid cells (the tracer's table; dqn_upload_cell_cos)
-void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos144, sizeof(float) * DQ_OUT); }
 // With tdp.q_next set the kernel first derives the batch's TD targets itself (compute_td_targets, nn_rendering_helpers.cu:91-140:
 // reward + discount * max_a Q(s', a) cos(theta_a); terminal: the reward) -- eight warps x 18 cells per ray, combined through shared memory --
 // instead of reading them from a kernel of its own (8 us of a 130 us optimiser step).
@@ -903,7 +1109,8 @@ __global__ void __launch_bounds__(1024) k_collect_norm(ParamSegs t, const float*
 constexpr int ADAM_ROW_BLOCKS = DQ_H1, ADAM_ROW_ITEMS = 4;                // one CTA per row of W1; the first 4 x 256 inputs of the row are requested before the norm is known
 __global__ void __launch_bounds__(256) k_adam_fused(ParamSegs t, float* __restrict__ scalars, const float* __restrict__ sq_partial, float* __restrict__ loss_total,
                                                     float lr, float clip, float beta1, float beta2, float eps, const float* __restrict__ v, int k_in, float* __restrict__ c1, float* __restrict__ m1,
-                                                    __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w3p, __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t) {
+                                                    __nv_bfloat16* __restrict__ w2p, __nv_bfloat16* __restrict__ w3p, __nv_bfloat16* __restrict__ w4p, __nv_bfloat16* __restrict__ w3t, __nv_bfloat16* __restrict__ w2t,
+                                                    __nv_bfloat16* __restrict__ w3tp, __nv_bfloat16* __restrict__ w2tp) {
     __shared__ float s_n2; __shared__ float s_red[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool rows = blockIdx.x < ADAM_ROW_BLOCKS;
@@ -973,8 +1180,8 @@ __global__ void __launch_bounds__(256) k_adam_fused(ParamSegs t, float* __restri
     const float x = adam(g[0], mm[0], vv[0], xx[0]);
     t.m[s][j] = mm[0]; t.v[s][j] = vv[0]; t.x[s][j] = x;
     const __nv_bfloat16 xb = __float2bfloat16_rn(x);
-    if (s == 2) { const int r = j / DQ_H1, c = j - r * DQ_H1; { const size_t o = wpack_offset(DQ_L2_SPLIT, r, c, DQ_N2, DQ_K2); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2p) + q * DQ_W2P_STRIDE + o) = xb; } if (w2t) w2t[(size_t)c * DQ_K3 + r] = xb; }
-    else if (s == 4) { const int r = j / DQ_H2, c = j - r * DQ_H2; { const size_t o = wpack_offset(0, r, c, DQ_N3, DQ_K3); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3p) + q * DQ_W3P_STRIDE + o) = xb; } if (w3t) w3t[(size_t)c * DQ_K2 + r] = xb; }
+    if (s == 2) { const int r = j / DQ_H1, c = j - r * DQ_H1; { const size_t o = wpack_offset(DQ_L2_SPLIT, r, c, DQ_N2, DQ_K2); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2p) + q * DQ_W2P_STRIDE + o) = xb; } if (w2t) { w2t[(size_t)c * DQ_K3 + r] = xb; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w2tp) + wpack_offset(0, c, r, DQ_N3, DQ_K3)) = xb; } }
+    else if (s == 4) { const int r = j / DQ_H2, c = j - r * DQ_H2; { const size_t o = wpack_offset(0, r, c, DQ_N3, DQ_K3); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3p) + q * DQ_W3P_STRIDE + o) = xb; } if (w3t) { w3t[(size_t)c * DQ_K2 + r] = xb; *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w3tp) + wpack_offset(DQ_L2_SPLIT, c, r, DQ_N2, DQ_K2)) = xb; } }
     else if (s == 6) { const int r = j / DQ_H3, c = j - r * DQ_H3; { const size_t o = wpack_offset(0, r, c, DQ_N4, DQ_K4); for (int q = 0; q < DQ_REPLICAS; ++q) *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(w4p) + q * DQ_W4P_STRIDE + o) = xb; } }
 }
 static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
@@ -990,9 +1197,11 @@ static ParamSegs param_segs(const DqnDev& d, const DqnTrain& t) {
 void dqn_train_free(DqnTrain& t) {
     cudaFree(t.gall); cudaFree(t.sq_partial);
     for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
-    cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
+    cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.w3tp); cudaFree(t.w2tp); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
     cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
     if (t.side) cudaStreamDestroy(t.side);
+    if (t.side2) cudaStreamDestroy(t.side2);
+    if (t.side3) cudaStreamDestroy(t.side3);
     for (cudaEvent_t e : t.ev) if (e) cudaEventDestroy(e);
     t = DqnTrain{};
 }
@@ -1014,7 +1223,7 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
             DQ_CK(cudaMemset(t.mw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.mb[l], 0, 4 * nb)); DQ_CK(cudaMemset(t.vw[l], 0, 4 * nw)); DQ_CK(cudaMemset(t.vb[l], 0, 4 * nb));
         }
         DQ_CK(cudaMalloc(&t.dw3x, 4 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.dw2x, 4 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.dg, 4 * (size_t)DQ_K2 * 16));
-        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4)); DQ_CK(cudaMemset(t.scalars, 0, 4 * 4)); DQ_CK(cudaMalloc(&t.sq_partial, 4 * 128));
+        DQ_CK(cudaMalloc(&t.w3t, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2t, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.w3tp, 2 * (size_t)DQ_N2 * DQ_K2)); DQ_CK(cudaMalloc(&t.w2tp, 2 * (size_t)DQ_N3 * DQ_K3)); DQ_CK(cudaMalloc(&t.scalars, 4 * 4)); DQ_CK(cudaMemset(t.scalars, 0, 4 * 4)); DQ_CK(cudaMalloc(&t.sq_partial, 4 * 128));
         t.step = 0;
     }
     if (S > t.capacity) {
@@ -1026,7 +1235,17 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
     }
     return 0;
 }
+// out = packed (wpack_offset) bf16 copy of W^T for k_dqn_backward: W is [k][n] row-major, the operand has n_pad rows (W's columns) x k_pad inputs (W's rows)
+__global__ void k_pack_transposed(const float* __restrict__ w, int n, int k, int n_pad, int k_pad, int n_split, __nv_bfloat16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * k_pad) return;
+    const int row = i / k_pad, col = i % k_pad;
+    const float v = (row < n && col < k) ? w[(size_t)col * n + row] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + wpack_offset(n_split, row, col, n_pad, k_pad)) = __float2bfloat16_rn(v);
+}
 static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
+    k_pack_transposed<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H2, DQ_H3, DQ_N2, DQ_K2, DQ_L2_SPLIT, t.w3tp);       // W3 [200][300] -> W3^T as [304][208]
+    k_pack_transposed<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H1, DQ_H2, DQ_N3, DQ_K3, 0, t.w2tp);                 // W2 [300][200] -> W2^T as [208][304]
     // W3 is [200][300]: W3^T as [304][208] (row = layer-2 unit, K = layer-3 unit); W2 is [300][200]: W2^T as [208][304]
     k_transpose_bf16<<<(DQ_N2 * DQ_K2 + 255) / 256, 256, 0, s>>>(d.w[2], DQ_H3, DQ_H2, DQ_N2, DQ_K2, t.w3t);
     k_transpose_bf16<<<(DQ_N3 * DQ_K3 + 255) / 256, 256, 0, s>>>(d.w[1], DQ_H2, DQ_H1, DQ_N3, DQ_K3, t.w2t);
@@ -1044,7 +1263,8 @@ int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {          
     if (!t.transposes_fresh) { rc = refresh_transposes(d, t, s); if (rc) return rc; t.transposes_fresh = true; }
     if (!t.side) {
         if (const char* e = getenv("RLPT_NQ_PDL")) t.pdl = atoi(e) != 0;
-        DQ_CK(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking));
+        if (const char* e = getenv("RLPT_NQ_FUSED_BWD")) t.fused_bwd = atoi(e) != 0;
+        DQ_CK(cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking)); DQ_CK(cudaStreamCreateWithFlags(&t.side2, cudaStreamNonBlocking)); DQ_CK(cudaStreamCreateWithFlags(&t.side3, cudaStreamNonBlocking));
         for (cudaEvent_t& e : t.ev) DQ_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     return 0;
@@ -1080,7 +1300,23 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
         k_g4_full<<<dim3((S + 127) / 128, DQ_OUT), 128, 0, s>>>(t.q, targets, n, S, t.g4, t.scalars);
         k_delta3_full<<<dim3((S + 127) / 128, DQ_K4), 128, 0, s>>>(t.g4, d.w[3], t.h3t, n, S, t.d3, t.d3t);
         k_dw4_full<<<dim3((DQ_H3 + 1 + 7) / 8, DQ_OUT), 256, 0, s>>>(t.g4, t.h3t, n, S, t.gw[3], t.gb[3]);
-    } else {
+    } else if (t.fused_bwd) {
+        // TD step: output-layer delta, both data products and both masks in ONE kernel; the three weight-gradient GEMMs then run side by side
+        DqnBwdParams bp{}; bp.n = n; bp.S = S; bp.q = t.q; bp.actions = actions; bp.targets = const_cast<float*>(targets); if (tdp) bp.td = *tdp;
+        bp.w4 = d.w[3]; bp.h1t = t.h1t; bp.h2t = t.h2t; bp.h3t = t.h3t; bp.w3tp = t.w3tp; bp.w2tp = t.w2tp; bp.d3t = t.d3t; bp.d2t = t.d2t; bp.d1t = t.d1t;
+        bp.g_out = t.g3; bp.gb4 = t.gb[3]; bp.scalars = t.scalars;
+        rc = dqn_backward(bp, s); if (rc) return rc;
+        const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);
+        DQ_CK(cudaEventRecord(t.ev[0], s)); DQ_CK(cudaStreamWaitEvent(t.side, t.ev[0], 0)); DQ_CK(cudaStreamWaitEvent(t.side2, t.ev[0], 0));
+        rc = gemm_tn(t.d3t, S, t.h2t, S, t.dw3x, DQ_K3, DQ_K4, DQ_K3, S, ks, t.side); if (rc) return rc;                 // [208 x S] x [304 x S]^T
+        rc = gemm_tn(t.d2t, S, t.h1t, S, t.dw2x, DQ_K2, DQ_K3, DQ_K2, S, ks, t.side2); if (rc) return rc;                // [304 x S] x [208 x S]^T
+        rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s); if (rc) return rc;                                // [208 x S] x [16 x S]^T
+        k_dw4_rank1<<<(S + D3_RAYS - 1) / D3_RAYS, 256, 0, s>>>(t.g3, actions, n, S, t.h3t, t.gw[3]);       // (on a stream of its own: 85 -> 88 us per step)
+        DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
+        DQ_CK(cudaEventRecord(t.ev[1], t.side2)); DQ_CK(cudaStreamWaitEvent(s, t.ev[1], 0));
+    }
+    if (all_outputs || !t.fused_bwd) {
+    if (!all_outputs) {
         DqnTdParams td{}; if (tdp) td = *tdp;
         DQ_CK(launch_ex(pdl, k_delta3, dim3((S + D3_RAYS - 1) / D3_RAYS), dim3(256), 0, s, t.q, actions, const_cast<float*>(targets), td, n, S, d.w[3], t.h3t, t.d3, t.d3t, t.g3, t.gb[3], t.scalars));
     }
@@ -1102,6 +1338,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     DQ_CK(launch_ex(pdl, k_delta_hidden, dim3((S + DH_RAYS - 1) / DH_RAYS, (DQ_K2 + DH_FEATS - 1) / DH_FEATS), dim3(256), 0, s, t.p1, S, t.h1t, S, DQ_H1, DQ_K2, (__nv_bfloat16*)nullptr, t.d1t));
     rc = gemm_tn(t.d1t, S, t.xt, S, t.dg, 16, DQ_K2, 16, S, ks, s, 0, pdl); if (rc) return rc;                                // [208 x S] x [16 x S]^T
     DQ_CK(cudaEventRecord(t.ev[2], t.side)); DQ_CK(cudaStreamWaitEvent(s, t.ev[2], 0));
+    }
     if (allreduce) {
         const int n_collect = DQ_H1 * d.k_in + DQ_H2 * DQ_H1 + DQ_H3 * DQ_H2 + DQ_H1 + DQ_H2 + DQ_H3;
         k_collect_grads<<<(n_collect + 255) / 256, 256, 0, s>>>(t.dw3x, t.dw2x, t.dg, d.vertices, d.k_in, t.gw[0], t.gb[0], t.gw[1], t.gb[1], t.gw[2], t.gb[2]);
@@ -1116,7 +1353,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     {
         const int rest = segs.start[8] - segs.start[2];
         DQ_CK(launch_ex(pdl, k_adam_fused, dim3(ADAM_ROW_BLOCKS + (rest + 255) / 256), dim3(256), 0, s, segs, t.scalars, t.sq_partial, loss_total, t.lr, t.clip, t.beta1, t.beta2, t.eps, d.vertices, d.k_in, d.c1, d.m1,
-                        d.w2p, d.w3p, d.w4p, t.w3t, t.w2t));
+                        d.w2p, d.w3p, d.w4p, t.w3t, t.w2t, t.w3tp, t.w2tp));
     }
     return (int)cudaGetLastError();
 }

@@ -60,6 +60,7 @@ struct DqnTrain {
     float *vw[4] = { nullptr, nullptr, nullptr, nullptr }, *vb[4] = { nullptr, nullptr, nullptr, nullptr };      // Adam second moments
     float *dw3x = nullptr, *dw2x = nullptr, *dg = nullptr;      // GEMM outputs: [208][304] (col 300 = db3), [304][208] (col 200 = db2), [208][16] (cols 0-2 = G, col 3 = db1)
     __nv_bfloat16 *w3t = nullptr, *w2t = nullptr;   // transposed bf16 copies: W3^T [304][208], W2^T [208][304]
+    __nv_bfloat16 *w3tp = nullptr, *w2tp = nullptr; // the same transposes as k_dqn_backward streams them (packed chunks, wpack_offset)
     __nv_bfloat16 *h1t = nullptr, *h2t = nullptr, *h3t = nullptr, *xt = nullptr;
     __nv_bfloat16 *d3 = nullptr, *d2 = nullptr, *d3t = nullptr, *d2t = nullptr, *d1t = nullptr;
     float* g3 = nullptr;                            // [S] per-ray output-layer gradient of the TD step (k_delta3 -> k_dw4_rank1)
@@ -70,8 +71,10 @@ struct DqnTrain {
     unsigned long long step = 0;
     bool transposes_fresh = false;                  // W3^T / W2^T match the current parameters (k_pack_all refreshes them after every update)
     float lr = 1e-3f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, clip = 5.f;
-    cudaStream_t side = nullptr; cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };      // the weight-gradient GEMMs and the step's zeroing run beside the data path
+    cudaStream_t side = nullptr; cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };      // the weight-gradient GEMMs and the step's zeroing run beside the data path
     bool pdl = false;                               // programmatic dependent launch along the step's main chain (RLPT_NQ_PDL=1; measured: 100.9 -> 102.4 us per step, off)
+    bool fused_bwd = true;                          // TD step: the backward data path as one kernel (RLPT_NQ_FUSED_BWD=0: delta kernel + GEMMs + mask kernels)
+    cudaStream_t side2 = nullptr, side3 = nullptr;
     bool begun = false;                             // dqn_train_begin has been enqueued for the step dqn_train_batch is about to run
 };
 int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity);
@@ -79,6 +82,12 @@ void dqn_train_free(DqnTrain& t);
 // TD targets derived inside the output-layer delta kernel (q_next null: targets are read from the array instead)
 struct DqnTdParams { const float* q_next; int q_stride; const uint32_t* state; const float* reward; const float* discount; };
 void dqn_upload_cell_cos(const float* cos144);
+// k_dqn_backward's arguments (rlpt_dqn.cu): the TD step's backward data path of a batch
+struct DqnBwdParams {
+    int n, S; const float* q; const uint32_t* actions; float* targets; DqnTdParams td; const float* w4;
+    const __nv_bfloat16 *h1t, *h2t, *h3t, *w3tp, *w2tp; __nv_bfloat16 *d3t, *d2t, *d1t; float *g_out, *gb4, *scalars;
+};
+int dqn_backward(const DqnBwdParams& p, cudaStream_t s);
 // One optimiser step on a batch (G/deep_learning/neural_q_pathtracer.cu:476-512): forward with kept activations, loss
 // sum_b (target_b - Q(s_b)[a_b])^2, backward, Adam update, operands refreshed. pos/actions/targets are device pointers.
 // all-reduce hook (may be null): sums the gradient buffers across ranks before the update.
