@@ -1237,7 +1237,7 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
                         frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true, &td);
                         if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
                     }
-                    c->launches += 13.0;       // kernels of one optimiser step (staging, step begin, forward of both batches, 5 GEMMs, 3 deltas, collect + norm, Adam + operand refresh)
+                    c->launches += c->dq_train.fused_bwd ? 10.0 : 14.0;       // kernels of one optimiser step: staging, step begin, forward of both batches, backward data path (one kernel, or delta + 2 GEMMs + 2 masks), 3 weight-gradient GEMMs, dW4 scatter, collect + norm, Adam + operand refresh
                     c->k_all[4] += 1.0;
                 }
                 cudaEvent_t t1 = t0 ? kev_mark(c, c->stream) : nullptr;
