@@ -1197,47 +1197,44 @@ static int enqueue_nq_training_frame(rlpt_ctx* c, int batch) {
             c->launches += b > 0 ? 3.0 : 1.0;
             if (b > 0) {
                 cudaEvent_t t0 = kev_room(c) ? kev_mark(c, c->stream) : nullptr;
-                for (int start = 0; start < n; start += batch) {
-                    const int bn = std::min(batch, n - start);
-                    // One optimiser step is ~40 small launches (forward of the next states, TD targets, forward + backward GEMMs,
-                    // Adam, operand repacking): launch-bound. Full batches replay a CUDA graph captured once; the batch's slice of
-                    // the ray arrays is copied into fixed staging buffers first, so the graph holds no per-batch address.
-                    const bool use_graph = c->nq_graphs && !dist && bn == batch;
-                    if (use_graph) {
-                        launch_nqt_stage(c->nqt, start, bn, c->d_nqg_loc, c->d_nqg_sloc, c->d_nqg_action, c->d_nqg_state, c->d_nqg_reward, c->d_nqg_discount, c->stream);
-                        if (!c->nq_graph_exec || c->nq_graph_batch != batch) {
-                            if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; }
-                            int arc = dqn_train_prepare(c->dq, c->dq_train, batch, c->stream); if (arc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
-                            NqTrainState gs = c->nqt; gs.state = c->d_nqg_state; gs.reward = c->d_nqg_reward; gs.discount = c->d_nqg_discount;
-                            cudaGraph_t graph = nullptr;
-                            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                            // the step's zeroing runs beside the forward launch, which evaluates the batch's states (activations kept for the backward pass) and its
-                            // next states (Q only); the TD targets are derived from those inside the output-layer delta kernel
-                            int frc = dqn_train_begin(c->dq, c->dq_train, c->d_nqg_sloc, bn, true, c->stream);
-                            DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->d_nqg_sloc, bn);
-                            gp.pos2 = c->d_nqg_loc; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
-                            if (!frc) frc = dqn_forward(c->dq, gp, c->stream);
-                            const DqnTdParams td{ c->d_nqt_qnext, S, gs.state, gs.reward, gs.discount };
-                            if (!frc) frc = dqn_train_batch(c->dq, c->dq_train, c->d_nqg_sloc, c->d_nqg_action, c->d_nqt_targets, bn, true, nullptr, nullptr, c->stream, false, c->d_nqt_loss, true, &td);
-                            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-                            if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(RLPT_ERR_CUDA, "Neural-Q training step: graph capture failed"); }
-                            ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
-                            cudaGraphDestroy(graph);
-                            if (ce != cudaSuccess) { c->nq_graph_exec = nullptr; return fail(RLPT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
-                            c->nq_graph_batch = batch;
-                        }
-                        CK(cudaGraphLaunch(c->nq_graph_exec, c->stream));
-                        c->dq_train.step++;
-                    } else {
-                        int frc = dqn_train_begin(c->dq, c->dq_train, c->nqt.sloc + start, bn, true, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
-                        DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->nqt.sloc + start, bn);
-                        gp.pos2 = c->nqt.loc + start; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
-                        frc = dqn_forward(c->dq, gp, c->stream); if (frc) return fail(RLPT_ERR_CUDA, "DQN forward launch failed");
-                        const DqnTdParams td{ c->d_nqt_qnext, S, c->nqt.state + start, c->nqt.reward + start, c->nqt.discount + start };
-                        frc = dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true, &td);
-                        if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
+                // One optimiser step is ten small launches (step begin, forward of states and next states, backward data path, three weight-gradient
+                // GEMMs, dW4 scatter, gather + norm, Adam + operands): launch-bound. All FULL batches of a bounce replay ONE CUDA graph captured once
+                // (the batch offsets are the same every bounce, so the nodes read the ray arrays in place -- no staging copy, one graph launch per
+                // bounce instead of one per step); a ragged last batch, and multi-GPU runs (the all-reduce hook is a host callback), go step by step.
+                const int full = (c->nq_graphs && !dist) ? n / batch : 0;
+                auto one_step = [&](int start, int bn) -> int {
+                    int frc = dqn_train_begin(c->dq, c->dq_train, c->nqt.sloc + start, bn, true, c->stream); if (frc) return frc;
+                    // the step's zeroing runs beside the forward launch, which evaluates the batch's states (activations kept for the backward pass) and
+                    // its next states (Q only); the TD targets are derived from those inside the backward kernel
+                    DqnFwdParams gp = dqn_train_forward_params(c->dq, c->dq_train, c->nqt.sloc + start, bn);
+                    gp.pos2 = c->nqt.loc + start; gp.n2 = bn; gp.q2 = c->d_nqt_qnext; gp.q_stride2 = S;
+                    frc = dqn_forward(c->dq, gp, c->stream); if (frc) return frc;
+                    const DqnTdParams td{ c->d_nqt_qnext, S, c->nqt.state + start, c->nqt.reward + start, c->nqt.discount + start };
+                    return dqn_train_batch(c->dq, c->dq_train, c->nqt.sloc + start, c->nqt.action + start, c->d_nqt_targets, bn, true, dist ? dqn_hook : nullptr, c, c->stream, false, c->d_nqt_loss, true, &td);
+                };
+                if (full > 0) {
+                    if (!c->nq_graph_exec || c->nq_graph_batch != batch) {
+                        if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; }
+                        int arc = dqn_train_prepare(c->dq, c->dq_train, batch, c->stream); if (arc) return fail(RLPT_ERR_CUDA, "Neural-Q training buffers");
+                        cudaGraph_t graph = nullptr; int frc = 0;
+                        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                        for (int k = 0; k < full && !frc; ++k) frc = one_step(k * batch, batch);
+                        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                        if (frc || ce != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); c->dq_train.begun = false; return fail(RLPT_ERR_CUDA, "Neural-Q training steps: graph capture failed"); }
+                        ce = cudaGraphInstantiate(&c->nq_graph_exec, graph, 0);
+                        cudaGraphDestroy(graph);
+                        if (ce != cudaSuccess) { c->nq_graph_exec = nullptr; return fail(RLPT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+                        c->nq_graph_batch = batch;
                     }
-                    c->launches += c->dq_train.fused_bwd ? 10.0 : 14.0;       // kernels of one optimiser step: staging, step begin, forward of both batches, backward data path (one kernel, or delta + 2 GEMMs + 2 masks), 3 weight-gradient GEMMs, dW4 scatter, collect + norm, Adam + operand refresh
+                    CK(cudaGraphLaunch(c->nq_graph_exec, c->stream));
+                    c->dq_train.step += (unsigned long long)full;
+                    c->launches += (c->dq_train.fused_bwd ? 9.0 : 13.0) * full; c->k_all[4] += (double)full;
+                }
+                for (int start = full * batch; start < n; start += batch) {
+                    const int bn = std::min(batch, n - start);
+                    int frc = one_step(start, bn);
+                    if (frc) return fail(frc == -2 ? RLPT_ERR_COLLECTIVE : RLPT_ERR_CUDA, "Neural-Q training step failed");
+                    c->launches += c->dq_train.fused_bwd ? 9.0 : 13.0;       // kernels of one optimiser step: step begin, forward of both batches, backward data path (one kernel, or delta + 2 GEMMs + 2 masks), 3 weight-gradient GEMMs, dW4 scatter, gather + norm, Adam + operand refresh
                     c->k_all[4] += 1.0;
                 }
                 cudaEvent_t t1 = t0 ? kev_mark(c, c->stream) : nullptr;

@@ -942,10 +942,15 @@ __global__ void __launch_bounds__(256) k_dw4_rank1(const float* __restrict__ g_i
     const float g = g_in[i];
     if (g == 0.f) return;
     const int a = (int)actions[i];
-#pragma unroll 5
-    for (int j = jj; j < DQ_H3; j += 8) {
-        const float h = __bfloat162float(h3t[(size_t)j * S + i]);
-        if (h > 0.f) atomicAdd(gw4 + (size_t)a * DQ_H3 + j, g * h);
+    const unsigned short* h3 = reinterpret_cast<const unsigned short*>(h3t) + i;
+    // four consecutive units per 16-byte vector reduction (a row of W4 is 800 bytes: 16-byte aligned); units behind a dead ReLU add zero
+#pragma unroll 7
+    for (int j0 = 4 * jj; j0 < DQ_H3; j0 += 32) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float h = __uint_as_float((uint32_t)__ldg(h3 + (size_t)(j0 + e) * S) << 16); v[e] = h > 0.f ? g * h : 0.f; }
+        if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gw4 + (size_t)a * DQ_H3 + j0), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     }
 }
 // Supervised variant (NN_Q_Value_Trainer/Source/main.cu:110-117: loss = sum_batches squared_distance(targets, Q(s)) over ALL
