@@ -203,9 +203,10 @@ struct ChunkRow { uint32_t src_lo, src_hi, bytes, a_lo, a_hi, b_hi, idesc, tmem_
 constexpr uint32_t SM_TABLE_BYTES = DQ_CHUNKS_PER_TILE * sizeof(ChunkRow);
 
 // 32 (or 16) accumulator columns of one ray: + bias, ReLU, bf16; written as the next layer's A operand and optionally kept feature-major in HBM
-template <int NC>
+template <int NC, bool KEEP>
 __device__ __forceinline__ void hidden_block(uint8_t* smem, const uint32_t* r, int c0, const float* bias, uint32_t a_next_off, int k_pad_next, int row,
-                                             __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
+                                             __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid, uint32_t* maskw) {
+    uint32_t mword = 0;                                                    // relu'(h) of these units as bits (kept for k_dqn_backward: one word instead of 32 activations)
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
         __nv_bfloat162 pk[4];
@@ -217,18 +218,23 @@ __device__ __forceinline__ void hidden_block(uint8_t* smem, const uint32_t* r, i
             pk[j] = __floats2bfloat162_rn(a, b);
         }
         *reinterpret_cast<uint4*>(smem + a_next_off + operand_offset(row, c0 + 8 * q, k_pad_next)) = *reinterpret_cast<uint4*>(&pk[0]);
-        if (keep && ray_valid) {
+        if (KEEP && keep && ray_valid) {
             __nv_bfloat16* kp = keep + (size_t)(c0 + 8 * q) * keep_stride + ray;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { kp[0] = pk[j].x; kp[keep_stride] = pk[j].y; kp += 2 * (size_t)keep_stride; }
+            for (int j = 0; j < 4; ++j) {
+                kp[0] = pk[j].x; kp[keep_stride] = pk[j].y; kp += 2 * (size_t)keep_stride;
+                mword |= ((__bfloat16_as_ushort(pk[j].x) & 0x7fffu) ? 1u : 0u) << (8 * q + 2 * j) | ((__bfloat16_as_ushort(pk[j].y) & 0x7fffu) ? 1u : 0u) << (8 * q + 2 * j + 1);
+            }
         }
     }
+    if (KEEP && maskw && ray_valid) maskw[(size_t)(c0 >> 5) * keep_stride + ray] = mword;
 }
 // Epilogue of a hidden layer for one epilogue thread: its warpgroup's 32-column blocks (alternating with the other warpgroup's), each as soon
 // as the N part that holds it is complete (n_split: first column of the second part, 0 = one part). Bit c of done_par = parity of the
 // completions of part_done[c] before this layer.
+template <bool KEEP>
 __device__ __forceinline__ void hidden_epilogue(uint8_t* smem, uint64_t* part_done, uint32_t done_par, int n_split, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad,
-                                                const float* bias, uint32_t a_next_off, int k_pad_next, int row, int half, __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid) {
+                                                const float* bias, uint32_t a_next_off, int k_pad_next, int row, int half, __nv_bfloat16* keep, int keep_stride, int ray, bool ray_valid, uint32_t* maskw) {
     const int n_blocks = (n_pad + 31) / 32;
     for (int b = half; b < n_blocks; b += DQ_EPI_GROUPS) {
         const int c0 = 32 * b, c = (n_split > 0 && c0 >= n_split) ? 1 : 0;
@@ -236,14 +242,16 @@ __device__ __forceinline__ void hidden_epilogue(uint8_t* smem, uint64_t* part_do
         uint32_t r[32];
         if (c0 + 32 <= n_pad) {
             tmem_ld32_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait();
-            hidden_block<32>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid);
+            hidden_block<32, KEEP>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid, maskw);
         } else {
             tmem_ld16_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait();
-            hidden_block<16>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid);
+            hidden_block<16, KEEP>(smem, r, c0, bias, a_next_off, k_pad_next, row, keep, keep_stride, ray, ray_valid, maskw);
         }
     }
 }
 
+// KEEP: the training launch (activations and relu' bits of the first batch kept for the backward pass); the inference launches carry none of that code
+template <bool KEEP>
 __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_constant__ DqnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const float4* s_l1c = reinterpret_cast<const float4*>(smem + SM_C1); float4* s_l1 = reinterpret_cast<float4*>(smem + SM_C1);
@@ -371,10 +379,16 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
                     pk[j] = __floats2bfloat162_rn(ha, hb);
                 }
                 *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(row, j0, DQ_K2)) = *reinterpret_cast<uint4*>(&pk[0]);
-                if (k1 && valid) {
+                if (KEEP && k1 && valid) {
                     __nv_bfloat16* kp = k1 + (size_t)j0 * p.h_stride + ray;
+                    uint32_t mb = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { kp[0] = pk[j].x; kp[p.h_stride] = pk[j].y; kp += 2 * (size_t)p.h_stride; }
+                    for (int j = 0; j < 4; ++j) {
+                        kp[0] = pk[j].x; kp[p.h_stride] = pk[j].y; kp += 2 * (size_t)p.h_stride;
+                        mb |= ((__bfloat16_as_ushort(pk[j].x) & 0x7fffu) ? 1u : 0u) << (2 * j) | ((__bfloat16_as_ushort(pk[j].y) & 0x7fffu) ? 1u : 0u) << (2 * j + 1);
+                    }
+                    // units j0 .. j0 + 7 = byte (j0 & 31) / 8 of mask word j0 / 32 (with four warpgroups: byte `half` of word number `iteration`)
+                    if (p.mask1) reinterpret_cast<uint8_t*>(p.mask1)[((size_t)(j0 >> 5) * p.h_stride + ray) * 4 + ((j0 & 31) >> 3)] = (uint8_t)mb;
                 }
             }
             if (t == 0) DQ_TR(it);
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
 #ifdef RLPT_DQN_TRACE
             if (t == 0) { mbar_wait(&part_done[0], done_par & 1u); DQ_TR(it); }
 #endif
-            hidden_epilogue(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, row, half, k2, p.h_stride, ray, valid);
+            hidden_epilogue<KEEP>(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, s_b2, SM_A2, DQ_K3, row, half, k2, p.h_stride, ray, valid, second ? nullptr : p.mask2);
             done_par ^= 3u;
             if (t == 0) DQ_TR(it);
             fence_proxy_async(); tc_fence_before(); compute_sync();
@@ -393,7 +407,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
 #ifdef RLPT_DQN_TRACE
             if (t == 0) { mbar_wait(&part_done[0], done_par & 1u); DQ_TR(it); }
 #endif
-            hidden_epilogue(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, row, half, k3, p.h_stride, ray, valid);
+            hidden_epilogue<KEEP>(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, s_b3, SM_A1, DQ_K4, row, half, k3, p.h_stride, ray, valid, second ? nullptr : p.mask3);
             done_par ^= 1u;
             if (t == 0) DQ_TR(it);
             fence_proxy_async(); tc_fence_before(); compute_sync();
@@ -430,7 +444,8 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
 int dqn_gemm_set_smem_limit();
 __global__ void k_dqn_backward(const __grid_constant__ DqnBwdParams p);
 int dqn_set_smem_limit() {
-    int rc = (int)cudaFuncSetAttribute(k_dqn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    int rc = (int)cudaFuncSetAttribute(k_dqn_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
+    if (!rc) rc = (int)cudaFuncSetAttribute(k_dqn_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
     if (!rc) rc = (int)cudaFuncSetAttribute(k_dqn_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
     return rc ? rc : dqn_gemm_set_smem_limit();
 }
@@ -439,7 +454,8 @@ int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
     if (!d.ready || p.n <= 0) return p.n == 0 ? 0 : -1;        // p.n bounds the launch; p.n_ptr (if set) gives the live count
     int dev = 0, n_sm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int n_tiles = (p.n + DQ_TILE - 1) / DQ_TILE + (p.pos2 ? (p.n2 + DQ_TILE - 1) / DQ_TILE : 0);
-    k_dqn_forward<<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
+    if (p.h1t) k_dqn_forward<true><<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
+    else k_dqn_forward<false><<<n_tiles < n_sm ? n_tiles : n_sm, DQ_THREADS, SM_TOTAL, s>>>(p);
     return (int)cudaGetLastError();
 }
 
@@ -453,6 +469,7 @@ int dqn_forward(const DqnDev& d, const DqnFwdParams& p, cudaStream_t s) {
 // It replaces k_delta3, two data GEMMs and two mask kernels (43 us of a 92 us optimiser step) -- the activations never leave the SM between the products.
 constexpr int DQ_BWD_CHUNKS = 2 * DQ_NKC2 + DQ_NKC3;
 static_assert(DQ_REPLICAS == 1, "the packed transposes of k_dqn_backward have no replicas");
+static_assert(DQ_EPI_GROUPS == 4, "mask bytes of layer 1 / phase 0 of k_dqn_backward: four warpgroups, eight units each per 32-unit word");
 template <int NC>
 __device__ __forceinline__ void bwd_block(uint8_t* smem, const uint32_t* r, uint32_t mbits, int c0, bool write_a, uint32_t a_next_off, int k_pad_next, int row, __nv_bfloat16* out, int S, int ray) {
 #pragma unroll
@@ -470,19 +487,13 @@ __device__ __forceinline__ void bwd_block(uint8_t* smem, const uint32_t* r, uint
     }
 }
 __device__ __forceinline__ void bwd_epilogue(uint8_t* smem, uint64_t* part_done, uint32_t done_par, int n_split, uint32_t tmem_lane_addr, uint32_t tmem_col, int n_pad, int n_feat,
-                                             const __nv_bfloat16* __restrict__ mask_src, bool write_a, uint32_t a_next_off, int k_pad_next, int row, int grp, __nv_bfloat16* out, int S, int ray) {
+                                             const uint32_t* __restrict__ maskw, bool write_a, uint32_t a_next_off, int k_pad_next, int row, int grp, __nv_bfloat16* out, int S, int ray) {
     const int n_blocks = (n_pad + 31) / 32;
     for (int b = grp; b < n_blocks; b += DQ_EPI_GROUPS) {
         const int c0 = 32 * b, c = (n_split > 0 && c0 >= n_split) ? 1 : 0, nc = min(32, n_pad - c0);
-        uint32_t mbits = 0;                                                // relu'(h) of this block's units, requested before the product is waited for
-        {   // all 32 loads first, then the bits: with load and test in one loop the compiler chained them (one memory round trip per unit: 62 us per launch)
-            const unsigned short* ms = reinterpret_cast<const unsigned short*>(mask_src) + (size_t)c0 * S + ray;
-            unsigned short hb[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) hb[e] = (e < nc && c0 + e < n_feat) ? __ldg(ms + (size_t)e * S) : (unsigned short)0;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) mbits |= (hb[e] != 0 && hb[e] < 0x8000u) ? (1u << e) : 0u;
-        }
+        // relu'(h) of this block's units: one word the forward pass left behind (requested before the product is waited for); padding units masked off
+        const int nf = n_feat - c0;
+        const uint32_t mbits = __ldg(maskw + (size_t)b * S + ray) & (nf >= 32 ? 0xffffffffu : (nf > 0 ? (1u << nf) - 1u : 0u));
         mbar_wait(&part_done[c], (done_par >> c) & 1u); tc_fence_after();
         uint32_t r[32];
         if (nc == 32) { tmem_ld32_issue(tmem_lane_addr + tmem_col + (uint32_t)c0, r); tmem_ld_wait(); bwd_block<32>(smem, r, mbits, c0, write_a, a_next_off, k_pad_next, row, out, S, ray); }
@@ -598,12 +609,16 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_con
             epi_sync();
             {
                 const float g = s_g[row]; const int a = s_a[row];
-                const unsigned short* h3 = reinterpret_cast<const unsigned short*>(p.h3t) + ray;       // read-only path: the loads of several iterations may then be in flight together
-#pragma unroll 4
-                for (int j0 = 8 * grp; j0 < DQ_K4; j0 += 8 * DQ_EPI_GROUPS) {
-                    float h[8], w[8];
+                // relu'(h3) as mask words (unit j0 + e = bit 8 grp + e of word number j0 / 32): seven loads per thread, all in flight together
+                uint32_t m3[(DQ_K4 + 31) / 32];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) h[e] = (valid && j0 + e < DQ_H3) ? __uint_as_float((uint32_t)__ldg(h3 + (size_t)(j0 + e) * S) << 16) : 0.f;
+                for (int w = 0; w < (DQ_K4 + 31) / 32; ++w) m3[w] = valid ? __ldg(p.mask3 + (size_t)w * S + ray) : 0u;
+#pragma unroll
+                for (int it = 0; it < (DQ_K4 + 31) / 32; ++it) {
+                    const int j0 = 8 * grp + 32 * it;
+                    if (j0 >= DQ_K4) break;
+                    float w[8];
+                    const uint32_t hbits = j0 < DQ_H3 ? (m3[it] >> (8 * grp)) & 0xffu : 0u;
                     if (g != 0.f && j0 < DQ_H3) {
                         const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w4 + (size_t)a * DQ_H3 + j0)), w1 = __ldg(reinterpret_cast<const float4*>(p.w4 + (size_t)a * DQ_H3 + j0 + 4));
                         w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
@@ -614,7 +629,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_con
                     __nv_bfloat162 pk[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
-                        const bool on0 = g != 0.f && h[e] > 0.f, on1 = g != 0.f && h[e + 1] > 0.f;
+                        const bool on0 = g != 0.f && ((hbits >> e) & 1u), on1 = g != 0.f && ((hbits >> (e + 1)) & 1u);
                         pk[e >> 1] = __floats2bfloat162_rn(on0 ? g * w[e] : 0.f, on1 ? g * w[e + 1] : 0.f);       // (dW4's scatter-adds: k_dw4_rank1 beside the GEMMs -- from these 32 SMs they took 45 us)
                     }
                     *reinterpret_cast<uint4*>(smem + SM_A1 + operand_offset(row, j0, DQ_K4)) = *reinterpret_cast<uint4*>(&pk[0]);
@@ -625,11 +640,11 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_con
             }
             fence_proxy_async(); tc_fence_before(); compute_sync();
             // ---- P2 = delta3 W3 -> relu'(h2) -> delta2 (A operand + d2t)
-            bwd_epilogue(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, DQ_H2, p.h2t, true, SM_A2, DQ_K3, row, grp, p.d2t, S, ray);
+            bwd_epilogue(smem, part_done, done_par, DQ_L2_SPLIT, tmem_lane, 0, DQ_N2, DQ_H2, p.mask2, true, SM_A2, DQ_K3, row, grp, p.d2t, S, ray);
             done_par ^= 3u;
             fence_proxy_async(); tc_fence_before(); compute_sync();
             // ---- P1 = delta2 W2 -> relu'(h1) -> d1t
-            bwd_epilogue(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, DQ_H1, p.h1t, false, 0, 0, row, grp, p.d1t, S, ray);
+            bwd_epilogue(smem, part_done, done_par, 0, tmem_lane, DQ_N2, DQ_N3, DQ_H1, p.mask1, false, 0, 0, row, grp, p.d1t, S, ray);
             done_par ^= 1u;
             tc_fence_before();
         }
@@ -1203,7 +1218,7 @@ void dqn_train_free(DqnTrain& t) {
     cudaFree(t.gall); cudaFree(t.sq_partial);
     for (int l = 0; l < 4; ++l) { cudaFree(t.mw[l]); cudaFree(t.mb[l]); cudaFree(t.vw[l]); cudaFree(t.vb[l]); }
     cudaFree(t.dw3x); cudaFree(t.dw2x); cudaFree(t.dg); cudaFree(t.w3t); cudaFree(t.w2t); cudaFree(t.w3tp); cudaFree(t.w2tp); cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt);
-    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
+    cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.mask1); cudaFree(t.mask2); cudaFree(t.mask3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q); cudaFree(t.scalars); cudaFree(t.g4);
     if (t.side) cudaStreamDestroy(t.side);
     if (t.side2) cudaStreamDestroy(t.side2);
     if (t.side3) cudaStreamDestroy(t.side3);
@@ -1232,10 +1247,12 @@ int dqn_train_alloc(DqnTrain& t, const DqnDev& d, int capacity) {
         t.step = 0;
     }
     if (S > t.capacity) {
-        cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt); cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q);
+        cudaFree(t.h1t); cudaFree(t.h2t); cudaFree(t.h3t); cudaFree(t.xt); cudaFree(t.d3); cudaFree(t.d2); cudaFree(t.d3t); cudaFree(t.d2t); cudaFree(t.d1t); cudaFree(t.g3); cudaFree(t.mask1); cudaFree(t.mask2); cudaFree(t.mask3); cudaFree(t.p2); cudaFree(t.p1); cudaFree(t.q);
         DQ_CK(cudaMalloc(&t.h1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.h2t, 2 * (size_t)DQ_K3 * S)); DQ_CK(cudaMalloc(&t.h3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.xt, 2 * (size_t)16 * S));
         DQ_CK(cudaMalloc(&t.d3, 2 * (size_t)S * DQ_K4)); DQ_CK(cudaMalloc(&t.d2, 2 * (size_t)S * DQ_K3)); DQ_CK(cudaMalloc(&t.d3t, 2 * (size_t)DQ_K4 * S)); DQ_CK(cudaMalloc(&t.d2t, 2 * (size_t)DQ_K3 * S));
-        DQ_CK(cudaMalloc(&t.d1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.g3, 4 * (size_t)S)); DQ_CK(cudaMalloc(&t.p2, 4 * (size_t)S * DQ_N2)); DQ_CK(cudaMalloc(&t.p1, 4 * (size_t)S * DQ_N3)); DQ_CK(cudaMalloc(&t.q, 4 * (size_t)DQ_OUT * S));
+        DQ_CK(cudaMalloc(&t.d1t, 2 * (size_t)DQ_K2 * S)); DQ_CK(cudaMalloc(&t.g3, 4 * (size_t)S));
+        DQ_CK(cudaMalloc(&t.mask1, 4 * (size_t)((DQ_K2 + 31) / 32) * S)); DQ_CK(cudaMalloc(&t.mask2, 4 * (size_t)((DQ_K3 + 31) / 32) * S)); DQ_CK(cudaMalloc(&t.mask3, 4 * (size_t)((DQ_K4 + 31) / 32) * S));
+        DQ_CK(cudaMemset(t.mask1, 0, 4 * (size_t)((DQ_K2 + 31) / 32) * S)); DQ_CK(cudaMemset(t.mask2, 0, 4 * (size_t)((DQ_K3 + 31) / 32) * S)); DQ_CK(cudaMemset(t.mask3, 0, 4 * (size_t)((DQ_K4 + 31) / 32) * S)); DQ_CK(cudaMalloc(&t.p2, 4 * (size_t)S * DQ_N2)); DQ_CK(cudaMalloc(&t.p1, 4 * (size_t)S * DQ_N3)); DQ_CK(cudaMalloc(&t.q, 4 * (size_t)DQ_OUT * S));
         t.capacity = S;
     }
     return 0;
@@ -1260,7 +1277,7 @@ static int refresh_transposes(const DqnDev& d, DqnTrain& t, cudaStream_t s) {
 DqnFwdParams dqn_train_forward_params(const DqnDev& d, DqnTrain& t, const float4* pos, int n) {
     const int S = (n + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     DqnFwdParams fp{}; fp.pos = pos; fp.n = n; fp.c1 = d.c1; fp.m1 = d.m1; fp.b2 = d.b[1]; fp.b3 = d.b[2]; fp.b4 = d.b[3]; fp.w2p = d.w2p; fp.w3p = d.w3p; fp.w4p = d.w4p;
-    fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S;
+    fp.q = t.q; fp.q_stride = S; fp.h1t = t.h1t; fp.h2t = t.h2t; fp.h3t = t.h3t; fp.h_stride = S; fp.mask1 = t.mask1; fp.mask2 = t.mask2; fp.mask3 = t.mask3;
     return fp;
 }
 int dqn_train_prepare(DqnDev& d, DqnTrain& t, int n, cudaStream_t s) {           // everything a captured step must not contain: allocations, the first transposes, the side stream
@@ -1308,7 +1325,7 @@ int dqn_train_batch(DqnDev& d, DqnTrain& t, const float4* pos, const uint32_t* a
     } else if (t.fused_bwd) {
         // TD step: output-layer delta, both data products and both masks in ONE kernel; the three weight-gradient GEMMs then run side by side
         DqnBwdParams bp{}; bp.n = n; bp.S = S; bp.q = t.q; bp.actions = actions; bp.targets = const_cast<float*>(targets); if (tdp) bp.td = *tdp;
-        bp.w4 = d.w[3]; bp.h1t = t.h1t; bp.h2t = t.h2t; bp.h3t = t.h3t; bp.w3tp = t.w3tp; bp.w2tp = t.w2tp; bp.d3t = t.d3t; bp.d2t = t.d2t; bp.d1t = t.d1t;
+        bp.w4 = d.w[3]; bp.mask1 = t.mask1; bp.mask2 = t.mask2; bp.mask3 = t.mask3; bp.w3tp = t.w3tp; bp.w2tp = t.w2tp; bp.d3t = t.d3t; bp.d2t = t.d2t; bp.d1t = t.d1t;
         bp.g_out = t.g3; bp.gb4 = t.gb[3]; bp.scalars = t.scalars;
         rc = dqn_backward(bp, s); if (rc) return rc;
         const int ks = S >= 2048 ? 16 : (S >= 512 ? 4 : 1);

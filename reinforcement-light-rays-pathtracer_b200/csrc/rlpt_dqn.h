@@ -43,6 +43,7 @@ struct DqnFwdParams {
     const __nv_bfloat16 *w2p, *w3p, *w4p;
     float* q; int q_stride;                         // out: [144][q_stride], action-major (coalesced for producer and consumers)
     __nv_bfloat16 *h1t, *h2t, *h3t; int h_stride;   // optional: activations kept for the backward pass, feature-major [K_pad][h_stride]
+    uint32_t *mask1, *mask2, *mask3;                // optional, with the kept activations: relu'(h) as bit words [K_pad / 32][h_stride] (unit j = bit j % 32 of word j / 32)
     const float4* pos2; int n2; float* q2; int q_stride2;       // optional second batch evaluated by the same launch (no activations kept): tiles follow the first batch's
 };
 
@@ -63,6 +64,7 @@ struct DqnTrain {
     __nv_bfloat16 *w3tp = nullptr, *w2tp = nullptr; // the same transposes as k_dqn_backward streams them (packed chunks, wpack_offset)
     __nv_bfloat16 *h1t = nullptr, *h2t = nullptr, *h3t = nullptr, *xt = nullptr;
     __nv_bfloat16 *d3 = nullptr, *d2 = nullptr, *d3t = nullptr, *d2t = nullptr, *d1t = nullptr;
+    uint32_t *mask1 = nullptr, *mask2 = nullptr, *mask3 = nullptr;      // relu'(h1), relu'(h2), relu'(h3) as bit words [K_pad / 32][S] (k_dqn_forward -> k_dqn_backward)
     float* g3 = nullptr;                            // [S] per-ray output-layer gradient of the TD step (k_delta3 -> k_dw4_rank1)
     float *p2 = nullptr, *p1 = nullptr;             // pre-activation deltas [S][304], [S][208] (fp32 GEMM outputs)
     float* q = nullptr;                             // [144][S] predictions of the batch
@@ -85,7 +87,7 @@ void dqn_upload_cell_cos(const float* cos144);
 // k_dqn_backward's arguments (rlpt_dqn.cu): the TD step's backward data path of a batch
 struct DqnBwdParams {
     int n, S; const float* q; const uint32_t* actions; float* targets; DqnTdParams td; const float* w4;
-    const __nv_bfloat16 *h1t, *h2t, *h3t, *w3tp, *w2tp; __nv_bfloat16 *d3t, *d2t, *d1t; float *g_out, *gb4, *scalars;
+    const uint32_t *mask1, *mask2, *mask3; const __nv_bfloat16 *w3tp, *w2tp; __nv_bfloat16 *d3t, *d2t, *d1t; float *g_out, *gb4, *scalars;
 };
 int dqn_backward(const DqnBwdParams& p, cudaStream_t s);
 // One optimiser step on a batch (G/deep_learning/neural_q_pathtracer.cu:476-512): forward with kept activations, loss
