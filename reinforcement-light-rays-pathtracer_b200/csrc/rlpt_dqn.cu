@@ -301,7 +301,11 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
                 const ChunkRow& cr = table[srow];
                 const uint32_t bytes = cr.bytes;
                 mbar_expect_tx(&b_full[stage], bytes);
-                bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES, reinterpret_cast<const void*>(((uint64_t)cr.src_hi << 32) | cr.src_lo), bytes, &b_full[stage]);
+                {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(((uint64_t)cr.src_hi << 32) | cr.src_lo);
+                    const uint32_t piece = RLPT_DQN_PIECES > 1 ? (((bytes / RLPT_DQN_PIECES) + 127u) & ~127u) : bytes;       // (several bulk copies per chunk: an A/B switch)
+                    for (uint32_t o = 0; o < bytes; o += piece) bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES + o, src + o, min(piece, bytes - o), &b_full[stage]);
+                }
                 if (++srow == DQ_CHUNKS_PER_TILE) srow = 0;
                 if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
             }
@@ -539,7 +543,11 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_con
                 const ChunkRow& cr = table[srow];
                 const uint32_t bytes = cr.bytes;
                 mbar_expect_tx(&b_full[stage], bytes);
-                bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES, reinterpret_cast<const void*>(((uint64_t)cr.src_hi << 32) | cr.src_lo), bytes, &b_full[stage]);
+                {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(((uint64_t)cr.src_hi << 32) | cr.src_lo);
+                    const uint32_t piece = RLPT_DQN_PIECES > 1 ? (((bytes / RLPT_DQN_PIECES) + 127u) & ~127u) : bytes;       // (several bulk copies per chunk: an A/B switch)
+                    for (uint32_t o = 0; o < bytes; o += piece) bulk_copy_g2s(smem + SM_B0 + stage * DQ_STAGE_BYTES + o, src + o, min(piece, bytes - o), &b_full[stage]);
+                }
                 if (++srow == DQ_BWD_CHUNKS) srow = 0;
                 if (++stage == DQ_STAGES) { stage = 0; par ^= 1u; }
             }
