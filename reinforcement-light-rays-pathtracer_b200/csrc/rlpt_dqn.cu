@@ -82,20 +82,26 @@ __host__ __device__ __forceinline__ size_t operand_offset(int row, int k, int k_
 }
 
 // Packed weights of a layer as k_dqn_forward streams them (B operands): the layer's output rows are cut into N parts (layer 2: rows [0,160) and
-// [160,304), so that the epilogue of the first part runs under the MMAs of the second; layers 3 and 4: one part), each part into K chunks of 64
+// [160,304), so that the epilogue of the first part runs under the MMAs of the second; layers 3 and 4: one part), each part into K chunks of dq_kc
 // inputs; a chunk is one contiguous block = one bulk copy = the B operand of kw / 16 MMAs with N = the part's rows (large N: an SS-mode MMA re-reads
 // its 4 KB of A from shared memory, so N = 64 pieces are shared-memory-bound and issue-bound). Inside a chunk: canonical K-major no-swizzle form,
 // 8x8 core matrices of 128 bytes, K-adjacent ones 128 bytes apart (LBO), 8-row groups kw * 16 bytes apart (SBO).
-#ifndef RLPT_DQN_KC
-#define RLPT_DQN_KC 64
+#ifndef RLPT_DQN_KC_A
+#define RLPT_DQN_KC_A 112        // inputs per weight chunk of the 208-input layers (2 and 4; 208 = 112 + 96)
+#endif
+#ifndef RLPT_DQN_KC_B
+#define RLPT_DQN_KC_B 80         // ... of the 304-input layer (3; 304 = 3 x 80 + 64)
 #endif
 #ifndef RLPT_DQN_STAGES
-#define RLPT_DQN_STAGES 3
+#define RLPT_DQN_STAGES 2
 #endif
 #ifndef RLPT_DQN_PIECES
 #define RLPT_DQN_PIECES 1
 #endif
-constexpr int DQ_KC = RLPT_DQN_KC;                                          // inputs per weight chunk
+// Inputs per weight chunk. One cp.async.bulk occupies the SM's copy engine for >= ~360 cycles whatever its size, and copies are served one after the other
+// (scratch/ubench/copy_bw.cu: 5 KB copies 14 B/cycle, 20 KB 57, 33 KB 91, >= 40 KB 113 B/cycle per SM): few large chunks, not many small ones.
+__host__ __device__ constexpr int dq_kc(int k_pad) { return k_pad == DQ_K3 ? RLPT_DQN_KC_B : RLPT_DQN_KC_A; }
+static_assert(RLPT_DQN_KC_A % 16 == 0 && RLPT_DQN_KC_B % 16 == 0, "chunks are whole MMA K steps");
 constexpr int DQ_L2_SPLIT = 160;                                           // layer 2's first N part
 // The packed weights exist DQ_REPLICAS times in global memory (replica r at byte offset r * stride): CTA b streams replica b % DQ_REPLICAS. All CTAs of a
 // full-frame forward walk the chunk stream in step, so without replicas 148 SMs ask the same 128-byte lines of the same L2 slices at the same moment
@@ -107,16 +113,16 @@ constexpr int DQ_REPLICAS = RLPT_DQN_REPLICAS;
 constexpr size_t DQ_W2P_STRIDE = 2 * (size_t)DQ_N2 * DQ_K2 + 128 * 3, DQ_W3P_STRIDE = 2 * (size_t)DQ_N3 * DQ_K3 + 128 * 5, DQ_W4P_STRIDE = 2 * (size_t)DQ_N4 * DQ_K4 + 128 * 7;       // bytes; odd multiples of a line apart
 __host__ __device__ __forceinline__ size_t wpack_offset(int n_split, int row, int k, int n_pad, int k_pad) {
     const int n0 = (n_split > 0 && row >= n_split) ? n_split : 0, rows = n_split > 0 ? (row >= n_split ? n_pad - n_split : n_split) : n_pad;
-    const int kc = k / DQ_KC, kw = min(DQ_KC, k_pad - kc * DQ_KC), r = row - n0, kk = k - kc * DQ_KC;
-    return (size_t)n0 * k_pad * 2 + (size_t)rows * DQ_KC * 2 * kc + (size_t)(r >> 3) * ((size_t)kw * 16) + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
+    const int KC = dq_kc(k_pad), kc = k / KC, kw = min(KC, k_pad - kc * KC), r = row - n0, kk = k - kc * KC;
+    return (size_t)n0 * k_pad * 2 + (size_t)rows * KC * 2 * kc + (size_t)(r >> 3) * ((size_t)kw * 16) + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
 }
 
 __constant__ float c_dq_cos[DQ_OUT];                                     // cos(theta) of the 144 grid cells (the tracer's table; dqn_upload_cell_cos)
 void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos144, sizeof(float) * DQ_OUT); }
 // ------------------------------------------------------------------------------------------------ forward kernel
 constexpr int DQ_STAGES = RLPT_DQN_STAGES;
-constexpr uint32_t DQ_STAGE_BYTES = DQ_N3 * DQ_KC * 2;                     // largest chunk: layer 3, 208 rows x 64 inputs
-static_assert(DQ_L2_SPLIT * DQ_KC * 2 <= DQ_STAGE_BYTES && DQ_N4 * DQ_KC * 2 <= DQ_STAGE_BYTES, "chunk fits a stage");
+constexpr uint32_t dq_max3(uint32_t a, uint32_t b, uint32_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+constexpr uint32_t DQ_STAGE_BYTES = (dq_max3(DQ_L2_SPLIT * dq_kc(DQ_K2) * 2, DQ_N3 * dq_kc(DQ_K3) * 2, DQ_N4 * dq_kc(DQ_K4) * 2) + 127u) & ~127u;       // largest chunk (160 rows x 112 inputs = 35 KB)
 constexpr uint32_t SM_A1 = 0;                                             // 128 x 208 bf16: layer-2 A, later layer-4 A
 constexpr uint32_t SM_A2 = SM_A1 + DQ_TILE * DQ_K2 * 2;                   // 128 x 304 bf16: layer-3 A
 constexpr uint32_t SM_B0 = SM_A2 + DQ_TILE * DQ_K3 * 2;                   // DQ_STAGES weight chunks
@@ -144,7 +150,7 @@ static_assert(SM_BAR % 8 == 0 && SM_B0 % 128 == 0 && DQ_STAGE_BYTES % 128 == 0, 
 // and the next tile's first chunks included -- weights do not depend on activations). The MMA lane commits every N part to its own mbarrier, so
 // layer 2's first part is converted (TMEM -> +bias, ReLU -> bf16 A operand of layer 3) under the MMAs of its second part. (One lane doing both, with
 // the chunk geometry recomputed per chunk, spent ~1000 cycles of dependent scalar instructions per chunk -- three times the chunk's MMA time.)
-constexpr int DQ_NKC2 = (DQ_K2 + DQ_KC - 1) / DQ_KC, DQ_NKC3 = (DQ_K3 + DQ_KC - 1) / DQ_KC, DQ_NKC4 = (DQ_K4 + DQ_KC - 1) / DQ_KC;       // K chunks per layer (4, 5, 4 at 64 inputs per chunk)
+constexpr int DQ_NKC2 = (DQ_K2 + dq_kc(DQ_K2) - 1) / dq_kc(DQ_K2), DQ_NKC3 = (DQ_K3 + dq_kc(DQ_K3) - 1) / dq_kc(DQ_K3), DQ_NKC4 = (DQ_K4 + dq_kc(DQ_K4) - 1) / dq_kc(DQ_K4);       // K chunks per layer (2, 4, 2)
 constexpr int DQ_EPI_GROUPS = RLPT_DQN_EPI_GROUPS, DQ_EPI_THREADS = 128 * DQ_EPI_GROUPS, DQ_CHUNKS_PER_TILE = 2 * DQ_NKC2 + DQ_NKC3 + DQ_NKC4;
 constexpr int DQ_COMPUTE_THREADS = DQ_EPI_THREADS + 32, DQ_THREADS = DQ_EPI_THREADS + 64;        // epilogue warps + MMA warp (named barrier 1) + copy warp
 #ifdef RLPT_DQN_TRACE           // debug build: phase timestamps of CTA 0's second tile (epilogue thread 0 and the issuer lane), printed at kernel end
@@ -157,21 +163,21 @@ constexpr int DQ_COMPUTE_THREADS = DQ_EPI_THREADS + 32, DQ_THREADS = DQ_EPI_THRE
 #define DQ_TR_PRINT(who) do {} while (0)
 #endif
 
-struct ChunkInfo { const __nv_bfloat16* src; int rows, kw, kc, last, part; uint32_t a_off, a_kpad, tmem_col; };
+struct ChunkInfo { const __nv_bfloat16* src; int rows, kw, kc, k0, last, part; uint32_t a_off, a_kpad, tmem_col; };
 __device__ __forceinline__ ChunkInfo chunk_info(const __nv_bfloat16* w2p, const __nv_bfloat16* w3p, const __nv_bfloat16* w4p, int s) {          // s = position in the tile's stream, 0..16
     ChunkInfo ci; const size_t rep = blockIdx.x % DQ_REPLICAS;       // (strides are in bytes, pointers in bf16)
     if (s < 2 * DQ_NKC2) {
         const int part = s >= DQ_NKC2 ? 1 : 0, kc = s - part * DQ_NKC2, n0 = part ? DQ_L2_SPLIT : 0;
-        ci.rows = part ? DQ_N2 - DQ_L2_SPLIT : DQ_L2_SPLIT; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K2 - kc * DQ_KC); ci.last = kc == DQ_NKC2 - 1; ci.part = part;
-        ci.src = w2p + rep * (DQ_W2P_STRIDE / 2) + (size_t)n0 * DQ_K2 + (size_t)ci.rows * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
+        ci.rows = part ? DQ_N2 - DQ_L2_SPLIT : DQ_L2_SPLIT; ci.kc = kc; ci.k0 = kc * dq_kc(DQ_K2); ci.kw = min(dq_kc(DQ_K2), DQ_K2 - ci.k0); ci.last = kc == DQ_NKC2 - 1; ci.part = part;
+        ci.src = w2p + rep * (DQ_W2P_STRIDE / 2) + (size_t)n0 * DQ_K2 + (size_t)ci.rows * ci.k0; ci.a_off = SM_A1; ci.a_kpad = DQ_K2; ci.tmem_col = (uint32_t)n0;
     } else if (s < 2 * DQ_NKC2 + DQ_NKC3) {
         const int kc = s - 2 * DQ_NKC2;
-        ci.rows = DQ_N3; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K3 - kc * DQ_KC); ci.last = kc == DQ_NKC3 - 1; ci.part = 0;
-        ci.src = w3p + rep * (DQ_W3P_STRIDE / 2) + (size_t)DQ_N3 * DQ_KC * kc; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
+        ci.rows = DQ_N3; ci.kc = kc; ci.k0 = kc * dq_kc(DQ_K3); ci.kw = min(dq_kc(DQ_K3), DQ_K3 - ci.k0); ci.last = kc == DQ_NKC3 - 1; ci.part = 0;
+        ci.src = w3p + rep * (DQ_W3P_STRIDE / 2) + (size_t)DQ_N3 * ci.k0; ci.a_off = SM_A2; ci.a_kpad = DQ_K3; ci.tmem_col = DQ_N2;
     } else {
         const int kc = s - 2 * DQ_NKC2 - DQ_NKC3;
-        ci.rows = DQ_N4; ci.kc = kc; ci.kw = min(DQ_KC, DQ_K4 - kc * DQ_KC); ci.last = kc == DQ_NKC4 - 1; ci.part = 0;
-        ci.src = w4p + rep * (DQ_W4P_STRIDE / 2) + (size_t)DQ_N4 * DQ_KC * kc; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
+        ci.rows = DQ_N4; ci.kc = kc; ci.k0 = kc * dq_kc(DQ_K4); ci.kw = min(dq_kc(DQ_K4), DQ_K4 - ci.k0); ci.last = kc == DQ_NKC4 - 1; ci.part = 0;
+        ci.src = w4p + rep * (DQ_W4P_STRIDE / 2) + (size_t)DQ_N4 * ci.k0; ci.a_off = SM_A1; ci.a_kpad = DQ_K4; ci.tmem_col = 0;
     }
     return ci;
 }
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_forward(const __grid_cons
     ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
     if (t < DQ_CHUNKS_PER_TILE) {
         const ChunkInfo ci = chunk_info(p.w2p, p.w3p, p.w4p, t);
-        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.kc * (DQ_KC * 16u);
+        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.k0 * 16u;
         ChunkRow cr;
         cr.src_lo = (uint32_t)reinterpret_cast<uint64_t>(ci.src); cr.src_hi = (uint32_t)(reinterpret_cast<uint64_t>(ci.src) >> 32); cr.bytes = (uint32_t)ci.rows * (uint32_t)ci.kw * 2u;
         cr.a_lo = ((a_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); cr.a_hi = ((ci.a_kpad * 16u) >> 4) | (1u << 14); cr.b_hi = (((uint32_t)ci.kw * 16u) >> 4) | (1u << 14);
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(DQ_THREADS, 1) k_dqn_backward(const __grid_con
     ChunkRow* table = reinterpret_cast<ChunkRow*>(smem + SM_TABLE);
     if (t < DQ_BWD_CHUNKS) {
         const ChunkInfo ci = chunk_info(p.w3tp, p.w2tp, nullptr, t);
-        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.kc * (DQ_KC * 16u);
+        const uint32_t a_addr = smem_u32(smem + ci.a_off) + (uint32_t)ci.k0 * 16u;
         ChunkRow cr;
         cr.src_lo = (uint32_t)reinterpret_cast<uint64_t>(ci.src); cr.src_hi = (uint32_t)(reinterpret_cast<uint64_t>(ci.src) >> 32); cr.bytes = (uint32_t)ci.rows * (uint32_t)ci.kw * 2u;
         cr.a_lo = ((a_addr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); cr.a_hi = ((ci.a_kpad * 16u) >> 4) | (1u << 14); cr.b_hi = (((uint32_t)ci.kw * 16u) >> 4) | (1u << 14);
