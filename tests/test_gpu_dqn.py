@@ -203,6 +203,41 @@ def test_training_step_gradients_match_numpy(ctx, golden_scenes, dqn_golden):
     assert np.array_equal(ctx.dqn_get_params(), dqn_golden["params"])              # apply_update=False left the weights alone
 
 
+def test_fused_backward_kernel_matches_the_unfused_chain(golden_scenes, dqn_golden, monkeypatch):
+    """k_dqn_backward (output-layer delta, both data products and both ReLU masks in one tcgen05 kernel, masks read from the bit words the
+    forward pass leaves behind) against the chain it replaces (k_delta3 + two GEMMs + two mask kernels reading the kept activations;
+    RLPT_NQ_FUSED_BWD=0): same bf16 roundings at the same places, so loss and gradients agree up to the order of the fp32 sums
+    (tolerance 1e-4 relative L2 per tensor) -- on a ragged batch, a full one, and after Adam steps (the packed transposes the fused kernel
+    streams are kept current by k_adam_fused, the plain ones the chain multiplies by as well)."""
+    import rlpt
+    s = golden_scenes["cornell"]
+    rs = np.random.RandomState(23)
+    cases = []
+    for n in (300, 4096):
+        pos = dqn_golden["pos"][rs.randint(0, len(dqn_golden["pos"]), n)]
+        cases.append((pos, rs.randint(0, 144, n).astype(np.uint32), (rs.rand(n) * 1500).astype(np.float32)))
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("RLPT_NQ_FUSED_BWD", fused)              # read when the context's training state is created
+        c = rlpt.Context(0, width=64, height=64, spp=1, max_bounces=80)
+        load_scene(c, s)
+        c.dqn_set_params(dqn_golden["params"])
+        res = []
+        for pos, actions, targets in cases:
+            res.append((c.dqn_train_batch(pos, actions, targets, apply_update=False), c.dqn_get_grads()))
+        for _ in range(3):
+            c.dqn_train_batch(*cases[1])                            # three Adam steps, then the gradients at the new parameters
+        res.append((c.dqn_train_batch(*cases[0], apply_update=False), c.dqn_get_grads()))
+        res.append((0.0, c.dqn_get_params()))
+        out[fused] = res
+        del c
+    for k, ((la, ga), (lb, gb)) in enumerate(zip(out["1"], out["0"])):
+        assert abs(la - lb) <= 1e-5 * max(abs(lb), 1e-30), (la, lb)
+        rep = _tensor_report(ga, gb, 342)
+        # (after the Adam steps the two parameter sets differ in the last bits, and a hidden unit at the edge of its ReLU may flip: looser bar there)
+        assert all(r <= (1e-4 if k < 2 else 2e-3) for _, r in rep), (k, rep)
+
+
 def test_supervised_step_matches_numpy_and_fits_a_q_table(ctx, golden_scenes, dqn_golden):
     """The offline trainer's step (NN_Q_Value_Trainer/Source/main.cu:67-135): squared distance over all 144 outputs. Gradients
     against the numpy restatement (same bars as the TD step), then a few hundred Adam steps on a fixed batch of 128 (the
