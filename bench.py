@@ -75,6 +75,28 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc = [], None
+        # NVML polled from a thread every ~2 ms (the timed region of the default run is only ~80 ms: nvidia-smi -lms 20 yields five samples);
+        # nvidia-smi stays as the fallback when the binding is missing
+        self.nvml_rows, self._stop = [], False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)); pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0; rs = int(reasons_fn(h))
+                        self.nvml_rows.append((time.perf_counter(), sm, smax, pw, rs))
+                    except Exception:
+                        break
+                    time.sleep(0.002)
+            self.nvml_t = threading.Thread(target=poll, daemon=True)
+            self.nvml_t.start()
+        except Exception:
+            self.nvml_rows = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -88,6 +110,15 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
+        self._stop = True
+        if self.nvml_rows:
+            rows = [r for r in self.nvml_rows if t0 <= r[0] <= t1] or self.nvml_rows
+            sm = sorted(r[1] for r in rows)
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            reasons = [n for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap") if any(r[4] & bits[n] for r in rows)]
+            if self.proc:
+                self.proc.terminate()
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][2], "power_w_max": max(r[3] for r in rows), "reasons": reasons, "samples": len(rows), "source": "NVML polled every 2 ms"}
         if not self.proc:
             return None
         time.sleep(0.15)
