@@ -215,7 +215,7 @@ __device__ __forceinline__ unsigned long long unit_scan_mask(const SceneView<STA
 // Closest hit of one ray: Ray::closest_intersection (G/rays/ray.cu:16-36). (dx,dy,dz) is the normalised direction;
 // H = SCREEN_HEIGHT. Result: best_t in the reference's units and the primitive id (-1 = NOTHING). The winner is the
 // lexicographic minimum of (t, gid), which is what the reference's scan order with strict < produces.
-template <bool STAGED, bool COUNT>
+template <bool STAGED, bool COUNT, bool ALLOW_BVH = true>
 __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox, float oy, float oz, float dx, float dy, float dz, float H,
                                             float& best_t, int& best_gid, float& sdx, float& sdy, float& sdz, unsigned& n_tri, unsigned& n_box) {
     sdx = RLPT_MUL(dx, H); sdy = RLPT_MUL(dy, H); sdz = RLPT_MUL(dz, H);          // dir * SCREEN_HEIGHT (ray.cu:53)
@@ -282,7 +282,9 @@ __device__ __forceinline__ void closest_hit(const SceneView<STAGED>& v, float ox
         }
         return;
     }
-    bvh4_closest_hit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, sdx, sdy, sdz, best_t, best_gid, n_tri, n_box);
+    // (k_isect is launched for brute-force scenes only -- BVH scenes go to k_isect_bvh -- and is instantiated without the tree walk: its 96-entry local stack and
+    // registers are then not part of a kernel that is tuned to 40 registers)
+    if (ALLOW_BVH) bvh4_closest_hit<STAGED, COUNT>(v, ox, oy, oz, a0, a1, a2, sdx, sdy, sdz, best_t, best_gid, n_tri, n_box);
 }
 
 // Closest hit for a warp of CAMERA rays: same origin, directions within a pixel or two. Phase 1 is done once per warp instead
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(BLOCK, RLPT_ISECT_MINBLOCKS) k_isect(const __g
             if (slot < dyn.capture_max) { p.capture_o[slot] = make_float4(ox, oy, oz, 0.f); p.capture_d[slot] = make_float4(dx, dy, dz, 0.f); }
         }
         float t, sdx, sdy, sdz; int gid;
-        closest_hit<STAGED, true>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
+        closest_hit<STAGED, true, false>(v, ox, oy, oz, dx, dy, dz, H, t, gid, sdx, sdy, sdz, n_tri, n_box);
         __stcs(p.hit + sq.base + i, make_float2(t, __int_as_float(gid)));
     }
     flush_work_counters(p, n_tri, n_box);
@@ -1059,7 +1061,7 @@ void launch_tail(const FrameParams& p, const FrameDyn& dyn, int method, int boun
 }
 void launch_isect(const FrameParams& p, const FrameDyn& dyn, int bounce, int grid, size_t smem, cudaStream_t s) {
     const bool staged = scene_staged(p.scene);
-    if (!p.scene.brute && p.cursor) {
+    if (!p.scene.brute) {                                                  // (p.cursor is set by every caller: the frame loops allocate it with the queues)
         const size_t sm = smem + B4_CTA_BYTES;
         if (bounce == 0) { if (staged) k_isect_bvh<true, true><<<grid, BLOCK, sm, s>>>(p, dyn, 0); else k_isect_bvh<false, true><<<grid, BLOCK, sm, s>>>(p, dyn, 0); }
         else { if (staged) k_isect_bvh<true, false><<<grid, BLOCK, sm, s>>>(p, dyn, bounce); else k_isect_bvh<false, false><<<grid, BLOCK, sm, s>>>(p, dyn, bounce); }
