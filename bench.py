@@ -97,6 +97,8 @@ class ClockSampler:
             self.nvml_t.start()
         except Exception:
             self.nvml_rows = None
+        if self.nvml_rows is not None and not os.environ.get("RLPT_BENCH_SMI"):
+            return                                             # NVML answers: no nvidia-smi child per rank (eight of them polling beside eight ranks is host noise)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)

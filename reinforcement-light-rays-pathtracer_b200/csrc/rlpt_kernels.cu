@@ -1455,7 +1455,7 @@ void launch_merge(const RadianceDev& rm, const float* surf_lum_over_pi, float th
 // NVLink / NVSwitch), merges, rebuilds the CDFs of the slice and stores the results into every rank's tables (P2P stores):
 // reduce-scatter, the merge and the all-gather in one kernel, 1/N of the all-reduce's traffic per GPU on the way in, only
 // the volumes that were actually visited on the way out. Replicas end bit-identical by construction (one owner computes
-// each volume; the sum runs over the ranks in rank order). Synchronisation is two flag rounds in peer memory:
+// each volume; the sum runs over the ranks in rank order). Each rank clears its own accumulators after the exchange. Synchronisation is two flag rounds in peer memory:
 //   start  block 0 announces "my accumulators of this epoch are complete" (the kernel is stream-ordered after the tracing)
 //          to every rank; every CTA waits until all ranks have announced
 //   end    the last CTA to finish announces "my slice is stored everywhere"; k_wait_peers (next in the stream) waits for
@@ -1465,6 +1465,9 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned
 // A rank that never arrives (it skipped its merge, failed before it, or rebuilt its map on its own) must not hang the others inside a
 // kernel: every wait gives up after P2P_TIMEOUT_NS of %globaltimer and raises the rank's error word (pt.error, checked by the
 // host after every merge; the exchange is then marked broken and the frame fails with RLPT_ERR_COLLECTIVE).
+#ifndef RLPT_P2P_REMOTE_ZERO
+#define RLPT_P2P_REMOTE_ZERO 0        // 1: the consuming rank clears the accumulator cells through peer stores (round 1's form)
+#endif
 constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ bool wait_flag(const unsigned* p, unsigned epoch, unsigned* error) {
@@ -1513,7 +1516,11 @@ __global__ void __launch_bounds__(BLOCK) k_merge_cdf_p2p(RadianceDev rm, const _
                 uint32_t cnt = 0; float sum = 0.f;
 #pragma unroll
                 for (int r = 0; r < MAX_PEERS; ++r) {                     // rank order: the same sum on whichever rank owns the volume
+#if RLPT_P2P_REMOTE_ZERO
                     if (r < pt.world && cn[c][r]) { cnt += cn[c][r]; sum += sm[c][r]; pt.acc_cnt[r][base + k] = 0u; pt.acc_sum[r][base + k] = 0.f; }
+#else
+                    if (r < pt.world && cn[c][r]) { cnt += cn[c][r]; sum += sm[c][r]; }       // (the accumulators are cleared by their owner afterwards: launch_merge_p2p)
+#endif
                 }
                 if (cnt) {
                     const float vs = (float)rm.visits[base + k];
@@ -1565,6 +1572,13 @@ void launch_merge_p2p(const RadianceDev& rm, const PeerTables& pt, const float* 
     int grid = (slice + warps_per_block - 1) / warps_per_block; if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
     k_merge_cdf_p2p<<<grid, BLOCK, 0, s>>>(rm, pt, surf_lum_over_pi, threshold, epoch, done_counter);
     k_wait_peers<<<1, 32, 0, s>>>(pt.flags[pt.rank], pt.world, epoch, pt.error);
+    // Every rank has now read this rank's accumulators (its "slice stored" announcement comes after its loads): they are cleared HERE, locally (2 x 14 MB of
+    // HBM writes for Cornell), instead of cell by cell through peer stores by whichever rank consumed them -- at 8 GPUs that was 7/8 of 28 MB of NVLink stores
+    // per rank and frame inside the exchange kernel.
+#if !RLPT_P2P_REMOTE_ZERO
+    cudaMemsetAsync(rm.acc_sum, 0, sizeof(float) * (size_t)rm.n_vol * CELLS, s);
+    cudaMemsetAsync(rm.acc_cnt, 0, sizeof(uint32_t) * (size_t)rm.n_vol * CELLS, s);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ frame buffer
