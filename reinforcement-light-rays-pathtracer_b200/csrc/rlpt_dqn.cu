@@ -5,15 +5,22 @@
 // (N/dq_network.cu:37-49, called at G/deep_learning/neural_q_pathtracer.cu:321-325,440-444,494-499).
 //
 // One CTA = one tile of 128 rays = the M dimension of tcgen05.mma (cta_group::1), accumulators in TMEM (128 lanes x
-// 512 fp32 columns: layer 2 in columns [0,304), layer 3 in [304,512), layer 4 reuses [0,144)). Per tile:
+// 512 fp32 columns: layer 2 in columns [0,304), layer 3 in [304,512), layer 4 reuses [0,144)). 576 threads per CTA:
+// 16 epilogue / layer-1 warps, one MMA warp, one copy warp. Per tile:
 //   layer 1   fp32 on the CUDA cores, c1 - M1 x (rlpt_dqn.h), ReLU, written as the bf16 A operand into shared memory
-//   layer 2-4 weights stream from L2 in 64-row chunks with cp.async.bulk into a double-buffered B operand; one elected
-//             thread issues K/16 tcgen05.mma per chunk; tcgen05.commit signals mbarriers (buffer free / layer done);
-//             the epilogue reads TMEM with tcgen05.ld (thread t <-> lane t <-> ray t), adds the bias, applies ReLU and
-//             writes the next layer's A operand (bf16) straight back into shared memory -- activations never touch HBM
+//   layer 2-4 the packed weights (wpack_offset: N parts x K chunks of 27-36 KB) stream from L2 through a two-stage ring of
+//             cp.async.bulk copies issued by the copy lane from a chunk table in shared memory; the MMA lane issues kw / 16
+//             tcgen05.mma per chunk with the part's full N; tcgen05.commit signals mbarriers (stage free / N part done);
+//             the epilogue warps read TMEM with tcgen05.ld.32x32b.x32 (thread t <-> lane t & 127 <-> ray, the four warpgroups
+//             take 32-column blocks in turn), add the bias, apply ReLU and write the next layer's A operand (bf16) straight
+//             back into shared memory -- activations never touch HBM (the training instantiation also keeps them, and relu'
+//             as bit words, for the backward pass)
 //   output    Q values, fp32, action-major [144][n] so that producer and consumers are coalesced
+// k_dqn_backward (the TD step's backward data path) has the same shape; k_gemm_bf16_tn (weight gradients) is a single-shot
+// cp.async GEMM. DESIGN.md section 3b has the measurements that led here.
 // Operand layout (both A and B): K-major, SWIZZLE_NONE canonical form: 8x8 core matrices of 128 contiguous bytes
-// (8 rows x 16 bytes), K-adjacent core matrices 128 bytes apart (LBO), 8-row groups K_pad*16 bytes apart (SBO).
+// (8 rows x 16 bytes), K-adjacent core matrices 128 bytes apart (LBO), 8-row groups K_pad*16 bytes apart (SBO; kw*16 inside a
+// streamed weight chunk).
 #include "rlpt_dqn.h"
 
 #include <cmath>

@@ -26,13 +26,13 @@ struct DqnHost {
 // Device state. fp32 master parameters (the optimiser works on these) and the operands derived from them:
 //   layer 1 is affine in the 3-vector x because the input is (v_i - x) for every scene vertex v_i (nn_rendering_helpers.cu:280-298):
 //   W1 (v - 1 (x) x) + b1 = c1 - M1 x with c1 = b1 + W1 v, M1[:, d] = sum of the columns i of W1 with i % 3 == d; evaluated in fp32.
-//   layers 2..4: bf16 copies in the tcgen05 shared-memory operand layout (K-major, no swizzle, 8x8 core matrices).
+//   layers 2..4: bf16 copies in the tcgen05 shared-memory operand layout (K-major, no swizzle, 8x8 core matrices), cut into the chunks the kernel copies.
 struct DqnDev {
     int k_in = 0;
     float* w[4] = { nullptr, nullptr, nullptr, nullptr }; float* b[4] = { nullptr, nullptr, nullptr, nullptr };
     float* vertices = nullptr;                      // [k_in] scene vertices, the network's constant input part
     float *c1 = nullptr, *m1 = nullptr;             // [200], [200][3]
-    __nv_bfloat16 *w2p = nullptr, *w3p = nullptr, *w4p = nullptr;       // packed [N_pad][K_pad]
+    __nv_bfloat16 *w2p = nullptr, *w3p = nullptr, *w4p = nullptr;       // packed B operands as k_dqn_forward streams them (wpack_offset in rlpt_dqn.cu: N parts x K chunks)
     bool ready = false;
 };
 
