@@ -59,7 +59,6 @@ struct rlpt_ctx {
     NqTrainState nqt{}; int nqt_n = 0; float *d_nqt_qcur = nullptr, *d_nqt_qnext = nullptr, *d_nqt_targets = nullptr, *d_nqt_loss = nullptr; int nqt_batch = 0;
     // CUDA graph of one full-batch optimiser step + fixed staging buffers for the batch's slice of the ray arrays
     int nq_graphs = 1; cudaGraphExec_t nq_graph_exec = nullptr; int nq_graph_batch = 0;
-    float4 *d_nqg_loc = nullptr, *d_nqg_sloc = nullptr; uint32_t *d_nqg_action = nullptr, *d_nqg_state = nullptr; float *d_nqg_reward = nullptr, *d_nqg_discount = nullptr; int nqg_capacity = 0;
     float nq_epsilon = 0.05f, nq_eps_decay = 0.01f, nq_eps_min = 0.05f, nq_lr = 1e-3f; double nq_loss_total = 0.0;     // EPSILON_START / DECAY / MIN (G/constants/deep_learning_settings.h:5-7)
     float* d_nq_q = nullptr; size_t nq_q_capacity = 0;           // Q values of the live paths, [144][capacity]
     // wavefront state
@@ -139,8 +138,6 @@ static void free_lanes(rlpt_ctx* c) {
 static void nq_graph_reset(rlpt_ctx* c) { if (c->nq_graph_exec) { cudaGraphExecDestroy(c->nq_graph_exec); c->nq_graph_exec = nullptr; } c->nq_graph_batch = 0; }
 static void free_nqt(rlpt_ctx* c) {
     nq_graph_reset(c);
-    cudaFree(c->d_nqg_loc); cudaFree(c->d_nqg_sloc); cudaFree(c->d_nqg_action); cudaFree(c->d_nqg_state); cudaFree(c->d_nqg_reward); cudaFree(c->d_nqg_discount);
-    c->d_nqg_loc = c->d_nqg_sloc = nullptr; c->d_nqg_action = c->d_nqg_state = nullptr; c->d_nqg_reward = c->d_nqg_discount = nullptr;
     cudaFree(c->nqt.loc); cudaFree(c->nqt.sloc); cudaFree(c->nqt.dir); cudaFree(c->nqt.thr); cudaFree(c->nqt.state); cudaFree(c->nqt.reward); cudaFree(c->nqt.discount);
     cudaFree(c->nqt.action); cudaFree(c->nqt.alive); cudaFree(c->d_nqt_qcur); cudaFree(c->d_nqt_qnext); cudaFree(c->d_nqt_targets); cudaFree(c->d_nqt_loss);
     c->nqt = NqTrainState{}; c->nqt_n = 0; c->nqt_batch = 0; c->d_nqt_qcur = c->d_nqt_qnext = c->d_nqt_targets = c->d_nqt_loss = nullptr;
@@ -1155,8 +1152,6 @@ static int ensure_nqt(rlpt_ctx* c, int batch) {
     const int S = (batch + DQ_TILE - 1) / DQ_TILE * DQ_TILE;
     CK(cudaMalloc(&c->d_nqt_qcur, sizeof(float) * DQ_OUT * (size_t)n)); CK(cudaMalloc(&c->d_nqt_qnext, sizeof(float) * DQ_OUT * (size_t)S));
     CK(cudaMalloc(&c->d_nqt_targets, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqt_loss, 4)); CK(cudaMemset(c->d_nqt_loss, 0, 4));
-    CK(cudaMalloc(&c->d_nqg_loc, sizeof(float4) * (size_t)S)); CK(cudaMalloc(&c->d_nqg_sloc, sizeof(float4) * (size_t)S)); CK(cudaMalloc(&c->d_nqg_action, 4 * (size_t)S));
-    CK(cudaMalloc(&c->d_nqg_state, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqg_reward, 4 * (size_t)S)); CK(cudaMalloc(&c->d_nqg_discount, 4 * (size_t)S));
     c->nqt_n = n; c->nqt_batch = batch;
     return RLPT_OK;
 }

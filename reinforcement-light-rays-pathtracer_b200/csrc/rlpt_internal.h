@@ -116,8 +116,6 @@ struct NqTrainState {
 void launch_nqt_init(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, cudaStream_t s);
 void launch_nqt_sample(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, const float* q, int q_stride, float epsilon, cudaStream_t s);
 void launch_nqt_trace(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, int grid, size_t smem, cudaStream_t s);
-void launch_nqt_stage(const NqTrainState& st, int start, int n, float4* loc, float4* sloc, uint32_t* action, uint32_t* state, float* reward, float* discount, cudaStream_t s);
-void launch_nqt_targets(const NqTrainState& st, int start, int n, const float* q_next, int q_stride, float* targets, cudaStream_t s);
 void launch_nqt_respawn(const FrameParams& p, const FrameDyn& dyn, const NqTrainState& st, int bounce, cudaStream_t s);
 void launch_add_scalar(float* dst, const float* src, cudaStream_t s);
 // Neural-Q wavefront (rlpt_kernels.cu): trace without sampling (the direction comes from the network), and the sampler

@@ -1313,37 +1313,8 @@ void launch_nqt_trace(const FrameParams& p, const FrameDyn& dyn, const NqTrainSt
     if (staged) k_nqt_trace<true><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce); else k_nqt_trace<false><<<grid, BLOCK, smem, s>>>(p, dyn, st, bounce);
 }
 
-// compute_td_targets (nn_rendering_helpers.cu:91-140): reward + discount * max_a Q(s', a) cos(theta_a); terminal: the reward
-// Four threads per ray (36 cells each, combined with two shuffles): a batch is only 4096 rays, one thread per ray leaves the GPU empty (9 us -> 3).
-__global__ void k_nqt_targets(NqTrainState st, int start, int n, const float* __restrict__ q_next, int q_stride, float* __restrict__ targets) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, j = tid >> 2, part = tid & 3;
-    const bool valid = j < n;
-    float best = 0.f;
-    if (valid) {
-#pragma unroll 6
-        for (int k = part * 36; k < part * 36 + 36; ++k) best = fmaxf(best, __ldg(q_next + (size_t)k * q_stride + j) * c_cell_cos[k]);
-    }
-    best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 1)); best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, 2));
-    if (!valid || part) return;
-    const int i = start + j;
-    float target = st.reward[i];
-    if (st.state[i] != 1u) target += best * st.discount[i];
-    targets[j] = target;
-}
-// the batch's slice of the ray arrays -> fixed staging buffers (the captured optimiser step reads only those)
-__global__ void k_nqt_stage(NqTrainState st, int start, int n, float4* __restrict__ loc, float4* __restrict__ sloc, uint32_t* __restrict__ action,
-                            uint32_t* __restrict__ state, float* __restrict__ reward, float* __restrict__ discount) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const int i = start + j;
-    loc[j] = st.loc[i]; sloc[j] = st.sloc[i]; action[j] = st.action[i]; state[j] = st.state[i]; reward[j] = st.reward[i]; discount[j] = st.discount[i];
-}
-void launch_nqt_stage(const NqTrainState& st, int start, int n, float4* loc, float4* sloc, uint32_t* action, uint32_t* state, float* reward, float* discount, cudaStream_t s) {
-    k_nqt_stage<<<(n + 255) / 256, 256, 0, s>>>(st, start, n, loc, sloc, action, state, reward, discount);
-}
-void launch_nqt_targets(const NqTrainState& st, int start, int n, const float* q_next, int q_stride, float* targets, cudaStream_t s) {
-    k_nqt_targets<<<(4 * n + 127) / 128, 128, 0, s>>>(st, start, n, q_next, q_stride, targets);
-}
+// (compute_td_targets, nn_rendering_helpers.cu:91-140 -- reward + discount * max_a Q(s', a) cos(theta_a); terminal: the reward -- is evaluated inside the
+// training step's backward kernel, rlpt_dqn.cu: k_dqn_backward phase 0 / k_delta3; the batch's slice of the ray arrays is read in place)
 
 // sample_random_scene_pos_for_terminated_rays (nn_rendering_helpers.cu:241-277): a uniformly chosen surface, a uniform point
 // on it. Fixed here (DESIGN.md deviation 9): the index cannot reach n_surfaces, and y / z are not swapped.
