@@ -84,23 +84,14 @@ __host__ __device__ __forceinline__ size_t operand_offset(int row, int k, int k_
 // inputs; a chunk is one contiguous block = one bulk copy = the B operand of kw / 16 MMAs with N = the part's rows (large N: an SS-mode MMA re-reads
 // its 4 KB of A from shared memory, so N = 64 pieces are shared-memory-bound and issue-bound). Inside a chunk: canonical K-major no-swizzle form,
 // 8x8 core matrices of 128 bytes, K-adjacent ones 128 bytes apart (LBO), 8-row groups kw * 16 bytes apart (SBO).
-#ifndef RLPT_DQN_KC_A
-#define RLPT_DQN_KC_A 112        // inputs per weight chunk of the 208-input layers (2 and 4; 208 = 112 + 96)
-#endif
-#ifndef RLPT_DQN_KC_B
-#define RLPT_DQN_KC_B 80         // ... of the 304-input layer (3; 304 = 3 x 80 + 64)
-#endif
 #ifndef RLPT_DQN_STAGES
 #define RLPT_DQN_STAGES 2
 #endif
 #ifndef RLPT_DQN_PIECES
 #define RLPT_DQN_PIECES 1
 #endif
-// Inputs per weight chunk. One cp.async.bulk occupies the SM's copy engine for >= ~360 cycles whatever its size, and copies are served one after the other
-// (scratch/ubench/copy_bw.cu: 5 KB copies 14 B/cycle, 20 KB 57, 33 KB 91, >= 40 KB 113 B/cycle per SM): few large chunks, not many small ones.
-__host__ __device__ constexpr int dq_kc(int k_pad) { return k_pad == DQ_K3 ? RLPT_DQN_KC_B : RLPT_DQN_KC_A; }
-static_assert(RLPT_DQN_KC_A % 16 == 0 && RLPT_DQN_KC_B % 16 == 0, "chunks are whole MMA K steps");
-constexpr int DQ_L2_SPLIT = 160;                                           // layer 2's first N part
+// (chunk sizes, dq_kc, DQ_L2_SPLIT and wpack_offset: rlpt_dqn_layout.h -- plain C++, also compiled into a host test)
+static_assert(DQ_LAYOUT_K3 == DQ_K3, "rlpt_dqn_layout.h tells the 304-input layer by its width");
 // The packed weights exist DQ_REPLICAS times in global memory (replica r at byte offset r * stride): CTA b streams replica b % DQ_REPLICAS. All CTAs of a
 // full-frame forward walk the chunk stream in step, so without replicas 148 SMs ask the same 128-byte lines of the same L2 slices at the same moment
 // (an A/B switch: it made no difference).
@@ -109,11 +100,6 @@ constexpr int DQ_L2_SPLIT = 160;                                           // la
 #endif
 constexpr int DQ_REPLICAS = RLPT_DQN_REPLICAS;
 constexpr size_t DQ_W2P_STRIDE = 2 * (size_t)DQ_N2 * DQ_K2 + 128 * 3, DQ_W3P_STRIDE = 2 * (size_t)DQ_N3 * DQ_K3 + 128 * 5, DQ_W4P_STRIDE = 2 * (size_t)DQ_N4 * DQ_K4 + 128 * 7;       // bytes; odd multiples of a line apart
-__host__ __device__ __forceinline__ size_t wpack_offset(int n_split, int row, int k, int n_pad, int k_pad) {
-    const int n0 = (n_split > 0 && row >= n_split) ? n_split : 0, rows = n_split > 0 ? (row >= n_split ? n_pad - n_split : n_split) : n_pad;
-    const int KC = dq_kc(k_pad), kc = k / KC, kw = min(KC, k_pad - kc * KC), r = row - n0, kk = k - kc * KC;
-    return (size_t)n0 * k_pad * 2 + (size_t)rows * KC * 2 * kc + (size_t)(r >> 3) * ((size_t)kw * 16) + (size_t)(kk >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(kk & 7) * 2;
-}
 
 __constant__ float c_dq_cos[DQ_OUT];                                     // cos(theta) of the 144 grid cells (the tracer's table; dqn_upload_cell_cos)
 void dqn_upload_cell_cos(const float* cos144) { cudaMemcpyToSymbol(c_dq_cos, cos144, sizeof(float) * DQ_OUT); }

@@ -13,6 +13,9 @@ constexpr int DQ_H1 = 200, DQ_H2 = 300, DQ_H3 = 200, DQ_OUT = 144;
 // MMA shapes: K padded to a multiple of 16 (bf16 UMMA_K), N to a multiple of 16 (UMMA_N granularity at M = 128)
 constexpr int DQ_K2 = 208, DQ_N2 = 304, DQ_K3 = 304, DQ_N3 = 208, DQ_K4 = 208, DQ_N4 = 144;
 constexpr int DQ_TILE = 128;        // rays per CTA tile = UMMA_M = TMEM lanes
+}  // namespace rlpt
+#include "rlpt_dqn_layout.h"
+namespace rlpt {
 constexpr int DQ_CHUNK = 64;        // weight rows (outputs) staged per shared-memory buffer
 
 // Host copy of the parameters in the reference's order (DyNet TextFileSaver blocks /_0 .. /_7), row-major [out][in].
